@@ -1,0 +1,207 @@
+/*
+ * stitchb200.h — C ABI of libstitchb200.so: the B200-native (sm_100a CUDA) per-frame
+ * compositing path of StitchingVideo's OpenCV 2.4.11 cv::detail pipeline
+ * (warp -> exposure gain -> blend).  Plain pointers and sizes only.
+ *
+ * Every entry point replaces one reference interface; citations use
+ *   LIB = /root/reference/stitching/OpenCV2.4.11-Stitching-64bit/OpenCV2.4.11-Stitching
+ *   INC = LIB/include/opencv2/stitching
+ *
+ * There is no CPU fallback: a missing device or a failed launch is an error
+ * (SB_ERR_CUDA), never a downgrade.  Calls on one handle must be serialised by
+ * the caller (the reference objects are stateful); distinct
+ * handles are independent and each owns a CUDA stream.
+ *
+ * Images are `sb_image` PODs — the cv::Mat / gpu::GpuMat overload pair of
+ * INC/detail/warpers.hpp:385-414 collapsed into one struct: `device < 0` means
+ * `data` is a host pointer (staged through the handle's device buffers),
+ * `device >= 0` means a CUDA device pointer on that ordinal (zero copy).
+ */
+#ifndef STITCHB200_H
+#define STITCHB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- type / flag codes: numerically identical to OpenCV 2.4.11 ---- */
+enum { SB_8U = 0, SB_16S = 3, SB_32F = 5,
+       SB_8UC1 = 0, SB_8UC3 = 16, SB_16SC1 = 3, SB_16SC3 = 19, SB_32FC1 = 5 };
+enum { SB_INTER_NEAREST = 0, SB_INTER_LINEAR = 1 };
+enum { SB_BORDER_CONSTANT = 0, SB_BORDER_REPLICATE = 1, SB_BORDER_REFLECT = 2,
+       SB_BORDER_WRAP = 3, SB_BORDER_REFLECT_101 = 4 };
+
+/* status codes mirror the cv::Exception codes the reference throws (SURVEY.md §8b "Errors") */
+enum { SB_OK = 0,
+       SB_ERR_NO_MEM = -4,      /* CV_StsNoMem */
+       SB_ERR_BAD_ARG = -5,     /* CV_StsBadArg: unsupported factory type (blenders.cpp:60, exposure_compensate.cpp:58) */
+       SB_ERR_ASSERT = -215,    /* CV_StsAssert: CV_Assert on types/sizes (blenders.cpp:83-84,125-126,238-239; warpers.cpp:52-54) */
+       SB_ERR_NOT_IMPL = -213,  /* CV_StsNotImplemented */
+       SB_ERR_CUDA = -217 };    /* CV_GpuApiCallError */
+
+typedef struct sb_image {
+    void  *data;
+    int    rows, cols, type;
+    size_t step;        /* bytes per row */
+    int    device;      /* -1: host memory; >= 0: CUDA device ordinal */
+} sb_image;
+typedef struct sb_point { int x, y; } sb_point;
+typedef struct sb_size  { int width, height; } sb_size;
+typedef struct sb_rect  { int x, y, width, height; } sb_rect;
+
+/* thread-local description of the last failure on this thread */
+const char *sb_last_error(void);
+const char *sb_version(void);
+/* number of kernels this library has launched since load (all handles); bench.py's gpu_launches */
+uint64_t sb_kernel_launch_count(void);
+int sb_device_count(void);
+/* page-locked host memory for the pipelined compositor path (host<->device copies overlap compute) */
+int  sb_host_alloc(void **ptr, size_t bytes);
+void sb_host_free(void *ptr);
+
+/* =====================================================================================
+ * RotationWarper — INC/detail/warpers.hpp:53-72 (interface), :102-125 (RotationWarperBase),
+ * factories INC/warpers.hpp:50-167.  kind selects the projector.
+ * ===================================================================================== */
+enum { SB_WARP_PLANE = 0,        /* PlaneWarper      INC/detail/warpers.hpp:135-161 */
+       SB_WARP_CYLINDRICAL = 1,  /* CylindricalWarper INC/detail/warpers.hpp:352-364 */
+       SB_WARP_SPHERICAL = 2 };  /* SphericalWarper   INC/detail/warpers.hpp:330-340 */
+typedef struct sb_warper sb_warper;
+
+/* WarperCreator::create(scale) (INC/warpers.hpp:50-83) */
+int   sb_warper_create(int kind, float scale, int device, sb_warper **out);
+void  sb_warper_destroy(sb_warper *w);
+float sb_warper_get_scale(const sb_warper *w);                       /* warpers.hpp:118 */
+int   sb_warper_set_scale(sb_warper *w, float scale);                /* warpers.hpp:119 */
+/* PlaneWarper's T overloads (warpers.cpp:81-137): translation used by subsequent calls (default 0) */
+int   sb_warper_set_translation(sb_warper *w, const float T[3]);
+
+/* RotationWarper::warpPoint (warpers_inl.hpp:52-59).  K, R: row-major 3x3 float32 (warpers.cpp:52-54) */
+int sb_warper_warp_point(sb_warper *w, const float pt[2], const float K[9], const float R[9], float uv[2]);
+/* RotationWarper::warpRoi (warpers_inl.hpp:131-139): Rect(tl, br + 1) */
+int sb_warper_warp_roi(sb_warper *w, sb_size src_size, const float K[9], const float R[9], sb_rect *roi);
+/* RotationWarper::buildMaps (warpers_inl.hpp:62-85).  Returns Rect(tl, br) in *roi (width = br.x - tl.x);
+ * maps are (roi.height+1) x (roi.width+1) CV_32FC1.  The maps stay cached in the handle for
+ * sb_warper_remap.  xmap/ymap may be NULL (cache only); if non-NULL with data == NULL they are
+ * pointed at the handle-owned device maps (valid until the next build on this handle). */
+int sb_warper_build_maps(sb_warper *w, sb_size src_size, const float K[9], const float R[9],
+                         sb_image *xmap, sb_image *ymap, sb_rect *roi);
+/* RotationWarper::warp (warpers_inl.hpp:88-99): buildMaps + cv::remap.  dst must be
+ * (roi.height+1) x (roi.width+1) of src's type, or have data == NULL to receive a handle-owned
+ * device image (valid until the next warp/remap on this handle).  *tl = dst_roi.tl(). */
+int sb_warper_warp(sb_warper *w, const sb_image *src, const float K[9], const float R[9],
+                   int interp_mode, int border_mode, sb_image *dst, sb_point *tl);
+/* The cached-map video path of the app (APP64:188-198 caches xmap1/ymap1, APP64:752 remaps every
+ * frame): cv::remap(src, dst, cached xmap, cached ymap, interp, border). */
+int sb_warper_remap(sb_warper *w, const sb_image *src, int interp_mode, int border_mode, sb_image *dst);
+/* RotationWarper::warpBackward (warpers_inl.hpp:102-128) */
+int sb_warper_warp_backward(sb_warper *w, const sb_image *src, const float K[9], const float R[9],
+                            int interp_mode, int border_mode, sb_size dst_size, sb_image *dst);
+
+/* cv::remap itself (OpenCV 2.4.11 imgproc; call sites warpers_inl.hpp:96,127, APP64:752): 8UC1/8UC3,
+ * CV_32FC1 maps, INTER_LINEAR (fixed-point INTER_TAB_SIZE=32) or INTER_NEAREST. */
+int sb_remap(const sb_image *src, sb_image *dst, const sb_image *xmap, const sb_image *ymap,
+             int interp_mode, int border_mode, const uint8_t border_value[4], int device);
+
+/* =====================================================================================
+ * ExposureCompensator — INC/detail/exposure_compensate.hpp:51-101.
+ * feed() (gain estimation) is calibration and stays on the host (north_star); its result is
+ * handed in with sb_comp_set_gains / sb_comp_set_gain_maps.
+ * ===================================================================================== */
+enum { SB_COMP_NO = 0, SB_COMP_GAIN = 1, SB_COMP_GAIN_BLOCKS = 2 };   /* exposure_compensate.hpp:56 */
+typedef struct sb_comp sb_comp;
+/* ExposureCompensator::createDefault (exposure_compensate.cpp:51-61) */
+int  sb_comp_create(int kind, int device, sb_comp **out);
+void sb_comp_destroy(sb_comp *c);
+/* GainCompensator::gains_ (exposure_compensate.cpp:144, :156-162) */
+int  sb_comp_set_gains(sb_comp *c, const double *gains, int n);
+int  sb_comp_get_gains(const sb_comp *c, double *gains, int n);
+/* BlocksGainCompensator::gain_maps_ (exposure_compensate.cpp:203-221): n host CV_32FC1 maps */
+int  sb_comp_set_gain_maps(sb_comp *c, const sb_image *maps, int n);
+/* ExposureCompensator::apply (exposure_compensate.cpp:150-153, 225-246): in place on 8UC3 */
+int  sb_comp_apply(sb_comp *c, int index, sb_point corner, sb_image *image, const sb_image *mask);
+
+/* =====================================================================================
+ * Blender / FeatherBlender / MultiBandBlender — INC/detail/blenders.hpp:53-117, blenders.cpp
+ * ===================================================================================== */
+enum { SB_BLEND_NO = 0, SB_BLEND_FEATHER = 1, SB_BLEND_MULTI_BAND = 2 };   /* blenders.hpp:58 */
+typedef struct sb_blender sb_blender;
+/* Blender::createDefault (blenders.cpp:52-62) + ctor parameters: FeatherBlender(sharpness = 0.02f)
+ * (blenders.hpp:75), MultiBandBlender(try_gpu, num_bands = 5, weight_type = CV_32F) (blenders.hpp:99). */
+int  sb_blender_create(int kind, int num_bands, int weight_type, float sharpness, int device, sb_blender **out);
+void sb_blender_destroy(sb_blender *b);
+int  sb_blender_num_bands(const sb_blender *b);                      /* blenders.hpp:101 */
+int  sb_blender_set_num_bands(sb_blender *b, int n);                 /* blenders.hpp:102 */
+float sb_blender_sharpness(const sb_blender *b);                     /* blenders.hpp:77 */
+int  sb_blender_set_sharpness(sb_blender *b, float s);               /* blenders.hpp:78 */
+/* Blender::prepare(corners, sizes) (blenders.cpp:65-68) / virtual prepare(Rect) (:71-78,115-120,203-233) */
+int  sb_blender_prepare(sb_blender *b, const sb_point *corners, const sb_size *sizes, int n);
+int  sb_blender_prepare_rect(sb_blender *b, sb_rect dst_roi);
+/* Blender::feed (blenders.cpp:81-102, 123-147, 236-356): img CV_16SC3 (multi-band also CV_8UC3),
+ * mask CV_8U.  Asynchronous on the handle's stream when the inputs are device images. */
+int  sb_blender_feed(sb_blender *b, const sb_image *img, const sb_image *mask, sb_point tl);
+/* size of the image blend() will return (dst_roi_final_ for multi-band) */
+int  sb_blender_result_size(const sb_blender *b, sb_size *size);
+/* Blender::blend (blenders.cpp:105-112, 150-155, 359-377): dst CV_16SC3, dst_mask CV_8U; either may
+ * have data == NULL to receive handle-owned device images.  Synchronises the stream.  Like the
+ * reference (which hands its buffers to the caller), prepare must be called again afterwards. */
+int  sb_blender_blend(sb_blender *b, sb_image *dst, sb_image *dst_mask);
+
+/* blenders.hpp:122-133 auxiliary functions */
+int sb_normalize_using_weight_map(const sb_image *weight, sb_image *src, int device);          /* blenders.cpp:383-424 */
+int sb_create_weight_map(const sb_image *mask, float sharpness, sb_image *weight, int device); /* blenders.cpp:427-432 */
+/* createLaplacePyr (blenders.cpp:435-489): pyr[0..num_levels] caller-allocated CV_16SC3, sizes halving */
+int sb_create_laplace_pyr(const sb_image *img, int num_levels, sb_image *pyr, int device);
+int sb_restore_image_from_laplace_pyr(sb_image *pyr, int num_images, int device);              /* blenders.cpp:520-530 */
+
+/* =====================================================================================
+ * Compositor — the per-frame loop of Stitcher::composePanorama (LIB/src/stitcher.cpp:221-313) and
+ * of the live app's StitchingAll (APP64:724-770) with calibration fixed: everything
+ * frame-independent (maps, seam masks, weight pyramids, weight sums, gains) is built once at
+ * create time and kept resident in HBM; compose() runs warp -> gain -> convertTo(16S) ->
+ * Blender::feed x n -> Blender::blend -> convertTo(8U) for one frame set.
+ * ===================================================================================== */
+typedef struct sb_compositor sb_compositor;
+typedef struct sb_compositor_config {
+    int      n_cameras;
+    sb_size  src_size;            /* all cameras share one frame size */
+    int      warper_kind;         /* SB_WARP_* */
+    float    warper_scale;
+    const float *K;               /* n x 9 row-major float32 */
+    const float *R;               /* n x 9 */
+    int      blender_kind;        /* SB_BLEND_* */
+    int      num_bands;           /* multi-band */
+    int      weight_type;         /* SB_32F or SB_16S (multi-band) */
+    float    sharpness;           /* feather */
+    int      comp_kind;           /* SB_COMP_NO or SB_COMP_GAIN */
+    const double *gains;          /* n gains (SB_COMP_GAIN) */
+    /* optional n seam masks in warped coordinates (host CV_8UC1, size of each camera's warped
+     * image), ANDed with the warped all-255 mask exactly as stitcher.cpp:278-294; NULL = none */
+    const sb_image *seam_masks;
+    int      output_type;         /* SB_8UC3 (result.convertTo(CV_8U), stitcher.cpp:313) or SB_16SC3 */
+} sb_compositor_config;
+
+int  sb_compositor_create(const sb_compositor_config *cfg, int device, sb_compositor **out);
+void sb_compositor_destroy(sb_compositor *c);
+/* geometry fixed by the calibration: per-camera warped corner/size and the panorama rect */
+int  sb_compositor_pano_size(const sb_compositor *c, sb_size *size);
+int  sb_compositor_camera_roi(const sb_compositor *c, int index, sb_rect *roi);
+/* One frame set: srcs[n] CV_8UC3 (host or device) -> pano (output_type) + pano_mask (CV_8U, may be NULL).
+ * Synchronous. */
+int  sb_compositor_compose(sb_compositor *c, const sb_image *srcs, sb_image *pano, sb_image *pano_mask);
+/* Pipelined form for throughput: up to `depth` frame sets in flight, each on its own stream/slot.
+ * enqueue returns a slot id; wait blocks until that slot's pano has landed in the buffers given
+ * to enqueue. */
+int  sb_compositor_set_depth(sb_compositor *c, int depth);
+int  sb_compositor_enqueue(sb_compositor *c, const sb_image *srcs, sb_image *pano, sb_image *pano_mask, int *slot);
+int  sb_compositor_wait(sb_compositor *c, int slot);
+/* device-resident timing of the last compose on a slot, ms (CUDA events on the slot's stream) */
+int  sb_compositor_last_gpu_ms(sb_compositor *c, int slot, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,583 @@
+"""ctypes binding of libstitchb200.so (include/stitchb200.h) and the host-side mirror of the
+reference's operator interfaces for the per-frame compositing path:
+
+    detail::RotationWarper       (warpers.hpp:53-72)            -> SphericalWarper / CylindricalWarper / PlaneWarper
+    detail::ExposureCompensator  (exposure_compensate.hpp:51-101) -> NoExposureCompensator / GainCompensator / BlocksGainCompensator
+    detail::Blender              (blenders.hpp:53-117)           -> Blender / FeatherBlender / MultiBandBlender
+    Stitcher::composePanorama's frame loop (stitcher.cpp:221-313) -> Compositor
+
+Same names, argument meaning and error behaviour (cv::Exception -> StitchError carrying the same
+status code).  There is NO CPU fallback: if the shared library is missing or no CUDA device is
+usable, every operation raises.  numpy arrays stand in for cv::Mat (host), DeviceImage for GpuMat.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstitchb200.so")
+
+# OpenCV-numbered constants
+CV_8U, CV_16S, CV_32F = 0, 3, 5
+CV_8UC1, CV_8UC3, CV_16SC1, CV_16SC3, CV_32FC1 = 0, 16, 3, 19, 5
+INTER_NEAREST, INTER_LINEAR = 0, 1
+BORDER_CONSTANT, BORDER_REPLICATE, BORDER_REFLECT, BORDER_WRAP, BORDER_REFLECT_101 = 0, 1, 2, 3, 4
+WARP_PLANE, WARP_CYLINDRICAL, WARP_SPHERICAL = 0, 1, 2
+COMP_NO, COMP_GAIN, COMP_GAIN_BLOCKS = 0, 1, 2
+BLEND_NO, BLEND_FEATHER, BLEND_MULTI_BAND = 0, 1, 2
+SB_OK, SB_ERR_NO_MEM, SB_ERR_BAD_ARG, SB_ERR_ASSERT, SB_ERR_NOT_IMPL, SB_ERR_CUDA = 0, -4, -5, -215, -213, -217
+
+
+class StitchError(RuntimeError):
+    """cv::Exception stand-in: .code is the OpenCV status code the reference would throw."""
+
+    def __init__(self, code, msg):
+        super().__init__("stitchb200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class SbImage(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int), ("type", C.c_int),
+                ("step", C.c_size_t), ("device", C.c_int)]
+
+
+class SbPoint(C.Structure):
+    _fields_ = [("x", C.c_int), ("y", C.c_int)]
+
+
+class SbSize(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int)]
+
+
+class SbRect(C.Structure):
+    _fields_ = [("x", C.c_int), ("y", C.c_int), ("width", C.c_int), ("height", C.c_int)]
+
+
+class SbCompositorConfig(C.Structure):
+    _fields_ = [("n_cameras", C.c_int), ("src_size", SbSize), ("warper_kind", C.c_int), ("warper_scale", C.c_float),
+                ("K", C.POINTER(C.c_float)), ("R", C.POINTER(C.c_float)), ("blender_kind", C.c_int),
+                ("num_bands", C.c_int), ("weight_type", C.c_int), ("sharpness", C.c_float), ("comp_kind", C.c_int),
+                ("gains", C.POINTER(C.c_double)), ("seam_masks", C.POINTER(SbImage)), ("output_type", C.c_int)]
+
+
+# every symbol include/stitchb200.h declares: name -> (restype, argtypes)
+_P = C.POINTER
+_F9 = _P(C.c_float)
+API = {
+    "sb_last_error": (C.c_char_p, []),
+    "sb_version": (C.c_char_p, []),
+    "sb_kernel_launch_count": (C.c_uint64, []),
+    "sb_device_count": (C.c_int, []),
+    "sb_host_alloc": (C.c_int, [_P(C.c_void_p), C.c_size_t]),
+    "sb_host_free": (None, [C.c_void_p]),
+    "sb_warper_create": (C.c_int, [C.c_int, C.c_float, C.c_int, _P(C.c_void_p)]),
+    "sb_warper_destroy": (None, [C.c_void_p]),
+    "sb_warper_get_scale": (C.c_float, [C.c_void_p]),
+    "sb_warper_set_scale": (C.c_int, [C.c_void_p, C.c_float]),
+    "sb_warper_set_translation": (C.c_int, [C.c_void_p, _F9]),
+    "sb_warper_warp_point": (C.c_int, [C.c_void_p, _F9, _F9, _F9, _F9]),
+    "sb_warper_warp_roi": (C.c_int, [C.c_void_p, SbSize, _F9, _F9, _P(SbRect)]),
+    "sb_warper_build_maps": (C.c_int, [C.c_void_p, SbSize, _F9, _F9, _P(SbImage), _P(SbImage), _P(SbRect)]),
+    "sb_warper_warp": (C.c_int, [C.c_void_p, _P(SbImage), _F9, _F9, C.c_int, C.c_int, _P(SbImage), _P(SbPoint)]),
+    "sb_warper_remap": (C.c_int, [C.c_void_p, _P(SbImage), C.c_int, C.c_int, _P(SbImage)]),
+    "sb_warper_warp_backward": (C.c_int, [C.c_void_p, _P(SbImage), _F9, _F9, C.c_int, C.c_int, SbSize, _P(SbImage)]),
+    "sb_remap": (C.c_int, [_P(SbImage), _P(SbImage), _P(SbImage), _P(SbImage), C.c_int, C.c_int, _P(C.c_uint8), C.c_int]),
+    "sb_comp_create": (C.c_int, [C.c_int, C.c_int, _P(C.c_void_p)]),
+    "sb_comp_destroy": (None, [C.c_void_p]),
+    "sb_comp_set_gains": (C.c_int, [C.c_void_p, _P(C.c_double), C.c_int]),
+    "sb_comp_get_gains": (C.c_int, [C.c_void_p, _P(C.c_double), C.c_int]),
+    "sb_comp_set_gain_maps": (C.c_int, [C.c_void_p, _P(SbImage), C.c_int]),
+    "sb_comp_apply": (C.c_int, [C.c_void_p, C.c_int, SbPoint, _P(SbImage), _P(SbImage)]),
+    "sb_blender_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P(C.c_void_p)]),
+    "sb_blender_destroy": (None, [C.c_void_p]),
+    "sb_blender_num_bands": (C.c_int, [C.c_void_p]),
+    "sb_blender_set_num_bands": (C.c_int, [C.c_void_p, C.c_int]),
+    "sb_blender_sharpness": (C.c_float, [C.c_void_p]),
+    "sb_blender_set_sharpness": (C.c_int, [C.c_void_p, C.c_float]),
+    "sb_blender_prepare": (C.c_int, [C.c_void_p, _P(SbPoint), _P(SbSize), C.c_int]),
+    "sb_blender_prepare_rect": (C.c_int, [C.c_void_p, SbRect]),
+    "sb_blender_feed": (C.c_int, [C.c_void_p, _P(SbImage), _P(SbImage), SbPoint]),
+    "sb_blender_result_size": (C.c_int, [C.c_void_p, _P(SbSize)]),
+    "sb_blender_blend": (C.c_int, [C.c_void_p, _P(SbImage), _P(SbImage)]),
+    "sb_normalize_using_weight_map": (C.c_int, [_P(SbImage), _P(SbImage), C.c_int]),
+    "sb_create_weight_map": (C.c_int, [_P(SbImage), C.c_float, _P(SbImage), C.c_int]),
+    "sb_create_laplace_pyr": (C.c_int, [_P(SbImage), C.c_int, _P(SbImage), C.c_int]),
+    "sb_restore_image_from_laplace_pyr": (C.c_int, [_P(SbImage), C.c_int, C.c_int]),
+    "sb_compositor_create": (C.c_int, [_P(SbCompositorConfig), C.c_int, _P(C.c_void_p)]),
+    "sb_compositor_destroy": (None, [C.c_void_p]),
+    "sb_compositor_pano_size": (C.c_int, [C.c_void_p, _P(SbSize)]),
+    "sb_compositor_camera_roi": (C.c_int, [C.c_void_p, C.c_int, _P(SbRect)]),
+    "sb_compositor_compose": (C.c_int, [C.c_void_p, _P(SbImage), _P(SbImage), _P(SbImage)]),
+    "sb_compositor_set_depth": (C.c_int, [C.c_void_p, C.c_int]),
+    "sb_compositor_enqueue": (C.c_int, [C.c_void_p, _P(SbImage), _P(SbImage), _P(SbImage), _P(C.c_int)]),
+    "sb_compositor_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "sb_compositor_last_gpu_ms": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_float)]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libstitchb200.so.  Raises (never falls back) when the CUDA library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise StitchError(SB_ERR_CUDA, "%s is missing: build it with `python -c 'import __graft_entry__ as g; "
+                              "g.build()'` (there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in API.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != SB_OK:
+        raise StitchError(rc, lib().sb_last_error().decode("utf-8", "replace"))
+
+
+_NP2CV = {np.dtype(np.uint8): CV_8U, np.dtype(np.int16): CV_16S, np.dtype(np.float32): CV_32F}
+_CV2NP = {CV_8U: np.uint8, CV_16S: np.int16, CV_32F: np.float32}
+
+
+def _depth(t):
+    return t & 7
+
+
+def _cn(t):
+    return ((t >> 3) & 63) + 1
+
+
+class DeviceImage:
+    """GpuMat stand-in: a device pointer plus geometry.  `owner` keeps the allocation alive."""
+
+    def __init__(self, ptr, rows, cols, cvtype, step, device, owner=None):
+        self.ptr, self.rows, self.cols, self.type, self.step, self.device, self.owner = ptr, rows, cols, cvtype, step, device, owner
+
+    @staticmethod
+    def from_torch(t):
+        import torch
+        assert t.is_cuda and t.is_contiguous()
+        dt = {torch.uint8: CV_8U, torch.int16: CV_16S, torch.float32: CV_32F}[t.dtype]
+        cn = 1 if t.dim() == 2 else t.shape[2]
+        return DeviceImage(t.data_ptr(), t.shape[0], t.shape[1], dt + ((cn - 1) << 3), t.stride(0) * t.element_size(),
+                           t.device.index, owner=t)
+
+    def sb(self):
+        return SbImage(self.ptr, self.rows, self.cols, self.type, self.step, self.device)
+
+
+def _image(a):
+    """numpy array | DeviceImage -> (SbImage, keepalive)."""
+    if isinstance(a, DeviceImage):
+        return a.sb(), a
+    a = np.asarray(a)
+    if a.dtype not in _NP2CV:
+        raise StitchError(SB_ERR_ASSERT, "unsupported dtype %s" % a.dtype)
+    if a.ndim not in (2, 3):
+        raise StitchError(SB_ERR_ASSERT, "image must be 2-D or 3-D")
+    cn = 1 if a.ndim == 2 else a.shape[2]
+    if a.strides[-1] != a.itemsize or (a.ndim == 3 and a.strides[1] != a.itemsize * cn):
+        a = np.ascontiguousarray(a)
+    return SbImage(a.ctypes.data, a.shape[0], a.shape[1], _NP2CV[a.dtype] + ((cn - 1) << 3), a.strides[0], -1), a
+
+
+def _empty(rows, cols, cvtype):
+    cn = _cn(cvtype)
+    shape = (rows, cols) if cn == 1 else (rows, cols, cn)
+    return np.empty(shape, _CV2NP[_depth(cvtype)])
+
+
+def _f9(m):
+    a = np.ascontiguousarray(m, np.float32)
+    if a.size != 9:
+        raise StitchError(SB_ERR_ASSERT, "K.size() == Size(3, 3) && K.type() == CV_32F")   # warpers.cpp:52-53
+    return a.reshape(9)
+
+
+def _fp(a):
+    return a.ctypes.data_as(_F9)
+
+
+def kernel_launch_count():
+    return int(lib().sb_kernel_launch_count())
+
+
+def device_count():
+    return int(lib().sb_device_count())
+
+
+# ======================================================================================= warpers
+class RotationWarper:
+    """detail::RotationWarper (warpers.hpp:53-72) / RotationWarperBase (warpers.hpp:102-125)."""
+    KIND = None
+
+    def __init__(self, scale=1.0, device=0):
+        self._h = C.c_void_p()
+        self.device = device
+        _check(lib().sb_warper_create(self.KIND, C.c_float(scale), device, C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.sb_warper_destroy(self._h)
+            self._h = None
+
+    def getScale(self):
+        return lib().sb_warper_get_scale(self._h)
+
+    def setScale(self, v):
+        _check(lib().sb_warper_set_scale(self._h, C.c_float(v)))
+
+    def warpPoint(self, pt, K, R):
+        K, R = _f9(K), _f9(R)
+        p = np.asarray(pt, np.float32).reshape(2)
+        uv = np.zeros(2, np.float32)
+        _check(lib().sb_warper_warp_point(self._h, _fp(p), _fp(K), _fp(R), _fp(uv)))
+        return float(uv[0]), float(uv[1])
+
+    def warpRoi(self, src_size, K, R):
+        K, R = _f9(K), _f9(R)
+        r = SbRect()
+        _check(lib().sb_warper_warp_roi(self._h, SbSize(*src_size), _fp(K), _fp(R), C.byref(r)))
+        return (r.x, r.y, r.width, r.height)
+
+    def buildMaps(self, src_size, K, R):
+        """-> (Rect(tl, br) as (x, y, w, h), xmap, ymap); maps are float32 (h+1, w+1)."""
+        K, R = _f9(K), _f9(R)
+        r = SbRect()
+        _check(lib().sb_warper_build_maps(self._h, SbSize(*src_size), _fp(K), _fp(R), None, None, C.byref(r)))
+        xmap = np.empty((r.height + 1, r.width + 1), np.float32)
+        ymap = np.empty_like(xmap)
+        ix, _k1 = _image(xmap)
+        iy, _k2 = _image(ymap)
+        _check(lib().sb_warper_build_maps(self._h, SbSize(*src_size), _fp(K), _fp(R), C.byref(ix), C.byref(iy), C.byref(r)))
+        self._map_shape = xmap.shape
+        return (r.x, r.y, r.width, r.height), xmap, ymap
+
+    def warp(self, src, K, R, interp_mode=INTER_LINEAR, border_mode=BORDER_REFLECT):
+        """-> (tl, dst)  (warpers_inl.hpp:88-99); dst is (roi.height+1, roi.width+1) of src's type."""
+        K, R = _f9(K), _f9(R)
+        isrc, keep = _image(src)
+        roi = self.warpRoi((isrc.cols, isrc.rows), K, R)
+        dst = _empty(roi[3], roi[2], isrc.type)
+        idst, _k = _image(dst)
+        tl = SbPoint()
+        _check(lib().sb_warper_warp(self._h, C.byref(isrc), _fp(K), _fp(R), interp_mode, border_mode, C.byref(idst), C.byref(tl)))
+        return (tl.x, tl.y), dst
+
+    def remap(self, src, interp_mode=INTER_LINEAR, border_mode=BORDER_REFLECT):
+        """cv::remap with the maps cached by the last buildMaps (the app's video path, APP64:752)."""
+        isrc, keep = _image(src)
+        if getattr(self, "_map_shape", None) is None:
+            raise StitchError(SB_ERR_ASSERT, "remap: no cached maps; call buildMaps first")
+        dst = _empty(self._map_shape[0], self._map_shape[1], isrc.type)
+        idst, _k = _image(dst)
+        _check(lib().sb_warper_remap(self._h, C.byref(isrc), interp_mode, border_mode, C.byref(idst)))
+        return dst
+
+    def warpBackward(self, src, K, R, interp_mode, border_mode, dst_size):
+        K, R = _f9(K), _f9(R)
+        isrc, keep = _image(src)
+        dst = _empty(dst_size[1], dst_size[0], isrc.type)
+        idst, _k = _image(dst)
+        _check(lib().sb_warper_warp_backward(self._h, C.byref(isrc), _fp(K), _fp(R), interp_mode, border_mode,
+                                             SbSize(*dst_size), C.byref(idst)))
+        return dst
+
+
+class PlaneWarper(RotationWarper):
+    KIND = WARP_PLANE
+
+    def setTranslation(self, T):
+        t = np.ascontiguousarray(T, np.float32).reshape(3)
+        _check(lib().sb_warper_set_translation(self._h, _fp(t)))
+
+
+class CylindricalWarper(RotationWarper):
+    KIND = WARP_CYLINDRICAL
+
+
+class SphericalWarper(RotationWarper):
+    KIND = WARP_SPHERICAL
+
+
+def remap(src, xmap, ymap, interp_mode=INTER_LINEAR, border_mode=BORDER_CONSTANT, border_value=(0, 0, 0, 0), device=0):
+    isrc, k0 = _image(src)
+    ix, k1 = _image(np.ascontiguousarray(xmap, np.float32))
+    iy, k2 = _image(np.ascontiguousarray(ymap, np.float32))
+    dst = _empty(ix.rows, ix.cols, isrc.type)
+    idst, k3 = _image(dst)
+    bv = (C.c_uint8 * 4)(*border_value)
+    _check(lib().sb_remap(C.byref(isrc), C.byref(idst), C.byref(ix), C.byref(iy), interp_mode, border_mode, bv, device))
+    return dst
+
+
+# ======================================================================================= exposure
+class ExposureCompensator:
+    """detail::ExposureCompensator (exposure_compensate.hpp:51-64).  feed() is calibration (host)."""
+    NO, GAIN, GAIN_BLOCKS = COMP_NO, COMP_GAIN, COMP_GAIN_BLOCKS
+    KIND = COMP_NO
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _check(lib().sb_comp_create(self.KIND, device, C.byref(self._h)))
+
+    @staticmethod
+    def createDefault(kind, device=0):
+        cls = {COMP_NO: NoExposureCompensator, COMP_GAIN: GainCompensator, COMP_GAIN_BLOCKS: BlocksGainCompensator}.get(kind)
+        if cls is None:
+            h = C.c_void_p()
+            _check(lib().sb_comp_create(kind, device, C.byref(h)))     # raises CV_StsBadArg
+        return cls(device)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.sb_comp_destroy(self._h)
+            self._h = None
+
+    def apply(self, index, corner, image, mask=None):
+        """In place on a host uint8 array or a DeviceImage (exposure_compensate.cpp:150-153, 225-246)."""
+        img, keep = _image(image)
+        if keep is not image and not isinstance(image, DeviceImage):
+            raise StitchError(SB_ERR_ASSERT, "apply() works in place: pass a contiguous array")
+        _check(lib().sb_comp_apply(self._h, index, SbPoint(*corner), C.byref(img), None))
+        return image
+
+
+class NoExposureCompensator(ExposureCompensator):
+    KIND = COMP_NO
+
+
+class GainCompensator(ExposureCompensator):
+    KIND = COMP_GAIN
+
+    def setGains(self, gains):
+        g = np.ascontiguousarray(gains, np.float64)
+        _check(lib().sb_comp_set_gains(self._h, g.ctypes.data_as(_P(C.c_double)), len(g)))
+        self._n = len(g)
+
+    def gains(self):
+        g = np.zeros(getattr(self, "_n", 0), np.float64)
+        _check(lib().sb_comp_get_gains(self._h, g.ctypes.data_as(_P(C.c_double)), len(g)))
+        return list(g)
+
+
+class BlocksGainCompensator(ExposureCompensator):
+    KIND = COMP_GAIN_BLOCKS
+
+    def setGainMaps(self, maps):
+        keep = [np.ascontiguousarray(m, np.float32) for m in maps]
+        arr = (SbImage * len(keep))(*[_image(m)[0] for m in keep])
+        _check(lib().sb_comp_set_gain_maps(self._h, arr, len(keep)))
+
+
+# ======================================================================================= blenders
+class Blender:
+    """detail::Blender (blenders.hpp:53-69): puts one image over another."""
+    NO, FEATHER, MULTI_BAND = BLEND_NO, BLEND_FEATHER, BLEND_MULTI_BAND
+    KIND = BLEND_NO
+
+    def __init__(self, device=0, _num_bands=5, _weight_type=CV_32F, _sharpness=0.02):
+        self._h = C.c_void_p()
+        self.device = device
+        _check(lib().sb_blender_create(self.KIND, _num_bands, _weight_type, C.c_float(_sharpness), device, C.byref(self._h)))
+
+    @staticmethod
+    def createDefault(kind, try_gpu=False, device=0):
+        cls = {BLEND_NO: Blender, BLEND_FEATHER: FeatherBlender, BLEND_MULTI_BAND: MultiBandBlender}.get(kind)
+        if cls is None:
+            h = C.c_void_p()
+            _check(lib().sb_blender_create(kind, 5, CV_32F, C.c_float(0.02), device, C.byref(h)))   # CV_StsBadArg
+        return cls(device=device)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.sb_blender_destroy(self._h)
+            self._h = None
+
+    def prepare(self, corners_or_rect, sizes=None):
+        if sizes is None:
+            x, y, w, h = corners_or_rect
+            _check(lib().sb_blender_prepare_rect(self._h, SbRect(x, y, w, h)))
+        else:
+            n = len(corners_or_rect)
+            if n != len(sizes):
+                raise StitchError(SB_ERR_ASSERT, "sizes.size() == corners.size()")     # util.cpp:129
+            pts = (SbPoint * n)(*[SbPoint(int(c[0]), int(c[1])) for c in corners_or_rect])
+            szs = (SbSize * n)(*[SbSize(int(s[0]), int(s[1])) for s in sizes])
+            _check(lib().sb_blender_prepare(self._h, pts, szs, n))
+
+    def feed(self, img, mask, tl):
+        i, k0 = _image(img)
+        m, k1 = _image(mask)
+        _check(lib().sb_blender_feed(self._h, C.byref(i), C.byref(m), SbPoint(int(tl[0]), int(tl[1]))))
+
+    def blend(self):
+        """-> (dst int16 HxWx3, dst_mask uint8 HxW)."""
+        s = SbSize()
+        _check(lib().sb_blender_result_size(self._h, C.byref(s)))
+        dst = np.empty((s.height, s.width, 3), np.int16)
+        dmask = np.empty((s.height, s.width), np.uint8)
+        i, k0 = _image(dst)
+        m, k1 = _image(dmask)
+        _check(lib().sb_blender_blend(self._h, C.byref(i), C.byref(m)))
+        return dst, dmask
+
+
+class FeatherBlender(Blender):
+    KIND = BLEND_FEATHER
+
+    def __init__(self, sharpness=0.02, device=0):
+        super().__init__(device=device, _sharpness=sharpness)
+
+    def sharpness(self):
+        return lib().sb_blender_sharpness(self._h)
+
+    def setSharpness(self, v):
+        _check(lib().sb_blender_set_sharpness(self._h, C.c_float(v)))
+
+
+class MultiBandBlender(Blender):
+    KIND = BLEND_MULTI_BAND
+
+    def __init__(self, try_gpu=False, num_bands=5, weight_type=CV_32F, device=0):
+        super().__init__(device=device, _num_bands=num_bands, _weight_type=weight_type)
+
+    def numBands(self):
+        return lib().sb_blender_num_bands(self._h)
+
+    def setNumBands(self, v):
+        _check(lib().sb_blender_set_num_bands(self._h, int(v)))
+
+
+def normalizeUsingWeightMap(weight, src, device=0):
+    w, k0 = _image(weight)
+    s, k1 = _image(src)
+    _check(lib().sb_normalize_using_weight_map(C.byref(w), C.byref(s), device))
+    return src
+
+
+def createWeightMap(mask, sharpness, device=0):
+    m, k0 = _image(mask)
+    out = np.empty((m.rows, m.cols), np.float32)
+    o, k1 = _image(out)
+    _check(lib().sb_create_weight_map(C.byref(m), C.c_float(sharpness), C.byref(o), device))
+    return out
+
+
+def createLaplacePyr(img, num_levels, device=0):
+    i, k0 = _image(img)
+    pyr, r, c = [], i.rows, i.cols
+    for _ in range(num_levels + 1):
+        pyr.append(np.empty((r, c, 3), np.int16))
+        r, c = (r + 1) // 2, (c + 1) // 2
+    arr = (SbImage * len(pyr))(*[_image(p)[0] for p in pyr])
+    _check(lib().sb_create_laplace_pyr(C.byref(i), num_levels, arr, device))
+    return pyr
+
+
+def restoreImageFromLaplacePyr(pyr, device=0):
+    pyr = [np.ascontiguousarray(p).copy() for p in pyr]
+    arr = (SbImage * len(pyr))(*[_image(p)[0] for p in pyr])
+    _check(lib().sb_restore_image_from_laplace_pyr(arr, len(pyr), device))
+    return pyr[0]
+
+
+# ======================================================================================= compositor
+class Compositor:
+    """The per-frame loop of Stitcher::composePanorama (stitcher.cpp:221-313) with calibration fixed."""
+
+    def __init__(self, src_size, Ks, Rs, warper="spherical", scale=None, blender="multiband", num_bands=5,
+                 weight_type=CV_32F, sharpness=0.02, gains=None, seam_masks=None, output_type=CV_8UC3, device=0):
+        n = len(Ks)
+        self.n = n
+        self.device = device
+        self.src_size = tuple(src_size)
+        K = np.ascontiguousarray(np.stack([_f9(k) for k in Ks]), np.float32)
+        R = np.ascontiguousarray(np.stack([_f9(r) for r in Rs]), np.float32)
+        cfg = SbCompositorConfig()
+        cfg.n_cameras = n
+        cfg.src_size = SbSize(*self.src_size)
+        cfg.warper_kind = {"plane": WARP_PLANE, "cylindrical": WARP_CYLINDRICAL, "spherical": WARP_SPHERICAL}.get(warper, warper)
+        cfg.warper_scale = float(scale)
+        cfg.K = K.ctypes.data_as(_F9)
+        cfg.R = R.ctypes.data_as(_F9)
+        cfg.blender_kind = {"no": BLEND_NO, "feather": BLEND_FEATHER, "multiband": BLEND_MULTI_BAND}.get(blender, blender)
+        cfg.num_bands = num_bands
+        cfg.weight_type = weight_type
+        cfg.sharpness = sharpness
+        g = None
+        if gains is not None:
+            g = np.ascontiguousarray(gains, np.float64)
+            cfg.comp_kind = COMP_GAIN
+            cfg.gains = g.ctypes.data_as(_P(C.c_double))
+        else:
+            cfg.comp_kind = COMP_NO
+        keep = None
+        if seam_masks is not None:
+            keep = [np.ascontiguousarray(m, np.uint8) for m in seam_masks]
+            arr = (SbImage * n)(*[_image(m)[0] for m in keep])
+            cfg.seam_masks = arr
+        cfg.output_type = output_type
+        self.output_type = output_type
+        self._h = C.c_void_p()
+        _check(lib().sb_compositor_create(C.byref(cfg), device, C.byref(self._h)))
+        s = SbSize()
+        _check(lib().sb_compositor_pano_size(self._h, C.byref(s)))
+        self.pano_size = (s.width, s.height)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.sb_compositor_destroy(self._h)
+            self._h = None
+
+    def camera_roi(self, i):
+        r = SbRect()
+        _check(lib().sb_compositor_camera_roi(self._h, i, C.byref(r)))
+        return (r.x, r.y, r.width, r.height)
+
+    def _srcs(self, frames):
+        if len(frames) != self.n:
+            raise StitchError(SB_ERR_ASSERT, "expected %d frames" % self.n)
+        pairs = [_image(f) for f in frames]
+        return (SbImage * self.n)(*[p[0] for p in pairs]), pairs
+
+    def new_output(self):
+        w, h = self.pano_size
+        return _empty(h, w, self.output_type), np.empty((h, w), np.uint8)
+
+    def compose(self, frames, pano=None, pano_mask=None):
+        """frames: n uint8 (H, W, 3) arrays or DeviceImages -> (pano, pano_mask)."""
+        if pano is None:
+            pano, pano_mask = self.new_output()
+        arr, keep = self._srcs(frames)
+        ip, k0 = _image(pano)
+        im = None
+        if pano_mask is not None:
+            im, k1 = _image(pano_mask)
+        _check(lib().sb_compositor_compose(self._h, arr, C.byref(ip), C.byref(im) if im is not None else None))
+        return pano, pano_mask
+
+    def set_depth(self, depth):
+        _check(lib().sb_compositor_set_depth(self._h, depth))
+
+    def enqueue(self, frames, pano, pano_mask=None):
+        arr, keep = self._srcs(frames)
+        ip, k0 = _image(pano)
+        im = None
+        if pano_mask is not None:
+            im, k1 = _image(pano_mask)
+        slot = C.c_int(-1)
+        _check(lib().sb_compositor_enqueue(self._h, arr, C.byref(ip), C.byref(im) if im is not None else None, C.byref(slot)))
+        return slot.value
+
+    def wait(self, slot):
+        _check(lib().sb_compositor_wait(self._h, slot))
+
+    def last_gpu_ms(self, slot=0):
+        ms = C.c_float()
+        _check(lib().sb_compositor_last_gpu_ms(self._h, slot, C.byref(ms)))
+        return ms.value

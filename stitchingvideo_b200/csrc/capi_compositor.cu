@@ -1,0 +1,403 @@
+// capi_compositor.cu — the per-frame compositing loop with calibration fixed.
+//
+// Host-side shape: Stitcher::composePanorama's full-resolution loop (LIB/src/stitcher.cpp:221-313)
+// and the live app's StitchingAll (APP64:724-770):
+//   warp(img) -> compensator.apply -> convertTo(CV_16S) -> blender.feed  (x n) -> blender.blend
+//   -> convertTo(CV_8U).
+// Everything that depends only on the calibration is hoisted to create() and kept resident in HBM,
+// exactly as the reference app hoists its maps/LUTs out of the frame loop:
+//   separable trig tables per camera (replace the 8 B/px float maps), warped masks, float/int16
+//   weight pyramids per camera, per-level weight sums (dst_band_weights_), feather weight maps.
+// compose() then launches only the image-dependent kernels.
+#include <algorithm>
+#include <cmath>
+
+#include "sb_host_projector.h"
+#include "sb_kernels.h"
+
+using namespace sb;
+
+namespace {
+
+struct Camera {
+    ProjParams proj;
+    sb_point tl;                 // corner of the warped image in panorama coordinates
+    int ww = 0, wh = 0;          // warped size (br - tl + 1)
+    float gain = 1.f;
+    DevBuf tables;               // col_sin | col_cos | row_a | row_b
+    WarpTables wt{};
+    DevImage mask;               // warped (and seam-ANDed) mask, 8UC1 ww x wh
+    // multi-band: padded feed rect (blenders.cpp:241-269), in dst_roi_ coordinates
+    int rx = 0, ry = 0, rw = 0, rh = 0, top = 0, left = 0;
+    std::vector<DevImage> w_pyr; // weight pyramid (sequence-constant)
+    DevImage feather_w;          // feather weight map (sequence-constant)
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    bool busy = false;
+    std::vector<DevImage> src;                   // staged source frames (host input)
+    std::vector<std::vector<DevImage>> gpyr;     // per camera Gaussian pyramid of the padded warped image
+    DevImage warped;                             // feather / no-blend: one warped image at a time
+    std::vector<DevImage> acc;                   // dst_pyr_laplace_ (level 0 = dst_)
+    DevImage acc_mask;                           // Blender::NO dst_mask_
+    DevImage out, out_mask;
+};
+
+}  // namespace
+
+struct sb_compositor {
+    int device = 0;
+    sb_compositor_config cfg{};
+    std::vector<Camera> cams;
+    sb_rect dst_roi{}, dst_roi_final{};
+    int num_bands = 0;
+    std::vector<DevImage> wsum;                  // dst_band_weights_ / dst_weight_map_ (sequence-constant)
+    std::vector<Slot> slots;
+    int next_slot = 0;
+    cudaStream_t setup_stream = nullptr;
+};
+
+namespace {
+
+int make_slot(sb_compositor *c, Slot &s)
+{
+    SB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    SB_CUDA(cudaEventCreate(&s.ev_start));
+    SB_CUDA(cudaEventCreate(&s.ev_stop));
+    const int n = c->cfg.n_cameras;
+    s.src.resize(n);
+    s.gpyr.resize(n);
+    const int levels = c->cfg.blender_kind == SB_BLEND_MULTI_BAND ? c->num_bands : 0;
+    s.acc.resize(levels + 1);
+    int rows = c->dst_roi.height, cols = c->dst_roi.width;
+    for (int l = 0; l <= levels; ++l) {
+        SB_TRY(s.acc[l].create(rows, cols, SB_16SC3));
+        rows = (rows + 1) / 2; cols = (cols + 1) / 2;
+    }
+    if (c->cfg.blender_kind == SB_BLEND_NO) SB_TRY(s.acc_mask.create(c->dst_roi.height, c->dst_roi.width, SB_8UC1));
+    if (c->cfg.blender_kind == SB_BLEND_MULTI_BAND) {
+        for (int i = 0; i < n; ++i) {
+            const Camera &cam = c->cams[i];
+            s.gpyr[i].resize(levels + 1);
+            int r = cam.rh, w = cam.rw;
+            for (int l = 0; l <= levels; ++l) {
+                SB_TRY(s.gpyr[i][l].create(r, w, SB_16SC3));
+                r = (r + 1) / 2; w = (w + 1) / 2;
+            }
+        }
+    }
+    SB_TRY(s.out.create(c->dst_roi_final.height, c->dst_roi_final.width, c->cfg.output_type));
+    SB_TRY(s.out_mask.create(c->dst_roi_final.height, c->dst_roi_final.width, SB_8UC1));
+    return SB_OK;
+}
+
+void free_slot(Slot &s)
+{
+    if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+    if (s.ev_start) cudaEventDestroy(s.ev_start);
+    if (s.ev_stop) cudaEventDestroy(s.ev_stop);
+    s.stream = nullptr; s.ev_start = s.ev_stop = nullptr;
+}
+
+// calibration-time work: geometry, tables, masks, weights
+int setup(sb_compositor *c)
+{
+    const sb_compositor_config &cfg = c->cfg;
+    cudaStream_t s = c->setup_stream;
+    const int n = cfg.n_cameras;
+    c->cams.resize(n);
+    int tlx = INT32_MAX, tly = INT32_MAX, brx = INT32_MIN, bry = INT32_MIN;
+    DevImage ones, xmap, ymap;
+    SB_TRY(ones.create(cfg.src_size.height, cfg.src_size.width, SB_8UC1));
+    SB_CUDA(cudaMemset2DAsync(ones.v.data, ones.v.step, 255, ones.v.cols, ones.v.rows, s));
+    const float zeroT[3] = {0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+        Camera &cam = c->cams[i];
+        projector_set(cam.proj, cfg.warper_kind, cfg.warper_scale, cfg.K + 9 * i, cfg.R + 9 * i, zeroT);
+        sb_point br;
+        projector_detect_result_roi(cam.proj, cfg.src_size.width, cfg.src_size.height, &cam.tl, &br);
+        long long ww = (long long)br.x - cam.tl.x + 1, wh = (long long)br.y - cam.tl.y + 1;
+        if (ww <= 0 || wh <= 0 || ww * wh > (1LL << 31)) return fail(SB_ERR_ASSERT, "camera %d: degenerate warped ROI", i);
+        cam.ww = (int)ww; cam.wh = (int)wh;
+        cam.gain = (cfg.comp_kind == SB_COMP_GAIN && cfg.gains) ? (float)cfg.gains[i] : 1.f;
+        tlx = std::min(tlx, cam.tl.x); tly = std::min(tly, cam.tl.y);
+        brx = std::max(brx, cam.tl.x + cam.ww); bry = std::max(bry, cam.tl.y + cam.wh);
+        // separable trig tables
+        SB_TRY(cam.tables.ensure(sizeof(float) * 2 * (size_t)(cam.ww + cam.wh)));
+        float *t = static_cast<float *>(cam.tables.p);
+        SB_TRY(launch_build_warp_tables(cam.proj, cam.tl.x, cam.tl.y, cam.ww, cam.wh, t, t + cam.ww, t + 2 * cam.ww, t + 2 * cam.ww + cam.wh, s));
+        cam.wt.col_sin = t; cam.wt.col_cos = t + cam.ww; cam.wt.row_a = t + 2 * cam.ww; cam.wt.row_b = t + 2 * cam.ww + cam.wh;
+        // warped mask: w->warp(mask, K, R, INTER_NEAREST, BORDER_CONSTANT) (stitcher.cpp:278-280)
+        SB_TRY(xmap.create(cam.wh, cam.ww, SB_32FC1));
+        SB_TRY(ymap.create(cam.wh, cam.ww, SB_32FC1));
+        SB_TRY(launch_build_maps(cam.proj, cam.tl.x, cam.tl.y, xmap.v, ymap.v, s));
+        SB_TRY(cam.mask.create(cam.wh, cam.ww, SB_8UC1));
+        SB_TRY(launch_remap(ones.v, cam.mask.v, xmap.v, ymap.v, SB_INTER_NEAREST, SB_BORDER_CONSTANT, nullptr, s));
+        if (cfg.seam_masks) {   // mask_warped = seam_mask & mask_warped (stitcher.cpp:294)
+            const sb_image &sm = cfg.seam_masks[i];
+            SB_ASSERT(sm.type == SB_8UC1 && sm.rows == cam.wh && sm.cols == cam.ww && sm.data);
+            DevImage st;
+            DImage dsm;
+            SB_TRY(to_device(sm, st, s, &dsm));
+            SB_TRY(launch_and_8u(dsm, cam.mask.v, s));
+            SB_CUDA(cudaStreamSynchronize(s));
+        }
+    }
+    // Blender::prepare(corners, sizes) -> resultRoi (util.cpp:127-140) -> prepare(Rect)
+    sb_rect roi = {tlx, tly, brx - tlx, bry - tly};
+    c->dst_roi_final = roi;
+    c->num_bands = 0;
+    if (cfg.blender_kind == SB_BLEND_MULTI_BAND) {
+        double max_len = static_cast<double>(std::max(roi.width, roi.height));
+        c->num_bands = std::min(cfg.num_bands, static_cast<int>(std::ceil(std::log(max_len) / std::log(2.0))));
+        SB_ASSERT(c->num_bands >= 0 && c->num_bands < 24);
+        const int m = 1 << c->num_bands;
+        roi.width += (m - roi.width % m) % m;
+        roi.height += (m - roi.height % m) % m;
+    }
+    c->dst_roi = roi;
+
+    if (cfg.blender_kind == SB_BLEND_MULTI_BAND) {
+        const int nb = c->num_bands, m = 1 << nb, gap = 3 * m;
+        const int wt = cfg.weight_type == SB_32F ? SB_32FC1 : SB_16SC1;
+        c->wsum.resize(nb + 1);
+        int rows = roi.height, cols = roi.width;
+        for (int l = 0; l <= nb; ++l) {
+            SB_TRY(c->wsum[l].create_zero(rows, cols, wt, s));
+            rows = (rows + 1) / 2; cols = (cols + 1) / 2;
+        }
+        const int rbr_x = roi.x + roi.width, rbr_y = roi.y + roi.height;
+        for (int i = 0; i < n; ++i) {
+            Camera &cam = c->cams[i];
+            // MultiBandBlender::feed geometry (blenders.cpp:241-269)
+            sb_point tl_new = {std::max(roi.x, cam.tl.x - gap), std::max(roi.y, cam.tl.y - gap)};
+            sb_point br_new = {std::min(rbr_x, cam.tl.x + cam.ww + gap), std::min(rbr_y, cam.tl.y + cam.wh + gap)};
+            tl_new.x = roi.x + (((tl_new.x - roi.x) >> nb) << nb);
+            tl_new.y = roi.y + (((tl_new.y - roi.y) >> nb) << nb);
+            int width = br_new.x - tl_new.x, height = br_new.y - tl_new.y;
+            width += (m - width % m) % m;
+            height += (m - height % m) % m;
+            br_new.x = tl_new.x + width; br_new.y = tl_new.y + height;
+            const int dy = std::max(br_new.y - rbr_y, 0), dx = std::max(br_new.x - rbr_x, 0);
+            tl_new.x -= dx; br_new.x -= dx; tl_new.y -= dy; br_new.y -= dy;
+            cam.top = cam.tl.y - tl_new.y; cam.left = cam.tl.x - tl_new.x;
+            cam.rx = tl_new.x - roi.x; cam.ry = tl_new.y - roi.y; cam.rw = width; cam.rh = height;
+            SB_ASSERT(cam.top >= 0 && cam.left >= 0 && cam.rx >= 0 && cam.ry >= 0);
+            // weight pyramid (:282-298) and its contribution to dst_band_weights_ (:324, :349)
+            cam.w_pyr.resize(nb + 1);
+            SB_TRY(cam.w_pyr[0].create(height, width, wt));
+            SB_TRY(launch_mask_to_weight(cam.mask.v, cam.w_pyr[0].v, cam.top, cam.left, s));
+            int x_tl = cam.rx, y_tl = cam.ry;
+            for (int l = 0; l <= nb; ++l) {
+                if (l > 0) {
+                    const DImage &p = cam.w_pyr[l - 1].v;
+                    SB_TRY(cam.w_pyr[l].create((p.rows + 1) / 2, (p.cols + 1) / 2, wt));
+                    SB_TRY(launch_pyr_down(p, cam.w_pyr[l].v, s));
+                }
+                SB_TRY(launch_weight_accumulate(cam.w_pyr[l].v, c->wsum[l].v, x_tl, y_tl, s));
+                x_tl /= 2; y_tl /= 2;
+            }
+        }
+    } else if (cfg.blender_kind == SB_BLEND_FEATHER) {
+        c->wsum.resize(1);
+        SB_TRY(c->wsum[0].create_zero(roi.height, roi.width, SB_32FC1, s));
+        DevBuf scratch;
+        for (int i = 0; i < n; ++i) {
+            Camera &cam = c->cams[i];
+            SB_TRY(cam.feather_w.create(cam.wh, cam.ww, SB_32FC1));
+            SB_TRY(launch_distance_l1(cam.mask.v, cam.feather_w.v, scratch, s));
+            SB_TRY(launch_weight_from_dist(cam.feather_w.v, cfg.sharpness, s));
+            SB_TRY(launch_weight_accumulate(cam.feather_w.v, c->wsum[0].v, cam.tl.x - roi.x, cam.tl.y - roi.y, s));
+        }
+        SB_CUDA(cudaStreamSynchronize(s));
+    }
+    SB_CUDA(cudaStreamSynchronize(s));
+    return SB_OK;
+}
+
+int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
+{
+    const sb_compositor_config &cfg = c->cfg;
+    const int n = cfg.n_cameras;
+    const bool gain_on = cfg.comp_kind == SB_COMP_GAIN;
+    cudaStream_t st = s.stream;
+    DImage none;
+    // Blender::prepare: zero the accumulators (blenders.cpp:71-78, 227-232); weight sums are resident
+    for (auto &a : s.acc) SB_CUDA(cudaMemsetAsync(a.v.data, 0, a.v.step * (size_t)a.v.rows, st));
+    if (cfg.blender_kind == SB_BLEND_MULTI_BAND) {
+        const int nb = c->num_bands;
+        for (int i = 0; i < n; ++i) {
+            const Camera &cam = c->cams[i];
+            auto &g = s.gpyr[i];
+            // warp + gain + convertTo(16S) + copyMakeBorder(REFLECT) -> Gaussian level 0
+            SB_TRY(launch_warp_fused(cam.proj, cam.wt, src[i], cam.ww, cam.wh, cam.left, cam.top, cam.gain, gain_on, g[0].v, st));
+            for (int l = 0; l < nb; ++l) SB_TRY(launch_pyr_down(g[l].v, g[l + 1].v, st));
+            int x_tl = cam.rx, y_tl = cam.ry;
+            for (int l = 0; l <= nb; ++l) {
+                SB_TRY(launch_lap_accumulate(g[l].v, l < nb ? g[l + 1].v : none, cam.w_pyr[l].v, s.acc[l].v, none, x_tl, y_tl, st));
+                x_tl /= 2; y_tl /= 2;
+            }
+        }
+        SB_TRY(launch_normalize(c->wsum[nb].v, s.acc[nb].v, st));
+        for (int l = nb - 1; l >= 0; --l) SB_TRY(launch_normalize_collapse(s.acc[l + 1].v, c->wsum[l].v, s.acc[l].v, st));
+        SB_TRY(launch_finalize(s.acc[0].v, c->wsum[0].v, nullptr, s.out.v, s.out_mask.v, st));
+    } else {
+        if (cfg.blender_kind == SB_BLEND_NO) SB_CUDA(cudaMemsetAsync(s.acc_mask.v.data, 0, s.acc_mask.v.step * (size_t)s.acc_mask.v.rows, st));
+        for (int i = 0; i < n; ++i) {
+            const Camera &cam = c->cams[i];
+            SB_TRY(s.warped.create(cam.wh, cam.ww, SB_8UC3));
+            SB_TRY(launch_warp_fused(cam.proj, cam.wt, src[i], cam.ww, cam.wh, 0, 0, cam.gain, gain_on, s.warped.v, st));
+            const int dx = cam.tl.x - c->dst_roi.x, dy = cam.tl.y - c->dst_roi.y;
+            if (cfg.blender_kind == SB_BLEND_FEATHER)
+                SB_TRY(launch_feather_accumulate(s.warped.v, cam.feather_w.v, s.acc[0].v, none, dx, dy, st));
+            else
+                SB_TRY(launch_masked_copy(s.warped.v, cam.mask.v, s.acc[0].v, s.acc_mask.v, dx, dy, st));
+        }
+        if (cfg.blender_kind == SB_BLEND_FEATHER) {
+            SB_TRY(launch_normalize(c->wsum[0].v, s.acc[0].v, st));
+            SB_TRY(launch_finalize(s.acc[0].v, c->wsum[0].v, nullptr, s.out.v, s.out_mask.v, st));
+        } else
+            SB_TRY(launch_finalize(s.acc[0].v, none, &s.acc_mask.v, s.out.v, s.out_mask.v, st));
+    }
+    return SB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sb_compositor_create(const sb_compositor_config *cfg, int device, sb_compositor **out)
+{
+    if (!out) return fail(SB_ERR_ASSERT, "out is null");
+    *out = nullptr;
+    SB_ASSERT(cfg && cfg->n_cameras > 0 && cfg->K && cfg->R);
+    SB_ASSERT(cfg->src_size.width > 0 && cfg->src_size.height > 0);
+    if (cfg->warper_kind != SB_WARP_PLANE && cfg->warper_kind != SB_WARP_CYLINDRICAL && cfg->warper_kind != SB_WARP_SPHERICAL)
+        return fail(SB_ERR_BAD_ARG, "unsupported warper kind %d", cfg->warper_kind);
+    if (cfg->blender_kind != SB_BLEND_NO && cfg->blender_kind != SB_BLEND_FEATHER && cfg->blender_kind != SB_BLEND_MULTI_BAND)
+        return fail(SB_ERR_BAD_ARG, "unsupported blending method");
+    if (cfg->comp_kind != SB_COMP_NO && cfg->comp_kind != SB_COMP_GAIN)
+        return fail(SB_ERR_BAD_ARG, "compositor supports SB_COMP_NO and SB_COMP_GAIN");
+    if (cfg->blender_kind == SB_BLEND_MULTI_BAND) SB_ASSERT(cfg->weight_type == SB_32F || cfg->weight_type == SB_16S);
+    SB_ASSERT(cfg->output_type == SB_8UC3 || cfg->output_type == SB_16SC3);
+    SB_ASSERT(cfg->comp_kind != SB_COMP_GAIN || cfg->gains);
+    DeviceGuard g(device);
+    if (!g.ok) return SB_ERR_CUDA;
+    sb_compositor *c = new sb_compositor;
+    c->device = device;
+    c->cfg = *cfg;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->setup_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return fail(SB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    int rc = setup(c);
+    if (rc == SB_OK) {
+        c->slots.resize(1);
+        rc = make_slot(c, c->slots[0]);
+    }
+    // the config's pointers are not retained
+    c->cfg.K = c->cfg.R = nullptr; c->cfg.gains = nullptr; c->cfg.seam_masks = nullptr;
+    if (rc != SB_OK) { sb_compositor_destroy(c); return rc; }
+    *out = c;
+    return SB_OK;
+}
+
+void sb_compositor_destroy(sb_compositor *c)
+{
+    if (!c) return;
+    DeviceGuard g(c->device);
+    for (auto &s : c->slots) free_slot(s);
+    if (c->setup_stream) cudaStreamDestroy(c->setup_stream);
+    delete c;
+}
+
+int sb_compositor_pano_size(const sb_compositor *c, sb_size *size)
+{
+    SB_ASSERT(c && size);
+    size->width = c->dst_roi_final.width; size->height = c->dst_roi_final.height;
+    return SB_OK;
+}
+
+int sb_compositor_camera_roi(const sb_compositor *c, int index, sb_rect *roi)
+{
+    SB_ASSERT(c && roi && index >= 0 && index < (int)c->cams.size());
+    const Camera &cam = c->cams[index];
+    roi->x = cam.tl.x; roi->y = cam.tl.y; roi->width = cam.ww; roi->height = cam.wh;
+    return SB_OK;
+}
+
+int sb_compositor_set_depth(sb_compositor *c, int depth)
+{
+    SB_ASSERT(c && depth >= 1 && depth <= 16);
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    for (auto &s : c->slots) if (s.busy) return fail(SB_ERR_ASSERT, "set_depth with frames in flight");
+    while ((int)c->slots.size() > depth) { free_slot(c->slots.back()); c->slots.pop_back(); }
+    while ((int)c->slots.size() < depth) {
+        c->slots.emplace_back();
+        SB_TRY(make_slot(c, c->slots.back()));
+    }
+    c->next_slot = 0;
+    return SB_OK;
+}
+
+int sb_compositor_enqueue(sb_compositor *c, const sb_image *srcs, sb_image *pano, sb_image *pano_mask, int *slot)
+{
+    SB_ASSERT(c && srcs && pano && slot);
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    const int si = c->next_slot;
+    Slot &s = c->slots[si];
+    if (s.busy) return fail(SB_ERR_ASSERT, "slot %d still in flight: call sb_compositor_wait first", si);
+    const int n = c->cfg.n_cameras;
+    SB_CUDA(cudaEventRecord(s.ev_start, s.stream));
+    std::vector<DImage> src(n);
+    for (int i = 0; i < n; ++i) {
+        SB_ASSERT(srcs[i].type == SB_8UC3 && srcs[i].rows == c->cfg.src_size.height && srcs[i].cols == c->cfg.src_size.width);
+        SB_TRY(to_device(srcs[i], s.src[i], s.stream, &src[i]));
+    }
+    SB_TRY(run_frame(c, s, src));
+    if (!pano->data) lend(s.out.v, c->device, pano);
+    else SB_TRY(from_device(s.out.v, pano, s.stream));
+    if (pano_mask) {
+        if (!pano_mask->data) lend(s.out_mask.v, c->device, pano_mask);
+        else SB_TRY(from_device(s.out_mask.v, pano_mask, s.stream));
+    }
+    SB_CUDA(cudaEventRecord(s.ev_stop, s.stream));
+    s.busy = true;
+    *slot = si;
+    c->next_slot = (si + 1) % (int)c->slots.size();
+    return SB_OK;
+}
+
+int sb_compositor_wait(sb_compositor *c, int slot)
+{
+    SB_ASSERT(c && slot >= 0 && slot < (int)c->slots.size());
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    Slot &s = c->slots[slot];
+    if (!s.busy) return SB_OK;
+    SB_CUDA(cudaEventSynchronize(s.ev_stop));
+    s.busy = false;
+    return SB_OK;
+}
+
+int sb_compositor_compose(sb_compositor *c, const sb_image *srcs, sb_image *pano, sb_image *pano_mask)
+{
+    int slot = -1;
+    SB_TRY(sb_compositor_enqueue(c, srcs, pano, pano_mask, &slot));
+    return sb_compositor_wait(c, slot);
+}
+
+int sb_compositor_last_gpu_ms(sb_compositor *c, int slot, float *ms)
+{
+    SB_ASSERT(c && ms && slot >= 0 && slot < (int)c->slots.size());
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    Slot &s = c->slots[slot];
+    SB_CUDA(cudaEventSynchronize(s.ev_stop));
+    SB_CUDA(cudaEventElapsedTime(ms, s.ev_start, s.ev_stop));
+    return SB_OK;
+}
+
+}  // extern "C"

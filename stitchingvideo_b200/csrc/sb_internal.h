@@ -1,0 +1,103 @@
+// sb_internal.h — shared host-side plumbing of libstitchb200 (error state, device buffers, staging).
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/stitchb200.h"
+
+namespace sb {
+
+extern thread_local std::string g_last_error;
+extern std::atomic<uint64_t> g_launches;
+
+int fail(int code, const char *fmt, ...);
+
+#define SB_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return sb::fail(SB_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define SB_TRY(expr)                  \
+    do {                              \
+        int rc_ = (expr);             \
+        if (rc_ != SB_OK) return rc_; \
+    } while (0)
+// CV_Assert-shaped argument check
+#define SB_ASSERT(cond)                                                                            \
+    do {                                                                                           \
+        if (!(cond)) return sb::fail(SB_ERR_ASSERT, "assertion failed: %s (%s:%d)", #cond, __FILE__, __LINE__); \
+    } while (0)
+// after every kernel launch: count it and surface launch-configuration errors
+#define SB_LAUNCHED()                                                                              \
+    do {                                                                                           \
+        sb::g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
+        cudaError_t e_ = cudaPeekAtLastError();                                                    \
+        if (e_ != cudaSuccess)                                                                     \
+            return sb::fail(SB_ERR_CUDA, "kernel launch: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline int type_depth(int type) { return type & 7; }
+inline int type_cn(int type) { return ((type >> 3) & 63) + 1; }
+inline int depth_size(int depth) { return depth == SB_8U ? 1 : depth == SB_16S ? 2 : depth == SB_32F ? 4 : 0; }
+inline int elem_size(int type) { return depth_size(type_depth(type)) * type_cn(type); }
+inline bool type_supported(int type)
+{
+    return type == SB_8UC1 || type == SB_8UC3 || type == SB_16SC1 || type == SB_16SC3 || type == SB_32FC1;
+}
+inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// device image view
+struct DImage {
+    void *data = nullptr;
+    int rows = 0, cols = 0, type = 0;
+    size_t step = 0;
+    template <typename T> T *ptr() const { return static_cast<T *>(data); }
+    bool empty() const { return data == nullptr || rows <= 0 || cols <= 0; }
+};
+
+// grow-only device allocation (kept across frames: no cudaMalloc on the per-frame path)
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+    ~DevBuf() { release(); }
+    int ensure(size_t bytes);
+    void release();
+};
+
+// owned device image with a 256-byte aligned pitch
+struct DevImage {
+    DevBuf buf;
+    DImage v;
+    int create(int rows, int cols, int type);   // contents undefined
+    int create_zero(int rows, int cols, int type, cudaStream_t s);
+};
+
+inline size_t aligned_step(int cols, int type) { return ((size_t)cols * elem_size(type) + 255) & ~(size_t)255; }
+
+int check_image(const sb_image *img, const char *what);
+// Device view of an sb_image: zero copy for device images, else staged H2D into `stage`.
+int to_device(const sb_image &img, DevImage &stage, cudaStream_t s, DImage *out);
+// Copy a device image into the caller's sb_image (host or device); sizes/types must match.
+int from_device(const DImage &src, sb_image *dst, cudaStream_t s);
+// Point a caller sb_image with data == NULL at a handle-owned device image.
+void lend(const DImage &src, int device, sb_image *dst);
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int device);
+    ~DeviceGuard();
+};
+
+}  // namespace sb
