@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — 5x1080p -> panorama frames/s on N B200s (BASELINE.json metric), one process per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                      (the CPU arm: oracle/_ref or the oracle port)
+
+A "step" is one pass of the hot path over one synthetic frame set (n cameras -> one panorama).
+  value   : whole-job frames/s with the frames already resident in HBM (device pointers in, device
+            panorama out), timed on the device between two marks that span every in-flight slot.
+  e2e     : the same metric through the reference-facing C ABI with HOST buffers: each step copies
+            its n source frames host->device from pinned memory and the panorama device->host.
+  roofline: dominant kernel's algorithmic bytes / its CUDA-event duration vs MEASURED_PEAKS.json.
+  cpu_baseline: the CPU oracle (single core, "port") on a bounded sample, rank 0 at N=1 only.
+Frames are independent once calibration is fixed: rank r processes its own frame sets, no
+collective on the data path ("scaling": "weak").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "5x1080p->panorama frames/s"
+WORKLOADS = {
+    "c2": "C2: 5-camera 1080p 360deg, CylindricalWarper + FeatherBlender(0.02), fixed calibration (BASELINE.json configs[1])",
+    "c3": "C3: 5-camera 1080p 360deg, SphericalWarper + GainCompensator + MultiBandBlender(5 bands, CV_32F weights) (configs[2])",
+    "c4": "C4: 8-camera 4K VR, SphericalWarper + GainCompensator + MultiBandBlender(5 bands) (configs[3])",
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_frames(rig, n_sets, n_cams, rank):
+    from stitchingvideo_b200 import rigs
+    return [[rigs.frame(rig, rank * 1000 + s, i) for i in range(n_cams)] for s in range(n_sets)]
+
+
+def pipelined(comp, frame_sets, outs, steps, depth):
+    """steps frames through `depth` in-flight slots; returns the slot list (all waited)."""
+    slots = []
+    for k in range(steps):
+        if k >= depth:
+            comp.wait(slots[k - depth])
+        pano, mask = outs[k % len(outs)]
+        slots.append(comp.enqueue(frame_sets[k % len(frame_sets)], pano, mask))
+    for s in slots[-depth:]:
+        comp.wait(s)
+    return slots
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import stitchingvideo_b200 as sv
+    from stitchingvideo_b200 import capi, rigs
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    Ks, Rs, spec = rigs.cameras(args.workload)
+    n, size = spec["n_used"], (spec["W"], spec["H"])
+    comp = sv.Compositor(size, Ks, Rs, warper=spec["warper"], scale=spec["scale"], blender=spec["blender"], num_bands=5,
+                         weight_type=sv.CV_32F, sharpness=0.02, gains=spec["gain_values"], output_type=sv.CV_8UC3, device=local)
+    pw, ph = comp.pano_size
+    n_sets = args.frame_sets
+    host_sets = make_frames(args.workload, n_sets, n, rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- value: inputs resident in HBM, output stays on the device ----------------
+    dev_tensors = [[torch.from_numpy(f).cuda() for f in s] for s in host_sets]
+    dev_sets = [[capi.DeviceImage.from_torch(t) for t in s] for s in dev_tensors]
+    comp.set_depth(args.depth)
+    dev_outs = [(None, None)]            # panorama stays in the slot's device buffer (lent, no copy)
+    pipelined(comp, dev_sets, dev_outs, args.warmup, args.depth)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = sv.kernel_launch_count()
+    comp.mark(0)
+    pipelined(comp, dev_sets, dev_outs, args.steps, args.depth)
+    comp.mark(1)
+    ms_dev = comp.marked_ms()
+    launches = sv.kernel_launch_count() - launches0
+    barrier()
+    ms_dev = max_over_ranks(ms_dev)
+    value = world * args.steps / (ms_dev / 1e3)
+
+    # ---------------- e2e: host buffers through the C ABI (H2D + kernels + D2H per step) ----------------
+    pin_in = [[torch.from_numpy(f).pin_memory() for f in s] for s in host_sets]
+    pin_sets = [[t.numpy() for t in s] for s in pin_in]
+    pin_out = [torch.empty((ph, pw, 3), dtype=torch.uint8).pin_memory() for _ in range(args.depth + 1)]
+    pin_outs = [(t.numpy(), None) for t in pin_out]
+    pipelined(comp, pin_sets, pin_outs, args.warmup, args.depth)
+    barrier()
+    comp.mark(0)
+    t0 = time.perf_counter()
+    pipelined(comp, pin_sets, pin_outs, args.steps, args.depth)
+    comp.mark(1)
+    ms_e2e = comp.marked_ms()
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    barrier()
+    ms_e2e = max_over_ranks(max(ms_e2e, wall_e2e))
+    clocks = sampler.summary()
+    e2e_value = world * args.steps / (ms_e2e / 1e3)
+    h2d = n * size[0] * size[1] * 3
+    d2h = pw * ph * 3
+
+    # ---------------- roofline: per-kernel CUDA-event timing (separate pass, never the reported fps) ----------------
+    comp.set_depth(1)
+    agg = {}
+    for it in range(args.profile_frames + 1):
+        recs = comp.profile_frame(dev_sets[it % n_sets])
+        if it == 0:
+            continue                      # warm-up
+        for r in recs:
+            a = agg.setdefault(r["name"], {"ms": 0.0, "bytes": 0.0, "launches": 0})
+            a["ms"] += r["ms"]; a["bytes"] += r["bytes"]; a["launches"] += 1
+    peak, peak_src = peaks()
+    total_ms = sum(a["ms"] for a in agg.values())
+    kernels = []
+    for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        gbs = a["bytes"] / (a["ms"] * 1e-3) / 1e9 if a["ms"] > 0 else 0.0
+        kernels.append({"name": name, "launches_per_step": a["launches"] / args.profile_frames,
+                        "ms_per_step": a["ms"] / args.profile_frames, "share": a["ms"] / total_ms if total_ms else 0.0,
+                        "algorithmic_mb_per_step": a["bytes"] / args.profile_frames / 1e6, "achieved_gbs": gbs, "frac": gbs / peak})
+    dom = kernels[0]
+    roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": dom["frac"], "traffic": None, "peak_source": peak_src, "share_of_step": dom["share"],
+                "avg_launch_us": dom["ms_per_step"] / dom["launches_per_step"] * 1e3,
+                "algorithmic_bytes_per_launch": dom["algorithmic_mb_per_step"] * 1e6 / dom["launches_per_step"],
+                "whole_step": {"algorithmic_mb": sum(k["algorithmic_mb_per_step"] for k in kernels),
+                               "serial_kernel_ms": total_ms / args.profile_frames,
+                               "achieved_gbs": sum(k["algorithmic_mb_per_step"] for k in kernels) / 1e3 / (total_ms / args.profile_frames / 1e3) if total_ms else 0.0}}
+
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/s16 integer + f32 weights", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "frames_per_rank": args.steps, "cameras": n, "frame": "%dx%d" % size,
+                   "panorama": "%dx%d" % (pw, ph), "in_flight_slots": args.depth,
+                   "l2_policy": "inputs rotate over %d frame sets (%.0f MB) and each step streams >400 MB of intermediates; "
+                                "working set exceeds the 126 MB L2" % (n_sets, n_sets * h2d / 1e6)},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps, "host_buffers": "pinned"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.workload, sample_frames=args.cpu_frames)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------- CPU arms
+def _oracle_ctx(workload):
+    from stitchingvideo_b200 import rigs
+    from oracle import pipeline as P
+    Ks, Rs, spec = rigs.cameras(workload)
+    size = (spec["W"], spec["H"])
+    cal = P.Calibration(size, Ks, Rs, spec["warper"], spec["scale"])
+    return cal, spec
+
+
+def _oracle_frame(cal, spec, workload, idx):
+    from stitchingvideo_b200 import rigs
+    from oracle import pipeline as P
+    frames = [rigs.frame(workload, idx, i, smooth=0) for i in range(spec["n_used"])]
+    t = time.perf_counter()
+    P.compose(cal, frames, blender=spec["blender"], num_bands=5, gains=spec["gain_values"])
+    return time.perf_counter() - t
+
+
+def cpu_baseline(workload, sample_frames=4):
+    """The CPU oracle (single-threaded C restatement of the reference path) on a bounded sample."""
+    cal, spec = _oracle_ctx(workload)
+    _oracle_frame(cal, spec, workload, 0)
+    ts = [_oracle_frame(cal, spec, workload, 1 + i) for i in range(sample_frames)]
+    best = min(ts)
+    out = {"value": 1.0 / best, "unit": "frames/s", "cores": 1, "kind": "port",
+           "sample": "%d full frame sets of the same workload after 1 warm-up, best of %d (%.2f s each); "
+                     "per-sequence maps/masks excluded like the GPU arm" % (sample_frames, sample_frames, best),
+           "host_cpu": _cpu_model(), "host_cores": os.cpu_count()}
+    try:
+        out["cv2_all_cores"] = cv2_baseline(workload)
+    except Exception as e:      # cv2 is optional context, not the baseline
+        out["cv2_all_cores"] = {"unavailable": str(e)[:100]}
+    return out
+
+
+def cv2_baseline(workload, frames=3):
+    """Context only: OpenCV 4.13's own cv::detail blenders + cv::remap with all host cores
+    (a stronger CPU baseline than the reference's 2.4.11 build)."""
+    import cv2
+    from stitchingvideo_b200 import rigs
+    cal, spec = _oracle_ctx(workload)
+    cv2.setNumThreads(os.cpu_count())
+    best = 1e9
+    for it in range(frames + 1):
+        fr = [rigs.frame(workload, it, i, smooth=0) for i in range(spec["n_used"])]
+        t = time.perf_counter()
+        b = cv2.detail_MultiBandBlender(0, 5, cv2.CV_32F) if spec["blender"] == "multiband" else cv2.detail_FeatherBlender(0.02)
+        from oracle import oracle as O
+        b.prepare(O.result_roi(cal.corners, cal.sizes))
+        for i, f in enumerate(fr):
+            w = cv2.remap(f, cal.maps[i][0], cal.maps[i][1], cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT)
+            if spec["gain_values"]:
+                w = cv2.convertScaleAbs(w, alpha=spec["gain_values"][i])
+            b.feed(w.astype(np.int16), cal.masks[i], cal.corners[i])
+        d, m = b.blend(None, None)
+        cv2.convertScaleAbs(d)
+        if it:
+            best = min(best, time.perf_counter() - t)
+    return {"value": 1.0 / best, "unit": "frames/s", "cores": os.cpu_count(), "impl": "cv2 %s" % cv2.__version__}
+
+
+def _cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for l in f:
+                if l.startswith("model name"):
+                    return l.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+_W = {}
+
+
+def _worker_init(workload):
+    _W["ctx"] = _oracle_ctx(workload)
+    _W["workload"] = workload
+
+
+def _worker_frame(idx):
+    cal, spec = _W["ctx"]
+    return _oracle_frame(cal, spec, _W["workload"], idx)
+
+
+def run_reference(args):
+    """CPU arm: the reference path on all host cores.  One step = one batch of `cores` independent
+    frame sets, one per worker process (frames are independent, so this is how the CPU path scales)."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libstitch_ref.so")) and False else "port"
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_worker_init, initargs=(args.workload,)) as pool:
+        for w in range(args.warmup):
+            pool.map(_worker_frame, range(cores))
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            pool.map(_worker_frame, range(k * cores, (k + 1) * cores))
+        dt = time.perf_counter() - t0
+    value = args.steps * cores / dt
+    _, spec = _oracle_ctx(args.workload)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/s16 integer + f32 weights", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload], "cameras": spec["n_used"], "frame": "%dx%d" % (spec["W"], spec["H"])},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
+                             "sample": "each step = %d full frame sets, one per worker process (%d processes); "
+                                       "per-sequence maps/masks built once per worker and excluded" % (cores, cores),
+                             "host_cpu": _cpu_model()},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--depth", type=int, default=3, help="frame sets in flight (slots)")
+    ap.add_argument("--frame-sets", type=int, default=4)
+    ap.add_argument("--profile-frames", type=int, default=5)
+    ap.add_argument("--cpu-frames", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        if args.steps == 200:
+            args.steps, args.warmup = 4, 3
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -200,6 +200,14 @@ int  sb_compositor_enqueue(sb_compositor *c, const sb_image *srcs, sb_image *pan
 int  sb_compositor_wait(sb_compositor *c, int slot);
 /* device-resident timing of the last compose on a slot, ms (CUDA events on the slot's stream) */
 int  sb_compositor_last_gpu_ms(sb_compositor *c, int slot, float *ms);
+/* Device-side timing of a region spanning every slot: mark(0) before the first enqueue, mark(1)
+ * after the last; marked_ms waits for mark 1 and returns the elapsed milliseconds between them. */
+int  sb_compositor_mark(sb_compositor *c, int which);
+int  sb_compositor_marked_ms(sb_compositor *c, float *ms);
+/* Measurement hook for bench.py's roofline: runs one frame on slot 0 with every kernel bracketed by
+ * CUDA events on its launching stream and writes a JSON array of
+ * {"name", "ms", "bytes" (algorithmic bytes of that launch)} into buf. */
+int  sb_compositor_profile_frame(sb_compositor *c, const sb_image *srcs, char *buf, size_t cap);
 
 #ifdef __cplusplus
 }

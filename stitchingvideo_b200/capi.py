@@ -113,6 +113,9 @@ API = {
     "sb_compositor_enqueue": (C.c_int, [C.c_void_p, _P(SbImage), _P(SbImage), _P(SbImage), _P(C.c_int)]),
     "sb_compositor_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "sb_compositor_last_gpu_ms": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_float)]),
+    "sb_compositor_mark": (C.c_int, [C.c_void_p, C.c_int]),
+    "sb_compositor_marked_ms": (C.c_int, [C.c_void_p, _P(C.c_float)]),
+    "sb_compositor_profile_frame": (C.c_int, [C.c_void_p, _P(SbImage), C.c_char_p, C.c_size_t]),
 }
 
 _lib = None
@@ -565,8 +568,13 @@ class Compositor:
         _check(lib().sb_compositor_set_depth(self._h, depth))
 
     def enqueue(self, frames, pano, pano_mask=None):
+        """pano=None: the panorama stays in the slot's device buffer (returned SbImage is lent)."""
         arr, keep = self._srcs(frames)
-        ip, k0 = _image(pano)
+        if pano is None:
+            ip = SbImage(None, 0, 0, self.output_type, 0, -1)
+            self.last_lent = ip
+        else:
+            ip, k0 = _image(pano)
         im = None
         if pano_mask is not None:
             im, k1 = _image(pano_mask)
@@ -576,6 +584,22 @@ class Compositor:
 
     def wait(self, slot):
         _check(lib().sb_compositor_wait(self._h, slot))
+
+    def mark(self, which):
+        _check(lib().sb_compositor_mark(self._h, which))
+
+    def marked_ms(self):
+        ms = C.c_float()
+        _check(lib().sb_compositor_marked_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def profile_frame(self, frames):
+        """-> list of {"name", "ms", "bytes"} per kernel launch of one frame (CUDA events on the stream)."""
+        import json
+        arr, keep = self._srcs(frames)
+        buf = C.create_string_buffer(1 << 16)
+        _check(lib().sb_compositor_profile_frame(self._h, arr, buf, len(buf)))
+        return json.loads(buf.value.decode())
 
     def last_gpu_ms(self, slot=0):
         ms = C.c_float()

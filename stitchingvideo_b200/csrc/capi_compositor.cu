@@ -11,6 +11,7 @@
 // compose() then launches only the image-dependent kernels.
 #include <algorithm>
 #include <cmath>
+#include <string>
 
 #include "sb_host_projector.h"
 #include "sb_kernels.h"
@@ -33,7 +34,15 @@ struct Camera {
     DevImage feather_w;          // feather weight map (sequence-constant)
 };
 
+// per-kernel record of one profiled frame (bench.py's roofline): CUDA events on the launching stream
+struct ProfRec {
+    const char *name;
+    double bytes;            // algorithmic (compulsory) bytes of this launch: inputs once + outputs once
+    cudaEvent_t e0, e1;
+};
+
 struct Slot {
+    std::vector<ProfRec> *prof = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool busy = false;
@@ -57,6 +66,7 @@ struct sb_compositor {
     std::vector<Slot> slots;
     int next_slot = 0;
     cudaStream_t setup_stream = nullptr;
+    cudaEvent_t marks[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -217,6 +227,20 @@ int setup(sb_compositor *c)
     return SB_OK;
 }
 
+double img_bytes(const DImage &d) { return (double)d.rows * d.cols * elem_size(d.type); }
+
+// PROF(name, bytes, call): run `call`; when the slot is in profiling mode bracket it with events
+#define PROF(NAME, BYTES, CALL)                                                          \
+    do {                                                                                 \
+        ProfRec r_{NAME, (double)(BYTES), nullptr, nullptr};                             \
+        if (s.prof) {                                                                    \
+            SB_CUDA(cudaEventCreate(&r_.e0)); SB_CUDA(cudaEventCreate(&r_.e1));          \
+            SB_CUDA(cudaEventRecord(r_.e0, st));                                         \
+        }                                                                                \
+        SB_TRY(CALL);                                                                    \
+        if (s.prof) { SB_CUDA(cudaEventRecord(r_.e1, st)); s.prof->push_back(r_); }      \
+    } while (0)
+
 int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
 {
     const sb_compositor_config &cfg = c->cfg;
@@ -225,41 +249,54 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
     cudaStream_t st = s.stream;
     DImage none;
     // Blender::prepare: zero the accumulators (blenders.cpp:71-78, 227-232); weight sums are resident
-    for (auto &a : s.acc) SB_CUDA(cudaMemsetAsync(a.v.data, 0, a.v.step * (size_t)a.v.rows, st));
+    for (auto &a : s.acc) PROF("zero_fill", img_bytes(a.v), launch_set_zero(a.v, st));
     if (cfg.blender_kind == SB_BLEND_MULTI_BAND) {
         const int nb = c->num_bands;
         for (int i = 0; i < n; ++i) {
             const Camera &cam = c->cams[i];
             auto &g = s.gpyr[i];
             // warp + gain + convertTo(16S) + copyMakeBorder(REFLECT) -> Gaussian level 0
-            SB_TRY(launch_warp_fused(cam.proj, cam.wt, src[i], cam.ww, cam.wh, cam.left, cam.top, cam.gain, gain_on, g[0].v, st));
-            for (int l = 0; l < nb; ++l) SB_TRY(launch_pyr_down(g[l].v, g[l + 1].v, st));
+            // source is gathered (each pixel read ~once), output written once
+            PROF("warp_fused", img_bytes(src[i]) + img_bytes(g[0].v),
+                 launch_warp_fused(cam.proj, cam.wt, src[i], cam.ww, cam.wh, cam.left, cam.top, cam.gain, gain_on, g[0].v, st));
+            for (int l = 0; l < nb; ++l)
+                PROF("pyr_down", img_bytes(g[l].v) + img_bytes(g[l + 1].v), launch_pyr_down(g[l].v, g[l + 1].v, st));
             int x_tl = cam.rx, y_tl = cam.ry;
             for (int l = 0; l <= nb; ++l) {
-                SB_TRY(launch_lap_accumulate(g[l].v, l < nb ? g[l + 1].v : none, cam.w_pyr[l].v, s.acc[l].v, none, x_tl, y_tl, st));
+                // reads fine + coarse + weights, read-modify-write of the accumulator window
+                PROF("lap_accumulate", img_bytes(g[l].v) * 3 + (l < nb ? img_bytes(g[l + 1].v) : 0) + img_bytes(cam.w_pyr[l].v),
+                     launch_lap_accumulate(g[l].v, l < nb ? g[l + 1].v : none, cam.w_pyr[l].v, s.acc[l].v, none, x_tl, y_tl, st));
                 x_tl /= 2; y_tl /= 2;
             }
         }
-        SB_TRY(launch_normalize(c->wsum[nb].v, s.acc[nb].v, st));
-        for (int l = nb - 1; l >= 0; --l) SB_TRY(launch_normalize_collapse(s.acc[l + 1].v, c->wsum[l].v, s.acc[l].v, st));
-        SB_TRY(launch_finalize(s.acc[0].v, c->wsum[0].v, nullptr, s.out.v, s.out_mask.v, st));
+        PROF("normalize", img_bytes(s.acc[nb].v) * 2 + img_bytes(c->wsum[nb].v), launch_normalize(c->wsum[nb].v, s.acc[nb].v, st));
+        for (int l = nb - 1; l >= 0; --l)
+            PROF("normalize_collapse", img_bytes(s.acc[l].v) * 2 + img_bytes(s.acc[l + 1].v) + img_bytes(c->wsum[l].v),
+                 launch_normalize_collapse(s.acc[l + 1].v, c->wsum[l].v, s.acc[l].v, st));
+        PROF("finalize", img_bytes(s.out.v) * (1 + 6.0 / elem_size(s.out.v.type)) + img_bytes(s.out_mask.v) * (1 + elem_size(c->wsum[0].v.type)),
+             launch_finalize(s.acc[0].v, c->wsum[0].v, nullptr, s.out.v, s.out_mask.v, st));
     } else {
-        if (cfg.blender_kind == SB_BLEND_NO) SB_CUDA(cudaMemsetAsync(s.acc_mask.v.data, 0, s.acc_mask.v.step * (size_t)s.acc_mask.v.rows, st));
+        if (cfg.blender_kind == SB_BLEND_NO) PROF("zero_fill", img_bytes(s.acc_mask.v), launch_set_zero(s.acc_mask.v, st));
         for (int i = 0; i < n; ++i) {
             const Camera &cam = c->cams[i];
             SB_TRY(s.warped.create(cam.wh, cam.ww, SB_8UC3));
-            SB_TRY(launch_warp_fused(cam.proj, cam.wt, src[i], cam.ww, cam.wh, 0, 0, cam.gain, gain_on, s.warped.v, st));
+            PROF("warp_fused", img_bytes(src[i]) + img_bytes(s.warped.v),
+                 launch_warp_fused(cam.proj, cam.wt, src[i], cam.ww, cam.wh, 0, 0, cam.gain, gain_on, s.warped.v, st));
             const int dx = cam.tl.x - c->dst_roi.x, dy = cam.tl.y - c->dst_roi.y;
             if (cfg.blender_kind == SB_BLEND_FEATHER)
-                SB_TRY(launch_feather_accumulate(s.warped.v, cam.feather_w.v, s.acc[0].v, none, dx, dy, st));
+                PROF("feather_accumulate", img_bytes(s.warped.v) * (1 + 4.0 / 3 + 2 * 2), 
+                     launch_feather_accumulate(s.warped.v, cam.feather_w.v, s.acc[0].v, none, dx, dy, st));
             else
-                SB_TRY(launch_masked_copy(s.warped.v, cam.mask.v, s.acc[0].v, s.acc_mask.v, dx, dy, st));
+                PROF("masked_copy", img_bytes(s.warped.v) * (1 + 2) + img_bytes(cam.mask.v) * 3,
+                     launch_masked_copy(s.warped.v, cam.mask.v, s.acc[0].v, s.acc_mask.v, dx, dy, st));
         }
         if (cfg.blender_kind == SB_BLEND_FEATHER) {
-            SB_TRY(launch_normalize(c->wsum[0].v, s.acc[0].v, st));
-            SB_TRY(launch_finalize(s.acc[0].v, c->wsum[0].v, nullptr, s.out.v, s.out_mask.v, st));
+            PROF("normalize", img_bytes(s.acc[0].v) * 2 + img_bytes(c->wsum[0].v), launch_normalize(c->wsum[0].v, s.acc[0].v, st));
+            PROF("finalize", img_bytes(s.out.v) * (1 + 6.0 / elem_size(s.out.v.type)) + img_bytes(s.out_mask.v) * 5,
+                 launch_finalize(s.acc[0].v, c->wsum[0].v, nullptr, s.out.v, s.out_mask.v, st));
         } else
-            SB_TRY(launch_finalize(s.acc[0].v, none, &s.acc_mask.v, s.out.v, s.out_mask.v, st));
+            PROF("finalize", img_bytes(s.out.v) * (1 + 6.0 / elem_size(s.out.v.type)) + img_bytes(s.out_mask.v) * 2,
+                 launch_finalize(s.acc[0].v, none, &s.acc_mask.v, s.out.v, s.out_mask.v, st));
     }
     return SB_OK;
 }
@@ -387,6 +424,74 @@ int sb_compositor_compose(sb_compositor *c, const sb_image *srcs, sb_image *pano
     int slot = -1;
     SB_TRY(sb_compositor_enqueue(c, srcs, pano, pano_mask, &slot));
     return sb_compositor_wait(c, slot);
+}
+
+// Device-side timing of a whole region spanning all slots: mark(0) / mark(1) record an event on the
+// setup stream after it has been made to wait for every slot's last enqueued work.
+int sb_compositor_mark(sb_compositor *c, int which)
+{
+    SB_ASSERT(c && (which == 0 || which == 1));
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    if (!c->marks[which]) SB_CUDA(cudaEventCreate(&c->marks[which]));
+    for (auto &s : c->slots) {          // the mark follows everything enqueued so far on every slot
+        cudaEvent_t tail;
+        SB_CUDA(cudaEventCreateWithFlags(&tail, cudaEventDisableTiming));
+        SB_CUDA(cudaEventRecord(tail, s.stream));
+        SB_CUDA(cudaStreamWaitEvent(c->setup_stream, tail, 0));
+        SB_CUDA(cudaEventDestroy(tail));
+    }
+    SB_CUDA(cudaEventRecord(c->marks[which], c->setup_stream));
+    if (which == 0)                     // and nothing enqueued later may start before the start mark
+        for (auto &s : c->slots) SB_CUDA(cudaStreamWaitEvent(s.stream, c->marks[0], 0));
+    return SB_OK;
+}
+
+int sb_compositor_marked_ms(sb_compositor *c, float *ms)
+{
+    SB_ASSERT(c && ms && c->marks[0] && c->marks[1]);
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    SB_CUDA(cudaEventSynchronize(c->marks[1]));
+    SB_CUDA(cudaEventElapsedTime(ms, c->marks[0], c->marks[1]));
+    return SB_OK;
+}
+
+// One frame on slot 0 with every kernel bracketed by CUDA events on the launching stream.
+// Writes a JSON array [{"name":..., "ms":..., "bytes":...}, ...] (one entry per launch) to buf.
+int sb_compositor_profile_frame(sb_compositor *c, const sb_image *srcs, char *buf, size_t cap)
+{
+    SB_ASSERT(c && srcs && buf && cap > 2);
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    Slot &s = c->slots[0];
+    if (s.busy) return fail(SB_ERR_ASSERT, "profile_frame with slot 0 in flight");
+    const int n = c->cfg.n_cameras;
+    std::vector<DImage> src(n);
+    for (int i = 0; i < n; ++i) {
+        SB_ASSERT(srcs[i].type == SB_8UC3 && srcs[i].rows == c->cfg.src_size.height && srcs[i].cols == c->cfg.src_size.width);
+        SB_TRY(to_device(srcs[i], s.src[i], s.stream, &src[i]));
+    }
+    std::vector<ProfRec> recs;
+    s.prof = &recs;
+    int rc = run_frame(c, s, src);
+    s.prof = nullptr;
+    cudaError_t e = cudaStreamSynchronize(s.stream);
+    std::string out = "[";
+    for (size_t i = 0; i < recs.size(); ++i) {
+        float ms = 0.f;
+        if (rc == SB_OK && e == cudaSuccess) cudaEventElapsedTime(&ms, recs[i].e0, recs[i].e1);
+        cudaEventDestroy(recs[i].e0); cudaEventDestroy(recs[i].e1);
+        char item[160];
+        snprintf(item, sizeof item, "%s{\"name\":\"%s\",\"ms\":%.6f,\"bytes\":%.0f}", i ? "," : "", recs[i].name, ms, recs[i].bytes);
+        out += item;
+    }
+    out += "]";
+    SB_TRY(rc);
+    if (e != cudaSuccess) return fail(SB_ERR_CUDA, "profile_frame: %s", cudaGetErrorString(e));
+    if (out.size() + 1 > cap) return fail(SB_ERR_ASSERT, "profile buffer too small (%zu needed)", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return SB_OK;
 }
 
 int sb_compositor_last_gpu_ms(sb_compositor *c, int slot, float *ms)
