@@ -192,6 +192,10 @@ int  sb_compositor_camera_roi(const sb_compositor *c, int index, sb_rect *roi);
 /* One frame set: srcs[n] CV_8UC3 (host or device) -> pano (output_type) + pano_mask (CV_8U, may be NULL).
  * Synchronous. */
 int  sb_compositor_compose(sb_compositor *c, const sb_image *srcs, sb_image *pano, sb_image *pano_mask);
+/* fused != 0 (default): panorama-centric fused kernels (one pass per band / per frame);
+ * fused == 0: the staged, camera-by-camera path shaped like the reference's feed/blend calls.
+ * Both give identical results; the staged path is kept as a cross-check. */
+int  sb_compositor_set_fused(sb_compositor *c, int fused);
 /* Pipelined form for throughput: up to `depth` frame sets in flight, each on its own stream/slot.
  * enqueue returns a slot id; wait blocks until that slot's pano has landed in the buffers given
  * to enqueue. */

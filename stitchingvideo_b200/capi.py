@@ -110,6 +110,7 @@ API = {
     "sb_compositor_camera_roi": (C.c_int, [C.c_void_p, C.c_int, _P(SbRect)]),
     "sb_compositor_compose": (C.c_int, [C.c_void_p, _P(SbImage), _P(SbImage), _P(SbImage)]),
     "sb_compositor_set_depth": (C.c_int, [C.c_void_p, C.c_int]),
+    "sb_compositor_set_fused": (C.c_int, [C.c_void_p, C.c_int]),
     "sb_compositor_enqueue": (C.c_int, [C.c_void_p, _P(SbImage), _P(SbImage), _P(SbImage), _P(C.c_int)]),
     "sb_compositor_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "sb_compositor_last_gpu_ms": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_float)]),
@@ -563,6 +564,9 @@ class Compositor:
             im, k1 = _image(pano_mask)
         _check(lib().sb_compositor_compose(self._h, arr, C.byref(ip), C.byref(im) if im is not None else None))
         return pano, pano_mask
+
+    def set_fused(self, fused):
+        _check(lib().sb_compositor_set_fused(self._h, 1 if fused else 0))
 
     def set_depth(self, depth):
         _check(lib().sb_compositor_set_depth(self._h, depth))

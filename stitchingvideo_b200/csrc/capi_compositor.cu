@@ -10,9 +10,11 @@
 //   weight pyramids per camera, per-level weight sums (dst_band_weights_), feather weight maps.
 // compose() then launches only the image-dependent kernels.
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <string>
 
+#include "sb_fused.h"
 #include "sb_host_projector.h"
 #include "sb_kernels.h"
 
@@ -32,6 +34,8 @@ struct Camera {
     int rx = 0, ry = 0, rw = 0, rh = 0, top = 0, left = 0;
     std::vector<DevImage> w_pyr; // weight pyramid (sequence-constant)
     DevImage feather_w;          // feather weight map (sequence-constant)
+    // panorama(-level) column ranges that hold non-zero weights, per level: [s0,s1) U [s2,s3)
+    std::vector<std::array<int, 4>> spans;
 };
 
 // per-kernel record of one profiled frame (bench.py's roofline): CUDA events on the launching stream
@@ -67,6 +71,7 @@ struct sb_compositor {
     int next_slot = 0;
     cudaStream_t setup_stream = nullptr;
     cudaEvent_t marks[2] = {nullptr, nullptr};
+    bool fused = true;                           // panorama-centric fused kernels (default); false = staged reference-shaped path
 };
 
 namespace {
@@ -109,6 +114,35 @@ void free_slot(Slot &s)
     if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.ev_stop) cudaEventDestroy(s.ev_stop);
     s.stream = nullptr; s.ev_start = s.ev_stop = nullptr;
+}
+
+// Column ranges of a weight image that hold any non-zero weight, shifted by `offset` into
+// panorama(-level) coordinates.  A seam-straddling camera has two runs (both panorama ends).
+int weight_spans(const DImage &w, int offset, DevBuf &scratch, cudaStream_t s, std::array<int, 4> *out)
+{
+    SB_TRY(scratch.ensure(sizeof(int) * (size_t)w.cols));
+    SB_TRY(launch_column_nonzero(w, static_cast<int *>(scratch.p), s));
+    std::vector<int> flags(w.cols);
+    SB_CUDA(cudaMemcpyAsync(flags.data(), scratch.p, sizeof(int) * (size_t)w.cols, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    std::vector<std::pair<int, int>> runs;
+    for (int x = 0; x < w.cols;) {
+        if (!flags[x]) { ++x; continue; }
+        int e = x;
+        while (e < w.cols && flags[e]) ++e;
+        runs.push_back({x, e});
+        x = e;
+    }
+    *out = {0, 0, 0, 0};
+    if (runs.empty()) return SB_OK;
+    if (runs.size() == 1) { *out = {runs[0].first + offset, runs[0].second + offset, 0, 0}; return SB_OK; }
+    // more than two runs: keep the widest gap as the hole between the two spans
+    size_t gap_at = 0;
+    int gap = -1;
+    for (size_t i = 0; i + 1 < runs.size(); ++i)
+        if (runs[i + 1].first - runs[i].second > gap) { gap = runs[i + 1].first - runs[i].second; gap_at = i; }
+    *out = {runs.front().first + offset, runs[gap_at].second + offset, runs[gap_at + 1].first + offset, runs.back().second + offset};
+    return SB_OK;
 }
 
 // calibration-time work: geometry, tables, masks, weights
@@ -179,6 +213,7 @@ int setup(sb_compositor *c)
             rows = (rows + 1) / 2; cols = (cols + 1) / 2;
         }
         const int rbr_x = roi.x + roi.width, rbr_y = roi.y + roi.height;
+        DevBuf span_scratch;
         for (int i = 0; i < n; ++i) {
             Camera &cam = c->cams[i];
             // MultiBandBlender::feed geometry (blenders.cpp:241-269)
@@ -207,6 +242,8 @@ int setup(sb_compositor *c)
                     SB_TRY(launch_pyr_down(p, cam.w_pyr[l].v, s));
                 }
                 SB_TRY(launch_weight_accumulate(cam.w_pyr[l].v, c->wsum[l].v, x_tl, y_tl, s));
+                cam.spans.emplace_back();
+                SB_TRY(weight_spans(cam.w_pyr[l].v, x_tl, span_scratch, s, &cam.spans.back()));
                 x_tl /= 2; y_tl /= 2;
             }
         }
@@ -220,6 +257,8 @@ int setup(sb_compositor *c)
             SB_TRY(launch_distance_l1(cam.mask.v, cam.feather_w.v, scratch, s));
             SB_TRY(launch_weight_from_dist(cam.feather_w.v, cfg.sharpness, s));
             SB_TRY(launch_weight_accumulate(cam.feather_w.v, c->wsum[0].v, cam.tl.x - roi.x, cam.tl.y - roi.y, s));
+            cam.spans.emplace_back();
+            SB_TRY(weight_spans(cam.feather_w.v, cam.tl.x - roi.x, scratch, s, &cam.spans.back()));
         }
         SB_CUDA(cudaStreamSynchronize(s));
     }
@@ -248,9 +287,77 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
     const bool gain_on = cfg.comp_kind == SB_COMP_GAIN;
     cudaStream_t st = s.stream;
     DImage none;
-    // Blender::prepare: zero the accumulators (blenders.cpp:71-78, 227-232); weight sums are resident
-    for (auto &a : s.acc) PROF("zero_fill", img_bytes(a.v), launch_set_zero(a.v, st));
-    if (cfg.blender_kind == SB_BLEND_MULTI_BAND) {
+    // Blender::prepare zeroes the accumulators (blenders.cpp:71-78, 227-232): only the unfused
+    // (camera-by-camera) path has accumulators in HBM; the weight sums are resident either way
+    if (cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused) {
+        const int nb = c->num_bands;
+        for (int i = 0; i < n; ++i) {
+            const Camera &cam = c->cams[i];
+            auto &g = s.gpyr[i];
+            PROF("warp_fused", img_bytes(src[i]) + img_bytes(g[0].v),
+                 launch_warp_fused(cam.proj, cam.wt, src[i], cam.ww, cam.wh, cam.left, cam.top, cam.gain, gain_on, g[0].v, st));
+            for (int l = 0; l < nb; ++l)
+                PROF("pyr_down", img_bytes(g[l].v) + img_bytes(g[l + 1].v), launch_pyr_down(g[l].v, g[l + 1].v, st));
+        }
+        // bands coarse -> fine: Laplacian on the fly, weighted sum over cameras, normalise, collapse add
+        for (int l = nb; l >= 0; --l) {
+            BandFusedArgs a{};
+            a.n = n;
+            double bytes = 0;
+            for (int i = 0; i < n; ++i) {
+                const Camera &cam = c->cams[i];
+                BandCam &bc = a.cam[i];
+                const DImage &f = s.gpyr[i][l].v;
+                bc.fine = f.ptr<short>(); bc.fstep = f.step;
+                if (l < nb) { bc.coarse = s.gpyr[i][l + 1].v.ptr<short>(); bc.cstep = s.gpyr[i][l + 1].v.step; }
+                bc.weight = cam.w_pyr[l].v.data; bc.wstep = cam.w_pyr[l].v.step;
+                bc.rx = cam.rx >> l; bc.ry = cam.ry >> l; bc.rw = f.cols; bc.rh = f.rows;
+                for (int k = 0; k < 4; ++k) bc.span[k] = cam.spans[l][k];
+                // only the columns inside the spans are touched: fine + coarse/4 + weights
+                const double frac = std::min(1.0, (double)((bc.span[1] - bc.span[0]) + (bc.span[3] - bc.span[2])) / std::max(1, f.cols));
+                bytes += frac * (img_bytes(f) * (l < nb ? 1.25 : 1.0) + img_bytes(cam.w_pyr[l].v));
+            }
+            const DImage &ws = c->wsum[l].v;
+            a.wsum = ws.data; a.wsum_step = ws.step;
+            if (l < nb) { a.coarse_r = s.acc[l + 1].v.ptr<short>(); a.coarse_r_step = s.acc[l + 1].v.step; bytes += img_bytes(s.acc[l + 1].v); }
+            a.lw = s.acc[l].v.cols; a.lh = s.acc[l].v.rows;
+            const bool fin = l == 0;
+            if (fin) {
+                a.out = s.out.v.data; a.out_step = s.out.v.step; a.out_mask = s.out_mask.v.ptr<uint8_t>(); a.mask_step = s.out_mask.v.step;
+                a.out_w = s.out.v.cols; a.out_h = s.out.v.rows;
+                bytes += img_bytes(s.out.v) + img_bytes(s.out_mask.v) + (double)a.out_w * a.out_h * elem_size(ws.type);
+            } else {
+                a.out = s.acc[l].v.data; a.out_step = s.acc[l].v.step;
+                bytes += img_bytes(s.acc[l].v) + img_bytes(ws);
+            }
+            PROF(fin ? "band_fused_final" : "band_fused", bytes,
+                 launch_band_fused(a, cfg.weight_type == SB_32F, l < nb, fin, s.out.v.type == SB_8UC3, st));
+        }
+    } else if (cfg.blender_kind == SB_BLEND_FEATHER && c->fused) {
+        FeatherFusedArgs a{};
+        a.n = n;
+        double bytes = 0;
+        for (int i = 0; i < n; ++i) {
+            const Camera &cam = c->cams[i];
+            FusedCam &fc = a.cam[i];
+            for (int k = 0; k < 9; ++k) fc.k_rinv[k] = cam.proj.k_rinv[k];
+            fc.one_minus_t2 = 1.f - cam.proj.t[2];
+            fc.col_sin = cam.wt.col_sin; fc.col_cos = cam.wt.col_cos; fc.row_a = cam.wt.row_a; fc.row_b = cam.wt.row_b;
+            fc.src = src[i].ptr<uint8_t>(); fc.sstep = src[i].step; fc.sw = src[i].cols; fc.sh = src[i].rows;
+            fc.ww = cam.ww; fc.wh = cam.wh; fc.dx = cam.tl.x - c->dst_roi.x; fc.dy = cam.tl.y - c->dst_roi.y;
+            fc.gain = cam.gain; fc.apply_gain = gain_on ? 1 : 0;
+            fc.weight = cam.feather_w.v.ptr<float>(); fc.wstep = cam.feather_w.v.step;
+            for (int k = 0; k < 4; ++k) fc.span[k] = cam.spans[0][k];
+            const double frac = std::min(1.0, (double)((fc.span[1] - fc.span[0]) + (fc.span[3] - fc.span[2])) / std::max(1, cam.ww));
+            bytes += img_bytes(src[i]) + frac * img_bytes(cam.feather_w.v);     // source gathered ~once, weights inside the spans
+        }
+        a.wsum = c->wsum[0].v.ptr<float>(); a.wsum_step = c->wsum[0].v.step;
+        a.out = s.out.v.data; a.out_step = s.out.v.step; a.out_mask = s.out_mask.v.ptr<uint8_t>(); a.mask_step = s.out_mask.v.step;
+        a.pw = s.out.v.cols; a.ph = s.out.v.rows;
+        bytes += img_bytes(c->wsum[0].v) + img_bytes(s.out.v) + img_bytes(s.out_mask.v);
+        PROF("feather_fused", bytes, launch_feather_fused(a, cfg.warper_kind, s.out.v.type == SB_8UC3, st));
+    } else if (cfg.blender_kind == SB_BLEND_MULTI_BAND) {
+        for (auto &acc : s.acc) PROF("zero_fill", img_bytes(acc.v), launch_set_zero(acc.v, st));
         const int nb = c->num_bands;
         for (int i = 0; i < n; ++i) {
             const Camera &cam = c->cams[i];
@@ -276,6 +383,7 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
         PROF("finalize", img_bytes(s.out.v) * (1 + 6.0 / elem_size(s.out.v.type)) + img_bytes(s.out_mask.v) * (1 + elem_size(c->wsum[0].v.type)),
              launch_finalize(s.acc[0].v, c->wsum[0].v, nullptr, s.out.v, s.out_mask.v, st));
     } else {
+        PROF("zero_fill", img_bytes(s.acc[0].v), launch_set_zero(s.acc[0].v, st));
         if (cfg.blender_kind == SB_BLEND_NO) PROF("zero_fill", img_bytes(s.acc_mask.v), launch_set_zero(s.acc_mask.v, st));
         for (int i = 0; i < n; ++i) {
             const Camera &cam = c->cams[i];
@@ -320,6 +428,7 @@ int sb_compositor_create(const sb_compositor_config *cfg, int device, sb_composi
     if (cfg->blender_kind == SB_BLEND_MULTI_BAND) SB_ASSERT(cfg->weight_type == SB_32F || cfg->weight_type == SB_16S);
     SB_ASSERT(cfg->output_type == SB_8UC3 || cfg->output_type == SB_16SC3);
     SB_ASSERT(cfg->comp_kind != SB_COMP_GAIN || cfg->gains);
+    SB_ASSERT(cfg->n_cameras <= SB_MAX_CAMERAS);
     DeviceGuard g(device);
     if (!g.ok) return SB_ERR_CUDA;
     sb_compositor *c = new sb_compositor;
@@ -360,6 +469,13 @@ int sb_compositor_camera_roi(const sb_compositor *c, int index, sb_rect *roi)
     SB_ASSERT(c && roi && index >= 0 && index < (int)c->cams.size());
     const Camera &cam = c->cams[index];
     roi->x = cam.tl.x; roi->y = cam.tl.y; roi->width = cam.ww; roi->height = cam.wh;
+    return SB_OK;
+}
+
+int sb_compositor_set_fused(sb_compositor *c, int fused)
+{
+    SB_ASSERT(c);
+    c->fused = fused != 0;
     return SB_OK;
 }
 

@@ -270,11 +270,13 @@ def _compositor_case(gpu, rig, blender, weight_type=O.CV_32F, seams=False, gains
         assert (roi[0], roi[1]) == cal.corners[i] and (roi[2], roi[3]) == cal.sizes[i]
     for fi in range(2):                       # two frames through the same handle (tables stay resident)
         frames = [rigs.frame(rig, fi, i) for i in range(n)]
-        pano, mask = comp.compose(frames)
         ref, rmask = P.compose(cal, frames, blender=blender, num_bands=num_bands, weight_type=weight_type, gains=g,
                                output_8u=not out16)
-        assert_same(pano, ref, "%s/%s pano frame %d" % (rig, blender, fi))
-        assert_same(mask, rmask, "%s/%s mask frame %d" % (rig, blender, fi))
+        for fused in (True, False):           # panorama-centric fused kernels, then the staged feed/blend-shaped path
+            comp.set_fused(fused)
+            pano, mask = comp.compose(frames)
+            assert_same(pano, ref, "%s/%s pano frame %d fused=%s" % (rig, blender, fi, fused))
+            assert_same(mask, rmask, "%s/%s mask frame %d fused=%s" % (rig, blender, fi, fused))
 
 
 @pytest.mark.parametrize("case", [
