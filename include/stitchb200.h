@@ -58,6 +58,9 @@ const char *sb_version(void);
 /* number of kernels this library has launched since load (all handles); bench.py's gpu_launches */
 uint64_t sb_kernel_launch_count(void);
 int sb_device_count(void);
+/* Device self-test: the shared-divisor IEEE division used inside the fused kernels against
+ * div.rn.f32 on n pseudo-random operand pairs; *mismatches must come back 0. */
+int sb_selftest_division(int device, unsigned long long n, unsigned seed, unsigned long long *mismatches);
 /* page-locked host memory for the pipelined compositor path (host<->device copies overlap compute) */
 int  sb_host_alloc(void **ptr, size_t bytes);
 void sb_host_free(void *ptr);

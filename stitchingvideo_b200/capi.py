@@ -69,6 +69,7 @@ API = {
     "sb_version": (C.c_char_p, []),
     "sb_kernel_launch_count": (C.c_uint64, []),
     "sb_device_count": (C.c_int, []),
+    "sb_selftest_division": (C.c_int, [C.c_int, C.c_ulonglong, C.c_uint, _P(C.c_ulonglong)]),
     "sb_host_alloc": (C.c_int, [_P(C.c_void_p), C.c_size_t]),
     "sb_host_free": (None, [C.c_void_p]),
     "sb_warper_create": (C.c_int, [C.c_int, C.c_float, C.c_int, _P(C.c_void_p)]),
@@ -208,6 +209,12 @@ def _fp(a):
 
 def kernel_launch_count():
     return int(lib().sb_kernel_launch_count())
+
+
+def selftest_division(n=1 << 26, seed=1, device=0):
+    bad = C.c_ulonglong(0)
+    _check(lib().sb_selftest_division(device, n, seed, C.byref(bad)))
+    return int(bad.value)
 
 
 def device_count():

@@ -1,5 +1,6 @@
 // capi_common.cu — error state, device buffers, host<->device staging shared by the C ABI.
 #include "sb_internal.h"
+#include "sb_fused.h"
 
 namespace sb {
 
@@ -122,6 +123,13 @@ int sb_host_alloc(void **ptr, size_t bytes)
     return SB_OK;
 }
 void sb_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
+int sb_selftest_division(int device, unsigned long long n, unsigned seed, unsigned long long *mismatches)
+{
+    if (!mismatches) return sb::fail(SB_ERR_ASSERT, "mismatches is null");
+    sb::DeviceGuard g(device);
+    if (!g.ok) return SB_ERR_CUDA;
+    return sb::selftest_division(n, seed, mismatches);
+}
 int sb_device_count(void)
 {
     int n = 0;

@@ -34,6 +34,8 @@ struct Camera {
     int rx = 0, ry = 0, rw = 0, rh = 0, top = 0, left = 0;
     std::vector<DevImage> w_pyr; // weight pyramid (sequence-constant)
     DevImage feather_w;          // feather weight map (sequence-constant)
+    DevBuf feather_table;        // fixed-point map + distance, 8 B per warped pixel (sequence-constant)
+    size_t feather_tstep = 0;
     // panorama(-level) column ranges that hold non-zero weights, per level: [s0,s1) U [s2,s3)
     std::vector<std::array<int, 4>> spans;
 };
@@ -50,6 +52,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool busy = false;
+    bool want_mask = true;                       // the caller asked for dst_mask (else it is never materialised)
     std::vector<DevImage> src;                   // staged source frames (host input)
     std::vector<std::vector<DevImage>> gpyr;     // per camera Gaussian pyramid of the padded warped image
     DevImage warped;                             // feather / no-blend: one warped image at a time
@@ -71,6 +74,7 @@ struct sb_compositor {
     int next_slot = 0;
     cudaStream_t setup_stream = nullptr;
     cudaEvent_t marks[2] = {nullptr, nullptr};
+    DevBuf tile_cams;                            // feather: camera bitmask per panorama column block
     bool fused = true;                           // panorama-centric fused kernels (default); false = staged reference-shaped path
 };
 
@@ -255,11 +259,25 @@ int setup(sb_compositor *c)
             Camera &cam = c->cams[i];
             SB_TRY(cam.feather_w.create(cam.wh, cam.ww, SB_32FC1));
             SB_TRY(launch_distance_l1(cam.mask.v, cam.feather_w.v, scratch, s));
+            cam.feather_tstep = ((size_t)cam.ww * sizeof(uint2) + 255) & ~(size_t)255;
+            SB_TRY(cam.feather_table.ensure(cam.feather_tstep * cam.wh));
+            SB_TRY(launch_build_feather_table(cam.proj, cam.tl.x, cam.tl.y, cam.feather_w.v, static_cast<uint2 *>(cam.feather_table.p), cam.feather_tstep, s));
             SB_TRY(launch_weight_from_dist(cam.feather_w.v, cfg.sharpness, s));
             SB_TRY(launch_weight_accumulate(cam.feather_w.v, c->wsum[0].v, cam.tl.x - roi.x, cam.tl.y - roi.y, s));
             cam.spans.emplace_back();
             SB_TRY(weight_spans(cam.feather_w.v, cam.tl.x - roi.x, scratch, s, &cam.spans.back()));
         }
+        // per 128-pixel panorama column block: which cameras can contribute there
+        const int tiles = div_up(roi.width, SB_FEATHER_TILE_W);
+        std::vector<uint32_t> tc(tiles, 0u);
+        for (int t = 0; t < tiles; ++t)
+            for (int i = 0; i < n; ++i) {
+                const auto &sp = c->cams[i].spans[0];
+                const int x0 = t * SB_FEATHER_TILE_W, x1 = x0 + SB_FEATHER_TILE_W;
+                if ((x0 < sp[1] && x1 > sp[0]) || (x0 < sp[3] && x1 > sp[2])) tc[t] |= 1u << i;
+            }
+        SB_TRY(c->tile_cams.ensure(sizeof(uint32_t) * tiles));
+        SB_CUDA(cudaMemcpyAsync(c->tile_cams.p, tc.data(), sizeof(uint32_t) * tiles, cudaMemcpyHostToDevice, s));
         SB_CUDA(cudaStreamSynchronize(s));
     }
     SB_CUDA(cudaStreamSynchronize(s));
@@ -323,9 +341,10 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
             a.lw = s.acc[l].v.cols; a.lh = s.acc[l].v.rows;
             const bool fin = l == 0;
             if (fin) {
-                a.out = s.out.v.data; a.out_step = s.out.v.step; a.out_mask = s.out_mask.v.ptr<uint8_t>(); a.mask_step = s.out_mask.v.step;
+                a.out = s.out.v.data; a.out_step = s.out.v.step;
+                a.out_mask = s.want_mask ? s.out_mask.v.ptr<uint8_t>() : nullptr; a.mask_step = s.out_mask.v.step;
                 a.out_w = s.out.v.cols; a.out_h = s.out.v.rows;
-                bytes += img_bytes(s.out.v) + img_bytes(s.out_mask.v) + (double)a.out_w * a.out_h * elem_size(ws.type);
+                bytes += img_bytes(s.out.v) + (s.want_mask ? img_bytes(s.out_mask.v) : 0) + (double)a.out_w * a.out_h * elem_size(ws.type);
             } else {
                 a.out = s.acc[l].v.data; a.out_step = s.acc[l].v.step;
                 bytes += img_bytes(s.acc[l].v) + img_bytes(ws);
@@ -333,29 +352,28 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
             PROF(fin ? "band_fused_final" : "band_fused", bytes,
                  launch_band_fused(a, cfg.weight_type == SB_32F, l < nb, fin, s.out.v.type == SB_8UC3, st));
         }
-    } else if (cfg.blender_kind == SB_BLEND_FEATHER && c->fused) {
+    } else if (cfg.blender_kind == SB_BLEND_FEATHER && c->fused && cfg.sharpness > 0.f) {
         FeatherFusedArgs a{};
         a.n = n;
         double bytes = 0;
         for (int i = 0; i < n; ++i) {
             const Camera &cam = c->cams[i];
-            FusedCam &fc = a.cam[i];
-            for (int k = 0; k < 9; ++k) fc.k_rinv[k] = cam.proj.k_rinv[k];
-            fc.one_minus_t2 = 1.f - cam.proj.t[2];
-            fc.col_sin = cam.wt.col_sin; fc.col_cos = cam.wt.col_cos; fc.row_a = cam.wt.row_a; fc.row_b = cam.wt.row_b;
+            FeatherCam &fc = a.cam[i];
             fc.src = src[i].ptr<uint8_t>(); fc.sstep = src[i].step; fc.sw = src[i].cols; fc.sh = src[i].rows;
+            fc.table = static_cast<const uint2 *>(cam.feather_table.p); fc.tstep = cam.feather_tstep;
             fc.ww = cam.ww; fc.wh = cam.wh; fc.dx = cam.tl.x - c->dst_roi.x; fc.dy = cam.tl.y - c->dst_roi.y;
-            fc.gain = cam.gain; fc.apply_gain = gain_on ? 1 : 0;
-            fc.weight = cam.feather_w.v.ptr<float>(); fc.wstep = cam.feather_w.v.step;
-            for (int k = 0; k < 4; ++k) fc.span[k] = cam.spans[0][k];
-            const double frac = std::min(1.0, (double)((fc.span[1] - fc.span[0]) + (fc.span[3] - fc.span[2])) / std::max(1, cam.ww));
-            bytes += img_bytes(src[i]) + frac * img_bytes(cam.feather_w.v);     // source gathered ~once, weights inside the spans
+            fc.gain = cam.gain;
+            const auto &sp = cam.spans[0];
+            // source gathered ~once; table entries (8 B) read inside the non-zero-weight column spans
+            bytes += img_bytes(src[i]) + 8.0 * cam.wh * ((sp[1] - sp[0]) + (sp[3] - sp[2]));
         }
-        a.wsum = c->wsum[0].v.ptr<float>(); a.wsum_step = c->wsum[0].v.step;
-        a.out = s.out.v.data; a.out_step = s.out.v.step; a.out_mask = s.out_mask.v.ptr<uint8_t>(); a.mask_step = s.out_mask.v.step;
+        a.tile_cams = static_cast<const uint32_t *>(c->tile_cams.p);
+        a.sharpness = cfg.sharpness;
+        a.out = s.out.v.data; a.out_step = s.out.v.step;
+        a.out_mask = s.want_mask ? s.out_mask.v.ptr<uint8_t>() : nullptr; a.mask_step = s.out_mask.v.step;
         a.pw = s.out.v.cols; a.ph = s.out.v.rows;
-        bytes += img_bytes(c->wsum[0].v) + img_bytes(s.out.v) + img_bytes(s.out_mask.v);
-        PROF("feather_fused", bytes, launch_feather_fused(a, cfg.warper_kind, s.out.v.type == SB_8UC3, st));
+        bytes += img_bytes(s.out.v) + (s.want_mask ? img_bytes(s.out_mask.v) : 0);
+        PROF("feather_fused", bytes, launch_feather_fused(a, gain_on, s.out.v.type == SB_8UC3, st));
     } else if (cfg.blender_kind == SB_BLEND_MULTI_BAND) {
         for (auto &acc : s.acc) PROF("zero_fill", img_bytes(acc.v), launch_set_zero(acc.v, st));
         const int nb = c->num_bands;
@@ -509,6 +527,7 @@ int sb_compositor_enqueue(sb_compositor *c, const sb_image *srcs, sb_image *pano
         SB_ASSERT(srcs[i].type == SB_8UC3 && srcs[i].rows == c->cfg.src_size.height && srcs[i].cols == c->cfg.src_size.width);
         SB_TRY(to_device(srcs[i], s.src[i], s.stream, &src[i]));
     }
+    s.want_mask = pano_mask != nullptr;
     SB_TRY(run_frame(c, s, src));
     if (!pano->data) lend(s.out.v, c->device, pano);
     else SB_TRY(from_device(s.out.v, pano, s.stream));
@@ -590,6 +609,7 @@ int sb_compositor_profile_frame(sb_compositor *c, const sb_image *srcs, char *bu
     }
     std::vector<ProfRec> recs;
     s.prof = &recs;
+    s.want_mask = false;
     int rc = run_frame(c, s, src);
     s.prof = nullptr;
     cudaError_t e = cudaStreamSynchronize(s.stream);

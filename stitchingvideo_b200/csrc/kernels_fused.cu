@@ -8,8 +8,9 @@
 // (normalise -> [collapse add] -> mask -> convertTo(8U)) in registers.  No accumulator ever exists
 // in HBM: no zero-fill, no read-modify-write, no separate normalise / crop passes.
 //
-//   k_feather_fused : warp (maps on the fly from separable tables) + gain + convertTo(16S) +
-//                     FeatherBlender::feed over all cameras + blend + convertTo(8U)  — ONE launch per frame.
+//   k_feather_fused : remap (pre-quantised fixed-point map table, 8 B/px incl. the feather distance)
+//                     + gain + convertTo(16S) + FeatherBlender::feed over all cameras + blend +
+//                     convertTo(8U)  — ONE launch per frame.
 //   k_band_fused    : one Laplacian band of MultiBandBlender for all cameras: Laplacian formed on
 //                     the fly from the cameras' Gaussian levels, weighted sum, normalise, collapse
 //                     add of the coarser restored band, and at band 0 crop + mask + convertTo(8U).
@@ -19,6 +20,7 @@
 #include "sb_device.cuh"
 #include "sb_fused.h"
 #include "sb_pyr.cuh"
+#include "sb_warp.cuh"
 
 namespace sb {
 using namespace sbd;
@@ -30,98 +32,100 @@ __device__ __forceinline__ bool in_spans(const int span[4], int x0, int x1)   //
     return (x0 < span[1] && x1 > span[0]) || (x0 < span[3] && x1 > span[2]);
 }
 
-// mapBackward with the trig factored into per-column / per-row tables (bit-identical to the per-pixel
-// sinf/cosf form: the table entries ARE those sinf/cosf values) followed by the fixed-point bilinear
-// sample of cv::remap with BORDER_REFLECT.  Weights: every table entry carries the factor 32, so
-// (sum w*p + 2^14) >> 15 == (v + 512) >> 10 with v = sum of the 5-bit products; the (0,0) entry
-// {32767,0,0,1} of OpenCV's table equals an exact copy for 8-bit data, as does {32768,0,0,0}.
+// ------------------------------------------------------------------------------------ feather
+// setup: one table entry per warped pixel = what cv::remap's map conversion would compute every
+// frame (sx, sy, fx, fy; Appendix A1) + the L1 distance behind the feather weight.
 template <int KIND>
-__device__ __forceinline__ void warp_sample(const FusedCam &c, int wx, int wy, int out[3])
+__global__ void __launch_bounds__(256)
+k_build_feather_table(ProjParams p, int tl_x, int tl_y, const float *dist, size_t dstep, int w, int h, uint2 *table, size_t tstep)
 {
-    const float cs = __ldg(c.col_sin + wx), cc = __ldg(c.col_cos + wx), ra = __ldg(c.row_a + wy);
-    float x_, y_, z_;
-    if (KIND == SB_WARP_SPHERICAL) {
-        const float rb = __ldg(c.row_b + wy);
-        x_ = __fmul_rn(ra, cs); y_ = rb; z_ = __fmul_rn(ra, cc);
-    } else if (KIND == SB_WARP_CYLINDRICAL) {
-        x_ = cs; y_ = ra; z_ = cc;
-    } else {
-        x_ = cs; y_ = ra; z_ = c.one_minus_t2;
-    }
-    const float *m = c.k_rinv;
-    float x = __fadd_rn(__fadd_rn(__fmul_rn(m[0], x_), __fmul_rn(m[1], y_)), __fmul_rn(m[2], z_));
-    float y = __fadd_rn(__fadd_rn(__fmul_rn(m[3], x_), __fmul_rn(m[4], y_)), __fmul_rn(m[5], z_));
-    float z = __fadd_rn(__fadd_rn(__fmul_rn(m[6], x_), __fmul_rn(m[7], y_)), __fmul_rn(m[8], z_));
-    if (KIND == SB_WARP_PLANE || z > 0) {
-        x = __fdiv_rn(x, z);
-        y = __fdiv_rn(y, z);
-    } else
-        x = y = -1.f;
-    const int fsx = cvround(__fmul_rn(x, 32.f)), fsy = cvround(__fmul_rn(y, 32.f));
-    const int fx = fsx & 31, fy = fsy & 31;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    float mx, my;
+    map_backward<KIND>(p, (float)(tl_x + x), (float)(tl_y + y), mx, my);
+    const int fsx = cvround(__fmul_rn(mx, 32.f)), fsy = cvround(__fmul_rn(my, 32.f));
     const int sx = sat_s16(fsx >> 5), sy = sat_s16(fsy >> 5);
-    int x0 = sx, x1 = sx + 1, y0 = sy, y1 = sy + 1;
-    if (!((unsigned)sx < (unsigned)(c.sw - 1) && (unsigned)sy < (unsigned)(c.sh - 1))) {
-        x0 = border_interp<BORDER_REFLECT>(x0, c.sw); x1 = border_interp<BORDER_REFLECT>(x1, c.sw);
-        y0 = border_interp<BORDER_REFLECT>(y0, c.sh); y1 = border_interp<BORDER_REFLECT>(y1, c.sh);
-    }
-    const uint8_t *r0 = c.src + (size_t)y0 * c.sstep, *r1 = c.src + (size_t)y1 * c.sstep;
-    const uint8_t *p00 = r0 + x0 * 3, *p01 = r0 + x1 * 3, *p10 = r1 + x0 * 3, *p11 = r1 + x1 * 3;
-    const int ax = 32 - fx, ay = 32 - fy;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        int h0 = (int)__ldg(p00 + k) * ax + (int)__ldg(p01 + k) * fx;
-        int h1 = (int)__ldg(p10 + k) * ax + (int)__ldg(p11 + k) * fx;
-        int v = (h0 * ay + h1 * fy + 512) >> 10;          // <= 255: FixedPtCast never saturates here
-        if (c.apply_gain) v = sat_u8_f(__fmul_rn((float)v, c.gain));
-        out[k] = v;
-    }
+    const float d = crow<float>(dist, dstep, y)[x];
+    const unsigned di = d >= 65535.f ? 65535u : (unsigned)d;       // exact integers below the 8192 saturation
+    uint2 t;
+    t.x = ((unsigned)sx & 0xffffu) | ((unsigned)sy << 16);
+    t.y = (unsigned)(fsx & 31) | ((unsigned)(fsy & 31) << 5) | (di << 16);
+    reinterpret_cast<uint2 *>(reinterpret_cast<char *>(table) + (size_t)y * tstep)[x] = t;
 }
 
-// ------------------------------------------------------------------------------------ feather
-template <int KIND, bool OUT8>
+int launch_build_feather_table(const ProjParams &p, int tl_x, int tl_y, const DImage &dist, uint2 *table, size_t tstep, cudaStream_t s)
+{
+    SB_ASSERT(dist.type == SB_32FC1);
+    dim3 block(32, 8), grid(div_up(dist.cols, 32), div_up(dist.rows, 8));
+#define SB_FT(K) k_build_feather_table<K><<<grid, block, 0, s>>>(p, tl_x, tl_y, dist.ptr<float>(), dist.step, dist.cols, dist.rows, table, tstep)
+    switch (p.kind) {
+    case SB_WARP_PLANE: SB_FT(SB_WARP_PLANE); break;
+    case SB_WARP_CYLINDRICAL: SB_FT(SB_WARP_CYLINDRICAL); break;
+    case SB_WARP_SPHERICAL: SB_FT(SB_WARP_SPHERICAL); break;
+    default: return fail(SB_ERR_BAD_ARG, "unsupported projector kind %d", p.kind);
+    }
+#undef SB_FT
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
+// One launch per frame.  A non-zero distance implies the pixel lies inside the warped all-255 mask,
+// i.e. its source coordinate rounds into the image: sx in [-1, sw-1], sy in [-1, sh-1], where
+// BORDER_REFLECT coincides with clamping.  Every table weight carries the factor 32, so
+// (sum w*p + 2^14) >> 15 == (v + 512) >> 10 with v the sum of 5-bit products; OpenCV's (0,0) entry
+// {32767,0,0,1} equals an exact copy for 8-bit data, as does {32768,0,0,0}.  With 8-bit sources and
+// weights in [0,1] every intermediate stays inside [0, 255*n]: no saturation or wrap can fire.
+template <bool GAIN, bool OUT8>
 __global__ void __launch_bounds__(128)
 k_feather_fused(const __grid_constant__ FeatherFusedArgs a)
 {
-    const int X0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int Y = blockIdx.y * 4 + threadIdx.y;
     if (X0 >= a.pw || Y >= a.ph) return;
     int acc[4][3];
+    float wsum[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = 0;
+    for (int j = 0; j < 4; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = 0; wsum[j] = 0.f; }
 
-    for (int i = 0; i < a.n; ++i) {
-        const FusedCam &c = a.cam[i];
+    for (uint32_t cams = a.tile_cams[blockIdx.x]; cams; cams &= cams - 1) {   // ascending index = feed order
+        const FeatherCam &c = a.cam[__ffs(cams) - 1];
         const int y = Y - c.dy;
         if ((unsigned)y >= (unsigned)c.wh) continue;
-        if (!in_spans(c.span, X0, X0 + 4)) continue;
-        const float *wrow = reinterpret_cast<const float *>(reinterpret_cast<const char *>(c.weight) + (size_t)y * c.wstep);
+        const uint2 *trow = reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(c.table) + (size_t)y * c.tstep);
+        const int xb = X0 - c.dx;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int x = X0 + j - c.dx;
+            const int x = xb + j;
             if ((unsigned)x >= (unsigned)c.ww) continue;
-            const float w = __ldg(wrow + x);
-            if (w == 0.f) continue;                       // short(p * 0) == 0: exact skip
-            int p[3];
-            warp_sample<KIND>(c, x, y, p);
+            const uint2 t = __ldg(trow + x);
+            const unsigned dist = t.y >> 16;
+            if (dist == 0u) continue;                       // weight 0: short(p * 0) == 0 and dst_w += 0
+            // createWeightMap: threshold(dist * sharpness, 1, THRESH_TRUNC)
+            const float w = fminf(__fmul_rn((float)dist, a.sharpness), 1.f);
+            wsum[j] = __fadd_rn(wsum[j], w);
+            const int sx = (short)(t.x & 0xffffu), sy = (int)t.x >> 16;
+            const int fx = t.y & 31, fy = (t.y >> 5) & 31, ax = 32 - fx, ay = 32 - fy;
+            const int x0 = max(sx, 0), x1 = min(sx + 1, c.sw - 1), y0 = max(sy, 0), y1 = min(sy + 1, c.sh - 1);
+            const uint8_t *r0 = c.src + (size_t)y0 * c.sstep, *r1 = c.src + (size_t)y1 * c.sstep;
+            const uint8_t *p00 = r0 + x0 * 3, *p01 = r0 + x1 * 3, *p10 = r1 + x0 * 3, *p11 = r1 + x1 * 3;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) acc[j][k] += (int)trunc_short(__fmul_rn((float)p[k], w));
+            for (int k = 0; k < 3; ++k) {
+                const int h0 = (int)__ldg(p00 + k) * ax + (int)__ldg(p01 + k) * fx;
+                const int h1 = (int)__ldg(p10 + k) * ax + (int)__ldg(p11 + k) * fx;
+                int v = (h0 * ay + h1 * fy + 512) >> 10;
+                if (GAIN) v = min(max(__float2int_rn(__fmul_rn((float)v, c.gain)), 0), 255);   // saturate_cast<uchar>
+                acc[j][k] += __float2int_rz(__fmul_rn((float)v, w));                      // static_cast<short>(src * w)
+            }
         }
     }
     // FeatherBlender::blend: normalizeUsingWeightMap, mask = weight > eps, zero unmasked, convertTo(8U)
-    const float *ws = reinterpret_cast<const float *>(reinterpret_cast<const char *>(a.wsum) + (size_t)Y * a.wsum_step) + X0;
     int o[4][3], m[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float w = (X0 + j < a.pw) ? ws[j] : 0.f;
-        m[j] = w > SB_WEIGHT_EPS ? 255 : 0;
-        const float d = __fadd_rn(w, SB_WEIGHT_EPS);
+        m[j] = wsum[j] > SB_WEIGHT_EPS ? 255 : 0;
+        const SharedDiv div(__fadd_rn(wsum[j], SB_WEIGHT_EPS));        // in [1e-5, n + 1e-5]: fast-path range
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            int v = trunc_short(__fdiv_rn((float)(short)acc[j][k], d));
-            v = m[j] ? v : 0;
-            o[j][k] = OUT8 ? sat_u8(v) : v;
-        }
+        for (int k = 0; k < 3; ++k) o[j][k] = m[j] ? __float2int_rz(div((float)acc[j][k])) : 0;
     }
     const bool full = X0 + 4 <= a.pw;
     if (OUT8) {
@@ -149,18 +153,45 @@ k_feather_fused(const __grid_constant__ FeatherFusedArgs a)
     }
 }
 
-int launch_feather_fused(const FeatherFusedArgs &a, int kind, bool out8, cudaStream_t s)
+int launch_feather_fused(const FeatherFusedArgs &a, bool apply_gain, bool out8, cudaStream_t s)
 {
-    dim3 block(32, 4), grid(div_up(div_up(a.pw, 4), 32), div_up(a.ph, 4));
-#define SB_FF(K) do { if (out8) k_feather_fused<K, true><<<grid, block, 0, s>>>(a); else k_feather_fused<K, false><<<grid, block, 0, s>>>(a); } while (0)
-    switch (kind) {
-    case SB_WARP_PLANE: SB_FF(SB_WARP_PLANE); break;
-    case SB_WARP_CYLINDRICAL: SB_FF(SB_WARP_CYLINDRICAL); break;
-    case SB_WARP_SPHERICAL: SB_FF(SB_WARP_SPHERICAL); break;
-    default: return fail(SB_ERR_BAD_ARG, "unsupported projector kind %d", kind);
-    }
-#undef SB_FF
+    SB_ASSERT(a.sharpness > 0.f);
+    dim3 block(32, 4), grid(div_up(a.pw, SB_FEATHER_TILE_W), div_up(a.ph, 4));
+    if (apply_gain) { if (out8) k_feather_fused<true, true><<<grid, block, 0, s>>>(a); else k_feather_fused<true, false><<<grid, block, 0, s>>>(a); }
+    else            { if (out8) k_feather_fused<false, true><<<grid, block, 0, s>>>(a); else k_feather_fused<false, false><<<grid, block, 0, s>>>(a); }
     SB_LAUNCHED();
+    return SB_OK;
+}
+
+// device self-test: SharedDiv vs __fdiv_rn over pseudo-random operands in the ranges the kernels use
+__global__ void k_selftest_division(unsigned long long n, unsigned seed, unsigned long long *bad)
+{
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    unsigned long long local = 0;
+    for (; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned h = (unsigned)i * 2654435761u ^ seed;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+        unsigned g = h * 747796405u + 2891336453u;
+        g ^= g >> 16; g *= 2246822519u; g ^= g >> 13;
+        // divisor: any float with exponent in the accepted range; numerator: integers and general floats
+        float d = __uint_as_float(((87u + (h % 81u)) << 23) | (g & 0x7fffffu));
+        float a_ = (i & 1) ? (float)((int)(g >> 8) % 65536 - 32768) : __uint_as_float((g & 0x80000000u) | ((87u + ((g >> 3) % 81u)) << 23) | (h & 0x7fffffu));
+        if (!div_fast_ok(d, false) || !div_fast_ok(a_, true)) continue;
+        SharedDiv sd(d);
+        if (__float_as_uint(sd(a_)) != __float_as_uint(__fdiv_rn(a_, d))) ++local;
+    }
+    if (local) atomicAdd(bad, local);
+}
+
+int selftest_division(unsigned long long n, unsigned seed, unsigned long long *mismatches)
+{
+    unsigned long long *d_bad = nullptr;
+    SB_CUDA(cudaMalloc(&d_bad, sizeof *d_bad));
+    SB_CUDA(cudaMemset(d_bad, 0, sizeof *d_bad));
+    k_selftest_division<<<148 * 8, 256>>>(n, seed, d_bad);
+    SB_LAUNCHED();
+    SB_CUDA(cudaMemcpy(mismatches, d_bad, sizeof *d_bad, cudaMemcpyDeviceToHost));
+    cudaFree(d_bad);
     return SB_OK;
 }
 

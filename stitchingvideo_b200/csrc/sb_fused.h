@@ -6,28 +6,27 @@ namespace sb {
 
 constexpr int SB_MAX_CAMERAS = 12;
 
-// one camera as seen by k_feather_fused: projector, separable trig tables, source frame, weights
-struct FusedCam {
-    float k_rinv[9];
-    float one_minus_t2;
-    const float *col_sin, *col_cos, *row_a, *row_b;
+// Per-camera, per-warped-pixel table of the feather path (sequence-constant, 8 bytes/pixel):
+// the fixed-point map entry cv::remap derives from the float maps (A1: sx, sy after >> 5 and the
+// int16 clamp, 5+5 fractional bits) and the L1 distance createWeightMap turns into the weight.
+//   x: sx (low 16, signed) | sy (high 16, signed)      y: fx | fy << 5 (low 16) | dist (high 16)
+// dist == 0 marks a zero-weight pixel (outside the warped mask): the kernel skips it, exactly.
+struct FeatherCam {
     const uint8_t *src;
     size_t sstep;
     int sw, sh;            // source size
+    const uint2 *table;
+    size_t tstep;          // bytes per table row
     int ww, wh;            // warped size
     int dx, dy;            // warped corner in panorama coordinates
     float gain;
-    int apply_gain;
-    const float *weight;   // feather weight map (ww x wh), sequence-constant
-    size_t wstep;
-    int span[4];           // panorama column ranges [s0,s1) U [s2,s3) holding non-zero weights
 };
 
 struct FeatherFusedArgs {
     int n;
-    FusedCam cam[SB_MAX_CAMERAS];
-    const float *wsum;     // dst_weight_map_ (sequence-constant)
-    size_t wsum_step;
+    FeatherCam cam[SB_MAX_CAMERAS];
+    const uint32_t *tile_cams;   // per 128-pixel panorama column block: bitmask of cameras with non-zero weight there
+    float sharpness;
     void *out;             // 8UC3 or 16SC3 panorama
     size_t out_step;
     uint8_t *out_mask;     // may be null
@@ -62,7 +61,12 @@ struct BandFusedArgs {
     int out_w, out_h;      // band 0 only: dst_roi_final_ size
 };
 
-int launch_feather_fused(const FeatherFusedArgs &a, int kind, bool out8, cudaStream_t s);
+constexpr int SB_FEATHER_TILE_W = 128;    // panorama pixels per block column of k_feather_fused
+int launch_feather_fused(const FeatherFusedArgs &a, bool apply_gain, bool out8, cudaStream_t s);
+// setup: fixed-point map + distance table of one camera (dist: CV_32FC1 output of distanceTransform)
+int launch_build_feather_table(const ProjParams &p, int tl_x, int tl_y, const DImage &dist, uint2 *table, size_t tstep, cudaStream_t s);
+// device self-test of SharedDiv against __fdiv_rn; returns the number of mismatching quotients
+int selftest_division(unsigned long long n, unsigned seed, unsigned long long *mismatches);
 int launch_band_fused(const BandFusedArgs &a, bool float_weights, bool not_top, bool final_band, bool out8, cudaStream_t s);
 int launch_column_nonzero(const DImage &w, int *flags, cudaStream_t s);
 

@@ -293,6 +293,12 @@ def test_compositor_matches_reference_loop(gpu, case):
     _compositor_case(gpu, **case)
 
 
+def test_shared_divisor_division_selftest(gpu):
+    """The 3-FFMA shared-reciprocal quotient used inside the fused kernels equals div.rn.f32."""
+    assert gpu.capi.selftest_division(1 << 26, seed=7) == 0
+    assert gpu.capi.selftest_division(1 << 24, seed=12345) == 0
+
+
 def test_compositor_pipelined_slots(gpu):
     """Frames in flight on separate slots give the same panoramas as the synchronous call."""
     from stitchingvideo_b200 import rigs
