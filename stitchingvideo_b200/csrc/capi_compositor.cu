@@ -35,7 +35,9 @@ struct Camera {
     std::vector<DevImage> w_pyr; // weight pyramid (sequence-constant)
     DevImage feather_w;          // feather weight map (sequence-constant)
     DevBuf feather_table;        // fixed-point map + distance, 8 B per warped pixel (sequence-constant)
+    DevBuf feather_bbox;         // per panorama tile: source bounding box of this camera's samples
     size_t feather_tstep = 0;
+    int feather_tpad = 0;
     // panorama(-level) column ranges that hold non-zero weights, per level: [s0,s1) U [s2,s3)
     std::vector<std::array<int, 4>> spans;
 };
@@ -74,7 +76,8 @@ struct sb_compositor {
     int next_slot = 0;
     cudaStream_t setup_stream = nullptr;
     cudaEvent_t marks[2] = {nullptr, nullptr};
-    DevBuf tile_cams;                            // feather: camera bitmask per panorama column block
+    int feather_variant = 1;
+    DevBuf tile_cams;                            // feather: per panorama tile, bitmask of contributing cameras
     bool fused = true;                           // panorama-centric fused kernels (default); false = staged reference-shaped path
 };
 
@@ -259,25 +262,33 @@ int setup(sb_compositor *c)
             Camera &cam = c->cams[i];
             SB_TRY(cam.feather_w.create(cam.wh, cam.ww, SB_32FC1));
             SB_TRY(launch_distance_l1(cam.mask.v, cam.feather_w.v, scratch, s));
-            cam.feather_tstep = ((size_t)cam.ww * sizeof(uint2) + 255) & ~(size_t)255;
+            // rows padded by (dx mod 4) entries in front and 4 behind: quads aligned to the panorama load as 2 x 16 B
+            cam.feather_tpad = (((cam.tl.x - roi.x) % 4) + 4) % 4;
+            cam.feather_tstep = ((size_t)(cam.ww + cam.feather_tpad + 4) * sizeof(uint2) + 255) & ~(size_t)255;
             SB_TRY(cam.feather_table.ensure(cam.feather_tstep * cam.wh));
-            SB_TRY(launch_build_feather_table(cam.proj, cam.tl.x, cam.tl.y, cam.feather_w.v, static_cast<uint2 *>(cam.feather_table.p), cam.feather_tstep, s));
+            SB_CUDA(cudaMemsetAsync(cam.feather_table.p, 0, cam.feather_tstep * cam.wh, s));
+            SB_TRY(launch_build_feather_table(cam.proj, cam.tl.x, cam.tl.y, cam.feather_w.v, static_cast<uint2 *>(cam.feather_table.p), cam.feather_tstep, cam.feather_tpad, s));
             SB_TRY(launch_weight_from_dist(cam.feather_w.v, cfg.sharpness, s));
             SB_TRY(launch_weight_accumulate(cam.feather_w.v, c->wsum[0].v, cam.tl.x - roi.x, cam.tl.y - roi.y, s));
             cam.spans.emplace_back();
             SB_TRY(weight_spans(cam.feather_w.v, cam.tl.x - roi.x, scratch, s, &cam.spans.back()));
         }
-        // per 128-pixel panorama column block: which cameras can contribute there
-        const int tiles = div_up(roi.width, SB_FEATHER_TILE_W);
-        std::vector<uint32_t> tc(tiles, 0u);
-        for (int t = 0; t < tiles; ++t)
-            for (int i = 0; i < n; ++i) {
-                const auto &sp = c->cams[i].spans[0];
-                const int x0 = t * SB_FEATHER_TILE_W, x1 = x0 + SB_FEATHER_TILE_W;
-                if ((x0 < sp[1] && x1 > sp[0]) || (x0 < sp[3] && x1 > sp[2])) tc[t] |= 1u << i;
+        // per (panorama tile, camera): the source box the tile's non-zero-weight samples touch
+        const int tiles_x = div_up(roi.width, SB_FT_W), tiles_y = div_up(roi.height, SB_FT_H);
+        for (int i = 0; i < n; ++i) {
+            Camera &cam = c->cams[i];
+            SB_TRY(cam.feather_bbox.ensure(sizeof(int4) * (size_t)tiles_x * tiles_y));
+            FeatherCam fc{};
+            fc.sw = cfg.src_size.width; fc.sh = cfg.src_size.height;
+            fc.table = static_cast<const uint2 *>(cam.feather_table.p); fc.tstep = cam.feather_tstep; fc.tpad = cam.feather_tpad;
+            fc.ww = cam.ww; fc.wh = cam.wh; fc.dx = cam.tl.x - roi.x; fc.dy = cam.tl.y - roi.y;
+            SB_TRY(launch_feather_tile_bbox(fc, roi.width, roi.height, static_cast<int4 *>(cam.feather_bbox.p), s));
+            if (i == 0) {
+                SB_TRY(c->tile_cams.ensure(sizeof(uint32_t) * (size_t)tiles_x * tiles_y));
+                SB_CUDA(cudaMemsetAsync(c->tile_cams.p, 0, sizeof(uint32_t) * (size_t)tiles_x * tiles_y, s));
             }
-        SB_TRY(c->tile_cams.ensure(sizeof(uint32_t) * tiles));
-        SB_CUDA(cudaMemcpyAsync(c->tile_cams.p, tc.data(), sizeof(uint32_t) * tiles, cudaMemcpyHostToDevice, s));
+            SB_TRY(launch_feather_tile_mask(static_cast<const int4 *>(cam.feather_bbox.p), tiles_x * tiles_y, i, static_cast<uint32_t *>(c->tile_cams.p), s));
+        }
         SB_CUDA(cudaStreamSynchronize(s));
     }
     SB_CUDA(cudaStreamSynchronize(s));
@@ -360,15 +371,18 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
             const Camera &cam = c->cams[i];
             FeatherCam &fc = a.cam[i];
             fc.src = src[i].ptr<uint8_t>(); fc.sstep = src[i].step; fc.sw = src[i].cols; fc.sh = src[i].rows;
-            fc.table = static_cast<const uint2 *>(cam.feather_table.p); fc.tstep = cam.feather_tstep;
+            fc.table = static_cast<const uint2 *>(cam.feather_table.p); fc.tstep = cam.feather_tstep; fc.tpad = cam.feather_tpad;
             fc.ww = cam.ww; fc.wh = cam.wh; fc.dx = cam.tl.x - c->dst_roi.x; fc.dy = cam.tl.y - c->dst_roi.y;
             fc.gain = cam.gain;
+            fc.bbox = static_cast<const int4 *>(cam.feather_bbox.p);
             const auto &sp = cam.spans[0];
             // source gathered ~once; table entries (8 B) read inside the non-zero-weight column spans
             bytes += img_bytes(src[i]) + 8.0 * cam.wh * ((sp[1] - sp[0]) + (sp[3] - sp[2]));
         }
-        a.tile_cams = static_cast<const uint32_t *>(c->tile_cams.p);
+        a.tiles_x = div_up(s.out.v.cols, SB_FT_W);
         a.sharpness = cfg.sharpness;
+        a.variant = c->feather_variant;
+        a.tile_cams = static_cast<const uint32_t *>(c->tile_cams.p);
         a.out = s.out.v.data; a.out_step = s.out.v.step;
         a.out_mask = s.want_mask ? s.out_mask.v.ptr<uint8_t>() : nullptr; a.mask_step = s.out_mask.v.step;
         a.pw = s.out.v.cols; a.ph = s.out.v.rows;
@@ -494,6 +508,7 @@ int sb_compositor_set_fused(sb_compositor *c, int fused)
 {
     SB_ASSERT(c);
     c->fused = fused != 0;
+    if (fused >= 10) c->feather_variant = fused - 10;   // tuning hook: 10 / 11 select the feather kernel variant
     return SB_OK;
 }
 

@@ -17,6 +17,8 @@
 //
 // HBM-bound integer/byte work: each thread owns 4 consecutive panorama pixels so that the weight
 // sums load as float4 and the panorama stores as 3 x 32-bit (8U) or 3 x 64-bit (16S) words.
+#include <climits>
+
 #include "sb_device.cuh"
 #include "sb_fused.h"
 #include "sb_pyr.cuh"
@@ -37,7 +39,7 @@ __device__ __forceinline__ bool in_spans(const int span[4], int x0, int x1)   //
 // frame (sx, sy, fx, fy; Appendix A1) + the L1 distance behind the feather weight.
 template <int KIND>
 __global__ void __launch_bounds__(256)
-k_build_feather_table(ProjParams p, int tl_x, int tl_y, const float *dist, size_t dstep, int w, int h, uint2 *table, size_t tstep)
+k_build_feather_table(ProjParams p, int tl_x, int tl_y, const float *dist, size_t dstep, int w, int h, uint2 *table, size_t tstep, int tpad)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
@@ -50,14 +52,14 @@ k_build_feather_table(ProjParams p, int tl_x, int tl_y, const float *dist, size_
     uint2 t;
     t.x = ((unsigned)sx & 0xffffu) | ((unsigned)sy << 16);
     t.y = (unsigned)(fsx & 31) | ((unsigned)(fsy & 31) << 5) | (di << 16);
-    reinterpret_cast<uint2 *>(reinterpret_cast<char *>(table) + (size_t)y * tstep)[x] = t;
+    reinterpret_cast<uint2 *>(reinterpret_cast<char *>(table) + (size_t)y * tstep)[x + tpad] = t;
 }
 
-int launch_build_feather_table(const ProjParams &p, int tl_x, int tl_y, const DImage &dist, uint2 *table, size_t tstep, cudaStream_t s)
+int launch_build_feather_table(const ProjParams &p, int tl_x, int tl_y, const DImage &dist, uint2 *table, size_t tstep, int tpad, cudaStream_t s)
 {
     SB_ASSERT(dist.type == SB_32FC1);
     dim3 block(32, 8), grid(div_up(dist.cols, 32), div_up(dist.rows, 8));
-#define SB_FT(K) k_build_feather_table<K><<<grid, block, 0, s>>>(p, tl_x, tl_y, dist.ptr<float>(), dist.step, dist.cols, dist.rows, table, tstep)
+#define SB_FT(K) k_build_feather_table<K><<<grid, block, 0, s>>>(p, tl_x, tl_y, dist.ptr<float>(), dist.step, dist.cols, dist.rows, table, tstep, tpad)
     switch (p.kind) {
     case SB_WARP_PLANE: SB_FT(SB_WARP_PLANE); break;
     case SB_WARP_CYLINDRICAL: SB_FT(SB_WARP_CYLINDRICAL); break;
@@ -69,55 +71,156 @@ int launch_build_feather_table(const ProjParams &p, int tl_x, int tl_y, const DI
     return SB_OK;
 }
 
+// setup: source bounding box per (panorama tile, camera) — sequence-constant, so the per-frame
+// kernel can stage exactly the bytes it will sample into shared memory with 16-byte loads.
+__global__ void __launch_bounds__(256) k_feather_tile_bbox(FeatherCam c, int pw, int ph, int tiles_x, int4 *bbox)
+{
+    __shared__ int red[4][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int X0 = blockIdx.x * SB_FT_W + (tid & 7) * 4, Y = blockIdx.y * SB_FT_H + (tid >> 3);
+    int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
+    const int y = Y - c.dy;
+    if (Y < ph && (unsigned)y < (unsigned)c.wh) {
+        const uint2 *trow = reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(c.table) + (size_t)y * c.tstep) + c.tpad;
+        for (int j = 0; j < 4; ++j) {
+            const int x = X0 + j - c.dx;
+            if (X0 + j >= pw || (unsigned)x >= (unsigned)c.ww) continue;
+            const uint2 t = trow[x];
+            if ((t.y >> 16) == 0u) continue;
+            const int sx = (short)(t.x & 0xffffu), sy = (int)t.x >> 16;
+            mnx = min(mnx, max(sx, 0)); mxx = max(mxx, min(sx + 1, c.sw - 1));
+            mny = min(mny, max(sy, 0)); mxy = max(mxy, min(sy + 1, c.sh - 1));
+        }
+    }
+    mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
+    mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+    if (lane == 0) { red[0][warp] = mnx; red[1][warp] = mny; red[2][warp] = mxx; red[3][warp] = mxy; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w) {
+            mnx = min(mnx, red[0][w]); mny = min(mny, red[1][w]); mxx = max(mxx, red[2][w]); mxy = max(mxy, red[3][w]);
+        }
+        bbox[blockIdx.y * tiles_x + blockIdx.x] = (mxx < mnx) ? make_int4(0, 0, -1, -1) : make_int4(mnx, mny, mxx, mxy);
+    }
+}
+
+int launch_feather_tile_bbox(const FeatherCam &c, int pw, int ph, int4 *bbox, cudaStream_t s)
+{
+    dim3 block(256), grid(div_up(pw, SB_FT_W), div_up(ph, SB_FT_H));
+    k_feather_tile_bbox<<<grid, block, 0, s>>>(c, pw, ph, grid.x, bbox);
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
+__global__ void k_feather_tile_mask(const int4 *bbox, int n_tiles, int cam_index, uint32_t *tile_cams)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_tiles && bbox[i].z >= bbox[i].x) tile_cams[i] |= 1u << cam_index;
+}
+
+int launch_feather_tile_mask(const int4 *bbox, int n_tiles, int cam_index, uint32_t *tile_cams, cudaStream_t s)
+{
+    k_feather_tile_mask<<<div_up(n_tiles, 256), 256, 0, s>>>(bbox, n_tiles, cam_index, tile_cams);
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
 // One launch per frame.  A non-zero distance implies the pixel lies inside the warped all-255 mask,
 // i.e. its source coordinate rounds into the image: sx in [-1, sw-1], sy in [-1, sh-1], where
 // BORDER_REFLECT coincides with clamping.  Every table weight carries the factor 32, so
 // (sum w*p + 2^14) >> 15 == (v + 512) >> 10 with v the sum of 5-bit products; OpenCV's (0,0) entry
 // {32767,0,0,1} equals an exact copy for 8-bit data, as does {32768,0,0,0}.  With 8-bit sources and
 // weights in [0,1] every intermediate stays inside [0, 255*n]: no saturation or wrap can fire.
+//
+// The gather is the expensive part (12 byte taps per sample): the source box each tile needs is known
+// per calibration, so the block first stages it in shared memory with coalesced 16-byte loads and
+// then samples with conflict-free byte LDS (lanes are 12 bytes apart: 3 words, coprime with 32 banks).
 template <bool GAIN, bool OUT8>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_feather_fused(const __grid_constant__ FeatherFusedArgs a)
 {
-    const int X0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int Y = blockIdx.y * 4 + threadIdx.y;
-    if (X0 >= a.pw || Y >= a.ph) return;
+    __shared__ __align__(16) uint8_t stage[SB_STAGE_BYTES];
+    const int tile = blockIdx.y * a.tiles_x + blockIdx.x;
+    const int tid = threadIdx.x;
+    const int X0 = blockIdx.x * SB_FT_W + (tid & 7) * 4;       // 8 threads x 4 px across, 32 rows down
+    const int Y = blockIdx.y * SB_FT_H + (tid >> 3);
+    const bool active = X0 < a.pw && Y < a.ph;
     int acc[4][3];
     float wsum[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = 0; wsum[j] = 0.f; }
 
-    for (uint32_t cams = a.tile_cams[blockIdx.x]; cams; cams &= cams - 1) {   // ascending index = feed order
-        const FeatherCam &c = a.cam[__ffs(cams) - 1];
+    for (int i = 0; i < a.n; ++i) {                       // ascending index = feed order (float weight sums)
+        const FeatherCam &c = a.cam[i];
+        const int4 bb = __ldg(c.bbox + tile);             // block-uniform
+        if (bb.z < bb.x) continue;
+        const int bw = bb.z - bb.x + 1, bh = bb.w - bb.y + 1;
+        const uint8_t *g0 = c.src + (size_t)bb.y * c.sstep + bb.x * 3;
+        const unsigned o0 = (unsigned)(reinterpret_cast<uintptr_t>(g0) & 15), os = (unsigned)(c.sstep & 15);
+        const int nch = (bw * 3 + 15 + 15) >> 4;          // 16-byte chunks per staged row (upper bound over row alignments)
+        const int pitch = nch * 16;
+        const bool staged = pitch * bh <= SB_STAGE_BYTES;
+        if (staged) {
+            for (int idx = tid; idx < bh * nch; idx += 256) {
+                const int r = idx / nch, ch = idx - r * nch;
+                const uint8_t *gr = g0 + (size_t)r * c.sstep;
+                const unsigned orow = (unsigned)(reinterpret_cast<uintptr_t>(gr) & 15);
+                if (ch * 16 < (int)orow + bw * 3)
+                    *reinterpret_cast<uint4 *>(stage + r * pitch + ch * 16) = __ldg(reinterpret_cast<const uint4 *>(gr - orow) + ch);
+            }
+            __syncthreads();
+        }
         const int y = Y - c.dy;
-        if ((unsigned)y >= (unsigned)c.wh) continue;
-        const uint2 *trow = reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(c.table) + (size_t)y * c.tstep);
         const int xb = X0 - c.dx;
+        if (active && (unsigned)y < (unsigned)c.wh && xb + 3 >= 0 && xb < c.ww) {
+            // the quad's 4 table entries are 32-byte aligned (tpad) and lie inside the padded table row
+            const uint4 *tq = reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(c.table) + (size_t)y * c.tstep) + ((xb + c.tpad) >> 1);
+            const uint4 ta = __ldg(tq), tb = __ldg(tq + 1);
+            const uint2 te[4] = {make_uint2(ta.x, ta.y), make_uint2(ta.z, ta.w), make_uint2(tb.x, tb.y), make_uint2(tb.z, tb.w)};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int x = xb + j;
-            if ((unsigned)x >= (unsigned)c.ww) continue;
-            const uint2 t = __ldg(trow + x);
-            const unsigned dist = t.y >> 16;
-            if (dist == 0u) continue;                       // weight 0: short(p * 0) == 0 and dst_w += 0
-            // createWeightMap: threshold(dist * sharpness, 1, THRESH_TRUNC)
-            const float w = fminf(__fmul_rn((float)dist, a.sharpness), 1.f);
-            wsum[j] = __fadd_rn(wsum[j], w);
-            const int sx = (short)(t.x & 0xffffu), sy = (int)t.x >> 16;
-            const int fx = t.y & 31, fy = (t.y >> 5) & 31, ax = 32 - fx, ay = 32 - fy;
-            const int x0 = max(sx, 0), x1 = min(sx + 1, c.sw - 1), y0 = max(sy, 0), y1 = min(sy + 1, c.sh - 1);
-            const uint8_t *r0 = c.src + (size_t)y0 * c.sstep, *r1 = c.src + (size_t)y1 * c.sstep;
-            const uint8_t *p00 = r0 + x0 * 3, *p01 = r0 + x1 * 3, *p10 = r1 + x0 * 3, *p11 = r1 + x1 * 3;
+            for (int j = 0; j < 4; ++j) {
+                const int x = xb + j;
+                if ((unsigned)x >= (unsigned)c.ww) continue;
+                const uint2 t = te[j];
+                const unsigned dist = t.y >> 16;
+                if (dist == 0u) continue;                   // weight 0: short(p * 0) == 0 and dst_w += 0
+                // createWeightMap: threshold(dist * sharpness, 1, THRESH_TRUNC)
+                const float w = fminf(__fmul_rn((float)dist, a.sharpness), 1.f);
+                wsum[j] = __fadd_rn(wsum[j], w);
+                const int sx = (short)(t.x & 0xffffu), sy = (int)t.x >> 16;
+                const int fx = t.y & 31, fy = (t.y >> 5) & 31, ax = 32 - fx, ay = 32 - fy;
+                const int x0 = max(sx, 0), x1 = min(sx + 1, c.sw - 1), y0 = max(sy, 0), y1 = min(sy + 1, c.sh - 1);
+                int v[3];
+                if (staged) {
+                    const int r0 = y0 - bb.y, r1 = y1 - bb.y;
+                    const uint8_t *s0 = stage + r0 * pitch + ((o0 + r0 * os) & 15) - bb.x * 3;
+                    const uint8_t *s1 = stage + r1 * pitch + ((o0 + r1 * os) & 15) - bb.x * 3;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int h0 = (int)__ldg(p00 + k) * ax + (int)__ldg(p01 + k) * fx;
-                const int h1 = (int)__ldg(p10 + k) * ax + (int)__ldg(p11 + k) * fx;
-                int v = (h0 * ay + h1 * fy + 512) >> 10;
-                if (GAIN) v = min(max(__float2int_rn(__fmul_rn((float)v, c.gain)), 0), 255);   // saturate_cast<uchar>
-                acc[j][k] += __float2int_rz(__fmul_rn((float)v, w));                      // static_cast<short>(src * w)
+                    for (int k = 0; k < 3; ++k) {
+                        const int h0 = (int)s0[x0 * 3 + k] * ax + (int)s0[x1 * 3 + k] * fx;
+                        const int h1 = (int)s1[x0 * 3 + k] * ax + (int)s1[x1 * 3 + k] * fx;
+                        v[k] = (h0 * ay + h1 * fy + 512) >> 10;
+                    }
+                } else {
+                    const uint8_t *r0 = c.src + (size_t)y0 * c.sstep, *r1 = c.src + (size_t)y1 * c.sstep;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int h0 = (int)__ldg(r0 + x0 * 3 + k) * ax + (int)__ldg(r0 + x1 * 3 + k) * fx;
+                        const int h1 = (int)__ldg(r1 + x0 * 3 + k) * ax + (int)__ldg(r1 + x1 * 3 + k) * fx;
+                        v[k] = (h0 * ay + h1 * fy + 512) >> 10;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    int p = v[k];
+                    if (GAIN) p = min(max(__float2int_rn(__fmul_rn((float)p, c.gain)), 0), 255);   // saturate_cast<uchar>
+                    acc[j][k] += __float2int_rz(__fmul_rn((float)p, w));                            // static_cast<short>(src * w)
+                }
             }
         }
+        if (staged) __syncthreads();                      // the stage buffer is reused by the next camera
     }
+    if (!active) return;
     // FeatherBlender::blend: normalizeUsingWeightMap, mask = weight > eps, zero unmasked, convertTo(8U)
     int o[4][3], m[4];
 #pragma unroll
@@ -153,10 +256,97 @@ k_feather_fused(const __grid_constant__ FeatherFusedArgs a)
     }
 }
 
+// Variant with one panorama pixel per thread: a warp's 32 lanes sample 32 neighbouring pixels, so each
+// byte-tap request touches 3-4 sectors instead of ~20 (lanes 3 B apart rather than 4 px = 12 B apart).
+// One load fetches the tile's camera bitmask; the table entries of every contributing camera are
+// requested before any is consumed, so the DRAM latencies of the cameras overlap.
+template <bool GAIN, bool OUT8>
+__global__ void __launch_bounds__(256)
+k_feather_fused_px1(const __grid_constant__ FeatherFusedArgs a)
+{
+    const int X = blockIdx.x * 32 + threadIdx.x;
+    const int Y = blockIdx.y * 8 + threadIdx.y;
+    if (X >= a.pw || Y >= a.ph) return;
+    // tiles are SB_FT_W x SB_FT_H = 32 x 32 and blocks 32 x 8: the mask is block-uniform
+    uint32_t cams = __ldg(a.tile_cams + (blockIdx.y >> 2) * a.tiles_x + blockIdx.x);
+    constexpr int MAXC = 4;
+    uint2 t[MAXC];
+    int ci[MAXC];
+    int nc = 0;
+#pragma unroll
+    for (int q = 0; q < MAXC; ++q) {
+        t[q] = make_uint2(0u, 0u);
+        ci[q] = 0;
+        if (cams) {
+            const int i = __ffs(cams) - 1;
+            cams &= cams - 1;
+            const FeatherCam &c = a.cam[i];
+            const int y = Y - c.dy, x = X - c.dx;
+            ci[q] = i;
+            nc = q + 1;
+            if ((unsigned)y < (unsigned)c.wh && (unsigned)x < (unsigned)c.ww)
+                t[q] = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(c.table) + (size_t)y * c.tstep) + x + c.tpad);
+        }
+    }
+    int acc0 = 0, acc1 = 0, acc2 = 0;
+    float wsum = 0.f;
+    auto contribute = [&](const FeatherCam &c, const uint2 te) {
+        const unsigned dist = te.y >> 16;
+        if (dist == 0u) return;                             // weight 0: short(p * 0) == 0 and dst_w += 0
+        const float w = fminf(__fmul_rn((float)dist, a.sharpness), 1.f);      // createWeightMap
+        wsum = __fadd_rn(wsum, w);
+        const int sx = (short)(te.x & 0xffffu), sy = (int)te.x >> 16;
+        const int fx = te.y & 31, fy = (te.y >> 5) & 31, ax = 32 - fx, ay = 32 - fy;
+        const int x0 = max(sx, 0), x1 = min(sx + 1, c.sw - 1), y0 = max(sy, 0), y1 = min(sy + 1, c.sh - 1);
+        const uint8_t *r0 = c.src + (size_t)y0 * c.sstep, *r1 = c.src + (size_t)y1 * c.sstep;
+        const uint8_t *p00 = r0 + x0 * 3, *p01 = r0 + x1 * 3, *p10 = r1 + x0 * 3, *p11 = r1 + x1 * 3;
+        int v[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int h0 = (int)__ldg(p00 + k) * ax + (int)__ldg(p01 + k) * fx;
+            const int h1 = (int)__ldg(p10 + k) * ax + (int)__ldg(p11 + k) * fx;
+            v[k] = (h0 * ay + h1 * fy + 512) >> 10;
+            if (GAIN) v[k] = min(max(__float2int_rn(__fmul_rn((float)v[k], c.gain)), 0), 255);   // saturate_cast<uchar>
+        }
+        acc0 += __float2int_rz(__fmul_rn((float)v[0], w));                                          // static_cast<short>(src * w)
+        acc1 += __float2int_rz(__fmul_rn((float)v[1], w));
+        acc2 += __float2int_rz(__fmul_rn((float)v[2], w));
+    };
+#pragma unroll
+    for (int q = 0; q < MAXC; ++q)
+        if (q < nc) contribute(a.cam[ci[q]], t[q]);
+    for (; cams; cams &= cams - 1) {                        // more than MAXC overlapping cameras: rest in order
+        const FeatherCam &c = a.cam[__ffs(cams) - 1];
+        const int y = Y - c.dy, x = X - c.dx;
+        if ((unsigned)y < (unsigned)c.wh && (unsigned)x < (unsigned)c.ww)
+            contribute(c, __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(c.table) + (size_t)y * c.tstep) + x + c.tpad));
+    }
+    const int m = wsum > SB_WEIGHT_EPS ? 255 : 0;
+    const SharedDiv div(__fadd_rn(wsum, SB_WEIGHT_EPS));
+    const int o0 = m ? __float2int_rz(div((float)acc0)) : 0, o1 = m ? __float2int_rz(div((float)acc1)) : 0,
+              o2 = m ? __float2int_rz(div((float)acc2)) : 0;
+    if (OUT8) {
+        uint8_t *o = reinterpret_cast<uint8_t *>(a.out) + (size_t)Y * a.out_step + X * 3;
+        o[0] = (uint8_t)o0; o[1] = (uint8_t)o1; o[2] = (uint8_t)o2;
+    } else {
+        short *o = reinterpret_cast<short *>(reinterpret_cast<char *>(a.out) + (size_t)Y * a.out_step) + X * 3;
+        o[0] = (short)o0; o[1] = (short)o1; o[2] = (short)o2;
+    }
+    if (a.out_mask) a.out_mask[(size_t)Y * a.mask_step + X] = (uint8_t)m;
+}
+
 int launch_feather_fused(const FeatherFusedArgs &a, bool apply_gain, bool out8, cudaStream_t s)
 {
     SB_ASSERT(a.sharpness > 0.f);
-    dim3 block(32, 4), grid(div_up(a.pw, SB_FEATHER_TILE_W), div_up(a.ph, 4));
+    SB_ASSERT(div_up(a.pw, SB_FT_W) == a.tiles_x);
+    if (a.variant == 1) {
+        dim3 block(32, 8), grid(div_up(a.pw, 32), div_up(a.ph, 8));
+        if (apply_gain) { if (out8) k_feather_fused_px1<true, true><<<grid, block, 0, s>>>(a); else k_feather_fused_px1<true, false><<<grid, block, 0, s>>>(a); }
+        else            { if (out8) k_feather_fused_px1<false, true><<<grid, block, 0, s>>>(a); else k_feather_fused_px1<false, false><<<grid, block, 0, s>>>(a); }
+        SB_LAUNCHED();
+        return SB_OK;
+    }
+    dim3 block(256), grid(div_up(a.pw, SB_FT_W), div_up(a.ph, SB_FT_H));
     if (apply_gain) { if (out8) k_feather_fused<true, true><<<grid, block, 0, s>>>(a); else k_feather_fused<true, false><<<grid, block, 0, s>>>(a); }
     else            { if (out8) k_feather_fused<false, true><<<grid, block, 0, s>>>(a); else k_feather_fused<false, false><<<grid, block, 0, s>>>(a); }
     SB_LAUNCHED();
