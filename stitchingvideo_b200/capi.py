@@ -573,7 +573,8 @@ class Compositor:
         return pano, pano_mask
 
     def set_fused(self, fused):
-        _check(lib().sb_compositor_set_fused(self._h, 1 if fused else 0))
+        """True/1: fused kernels; False/0: staged feed/blend-shaped path; 10/11: fused with kernel variant 0/1."""
+        _check(lib().sb_compositor_set_fused(self._h, int(fused)))
 
     def set_depth(self, depth):
         _check(lib().sb_compositor_set_depth(self._h, depth))

@@ -16,6 +16,7 @@
 
 #include "sb_fused.h"
 #include "sb_host_projector.h"
+#include "sb_mb.h"
 #include "sb_kernels.h"
 
 using namespace sb;
@@ -36,10 +37,26 @@ struct Camera {
     DevImage feather_w;          // feather weight map (sequence-constant)
     DevBuf feather_table;        // fixed-point map + distance, 8 B per warped pixel (sequence-constant)
     DevBuf feather_bbox;         // per panorama tile: source bounding box of this camera's samples
+    DevBuf mb_table;             // multi-band fast path: resolved bilinear taps per padded-rect pixel (8 B)
+    size_t mb_tstep = 0;
     size_t feather_tstep = 0;
     int feather_tpad = 0;
     // panorama(-level) column ranges that hold non-zero weights, per level: [s0,s1) U [s2,s3)
     std::vector<std::array<int, 4>> spans;
+};
+
+// pitched device buffer for the pixel formats outside the OpenCV type set (RGBX bytes, short4)
+struct RawImage {
+    DevBuf buf;
+    size_t step = 0;
+    int rows = 0, cols = 0, esz = 0;
+    int create(int r, int c, int elem)
+    {
+        rows = r; cols = c; esz = elem;
+        step = ((size_t)c * elem + 255) & ~(size_t)255;
+        return buf.ensure(step * (size_t)(r > 0 ? r : 1));
+    }
+    double bytes() const { return (double)rows * cols * esz; }
 };
 
 // per-kernel record of one profiled frame (bench.py's roofline): CUDA events on the launching stream
@@ -58,6 +75,8 @@ struct Slot {
     std::vector<DevImage> src;                   // staged source frames (host input)
     std::vector<std::vector<DevImage>> gpyr;     // per camera Gaussian pyramid of the padded warped image
     DevImage warped;                             // feather / no-blend: one warped image at a time
+    std::vector<std::vector<RawImage>> grgbx;    // fast path: per camera Gaussian pyramid as RGBX bytes
+    std::vector<RawImage> rband;                 // fast path: restored bands 1..n as short4 pixels
     std::vector<DevImage> acc;                   // dst_pyr_laplace_ (level 0 = dst_)
     DevImage acc_mask;                           // Blender::NO dst_mask_
     DevImage out, out_mask;
@@ -77,6 +96,9 @@ struct sb_compositor {
     cudaStream_t setup_stream = nullptr;
     cudaEvent_t marks[2] = {nullptr, nullptr};
     int feather_variant = 1;
+    int mb_variant = 1;                          // 1: RGBX fast path, 0: CV_16S band kernels
+    bool mb_fast = false;                        // RGBX pyramid + tap-table path available (sources <= 4096 px)
+    std::vector<DevBuf> mb_tile_mask;            // per band: per 32x8 tile bitmask of contributing cameras
     DevBuf tile_cams;                            // feather: per panorama tile, bitmask of contributing cameras
     bool fused = true;                           // panorama-centric fused kernels (default); false = staged reference-shaped path
 };
@@ -109,6 +131,20 @@ int make_slot(sb_compositor *c, Slot &s)
                 r = (r + 1) / 2; w = (w + 1) / 2;
             }
         }
+    }
+    if (c->mb_fast) {
+        s.grgbx.resize(n);
+        for (int i = 0; i < n; ++i) {
+            const Camera &cam = c->cams[i];
+            s.grgbx[i].resize(levels + 1);
+            int r = cam.rh, w = cam.rw;
+            for (int l = 0; l <= levels; ++l) {
+                SB_TRY(s.grgbx[i][l].create(r, w, 4));
+                r = (r + 1) / 2; w = (w + 1) / 2;
+            }
+        }
+        s.rband.resize(levels + 1);
+        for (int l = 1; l <= levels; ++l) SB_TRY(s.rband[l].create(s.acc[l].v.rows, s.acc[l].v.cols, 8));
     }
     SB_TRY(s.out.create(c->dst_roi_final.height, c->dst_roi_final.width, c->cfg.output_type));
     SB_TRY(s.out_mask.create(c->dst_roi_final.height, c->dst_roi_final.width, SB_8UC1));
@@ -254,6 +290,31 @@ int setup(sb_compositor *c)
                 x_tl /= 2; y_tl /= 2;
             }
         }
+        // fast path tables: resolved taps per padded pixel, camera bitmask per band tile
+        c->mb_fast = cfg.src_size.width <= 4096 && cfg.src_size.height <= 4096;
+        if (c->mb_fast) {
+            for (int i = 0; i < n; ++i) {
+                Camera &cam = c->cams[i];
+                cam.mb_tstep = ((size_t)cam.rw * sizeof(uint2) + 255) & ~(size_t)255;
+                SB_TRY(cam.mb_table.ensure(cam.mb_tstep * cam.rh));
+                SB_TRY(launch_mb_tap_table(cam.proj, cam.tl.x, cam.tl.y, cam.ww, cam.wh, cam.left, cam.top, cfg.src_size.width,
+                                           cfg.src_size.height, static_cast<uint2 *>(cam.mb_table.p), cam.mb_tstep, cam.rw, cam.rh, s));
+            }
+            c->mb_tile_mask.resize(nb + 1);
+            for (int l = 0; l <= nb; ++l) {
+                MbBandGeom g{};
+                g.n = n;
+                g.lw = c->wsum[l].v.cols; g.lh = c->wsum[l].v.rows;
+                for (int i = 0; i < n; ++i) {
+                    const Camera &cam = c->cams[i];
+                    g.cam[i].weight = cam.w_pyr[l].v.data; g.cam[i].wstep = cam.w_pyr[l].v.step;
+                    g.cam[i].rx = cam.rx >> l; g.cam[i].ry = cam.ry >> l;
+                    g.cam[i].rw = cam.w_pyr[l].v.cols; g.cam[i].rh = cam.w_pyr[l].v.rows;
+                }
+                SB_TRY(c->mb_tile_mask[l].ensure(sizeof(uint32_t) * (size_t)div_up(g.lw, 32) * div_up(g.lh, 8)));
+                SB_TRY(launch_mb_tile_mask(g, wt == SB_32FC1, g.lw, g.lh, static_cast<uint32_t *>(c->mb_tile_mask[l].p), s));
+            }
+        }
     } else if (cfg.blender_kind == SB_BLEND_FEATHER) {
         c->wsum.resize(1);
         SB_TRY(c->wsum[0].create_zero(roi.height, roi.width, SB_32FC1, s));
@@ -318,7 +379,73 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
     DImage none;
     // Blender::prepare zeroes the accumulators (blenders.cpp:71-78, 227-232): only the unfused
     // (camera-by-camera) path has accumulators in HBM; the weight sums are resident either way
-    if (cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused) {
+    if (cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused && c->mb_fast && c->mb_variant == 1) {
+        const int nb = c->num_bands;
+        {   // K1: remap + gain + convertTo(16S) + copyMakeBorder for every camera, one launch
+            MbWarpArgs a{};
+            a.n = n;
+            double bytes = 0;
+            int mw = 0, mh = 0;
+            for (int i = 0; i < n; ++i) {
+                const Camera &cam = c->cams[i];
+                MbWarpCam &wc = a.cam[i];
+                wc.src = src[i].ptr<uint8_t>(); wc.sstep = src[i].step;
+                wc.table = static_cast<const uint2 *>(cam.mb_table.p); wc.tstep = cam.mb_tstep;
+                wc.g0 = static_cast<uint32_t *>(s.grgbx[i][0].buf.p); wc.gstep = s.grgbx[i][0].step;
+                wc.rw = cam.rw; wc.rh = cam.rh; wc.gain = cam.gain;
+                mw = std::max(mw, cam.rw); mh = std::max(mh, cam.rh);
+                bytes += img_bytes(src[i]) + (double)cam.rw * cam.rh * (8 + 4);
+            }
+            PROF("mb_warp", bytes, launch_mb_warp(a, gain_on, mw, mh, st));
+        }
+        for (int l = 0; l < nb; ++l) {   // K2: Gaussian level l -> l+1 for every camera, one launch
+            MbPyrArgs a{};
+            a.n = n;
+            double bytes = 0;
+            int mw = 0, mh = 0;
+            for (int i = 0; i < n; ++i) {
+                const RawImage &in = s.grgbx[i][l], &out = s.grgbx[i][l + 1];
+                a.cam[i].src = static_cast<const uint32_t *>(in.buf.p); a.cam[i].sstep = in.step; a.cam[i].sw = in.cols; a.cam[i].sh = in.rows;
+                a.cam[i].dst = static_cast<uint32_t *>(out.buf.p); a.cam[i].dstep = out.step;
+                mw = std::max(mw, out.cols); mh = std::max(mh, out.rows);
+                bytes += in.bytes() + out.bytes();
+            }
+            PROF("mb_pyr_down", bytes, launch_mb_pyr_down(a, mw, mh, st));
+        }
+        for (int l = nb; l >= 0; --l) {  // K3: bands coarse -> fine
+            MbBandArgs a{};
+            a.g.n = n;
+            double bytes = 0;
+            for (int i = 0; i < n; ++i) {
+                const Camera &cam = c->cams[i];
+                MbBandCam &bc = a.g.cam[i];
+                const RawImage &f = s.grgbx[i][l];
+                bc.fine = static_cast<const uint32_t *>(f.buf.p); bc.fstep = f.step;
+                if (l < nb) { bc.coarse = static_cast<const uint32_t *>(s.grgbx[i][l + 1].buf.p); bc.cstep = s.grgbx[i][l + 1].step; }
+                bc.weight = cam.w_pyr[l].v.data; bc.wstep = cam.w_pyr[l].v.step;
+                bc.rx = cam.rx >> l; bc.ry = cam.ry >> l; bc.rw = f.cols; bc.rh = f.rows;
+                const auto &sp = cam.spans[l];
+                const double frac = std::min(1.0, (double)((sp[1] - sp[0]) + (sp[3] - sp[2])) / std::max(1, f.cols));
+                bytes += frac * (f.bytes() * (l < nb ? 1.25 : 1.0) + img_bytes(cam.w_pyr[l].v));
+            }
+            const DImage &ws = c->wsum[l].v;
+            a.g.lw = ws.cols; a.g.lh = ws.rows;
+            a.tile_mask = static_cast<const uint32_t *>(c->mb_tile_mask[l].p); a.tiles_x = div_up(ws.cols, 32);
+            a.wsum = ws.data; a.wsum_step = ws.step;
+            if (l < nb) { a.coarse_r = static_cast<const short4 *>(s.rband[l + 1].buf.p); a.coarse_r_step = s.rband[l + 1].step; bytes += s.rband[l + 1].bytes(); }
+            const bool fin = l == 0;
+            if (fin) {
+                a.out = s.out.v.data; a.out_step = s.out.v.step;
+                a.out_mask = s.want_mask ? s.out_mask.v.ptr<uint8_t>() : nullptr; a.mask_step = s.out_mask.v.step;
+                a.out_w = s.out.v.cols; a.out_h = s.out.v.rows;
+                bytes += img_bytes(s.out.v) + (s.want_mask ? img_bytes(s.out_mask.v) : 0) + (double)a.out_w * a.out_h * elem_size(ws.type);
+            } else {
+                a.out = s.rband[l].buf.p; a.out_step = s.rband[l].step;
+                bytes += s.rband[l].bytes() + img_bytes(ws);
+            }
+            PROF(fin ? "mb_band_final" : "mb_band", bytes, launch_mb_band(a, cfg.weight_type == SB_32F, l < nb, fin, s.out.v.type == SB_8UC3, st));
+        }
+    } else if (cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused) {
         const int nb = c->num_bands;
         for (int i = 0; i < n; ++i) {
             const Camera &cam = c->cams[i];
@@ -508,7 +635,7 @@ int sb_compositor_set_fused(sb_compositor *c, int fused)
 {
     SB_ASSERT(c);
     c->fused = fused != 0;
-    if (fused >= 10) c->feather_variant = fused - 10;   // tuning hook: 10 / 11 select the feather kernel variant
+    if (fused >= 10) { c->feather_variant = fused - 10; c->mb_variant = fused - 10; }   // test/tuning hook: 10 / 11 select the kernel variant
     return SB_OK;
 }
 

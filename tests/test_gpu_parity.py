@@ -272,7 +272,9 @@ def _compositor_case(gpu, rig, blender, weight_type=O.CV_32F, seams=False, gains
         frames = [rigs.frame(rig, fi, i) for i in range(n)]
         ref, rmask = P.compose(cal, frames, blender=blender, num_bands=num_bands, weight_type=weight_type, gains=g,
                                output_8u=not out16)
-        for fused in (True, False):           # panorama-centric fused kernels, then the staged feed/blend-shaped path
+        # 11: fused fast kernels (RGBX pyramid / 1-px feather); 10: fused CV_16S band kernels / staged-smem
+        # feather; 0: the staged, camera-by-camera path shaped like the reference's feed/blend calls
+        for fused in (11, 10, 0):
             comp.set_fused(fused)
             pano, mask = comp.compose(frames)
             assert_same(pano, ref, "%s/%s pano frame %d fused=%s" % (rig, blender, fi, fused))
