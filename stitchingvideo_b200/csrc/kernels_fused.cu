@@ -299,12 +299,22 @@ k_feather_fused_px1(const __grid_constant__ FeatherFusedArgs a)
         const int fx = te.y & 31, fy = (te.y >> 5) & 31, ax = 32 - fx, ay = 32 - fy;
         const int x0 = max(sx, 0), x1 = min(sx + 1, c.sw - 1), y0 = max(sy, 0), y1 = min(sy + 1, c.sh - 1);
         const uint8_t *r0 = c.src + (size_t)y0 * c.sstep, *r1 = c.src + (size_t)y1 * c.sstep;
-        const uint8_t *p00 = r0 + x0 * 3, *p01 = r0 + x1 * 3, *p10 = r1 + x0 * 3, *p11 = r1 + x1 * 3;
+        unsigned q00, q01, q10, q11;                        // packed RGB of the four taps
+        if (x1 == x0 + 1) {                                 // the pair is 6 contiguous bytes: 2-3 word loads per row
+            load_pixel_pair_8uc3(r0 + x0 * 3, q00, q01);
+            load_pixel_pair_8uc3(r1 + x0 * 3, q10, q11);
+        } else {                                            // clamped at the image edge
+            const uint8_t *p00 = r0 + x0 * 3, *p01 = r0 + x1 * 3, *p10 = r1 + x0 * 3, *p11 = r1 + x1 * 3;
+            q00 = __ldg(p00) | (__ldg(p00 + 1) << 8) | (__ldg(p00 + 2) << 16);
+            q01 = __ldg(p01) | (__ldg(p01 + 1) << 8) | (__ldg(p01 + 2) << 16);
+            q10 = __ldg(p10) | (__ldg(p10 + 1) << 8) | (__ldg(p10 + 2) << 16);
+            q11 = __ldg(p11) | (__ldg(p11 + 1) << 8) | (__ldg(p11 + 2) << 16);
+        }
         int v[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const int h0 = (int)__ldg(p00 + k) * ax + (int)__ldg(p01 + k) * fx;
-            const int h1 = (int)__ldg(p10 + k) * ax + (int)__ldg(p11 + k) * fx;
+            const int h0 = (int)((q00 >> (8 * k)) & 0xff) * ax + (int)((q01 >> (8 * k)) & 0xff) * fx;
+            const int h1 = (int)((q10 >> (8 * k)) & 0xff) * ax + (int)((q11 >> (8 * k)) & 0xff) * fx;
             v[k] = (h0 * ay + h1 * fy + 512) >> 10;
             if (GAIN) v[k] = min(max(__float2int_rn(__fmul_rn((float)v[k], c.gain)), 0), 255);   // saturate_cast<uchar>
         }

@@ -103,32 +103,59 @@ int launch_mb_tile_mask(const MbBandGeom &g, bool float_weights, int lw, int lh,
 // remap (A1) + GainCompensator::apply + convertTo(CV_16S) + copyMakeBorder, all cameras in one launch
 // (blockIdx.z = camera).  (sum w*p + 2^14) >> 15 == (v + 512) >> 10 with the 5-bit weights; OpenCV's
 // (0,0) table entry {32767,0,0,1} equals an exact copy for 8-bit data, as does {32768,0,0,0}.
+// Each thread produces MB_WARP_ROWS pixels (same column, rows 8 apart): all their table entries are
+// requested first, then all 12*ROWS byte taps, so several DRAM round trips overlap per thread.
+constexpr int MB_WARP_ROWS = 4;
+
 template <bool GAIN>
 __global__ void __launch_bounds__(256) k_mb_warp(const __grid_constant__ MbWarpArgs a)
 {
     const MbWarpCam &c = a.cam[blockIdx.z];
-    const int px = blockIdx.x * 32 + threadIdx.x, py = blockIdx.y * 8 + threadIdx.y;
-    if (px >= c.rw || py >= c.rh) return;
-    const uint2 t = __ldg(rowp<uint2>(c.table, c.tstep, py) + px);
-    const int x0 = t.x & 0xfff, x1 = (t.x >> 12) & 0xfff, fx = t.x >> 24, ax = 32 - fx;
-    const int y0 = t.y & 0xfff, y1 = (t.y >> 12) & 0xfff, fy = t.y >> 24, ay = 32 - fy;
-    const uint8_t *r0 = c.src + (size_t)y0 * c.sstep, *r1 = c.src + (size_t)y1 * c.sstep;
-    const uint8_t *p00 = r0 + x0 * 3, *p01 = r0 + x1 * 3, *p10 = r1 + x0 * 3, *p11 = r1 + x1 * 3;
-    unsigned out = 0;
+    const int px = blockIdx.x * 32 + threadIdx.x, py0 = blockIdx.y * (8 * MB_WARP_ROWS) + threadIdx.y;
+    if (px >= c.rw || py0 >= c.rh) return;
+    uint2 t[MB_WARP_ROWS];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int h0 = (int)__ldg(p00 + k) * ax + (int)__ldg(p01 + k) * fx;
-        const int h1 = (int)__ldg(p10 + k) * ax + (int)__ldg(p11 + k) * fx;
-        int v = (h0 * ay + h1 * fy + 512) >> 10;
-        if (GAIN) v = min(max(__float2int_rn(__fmul_rn((float)v, c.gain)), 0), 255);      // saturate_cast<uchar>
-        out |= (unsigned)v << (8 * k);
+    for (int r = 0; r < MB_WARP_ROWS; ++r) {
+        const int py = min(py0 + 8 * r, c.rh - 1);
+        t[r] = __ldg(rowp<uint2>(c.table, c.tstep, py) + px);
     }
-    rowp<uint32_t>(c.g0, c.gstep, py)[px] = out;
+    unsigned tap[MB_WARP_ROWS][4];                          // p00, p01, p10, p11 as packed RGB
+#pragma unroll
+    for (int r = 0; r < MB_WARP_ROWS; ++r) {
+        const int x0 = t[r].x & 0xfff, x1 = (t[r].x >> 12) & 0xfff, y0 = t[r].y & 0xfff, y1 = (t[r].y >> 12) & 0xfff;
+        const uint8_t *r0 = c.src + (size_t)y0 * c.sstep, *r1 = c.src + (size_t)y1 * c.sstep;
+        if (x1 == x0 + 1) {                                 // interior: the pair is 6 contiguous bytes
+            load_pixel_pair_8uc3(r0 + x0 * 3, tap[r][0], tap[r][1]);
+            load_pixel_pair_8uc3(r1 + x0 * 3, tap[r][2], tap[r][3]);
+        } else {                                            // BORDER_REFLECT folded the pair
+            const uint8_t *p00 = r0 + x0 * 3, *p01 = r0 + x1 * 3, *p10 = r1 + x0 * 3, *p11 = r1 + x1 * 3;
+            tap[r][0] = __ldg(p00) | (__ldg(p00 + 1) << 8) | (__ldg(p00 + 2) << 16);
+            tap[r][1] = __ldg(p01) | (__ldg(p01 + 1) << 8) | (__ldg(p01 + 2) << 16);
+            tap[r][2] = __ldg(p10) | (__ldg(p10 + 1) << 8) | (__ldg(p10 + 2) << 16);
+            tap[r][3] = __ldg(p11) | (__ldg(p11 + 1) << 8) | (__ldg(p11 + 2) << 16);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < MB_WARP_ROWS; ++r) {
+        const int py = py0 + 8 * r;
+        if (py >= c.rh) break;
+        const int fx = t[r].x >> 24, ax = 32 - fx, fy = t[r].y >> 24, ay = 32 - fy;
+        unsigned out = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int h0 = (int)((tap[r][0] >> (8 * k)) & 0xff) * ax + (int)((tap[r][1] >> (8 * k)) & 0xff) * fx;
+            const int h1 = (int)((tap[r][2] >> (8 * k)) & 0xff) * ax + (int)((tap[r][3] >> (8 * k)) & 0xff) * fx;
+            int v = (h0 * ay + h1 * fy + 512) >> 10;
+            if (GAIN) v = min(max(__float2int_rn(__fmul_rn((float)v, c.gain)), 0), 255);      // saturate_cast<uchar>
+            out |= (unsigned)v << (8 * k);
+        }
+        rowp<uint32_t>(c.g0, c.gstep, py)[px] = out;
+    }
 }
 
 int launch_mb_warp(const MbWarpArgs &a, bool apply_gain, int max_rw, int max_rh, cudaStream_t s)
 {
-    dim3 block(32, 8), grid(div_up(max_rw, 32), div_up(max_rh, 8), a.n);
+    dim3 block(32, 8), grid(div_up(max_rw, 32), div_up(max_rh, 8 * MB_WARP_ROWS), a.n);
     if (apply_gain) k_mb_warp<true><<<grid, block, 0, s>>>(a); else k_mb_warp<false><<<grid, block, 0, s>>>(a);
     SB_LAUNCHED();
     return SB_OK;
@@ -139,157 +166,249 @@ int launch_mb_warp(const MbWarpArgs &a, bool apply_gain, int max_rw, int max_rh,
 __device__ __forceinline__ unsigned lanes02(unsigned v) { return v & 0x00ff00ffu; }
 __device__ __forceinline__ unsigned lane1(unsigned v) { return (v >> 8) & 0xffu; }
 
+// Each thread produces a 2x2 block of outputs from a 7x7 window of inputs.  With x2 the thread's
+// column, the window starts at input column 4*x2 - 2: per input row one 8-byte, one 16-byte and one
+// 4-byte load, all naturally aligned and contiguous across the warp's lanes (5.25 loads per output
+// instead of 25).  Windows that cross the image edge take the BORDER_REFLECT_101 scalar path.
+__device__ __forceinline__ unsigned pd_h02(const unsigned *v) { return lanes02(v[2]) * 6u + (lanes02(v[1]) + lanes02(v[3])) * 4u + lanes02(v[0]) + lanes02(v[4]); }
+__device__ __forceinline__ unsigned pd_h1(const unsigned *v) { return lane1(v[2]) * 6u + (lane1(v[1]) + lane1(v[3])) * 4u + lane1(v[0]) + lane1(v[4]); }
+
 __global__ void __launch_bounds__(256) k_mb_pyr_down(const __grid_constant__ MbPyrArgs a)
 {
     const MbPyrCam &c = a.cam[blockIdx.z];
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    const int x2 = blockIdx.x * 32 + threadIdx.x, y2 = blockIdx.y * 8 + threadIdx.y;
     const int dw = (c.sw + 1) >> 1, dh = (c.sh + 1) >> 1;
-    if (x >= dw || y >= dh) return;
-    int xs[5];
-    const int cx = 2 * x;
-    if (cx >= 2 && cx + 2 < c.sw) { xs[0] = cx - 2; xs[1] = cx - 1; xs[2] = cx; xs[3] = cx + 1; xs[4] = cx + 2; }
-    else {
+    if (2 * x2 >= dw || 2 * y2 >= dh) return;
+    const int ix = 4 * x2 - 2, iy = 4 * y2 - 2;            // top-left of the 7x7 input window
+    const bool interior = ix >= 0 && ix + 6 < c.sw && iy >= 0 && iy + 6 < c.sh;
+    unsigned ha02[7], ha1[7], hb02[7], hb1[7];              // horizontal sums of output columns 2*x2 and 2*x2+1, per input row
 #pragma unroll
-        for (int j = 0; j < 5; ++j) xs[j] = reflect101(cx + j - 2, c.sw);
+    for (int i = 0; i < 7; ++i) {
+        unsigned v[7];
+        if (interior) {
+            const uint32_t *row = rowp<uint32_t>(c.src, c.sstep, iy + i) + ix;
+            const uint2 p = __ldg(reinterpret_cast<const uint2 *>(row));
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(row + 2));
+            v[0] = p.x; v[1] = p.y; v[2] = q.x; v[3] = q.y; v[4] = q.z; v[5] = q.w; v[6] = __ldg(row + 6);
+        } else {
+            const uint32_t *row = rowp<uint32_t>(c.src, c.sstep, reflect101(iy + i, c.sh));
+#pragma unroll
+            for (int j = 0; j < 7; ++j) v[j] = __ldg(row + reflect101(ix + j, c.sw));
+        }
+        ha02[i] = pd_h02(v); ha1[i] = pd_h1(v);
+        hb02[i] = pd_h02(v + 2); hb1[i] = pd_h1(v + 2);
     }
-    unsigned v[5][5];
+    // vertical: <= 256*255 = 65280 (+128) per 16-bit lane, no carry between lanes; (s + 128) >> 8
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const uint32_t *row = rowp<uint32_t>(c.src, c.sstep, reflect101(2 * y + i - 2, c.sh));
-#pragma unroll
-        for (int j = 0; j < 5; ++j) v[i][j] = __ldg(row + xs[j]);
+    for (int oy = 0; oy < 2; ++oy) {
+        const int y = 2 * y2 + oy;
+        if (y >= dh) break;
+        const unsigned *A02 = ha02 + 2 * oy, *A1 = ha1 + 2 * oy, *B02 = hb02 + 2 * oy, *B1 = hb1 + 2 * oy;
+        const unsigned sa02 = A02[2] * 6u + (A02[1] + A02[3]) * 4u + A02[0] + A02[4] + 0x00800080u;
+        const unsigned sa1 = A1[2] * 6u + (A1[1] + A1[3]) * 4u + A1[0] + A1[4] + 128u;
+        const unsigned sb02 = B02[2] * 6u + (B02[1] + B02[3]) * 4u + B02[0] + B02[4] + 0x00800080u;
+        const unsigned sb1 = B1[2] * 6u + (B1[1] + B1[3]) * 4u + B1[0] + B1[4] + 128u;
+        const unsigned oa = ((sa02 >> 8) & 0x00ff00ffu) | ((sa1 >> 8) << 8), ob = ((sb02 >> 8) & 0x00ff00ffu) | ((sb1 >> 8) << 8);
+        uint32_t *d = rowp<uint32_t>(c.dst, c.dstep, y) + 2 * x2;
+        if (2 * x2 + 1 < dw) *reinterpret_cast<uint2 *>(d) = make_uint2(oa, ob);
+        else *d = oa;
     }
-    unsigned h02[5], h1[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {       // row = s2*6 + (s1+s3)*4 + s0 + s4, <= 16*255 per lane
-        h02[i] = lanes02(v[i][2]) * 6u + (lanes02(v[i][1]) + lanes02(v[i][3])) * 4u + lanes02(v[i][0]) + lanes02(v[i][4]);
-        h1[i] = lane1(v[i][2]) * 6u + (lane1(v[i][1]) + lane1(v[i][3])) * 4u + lane1(v[i][0]) + lane1(v[i][4]);
-    }
-    // <= 256*255 = 65280 per lane: no carry between the lanes; (s + 128) >> 8 per lane
-    const unsigned s02 = h02[2] * 6u + (h02[1] + h02[3]) * 4u + h02[0] + h02[4] + 0x00800080u;
-    const unsigned s1 = h1[2] * 6u + (h1[1] + h1[3]) * 4u + h1[0] + h1[4] + 128u;
-    // lane sums can reach 65280 + 128 = 65408 < 65536
-    const unsigned out = ((s02 >> 8) & 0x00ff00ffu) | ((s1 >> 8) << 8);
-    rowp<uint32_t>(c.dst, c.dstep, y)[x] = out;
 }
 
 int launch_mb_pyr_down(const MbPyrArgs &a, int max_dw, int max_dh, cudaStream_t s)
 {
-    dim3 block(32, 8), grid(div_up(max_dw, 32), div_up(max_dh, 8), a.n);
+    dim3 block(32, 8), grid(div_up(div_up(max_dw, 2), 32), div_up(div_up(max_dh, 2), 8), a.n);
     k_mb_pyr_down<<<grid, block, 0, s>>>(a);
     SB_LAUNCHED();
     return SB_OK;
 }
 
 // ------------------------------------------------------------------------------------ K3: one band
-// pyrUp(coarse)(y, x) for RGBX bytes, channels {0,2} packed + channel 1; value before the cast (<= 64*255)
-struct Up3 { unsigned s02, s1; };
-__device__ __forceinline__ Up3 pyr_up_rgbx(const uint32_t *coarse, size_t cstep, int cw, int ch, int y, int x)
-{
-    const int cx = x >> 1, cy = y >> 1;
-    const int xl = cx == 0 ? (cw > 1 ? 1 : 0) : cx - 1, xr = min(cx + 1, cw - 1);
-    const int yt = cy == 0 ? (ch > 1 ? 1 : 0) : cy - 1, yb = min(cy + 1, ch - 1);
-    const uint32_t *r0 = rowp<uint32_t>(coarse, cstep, yt), *r1 = rowp<uint32_t>(coarse, cstep, cy), *r2 = rowp<uint32_t>(coarse, cstep, yb);
-    const unsigned a0 = __ldg(r0 + xl), b0 = __ldg(r0 + cx), c0 = __ldg(r0 + xr);
-    const unsigned a1 = __ldg(r1 + xl), b1 = __ldg(r1 + cx), c1 = __ldg(r1 + xr);
-    const unsigned a2 = __ldg(r2 + xl), b2 = __ldg(r2 + cx), c2 = __ldg(r2 + xr);
-    unsigned h0_02, h1_02, h2_02, h0_1, h1_1, h2_1;
-    if (x & 1) {
-        h0_02 = (lanes02(b0) + lanes02(c0)) * 4u; h1_02 = (lanes02(b1) + lanes02(c1)) * 4u; h2_02 = (lanes02(b2) + lanes02(c2)) * 4u;
-        h0_1 = (lane1(b0) + lane1(c0)) * 4u; h1_1 = (lane1(b1) + lane1(c1)) * 4u; h2_1 = (lane1(b2) + lane1(c2)) * 4u;
-    } else {
-        h0_02 = lanes02(a0) + lanes02(b0) * 6u + lanes02(c0); h1_02 = lanes02(a1) + lanes02(b1) * 6u + lanes02(c1); h2_02 = lanes02(a2) + lanes02(b2) * 6u + lanes02(c2);
-        h0_1 = lane1(a0) + lane1(b0) * 6u + lane1(c0); h1_1 = lane1(a1) + lane1(b1) * 6u + lane1(c1); h2_1 = lane1(a2) + lane1(b2) * 6u + lane1(c2);
-    }
-    Up3 u;
-    if (y & 1) { u.s02 = (h1_02 + h2_02) * 4u; u.s1 = (h1_1 + h2_1) * 4u; }
-    else { u.s02 = h1_02 * 6u + h0_02 + h2_02; u.s1 = h1_1 * 6u + h0_1 + h2_1; }
-    return u;
-}
-
+// Each thread owns a 2x2 block of band pixels (X0, Y0 even).  For l < n every feed rect is aligned to
+// even coordinates at level l (blenders.cpp:252-253 snaps to 2^num_bands), so the block shares ONE
+// 3x3 neighbourhood of the coarser level: pyrUp (Appendix A3) gives
+//   even = s(-1) + 6 s(0) + s(+1)     odd = 4 (s(0) + s(+1))
+// with reflect-101 on the left/top and replicate on the right/bottom, 9 taps for 4 outputs.
 __device__ __forceinline__ int mb_weighted(int lap, float w) { return __float2int_rz(__fmul_rn((float)lap, w)); }   // |lap*w| < 2^31: no x86 indefinite
 __device__ __forceinline__ int mb_weighted(int lap, short w) { return (int)(short)((lap * (int)w) >> 8); }
 
-// restored coarser band (CV_16SC4 storage: 3 channels + pad), pyrUp value before the cast, per channel
-__device__ __forceinline__ void pyr_up_s16x4(const short4 *coarse, size_t cstep, int cw, int ch, int y, int x, int up[3])
+struct Nbr { int l, c, r; };                                // coarse neighbour indices along one axis
+__device__ __forceinline__ Nbr nbr_of(int c, int n)
 {
-    const int cx = x >> 1, cy = y >> 1;
-    const int xl = cx == 0 ? (cw > 1 ? 1 : 0) : cx - 1, xr = min(cx + 1, cw - 1);
-    const int yt = cy == 0 ? (ch > 1 ? 1 : 0) : cy - 1, yb = min(cy + 1, ch - 1);
-    const short4 *r0 = rowp<short4>(coarse, cstep, yt), *r1 = rowp<short4>(coarse, cstep, cy), *r2 = rowp<short4>(coarse, cstep, yb);
-    const short4 a0 = __ldg(r0 + xl), b0 = __ldg(r0 + cx), c0 = __ldg(r0 + xr);
-    const short4 a1 = __ldg(r1 + xl), b1 = __ldg(r1 + cx), c1 = __ldg(r1 + xr);
-    const short4 a2 = __ldg(r2 + xl), b2 = __ldg(r2 + cx), c2 = __ldg(r2 + xr);
-#define SB_H(A, B, C, F) ((x & 1) ? ((int)B.F + (int)C.F) * 4 : (int)A.F + (int)B.F * 6 + (int)C.F)
-#define SB_V(F) ((y & 1) ? (SB_H(a1, b1, c1, F) + SB_H(a2, b2, c2, F)) * 4 : SB_H(a1, b1, c1, F) * 6 + SB_H(a0, b0, c0, F) + SB_H(a2, b2, c2, F))
-    up[0] = SB_V(x); up[1] = SB_V(y); up[2] = SB_V(z);
-#undef SB_V
-#undef SB_H
+    Nbr k;
+    k.c = c; k.l = c == 0 ? (n > 1 ? 1 : 0) : c - 1; k.r = min(c + 1, n - 1);
+    return k;
 }
 
 template <typename WT, bool NOT_TOP, bool FINAL, bool OUT8>
 __global__ void __launch_bounds__(256) k_mb_band(const __grid_constant__ MbBandArgs a)
 {
-    const int X = blockIdx.x * 32 + threadIdx.x, Y = blockIdx.y * 8 + threadIdx.y;
+    // block = 32 x 8 threads = 64 x 16 band pixels = 2 x 2 mask tiles of 32 x 8
+    const int X0 = (blockIdx.x * 32 + threadIdx.x) * 2, Y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
     const int lw = FINAL ? a.out_w : a.g.lw, lh = FINAL ? a.out_h : a.g.lh;       // band 0 is cropped to dst_roi_final_
-    if (X >= lw || Y >= lh) return;
-    uint32_t cams = __ldg(a.tile_mask + blockIdx.y * a.tiles_x + blockIdx.x);     // block-uniform
-    const WT ws = __ldg(rowp<WT>(a.wsum, a.wsum_step, Y) + X);
-    int up_r[3] = {0, 0, 0};
-    if (NOT_TOP) pyr_up_s16x4(a.coarse_r, a.coarse_r_step, a.g.lw >> 1, a.g.lh >> 1, Y, X, up_r);
-    int acc0 = 0, acc1 = 0, acc2 = 0;
+    if (X0 >= lw || Y0 >= lh) return;
+    uint32_t cams = __ldg(a.tile_mask + (Y0 >> 3) * a.tiles_x + (X0 >> 5));       // the 2x2 block lies inside one 32x8 mask tile
+
+    int acc[2][2][3];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) acc[j][i][0] = acc[j][i][1] = acc[j][i][2] = 0;
+
     for (; cams; cams &= cams - 1) {
         const MbBandCam &c = a.g.cam[__ffs(cams) - 1];
-        const int x = X - c.rx, y = Y - c.ry;
-        if ((unsigned)x >= (unsigned)c.rw || (unsigned)y >= (unsigned)c.rh) continue;
-        const WT w = __ldg(rowp<WT>(c.weight, c.wstep, y) + x);
-        const unsigned g = __ldg(rowp<uint32_t>(c.fine, c.fstep, y) + x);
-        int l0 = g & 0xff, l1 = (g >> 8) & 0xff, l2 = (g >> 16) & 0xff;
+        const int x = X0 - c.rx, y = Y0 - c.ry;
+        if (x + 1 < 0 || y + 1 < 0 || x >= c.rw || y >= c.rh) continue;   // (for l < n rects are even-aligned and even-sized)
+        WT w[2][2];
+        unsigned g[2][2];
         if (NOT_TOP) {
-            const Up3 u = pyr_up_rgbx(c.coarse, c.cstep, c.rw >> 1, c.rh >> 1, y, x);
-            const unsigned u02 = ((u.s02 + 0x00200020u) >> 6) & 0x03ff03ffu;      // (v + 32) >> 6 per lane, <= 255
-            l0 -= (int)(u02 & 0xffffu); l2 -= (int)(u02 >> 16); l1 -= (int)((u.s1 + 32u) >> 6);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const WT *wr = rowp<WT>(c.weight, c.wstep, y + j) + x;
+                const uint2 gg = __ldg(reinterpret_cast<const uint2 *>(rowp<uint32_t>(c.fine, c.fstep, y + j) + x));
+                g[j][0] = gg.x; g[j][1] = gg.y;
+                w[j][0] = __ldg(wr); w[j][1] = __ldg(wr + 1);
+            }
+        } else {     // top level: rect corners may be odd, sizes may be odd
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const bool in = (unsigned)(x + i) < (unsigned)c.rw && (unsigned)(y + j) < (unsigned)c.rh;
+                    w[j][i] = in ? __ldg(rowp<WT>(c.weight, c.wstep, y + j) + x + i) : (WT)0;
+                    g[j][i] = in ? __ldg(rowp<uint32_t>(c.fine, c.fstep, y + j) + x + i) : 0u;
+                }
         }
-        if (w == (WT)0) continue;                          // short(lap * 0) == 0 and (lap * 0) >> 8 == 0
-        acc0 += mb_weighted(l0, w); acc1 += mb_weighted(l1, w); acc2 += mb_weighted(l2, w);
+        if (w[0][0] == (WT)0 && w[0][1] == (WT)0 && w[1][0] == (WT)0 && w[1][1] == (WT)0) continue;
+        unsigned u02[2][2] = {{0u, 0u}, {0u, 0u}}, u1[2][2] = {{0u, 0u}, {0u, 0u}};
+        if (NOT_TOP) {
+            const int cw = c.rw >> 1, ch = c.rh >> 1;
+            const Nbr kx = nbr_of(x >> 1, cw), ky = nbr_of(y >> 1, ch);
+            const int rows[3] = {ky.l, ky.c, ky.r};
+            unsigned e02[3], o02[3], e1[3], o1[3];          // horizontal even / odd sums per coarse row
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const uint32_t *cr = rowp<uint32_t>(c.coarse, c.cstep, rows[r]);
+                const unsigned ta = __ldg(cr + kx.l), tb = __ldg(cr + kx.c), tc = __ldg(cr + kx.r);
+                const unsigned a02 = lanes02(ta), b02 = lanes02(tb), c02 = lanes02(tc), a1 = lane1(ta), b1 = lane1(tb), c1 = lane1(tc);
+                e02[r] = a02 + b02 * 6u + c02; o02[r] = (b02 + c02) * 4u;
+                e1[r] = a1 + b1 * 6u + c1;     o1[r] = (b1 + c1) * 4u;
+            }
+            // vertical: even row = r0 + 6 r1 + r2, odd row = 4 (r1 + r2); <= 64 * 255 per 16-bit lane; then (v + 32) >> 6
+            u02[0][0] = (((e02[0] + e02[1] * 6u + e02[2]) + 0x00200020u) >> 6) & 0x03ff03ffu;
+            u02[0][1] = (((o02[0] + o02[1] * 6u + o02[2]) + 0x00200020u) >> 6) & 0x03ff03ffu;
+            u02[1][0] = ((((e02[1] + e02[2]) * 4u) + 0x00200020u) >> 6) & 0x03ff03ffu;
+            u02[1][1] = ((((o02[1] + o02[2]) * 4u) + 0x00200020u) >> 6) & 0x03ff03ffu;
+            u1[0][0] = ((e1[0] + e1[1] * 6u + e1[2]) + 32u) >> 6;
+            u1[0][1] = ((o1[0] + o1[1] * 6u + o1[2]) + 32u) >> 6;
+            u1[1][0] = (((e1[1] + e1[2]) * 4u) + 32u) >> 6;
+            u1[1][1] = (((o1[1] + o1[2]) * 4u) + 32u) >> 6;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (w[j][i] == (WT)0) continue;              // short(lap * 0) == 0 and (lap * 0) >> 8 == 0
+                const int l0 = (int)(g[j][i] & 0xff) - (int)(u02[j][i] & 0xffffu);
+                const int l1 = (int)((g[j][i] >> 8) & 0xff) - (int)u1[j][i];
+                const int l2 = (int)((g[j][i] >> 16) & 0xff) - (int)(u02[j][i] >> 16);
+                acc[j][i][0] += mb_weighted(l0, w[j][i]); acc[j][i][1] += mb_weighted(l1, w[j][i]); acc[j][i][2] += mb_weighted(l2, w[j][i]);
+            }
     }
-    // normalizeUsingWeightMap (blenders.cpp:383-424) on the wrapped 16-bit sums
-    int v0, v1, v2;
-    bool masked;
-    if (sizeof(WT) == 4) {
-        const float wf = (float)ws;
-        masked = wf > SB_WEIGHT_EPS;
-        const SharedDiv div(__fadd_rn(wf, SB_WEIGHT_EPS));          // [1e-5, n + 1e-5]: fast-path range
-        v0 = trunc_short(div((float)(short)acc0)); v1 = trunc_short(div((float)(short)acc1)); v2 = trunc_short(div((float)(short)acc2));
-    } else {
-        const int wi = (int)ws + 1;
-        masked = (int)ws > 0;
-        v0 = wi ? (short)((((int)(short)acc0) << 8) / wi) : 0; v1 = wi ? (short)((((int)(short)acc1) << 8) / wi) : 0;
-        v2 = wi ? (short)((((int)(short)acc2) << 8) / wi) : 0;
+
+    // restored coarser band: pyrUp per channel on CV_16S values (short4 pixels), shared 3x3 neighbourhood
+    int up[2][2][3];
+    if (NOT_TOP) {
+        const int cw = a.g.lw >> 1, ch = a.g.lh >> 1;
+        const Nbr kx = nbr_of(X0 >> 1, cw), ky = nbr_of(Y0 >> 1, ch);
+        const int rows[3] = {ky.l, ky.c, ky.r};
+        int e[3][3], o[3][3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const short4 *cr = rowp<short4>(a.coarse_r, a.coarse_r_step, rows[r]);
+            const short4 ta = __ldg(cr + kx.l), tb = __ldg(cr + kx.c), tc = __ldg(cr + kx.r);
+            e[r][0] = ta.x + tb.x * 6 + tc.x; o[r][0] = (tb.x + tc.x) * 4;
+            e[r][1] = ta.y + tb.y * 6 + tc.y; o[r][1] = (tb.y + tc.y) * 4;
+            e[r][2] = ta.z + tb.z * 6 + tc.z; o[r][2] = (tb.z + tc.z) * 4;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            up[0][0][k] = sat_s16((e[0][k] + e[1][k] * 6 + e[2][k] + 32) >> 6);
+            up[0][1][k] = sat_s16((o[0][k] + o[1][k] * 6 + o[2][k] + 32) >> 6);
+            up[1][0][k] = sat_s16(((e[1][k] + e[2][k]) * 4 + 32) >> 6);
+            up[1][1][k] = sat_s16(((o[1][k] + o[2][k]) * 4 + 32) >> 6);
+        }
     }
-    if (NOT_TOP) {   // restoreImageFromLaplacePyr: add(pyrUp(pyr[i+1]), pyr[i]) saturates
-        v0 = sat_s16(sat_s16((up_r[0] + 32) >> 6) + v0); v1 = sat_s16(sat_s16((up_r[1] + 32) >> 6) + v1);
-        v2 = sat_s16(sat_s16((up_r[2] + 32) >> 6) + v2);
-    }
-    if (FINAL) {
-        if (!masked) v0 = v1 = v2 = 0;                     // Blender::blend: dst_.setTo(0, dst_mask_ == 0)
-        if (OUT8) {
-            uint8_t *o = rowp<uint8_t>(a.out, a.out_step, Y) + X * 3;
-            o[0] = (uint8_t)sat_u8(v0); o[1] = (uint8_t)sat_u8(v1); o[2] = (uint8_t)sat_u8(v2);   // result.convertTo(CV_8U)
+
+    // normalizeUsingWeightMap (blenders.cpp:383-424) on the wrapped 16-bit sums, collapse add, output
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int Y = Y0 + j;
+        if (Y >= lh) break;
+        int v[2][3];
+        bool masked[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int X = X0 + i;
+            const WT ws = X < lw ? __ldg(rowp<WT>(a.wsum, a.wsum_step, Y) + X) : (WT)0;
+            if (sizeof(WT) == 4) {
+                const float wf = (float)ws;
+                masked[i] = wf > SB_WEIGHT_EPS;
+                const SharedDiv div(__fadd_rn(wf, SB_WEIGHT_EPS));      // [1e-5, n + 1e-5]: fast-path range
+#pragma unroll
+                for (int k = 0; k < 3; ++k) v[i][k] = trunc_short(div((float)(short)acc[j][i][k]));
+            } else {
+                const int wi = (int)ws + 1;
+                masked[i] = (int)ws > 0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) v[i][k] = wi ? (short)((((int)(short)acc[j][i][k]) << 8) / wi) : 0;
+            }
+            if (NOT_TOP) {   // restoreImageFromLaplacePyr: add(pyrUp(pyr[i+1]), pyr[i]) saturates
+#pragma unroll
+                for (int k = 0; k < 3; ++k) v[i][k] = sat_s16(up[j][i][k] + v[i][k]);
+            }
+            if (FINAL && !masked[i]) v[i][0] = v[i][1] = v[i][2] = 0;   // Blender::blend: dst_.setTo(0, dst_mask_ == 0)
+        }
+        const bool two = X0 + 1 < lw;
+        if (FINAL) {
+            if (OUT8) {      // result.convertTo(CV_8U); 2 px = 6 bytes at an even byte offset: three 16-bit stores
+                uint8_t *o = rowp<uint8_t>(a.out, a.out_step, Y) + X0 * 3;
+                const int b0 = sat_u8(v[0][0]), b1 = sat_u8(v[0][1]), b2 = sat_u8(v[0][2]);
+                if (two && ((reinterpret_cast<uintptr_t>(o) & 1) == 0)) {
+                    const int b3 = sat_u8(v[1][0]), b4 = sat_u8(v[1][1]), b5 = sat_u8(v[1][2]);
+                    unsigned short *q = reinterpret_cast<unsigned short *>(o);
+                    q[0] = (unsigned short)(b0 | (b1 << 8)); q[1] = (unsigned short)(b2 | (b3 << 8)); q[2] = (unsigned short)(b4 | (b5 << 8));
+                } else {
+                    o[0] = (uint8_t)b0; o[1] = (uint8_t)b1; o[2] = (uint8_t)b2;
+                    if (two) { o[3] = (uint8_t)sat_u8(v[1][0]); o[4] = (uint8_t)sat_u8(v[1][1]); o[5] = (uint8_t)sat_u8(v[1][2]); }
+                }
+            } else {
+                short *o = rowp<short>(a.out, a.out_step, Y) + X0 * 3;
+                o[0] = (short)v[0][0]; o[1] = (short)v[0][1]; o[2] = (short)v[0][2];
+                if (two) { o[3] = (short)v[1][0]; o[4] = (short)v[1][1]; o[5] = (short)v[1][2]; }
+            }
+            if (a.out_mask) {
+                uint8_t *m = a.out_mask + (size_t)Y * a.mask_step + X0;
+                m[0] = masked[0] ? 255 : 0;
+                if (two) m[1] = masked[1] ? 255 : 0;
+            }
         } else {
-            short *o = rowp<short>(a.out, a.out_step, Y) + X * 3;
-            o[0] = (short)v0; o[1] = (short)v1; o[2] = (short)v2;
+            short4 *o = rowp<short4>(a.out, a.out_step, Y) + X0;
+            if (two) {
+                uint4 pk;
+                pk.x = (unsigned)(v[0][0] & 0xffff) | ((unsigned)v[0][1] << 16); pk.y = (unsigned)(v[0][2] & 0xffff);
+                pk.z = (unsigned)(v[1][0] & 0xffff) | ((unsigned)v[1][1] << 16); pk.w = (unsigned)(v[1][2] & 0xffff);
+                *reinterpret_cast<uint4 *>(o) = pk;
+            } else
+                o[0] = make_short4((short)v[0][0], (short)v[0][1], (short)v[0][2], 0);
         }
-        if (a.out_mask) a.out_mask[(size_t)Y * a.mask_step + X] = masked ? 255 : 0;
-    } else {
-        rowp<short4>(a.out, a.out_step, Y)[X] = make_short4((short)v0, (short)v1, (short)v2, 0);
     }
 }
 
 int launch_mb_band(const MbBandArgs &a, bool float_weights, bool not_top, bool final_band, bool out8, cudaStream_t s)
 {
     const int lw = final_band ? a.out_w : a.g.lw, lh = final_band ? a.out_h : a.g.lh;
-    dim3 block(32, 8), grid(div_up(lw, 32), div_up(lh, 8));
+    dim3 block(32, 8), grid(div_up(lw, 64), div_up(lh, 16));
     SB_ASSERT(div_up(a.g.lw, 32) == a.tiles_x);
 #define SB_MB(WT, NT, FIN, O8) k_mb_band<WT, NT, FIN, O8><<<grid, block, 0, s>>>(a)
 #define SB_MB_W(WT)                                                                          \
