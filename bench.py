@@ -106,6 +106,8 @@ def run_ours(args):
     n, size = spec["n_used"], (spec["W"], spec["H"])
     comp = sv.Compositor(size, Ks, Rs, warper=spec["warper"], scale=spec["scale"], blender=spec["blender"], num_bands=5,
                          weight_type=sv.CV_32F, sharpness=0.02, gains=spec["gain_values"], output_type=sv.CV_8UC3, device=local)
+    if args.variant is not None:
+        comp.set_fused(10 + args.variant)      # kernel variant of the fused path (tuning hook)
     pw, ph = comp.pano_size
     n_sets = args.frame_sets
     host_sets = make_frames(args.workload, n_sets, n, rank)
@@ -338,6 +340,7 @@ def main():
     ap.add_argument("--profile-frames", type=int, default=5)
     ap.add_argument("--cpu-frames", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", type=int, default=None, choices=[0, 1], help="fused kernel variant (default: library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -36,11 +36,12 @@ struct Camera {
     std::vector<DevImage> w_pyr; // weight pyramid (sequence-constant)
     DevImage feather_w;          // feather weight map (sequence-constant)
     DevBuf feather_table;        // fixed-point map + distance, 8 B per warped pixel (sequence-constant)
-    DevBuf feather_bbox;         // per panorama tile: source bounding box of this camera's samples
     DevBuf mb_table;             // multi-band fast path: resolved bilinear taps per padded-rect pixel (8 B)
     size_t mb_tstep = 0;
     size_t feather_tstep = 0;
-    int feather_tpad = 0;
+    DevBuf feather_tiles;        // the same table tile-major (one 8 KB block per 128x8 panorama tile) for the streaming kernel
+    DevBuf feather_rec;          // per tile block: source box record
+    int ftx0 = 0, fty0 = 0, fntx = 0, fnty = 0;
     // panorama(-level) column ranges that hold non-zero weights, per level: [s0,s1) U [s2,s3)
     std::vector<std::array<int, 4>> spans;
 };
@@ -95,7 +96,12 @@ struct sb_compositor {
     int next_slot = 0;
     cudaStream_t setup_stream = nullptr;
     cudaEvent_t marks[2] = {nullptr, nullptr};
-    int feather_variant = 1;
+    bool feather_fast = false;                   // every weighted pixel's taps fit the resolved-tap table
+    bool feather_tma = false;                    // <= SB_FTT_MAXC cameras per 128x8 tile: persistent table-streaming kernel
+    int feather_variant = 1;                     // 1: k_feather_tma, 0: k_feather_fused_px1
+    DevBuf tma_desc;                             // per 128x8 panorama tile: camera slots + source boxes
+    int sm_count = 148;
+    DevBuf bilin_lut;                            // 1024 x uint2 bilinear product weights (sb_device.cuh)
     int mb_variant = 1;                          // 1: RGBX fast path, 0: CV_16S band kernels
     bool mb_fast = false;                        // RGBX pyramid + tap-table path available (sources <= 4096 px)
     std::vector<DevBuf> mb_tile_mask;            // per band: per 32x8 tile bitmask of contributing cameras
@@ -196,6 +202,8 @@ int setup(sb_compositor *c)
     const int n = cfg.n_cameras;
     c->cams.resize(n);
     int tlx = INT32_MAX, tly = INT32_MAX, brx = INT32_MIN, bry = INT32_MIN;
+    SB_TRY(c->bilin_lut.ensure(1024 * sizeof(uint2)));
+    SB_TRY(launch_build_bilin_lut(static_cast<uint2 *>(c->bilin_lut.p), s));
     DevImage ones, xmap, ymap;
     SB_TRY(ones.create(cfg.src_size.height, cfg.src_size.width, SB_8UC1));
     SB_CUDA(cudaMemset2DAsync(ones.v.data, ones.v.step, 255, ones.v.cols, ones.v.rows, s));
@@ -323,32 +331,58 @@ int setup(sb_compositor *c)
             Camera &cam = c->cams[i];
             SB_TRY(cam.feather_w.create(cam.wh, cam.ww, SB_32FC1));
             SB_TRY(launch_distance_l1(cam.mask.v, cam.feather_w.v, scratch, s));
-            // rows padded by (dx mod 4) entries in front and 4 behind: quads aligned to the panorama load as 2 x 16 B
-            cam.feather_tpad = (((cam.tl.x - roi.x) % 4) + 4) % 4;
-            cam.feather_tstep = ((size_t)(cam.ww + cam.feather_tpad + 4) * sizeof(uint2) + 255) & ~(size_t)255;
+            cam.feather_tstep = ((size_t)cam.ww * sizeof(uint2) + 255) & ~(size_t)255;
             SB_TRY(cam.feather_table.ensure(cam.feather_tstep * cam.wh));
-            SB_CUDA(cudaMemsetAsync(cam.feather_table.p, 0, cam.feather_tstep * cam.wh, s));
-            SB_TRY(launch_build_feather_table(cam.proj, cam.tl.x, cam.tl.y, cam.feather_w.v, static_cast<uint2 *>(cam.feather_table.p), cam.feather_tstep, cam.feather_tpad, s));
+            SB_TRY(launch_build_feather_table(cam.proj, cam.tl.x, cam.tl.y, cam.feather_w.v, cfg.src_size.width, cfg.src_size.height,
+                                              static_cast<uint2 *>(cam.feather_table.p), cam.feather_tstep, s));
             SB_TRY(launch_weight_from_dist(cam.feather_w.v, cfg.sharpness, s));
             SB_TRY(launch_weight_accumulate(cam.feather_w.v, c->wsum[0].v, cam.tl.x - roi.x, cam.tl.y - roi.y, s));
             cam.spans.emplace_back();
             SB_TRY(weight_spans(cam.feather_w.v, cam.tl.x - roi.x, scratch, s, &cam.spans.back()));
         }
-        // per (panorama tile, camera): the source box the tile's non-zero-weight samples touch
+        // per panorama tile: which cameras carry weight there
         const int tiles_x = div_up(roi.width, SB_FT_W), tiles_y = div_up(roi.height, SB_FT_H);
+        SB_TRY(c->tile_cams.ensure(sizeof(uint32_t) * ((size_t)tiles_x * tiles_y + 1)));
+        SB_CUDA(cudaMemsetAsync(c->tile_cams.p, 0, sizeof(uint32_t) * ((size_t)tiles_x * tiles_y + 1), s));
+        unsigned *bad = static_cast<unsigned *>(c->tile_cams.p) + (size_t)tiles_x * tiles_y;
         for (int i = 0; i < n; ++i) {
             Camera &cam = c->cams[i];
-            SB_TRY(cam.feather_bbox.ensure(sizeof(int4) * (size_t)tiles_x * tiles_y));
             FeatherCam fc{};
-            fc.sw = cfg.src_size.width; fc.sh = cfg.src_size.height;
-            fc.table = static_cast<const uint2 *>(cam.feather_table.p); fc.tstep = cam.feather_tstep; fc.tpad = cam.feather_tpad;
+            fc.table = static_cast<const uint2 *>(cam.feather_table.p); fc.tstep = cam.feather_tstep;
             fc.ww = cam.ww; fc.wh = cam.wh; fc.dx = cam.tl.x - roi.x; fc.dy = cam.tl.y - roi.y;
-            SB_TRY(launch_feather_tile_bbox(fc, roi.width, roi.height, static_cast<int4 *>(cam.feather_bbox.p), s));
-            if (i == 0) {
-                SB_TRY(c->tile_cams.ensure(sizeof(uint32_t) * (size_t)tiles_x * tiles_y));
-                SB_CUDA(cudaMemsetAsync(c->tile_cams.p, 0, sizeof(uint32_t) * (size_t)tiles_x * tiles_y, s));
+            SB_TRY(launch_feather_tile_cams(fc, i, roi.width, roi.height, static_cast<uint32_t *>(c->tile_cams.p), bad, s));
+        }
+        unsigned h_bad = 1;
+        SB_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof h_bad, cudaMemcpyDeviceToHost, s));
+        SB_CUDA(cudaStreamSynchronize(s));
+        c->feather_fast = h_bad == 0 && cfg.src_size.width <= 8192 && cfg.src_size.height <= 8192;
+        if (c->feather_fast) {   // tile-major tables, source boxes and per-tile descriptors for the streaming kernel
+            FtsSetup ta{};
+            ta.n = n;
+            ta.tiles_x = div_up(roi.width, SB_FTT_W);
+            ta.n_tiles = ta.tiles_x * div_up(roi.height, SB_FTT_H);
+            for (int i = 0; i < n; ++i) {
+                Camera &cam = c->cams[i];
+                const int dx = cam.tl.x - roi.x, dy = cam.tl.y - roi.y;
+                cam.ftx0 = dx / SB_FTT_W; cam.fty0 = dy / SB_FTT_H;
+                cam.fntx = div_up(dx + cam.ww, SB_FTT_W) - cam.ftx0; cam.fnty = div_up(dy + cam.wh, SB_FTT_H) - cam.fty0;
+                SB_TRY(cam.feather_tiles.ensure(sizeof(uint2) * SB_FTT_W * SB_FTT_H * (size_t)cam.fntx * cam.fnty));
+                SB_TRY(cam.feather_rec.ensure(sizeof(uint4) * (size_t)cam.fntx * cam.fnty));
+                SB_TRY(launch_fts_camera_tiles(static_cast<const uint2 *>(cam.feather_table.p), cam.feather_tstep, cam.ww, cam.wh, dx, dy,
+                                               cam.ftx0, cam.fty0, cam.fntx, cam.fnty, static_cast<uint4 *>(cam.feather_rec.p),
+                                               static_cast<uint2 *>(cam.feather_tiles.p), s));
+                ta.cam[i].rec = static_cast<const uint4 *>(cam.feather_rec.p);
+                ta.cam[i].tx0 = cam.ftx0; ta.cam[i].ty0 = cam.fty0; ta.cam[i].ntx = cam.fntx; ta.cam[i].nty = cam.fnty;
             }
-            SB_TRY(launch_feather_tile_mask(static_cast<const int4 *>(cam.feather_bbox.p), tiles_x * tiles_y, i, static_cast<uint32_t *>(c->tile_cams.p), s));
+            SB_TRY(c->tma_desc.ensure(sizeof(uint4) * (1 + SB_FTT_MAXC) * (size_t)ta.n_tiles + 16));
+            int *status = reinterpret_cast<int *>(static_cast<uint4 *>(c->tma_desc.p) + (size_t)(1 + SB_FTT_MAXC) * ta.n_tiles);
+            SB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), s));
+            SB_TRY(launch_fts_descriptors(ta, static_cast<uint4 *>(c->tma_desc.p), status, s));
+            int h_status = 1;
+            SB_CUDA(cudaMemcpyAsync(&h_status, status, sizeof h_status, cudaMemcpyDeviceToHost, s));
+            SB_CUDA(cudaStreamSynchronize(s));
+            c->feather_tma = h_status == 0 && n <= 16;
+            SB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
         }
         SB_CUDA(cudaStreamSynchronize(s));
     }
@@ -384,6 +418,7 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
         {   // K1: remap + gain + convertTo(16S) + copyMakeBorder for every camera, one launch
             MbWarpArgs a{};
             a.n = n;
+            a.bilin_lut = static_cast<const uint2 *>(c->bilin_lut.p);
             double bytes = 0;
             int mw = 0, mh = 0;
             for (int i = 0; i < n; ++i) {
@@ -490,31 +525,54 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
             PROF(fin ? "band_fused_final" : "band_fused", bytes,
                  launch_band_fused(a, cfg.weight_type == SB_32F, l < nb, fin, s.out.v.type == SB_8UC3, st));
         }
-    } else if (cfg.blender_kind == SB_BLEND_FEATHER && c->fused && cfg.sharpness > 0.f) {
-        FeatherFusedArgs a{};
-        a.n = n;
+    } else if (cfg.blender_kind == SB_BLEND_FEATHER && c->fused && c->feather_fast && cfg.sharpness > 0.f) {
         double bytes = 0;
         for (int i = 0; i < n; ++i) {
-            const Camera &cam = c->cams[i];
-            FeatherCam &fc = a.cam[i];
-            fc.src = src[i].ptr<uint8_t>(); fc.sstep = src[i].step; fc.sw = src[i].cols; fc.sh = src[i].rows;
-            fc.table = static_cast<const uint2 *>(cam.feather_table.p); fc.tstep = cam.feather_tstep; fc.tpad = cam.feather_tpad;
-            fc.ww = cam.ww; fc.wh = cam.wh; fc.dx = cam.tl.x - c->dst_roi.x; fc.dy = cam.tl.y - c->dst_roi.y;
-            fc.gain = cam.gain;
-            fc.bbox = static_cast<const int4 *>(cam.feather_bbox.p);
-            const auto &sp = cam.spans[0];
+            const auto &sp = c->cams[i].spans[0];
             // source gathered ~once; table entries (8 B) read inside the non-zero-weight column spans
-            bytes += img_bytes(src[i]) + 8.0 * cam.wh * ((sp[1] - sp[0]) + (sp[3] - sp[2]));
+            bytes += img_bytes(src[i]) + 8.0 * c->cams[i].wh * ((sp[1] - sp[0]) + (sp[3] - sp[2]));
         }
-        a.tiles_x = div_up(s.out.v.cols, SB_FT_W);
-        a.sharpness = cfg.sharpness;
-        a.variant = c->feather_variant;
-        a.tile_cams = static_cast<const uint32_t *>(c->tile_cams.p);
-        a.out = s.out.v.data; a.out_step = s.out.v.step;
-        a.out_mask = s.want_mask ? s.out_mask.v.ptr<uint8_t>() : nullptr; a.mask_step = s.out_mask.v.step;
-        a.pw = s.out.v.cols; a.ph = s.out.v.rows;
         bytes += img_bytes(s.out.v) + (s.want_mask ? img_bytes(s.out_mask.v) : 0);
-        PROF("feather_fused", bytes, launch_feather_fused(a, gain_on, s.out.v.type == SB_8UC3, st));
+        bool tma = c->feather_tma && c->feather_variant == 1;
+        for (int i = 0; i < n && tma; ++i)      // bulk copies need 16-byte aligned rows
+            tma = src[i].step % 16 == 0 && src[i].step < (1ull << 24) && reinterpret_cast<uintptr_t>(src[i].data) % 16 == 0;
+        if (tma) {
+            FeatherTmaArgs a{};
+            a.n = n;
+            for (int i = 0; i < n; ++i) {
+                const Camera &cam = c->cams[i];
+                FeatherTmaCam &fc = a.cam[i];
+                fc.src = src[i].ptr<uint8_t>(); fc.sstep = (unsigned)src[i].step; fc.gain = cam.gain;
+                fc.tiles = static_cast<const uint2 *>(cam.feather_tiles.p);
+            }
+            a.desc = static_cast<const uint4 *>(c->tma_desc.p);
+            a.bilin_lut = static_cast<const uint2 *>(c->bilin_lut.p);
+            a.sharpness = cfg.sharpness;
+            a.out = s.out.v.data; a.out_step = s.out.v.step;
+            a.out_mask = s.want_mask ? s.out_mask.v.ptr<uint8_t>() : nullptr; a.mask_step = s.out_mask.v.step;
+            a.pw = s.out.v.cols; a.ph = s.out.v.rows;
+            a.tiles_x = div_up(a.pw, SB_FTT_W); a.n_tiles = a.tiles_x * div_up(a.ph, SB_FTT_H);
+            PROF("feather_stream", bytes, launch_feather_stream(a, gain_on, s.out.v.type == SB_8UC3, c->sm_count, st));
+        } else {
+            FeatherFusedArgs a{};
+            a.n = n;
+            for (int i = 0; i < n; ++i) {
+                const Camera &cam = c->cams[i];
+                FeatherCam &fc = a.cam[i];
+                fc.src = src[i].ptr<uint8_t>(); fc.sstep = src[i].step;
+                fc.table = static_cast<const uint2 *>(cam.feather_table.p); fc.tstep = cam.feather_tstep;
+                fc.ww = cam.ww; fc.wh = cam.wh; fc.dx = cam.tl.x - c->dst_roi.x; fc.dy = cam.tl.y - c->dst_roi.y;
+                fc.gain = cam.gain;
+            }
+            a.tiles_x = div_up(s.out.v.cols, SB_FT_W);
+            a.sharpness = cfg.sharpness;
+            a.bilin_lut = static_cast<const uint2 *>(c->bilin_lut.p);
+            a.tile_cams = static_cast<const uint32_t *>(c->tile_cams.p);
+            a.out = s.out.v.data; a.out_step = s.out.v.step;
+            a.out_mask = s.want_mask ? s.out_mask.v.ptr<uint8_t>() : nullptr; a.mask_step = s.out_mask.v.step;
+            a.pw = s.out.v.cols; a.ph = s.out.v.rows;
+            PROF("feather_fused", bytes, launch_feather_fused(a, gain_on, s.out.v.type == SB_8UC3, st));
+        }
     } else if (cfg.blender_kind == SB_BLEND_MULTI_BAND) {
         for (auto &acc : s.acc) PROF("zero_fill", img_bytes(acc.v), launch_set_zero(acc.v, st));
         const int nb = c->num_bands;

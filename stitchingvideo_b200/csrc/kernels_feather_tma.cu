@@ -1,0 +1,362 @@
+// kernels_feather_tma.cu — the feather frame kernel as a persistent, warp-specialised streaming kernel.
+//
+// Same arithmetic as k_feather_fused_px1 (kernels_fused.cu): remap + gain + convertTo(16S) +
+// FeatherBlender::feed over all cameras + blend + convertTo(8U), one launch per frame.  What changes
+// is how the bytes move.  In the one-pixel-per-thread kernel every warp waits for its tile mask, then
+// for its table entries, then for its taps: three dependent DRAM round trips, and the profile is
+// latency-bound (long-scoreboard stalls, < 20 % of HBM bandwidth).  Here
+//   * the panorama is cut into 32x16 tiles; per (tile, camera) the sequence-constant table is stored
+//     TILE-MAJOR as one contiguous 4 KB block, and the bounding box of the source pixels the tile
+//     samples is known per calibration (a 64-byte descriptor per tile);
+//   * each CTA is persistent (one per SM) and walks tiles round-robin; a PRODUCER warp streams, three
+//     tiles ahead, the table blocks (one cp.async.bulk / TMA each, mbarrier complete_tx) and the source
+//     boxes (16-byte cp.async chunks, lanes in parallel, mbarrier arrive.noinc) into a 4-stage ring;
+//   * 16 CONSUMER warps compute pixels purely from shared memory (table entry -> box-relative tap
+//     offset -> aligned LDS + funnel shift -> byte dot products) and hand the stage back through an
+//     "empty" mbarrier.  No thread ever waits on a global load.
+#include <algorithm>
+#include <climits>
+
+#include "sb_device.cuh"
+#include "sb_fused.h"
+#include "sb_tma.cuh"
+
+namespace sb {
+using namespace sbd;
+using namespace sbt;
+
+#define SB_WEIGHT_EPS 1e-5f
+
+// ------------------------------------------------------------------------------------ setup
+// pass 1: per (camera, tile) the source bounding box of the weighted entries -> descriptor record
+__global__ void __launch_bounds__(256)
+k_fts_bbox(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int tx0, int ty0, int ntx, uint4 *rec)
+{
+    __shared__ int red[4][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
+    for (int e = tid; e < SB_FTT_W * SB_FTT_H; e += blockDim.x) {
+        const int lx = e % SB_FTT_W, ly = e / SB_FTT_W;
+        const int x = (tx0 + (int)blockIdx.x) * SB_FTT_W + lx - dx, y = (ty0 + (int)blockIdx.y) * SB_FTT_H + ly - dy;
+        if ((unsigned)x >= (unsigned)ww || (unsigned)y >= (unsigned)wh) continue;
+        const uint2 t = reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(table) + (size_t)y * tstep)[x];
+        if ((t.y >> 16) == 0u) continue;
+        const int x0 = t.x & 0x1fff, y0 = (t.x >> 13) & 0x1fff;
+        const int x1 = x0 + 1 - (int)((t.x >> 26) & 1u), y1 = y0 + 1 - (int)((t.x >> 27) & 1u);
+        mnx = min(mnx, x0); mxx = max(mxx, x1); mny = min(mny, y0); mxy = max(mxy, y1);
+    }
+    mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
+    mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+    if (lane == 0) { red[0][warp] = mnx; red[1][warp] = mny; red[2][warp] = mxx; red[3][warp] = mxy; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w) {
+            mnx = min(mnx, red[0][w]); mny = min(mny, red[1][w]); mxx = max(mxx, red[2][w]); mxy = max(mxy, red[3][w]);
+        }
+        uint4 r = make_uint4(0u, 0u, 0u, 0u);                // n_rows == 0: the camera carries no weight in this tile
+        if (mxx >= mnx) {
+            const unsigned xlo = ((unsigned)mnx * 3u) & ~15u;             // box start, 16-byte aligned
+            const unsigned need_end = (unsigned)(mxx + 1) * 3u + 3u;      // last needed byte + the aligned-word slack of load_6bytes
+            const unsigned pitch = ((need_end + 15u) & ~15u) - xlo;
+            unsigned n_rows = (unsigned)(mxy - mny + 1);
+            if (n_rows > (unsigned)SB_FTS_MAX_ROWS || n_rows * pitch > (unsigned)SB_FTS_BOX_BYTES) n_rows = SB_FTS_DIRECT;
+            r = make_uint4(xlo | ((unsigned)mny << 16), need_end | (n_rows << 24), pitch, 0u);
+        }
+        rec[blockIdx.y * ntx + blockIdx.x] = r;
+    }
+}
+
+// pass 2: tile-major entries, tap position relative to the tile's source box:
+//   x = box byte offset of tap (y0, x0) | (x1 == x0) << 26 | (y1 == y0) << 27     y = fx | fy << 5 | dist << 16
+// (boxes too large for a shared-memory slot: x = x0 | y0 << 13 | flags, the row-major format, taps gathered directly)
+__global__ void __launch_bounds__(256)
+k_fts_entries(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int tx0, int ty0, int ntx, const uint4 *rec, uint2 *tiles)
+{
+    const uint4 r = rec[blockIdx.y * ntx + blockIdx.x];
+    const unsigned xlo = r.x & 0xffffu, ylo = r.x >> 16, pitch = r.z;
+    uint2 *dst = tiles + ((size_t)blockIdx.y * ntx + blockIdx.x) * (SB_FTT_W * SB_FTT_H);
+    for (int e = threadIdx.x; e < SB_FTT_W * SB_FTT_H; e += blockDim.x) {
+        const int lx = e % SB_FTT_W, ly = e / SB_FTT_W;
+        const int x = (tx0 + (int)blockIdx.x) * SB_FTT_W + lx - dx, y = (ty0 + (int)blockIdx.y) * SB_FTT_H + ly - dy;
+        uint2 t = make_uint2(0u, 0u);
+        if ((unsigned)x < (unsigned)ww && (unsigned)y < (unsigned)wh) {
+            const uint2 s = reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(table) + (size_t)y * tstep)[x];
+            if ((s.y >> 16) != 0u) {
+                const unsigned x0 = s.x & 0x1fffu, y0 = (s.x >> 13) & 0x1fffu;
+                t.x = (r.y >> 24) == (unsigned)SB_FTS_DIRECT ? s.x : (((y0 - ylo) * pitch + x0 * 3u - xlo) | (s.x & (3u << 26)));
+                t.y = s.y;
+            }
+        }
+        dst[e] = t;
+    }
+}
+
+int launch_fts_camera_tiles(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int tx0, int ty0, int ntx, int nty,
+                            uint4 *rec, uint2 *tiles, cudaStream_t s)
+{
+    k_fts_bbox<<<dim3(ntx, nty), 256, 0, s>>>(table, tstep, ww, wh, dx, dy, tx0, ty0, ntx, rec);
+    SB_LAUNCHED();
+    k_fts_entries<<<dim3(ntx, nty), 256, 0, s>>>(table, tstep, ww, wh, dx, dy, tx0, ty0, ntx, rec, tiles);
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
+// pass 3: one 64-byte descriptor per panorama tile: {n_cams, 0, 0, 0} + per camera slot (ascending
+// camera index = feed order) {xlo | ylo << 16, need_end | n_rows << 24, pitch, cam | table block index << 4}.
+// *status: bit 0 = some tile has more than SB_FTT_MAXC cameras, bit 1 = block index overflow.
+__global__ void k_fts_descriptors(FtsSetup a, uint4 *desc, int *status)
+{
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= a.n_tiles) return;
+    const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+    uint4 out[1 + SB_FTT_MAXC];
+    for (int k = 0; k <= SB_FTT_MAXC; ++k) out[k] = make_uint4(0u, 0u, 0u, 0u);
+    int k = 0, bad = 0;
+    for (int i = 0; i < a.n; ++i) {
+        const int rx = tx - a.cam[i].tx0, ry = ty - a.cam[i].ty0;
+        if ((unsigned)rx >= (unsigned)a.cam[i].ntx || (unsigned)ry >= (unsigned)a.cam[i].nty) continue;
+        const unsigned block = (unsigned)(ry * a.cam[i].ntx + rx);
+        uint4 r = a.cam[i].rec[block];
+        const unsigned n_rows = r.y >> 24;
+        if (n_rows == 0u) continue;
+        if (block >= (1u << 28)) bad |= 2;
+        if (k == SB_FTT_MAXC) { bad |= 1; break; }
+        r.w = (unsigned)i | (block << 4);
+        out[1 + k++] = r;
+    }
+    out[0].x = (unsigned)k;
+    for (int j = 0; j <= SB_FTT_MAXC; ++j) desc[(size_t)tile * (1 + SB_FTT_MAXC) + j] = out[j];
+    if (bad) atomicOr(status, bad);
+}
+
+int launch_fts_descriptors(const FtsSetup &a, uint4 *desc, int *status, cudaStream_t s)
+{
+    k_fts_descriptors<<<div_up(a.n_tiles, 128), 128, 0, s>>>(a, desc, status);
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
+// ------------------------------------------------------------------------------------ frame kernel
+// Shared memory: a ring of SB_FTS_SLOTS camera slots (table block + source box) allocated to tiles in
+// order, as many as the tile has cameras (0..SB_FTT_MAXC; 1.2 on average), and a ring of SB_FTT_STAGES
+// tile entries (descriptor + full/empty barriers).  ~10 tiles are in flight per CTA.
+struct FtsSlot {
+    uint2 tab[SB_FTT_H][SB_FTT_W];                          // 4 KB
+    unsigned char box[SB_FTS_BOX_BYTES];
+};
+struct FtsSmem {
+    FtsSlot slot[SB_FTS_SLOTS];
+    uint4 desc[SB_FTT_STAGES][1 + SB_FTT_MAXC];             // [0] = {n_cams, first slot, 0, 0}
+    uint64_t full[SB_FTT_STAGES], empty[SB_FTT_STAGES];
+    int nc_hist[SB_FTS_PRODUCER_WARPS][SB_FTT_STAGES];      // per producer warp: cameras of its tiles in flight
+};
+
+// lo = bytes 0..3, hi = bytes 4..7 of the 6 tap bytes at shared-memory byte address `a`
+__device__ __forceinline__ void lds_6bytes(uint32_t a, unsigned &lo, unsigned &hi)
+{
+    const unsigned o = a & 3u;
+    const uint32_t b = a - o;
+    unsigned w0, w1, w2;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(b));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(b));
+    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(b));
+    lo = __funnelshift_r(w0, w1, o * 8);
+    hi = __funnelshift_r(w1, w2, o * 8);
+}
+
+template <bool GAIN, bool OUT8>
+__global__ void __launch_bounds__(SB_FTS_THREADS, SB_FTS_CTAS_PER_SM)
+k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FtsSmem &sm = *reinterpret_cast<FtsSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x;
+    if (tid == 0) {
+        for (int s = 0; s < SB_FTT_STAGES; ++s) {
+            mbar_init(&sm.full[s], SB_FTS_PRODUCER_WARPS * 32 + 1);   // every producer lane (cp.async) + the table copies' expect_tx
+            mbar_init(&sm.empty[s], SB_FTS_CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp >= SB_FTS_CONSUMER_WARPS) {
+        // ------------------------------------------------ producer warps
+        const int pw = warp - SB_FTS_CONSUMER_WARPS;
+        int stage = 0, head = 0, used = 0;                  // tile entry of this tile; next free slot; slots held by tiles in flight
+        int seq = 0, oldest = 0;                            // tiles issued / retired by this CTA
+        uint4 d_next = make_uint4(0u, 0u, 0u, 0u);          // descriptors are fetched one tile ahead of their use
+        if (lane <= SB_FTT_MAXC) d_next = __ldg(a.desc + (size_t)blockIdx.x * (1 + SB_FTT_MAXC) + lane);
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += G, ++seq) {
+            uint4 d = d_next;
+            if (lane <= SB_FTT_MAXC && tile + G < a.n_tiles) d_next = __ldg(a.desc + (size_t)(tile + G) * (1 + SB_FTT_MAXC) + lane);
+            const int nc = (int)__shfl_sync(0xffffffffu, d.x, 0);
+            // retire the oldest tiles until a tile entry and nc slots are free (tiles complete in order)
+            while (seq - oldest >= SB_FTT_STAGES || used + nc > SB_FTS_SLOTS) {
+                const int e = oldest % SB_FTT_STAGES;
+                mbar_wait(&sm.empty[e], (unsigned)(oldest / SB_FTT_STAGES) & 1u);   // every consumer warp is done with it
+                used -= sm.nc_hist[pw][e];
+                ++oldest;
+            }
+            sm.nc_hist[pw][stage] = nc;                     // (every lane stores the same value)
+            if (lane == 0) d.y = (unsigned)head;
+            if (pw == 0 && lane <= SB_FTT_MAXC) sm.desc[stage][lane] = d;
+            // table blocks: one bulk copy (TMA) per camera slot, completion by expect_tx
+            if (pw == 0 && lane == 0) {
+                if (nc == 0) mbar_arrive(&sm.full[stage]);
+                else mbar_arrive_expect_tx(&sm.full[stage], (unsigned)nc * (unsigned)(SB_FTT_W * SB_FTT_H * sizeof(uint2)));
+            }
+            __syncwarp();
+            for (int k = 0; k < nc; ++k) {
+                const unsigned dx_ = __shfl_sync(0xffffffffu, d.x, k + 1), dy_ = __shfl_sync(0xffffffffu, d.y, k + 1);
+                const unsigned dw_ = __shfl_sync(0xffffffffu, d.w, k + 1), pitch = __shfl_sync(0xffffffffu, d.z, k + 1);
+                const FeatherTmaCam &c = a.cam[dw_ & 15u];
+                const int slot = head + k < SB_FTS_SLOTS ? head + k : head + k - SB_FTS_SLOTS;
+                if (pw == 0 && lane == 0)
+                    bulk_g2s(&sm.slot[slot].tab[0][0], c.tiles + (size_t)(dw_ >> 4) * (SB_FTT_W * SB_FTT_H),
+                             SB_FTT_W * SB_FTT_H * sizeof(uint2), &sm.full[stage]);
+                unsigned n_rows = dy_ >> 24;
+                if (n_rows == (unsigned)SB_FTS_DIRECT) n_rows = 0u;
+                // source box: 16-byte cp.async chunks, all lanes (row length clamped to the pitch of the source image)
+                const unsigned xlo = dx_ & 0xffffu, ylo = dx_ >> 16, need_end = dy_ & 0xffffffu;
+                const unsigned cpr = (min((need_end + 15u) & ~15u, c.sstep) - xlo) >> 4;           // chunks per row
+                const float inv = 1.f / (float)cpr;
+                const unsigned n_chunks = n_rows * cpr;
+                const uint32_t box = smem_u32(&sm.slot[slot].box[0]);
+                const uint8_t *g = c.src + (size_t)ylo * c.sstep + xlo;
+                for (unsigned ch = pw * 32 + lane; ch < n_chunks; ch += 32u * SB_FTS_PRODUCER_WARPS) {
+                    const unsigned r = (unsigned)__float2int_rz(__fmul_rn((float)ch + 0.5f, inv));  // exact: ch < 1024
+                    const unsigned col = ch - r * cpr;
+                    cp_async_16(box + r * pitch + col * 16u, g + (size_t)r * c.sstep + col * 16u);
+                }
+            }
+            cp_async_mbar_arrive_noinc(&sm.full[stage]);    // one arrival per lane when its chunks have landed
+            head = head + nc < SB_FTS_SLOTS ? head + nc : head + nc - SB_FTS_SLOTS;
+            used += nc;
+            if (++stage == SB_FTT_STAGES) stage = 0;
+        }
+        return;
+    }
+
+    // ---------------------------------------------------- consumer warps
+    // warp w covers columns (w % SEGS) * 32 .. +31 of tile rows (w / SEGS) + RPP * p, p = 0 .. PX-1
+    constexpr int SEGS = SB_FTT_W / 32, RPP = SB_FTS_CONSUMER_WARPS / SEGS, PX = SB_FTT_H / RPP;
+    const int lx = (warp % SEGS) * 32 + lane, ly = warp / SEGS;
+    const int gx = G % a.tiles_x, gy = G / a.tiles_x;       // tile -> (tx, ty) advanced incrementally
+    int tx = blockIdx.x % a.tiles_x, ty = blockIdx.x / a.tiles_x;
+    int stage = 0;
+    unsigned parity = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += G) {
+        mbar_wait(&sm.full[stage], parity);
+        const int nc = (int)sm.desc[stage][0].x, first = (int)sm.desc[stage][0].y;
+        const int X = tx * SB_FTT_W + lx, Y0 = ty * SB_FTT_H + ly;
+        int acc[PX][3];
+        float wsum[PX];
+#pragma unroll
+        for (int p = 0; p < PX; ++p) { acc[p][0] = acc[p][1] = acc[p][2] = 0; wsum[p] = 0.f; }
+        for (int k = 0; k < nc; ++k) {                      // ascending camera index = feed order (float weight sums)
+            const uint4 rec = sm.desc[stage][1 + k];
+            const unsigned pitch = rec.z;
+            const bool direct = (rec.y >> 24) == (unsigned)SB_FTS_DIRECT;    // block-uniform
+            const FtsSlot &sl = sm.slot[first + k < SB_FTS_SLOTS ? first + k : first + k - SB_FTS_SLOTS];
+            const uint32_t box = smem_u32(&sl.box[0]);
+            uint2 te[PX], bw[PX];
+            unsigned lo0[PX], hi0[PX], lo1[PX], hi1[PX];
+#pragma unroll
+            for (int p = 0; p < PX; ++p) {
+                te[p] = sl.tab[ly + RPP * p][lx];
+                bw[p] = __ldg(a.bilin_lut + (te[p].y & 1023u));
+                if (!direct) {
+                    const uint32_t r0 = box + (te[p].x & 0x3ffffu);
+                    const uint32_t r1 = (te[p].x & (1u << 27)) ? r0 : r0 + pitch;
+                    lds_6bytes(r0, lo0[p], hi0[p]);
+                    lds_6bytes(r1, lo1[p], hi1[p]);
+                    if (te[p].x & (1u << 26)) {             // x1 == x0 at the image edge: repeat the pixel
+                        hi0[p] = lo0[p] >> 8; lo0[p] = (lo0[p] & 0x00ffffffu) | (lo0[p] << 24);
+                        hi1[p] = lo1[p] >> 8; lo1[p] = (lo1[p] & 0x00ffffffu) | (lo1[p] << 24);
+                    }
+                } else {                                    // box too large for the slot: gather from global memory
+                    lo0[p] = hi0[p] = lo1[p] = hi1[p] = 0u;
+                    if ((te[p].y >> 16) != 0u) {
+                        const FeatherTmaCam &c = a.cam[rec.w & 15u];
+                        const unsigned x0 = te[p].x & 0x1fffu, y0 = (te[p].x >> 13) & 0x1fffu;
+                        const uint8_t *g0 = c.src + (size_t)(y0 * c.sstep);
+                        const uint8_t *g1 = (te[p].x & (1u << 27)) ? g0 : g0 + c.sstep;
+                        const unsigned x1 = x0 + 1u - ((te[p].x >> 26) & 1u);
+                        load_tap_row(g0, x0, x1, lo0[p], hi0[p]);
+                        load_tap_row(g1, x0, x1, lo1[p], hi1[p]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < PX; ++p) {
+                const unsigned dist = te[p].y >> 16;        // 0: short(p * 0) == 0 and dst_w += 0 -> contributes nothing
+                const float w = fminf(__fmul_rn((float)dist, a.sharpness), 1.f);   // createWeightMap
+                wsum[p] = __fadd_rn(wsum[p], w);
+                int v0, v1, v2;
+                bilinear_rgb(lo0[p], hi0[p], lo1[p], hi1[p], bw[p], v0, v1, v2);
+                if (GAIN) {                                 // saturate_cast<uchar>(p * gain)
+                    const float g = a.cam[rec.w & 15u].gain;
+                    v0 = min(max(__float2int_rn(__fmul_rn((float)v0, g)), 0), 255);
+                    v1 = min(max(__float2int_rn(__fmul_rn((float)v1, g)), 0), 255);
+                    v2 = min(max(__float2int_rn(__fmul_rn((float)v2, g)), 0), 255);
+                }
+                acc[p][0] += __float2int_rz(__fmul_rn((float)v0, w));              // static_cast<short>(src * w)
+                acc[p][1] += __float2int_rz(__fmul_rn((float)v1, w));
+                acc[p][2] += __float2int_rz(__fmul_rn((float)v2, w));
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[stage]);       // this warp no longer reads the stage
+        // FeatherBlender::blend: normalizeUsingWeightMap, mask = weight > eps, zero unmasked, convertTo(8U)
+        if (X < a.pw) {
+            unsigned char *orow = reinterpret_cast<unsigned char *>(a.out) + (size_t)Y0 * a.out_step + (size_t)X * (OUT8 ? 3 : 6);
+            uint8_t *mrow_ = a.out_mask ? a.out_mask + (size_t)Y0 * a.mask_step + X : nullptr;
+#pragma unroll
+            for (int p = 0; p < PX; ++p) {
+                if (Y0 + RPP * p >= a.ph) break;
+                const int m = wsum[p] > SB_WEIGHT_EPS ? 255 : 0;
+                const SharedDiv div(__fadd_rn(wsum[p], SB_WEIGHT_EPS));            // in [1e-5, n + 1e-5]: fast-path range
+                const int o0 = m ? __float2int_rz(div((float)acc[p][0])) : 0, o1 = m ? __float2int_rz(div((float)acc[p][1])) : 0,
+                          o2 = m ? __float2int_rz(div((float)acc[p][2])) : 0;
+                if (OUT8) {
+                    orow[0] = (uint8_t)o0; orow[1] = (uint8_t)o1; orow[2] = (uint8_t)o2;
+                } else {
+                    short *o = reinterpret_cast<short *>(orow);
+                    o[0] = (short)o0; o[1] = (short)o1; o[2] = (short)o2;
+                }
+                if (mrow_) { *mrow_ = (uint8_t)m; mrow_ += RPP * a.mask_step; }
+                orow += RPP * a.out_step;
+            }
+        }
+        tx += gx; ty += gy;
+        if (tx >= a.tiles_x) { tx -= a.tiles_x; ++ty; }
+        if (++stage == SB_FTT_STAGES) { stage = 0; parity ^= 1u; }
+    }
+}
+
+int launch_feather_stream(const FeatherTmaArgs &a, bool apply_gain, bool out8, int sm_count, cudaStream_t s)
+{
+    SB_ASSERT(a.sharpness > 0.f && a.bilin_lut && a.desc && a.n_tiles > 0 && a.n <= 16);
+    const size_t smem = sizeof(FtsSmem);
+    static bool configured[4] = {false, false, false, false};
+    const void *fn[4] = {(const void *)k_feather_stream<false, false>, (const void *)k_feather_stream<false, true>,
+                         (const void *)k_feather_stream<true, false>, (const void *)k_feather_stream<true, true>};
+    const int v = (apply_gain ? 2 : 0) + (out8 ? 1 : 0);
+    if (!configured[v]) {
+        SB_CUDA(cudaFuncSetAttribute(fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[v] = true;
+    }
+    const int grid = std::min(a.n_tiles, SB_FTS_CTAS_PER_SM * sm_count);
+    switch (v) {
+    case 0: k_feather_stream<false, false><<<grid, SB_FTS_THREADS, smem, s>>>(a); break;
+    case 1: k_feather_stream<false, true><<<grid, SB_FTS_THREADS, smem, s>>>(a); break;
+    case 2: k_feather_stream<true, false><<<grid, SB_FTS_THREADS, smem, s>>>(a); break;
+    default: k_feather_stream<true, true><<<grid, SB_FTS_THREADS, smem, s>>>(a); break;
+    }
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
+}  // namespace sb

@@ -35,11 +35,31 @@ __device__ __forceinline__ bool in_spans(const int span[4], int x0, int x1)   //
 }
 
 // ------------------------------------------------------------------------------------ feather
+// setup: the bilinear product table shared by every remap-type kernel (sb_device.cuh)
+__global__ void k_build_bilin_lut(uint2 *lut)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 1024) lut[i] = bilin_weights(i & 31, i >> 5);
+}
+
+int launch_build_bilin_lut(uint2 *lut, cudaStream_t s)
+{
+    k_build_bilin_lut<<<4, 256, 0, s>>>(lut);
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
 // setup: one table entry per warped pixel = what cv::remap's map conversion would compute every
-// frame (sx, sy, fx, fy; Appendix A1) + the L1 distance behind the feather weight.
+// frame (Appendix A1: sx, sy after >> 5 and the int16 clamp, 5+5 fractional bits) with the
+// BORDER_REFLECT of the two tap coordinates already resolved, + the L1 distance behind the feather
+// weight:   x = x0 | y0 << 13 | (x1 == x0) << 26 | (y1 == y0) << 27      y = fx | fy << 5 | dist << 16
+// A non-zero distance implies the pixel lies inside the warped all-255 mask, i.e. its source
+// coordinate rounds into the image (sx in [-1, sw-1], sy in [-1, sh-1]): there x1 is x0 or x0 + 1.
+// Pixels whose taps are folded any other way are given distance 0 only if the mask is 0 there, so the
+// kernel asserts nothing: entries with dist == 0 are skipped, exactly (short(p * 0) == 0, w += 0).
 template <int KIND>
 __global__ void __launch_bounds__(256)
-k_build_feather_table(ProjParams p, int tl_x, int tl_y, const float *dist, size_t dstep, int w, int h, uint2 *table, size_t tstep, int tpad)
+k_build_feather_table(ProjParams p, int tl_x, int tl_y, const float *dist, size_t dstep, int w, int h, int sw, int sh, uint2 *table, size_t tstep)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
@@ -48,18 +68,24 @@ k_build_feather_table(ProjParams p, int tl_x, int tl_y, const float *dist, size_
     const int fsx = cvround(__fmul_rn(mx, 32.f)), fsy = cvround(__fmul_rn(my, 32.f));
     const int sx = sat_s16(fsx >> 5), sy = sat_s16(fsy >> 5);
     const float d = crow<float>(dist, dstep, y)[x];
-    const unsigned di = d >= 65535.f ? 65535u : (unsigned)d;       // exact integers below the 8192 saturation
+    unsigned di = d >= 65535.f ? 65535u : (unsigned)d;       // exact integers below the 8192 saturation
+    const int x0 = border_interp<BORDER_REFLECT>(sx, sw), x1 = border_interp<BORDER_REFLECT>(sx + 1, sw);
+    const int y0 = border_interp<BORDER_REFLECT>(sy, sh), y1 = border_interp<BORDER_REFLECT>(sy + 1, sh);
+    const bool xs = x1 == x0, ys = y1 == y0;
+    // representable: taps are (x0, x0 or x0+1) x (y0, y0 or y0+1); anything else cannot carry weight
+    const bool ok = (xs || x1 == x0 + 1) && (ys || y1 == y0 + 1);
     uint2 t;
-    t.x = ((unsigned)sx & 0xffffu) | ((unsigned)sy << 16);
+    t.x = (unsigned)x0 | ((unsigned)y0 << 13) | ((unsigned)xs << 26) | ((unsigned)ys << 27) | ((unsigned)!ok << 28);
     t.y = (unsigned)(fsx & 31) | ((unsigned)(fsy & 31) << 5) | (di << 16);
-    reinterpret_cast<uint2 *>(reinterpret_cast<char *>(table) + (size_t)y * tstep)[x + tpad] = t;
+    reinterpret_cast<uint2 *>(reinterpret_cast<char *>(table) + (size_t)y * tstep)[x] = t;
 }
 
-int launch_build_feather_table(const ProjParams &p, int tl_x, int tl_y, const DImage &dist, uint2 *table, size_t tstep, int tpad, cudaStream_t s)
+int launch_build_feather_table(const ProjParams &p, int tl_x, int tl_y, const DImage &dist, int sw, int sh, uint2 *table, size_t tstep, cudaStream_t s)
 {
     SB_ASSERT(dist.type == SB_32FC1);
+    SB_ASSERT(sw <= 8192 && sh <= 8192);
     dim3 block(32, 8), grid(div_up(dist.cols, 32), div_up(dist.rows, 8));
-#define SB_FT(K) k_build_feather_table<K><<<grid, block, 0, s>>>(p, tl_x, tl_y, dist.ptr<float>(), dist.step, dist.cols, dist.rows, table, tstep, tpad)
+#define SB_FT(K) k_build_feather_table<K><<<grid, block, 0, s>>>(p, tl_x, tl_y, dist.ptr<float>(), dist.step, dist.cols, dist.rows, sw, sh, table, tstep)
     switch (p.kind) {
     case SB_WARP_PLANE: SB_FT(SB_WARP_PLANE); break;
     case SB_WARP_CYLINDRICAL: SB_FT(SB_WARP_CYLINDRICAL); break;
@@ -71,204 +97,42 @@ int launch_build_feather_table(const ProjParams &p, int tl_x, int tl_y, const DI
     return SB_OK;
 }
 
-// setup: source bounding box per (panorama tile, camera) — sequence-constant, so the per-frame
-// kernel can stage exactly the bytes it will sample into shared memory with 16-byte loads.
-__global__ void __launch_bounds__(256) k_feather_tile_bbox(FeatherCam c, int pw, int ph, int tiles_x, int4 *bbox)
+// setup: tile_cams[tile] |= 1 << cam when camera `cam` has a non-zero feather distance inside the
+// SB_FT_W x SB_FT_H panorama tile; *bad counts weighted entries whose taps are not representable.
+__global__ void __launch_bounds__(256) k_feather_tile_cams(FeatherCam c, int cam_index, int pw, int ph, int tiles_x, uint32_t *tile_cams, unsigned *bad)
 {
-    __shared__ int red[4][8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int X0 = blockIdx.x * SB_FT_W + (tid & 7) * 4, Y = blockIdx.y * SB_FT_H + (tid >> 3);
-    int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
-    const int y = Y - c.dy;
-    if (Y < ph && (unsigned)y < (unsigned)c.wh) {
-        const uint2 *trow = reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(c.table) + (size_t)y * c.tstep) + c.tpad;
-        for (int j = 0; j < 4; ++j) {
-            const int x = X0 + j - c.dx;
-            if (X0 + j >= pw || (unsigned)x >= (unsigned)c.ww) continue;
-            const uint2 t = trow[x];
-            if ((t.y >> 16) == 0u) continue;
-            const int sx = (short)(t.x & 0xffffu), sy = (int)t.x >> 16;
-            mnx = min(mnx, max(sx, 0)); mxx = max(mxx, min(sx + 1, c.sw - 1));
-            mny = min(mny, max(sy, 0)); mxy = max(mxy, min(sy + 1, c.sh - 1));
-        }
+    const int X = blockIdx.x * SB_FT_W + threadIdx.x, Y = blockIdx.y * SB_FT_H + threadIdx.y;
+    const int x = X - c.dx, y = Y - c.dy;
+    bool nz = false;
+    if (X < pw && Y < ph && (unsigned)x < (unsigned)c.ww && (unsigned)y < (unsigned)c.wh) {
+        const uint2 t = reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(c.table) + (size_t)y * c.tstep)[x];
+        nz = (t.y >> 16) != 0u;
+        if (nz && ((t.x >> 28) & 1u)) atomicAdd(bad, 1u);
     }
-    mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
-    mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
-    if (lane == 0) { red[0][warp] = mnx; red[1][warp] = mny; red[2][warp] = mxx; red[3][warp] = mxy; }
-    __syncthreads();
-    if (tid == 0) {
-        for (int w = 1; w < 8; ++w) {
-            mnx = min(mnx, red[0][w]); mny = min(mny, red[1][w]); mxx = max(mxx, red[2][w]); mxy = max(mxy, red[3][w]);
-        }
-        bbox[blockIdx.y * tiles_x + blockIdx.x] = (mxx < mnx) ? make_int4(0, 0, -1, -1) : make_int4(mnx, mny, mxx, mxy);
-    }
+    if (__syncthreads_or(nz) && threadIdx.x == 0 && threadIdx.y == 0) tile_cams[blockIdx.y * tiles_x + blockIdx.x] |= 1u << cam_index;
 }
 
-int launch_feather_tile_bbox(const FeatherCam &c, int pw, int ph, int4 *bbox, cudaStream_t s)
+int launch_feather_tile_cams(const FeatherCam &c, int cam_index, int pw, int ph, uint32_t *tile_cams, unsigned *bad, cudaStream_t s)
 {
-    dim3 block(256), grid(div_up(pw, SB_FT_W), div_up(ph, SB_FT_H));
-    k_feather_tile_bbox<<<grid, block, 0, s>>>(c, pw, ph, grid.x, bbox);
+    dim3 block(SB_FT_W, SB_FT_H), grid(div_up(pw, SB_FT_W), div_up(ph, SB_FT_H));
+    k_feather_tile_cams<<<grid, block, 0, s>>>(c, cam_index, pw, ph, grid.x, tile_cams, bad);
     SB_LAUNCHED();
     return SB_OK;
 }
 
-__global__ void k_feather_tile_mask(const int4 *bbox, int n_tiles, int cam_index, uint32_t *tile_cams)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_tiles && bbox[i].z >= bbox[i].x) tile_cams[i] |= 1u << cam_index;
-}
-
-int launch_feather_tile_mask(const int4 *bbox, int n_tiles, int cam_index, uint32_t *tile_cams, cudaStream_t s)
-{
-    k_feather_tile_mask<<<div_up(n_tiles, 256), 256, 0, s>>>(bbox, n_tiles, cam_index, tile_cams);
-    SB_LAUNCHED();
-    return SB_OK;
-}
-
-// One launch per frame.  A non-zero distance implies the pixel lies inside the warped all-255 mask,
-// i.e. its source coordinate rounds into the image: sx in [-1, sw-1], sy in [-1, sh-1], where
-// BORDER_REFLECT coincides with clamping.  Every table weight carries the factor 32, so
-// (sum w*p + 2^14) >> 15 == (v + 512) >> 10 with v the sum of 5-bit products; OpenCV's (0,0) entry
-// {32767,0,0,1} equals an exact copy for 8-bit data, as does {32768,0,0,0}.  With 8-bit sources and
-// weights in [0,1] every intermediate stays inside [0, 255*n]: no saturation or wrap can fire.
-//
-// The gather is the expensive part (12 byte taps per sample): the source box each tile needs is known
-// per calibration, so the block first stages it in shared memory with coalesced 16-byte loads and
-// then samples with conflict-free byte LDS (lanes are 12 bytes apart: 3 words, coprime with 32 banks).
-template <bool GAIN, bool OUT8>
-__global__ void __launch_bounds__(256)
-k_feather_fused(const __grid_constant__ FeatherFusedArgs a)
-{
-    __shared__ __align__(16) uint8_t stage[SB_STAGE_BYTES];
-    const int tile = blockIdx.y * a.tiles_x + blockIdx.x;
-    const int tid = threadIdx.x;
-    const int X0 = blockIdx.x * SB_FT_W + (tid & 7) * 4;       // 8 threads x 4 px across, 32 rows down
-    const int Y = blockIdx.y * SB_FT_H + (tid >> 3);
-    const bool active = X0 < a.pw && Y < a.ph;
-    int acc[4][3];
-    float wsum[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = 0; wsum[j] = 0.f; }
-
-    for (int i = 0; i < a.n; ++i) {                       // ascending index = feed order (float weight sums)
-        const FeatherCam &c = a.cam[i];
-        const int4 bb = __ldg(c.bbox + tile);             // block-uniform
-        if (bb.z < bb.x) continue;
-        const int bw = bb.z - bb.x + 1, bh = bb.w - bb.y + 1;
-        const uint8_t *g0 = c.src + (size_t)bb.y * c.sstep + bb.x * 3;
-        const unsigned o0 = (unsigned)(reinterpret_cast<uintptr_t>(g0) & 15), os = (unsigned)(c.sstep & 15);
-        const int nch = (bw * 3 + 15 + 15) >> 4;          // 16-byte chunks per staged row (upper bound over row alignments)
-        const int pitch = nch * 16;
-        const bool staged = pitch * bh <= SB_STAGE_BYTES;
-        if (staged) {
-            for (int idx = tid; idx < bh * nch; idx += 256) {
-                const int r = idx / nch, ch = idx - r * nch;
-                const uint8_t *gr = g0 + (size_t)r * c.sstep;
-                const unsigned orow = (unsigned)(reinterpret_cast<uintptr_t>(gr) & 15);
-                if (ch * 16 < (int)orow + bw * 3)
-                    *reinterpret_cast<uint4 *>(stage + r * pitch + ch * 16) = __ldg(reinterpret_cast<const uint4 *>(gr - orow) + ch);
-            }
-            __syncthreads();
-        }
-        const int y = Y - c.dy;
-        const int xb = X0 - c.dx;
-        if (active && (unsigned)y < (unsigned)c.wh && xb + 3 >= 0 && xb < c.ww) {
-            // the quad's 4 table entries are 32-byte aligned (tpad) and lie inside the padded table row
-            const uint4 *tq = reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(c.table) + (size_t)y * c.tstep) + ((xb + c.tpad) >> 1);
-            const uint4 ta = __ldg(tq), tb = __ldg(tq + 1);
-            const uint2 te[4] = {make_uint2(ta.x, ta.y), make_uint2(ta.z, ta.w), make_uint2(tb.x, tb.y), make_uint2(tb.z, tb.w)};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int x = xb + j;
-                if ((unsigned)x >= (unsigned)c.ww) continue;
-                const uint2 t = te[j];
-                const unsigned dist = t.y >> 16;
-                if (dist == 0u) continue;                   // weight 0: short(p * 0) == 0 and dst_w += 0
-                // createWeightMap: threshold(dist * sharpness, 1, THRESH_TRUNC)
-                const float w = fminf(__fmul_rn((float)dist, a.sharpness), 1.f);
-                wsum[j] = __fadd_rn(wsum[j], w);
-                const int sx = (short)(t.x & 0xffffu), sy = (int)t.x >> 16;
-                const int fx = t.y & 31, fy = (t.y >> 5) & 31, ax = 32 - fx, ay = 32 - fy;
-                const int x0 = max(sx, 0), x1 = min(sx + 1, c.sw - 1), y0 = max(sy, 0), y1 = min(sy + 1, c.sh - 1);
-                int v[3];
-                if (staged) {
-                    const int r0 = y0 - bb.y, r1 = y1 - bb.y;
-                    const uint8_t *s0 = stage + r0 * pitch + ((o0 + r0 * os) & 15) - bb.x * 3;
-                    const uint8_t *s1 = stage + r1 * pitch + ((o0 + r1 * os) & 15) - bb.x * 3;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const int h0 = (int)s0[x0 * 3 + k] * ax + (int)s0[x1 * 3 + k] * fx;
-                        const int h1 = (int)s1[x0 * 3 + k] * ax + (int)s1[x1 * 3 + k] * fx;
-                        v[k] = (h0 * ay + h1 * fy + 512) >> 10;
-                    }
-                } else {
-                    const uint8_t *r0 = c.src + (size_t)y0 * c.sstep, *r1 = c.src + (size_t)y1 * c.sstep;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const int h0 = (int)__ldg(r0 + x0 * 3 + k) * ax + (int)__ldg(r0 + x1 * 3 + k) * fx;
-                        const int h1 = (int)__ldg(r1 + x0 * 3 + k) * ax + (int)__ldg(r1 + x1 * 3 + k) * fx;
-                        v[k] = (h0 * ay + h1 * fy + 512) >> 10;
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    int p = v[k];
-                    if (GAIN) p = min(max(__float2int_rn(__fmul_rn((float)p, c.gain)), 0), 255);   // saturate_cast<uchar>
-                    acc[j][k] += __float2int_rz(__fmul_rn((float)p, w));                            // static_cast<short>(src * w)
-                }
-            }
-        }
-        if (staged) __syncthreads();                      // the stage buffer is reused by the next camera
-    }
-    if (!active) return;
-    // FeatherBlender::blend: normalizeUsingWeightMap, mask = weight > eps, zero unmasked, convertTo(8U)
-    int o[4][3], m[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        m[j] = wsum[j] > SB_WEIGHT_EPS ? 255 : 0;
-        const SharedDiv div(__fadd_rn(wsum[j], SB_WEIGHT_EPS));        // in [1e-5, n + 1e-5]: fast-path range
-#pragma unroll
-        for (int k = 0; k < 3; ++k) o[j][k] = m[j] ? __float2int_rz(div((float)acc[j][k])) : 0;
-    }
-    const bool full = X0 + 4 <= a.pw;
-    if (OUT8) {
-        uint8_t *orow = reinterpret_cast<uint8_t *>(a.out) + (size_t)Y * a.out_step + X0 * 3;
-        if (full && ((reinterpret_cast<uintptr_t>(orow) & 3) == 0)) {
-            uint32_t *q = reinterpret_cast<uint32_t *>(orow);
-            q[0] = o[0][0] | (o[0][1] << 8) | (o[0][2] << 16) | (o[1][0] << 24);
-            q[1] = o[1][1] | (o[1][2] << 8) | (o[2][0] << 16) | (o[2][1] << 24);
-            q[2] = o[2][2] | (o[3][0] << 8) | (o[3][1] << 16) | (o[3][2] << 24);
-        } else {
-            for (int j = 0; j < 4 && X0 + j < a.pw; ++j)
-                for (int k = 0; k < 3; ++k) orow[j * 3 + k] = (uint8_t)o[j][k];
-        }
-    } else {
-        short *orow = reinterpret_cast<short *>(reinterpret_cast<char *>(a.out) + (size_t)Y * a.out_step) + X0 * 3;
-        for (int j = 0; j < 4 && X0 + j < a.pw; ++j)
-            for (int k = 0; k < 3; ++k) orow[j * 3 + k] = (short)o[j][k];
-    }
-    if (a.out_mask) {
-        uint8_t *mrow_ = a.out_mask + (size_t)Y * a.mask_step + X0;
-        if (full && ((reinterpret_cast<uintptr_t>(mrow_) & 3) == 0))
-            *reinterpret_cast<uint32_t *>(mrow_) = m[0] | (m[1] << 8) | (m[2] << 16) | (m[3] << 24);
-        else
-            for (int j = 0; j < 4 && X0 + j < a.pw; ++j) mrow_[j] = (uint8_t)m[j];
-    }
-}
-
-// Variant with one panorama pixel per thread: a warp's 32 lanes sample 32 neighbouring pixels, so each
-// byte-tap request touches 3-4 sectors instead of ~20 (lanes 3 B apart rather than 4 px = 12 B apart).
-// One load fetches the tile's camera bitmask; the table entries of every contributing camera are
-// requested before any is consumed, so the DRAM latencies of the cameras overlap.
+// One launch per frame, one panorama pixel per thread: a warp's 32 lanes sample 32 neighbouring
+// pixels, so each tap request touches a few 32-byte sectors.  One load fetches the tile's camera
+// bitmask; the table entries of every contributing camera are requested before any is consumed, so
+// the DRAM latencies of the cameras overlap.  With 8-bit sources and weights in [0,1] every
+// intermediate stays inside [0, 255*n]: no saturation or wrap can fire.
 template <bool GAIN, bool OUT8>
 __global__ void __launch_bounds__(256)
 k_feather_fused_px1(const __grid_constant__ FeatherFusedArgs a)
 {
-    const int X = blockIdx.x * 32 + threadIdx.x;
-    const int Y = blockIdx.y * 8 + threadIdx.y;
+    const int X = blockIdx.x * SB_FT_W + threadIdx.x;
+    const int Y = blockIdx.y * SB_FT_H + threadIdx.y;
     if (X >= a.pw || Y >= a.ph) return;
-    // tiles are SB_FT_W x SB_FT_H = 32 x 32 and blocks 32 x 8: the mask is block-uniform
-    uint32_t cams = __ldg(a.tile_cams + (blockIdx.y >> 2) * a.tiles_x + blockIdx.x);
+    uint32_t cams = __ldg(a.tile_cams + blockIdx.y * a.tiles_x + blockIdx.x);      // block == tile
     constexpr int MAXC = 4;
     uint2 t[MAXC];
     int ci[MAXC];
@@ -285,7 +149,7 @@ k_feather_fused_px1(const __grid_constant__ FeatherFusedArgs a)
             ci[q] = i;
             nc = q + 1;
             if ((unsigned)y < (unsigned)c.wh && (unsigned)x < (unsigned)c.ww)
-                t[q] = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(c.table) + (size_t)y * c.tstep) + x + c.tpad);
+                t[q] = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(c.table) + (size_t)y * c.tstep) + x);
         }
     }
     int acc0 = 0, acc1 = 0, acc2 = 0;
@@ -293,34 +157,26 @@ k_feather_fused_px1(const __grid_constant__ FeatherFusedArgs a)
     auto contribute = [&](const FeatherCam &c, const uint2 te) {
         const unsigned dist = te.y >> 16;
         if (dist == 0u) return;                             // weight 0: short(p * 0) == 0 and dst_w += 0
+        const uint2 bw = __ldg(a.bilin_lut + (te.y & 1023u));
         const float w = fminf(__fmul_rn((float)dist, a.sharpness), 1.f);      // createWeightMap
         wsum = __fadd_rn(wsum, w);
-        const int sx = (short)(te.x & 0xffffu), sy = (int)te.x >> 16;
-        const int fx = te.y & 31, fy = (te.y >> 5) & 31, ax = 32 - fx, ay = 32 - fy;
-        const int x0 = max(sx, 0), x1 = min(sx + 1, c.sw - 1), y0 = max(sy, 0), y1 = min(sy + 1, c.sh - 1);
-        const uint8_t *r0 = c.src + (size_t)y0 * c.sstep, *r1 = c.src + (size_t)y1 * c.sstep;
-        unsigned q00, q01, q10, q11;                        // packed RGB of the four taps
-        if (x1 == x0 + 1) {                                 // the pair is 6 contiguous bytes: 2-3 word loads per row
-            load_pixel_pair_8uc3(r0 + x0 * 3, q00, q01);
-            load_pixel_pair_8uc3(r1 + x0 * 3, q10, q11);
-        } else {                                            // clamped at the image edge
-            const uint8_t *p00 = r0 + x0 * 3, *p01 = r0 + x1 * 3, *p10 = r1 + x0 * 3, *p11 = r1 + x1 * 3;
-            q00 = __ldg(p00) | (__ldg(p00 + 1) << 8) | (__ldg(p00 + 2) << 16);
-            q01 = __ldg(p01) | (__ldg(p01 + 1) << 8) | (__ldg(p01 + 2) << 16);
-            q10 = __ldg(p10) | (__ldg(p10 + 1) << 8) | (__ldg(p10 + 2) << 16);
-            q11 = __ldg(p11) | (__ldg(p11 + 1) << 8) | (__ldg(p11 + 2) << 16);
+        const unsigned x0 = te.x & 0x1fffu, y0 = (te.x >> 13) & 0x1fffu;
+        const uint8_t *r0 = c.src + (size_t)y0 * c.sstep;
+        const uint8_t *r1 = (te.x & (1u << 27)) ? r0 : r0 + c.sstep;
+        const unsigned x1 = x0 + 1u - ((te.x >> 26) & 1u);                    // x1 == x0 at the image edge
+        unsigned lo0, hi0, lo1, hi1;
+        load_tap_row(r0, x0, x1, lo0, hi0);
+        load_tap_row(r1, x0, x1, lo1, hi1);
+        int v0, v1, v2;
+        bilinear_rgb(lo0, hi0, lo1, hi1, bw, v0, v1, v2);
+        if (GAIN) {                                                           // saturate_cast<uchar>(p * gain)
+            v0 = min(max(__float2int_rn(__fmul_rn((float)v0, c.gain)), 0), 255);
+            v1 = min(max(__float2int_rn(__fmul_rn((float)v1, c.gain)), 0), 255);
+            v2 = min(max(__float2int_rn(__fmul_rn((float)v2, c.gain)), 0), 255);
         }
-        int v[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int h0 = (int)((q00 >> (8 * k)) & 0xff) * ax + (int)((q01 >> (8 * k)) & 0xff) * fx;
-            const int h1 = (int)((q10 >> (8 * k)) & 0xff) * ax + (int)((q11 >> (8 * k)) & 0xff) * fx;
-            v[k] = (h0 * ay + h1 * fy + 512) >> 10;
-            if (GAIN) v[k] = min(max(__float2int_rn(__fmul_rn((float)v[k], c.gain)), 0), 255);   // saturate_cast<uchar>
-        }
-        acc0 += __float2int_rz(__fmul_rn((float)v[0], w));                                          // static_cast<short>(src * w)
-        acc1 += __float2int_rz(__fmul_rn((float)v[1], w));
-        acc2 += __float2int_rz(__fmul_rn((float)v[2], w));
+        acc0 += __float2int_rz(__fmul_rn((float)v0, w));                      // static_cast<short>(src * w)
+        acc1 += __float2int_rz(__fmul_rn((float)v1, w));
+        acc2 += __float2int_rz(__fmul_rn((float)v2, w));
     };
 #pragma unroll
     for (int q = 0; q < MAXC; ++q)
@@ -329,10 +185,11 @@ k_feather_fused_px1(const __grid_constant__ FeatherFusedArgs a)
         const FeatherCam &c = a.cam[__ffs(cams) - 1];
         const int y = Y - c.dy, x = X - c.dx;
         if ((unsigned)y < (unsigned)c.wh && (unsigned)x < (unsigned)c.ww)
-            contribute(c, __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(c.table) + (size_t)y * c.tstep) + x + c.tpad));
+            contribute(c, __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(c.table) + (size_t)y * c.tstep) + x));
     }
+    // FeatherBlender::blend: normalizeUsingWeightMap, mask = weight > eps, zero unmasked, convertTo(8U)
     const int m = wsum > SB_WEIGHT_EPS ? 255 : 0;
-    const SharedDiv div(__fadd_rn(wsum, SB_WEIGHT_EPS));
+    const SharedDiv div(__fadd_rn(wsum, SB_WEIGHT_EPS));    // in [1e-5, n + 1e-5]: fast-path range
     const int o0 = m ? __float2int_rz(div((float)acc0)) : 0, o1 = m ? __float2int_rz(div((float)acc1)) : 0,
               o2 = m ? __float2int_rz(div((float)acc2)) : 0;
     if (OUT8) {
@@ -347,18 +204,11 @@ k_feather_fused_px1(const __grid_constant__ FeatherFusedArgs a)
 
 int launch_feather_fused(const FeatherFusedArgs &a, bool apply_gain, bool out8, cudaStream_t s)
 {
-    SB_ASSERT(a.sharpness > 0.f);
+    SB_ASSERT(a.sharpness > 0.f && a.bilin_lut && a.tile_cams);
     SB_ASSERT(div_up(a.pw, SB_FT_W) == a.tiles_x);
-    if (a.variant == 1) {
-        dim3 block(32, 8), grid(div_up(a.pw, 32), div_up(a.ph, 8));
-        if (apply_gain) { if (out8) k_feather_fused_px1<true, true><<<grid, block, 0, s>>>(a); else k_feather_fused_px1<true, false><<<grid, block, 0, s>>>(a); }
-        else            { if (out8) k_feather_fused_px1<false, true><<<grid, block, 0, s>>>(a); else k_feather_fused_px1<false, false><<<grid, block, 0, s>>>(a); }
-        SB_LAUNCHED();
-        return SB_OK;
-    }
-    dim3 block(256), grid(div_up(a.pw, SB_FT_W), div_up(a.ph, SB_FT_H));
-    if (apply_gain) { if (out8) k_feather_fused<true, true><<<grid, block, 0, s>>>(a); else k_feather_fused<true, false><<<grid, block, 0, s>>>(a); }
-    else            { if (out8) k_feather_fused<false, true><<<grid, block, 0, s>>>(a); else k_feather_fused<false, false><<<grid, block, 0, s>>>(a); }
+    dim3 block(SB_FT_W, SB_FT_H), grid(div_up(a.pw, SB_FT_W), div_up(a.ph, SB_FT_H));
+    if (apply_gain) { if (out8) k_feather_fused_px1<true, true><<<grid, block, 0, s>>>(a); else k_feather_fused_px1<true, false><<<grid, block, 0, s>>>(a); }
+    else            { if (out8) k_feather_fused_px1<false, true><<<grid, block, 0, s>>>(a); else k_feather_fused_px1<false, false><<<grid, block, 0, s>>>(a); }
     SB_LAUNCHED();
     return SB_OK;
 }

@@ -101,8 +101,7 @@ int launch_mb_tile_mask(const MbBandGeom &g, bool float_weights, int lw, int lh,
 
 // ------------------------------------------------------------------------------------ K1: warp -> G0 (RGBX)
 // remap (A1) + GainCompensator::apply + convertTo(CV_16S) + copyMakeBorder, all cameras in one launch
-// (blockIdx.z = camera).  (sum w*p + 2^14) >> 15 == (v + 512) >> 10 with the 5-bit weights; OpenCV's
-// (0,0) table entry {32767,0,0,1} equals an exact copy for 8-bit data, as does {32768,0,0,0}.
+// (blockIdx.z = camera), with the byte-dot-product bilinear core of sb_device.cuh.
 // Each thread produces MB_WARP_ROWS pixels (same column, rows 8 apart): all their table entries are
 // requested first, then all 12*ROWS byte taps, so several DRAM round trips overlap per thread.
 constexpr int MB_WARP_ROWS = 4;
@@ -119,37 +118,27 @@ __global__ void __launch_bounds__(256) k_mb_warp(const __grid_constant__ MbWarpA
         const int py = min(py0 + 8 * r, c.rh - 1);
         t[r] = __ldg(rowp<uint2>(c.table, c.tstep, py) + px);
     }
-    unsigned tap[MB_WARP_ROWS][4];                          // p00, p01, p10, p11 as packed RGB
+    unsigned tap[MB_WARP_ROWS][4];                          // lo/hi of tap row 0, lo/hi of tap row 1 (sb_device.cuh)
+    uint2 bw[MB_WARP_ROWS];
 #pragma unroll
     for (int r = 0; r < MB_WARP_ROWS; ++r) {
-        const int x0 = t[r].x & 0xfff, x1 = (t[r].x >> 12) & 0xfff, y0 = t[r].y & 0xfff, y1 = (t[r].y >> 12) & 0xfff;
-        const uint8_t *r0 = c.src + (size_t)y0 * c.sstep, *r1 = c.src + (size_t)y1 * c.sstep;
-        if (x1 == x0 + 1) {                                 // interior: the pair is 6 contiguous bytes
-            load_pixel_pair_8uc3(r0 + x0 * 3, tap[r][0], tap[r][1]);
-            load_pixel_pair_8uc3(r1 + x0 * 3, tap[r][2], tap[r][3]);
-        } else {                                            // BORDER_REFLECT folded the pair
-            const uint8_t *p00 = r0 + x0 * 3, *p01 = r0 + x1 * 3, *p10 = r1 + x0 * 3, *p11 = r1 + x1 * 3;
-            tap[r][0] = __ldg(p00) | (__ldg(p00 + 1) << 8) | (__ldg(p00 + 2) << 16);
-            tap[r][1] = __ldg(p01) | (__ldg(p01 + 1) << 8) | (__ldg(p01 + 2) << 16);
-            tap[r][2] = __ldg(p10) | (__ldg(p10 + 1) << 8) | (__ldg(p10 + 2) << 16);
-            tap[r][3] = __ldg(p11) | (__ldg(p11 + 1) << 8) | (__ldg(p11 + 2) << 16);
-        }
+        const unsigned x0 = t[r].x & 0xfff, x1 = (t[r].x >> 12) & 0xfff, y0 = t[r].y & 0xfff, y1 = (t[r].y >> 12) & 0xfff;
+        bw[r] = __ldg(a.bilin_lut + ((t[r].x >> 24) | ((t[r].y >> 24) << 5)));
+        load_tap_row(c.src + (size_t)y0 * c.sstep, x0, x1, tap[r][0], tap[r][1]);
+        load_tap_row(c.src + (size_t)y1 * c.sstep, x0, x1, tap[r][2], tap[r][3]);
     }
 #pragma unroll
     for (int r = 0; r < MB_WARP_ROWS; ++r) {
         const int py = py0 + 8 * r;
         if (py >= c.rh) break;
-        const int fx = t[r].x >> 24, ax = 32 - fx, fy = t[r].y >> 24, ay = 32 - fy;
-        unsigned out = 0;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int h0 = (int)((tap[r][0] >> (8 * k)) & 0xff) * ax + (int)((tap[r][1] >> (8 * k)) & 0xff) * fx;
-            const int h1 = (int)((tap[r][2] >> (8 * k)) & 0xff) * ax + (int)((tap[r][3] >> (8 * k)) & 0xff) * fx;
-            int v = (h0 * ay + h1 * fy + 512) >> 10;
-            if (GAIN) v = min(max(__float2int_rn(__fmul_rn((float)v, c.gain)), 0), 255);      // saturate_cast<uchar>
-            out |= (unsigned)v << (8 * k);
+        int v0, v1, v2;
+        bilinear_rgb(tap[r][0], tap[r][1], tap[r][2], tap[r][3], bw[r], v0, v1, v2);
+        if (GAIN) {                                         // saturate_cast<uchar>(p * gain)
+            v0 = min(max(__float2int_rn(__fmul_rn((float)v0, c.gain)), 0), 255);
+            v1 = min(max(__float2int_rn(__fmul_rn((float)v1, c.gain)), 0), 255);
+            v2 = min(max(__float2int_rn(__fmul_rn((float)v2, c.gain)), 0), 255);
         }
-        rowp<uint32_t>(c.g0, c.gstep, py)[px] = out;
+        rowp<uint32_t>(c.g0, c.gstep, py)[px] = (unsigned)v0 | ((unsigned)v1 << 8) | ((unsigned)v2 << 16);
     }
 }
 

@@ -6,35 +6,30 @@ namespace sb {
 
 constexpr int SB_MAX_CAMERAS = 12;
 
-// Per-camera, per-warped-pixel table of the feather path (sequence-constant, 8 bytes/pixel):
-// the fixed-point map entry cv::remap derives from the float maps (A1: sx, sy after >> 5 and the
-// int16 clamp, 5+5 fractional bits) and the L1 distance createWeightMap turns into the weight.
-//   x: sx (low 16, signed) | sy (high 16, signed)      y: fx | fy << 5 (low 16) | dist (high 16)
+// Per-camera, per-warped-pixel table of the feather path (sequence-constant, 8 bytes/pixel): the
+// resolved taps of cv::remap's fixed-point map entry (A1) and the L1 distance createWeightMap turns
+// into the weight.
+//   x: x0 | y0 << 13 | (x1 == x0) << 26 | (y1 == y0) << 27 | unrepresentable << 28
+//   y: fx | fy << 5 (low 10 bits = bilinear product table index) | dist << 16
 // dist == 0 marks a zero-weight pixel (outside the warped mask): the kernel skips it, exactly.
 struct FeatherCam {
     const uint8_t *src;
     size_t sstep;
-    int sw, sh;            // source size
-    const uint2 *table;    // row y starts at table + y*tstep; entry of warped column x is at index x + tpad
+    const uint2 *table;    // row y of the warped image starts at table + y*tstep
     size_t tstep;          // bytes per table row
-    int tpad;              // (dx mod 4): makes the 4 entries of a panorama-aligned pixel quad 32-byte aligned
     int ww, wh;            // warped size
     int dx, dy;            // warped corner in panorama coordinates
     float gain;
-    // per panorama tile (SB_FT_W x SB_FT_H): bounding box {x0, y0, x1, y1} (inclusive) of the source
-    // pixels the tile's non-zero-weight samples touch; x1 < x0 = the camera does not contribute
-    const int4 *bbox;
 };
 
-constexpr int SB_FT_W = 32, SB_FT_H = 32;        // panorama pixels per block of k_feather_fused (8 x 32 threads, 4 px each)
-constexpr int SB_STAGE_BYTES = 16384;            // shared-memory stage for one camera's source box (pitch * rows must fit)
+constexpr int SB_FT_W = 32, SB_FT_H = 8;         // panorama pixels per block of k_feather_fused_px1 = camera-mask tile
 
 struct FeatherFusedArgs {
     int n;
     FeatherCam cam[SB_MAX_CAMERAS];
     int tiles_x;
-    const uint32_t *tile_cams;   // per panorama tile: bitmask of the cameras whose bbox there is non-empty
-    int variant;           // 0: 4 px/thread with the source box staged in shared memory; 1: 1 px/thread, direct taps
+    const uint32_t *tile_cams;   // per panorama tile: bitmask of the cameras with non-zero weight there
+    const uint2 *bilin_lut;      // 1024 x {hi, lo} bilinear product weights (sb_device.cuh)
     float sharpness;
     void *out;             // 8UC3 or 16SC3 panorama
     size_t out_step;
@@ -42,6 +37,53 @@ struct FeatherFusedArgs {
     size_t mask_step;
     int pw, ph;
 };
+
+// ---- persistent, warp-specialised streaming feather kernel (kernels_feather_tma.cu) ----
+constexpr int SB_FTT_W = 32, SB_FTT_H = 16;      // panorama tile: one contiguous 4 KB table block per camera
+constexpr int SB_FTT_MAXC = 3;                   // cameras with weight inside one tile (more -> k_feather_fused_px1)
+constexpr int SB_FTT_STAGES = 8;                 // tile entries (descriptor + barriers) in flight per CTA
+constexpr int SB_FTS_SLOTS = 6;                  // shared-memory ring of camera slots (16 KB each)
+constexpr int SB_FTS_BOX_BYTES = 12288;          // shared-memory slot for one (tile, camera) source box; larger boxes are gathered directly
+constexpr int SB_FTS_MAX_ROWS = 64;              // box rows copied by the producer warp (2 per lane)
+constexpr int SB_FTS_DIRECT = 0xff;              // n_rows marker: no box, taps come from global memory
+constexpr int SB_FTS_CONSUMER_WARPS = 16;        // 512 pixel threads
+constexpr int SB_FTS_PRODUCER_WARPS = 2;         // all walk the tile sequence; each issues a quarter of the box chunks
+constexpr int SB_FTS_CTAS_PER_SM = 2;
+constexpr int SB_FTS_THREADS = (SB_FTS_CONSUMER_WARPS + SB_FTS_PRODUCER_WARPS) * 32;
+
+struct FeatherTmaCam {
+    const uint8_t *src;    // 16-byte aligned, sstep a multiple of 16
+    unsigned sstep;
+    float gain;
+    const uint2 *tiles;    // tile-major table blocks of this camera
+};
+struct FeatherTmaArgs {
+    int n;
+    FeatherTmaCam cam[SB_MAX_CAMERAS];
+    const uint4 *desc;           // per panorama tile: 1 + SB_FTT_MAXC records (kernels_feather_tma.cu)
+    const uint2 *bilin_lut;
+    float sharpness;
+    void *out;
+    size_t out_step;
+    uint8_t *out_mask;
+    size_t mask_step;
+    int pw, ph, tiles_x, n_tiles;
+};
+struct FtsSetupCam {
+    const uint4 *rec;      // per tile block of this camera: source box record
+    int tx0, ty0, ntx, nty;
+};
+struct FtsSetup {
+    int n;
+    FtsSetupCam cam[SB_MAX_CAMERAS];
+    int tiles_x, n_tiles;
+};
+// setup: box records + tile-major entries of one camera
+int launch_fts_camera_tiles(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int tx0, int ty0, int ntx, int nty,
+                            uint4 *rec, uint2 *tiles, cudaStream_t s);
+// setup: the per-tile descriptors; *status != 0 -> the streaming kernel cannot be used for this calibration
+int launch_fts_descriptors(const FtsSetup &a, uint4 *desc, int *status, cudaStream_t s);
+int launch_feather_stream(const FeatherTmaArgs &a, bool apply_gain, bool out8, int sm_count, cudaStream_t s);
 
 // one camera as seen by k_band_fused at one pyramid level
 struct BandCam {
@@ -70,13 +112,12 @@ struct BandFusedArgs {
     int out_w, out_h;      // band 0 only: dst_roi_final_ size
 };
 
-// setup: per panorama tile, the source bounding box of one camera's non-zero-weight samples
-int launch_feather_tile_bbox(const FeatherCam &c, int pw, int ph, int4 *bbox, cudaStream_t s);
-// setup: tile_cams[tile] |= 1 << cam_index where that camera's bbox is non-empty
-int launch_feather_tile_mask(const int4 *bbox, int n_tiles, int cam_index, uint32_t *tile_cams, cudaStream_t s);
+int launch_build_bilin_lut(uint2 *lut, cudaStream_t s);
+// setup: tile_cams[tile] |= 1 << cam_index where the camera has weight; *bad += weighted entries with unrepresentable taps
+int launch_feather_tile_cams(const FeatherCam &c, int cam_index, int pw, int ph, uint32_t *tile_cams, unsigned *bad, cudaStream_t s);
 int launch_feather_fused(const FeatherFusedArgs &a, bool apply_gain, bool out8, cudaStream_t s);
-// setup: fixed-point map + distance table of one camera (dist: CV_32FC1 output of distanceTransform)
-int launch_build_feather_table(const ProjParams &p, int tl_x, int tl_y, const DImage &dist, uint2 *table, size_t tstep, int tpad, cudaStream_t s);
+// setup: resolved-tap + distance table of one camera (dist: CV_32FC1 output of distanceTransform)
+int launch_build_feather_table(const ProjParams &p, int tl_x, int tl_y, const DImage &dist, int sw, int sh, uint2 *table, size_t tstep, cudaStream_t s);
 // device self-test of SharedDiv against __fdiv_rn; returns the number of mismatching quotients
 int selftest_division(unsigned long long n, unsigned seed, unsigned long long *mismatches);
 int launch_band_fused(const BandFusedArgs &a, bool float_weights, bool not_top, bool final_band, bool out8, cudaStream_t s);

@@ -16,6 +16,7 @@ struct MbWarpCam {
 };
 struct MbWarpArgs {
     int n;
+    const uint2 *bilin_lut;   // 1024 x {hi, lo} bilinear product weights (sb_device.cuh)
     MbWarpCam cam[SB_MAX_CAMERAS];
 };
 
