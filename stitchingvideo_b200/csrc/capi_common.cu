@@ -48,6 +48,14 @@ int DevImage::create(int rows, int cols, int type)
     return SB_OK;
 }
 
+int DevImage::create_packed(int rows, int cols, int type)
+{
+    size_t step = ((size_t)cols * elem_size(type) + 15) & ~(size_t)15;
+    SB_TRY(buf.ensure(step * (size_t)(rows > 0 ? rows : 1) + 16));
+    v.data = buf.p; v.rows = rows; v.cols = cols; v.type = type; v.step = step;
+    return SB_OK;
+}
+
 int DevImage::create_zero(int rows, int cols, int type, cudaStream_t s)
 {
     SB_TRY(create(rows, cols, type));
@@ -73,9 +81,13 @@ int to_device(const sb_image &img, DevImage &stage, cudaStream_t s, DImage *out)
         out->data = img.data; out->rows = img.rows; out->cols = img.cols; out->type = img.type; out->step = img.step;
         return SB_OK;
     }
-    SB_TRY(stage.create(img.rows, img.cols, img.type));
-    if (img.rows > 0 && img.cols > 0)
-        SB_CUDA(cudaMemcpy2DAsync(stage.v.data, stage.v.step, img.data, img.step, (size_t)img.cols * elem_size(img.type), img.rows, cudaMemcpyHostToDevice, s));
+    SB_TRY(stage.create_packed(img.rows, img.cols, img.type));
+    if (img.rows > 0 && img.cols > 0) {
+        if (img.step == stage.v.step)       // contiguous on both sides: one linear DMA
+            SB_CUDA(cudaMemcpyAsync(stage.v.data, img.data, img.step * (size_t)(img.rows - 1) + (size_t)img.cols * elem_size(img.type), cudaMemcpyHostToDevice, s));
+        else
+            SB_CUDA(cudaMemcpy2DAsync(stage.v.data, stage.v.step, img.data, img.step, (size_t)img.cols * elem_size(img.type), img.rows, cudaMemcpyHostToDevice, s));
+    }
     *out = stage.v;
     return SB_OK;
 }
@@ -86,9 +98,13 @@ int from_device(const DImage &src, sb_image *dst, cudaStream_t s)
     if (!dst->data) return fail(SB_ERR_ASSERT, "output image has no data");
     if (dst->rows != src.rows || dst->cols != src.cols || dst->type != src.type)
         return fail(SB_ERR_ASSERT, "output image is %dx%d type %d, expected %dx%d type %d", dst->rows, dst->cols, dst->type, src.rows, src.cols, src.type);
-    if (src.rows > 0 && src.cols > 0)
-        SB_CUDA(cudaMemcpy2DAsync(dst->data, dst->step, src.data, src.step, (size_t)src.cols * elem_size(src.type), src.rows,
-                                  dst->device >= 0 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    if (src.rows > 0 && src.cols > 0) {
+        const cudaMemcpyKind kind = dst->device >= 0 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        if (dst->step == src.step)          // same pitch on both sides: one linear DMA
+            SB_CUDA(cudaMemcpyAsync(dst->data, src.data, src.step * (size_t)(src.rows - 1) + (size_t)src.cols * elem_size(src.type), kind, s));
+        else
+            SB_CUDA(cudaMemcpy2DAsync(dst->data, dst->step, src.data, src.step, (size_t)src.cols * elem_size(src.type), src.rows, kind, s));
+    }
     return SB_OK;
 }
 

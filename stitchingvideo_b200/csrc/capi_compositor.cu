@@ -152,8 +152,13 @@ int make_slot(sb_compositor *c, Slot &s)
         s.rband.resize(levels + 1);
         for (int l = 1; l <= levels; ++l) SB_TRY(s.rband[l].create(s.acc[l].v.rows, s.acc[l].v.cols, 8));
     }
+    // packed rows: the device->host copy of the panorama into a contiguous host image is one linear DMA
     SB_TRY(s.out.create(c->dst_roi_final.height, c->dst_roi_final.width, c->cfg.output_type));
+    if (((size_t)c->dst_roi_final.width * elem_size(c->cfg.output_type)) % 4 == 0) {
+        s.out.v.step = (size_t)c->dst_roi_final.width * elem_size(c->cfg.output_type);
+    }
     SB_TRY(s.out_mask.create(c->dst_roi_final.height, c->dst_roi_final.width, SB_8UC1));
+    if (c->dst_roi_final.width % 4 == 0) s.out_mask.v.step = (size_t)c->dst_roi_final.width;
     return SB_OK;
 }
 

@@ -80,6 +80,9 @@ struct DevImage {
     DevBuf buf;
     DImage v;
     int create(int rows, int cols, int type);   // contents undefined
+    // rows packed back to back (pitch = row bytes rounded up to 16): host<->device transfers of
+    // contiguous host images become one linear DMA instead of a pitched 2D copy
+    int create_packed(int rows, int cols, int type);
     int create_zero(int rows, int cols, int type, cudaStream_t s);
 };
 
