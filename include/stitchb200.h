@@ -216,6 +216,38 @@ int  sb_compositor_marked_ms(sb_compositor *c, float *ms);
  * {"name", "ms", "bytes" (algorithmic bytes of that launch)} into buf. */
 int  sb_compositor_profile_frame(sb_compositor *c, const sb_image *srcs, char *buf, size_t cap);
 
+/* =====================================================================================
+ * Latency ("strip") mode — SURVEY.md §8e, BASELINE.json configs[4]: ONE very wide panorama cut into
+ * `world` column strips (boundaries are multiples of 2^num_bands of the padded panorama), one rank per
+ * strip.  Multi-band path.  The reference has no counterpart (it bounds the work per image with the
+ * padded sub-rectangle of blenders.cpp:242-264); results are bit-identical to the unsplit panorama.
+ * One frame on every rank, in lock step (stitchingvideo_b200/strips.py drives this over NCCL send/recv):
+ *     strip_warp(srcs)
+ *     for l = 0 .. num_bands:   exchange(SB_HALO_GAUSS, l);  if l < num_bands: strip_down(l)
+ *     for l = num_bands .. 0:   strip_band(l);               if l >= 1: exchange(SB_HALO_RESTORED, l)
+ *     strip_result(...)
+ * exchange(what, l) = for both sides: strip_pack into a device buffer, send it to that neighbour, receive the
+ * neighbour's buffer, strip_unpack.  Everything is asynchronous on the handle's stream (set_stream lets it
+ * share the stream the collective library is ordered with); strip_result synchronises.
+ * ===================================================================================== */
+enum { SB_HALO_GAUSS = 0,      /* 2 columns of every camera's Gaussian level (pyrDown / Laplacian pyrUp taps) */
+       SB_HALO_RESTORED = 1 }; /* 1 column of the restored band (collapse pyrUp taps), levels 1..num_bands */
+enum { SB_SIDE_LEFT = 0, SB_SIDE_RIGHT = 1 };
+int  sb_compositor_num_bands(const sb_compositor *c);      /* effective number of bands (blenders.cpp:205-209) */
+int  sb_compositor_set_strip(sb_compositor *c, int rank, int world);
+/* columns [*x0, *x1) of the final panorama that strip `rank` of `world` produces */
+int  sb_compositor_strip_range(const sb_compositor *c, int rank, int world, int *x0, int *x1);
+/* run slot 0 on the caller's CUDA stream (a cudaStream_t) */
+int  sb_compositor_set_stream(sb_compositor *c, void *cuda_stream);
+int  sb_compositor_strip_halo_bytes(sb_compositor *c, int what, int level, int side, size_t *send_bytes, size_t *recv_bytes);
+int  sb_compositor_strip_pack(sb_compositor *c, int what, int level, int side, void *device_buf);
+int  sb_compositor_strip_unpack(sb_compositor *c, int what, int level, int side, const void *device_buf);
+int  sb_compositor_strip_warp(sb_compositor *c, const sb_image *srcs);
+int  sb_compositor_strip_down(sb_compositor *c, int level);
+int  sb_compositor_strip_band(sb_compositor *c, int level);
+/* this rank's columns of the panorama (and mask); data == NULL lends a view of the device buffer */
+int  sb_compositor_strip_result(sb_compositor *c, sb_image *strip, sb_image *strip_mask);
+
 #ifdef __cplusplus
 }
 #endif

@@ -118,6 +118,17 @@ API = {
     "sb_compositor_mark": (C.c_int, [C.c_void_p, C.c_int]),
     "sb_compositor_marked_ms": (C.c_int, [C.c_void_p, _P(C.c_float)]),
     "sb_compositor_profile_frame": (C.c_int, [C.c_void_p, _P(SbImage), C.c_char_p, C.c_size_t]),
+    "sb_compositor_num_bands": (C.c_int, [C.c_void_p]),
+    "sb_compositor_set_strip": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "sb_compositor_strip_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(C.c_int), _P(C.c_int)]),
+    "sb_compositor_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sb_compositor_strip_halo_bytes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _P(C.c_size_t), _P(C.c_size_t)]),
+    "sb_compositor_strip_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sb_compositor_strip_unpack": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sb_compositor_strip_warp": (C.c_int, [C.c_void_p, _P(SbImage)]),
+    "sb_compositor_strip_down": (C.c_int, [C.c_void_p, C.c_int]),
+    "sb_compositor_strip_band": (C.c_int, [C.c_void_p, C.c_int]),
+    "sb_compositor_strip_result": (C.c_int, [C.c_void_p, _P(SbImage), _P(SbImage)]),
 }
 
 _lib = None
@@ -617,3 +628,51 @@ class Compositor:
         ms = C.c_float()
         _check(lib().sb_compositor_last_gpu_ms(self._h, slot, C.byref(ms)))
         return ms.value
+
+
+    # ---- latency ("strip") mode: see stitchingvideo_b200/strips.py for the driver ----
+    @property
+    def num_bands(self):
+        return int(lib().sb_compositor_num_bands(self._h))
+
+    def set_strip(self, rank, world):
+        _check(lib().sb_compositor_set_strip(self._h, rank, world))
+
+    def strip_range(self, rank, world):
+        x0, x1 = C.c_int(), C.c_int()
+        _check(lib().sb_compositor_strip_range(self._h, rank, world, C.byref(x0), C.byref(x1)))
+        return x0.value, x1.value
+
+    def set_stream(self, cuda_stream):
+        _check(lib().sb_compositor_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def strip_halo_bytes(self, what, level, side):
+        a, b = C.c_size_t(), C.c_size_t()
+        _check(lib().sb_compositor_strip_halo_bytes(self._h, what, level, side, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def strip_pack(self, what, level, side, device_ptr):
+        _check(lib().sb_compositor_strip_pack(self._h, what, level, side, C.c_void_p(device_ptr)))
+
+    def strip_unpack(self, what, level, side, device_ptr):
+        _check(lib().sb_compositor_strip_unpack(self._h, what, level, side, C.c_void_p(device_ptr)))
+
+    def strip_warp(self, frames):
+        arr, keep = self._srcs(frames)
+        _check(lib().sb_compositor_strip_warp(self._h, arr))
+
+    def strip_down(self, level):
+        _check(lib().sb_compositor_strip_down(self._h, level))
+
+    def strip_band(self, level):
+        _check(lib().sb_compositor_strip_band(self._h, level))
+
+    def strip_result(self, rank, world):
+        """-> (strip, strip_mask) host arrays holding this rank's columns of the panorama."""
+        x0, x1 = self.strip_range(rank, world)
+        strip = _empty(self.pano_size[1], x1 - x0, self.output_type)
+        smask = np.empty((self.pano_size[1], x1 - x0), np.uint8)
+        i0, k0 = _image(strip)
+        i1, k1 = _image(smask)
+        _check(lib().sb_compositor_strip_result(self._h, C.byref(i0), C.byref(i1)))
+        return strip, smask

@@ -107,6 +107,10 @@ struct sb_compositor {
     std::vector<DevBuf> mb_tile_mask;            // per band: per 32x8 tile bitmask of contributing cameras
     DevBuf tile_cams;                            // feather: per panorama tile, bitmask of contributing cameras
     bool fused = true;                           // panorama-centric fused kernels (default); false = staged reference-shaped path
+    // latency ("strip") mode: this handle produces padded-panorama columns [strip_x0, strip_x1)
+    int strip_rank = 0, strip_world = 1, strip_x0 = 0, strip_x1 = 0;
+    bool external_stream = false;
+    std::vector<DImage> strip_src;               // device views of the current frame's sources
 };
 
 namespace {
@@ -162,9 +166,9 @@ int make_slot(sb_compositor *c, Slot &s)
     return SB_OK;
 }
 
-void free_slot(Slot &s)
+void free_slot(Slot &s, bool external = false)
 {
-    if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+    if (s.stream && !external) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
     if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.ev_stop) cudaEventDestroy(s.ev_stop);
     s.stream = nullptr; s.ev_start = s.ev_stop = nullptr;
@@ -409,6 +413,106 @@ double img_bytes(const DImage &d) { return (double)d.rows * d.cols * elem_size(d
         if (s.prof) { SB_CUDA(cudaEventRecord(r_.e1, st)); s.prof->push_back(r_); }      \
     } while (0)
 
+// ---- the multi-band fast path, stage by stage.  [x0, x1) is the range of padded-panorama columns (level-0
+// coordinates, multiples of 2^num_bands) this call produces: the whole width for a frame on one GPU, one
+// column strip in latency mode, where the host exchanges halo columns between the stages.
+int mb_warp_stage(sb_compositor *c, Slot &s, const std::vector<DImage> &src, int x0, int x1)
+{
+    // K1: remap + gain + convertTo(16S) + copyMakeBorder for every camera, one launch
+    const int n = c->cfg.n_cameras;
+    cudaStream_t st = s.stream;
+    MbWarpArgs a{};
+    a.n = n;
+    a.bilin_lut = static_cast<const uint2 *>(c->bilin_lut.p);
+    double bytes = 0;
+    int mw = 0, mh = 0;
+    for (int i = 0; i < n; ++i) {
+        const Camera &cam = c->cams[i];
+        MbWarpCam &wc = a.cam[i];
+        wc.src = src[i].ptr<uint8_t>(); wc.sstep = src[i].step;
+        wc.table = static_cast<const uint2 *>(cam.mb_table.p); wc.tstep = cam.mb_tstep;
+        wc.g0 = static_cast<uint32_t *>(s.grgbx[i][0].buf.p); wc.gstep = s.grgbx[i][0].step;
+        wc.rw = cam.rw; wc.rh = cam.rh; wc.gain = cam.gain;
+        wc.cx0 = std::max(0, x0 - cam.rx); wc.cx1 = std::min(cam.rw, x1 - cam.rx);
+        if (wc.cx1 <= wc.cx0) { wc.cx0 = wc.cx1 = 0; continue; }
+        mw = std::max(mw, wc.cx1); mh = std::max(mh, cam.rh);
+        const double frac = (double)(wc.cx1 - wc.cx0) / cam.rw;
+        bytes += frac * (img_bytes(src[i]) + (double)cam.rw * cam.rh * (8 + 4));
+    }
+    if (mw == 0) return SB_OK;
+    PROF("mb_warp", bytes, launch_mb_warp(a, c->cfg.comp_kind == SB_COMP_GAIN, mw, mh, st));
+    return SB_OK;
+}
+
+int mb_down_stage(sb_compositor *c, Slot &s, int l, int x0, int x1)
+{
+    // K2: Gaussian level l -> l+1 for every camera, one launch
+    const int n = c->cfg.n_cameras;
+    cudaStream_t st = s.stream;
+    MbPyrArgs a{};
+    a.n = n;
+    double bytes = 0;
+    int mw = 0, mh = 0;
+    for (int i = 0; i < n; ++i) {
+        const Camera &cam = c->cams[i];
+        const RawImage &in = s.grgbx[i][l], &out = s.grgbx[i][l + 1];
+        a.cam[i].src = static_cast<const uint32_t *>(in.buf.p); a.cam[i].sstep = in.step; a.cam[i].sw = in.cols; a.cam[i].sh = in.rows;
+        a.cam[i].dst = static_cast<uint32_t *>(out.buf.p); a.cam[i].dstep = out.step;
+        const int rx = cam.rx >> (l + 1);
+        a.cam[i].ox0 = std::max(0, (x0 >> (l + 1)) - rx); a.cam[i].ox1 = std::min(out.cols, (x1 >> (l + 1)) - rx);
+        if (a.cam[i].ox1 <= a.cam[i].ox0) { a.cam[i].ox0 = a.cam[i].ox1 = 0; continue; }
+        mw = std::max(mw, a.cam[i].ox1); mh = std::max(mh, out.rows);
+        bytes += (in.bytes() + out.bytes()) * (double)(a.cam[i].ox1 - a.cam[i].ox0) / out.cols;
+    }
+    if (mw == 0) return SB_OK;
+    PROF("mb_pyr_down", bytes, launch_mb_pyr_down(a, mw, mh, st));
+    return SB_OK;
+}
+
+int mb_band_stage(sb_compositor *c, Slot &s, int l, int x0, int x1)
+{
+    // K3: band l for every camera, restored coarse -> fine
+    const sb_compositor_config &cfg = c->cfg;
+    const int n = cfg.n_cameras, nb = c->num_bands;
+    cudaStream_t st = s.stream;
+    MbBandArgs a{};
+    a.g.n = n;
+    const DImage &ws = c->wsum[l].v;
+    a.x_begin = x0 >> l; a.x_end = std::min(ws.cols, x1 >> l);
+    if (a.x_end <= a.x_begin) return SB_OK;
+    const double part = (double)(a.x_end - a.x_begin) / ws.cols;
+    double bytes = 0;
+    for (int i = 0; i < n; ++i) {
+        const Camera &cam = c->cams[i];
+        MbBandCam &bc = a.g.cam[i];
+        const RawImage &f = s.grgbx[i][l];
+        bc.fine = static_cast<const uint32_t *>(f.buf.p); bc.fstep = f.step;
+        if (l < nb) { bc.coarse = static_cast<const uint32_t *>(s.grgbx[i][l + 1].buf.p); bc.cstep = s.grgbx[i][l + 1].step; }
+        bc.weight = cam.w_pyr[l].v.data; bc.wstep = cam.w_pyr[l].v.step;
+        bc.rx = cam.rx >> l; bc.ry = cam.ry >> l; bc.rw = f.cols; bc.rh = f.rows;
+        const auto &sp = cam.spans[l];
+        const double frac = std::min(1.0, (double)((sp[1] - sp[0]) + (sp[3] - sp[2])) / std::max(1, f.cols));
+        bytes += part * frac * (f.bytes() * (l < nb ? 1.25 : 1.0) + img_bytes(cam.w_pyr[l].v));
+    }
+    a.g.lw = ws.cols; a.g.lh = ws.rows;
+    a.tile_mask = static_cast<const uint32_t *>(c->mb_tile_mask[l].p); a.tiles_x = div_up(ws.cols, 32);
+    a.wsum = ws.data; a.wsum_step = ws.step;
+    if (l < nb) { a.coarse_r = static_cast<const short4 *>(s.rband[l + 1].buf.p); a.coarse_r_step = s.rband[l + 1].step; bytes += part * s.rband[l + 1].bytes(); }
+    const bool fin = l == 0;
+    if (fin) {
+        a.out = s.out.v.data; a.out_step = s.out.v.step;
+        a.out_mask = s.want_mask ? s.out_mask.v.ptr<uint8_t>() : nullptr; a.mask_step = s.out_mask.v.step;
+        a.out_w = s.out.v.cols; a.out_h = s.out.v.rows;
+        a.x_end = std::min(a.x_end, a.out_w);
+        bytes += part * (img_bytes(s.out.v) + (s.want_mask ? img_bytes(s.out_mask.v) : 0) + (double)a.out_w * a.out_h * elem_size(ws.type));
+    } else {
+        a.out = s.rband[l].buf.p; a.out_step = s.rband[l].step;
+        bytes += part * (s.rband[l].bytes() + img_bytes(ws));
+    }
+    PROF(fin ? "mb_band_final" : "mb_band", bytes, launch_mb_band(a, cfg.weight_type == SB_32F, l < nb, fin, s.out.v.type == SB_8UC3, st));
+    return SB_OK;
+}
+
 int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
 {
     const sb_compositor_config &cfg = c->cfg;
@@ -419,72 +523,10 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
     // Blender::prepare zeroes the accumulators (blenders.cpp:71-78, 227-232): only the unfused
     // (camera-by-camera) path has accumulators in HBM; the weight sums are resident either way
     if (cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused && c->mb_fast && c->mb_variant == 1) {
-        const int nb = c->num_bands;
-        {   // K1: remap + gain + convertTo(16S) + copyMakeBorder for every camera, one launch
-            MbWarpArgs a{};
-            a.n = n;
-            a.bilin_lut = static_cast<const uint2 *>(c->bilin_lut.p);
-            double bytes = 0;
-            int mw = 0, mh = 0;
-            for (int i = 0; i < n; ++i) {
-                const Camera &cam = c->cams[i];
-                MbWarpCam &wc = a.cam[i];
-                wc.src = src[i].ptr<uint8_t>(); wc.sstep = src[i].step;
-                wc.table = static_cast<const uint2 *>(cam.mb_table.p); wc.tstep = cam.mb_tstep;
-                wc.g0 = static_cast<uint32_t *>(s.grgbx[i][0].buf.p); wc.gstep = s.grgbx[i][0].step;
-                wc.rw = cam.rw; wc.rh = cam.rh; wc.gain = cam.gain;
-                mw = std::max(mw, cam.rw); mh = std::max(mh, cam.rh);
-                bytes += img_bytes(src[i]) + (double)cam.rw * cam.rh * (8 + 4);
-            }
-            PROF("mb_warp", bytes, launch_mb_warp(a, gain_on, mw, mh, st));
-        }
-        for (int l = 0; l < nb; ++l) {   // K2: Gaussian level l -> l+1 for every camera, one launch
-            MbPyrArgs a{};
-            a.n = n;
-            double bytes = 0;
-            int mw = 0, mh = 0;
-            for (int i = 0; i < n; ++i) {
-                const RawImage &in = s.grgbx[i][l], &out = s.grgbx[i][l + 1];
-                a.cam[i].src = static_cast<const uint32_t *>(in.buf.p); a.cam[i].sstep = in.step; a.cam[i].sw = in.cols; a.cam[i].sh = in.rows;
-                a.cam[i].dst = static_cast<uint32_t *>(out.buf.p); a.cam[i].dstep = out.step;
-                mw = std::max(mw, out.cols); mh = std::max(mh, out.rows);
-                bytes += in.bytes() + out.bytes();
-            }
-            PROF("mb_pyr_down", bytes, launch_mb_pyr_down(a, mw, mh, st));
-        }
-        for (int l = nb; l >= 0; --l) {  // K3: bands coarse -> fine
-            MbBandArgs a{};
-            a.g.n = n;
-            double bytes = 0;
-            for (int i = 0; i < n; ++i) {
-                const Camera &cam = c->cams[i];
-                MbBandCam &bc = a.g.cam[i];
-                const RawImage &f = s.grgbx[i][l];
-                bc.fine = static_cast<const uint32_t *>(f.buf.p); bc.fstep = f.step;
-                if (l < nb) { bc.coarse = static_cast<const uint32_t *>(s.grgbx[i][l + 1].buf.p); bc.cstep = s.grgbx[i][l + 1].step; }
-                bc.weight = cam.w_pyr[l].v.data; bc.wstep = cam.w_pyr[l].v.step;
-                bc.rx = cam.rx >> l; bc.ry = cam.ry >> l; bc.rw = f.cols; bc.rh = f.rows;
-                const auto &sp = cam.spans[l];
-                const double frac = std::min(1.0, (double)((sp[1] - sp[0]) + (sp[3] - sp[2])) / std::max(1, f.cols));
-                bytes += frac * (f.bytes() * (l < nb ? 1.25 : 1.0) + img_bytes(cam.w_pyr[l].v));
-            }
-            const DImage &ws = c->wsum[l].v;
-            a.g.lw = ws.cols; a.g.lh = ws.rows;
-            a.tile_mask = static_cast<const uint32_t *>(c->mb_tile_mask[l].p); a.tiles_x = div_up(ws.cols, 32);
-            a.wsum = ws.data; a.wsum_step = ws.step;
-            if (l < nb) { a.coarse_r = static_cast<const short4 *>(s.rband[l + 1].buf.p); a.coarse_r_step = s.rband[l + 1].step; bytes += s.rband[l + 1].bytes(); }
-            const bool fin = l == 0;
-            if (fin) {
-                a.out = s.out.v.data; a.out_step = s.out.v.step;
-                a.out_mask = s.want_mask ? s.out_mask.v.ptr<uint8_t>() : nullptr; a.mask_step = s.out_mask.v.step;
-                a.out_w = s.out.v.cols; a.out_h = s.out.v.rows;
-                bytes += img_bytes(s.out.v) + (s.want_mask ? img_bytes(s.out_mask.v) : 0) + (double)a.out_w * a.out_h * elem_size(ws.type);
-            } else {
-                a.out = s.rband[l].buf.p; a.out_step = s.rband[l].step;
-                bytes += s.rband[l].bytes() + img_bytes(ws);
-            }
-            PROF(fin ? "mb_band_final" : "mb_band", bytes, launch_mb_band(a, cfg.weight_type == SB_32F, l < nb, fin, s.out.v.type == SB_8UC3, st));
-        }
+        const int nb = c->num_bands, W = c->dst_roi.width;
+        SB_TRY(mb_warp_stage(c, s, src, 0, W));
+        for (int l = 0; l < nb; ++l) SB_TRY(mb_down_stage(c, s, l, 0, W));
+        for (int l = nb; l >= 0; --l) SB_TRY(mb_band_stage(c, s, l, 0, W));
     } else if (cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused) {
         const int nb = c->num_bands;
         for (int i = 0; i < n; ++i) {
@@ -674,7 +716,7 @@ void sb_compositor_destroy(sb_compositor *c)
 {
     if (!c) return;
     DeviceGuard g(c->device);
-    for (auto &s : c->slots) free_slot(s);
+    for (size_t i = 0; i < c->slots.size(); ++i) free_slot(c->slots[i], i == 0 && c->external_stream);
     if (c->setup_stream) cudaStreamDestroy(c->setup_stream);
     delete c;
 }
@@ -844,6 +886,223 @@ int sb_compositor_last_gpu_ms(sb_compositor *c, int slot, float *ms)
     SB_CUDA(cudaEventSynchronize(s.ev_stop));
     SB_CUDA(cudaEventElapsedTime(ms, s.ev_start, s.ev_stop));
     return SB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------ latency ("strip") mode
+// one very wide panorama cut into column strips, one per rank.  Every stage of the multi-band
+// fast path runs on this rank's columns only; between stages the host exchanges the pyramid halo columns with
+// the two neighbouring ranks (NCCL send/recv): 2 columns of every camera's Gaussian level l (the pyrDown taps
+// of level l+1 and the pyrUp taps of the Laplacian of level l-1) and 1 column of every restored band (the
+// pyrUp taps of the collapse).  Buffers are full-size on every rank, so halo columns live at their true
+// coordinates and the kernels are the single-GPU kernels restricted to a column range.
+
+namespace {
+
+struct HaloSeg {
+    char *base;          // first byte of the buffer
+    size_t step;
+    int esz, rows;
+    int send_col, recv_col, ncols_send, ncols_recv;
+};
+
+void strip_bounds(const sb_compositor *c, int rank, int world, int *x0, int *x1)
+{
+    const int m = 1 << c->num_bands, units = c->dst_roi.width / m;
+    *x0 = (int)((long long)units * rank / world) * m;
+    *x1 = (int)((long long)units * (rank + 1) / world) * m;
+}
+
+// segments of one halo message, in camera order (both neighbours derive the same list from the calibration)
+int halo_segments(sb_compositor *c, int what, int level, int side, std::vector<HaloSeg> *out)
+{
+    out->clear();
+    SB_ASSERT(c->strip_world > 1);
+    SB_ASSERT(what == SB_HALO_GAUSS || what == SB_HALO_RESTORED);
+    SB_ASSERT(side == SB_SIDE_LEFT || side == SB_SIDE_RIGHT);
+    const int nb = c->num_bands;
+    const int B = side == SB_SIDE_LEFT ? c->strip_x0 : c->strip_x1;
+    if (B <= 0 || B >= c->dst_roi.width) return SB_OK;      // panorama edge: no neighbour on this side
+    const int Bl = B >> level;
+    Slot &s = c->slots[0];
+    if (what == SB_HALO_GAUSS) {
+        SB_ASSERT(level >= 0 && level <= nb);
+        for (int i = 0; i < c->cfg.n_cameras; ++i) {
+            RawImage &g = s.grgbx[i][level];
+            const int rx = c->cams[i].rx >> level, rw = g.cols;
+            if (!(rx < Bl && Bl < rx + rw)) continue;       // the feed rect does not straddle the boundary
+            const int lo = std::max(Bl - 2, rx) - rx, mid = Bl - rx, hi = std::min(Bl + 2, rx + rw) - rx;
+            HaloSeg h{static_cast<char *>(g.buf.p), g.step, 4, g.rows, 0, 0, 0, 0};
+            if (side == SB_SIDE_RIGHT) { h.send_col = lo; h.ncols_send = mid - lo; h.recv_col = mid; h.ncols_recv = hi - mid; }
+            else                       { h.send_col = mid; h.ncols_send = hi - mid; h.recv_col = lo; h.ncols_recv = mid - lo; }
+            out->push_back(h);
+        }
+    } else {
+        SB_ASSERT(level >= 1 && level <= nb);
+        RawImage &r = s.rband[level];
+        HaloSeg h{static_cast<char *>(r.buf.p), r.step, 8, r.rows, 0, 0, 1, 1};
+        if (side == SB_SIDE_RIGHT) { h.send_col = Bl - 1; h.recv_col = Bl; }
+        else                       { h.send_col = Bl; h.recv_col = Bl - 1; }
+        out->push_back(h);
+    }
+    return SB_OK;
+}
+
+int strip_ready(sb_compositor *c)
+{
+    SB_ASSERT(c);
+    if (c->strip_world <= 1) return fail(SB_ERR_ASSERT, "strip mode is not enabled: call sb_compositor_set_strip first");
+    return SB_OK;
+}
+
+}  // namespace
+
+int sb_compositor_set_strip(sb_compositor *c, int rank, int world)
+{
+    SB_ASSERT(c && world >= 1 && rank >= 0 && rank < world);
+    if (c->cfg.blender_kind != SB_BLEND_MULTI_BAND || !c->mb_fast)
+        return fail(SB_ERR_NOT_IMPL, "strip mode is implemented for the multi-band fast path (MultiBandBlender, sources <= 4096 px)");
+    const int m = 1 << c->num_bands;
+    if (world > 1 && c->dst_roi.width / m / world < 2)
+        return fail(SB_ERR_ASSERT, "panorama too narrow for %d strips: every strip needs at least 2 * 2^num_bands columns", world);
+    for (auto &s : c->slots) if (s.busy) return fail(SB_ERR_ASSERT, "set_strip with frames in flight");
+    c->strip_rank = rank; c->strip_world = world;
+    strip_bounds(c, rank, world, &c->strip_x0, &c->strip_x1);
+    c->fused = true; c->mb_variant = 1;
+    return SB_OK;
+}
+
+int sb_compositor_strip_range(const sb_compositor *c, int rank, int world, int *x0, int *x1)
+{
+    SB_ASSERT(c && x0 && x1 && world >= 1 && rank >= 0 && rank < world);
+    strip_bounds(c, rank, world, x0, x1);
+    *x0 = std::min(*x0, c->dst_roi_final.width);
+    *x1 = std::min(*x1, c->dst_roi_final.width);
+    return SB_OK;
+}
+
+int sb_compositor_set_stream(sb_compositor *c, void *cuda_stream)
+{
+    SB_ASSERT(c && !c->slots.empty());
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    Slot &s = c->slots[0];
+    if (s.busy) return fail(SB_ERR_ASSERT, "set_stream with a frame in flight");
+    if (s.stream && !c->external_stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+    s.stream = static_cast<cudaStream_t>(cuda_stream);
+    c->external_stream = true;
+    return SB_OK;
+}
+
+int sb_compositor_strip_halo_bytes(sb_compositor *c, int what, int level, int side, size_t *send_bytes, size_t *recv_bytes)
+{
+    SB_TRY(strip_ready(c));
+    SB_ASSERT(send_bytes && recv_bytes);
+    std::vector<HaloSeg> segs;
+    SB_TRY(halo_segments(c, what, level, side, &segs));
+    *send_bytes = *recv_bytes = 0;
+    for (const HaloSeg &h : segs) {
+        *send_bytes += (size_t)h.rows * h.ncols_send * h.esz;
+        *recv_bytes += (size_t)h.rows * h.ncols_recv * h.esz;
+    }
+    return SB_OK;
+}
+
+int sb_compositor_strip_pack(sb_compositor *c, int what, int level, int side, void *device_buf)
+{
+    SB_TRY(strip_ready(c));
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    std::vector<HaloSeg> segs;
+    SB_TRY(halo_segments(c, what, level, side, &segs));
+    char *dst = static_cast<char *>(device_buf);
+    for (const HaloSeg &h : segs) {
+        const size_t w = (size_t)h.ncols_send * h.esz;
+        if (w == 0) continue;
+        SB_ASSERT(device_buf);
+        SB_CUDA(cudaMemcpy2DAsync(dst, w, h.base + (size_t)h.send_col * h.esz, h.step, w, h.rows, cudaMemcpyDeviceToDevice, c->slots[0].stream));
+        dst += w * h.rows;
+    }
+    return SB_OK;
+}
+
+int sb_compositor_strip_unpack(sb_compositor *c, int what, int level, int side, const void *device_buf)
+{
+    SB_TRY(strip_ready(c));
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    std::vector<HaloSeg> segs;
+    SB_TRY(halo_segments(c, what, level, side, &segs));
+    const char *src = static_cast<const char *>(device_buf);
+    for (const HaloSeg &h : segs) {
+        const size_t w = (size_t)h.ncols_recv * h.esz;
+        if (w == 0) continue;
+        SB_ASSERT(device_buf);
+        SB_CUDA(cudaMemcpy2DAsync(h.base + (size_t)h.recv_col * h.esz, h.step, src, w, w, h.rows, cudaMemcpyDeviceToDevice, c->slots[0].stream));
+        src += w * h.rows;
+    }
+    return SB_OK;
+}
+
+int sb_compositor_strip_warp(sb_compositor *c, const sb_image *srcs)
+{
+    SB_TRY(strip_ready(c));
+    SB_ASSERT(srcs);
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    Slot &s = c->slots[0];
+    const int n = c->cfg.n_cameras;
+    c->strip_src.resize(n);
+    for (int i = 0; i < n; ++i) {
+        SB_ASSERT(srcs[i].type == SB_8UC3 && srcs[i].rows == c->cfg.src_size.height && srcs[i].cols == c->cfg.src_size.width);
+        SB_TRY(to_device(srcs[i], s.src[i], s.stream, &c->strip_src[i]));
+    }
+    s.want_mask = true;
+    return mb_warp_stage(c, s, c->strip_src, c->strip_x0, c->strip_x1);
+}
+
+int sb_compositor_strip_down(sb_compositor *c, int level)
+{
+    SB_TRY(strip_ready(c));
+    SB_ASSERT(level >= 0 && level < c->num_bands);
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    return mb_down_stage(c, c->slots[0], level, c->strip_x0, c->strip_x1);
+}
+
+int sb_compositor_strip_band(sb_compositor *c, int level)
+{
+    SB_TRY(strip_ready(c));
+    SB_ASSERT(level >= 0 && level <= c->num_bands);
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    return mb_band_stage(c, c->slots[0], level, c->strip_x0, c->strip_x1);
+}
+
+int sb_compositor_strip_result(sb_compositor *c, sb_image *strip, sb_image *strip_mask)
+{
+    SB_TRY(strip_ready(c));
+    SB_ASSERT(strip);
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    Slot &s = c->slots[0];
+    const int x0 = std::min(c->strip_x0, s.out.v.cols), x1 = std::min(c->strip_x1, s.out.v.cols);
+    DImage v = s.out.v, m = s.out_mask.v;
+    v.data = static_cast<char *>(v.data) + (size_t)x0 * elem_size(v.type); v.cols = x1 - x0;
+    m.data = static_cast<char *>(m.data) + x0; m.cols = x1 - x0;
+    if (!strip->data) lend(v, c->device, strip);
+    else SB_TRY(from_device(v, strip, s.stream));
+    if (strip_mask) {
+        if (!strip_mask->data) lend(m, c->device, strip_mask);
+        else SB_TRY(from_device(m, strip_mask, s.stream));
+    }
+    SB_CUDA(cudaStreamSynchronize(s.stream));
+    return SB_OK;
+}
+
+int sb_compositor_num_bands(const sb_compositor *c)
+{
+    return c ? c->num_bands : -1;
 }
 
 }  // extern "C"

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) k_mb_warp(const __grid_constant__ MbWarpA
 {
     const MbWarpCam &c = a.cam[blockIdx.z];
     const int px = blockIdx.x * 32 + threadIdx.x, py0 = blockIdx.y * (8 * MB_WARP_ROWS) + threadIdx.y;
-    if (px >= c.rw || py0 >= c.rh) return;
+    if (px >= c.cx1 || px < c.cx0 || py0 >= c.rh) return;
     uint2 t[MB_WARP_ROWS];
 #pragma unroll
     for (int r = 0; r < MB_WARP_ROWS; ++r) {
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) k_mb_pyr_down(const __grid_constant__ MbP
     const MbPyrCam &c = a.cam[blockIdx.z];
     const int x2 = blockIdx.x * 32 + threadIdx.x, y2 = blockIdx.y * 8 + threadIdx.y;
     const int dw = (c.sw + 1) >> 1, dh = (c.sh + 1) >> 1;
-    if (2 * x2 >= dw || 2 * y2 >= dh) return;
+    if (2 * x2 >= dw || 2 * y2 >= dh || 2 * x2 + 1 < c.ox0 || 2 * x2 >= c.ox1) return;
     const int ix = 4 * x2 - 2, iy = 4 * y2 - 2;            // top-left of the 7x7 input window
     const bool interior = ix >= 0 && ix + 6 < c.sw && iy >= 0 && iy + 6 < c.sh;
     unsigned ha02[7], ha1[7], hb02[7], hb1[7];              // horizontal sums of output columns 2*x2 and 2*x2+1, per input row
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) k_mb_band(const __grid_constant__ MbBandA
     // block = 32 x 8 threads = 64 x 16 band pixels = 2 x 2 mask tiles of 32 x 8
     const int X0 = (blockIdx.x * 32 + threadIdx.x) * 2, Y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
     const int lw = FINAL ? a.out_w : a.g.lw, lh = FINAL ? a.out_h : a.g.lh;       // band 0 is cropped to dst_roi_final_
-    if (X0 >= lw || Y0 >= lh) return;
+    if (X0 >= lw || Y0 >= lh || X0 + 1 < a.x_begin || X0 >= a.x_end) return;
     uint32_t cams = __ldg(a.tile_mask + (Y0 >> 3) * a.tiles_x + (X0 >> 5));       // the 2x2 block lies inside one 32x8 mask tile
 
     int acc[2][2][3];

@@ -13,6 +13,7 @@ struct MbWarpCam {
     size_t gstep;
     int rw, rh;            // padded feed rect (blenders.cpp:241-269)
     float gain;
+    int cx0, cx1;          // columns of the rect to produce (strip mode; whole rect: 0, rw)
 };
 struct MbWarpArgs {
     int n;
@@ -26,6 +27,7 @@ struct MbPyrCam {
     int sw, sh;
     uint32_t *dst;         // ((sw+1)/2, (sh+1)/2)
     size_t dstep;
+    int ox0, ox1;          // output columns to produce (strip mode; whole level: 0, (sw+1)/2)
 };
 struct MbPyrArgs {
     int n;
@@ -59,6 +61,7 @@ struct MbBandArgs {
     uint8_t *out_mask;
     size_t mask_step;
     int out_w, out_h;        // band 0 only: dst_roi_final_ size
+    int x_begin, x_end;      // band columns to produce (strip mode; whole band: 0, lw)
 };
 
 int launch_mb_tap_table(const ProjParams &p, int tl_x, int tl_y, int ww, int wh, int left, int top, int sw, int sh,
