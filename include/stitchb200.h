@@ -235,6 +235,10 @@ enum { SB_HALO_GAUSS = 0,      /* 2 columns of every camera's Gaussian level (py
 enum { SB_SIDE_LEFT = 0, SB_SIDE_RIGHT = 1 };
 int  sb_compositor_num_bands(const sb_compositor *c);      /* effective number of bands (blenders.cpp:205-209) */
 int  sb_compositor_set_strip(sb_compositor *c, int rank, int world);
+/* recompute != 0: no exchange at all — every rank recomputes the halo columns itself (about 94 level-0 columns per
+ * side for 5 bands, SURVEY.md §8e "alternative with zero comms"); strip_compose then runs a whole frame. */
+int  sb_compositor_set_strip_halo(sb_compositor *c, int recompute);
+int  sb_compositor_strip_compose(sb_compositor *c, const sb_image *srcs);
 /* columns [*x0, *x1) of the final panorama that strip `rank` of `world` produces */
 int  sb_compositor_strip_range(const sb_compositor *c, int rank, int world, int *x0, int *x1);
 /* run slot 0 on the caller's CUDA stream (a cudaStream_t) */

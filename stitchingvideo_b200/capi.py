@@ -120,6 +120,8 @@ API = {
     "sb_compositor_profile_frame": (C.c_int, [C.c_void_p, _P(SbImage), C.c_char_p, C.c_size_t]),
     "sb_compositor_num_bands": (C.c_int, [C.c_void_p]),
     "sb_compositor_set_strip": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "sb_compositor_set_strip_halo": (C.c_int, [C.c_void_p, C.c_int]),
+    "sb_compositor_strip_compose": (C.c_int, [C.c_void_p, _P(SbImage)]),
     "sb_compositor_strip_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(C.c_int), _P(C.c_int)]),
     "sb_compositor_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sb_compositor_strip_halo_bytes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _P(C.c_size_t), _P(C.c_size_t)]),
@@ -637,6 +639,14 @@ class Compositor:
 
     def set_strip(self, rank, world):
         _check(lib().sb_compositor_set_strip(self._h, rank, world))
+
+    def set_strip_halo(self, recompute):
+        _check(lib().sb_compositor_set_strip_halo(self._h, 1 if recompute else 0))
+
+    def strip_compose(self, frames):
+        """Recompute-halo mode: every stage of one frame on this rank's columns, no exchange; asynchronous."""
+        arr, keep = self._srcs(frames)
+        _check(lib().sb_compositor_strip_compose(self._h, arr))
 
     def strip_range(self, rank, world):
         x0, x1 = C.c_int(), C.c_int()

@@ -109,6 +109,9 @@ struct sb_compositor {
     bool fused = true;                           // panorama-centric fused kernels (default); false = staged reference-shaped path
     // latency ("strip") mode: this handle produces padded-panorama columns [strip_x0, strip_x1)
     int strip_rank = 0, strip_world = 1, strip_x0 = 0, strip_x1 = 0;
+    bool strip_recompute = false;                // halo columns recomputed locally instead of exchanged
+    // per level: Gaussian columns [g_lo, g_hi) and band columns [b_lo, b_hi) this rank produces (level coordinates)
+    std::vector<int> g_lo, g_hi, b_lo, b_hi;
     bool external_stream = false;
     std::vector<DImage> strip_src;               // device views of the current frame's sources
 };
@@ -444,7 +447,8 @@ int mb_warp_stage(sb_compositor *c, Slot &s, const std::vector<DImage> &src, int
     return SB_OK;
 }
 
-int mb_down_stage(sb_compositor *c, Slot &s, int l, int x0, int x1)
+// [ox0, ox1): columns of level l+1 (panorama level coordinates) to produce
+int mb_down_stage(sb_compositor *c, Slot &s, int l, int ox0, int ox1)
 {
     // K2: Gaussian level l -> l+1 for every camera, one launch
     const int n = c->cfg.n_cameras;
@@ -459,7 +463,7 @@ int mb_down_stage(sb_compositor *c, Slot &s, int l, int x0, int x1)
         a.cam[i].src = static_cast<const uint32_t *>(in.buf.p); a.cam[i].sstep = in.step; a.cam[i].sw = in.cols; a.cam[i].sh = in.rows;
         a.cam[i].dst = static_cast<uint32_t *>(out.buf.p); a.cam[i].dstep = out.step;
         const int rx = cam.rx >> (l + 1);
-        a.cam[i].ox0 = std::max(0, (x0 >> (l + 1)) - rx); a.cam[i].ox1 = std::min(out.cols, (x1 >> (l + 1)) - rx);
+        a.cam[i].ox0 = std::max(0, ox0 - rx); a.cam[i].ox1 = std::min(out.cols, ox1 - rx);
         if (a.cam[i].ox1 <= a.cam[i].ox0) { a.cam[i].ox0 = a.cam[i].ox1 = 0; continue; }
         mw = std::max(mw, a.cam[i].ox1); mh = std::max(mh, out.rows);
         bytes += (in.bytes() + out.bytes()) * (double)(a.cam[i].ox1 - a.cam[i].ox0) / out.cols;
@@ -469,7 +473,8 @@ int mb_down_stage(sb_compositor *c, Slot &s, int l, int x0, int x1)
     return SB_OK;
 }
 
-int mb_band_stage(sb_compositor *c, Slot &s, int l, int x0, int x1)
+// [bx0, bx1): columns of band l (panorama level coordinates) to produce
+int mb_band_stage(sb_compositor *c, Slot &s, int l, int bx0, int bx1)
 {
     // K3: band l for every camera, restored coarse -> fine
     const sb_compositor_config &cfg = c->cfg;
@@ -478,7 +483,7 @@ int mb_band_stage(sb_compositor *c, Slot &s, int l, int x0, int x1)
     MbBandArgs a{};
     a.g.n = n;
     const DImage &ws = c->wsum[l].v;
-    a.x_begin = x0 >> l; a.x_end = std::min(ws.cols, x1 >> l);
+    a.x_begin = std::max(0, bx0); a.x_end = std::min(ws.cols, bx1);
     if (a.x_end <= a.x_begin) return SB_OK;
     const double part = (double)(a.x_end - a.x_begin) / ws.cols;
     double bytes = 0;
@@ -525,8 +530,8 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
     if (cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused && c->mb_fast && c->mb_variant == 1) {
         const int nb = c->num_bands, W = c->dst_roi.width;
         SB_TRY(mb_warp_stage(c, s, src, 0, W));
-        for (int l = 0; l < nb; ++l) SB_TRY(mb_down_stage(c, s, l, 0, W));
-        for (int l = nb; l >= 0; --l) SB_TRY(mb_band_stage(c, s, l, 0, W));
+        for (int l = 0; l < nb; ++l) SB_TRY(mb_down_stage(c, s, l, 0, W >> (l + 1)));
+        for (int l = nb; l >= 0; --l) SB_TRY(mb_band_stage(c, s, l, 0, W >> l));
     } else if (cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused) {
         const int nb = c->num_bands;
         for (int i = 0; i < n; ++i) {
@@ -948,6 +953,40 @@ int halo_segments(sb_compositor *c, int what, int level, int side, std::vector<H
     return SB_OK;
 }
 
+// Column ranges per level.  Exchange mode: exactly this rank's columns (the neighbours supply the halos).
+// Recompute mode: the ranges grow towards the coarse levels' taps so that no halo is ever needed —
+//   band l is produced on own +- e_l with e_0 = 0, e_l = ceil(e_{l-1} / 2) + 1 (collapse pyrUp taps),
+//   Gaussian level l on the hull of band l, the Laplacian pyrUp taps of band l-1 and the pyrDown taps of level l+1
+//   (about 2 * (2^num_bands) + ... = 94 level-0 columns per side for 5 bands).
+void strip_plan(sb_compositor *c)
+{
+    const int nb = c->num_bands;
+    c->g_lo.assign(nb + 1, 0); c->g_hi.assign(nb + 1, 0); c->b_lo.assign(nb + 1, 0); c->b_hi.assign(nb + 1, 0);
+    int e = 0;
+    for (int l = 0; l <= nb; ++l) {
+        const int lw = c->dst_roi.width >> l;
+        if (l > 0) e = (e + 1) / 2 + 1;
+        const int m = c->strip_recompute ? e : 0;
+        c->b_lo[l] = std::max(0, (c->strip_x0 >> l) - m);
+        c->b_hi[l] = std::min(lw, (c->strip_x1 >> l) + m);
+    }
+    for (int l = nb; l >= 0; --l) {
+        const int lw = c->dst_roi.width >> l;
+        int lo = c->b_lo[l], hi = c->b_hi[l];
+        if (c->strip_recompute) {
+            if (l >= 1) {      // Laplacian of band l-1: pyrUp taps of this level
+                lo = std::min(lo, (c->b_lo[l - 1] >> 1) - 1);
+                hi = std::max(hi, ((c->b_hi[l - 1] - 1) >> 1) + 2);
+            }
+            if (l < nb) {      // pyrDown taps of level l+1
+                lo = std::min(lo, 2 * c->g_lo[l + 1] - 2);
+                hi = std::max(hi, 2 * c->g_hi[l + 1] + 1);
+            }
+        }
+        c->g_lo[l] = std::max(0, lo); c->g_hi[l] = std::min(lw, hi);
+    }
+}
+
 int strip_ready(sb_compositor *c)
 {
     SB_ASSERT(c);
@@ -969,6 +1008,26 @@ int sb_compositor_set_strip(sb_compositor *c, int rank, int world)
     c->strip_rank = rank; c->strip_world = world;
     strip_bounds(c, rank, world, &c->strip_x0, &c->strip_x1);
     c->fused = true; c->mb_variant = 1;
+    strip_plan(c);
+    return SB_OK;
+}
+
+int sb_compositor_set_strip_halo(sb_compositor *c, int recompute)
+{
+    SB_ASSERT(c);
+    for (auto &s : c->slots) if (s.busy) return fail(SB_ERR_ASSERT, "set_strip_halo with frames in flight");
+    c->strip_recompute = recompute != 0;
+    strip_plan(c);
+    return SB_OK;
+}
+
+int sb_compositor_strip_compose(sb_compositor *c, const sb_image *srcs)
+{
+    SB_TRY(strip_ready(c));
+    if (!c->strip_recompute) return fail(SB_ERR_ASSERT, "strip_compose needs the recompute halo mode (exchange mode is driven stage by stage)");
+    SB_TRY(sb_compositor_strip_warp(c, srcs));
+    for (int l = 0; l < c->num_bands; ++l) SB_TRY(sb_compositor_strip_down(c, l));
+    for (int l = c->num_bands; l >= 0; --l) SB_TRY(sb_compositor_strip_band(c, l));
     return SB_OK;
 }
 
@@ -1058,7 +1117,7 @@ int sb_compositor_strip_warp(sb_compositor *c, const sb_image *srcs)
         SB_TRY(to_device(srcs[i], s.src[i], s.stream, &c->strip_src[i]));
     }
     s.want_mask = true;
-    return mb_warp_stage(c, s, c->strip_src, c->strip_x0, c->strip_x1);
+    return mb_warp_stage(c, s, c->strip_src, c->g_lo[0], c->g_hi[0]);
 }
 
 int sb_compositor_strip_down(sb_compositor *c, int level)
@@ -1067,7 +1126,7 @@ int sb_compositor_strip_down(sb_compositor *c, int level)
     SB_ASSERT(level >= 0 && level < c->num_bands);
     DeviceGuard g(c->device);
     if (!g.ok) return SB_ERR_CUDA;
-    return mb_down_stage(c, c->slots[0], level, c->strip_x0, c->strip_x1);
+    return mb_down_stage(c, c->slots[0], level, c->g_lo[level + 1], c->g_hi[level + 1]);
 }
 
 int sb_compositor_strip_band(sb_compositor *c, int level)
@@ -1076,7 +1135,7 @@ int sb_compositor_strip_band(sb_compositor *c, int level)
     SB_ASSERT(level >= 0 && level <= c->num_bands);
     DeviceGuard g(c->device);
     if (!g.ok) return SB_ERR_CUDA;
-    return mb_band_stage(c, c->slots[0], level, c->strip_x0, c->strip_x1);
+    return mb_band_stage(c, c->slots[0], level, c->b_lo[level], c->b_hi[level]);
 }
 
 int sb_compositor_strip_result(sb_compositor *c, sb_image *strip, sb_image *strip_mask)

@@ -99,16 +99,31 @@ class TorchTransport:
 
 
 class StripCompositor:
-    """One rank of the strip-mode panorama: a Compositor restricted to its columns + a transport."""
+    """One rank of the strip-mode panorama: a Compositor restricted to its columns + a transport.
 
-    def __init__(self, comp, rank, world, transport=None, device=None):
+    halo="exchange": pyramid halo columns travel between neighbouring ranks (send/recv, 2 * num_bands + 1
+    exchanges per frame).  halo="recompute": no communication at all — every rank recomputes the ~94 level-0
+    halo columns per side itself (SURVEY.md §8e "alternative with zero comms"); the lowest-latency choice
+    when strips are wide compared with the halo."""
+
+    def __init__(self, comp, rank, world, transport=None, device=None, halo="exchange"):
         comp.set_strip(rank, world)
-        self.comp, self.rank, self.world = comp, rank, world
-        self.transport = transport or TorchTransport(comp, rank, world, device)
+        self.comp, self.rank, self.world, self.halo = comp, rank, world, halo
+        comp.set_strip_halo(halo == "recompute")
+        if halo == "recompute":
+            self.transport = None
+            if device is not None and str(device) != "cpu":
+                import torch
+                comp.set_stream(torch.cuda.current_stream(device).cuda_stream)
+        else:
+            self.transport = transport or TorchTransport(comp, rank, world, device)
         self.steps = schedule(comp.num_bands)
 
     def enqueue(self, frames):
         """All stages of one frame, asynchronous on the compositor's stream."""
+        if self.halo == "recompute":
+            self.comp.strip_compose(frames)
+            return
         for step in self.steps:
             if step[0] == "exchange":
                 self.transport.exchange(step[1], step[2])
@@ -132,6 +147,18 @@ class StripCompositor:
         return pano, pmask
 
 
+def run_local_recompute(comps, frames):
+    """Recompute-halo mode on one device: every handle composes its strip independently."""
+    world = len(comps)
+    out = []
+    for r, c in enumerate(comps):
+        c.set_strip(r, world)
+        c.set_strip_halo(True)
+        c.strip_compose(frames)
+        out.append(c.strip_result(r, world))
+    return out
+
+
 def run_local(comps, frames):
     """Single-process simulation used by the 1-GPU parity test: `comps[r]` plays rank r (all on one device),
     the stages run in lock step and the halo messages are handed over through device buffers.
@@ -140,6 +167,7 @@ def run_local(comps, frames):
     world = len(comps)
     for r, c in enumerate(comps):
         c.set_strip(r, world)
+        c.set_strip_halo(False)
     dev = torch.device("cuda", comps[0].device)
     for step in schedule(comps[0].num_bands):
         if step[0] != "exchange":
