@@ -248,12 +248,25 @@ def _oracle_ctx(workload):
     return cal, spec
 
 
+def _have_ref():
+    """oracle/_ref: the reference's own blenders.cpp / warpers.cpp compiled against the OpenCV stand-in."""
+    try:
+        from oracle import ref as RF
+        return RF.available()
+    except Exception:
+        return False
+
+
+REF_NOTE = ("blending = the reference's own blenders.cpp (oracle/_ref, compiled where it lies on an OpenCV stand-in); "
+            "remap / gain / pyramids = the stand-in's primitives (C restatement of OpenCV 2.4.11)")
+
+
 def _oracle_frame(cal, spec, workload, idx):
     from stitchingvideo_b200 import rigs
     from oracle import pipeline as P
     frames = [rigs.frame(workload, idx, i, smooth=0) for i in range(spec["n_used"])]
     t = time.perf_counter()
-    P.compose(cal, frames, blender=spec["blender"], num_bands=5, gains=spec["gain_values"])
+    P.compose(cal, frames, blender=spec["blender"], num_bands=5, gains=spec["gain_values"], use_ref=_have_ref())
     return time.perf_counter() - t
 
 
@@ -263,9 +276,10 @@ def cpu_baseline(workload, sample_frames=4):
     _oracle_frame(cal, spec, workload, 0)
     ts = [_oracle_frame(cal, spec, workload, 1 + i) for i in range(sample_frames)]
     best = min(ts)
-    out = {"value": 1.0 / best, "unit": "frames/s", "cores": 1, "kind": "port",
+    out = {"value": 1.0 / best, "unit": "frames/s", "cores": 1, "kind": "reference" if _have_ref() else "port",
            "sample": "%d full frame sets of the same workload after 1 warm-up, best of %d (%.2f s each); "
                      "per-sequence maps/masks excluded like the GPU arm" % (sample_frames, sample_frames, best),
+           "implementation": REF_NOTE if _have_ref() else "oracle port (C restatement of the reference path)",
            "host_cpu": _cpu_model(), "host_cores": os.cpu_count()}
     try:
         out["cv2_all_cores"] = cv2_baseline(workload)
@@ -332,7 +346,7 @@ def run_reference(args):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libstitch_ref.so")) and False else "port"
+    kind = "reference" if _have_ref() else "port"
     ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_worker_init, initargs=(args.workload,)) as pool:
         for w in range(args.warmup):
@@ -350,6 +364,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
                              "sample": "each step = %d full frame sets, one per worker process (%d processes); "
                                        "per-sequence maps/masks built once per worker and excluded" % (cores, cores),
+                             "implementation": REF_NOTE if kind == "reference" else "oracle port (C restatement of the reference path)",
                              "host_cpu": _cpu_model()},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

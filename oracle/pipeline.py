@@ -30,9 +30,14 @@ class Calibration:
 
 
 def compose(cal, frames, blender="multiband", num_bands=5, weight_type=O.CV_32F, sharpness=0.02, gains=None,
-            output_8u=True):
-    """One frame set through warp -> gain -> convertTo(16S) -> feed -> blend -> convertTo(8U)."""
-    b = O.Blender(_BLEND[blender], num_bands, weight_type, sharpness)
+            output_8u=True, use_ref=False):
+    """One frame set through warp -> gain -> convertTo(16S) -> feed -> blend -> convertTo(8U).
+    use_ref: blend with the reference's own blenders.cpp (oracle/_ref) instead of the oracle's restatement."""
+    if use_ref:
+        from . import ref as RF
+        b = RF.Blender(_BLEND[blender], num_bands, weight_type, sharpness)
+    else:
+        b = O.Blender(_BLEND[blender], num_bands, weight_type, sharpness)
     b.prepare(cal.corners, cal.sizes)                                          # stitcher.cpp:296-300
     for i, f in enumerate(frames):
         xmap, ymap = cal.maps[i]

@@ -1,0 +1,167 @@
+// oracle/_ref — the reference's OWN sources of the compositing path, compiled where they lie
+// (/root/reference/.../src/{blenders,warpers,util}.cpp + the detail/*.hpp headers they include), unmodified,
+// against the OpenCV stand-in of include/opencv2 (primitives = the oracle's restatement of OpenCV 2.4.11).
+// TEST INFRASTRUCTURE: tests/test_ref_shim.py compares the oracle (oracle/so_stitch.c) with this library.
+// Not built: exposure_compensate.cpp (its feed() needs solve/sepFilter2D/resize; the per-frame apply() is the
+// two-line `image *= gain` / `multiply by the resized gain map`, exposure_compensate.cpp:150-153,225-246).
+//
+// precomp.hpp pulls in every OpenCV module (features2d, calib3d, ...); its include guard is defined here so that
+// only the headers the three sources really need are seen.
+#define __OPENCV_STITCHING_PRECOMP_H__
+#include <algorithm>
+#include <cmath>
+#include <functional>
+#include <iostream>
+#include <limits>
+#include <list>
+#include <queue>
+#include <set>
+#include <sstream>
+#include <utility>
+#include <vector>
+
+#include "opencv2/core/core.hpp"
+#include "opencv2/stitching/detail/blenders.hpp"
+#include "opencv2/stitching/detail/util.hpp"
+#include "opencv2/stitching/detail/warpers.hpp"
+
+#include REF_SRC(blenders.cpp)
+#include REF_SRC(util.cpp)
+#include REF_SRC(warpers.cpp)
+
+// ------------------------------------------------------------------------------------ C API (ctypes)
+using cv::Mat;
+static Mat wrap(const so_mat *m) { return Mat(m->rows, m->cols, m->type, m->data, m->step); }
+static int copy_out(const Mat &src, so_mat *dst)
+{
+    if (src.rows != dst->rows || src.cols != dst->cols || src.type() != dst->type) return -1;
+    for (int y = 0; y < src.rows; ++y)
+        std::memcpy((char *)dst->data + (size_t)y * dst->step, src.ptr<unsigned char>(y), (size_t)src.cols * src.elemSize());
+    return 0;
+}
+static cv::Ptr<cv::detail::RotationWarper> make_warper(int kind, float scale)
+{
+    switch (kind) {
+    case SO_WARP_PLANE: return new cv::detail::PlaneWarper(scale);
+    case SO_WARP_CYLINDRICAL: return new cv::detail::CylindricalWarper(scale);
+    case SO_WARP_SPHERICAL: return new cv::detail::SphericalWarper(scale);
+    }
+    return cv::Ptr<cv::detail::RotationWarper>();
+}
+static Mat mat3(const float *m)
+{
+    Mat r(3, 3, CV_32F);
+    for (int i = 0; i < 9; ++i) r.at<float>(i / 3, i % 3) = m[i];
+    return r;
+}
+
+struct ref_blender {
+    cv::Ptr<cv::detail::Blender> b;
+    cv::Rect roi;
+};
+
+extern "C" {
+
+const char *ref_version(void) { return "reference sources (blenders.cpp, warpers.cpp, util.cpp) on the OpenCV shim"; }
+
+ref_blender *ref_blender_create(int kind, int num_bands, int weight_type, float sharpness)
+{
+    try {
+        ref_blender *h = new ref_blender;
+        if (kind == cv::detail::Blender::MULTI_BAND) h->b = new cv::detail::MultiBandBlender(false, num_bands, weight_type);
+        else if (kind == cv::detail::Blender::FEATHER) h->b = new cv::detail::FeatherBlender(sharpness);
+        else h->b = cv::detail::Blender::createDefault(kind, false);
+        return h;
+    } catch (const cv::Exception &) { return nullptr; }
+}
+void ref_blender_destroy(ref_blender *h) { delete h; }
+int ref_blender_prepare(ref_blender *h, const int *corners_xy, const int *sizes_wh, int n)
+{
+    try {
+        std::vector<cv::Point> c;
+        std::vector<cv::Size> s;
+        for (int i = 0; i < n; ++i) { c.push_back(cv::Point(corners_xy[2 * i], corners_xy[2 * i + 1])); s.push_back(cv::Size(sizes_wh[2 * i], sizes_wh[2 * i + 1])); }
+        h->roi = cv::detail::resultRoi(c, s);              // util.cpp:127-140
+        h->b->prepare(c, s);                               // blenders.cpp:65-68
+        return 0;
+    } catch (const cv::Exception &e) { return e.code; }
+}
+void ref_blender_roi(const ref_blender *h, int roi_xywh[4]) { roi_xywh[0] = h->roi.x; roi_xywh[1] = h->roi.y; roi_xywh[2] = h->roi.width; roi_xywh[3] = h->roi.height; }
+int ref_blender_feed(ref_blender *h, const so_mat *img, const so_mat *mask, int tl_x, int tl_y)
+{
+    try { h->b->feed(wrap(img), wrap(mask), cv::Point(tl_x, tl_y)); return 0; } catch (const cv::Exception &e) { return e.code; }
+}
+int ref_blender_blend(ref_blender *h, so_mat *dst, so_mat *dst_mask)
+{
+    try {
+        Mat d, m;
+        h->b->blend(d, m);
+        return copy_out(d, dst) | copy_out(m, dst_mask);
+    } catch (const cv::Exception &e) { return e.code; }
+}
+int ref_create_laplace_pyr(const so_mat *img, int num_levels, so_mat *pyr)
+{
+    try {
+        std::vector<Mat> p;
+        cv::detail::createLaplacePyr(wrap(img).clone(), num_levels, p);
+        int rc = 0;
+        for (int i = 0; i <= num_levels; ++i) rc |= copy_out(p[i], &pyr[i]);
+        return rc;
+    } catch (const cv::Exception &e) { return e.code; }
+}
+int ref_restore_image_from_laplace_pyr(so_mat *pyr, int n)
+{
+    try {
+        std::vector<Mat> p;
+        for (int i = 0; i < n; ++i) p.push_back(wrap(&pyr[i]).clone());
+        cv::detail::restoreImageFromLaplacePyr(p);
+        return copy_out(p[0], &pyr[0]);
+    } catch (const cv::Exception &e) { return e.code; }
+}
+int ref_normalize_using_weight_map(const so_mat *weight, so_mat *src)
+{
+    try { Mat s = wrap(src); cv::detail::normalizeUsingWeightMap(wrap(weight), s); return 0; } catch (const cv::Exception &e) { return e.code; }
+}
+int ref_create_weight_map(const so_mat *mask, float sharpness, so_mat *weight)
+{
+    try { Mat w; cv::detail::createWeightMap(wrap(mask), sharpness, w); return copy_out(w, weight); } catch (const cv::Exception &e) { return e.code; }
+}
+
+// RotationWarper (warpers.hpp:53-72) through the reference's own RotationWarperBase<P> / projectors
+int ref_warp_roi(int kind, float scale, int src_w, int src_h, const float K[9], const float R[9], int roi_xywh[4])
+{
+    try {
+        cv::Rect r = make_warper(kind, scale)->warpRoi(cv::Size(src_w, src_h), mat3(K), mat3(R));
+        roi_xywh[0] = r.x; roi_xywh[1] = r.y; roi_xywh[2] = r.width; roi_xywh[3] = r.height;
+        return 0;
+    } catch (const cv::Exception &e) { return e.code; }
+}
+int ref_warp_point(int kind, float scale, const float pt[2], const float K[9], const float R[9], float uv[2])
+{
+    try {
+        cv::Point2f p = make_warper(kind, scale)->warpPoint(cv::Point2f(pt[0], pt[1]), mat3(K), mat3(R));
+        uv[0] = p.x; uv[1] = p.y;
+        return 0;
+    } catch (const cv::Exception &e) { return e.code; }
+}
+// xmap / ymap: (roi.height + 1) x (roi.width + 1) CV_32F with roi from ref_warp_roi minus one (Rect(tl, br))
+int ref_build_maps(int kind, float scale, int src_w, int src_h, const float K[9], const float R[9], int roi_xywh[4], so_mat *xmap, so_mat *ymap)
+{
+    try {
+        Mat xm, ym;
+        cv::Rect r = make_warper(kind, scale)->buildMaps(cv::Size(src_w, src_h), mat3(K), mat3(R), xm, ym);
+        roi_xywh[0] = r.x; roi_xywh[1] = r.y; roi_xywh[2] = r.width; roi_xywh[3] = r.height;
+        return copy_out(xm, xmap) | copy_out(ym, ymap);
+    } catch (const cv::Exception &e) { return e.code; }
+}
+int ref_warp(int kind, float scale, const so_mat *src, const float K[9], const float R[9], int interp, int border, int tl[2], so_mat *dst)
+{
+    try {
+        Mat d;
+        cv::Point p = make_warper(kind, scale)->warp(wrap(src), mat3(K), mat3(R), interp, border, d);
+        tl[0] = p.x; tl[1] = p.y;
+        return copy_out(d, dst);
+    } catch (const cv::Exception &e) { return e.code; }
+}
+
+}  // extern "C"

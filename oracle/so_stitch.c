@@ -56,6 +56,10 @@ static void mul3x3_f(const float A[9], const float B[9], float D[9])
             D[i * 3 + j] = A[i * 3 + 0] * B[0 * 3 + j] + A[i * 3 + 1] * B[1 * 3 + j] + A[i * 3 + 2] * B[2 * 3 + j];
 }
 
+/* exported for oracle/ref_shim: the Mat::inv() / Mat * Mat primitives behind the reference's setCameraParams */
+void so_inv3x3_f32(const float S[9], float D[9]) { inv3x3_f(S, D); }
+void so_mul3x3_f32(const float A[9], const float B[9], float D[9]) { mul3x3_f(A, B, D); }
+
 void so_projector_set(so_projector *p, int kind, float scale, const float K[9], const float R[9], const float T[3])
 {
     float kinv[9];

@@ -68,6 +68,9 @@ float so_sinf(float x);                   /* portable restatement of glibc 2.39 
 float so_cosf(float x);
 
 /* ---- warpers: warpers.cpp:50-78,171-212; warpers_inl.hpp:52-300 ---- */
+/* 3x3 CV_32F cv::invert / cv::gemm as OpenCV 2.4.11 computes them (used by setCameraParams, warpers.cpp:61-74) */
+void so_inv3x3_f32(const float S[9], float D[9]);
+void so_mul3x3_f32(const float A[9], const float B[9], float D[9]);
 void so_projector_set(so_projector *p, int kind, float scale, const float K[9], const float R[9], const float T[3]);
 void so_map_forward(const so_projector *p, float x, float y, float *u, float *v);
 void so_map_backward(const so_projector *p, float u, float v, float *x, float *y);
