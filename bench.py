@@ -183,6 +183,8 @@ def run_ours(args):
 
     # ---------------- roofline: per-kernel CUDA-event timing (separate pass, never the reported fps) ----------------
     comp.set_depth(1)
+    if args.variant is None and args.depth > 1:
+        comp.set_fused(12)      # profile the kernels the pipelined timed region launched (one launch per pyramid level)
     agg = {}
     for it in range(args.profile_frames + 1):
         recs = comp.profile_frame(dev_sets[it % n_sets])
@@ -383,7 +385,7 @@ def main():
     ap.add_argument("--profile-frames", type=int, default=5)
     ap.add_argument("--cpu-frames", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--variant", type=int, default=None, choices=[0, 1], help="fused kernel variant (default: library default)")
+    ap.add_argument("--variant", type=int, default=None, choices=[0, 1, 2], help="fused kernel variant: 10 + v is passed to set_fused (default: library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

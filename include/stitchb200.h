@@ -197,7 +197,9 @@ int  sb_compositor_camera_roi(const sb_compositor *c, int index, sb_rect *roi);
 int  sb_compositor_compose(sb_compositor *c, const sb_image *srcs, sb_image *pano, sb_image *pano_mask);
 /* fused != 0 (default): panorama-centric fused kernels (one pass per band / per frame);
  * fused == 0: the staged, camera-by-camera path shaped like the reference's feed/blend calls.
- * Both give identical results; the staged path is kept as a cross-check. */
+ * Both give identical results; the staged path is kept as a cross-check.  Values >= 10 are tuning hooks that pick a
+ * kernel variant of the fused path (10: CV_16S band kernels / one-pixel-per-thread feather, 11: default fast paths,
+ * 12 / 13: multi-band fast path with one launch per pyramid level / with the multi-level launches forced). */
 int  sb_compositor_set_fused(sb_compositor *c, int fused);
 /* Pipelined form for throughput: up to `depth` frame sets in flight, each on its own stream/slot.
  * enqueue returns a slot id; wait blocks until that slot's pano has landed in the buffers given

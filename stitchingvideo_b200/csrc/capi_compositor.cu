@@ -44,6 +44,9 @@ struct Camera {
     int ftx0 = 0, fty0 = 0, fntx = 0, fnty = 0;
     // panorama(-level) column ranges that hold non-zero weights, per level: [s0,s1) U [s2,s3)
     std::vector<std::array<int, 4>> spans;
+    // rect-local columns of Gaussian level l that the weighted pixels can see through the pyramid taps (two runs):
+    // everything else of the padded rect (most of a seam-straddling camera's panorama-wide rect) is never produced
+    std::vector<std::array<int, 4>> g_runs;
 };
 
 // pitched device buffer for the pixel formats outside the OpenCV type set (RGBX bytes, short4)
@@ -106,6 +109,10 @@ struct sb_compositor {
     bool mb_fast = false;                        // RGBX pyramid + tap-table path available (sources <= 4096 px)
     std::vector<DevBuf> mb_tile_mask;            // per band: per 32x8 tile bitmask of contributing cameras
     DevBuf tile_cams;                            // feather: per panorama tile, bitmask of contributing cameras
+    // coarse pyramid levels / bands in one cooperative launch each: -1 = automatic (on when a single frame is in
+    // flight: lowest latency; off when frames are pipelined over several slots: the small per-level launches of one
+    // frame then overlap with the big kernels of the others, which is worth more than the saved launches), 0 / 1 = forced
+    int mb_multilevel = -1;
     bool fused = true;                           // panorama-centric fused kernels (default); false = staged reference-shaped path
     // latency ("strip") mode: this handle produces padded-panorama columns [strip_x0, strip_x1)
     int strip_rank = 0, strip_world = 1, strip_x0 = 0, strip_x1 = 0;
@@ -206,6 +213,54 @@ int weight_spans(const DImage &w, int offset, DevBuf &scratch, cudaStream_t s, s
     return SB_OK;
 }
 
+// Which columns of each Gaussian level of a camera's padded rect can influence a weighted pixel?  Band l reads level l
+// where the weight is non-zero (spans[l]) and level l+1 at (x >> 1) +- 1 (Laplacian pyrUp taps); level l+1 is made
+// from level l columns [2a - 2, 2b + 1) (pyrDown taps).  Same recurrences as strip_plan, per run of the weight spans.
+void gaussian_runs(Camera &cam, int nb)
+{
+    cam.g_runs.assign(nb + 1, std::array<int, 4>{0, 0, 0, 0});
+    for (int run = 0; run < 2; ++run) {
+        std::vector<int> lo(nb + 1, 0), hi(nb + 1, 0);
+        for (int l = nb; l >= 0; --l) {
+            const int rx = cam.rx >> l, w = cam.w_pyr[l].v.cols;
+            int a = cam.spans[l][2 * run] - rx, b = cam.spans[l][2 * run + 1] - rx;      // band l (rect-local)
+            bool any = b > a;
+            if (l >= 1) {
+                const int rxf = cam.rx >> (l - 1);
+                const int fa = cam.spans[l - 1][2 * run] - rxf, fb = cam.spans[l - 1][2 * run + 1] - rxf;
+                if (fb > fa) {
+                    const int ca = (fa >> 1) - 1, cb = ((fb - 1) >> 1) + 2;
+                    a = any ? std::min(a, ca) : ca; b = any ? std::max(b, cb) : cb; any = true;
+                }
+            }
+            if (l < nb && hi[l + 1] > lo[l + 1]) {
+                const int da = 2 * lo[l + 1] - 2, db = 2 * hi[l + 1] + 1;
+                a = any ? std::min(a, da) : da; b = any ? std::max(b, db) : db; any = true;
+            }
+            if (!any) { lo[l] = hi[l] = 0; continue; }
+            lo[l] = std::max(0, a); hi[l] = std::min(w, b);
+        }
+        for (int l = 0; l <= nb; ++l) { cam.g_runs[l][2 * run] = lo[l]; cam.g_runs[l][2 * run + 1] = hi[l]; }
+    }
+    for (int l = 0; l <= nb; ++l) {      // merge overlapping runs
+        auto &g = cam.g_runs[l];
+        if (g[3] > g[2] && g[1] > g[0] && g[2] <= g[1]) { g[1] = std::max(g[1], g[3]); g[0] = std::min(g[0], g[2]); g[2] = g[3] = 0; }
+    }
+}
+
+// runs of `g` (rect-local) clipped to the panorama-level range [x0, x1) given in panorama coordinates
+void clip_runs(const std::array<int, 4> &g, int rx, int x0, int x1, int out[4], int *max_col, double *cols)
+{
+    *cols = 0;
+    for (int r = 0; r < 2; ++r) {
+        int a = std::max(g[2 * r], x0 - rx), b = std::min(g[2 * r + 1], x1 - rx);
+        if (b <= a) a = b = 0;
+        out[2 * r] = a; out[2 * r + 1] = b;
+        *max_col = std::max(*max_col, b);
+        *cols += b - a;
+    }
+}
+
 // calibration-time work: geometry, tables, masks, weights
 int setup(sb_compositor *c)
 {
@@ -214,6 +269,7 @@ int setup(sb_compositor *c)
     const int n = cfg.n_cameras;
     c->cams.resize(n);
     int tlx = INT32_MAX, tly = INT32_MAX, brx = INT32_MIN, bry = INT32_MIN;
+    SB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
     SB_TRY(c->bilin_lut.ensure(1024 * sizeof(uint2)));
     SB_TRY(launch_build_bilin_lut(static_cast<uint2 *>(c->bilin_lut.p), s));
     DevImage ones, xmap, ymap;
@@ -310,6 +366,7 @@ int setup(sb_compositor *c)
                 x_tl /= 2; y_tl /= 2;
             }
         }
+        for (int i = 0; i < n; ++i) gaussian_runs(c->cams[i], nb);
         // fast path tables: resolved taps per padded pixel, camera bitmask per band tile
         c->mb_fast = cfg.src_size.width <= 4096 && cfg.src_size.height <= 4096;
         if (c->mb_fast) {
@@ -394,7 +451,6 @@ int setup(sb_compositor *c)
             SB_CUDA(cudaMemcpyAsync(&h_status, status, sizeof h_status, cudaMemcpyDeviceToHost, s));
             SB_CUDA(cudaStreamSynchronize(s));
             c->feather_tma = h_status == 0 && n <= 16;
-            SB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
         }
         SB_CUDA(cudaStreamSynchronize(s));
     }
@@ -436,57 +492,89 @@ int mb_warp_stage(sb_compositor *c, Slot &s, const std::vector<DImage> &src, int
         wc.table = static_cast<const uint2 *>(cam.mb_table.p); wc.tstep = cam.mb_tstep;
         wc.g0 = static_cast<uint32_t *>(s.grgbx[i][0].buf.p); wc.gstep = s.grgbx[i][0].step;
         wc.rw = cam.rw; wc.rh = cam.rh; wc.gain = cam.gain;
-        wc.cx0 = std::max(0, x0 - cam.rx); wc.cx1 = std::min(cam.rw, x1 - cam.rx);
-        if (wc.cx1 <= wc.cx0) { wc.cx0 = wc.cx1 = 0; continue; }
-        mw = std::max(mw, wc.cx1); mh = std::max(mh, cam.rh);
-        const double frac = (double)(wc.cx1 - wc.cx0) / cam.rw;
-        bytes += frac * (img_bytes(src[i]) + (double)cam.rw * cam.rh * (8 + 4));
+        double cols = 0;
+        int cmax = 0;
+        clip_runs(cam.g_runs[0], cam.rx, x0, x1, wc.cx, &cmax, &cols);
+        if (cols == 0) continue;
+        mw = std::max(mw, cmax); mh = std::max(mh, cam.rh);
+        // the source pixels behind the produced columns are gathered ~once; table entry in, RGBX pixel out
+        bytes += img_bytes(src[i]) * std::min(1.0, cols / (double)std::min(cam.ww, src[i].cols)) + cols * cam.rh * (8 + 4);
     }
     if (mw == 0) return SB_OK;
     PROF("mb_warp", bytes, launch_mb_warp(a, c->cfg.comp_kind == SB_COMP_GAIN, mw, mh, st));
     return SB_OK;
 }
 
-// [ox0, ox1): columns of level l+1 (panorama level coordinates) to produce
-int mb_down_stage(sb_compositor *c, Slot &s, int l, int ox0, int ox1)
+// [ox0, ox1): columns of level l+1 (panorama level coordinates) to produce.  Returns false when there is nothing to do.
+bool fill_down(sb_compositor *c, Slot &s, int l, int ox0, int ox1, MbPyrArgs &a, int tiles_x[SB_MAX_CAMERAS], int tiles[SB_MAX_CAMERAS],
+               int &mw, int &mh, double &bytes)
 {
-    // K2: Gaussian level l -> l+1 for every camera, one launch
     const int n = c->cfg.n_cameras;
-    cudaStream_t st = s.stream;
-    MbPyrArgs a{};
+    a = MbPyrArgs{};
     a.n = n;
-    double bytes = 0;
-    int mw = 0, mh = 0;
+    mw = mh = 0;
     for (int i = 0; i < n; ++i) {
         const Camera &cam = c->cams[i];
         const RawImage &in = s.grgbx[i][l], &out = s.grgbx[i][l + 1];
         a.cam[i].src = static_cast<const uint32_t *>(in.buf.p); a.cam[i].sstep = in.step; a.cam[i].sw = in.cols; a.cam[i].sh = in.rows;
         a.cam[i].dst = static_cast<uint32_t *>(out.buf.p); a.cam[i].dstep = out.step;
         const int rx = cam.rx >> (l + 1);
-        a.cam[i].ox0 = std::max(0, ox0 - rx); a.cam[i].ox1 = std::min(out.cols, ox1 - rx);
-        if (a.cam[i].ox1 <= a.cam[i].ox0) { a.cam[i].ox0 = a.cam[i].ox1 = 0; continue; }
-        mw = std::max(mw, a.cam[i].ox1); mh = std::max(mh, out.rows);
-        bytes += (in.bytes() + out.bytes()) * (double)(a.cam[i].ox1 - a.cam[i].ox0) / out.cols;
+        double cols = 0;
+        int cmax = 0;
+        clip_runs(cam.g_runs[l + 1], rx, ox0, ox1, a.cam[i].ox, &cmax, &cols);
+        tiles_x[i] = tiles[i] = 0;
+        if (cols == 0) continue;
+        tiles_x[i] = div_up(div_up(cmax, 2), 32);
+        tiles[i] = tiles_x[i] * div_up(div_up(out.rows, 2), 8);
+        mw = std::max(mw, cmax); mh = std::max(mh, out.rows);
+        bytes += (in.bytes() + out.bytes()) * cols / out.cols;
     }
-    if (mw == 0) return SB_OK;
+    return mw > 0;
+}
+
+int mb_down_stage(sb_compositor *c, Slot &s, int l, int ox0, int ox1)
+{
+    // K2: Gaussian level l -> l+1 for every camera, one launch
+    cudaStream_t st = s.stream;
+    MbPyrArgs a;
+    int tx[SB_MAX_CAMERAS], t[SB_MAX_CAMERAS], mw, mh;
+    double bytes = 0;
+    if (!fill_down(c, s, l, ox0, ox1, a, tx, t, mw, mh, bytes)) return SB_OK;
     PROF("mb_pyr_down", bytes, launch_mb_pyr_down(a, mw, mh, st));
     return SB_OK;
 }
 
-// [bx0, bx1): columns of band l (panorama level coordinates) to produce
-int mb_band_stage(sb_compositor *c, Slot &s, int l, int bx0, int bx1)
+// Gaussian levels l0 -> l0+1 -> ... -> l1 in ONE cooperative launch; lo[l] / hi[l]: columns of level l to produce
+int mb_down_tail(sb_compositor *c, Slot &s, int l0, int l1, const int *lo, const int *hi)
 {
-    // K3: band l for every camera, restored coarse -> fine
+    cudaStream_t st = s.stream;
+    MbPyrTailArgs a{};
+    double bytes = 0;
+    for (int l = l0; l < l1; ++l) {
+        const int k = a.n_levels;
+        int tx[SB_MAX_CAMERAS], t[SB_MAX_CAMERAS], mw, mh;
+        if (!fill_down(c, s, l, lo[l + 1], hi[l + 1], a.level[k], tx, t, mw, mh, bytes)) continue;
+        int first = 0;
+        for (int i = 0; i < c->cfg.n_cameras; ++i) { a.first_item[k][i] = first; a.tiles_x[k][i] = std::max(1, tx[i]); first += t[i]; }
+        a.items[k] = first;
+        ++a.n_levels;
+    }
+    if (a.n_levels == 0) return SB_OK;
+    PROF("mb_pyr_tail", bytes, launch_mb_pyr_tail(a, c->sm_count, st));
+    return SB_OK;
+}
+
+// [bx0, bx1): columns of band l (panorama level coordinates) to produce.  Returns false when there is nothing to do.
+bool fill_band(sb_compositor *c, Slot &s, int l, int bx0, int bx1, MbBandArgs &a, double &bytes)
+{
     const sb_compositor_config &cfg = c->cfg;
     const int n = cfg.n_cameras, nb = c->num_bands;
-    cudaStream_t st = s.stream;
-    MbBandArgs a{};
+    a = MbBandArgs{};
     a.g.n = n;
     const DImage &ws = c->wsum[l].v;
     a.x_begin = std::max(0, bx0); a.x_end = std::min(ws.cols, bx1);
-    if (a.x_end <= a.x_begin) return SB_OK;
+    if (a.x_end <= a.x_begin) return false;
     const double part = (double)(a.x_end - a.x_begin) / ws.cols;
-    double bytes = 0;
     for (int i = 0; i < n; ++i) {
         const Camera &cam = c->cams[i];
         MbBandCam &bc = a.g.cam[i];
@@ -503,8 +591,7 @@ int mb_band_stage(sb_compositor *c, Slot &s, int l, int bx0, int bx1)
     a.tile_mask = static_cast<const uint32_t *>(c->mb_tile_mask[l].p); a.tiles_x = div_up(ws.cols, 32);
     a.wsum = ws.data; a.wsum_step = ws.step;
     if (l < nb) { a.coarse_r = static_cast<const short4 *>(s.rband[l + 1].buf.p); a.coarse_r_step = s.rband[l + 1].step; bytes += part * s.rband[l + 1].bytes(); }
-    const bool fin = l == 0;
-    if (fin) {
+    if (l == 0) {
         a.out = s.out.v.data; a.out_step = s.out.v.step;
         a.out_mask = s.want_mask ? s.out_mask.v.ptr<uint8_t>() : nullptr; a.mask_step = s.out_mask.v.step;
         a.out_w = s.out.v.cols; a.out_h = s.out.v.rows;
@@ -514,7 +601,59 @@ int mb_band_stage(sb_compositor *c, Slot &s, int l, int bx0, int bx1)
         a.out = s.rband[l].buf.p; a.out_step = s.rband[l].step;
         bytes += part * (s.rband[l].bytes() + img_bytes(ws));
     }
-    PROF(fin ? "mb_band_final" : "mb_band", bytes, launch_mb_band(a, cfg.weight_type == SB_32F, l < nb, fin, s.out.v.type == SB_8UC3, st));
+    return true;
+}
+
+int mb_band_stage(sb_compositor *c, Slot &s, int l, int bx0, int bx1)
+{
+    // K3: band l for every camera, restored coarse -> fine
+    cudaStream_t st = s.stream;
+    MbBandArgs a;
+    double bytes = 0;
+    if (!fill_band(c, s, l, bx0, bx1, a, bytes)) return SB_OK;
+    const bool fin = l == 0;
+    PROF(fin ? "mb_band_final" : "mb_band", bytes,
+         launch_mb_band(a, c->cfg.weight_type == SB_32F, l < c->num_bands, fin, s.out.v.type == SB_8UC3, st));
+    return SB_OK;
+}
+
+// bands l_hi, l_hi - 1, ..., l_lo (l_lo >= 1) in ONE cooperative launch; lo[l] / hi[l]: columns of band l to produce
+int mb_band_head(sb_compositor *c, Slot &s, int l_hi, int l_lo, const int *lo, const int *hi)
+{
+    cudaStream_t st = s.stream;
+    MbBandHeadArgs a{};
+    a.top_is_top = l_hi == c->num_bands;
+    double bytes = 0;
+    for (int l = l_hi; l >= l_lo; --l) {
+        const int k = a.n_levels;
+        if (!fill_band(c, s, l, lo[l], hi[l], a.level[k], bytes)) {
+            if (k == 0) a.top_is_top = 0;      // (cannot happen for a non-empty strip; keep the flag honest)
+            continue;
+        }
+        a.tiles_x[k] = div_up(a.level[k].g.lw, 64);
+        a.items[k] = a.tiles_x[k] * div_up(a.level[k].g.lh, 16);
+        ++a.n_levels;
+    }
+    if (a.n_levels == 0) return SB_OK;
+    PROF("mb_band_head", bytes, launch_mb_band_head(a, c->cfg.weight_type == SB_32F, c->sm_count, st));
+    return SB_OK;
+}
+
+// the whole multi-band fast path for the column ranges g_lo/g_hi (Gaussian levels) and b_lo/b_hi (bands)
+int mb_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src, const int *g_lo, const int *g_hi, const int *b_lo, const int *b_hi)
+{
+    const int nb = c->num_bands;
+    SB_TRY(mb_warp_stage(c, s, src, g_lo[0], g_hi[0]));
+    const bool multilevel = c->mb_multilevel < 0 ? c->slots.size() == 1 : c->mb_multilevel != 0;
+    if (multilevel && nb >= 3 && nb <= SB_MB_MAX_FUSED_LEVELS) {
+        SB_TRY(mb_down_stage(c, s, 0, g_lo[1], g_hi[1]));
+        SB_TRY(mb_down_tail(c, s, 1, nb, g_lo, g_hi));
+        SB_TRY(mb_band_head(c, s, nb, 1, b_lo, b_hi));
+        SB_TRY(mb_band_stage(c, s, 0, b_lo[0], b_hi[0]));
+    } else {
+        for (int l = 0; l < nb; ++l) SB_TRY(mb_down_stage(c, s, l, g_lo[l + 1], g_hi[l + 1]));
+        for (int l = nb; l >= 0; --l) SB_TRY(mb_band_stage(c, s, l, b_lo[l], b_hi[l]));
+    }
     return SB_OK;
 }
 
@@ -529,9 +668,9 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
     // (camera-by-camera) path has accumulators in HBM; the weight sums are resident either way
     if (cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused && c->mb_fast && c->mb_variant == 1) {
         const int nb = c->num_bands, W = c->dst_roi.width;
-        SB_TRY(mb_warp_stage(c, s, src, 0, W));
-        for (int l = 0; l < nb; ++l) SB_TRY(mb_down_stage(c, s, l, 0, W >> (l + 1)));
-        for (int l = nb; l >= 0; --l) SB_TRY(mb_band_stage(c, s, l, 0, W >> l));
+        int zero[32] = {0}, full[32];
+        for (int l = 0; l <= nb; ++l) full[l] = W >> l;
+        SB_TRY(mb_frame(c, s, src, zero, full, zero, full));
     } else if (cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused) {
         const int nb = c->num_bands;
         for (int i = 0; i < n; ++i) {
@@ -745,7 +884,11 @@ int sb_compositor_set_fused(sb_compositor *c, int fused)
 {
     SB_ASSERT(c);
     c->fused = fused != 0;
-    if (fused >= 10) { c->feather_variant = fused - 10; c->mb_variant = fused - 10; }   // test/tuning hook: 10 / 11 select the kernel variant
+    if (fused >= 10) {   // 10: CV_16S band kernels / px1 feather; 11: fast paths (default); 12 / 13: fast paths with one launch per
+        // pyramid level / with the multi-level launches forced
+        c->feather_variant = fused == 10 ? 0 : 1; c->mb_variant = fused == 10 ? 0 : 1;
+        c->mb_multilevel = fused == 12 ? 0 : fused == 13 ? 1 : -1;
+    }   // test/tuning hook: 10 / 11 select the kernel variant
     return SB_OK;
 }
 
@@ -1025,10 +1168,17 @@ int sb_compositor_strip_compose(sb_compositor *c, const sb_image *srcs)
 {
     SB_TRY(strip_ready(c));
     if (!c->strip_recompute) return fail(SB_ERR_ASSERT, "strip_compose needs the recompute halo mode (exchange mode is driven stage by stage)");
-    SB_TRY(sb_compositor_strip_warp(c, srcs));
-    for (int l = 0; l < c->num_bands; ++l) SB_TRY(sb_compositor_strip_down(c, l));
-    for (int l = c->num_bands; l >= 0; --l) SB_TRY(sb_compositor_strip_band(c, l));
-    return SB_OK;
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    Slot &s = c->slots[0];
+    const int n = c->cfg.n_cameras;
+    c->strip_src.resize(n);
+    for (int i = 0; i < n; ++i) {
+        SB_ASSERT(srcs[i].type == SB_8UC3 && srcs[i].rows == c->cfg.src_size.height && srcs[i].cols == c->cfg.src_size.width);
+        SB_TRY(to_device(srcs[i], s.src[i], s.stream, &c->strip_src[i]));
+    }
+    s.want_mask = true;
+    return mb_frame(c, s, c->strip_src, c->g_lo.data(), c->g_hi.data(), c->b_lo.data(), c->b_hi.data());
 }
 
 int sb_compositor_strip_range(const sb_compositor *c, int rank, int world, int *x0, int *x1)

@@ -14,7 +14,10 @@
 // One thread per pixel with the warp's lanes on neighbouring pixels keeps every tap request inside
 // a few 32-byte sectors; per-tile camera bitmasks keep the per-pixel camera loop to the 1-3 cameras
 // that matter; all of a pixel's independent loads are issued before the first is consumed.
+#include <algorithm>
 #include <climits>
+
+#include <cooperative_groups.h>
 
 #include "sb_device.cuh"
 #include "sb_mb.h"
@@ -22,6 +25,7 @@
 
 namespace sb {
 using namespace sbd;
+namespace cg = cooperative_groups;
 
 #define SB_WEIGHT_EPS 1e-5f
 
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(256) k_mb_warp(const __grid_constant__ MbWarpA
 {
     const MbWarpCam &c = a.cam[blockIdx.z];
     const int px = blockIdx.x * 32 + threadIdx.x, py0 = blockIdx.y * (8 * MB_WARP_ROWS) + threadIdx.y;
-    if (px >= c.cx1 || px < c.cx0 || py0 >= c.rh) return;
+    if (py0 >= c.rh || !((px >= c.cx[0] && px < c.cx[1]) || (px >= c.cx[2] && px < c.cx[3]))) return;
     uint2 t[MB_WARP_ROWS];
 #pragma unroll
     for (int r = 0; r < MB_WARP_ROWS; ++r) {
@@ -162,12 +166,11 @@ __device__ __forceinline__ unsigned lane1(unsigned v) { return (v >> 8) & 0xffu;
 __device__ __forceinline__ unsigned pd_h02(const unsigned *v) { return lanes02(v[2]) * 6u + (lanes02(v[1]) + lanes02(v[3])) * 4u + lanes02(v[0]) + lanes02(v[4]); }
 __device__ __forceinline__ unsigned pd_h1(const unsigned *v) { return lane1(v[2]) * 6u + (lane1(v[1]) + lane1(v[3])) * 4u + lane1(v[0]) + lane1(v[4]); }
 
-__global__ void __launch_bounds__(256) k_mb_pyr_down(const __grid_constant__ MbPyrArgs a)
+__device__ __forceinline__ void mb_pyr_down_thread(const MbPyrCam &c, int x2, int y2)
 {
-    const MbPyrCam &c = a.cam[blockIdx.z];
-    const int x2 = blockIdx.x * 32 + threadIdx.x, y2 = blockIdx.y * 8 + threadIdx.y;
     const int dw = (c.sw + 1) >> 1, dh = (c.sh + 1) >> 1;
-    if (2 * x2 >= dw || 2 * y2 >= dh || 2 * x2 + 1 < c.ox0 || 2 * x2 >= c.ox1) return;
+    if (2 * x2 >= dw || 2 * y2 >= dh) return;
+    if (!((2 * x2 + 1 >= c.ox[0] && 2 * x2 < c.ox[1]) || (2 * x2 + 1 >= c.ox[2] && 2 * x2 < c.ox[3]))) return;
     const int ix = 4 * x2 - 2, iy = 4 * y2 - 2;            // top-left of the 7x7 input window
     const bool interior = ix >= 0 && ix + 6 < c.sw && iy >= 0 && iy + 6 < c.sh;
     unsigned ha02[7], ha1[7], hb02[7], hb1[7];              // horizontal sums of output columns 2*x2 and 2*x2+1, per input row
@@ -204,6 +207,11 @@ __global__ void __launch_bounds__(256) k_mb_pyr_down(const __grid_constant__ MbP
     }
 }
 
+__global__ void __launch_bounds__(256) k_mb_pyr_down(const __grid_constant__ MbPyrArgs a)
+{
+    mb_pyr_down_thread(a.cam[blockIdx.z], blockIdx.x * 32 + threadIdx.x, blockIdx.y * 8 + threadIdx.y);
+}
+
 int launch_mb_pyr_down(const MbPyrArgs &a, int max_dw, int max_dh, cudaStream_t s)
 {
     dim3 block(32, 8), grid(div_up(div_up(max_dw, 2), 32), div_up(div_up(max_dh, 2), 8), a.n);
@@ -230,10 +238,8 @@ __device__ __forceinline__ Nbr nbr_of(int c, int n)
 }
 
 template <typename WT, bool NOT_TOP, bool FINAL, bool OUT8>
-__global__ void __launch_bounds__(256) k_mb_band(const __grid_constant__ MbBandArgs a)
+__device__ __forceinline__ void mb_band_thread(const MbBandArgs &a, int X0, int Y0)
 {
-    // block = 32 x 8 threads = 64 x 16 band pixels = 2 x 2 mask tiles of 32 x 8
-    const int X0 = (blockIdx.x * 32 + threadIdx.x) * 2, Y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
     const int lw = FINAL ? a.out_w : a.g.lw, lh = FINAL ? a.out_h : a.g.lh;       // band 0 is cropped to dst_roi_final_
     if (X0 >= lw || Y0 >= lh || X0 + 1 < a.x_begin || X0 >= a.x_end) return;
     uint32_t cams = __ldg(a.tile_mask + (Y0 >> 3) * a.tiles_x + (X0 >> 5));       // the 2x2 block lies inside one 32x8 mask tile
@@ -394,6 +400,13 @@ __global__ void __launch_bounds__(256) k_mb_band(const __grid_constant__ MbBandA
     }
 }
 
+template <typename WT, bool NOT_TOP, bool FINAL, bool OUT8>
+__global__ void __launch_bounds__(256) k_mb_band(const __grid_constant__ MbBandArgs a)
+{
+    // block = 32 x 8 threads = 64 x 16 band pixels = 2 x 2 mask tiles of 32 x 8
+    mb_band_thread<WT, NOT_TOP, FINAL, OUT8>(a, (blockIdx.x * 32 + threadIdx.x) * 2, (blockIdx.y * 8 + threadIdx.y) * 2);
+}
+
 int launch_mb_band(const MbBandArgs &a, bool float_weights, bool not_top, bool final_band, bool out8, cudaStream_t s)
 {
     const int lw = final_band ? a.out_w : a.g.lw, lh = final_band ? a.out_h : a.g.lh;
@@ -409,6 +422,76 @@ int launch_mb_band(const MbBandArgs &a, bool float_weights, bool not_top, bool f
     if (float_weights) SB_MB_W(float); else SB_MB_W(short);
 #undef SB_MB_W
 #undef SB_MB
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
+// ------------------------------------------------------------------------------------ multi-level launches
+// The coarse pyramid levels are tiny (<= 1/16 of the level-0 pixels in total) and each of their launches costs
+// 7-13 us of latency on its own.  These two cooperative kernels run several levels in ONE launch: a persistent
+// grid walks the 32x8-thread work items of a level, then crosses a grid-wide barrier (the next level reads what
+// this one wrote through L2), level after level.
+__global__ void __launch_bounds__(256) k_mb_pyr_tail(const __grid_constant__ MbPyrTailArgs a)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int lv = 0; lv < a.n_levels; ++lv) {
+        const MbPyrArgs &L = a.level[lv];
+        for (int item = blockIdx.x; item < a.items[lv]; item += gridDim.x) {
+            int i = 0;
+            while (i + 1 < L.n && item >= a.first_item[lv][i + 1]) ++i;
+            const int local = item - a.first_item[lv][i], bx = local % a.tiles_x[lv][i], by = local / a.tiles_x[lv][i];
+            mb_pyr_down_thread(L.cam[i], bx * 32 + tx, by * 8 + ty);
+        }
+        if (lv + 1 < a.n_levels) grid.sync();
+    }
+}
+
+int launch_mb_pyr_tail(const MbPyrTailArgs &a, int sm_count, cudaStream_t s)
+{
+    int most = 0;
+    for (int lv = 0; lv < a.n_levels; ++lv) most = std::max(most, a.items[lv]);
+    if (most == 0) return SB_OK;
+    static int per_sm = 0;                                  // co-resident CTAs per SM: the cooperative grid may not exceed it
+    if (!per_sm) SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mb_pyr_tail, 256, 0));
+    dim3 grid(std::min(most, std::max(1, per_sm) * sm_count)), block(256);
+    void *params[] = {const_cast<MbPyrTailArgs *>(&a)};
+    SB_CUDA(cudaLaunchCooperativeKernel((const void *)k_mb_pyr_tail, grid, block, params, 0, s));
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
+template <typename WT> __global__ void __launch_bounds__(256) k_mb_band_head(const __grid_constant__ MbBandHeadArgs a)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int lv = 0; lv < a.n_levels; ++lv) {                // lv 0 = the top band, then finer
+        const MbBandArgs &L = a.level[lv];
+        for (int item = blockIdx.x; item < a.items[lv]; item += gridDim.x) {
+            const int bx = item % a.tiles_x[lv], by = item / a.tiles_x[lv];
+            const int X0 = (bx * 32 + tx) * 2, Y0 = (by * 8 + ty) * 2;
+            if (lv == 0 && a.top_is_top) mb_band_thread<WT, false, false, false>(L, X0, Y0);
+            else mb_band_thread<WT, true, false, false>(L, X0, Y0);
+        }
+        if (lv + 1 < a.n_levels) grid.sync();
+    }
+}
+
+int launch_mb_band_head(const MbBandHeadArgs &a, bool float_weights, int sm_count, cudaStream_t s)
+{
+    int most = 0;
+    for (int lv = 0; lv < a.n_levels; ++lv) most = std::max(most, a.items[lv]);
+    if (most == 0) return SB_OK;
+    static int per_sm[2] = {0, 0};
+    int &occ = per_sm[float_weights ? 1 : 0];
+    if (!occ) {
+        if (float_weights) SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mb_band_head<float>, 256, 0));
+        else SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mb_band_head<short>, 256, 0));
+    }
+    dim3 grid(std::min(most, std::max(1, occ) * sm_count)), block(256);
+    void *params[] = {const_cast<MbBandHeadArgs *>(&a)};
+    if (float_weights) SB_CUDA(cudaLaunchCooperativeKernel((const void *)k_mb_band_head<float>, grid, block, params, 0, s));
+    else SB_CUDA(cudaLaunchCooperativeKernel((const void *)k_mb_band_head<short>, grid, block, params, 0, s));
     SB_LAUNCHED();
     return SB_OK;
 }

@@ -13,7 +13,7 @@ struct MbWarpCam {
     size_t gstep;
     int rw, rh;            // padded feed rect (blenders.cpp:241-269)
     float gain;
-    int cx0, cx1;          // columns of the rect to produce (strip mode; whole rect: 0, rw)
+    int cx[4];             // columns of the rect to produce: [cx[0], cx[1]) and [cx[2], cx[3]) (empty runs have lo >= hi)
 };
 struct MbWarpArgs {
     int n;
@@ -27,7 +27,7 @@ struct MbPyrCam {
     int sw, sh;
     uint32_t *dst;         // ((sw+1)/2, (sh+1)/2)
     size_t dstep;
-    int ox0, ox1;          // output columns to produce (strip mode; whole level: 0, (sw+1)/2)
+    int ox[4];             // output columns to produce: [ox[0], ox[1]) and [ox[2], ox[3])
 };
 struct MbPyrArgs {
     int n;
@@ -63,6 +63,25 @@ struct MbBandArgs {
     int out_w, out_h;        // band 0 only: dst_roi_final_ size
     int x_begin, x_end;      // band columns to produce (strip mode; whole band: 0, lw)
 };
+
+// several coarse levels in one cooperative launch (kernels_mb.cu "multi-level launches")
+constexpr int SB_MB_MAX_FUSED_LEVELS = 6;
+struct MbPyrTailArgs {
+    int n_levels;                                          // level[k]: Gaussian level l0 + k -> l0 + k + 1
+    MbPyrArgs level[SB_MB_MAX_FUSED_LEVELS];
+    int items[SB_MB_MAX_FUSED_LEVELS];                     // 32x8-thread work items of the level (all cameras)
+    int first_item[SB_MB_MAX_FUSED_LEVELS][SB_MAX_CAMERAS];
+    int tiles_x[SB_MB_MAX_FUSED_LEVELS][SB_MAX_CAMERAS];
+};
+struct MbBandHeadArgs {
+    int n_levels;                                          // level[0] = the coarsest band of the run, then finer ones
+    int top_is_top;                                        // level[0] is the top of the pyramid (no coarser level)
+    MbBandArgs level[SB_MB_MAX_FUSED_LEVELS];
+    int items[SB_MB_MAX_FUSED_LEVELS];
+    int tiles_x[SB_MB_MAX_FUSED_LEVELS];
+};
+int launch_mb_pyr_tail(const MbPyrTailArgs &a, int sm_count, cudaStream_t s);
+int launch_mb_band_head(const MbBandHeadArgs &a, bool float_weights, int sm_count, cudaStream_t s);
 
 int launch_mb_tap_table(const ProjParams &p, int tl_x, int tl_y, int ww, int wh, int left, int top, int sw, int sh,
                         uint2 *table, size_t tstep, int rw, int rh, cudaStream_t s);

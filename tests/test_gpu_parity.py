@@ -272,9 +272,10 @@ def _compositor_case(gpu, rig, blender, weight_type=O.CV_32F, seams=False, gains
         frames = [rigs.frame(rig, fi, i) for i in range(n)]
         ref, rmask = P.compose(cal, frames, blender=blender, num_bands=num_bands, weight_type=weight_type, gains=g,
                                output_8u=not out16)
-        # 11: fused fast kernels (RGBX pyramid / 1-px feather); 10: fused CV_16S band kernels / staged-smem
-        # feather; 0: the staged, camera-by-camera path shaped like the reference's feed/blend calls
-        for fused in (11, 10, 0):
+        # 11: fused fast kernels (RGBX pyramid with multi-level launches / streaming feather); 12 / 13: the same with one
+        # launch per pyramid level / with the multi-level launches forced; 10: fused CV_16S band kernels / one-pixel-per-thread feather; 0: the staged,
+        # camera-by-camera path shaped like the reference's feed/blend calls
+        for fused in (11, 12, 13, 10, 0):
             comp.set_fused(fused)
             pano, mask = comp.compose(frames)
             assert_same(pano, ref, "%s/%s pano frame %d fused=%s" % (rig, blender, fi, fused))
