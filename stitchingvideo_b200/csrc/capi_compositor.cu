@@ -77,6 +77,7 @@ struct Slot {
     bool busy = false;
     bool want_mask = true;                       // the caller asked for dst_mask (else it is never materialised)
     std::vector<DevImage> src;                   // staged source frames (host input)
+    DevBuf src_all;                              // one staging block for a frame set that is contiguous in host memory
     std::vector<std::vector<DevImage>> gpyr;     // per camera Gaussian pyramid of the padded warped image
     DevImage warped;                             // feather / no-blend: one warped image at a time
     std::vector<std::vector<RawImage>> grgbx;    // fast path: per camera Gaussian pyramid as RGBX bytes
@@ -918,9 +919,24 @@ int sb_compositor_enqueue(sb_compositor *c, const sb_image *srcs, sb_image *pano
     const int n = c->cfg.n_cameras;
     SB_CUDA(cudaEventRecord(s.ev_start, s.stream));
     std::vector<DImage> src(n);
+    // A frame set delivered as ONE host block (camera i+1 starts where camera i ends, rows packed) crosses PCIe as a
+    // single DMA: n separate 6 MB copies cost ~20 % of the link's throughput in per-copy overhead.
+    bool one_block = n > 1;
+    const size_t row_bytes = (size_t)c->cfg.src_size.width * 3, img_bytes_ = row_bytes * c->cfg.src_size.height;
     for (int i = 0; i < n; ++i) {
         SB_ASSERT(srcs[i].type == SB_8UC3 && srcs[i].rows == c->cfg.src_size.height && srcs[i].cols == c->cfg.src_size.width);
-        SB_TRY(to_device(srcs[i], s.src[i], s.stream, &src[i]));
+        one_block = one_block && srcs[i].device < 0 && srcs[i].data && srcs[i].step == row_bytes && row_bytes % 16 == 0 &&
+                    (i == 0 || static_cast<const char *>(srcs[i].data) == static_cast<const char *>(srcs[i - 1].data) + img_bytes_);
+    }
+    if (one_block) {
+        SB_TRY(s.src_all.ensure(img_bytes_ * n + 16));
+        SB_CUDA(cudaMemcpyAsync(s.src_all.p, srcs[0].data, img_bytes_ * n, cudaMemcpyHostToDevice, s.stream));
+        for (int i = 0; i < n; ++i) {
+            src[i].data = static_cast<char *>(s.src_all.p) + img_bytes_ * i;
+            src[i].rows = srcs[i].rows; src[i].cols = srcs[i].cols; src[i].type = SB_8UC3; src[i].step = row_bytes;
+        }
+    } else {
+        for (int i = 0; i < n; ++i) SB_TRY(to_device(srcs[i], s.src[i], s.stream, &src[i]));
     }
     s.want_mask = pano_mask != nullptr;
     SB_TRY(run_frame(c, s, src));

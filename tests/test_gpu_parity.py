@@ -322,3 +322,18 @@ def test_compositor_pipelined_slots(gpu):
     for k in range(len(sets)):
         assert_same(outs[k][0], want[k], "pipelined frame %d" % k)
     assert comp.last_gpu_ms(0) > 0
+
+
+def test_frame_set_in_one_host_block(gpu):
+    """A frame set that is contiguous in host memory (one DMA) gives the same panorama as separate images."""
+    from stitchingvideo_b200 import rigs
+    for rig, blender in (("mini", "multiband"), ("mini_cyl", "feather")):
+        Ks, Rs, spec = rigs.cameras(rig)
+        n, size = spec["n_used"], (spec["W"], spec["H"])
+        comp = gpu.Compositor(size, Ks, Rs, warper=spec["warper"], scale=spec["scale"], blender=blender, gains=spec["gain_values"])
+        frames = [rigs.frame(rig, 3, i) for i in range(n)]
+        want, wmask = comp.compose(frames)
+        block = np.ascontiguousarray(np.stack(frames))          # (n, H, W, 3): camera i+1 starts where camera i ends
+        got, gmask = comp.compose([block[i] for i in range(n)])
+        assert_same(got, want, rig + " one-block frame set")
+        assert_same(gmask, wmask, rig + " one-block mask")
