@@ -439,7 +439,7 @@ int setup(sb_compositor *c)
                 SB_TRY(cam.feather_tiles.ensure(sizeof(uint2) * SB_FTT_W * SB_FTT_H * (size_t)cam.fntx * cam.fnty));
                 SB_TRY(cam.feather_rec.ensure(sizeof(uint4) * (size_t)cam.fntx * cam.fnty));
                 SB_TRY(launch_fts_camera_tiles(static_cast<const uint2 *>(cam.feather_table.p), cam.feather_tstep, cam.ww, cam.wh, dx, dy,
-                                               cam.ftx0, cam.fty0, cam.fntx, cam.fnty, static_cast<uint4 *>(cam.feather_rec.p),
+                                               cam.ftx0, cam.fty0, cam.fntx, cam.fnty, cfg.sharpness, static_cast<uint4 *>(cam.feather_rec.p),
                                                static_cast<uint2 *>(cam.feather_tiles.p), s));
                 ta.cam[i].rec = static_cast<const uint4 *>(cam.feather_rec.p);
                 ta.cam[i].tx0 = cam.ftx0; ta.cam[i].ty0 = cam.fty0; ta.cam[i].ntx = cam.fntx; ta.cam[i].nty = cam.fnty;

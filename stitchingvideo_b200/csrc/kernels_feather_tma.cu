@@ -30,16 +30,18 @@ using namespace sbt;
 // ------------------------------------------------------------------------------------ setup
 // pass 1: per (camera, tile) the source bounding box of the weighted entries -> descriptor record
 __global__ void __launch_bounds__(256)
-k_fts_bbox(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int tx0, int ty0, int ntx, uint4 *rec)
+k_fts_bbox(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int tx0, int ty0, int ntx, float sharpness, uint4 *rec)
 {
     __shared__ int red[4][8];
+    bool all_one = true;                                    // every pixel of the tile carries the full weight 1.0f
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
     for (int e = tid; e < SB_FTT_W * SB_FTT_H; e += blockDim.x) {
         const int lx = e % SB_FTT_W, ly = e / SB_FTT_W;
         const int x = (tx0 + (int)blockIdx.x) * SB_FTT_W + lx - dx, y = (ty0 + (int)blockIdx.y) * SB_FTT_H + ly - dy;
-        if ((unsigned)x >= (unsigned)ww || (unsigned)y >= (unsigned)wh) continue;
+        if ((unsigned)x >= (unsigned)ww || (unsigned)y >= (unsigned)wh) { all_one = false; continue; }
         const uint2 t = reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(table) + (size_t)y * tstep)[x];
+        all_one = all_one && fminf(__fmul_rn((float)(t.y >> 16), sharpness), 1.f) == 1.f;
         if ((t.y >> 16) == 0u) continue;
         const int x0 = t.x & 0x1fff, y0 = (t.x >> 13) & 0x1fff;
         const int x1 = x0 + 1 - (int)((t.x >> 26) & 1u), y1 = y0 + 1 - (int)((t.x >> 27) & 1u);
@@ -48,7 +50,7 @@ k_fts_bbox(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int
     mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
     mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
     if (lane == 0) { red[0][warp] = mnx; red[1][warp] = mny; red[2][warp] = mxx; red[3][warp] = mxy; }
-    __syncthreads();
+    const int every = __syncthreads_and(all_one);
     if (tid == 0) {
         for (int w = 1; w < 8; ++w) {
             mnx = min(mnx, red[0][w]); mny = min(mny, red[1][w]); mxx = max(mxx, red[2][w]); mxy = max(mxy, red[3][w]);
@@ -60,7 +62,7 @@ k_fts_bbox(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int
             const unsigned pitch = ((need_end + 15u) & ~15u) - xlo;
             unsigned n_rows = (unsigned)(mxy - mny + 1);
             if (n_rows > (unsigned)SB_FTS_MAX_ROWS || n_rows * pitch > (unsigned)SB_FTS_BOX_BYTES) n_rows = SB_FTS_DIRECT;
-            r = make_uint4(xlo | ((unsigned)mny << 16), need_end | (n_rows << 24), pitch, 0u);
+            r = make_uint4(xlo | ((unsigned)mny << 16), need_end | (n_rows << 24), pitch, every ? 0x80000000u : 0u);
         }
         rec[blockIdx.y * ntx + blockIdx.x] = r;
     }
@@ -92,9 +94,9 @@ k_fts_entries(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, 
 }
 
 int launch_fts_camera_tiles(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int tx0, int ty0, int ntx, int nty,
-                            uint4 *rec, uint2 *tiles, cudaStream_t s)
+                            float sharpness, uint4 *rec, uint2 *tiles, cudaStream_t s)
 {
-    k_fts_bbox<<<dim3(ntx, nty), 256, 0, s>>>(table, tstep, ww, wh, dx, dy, tx0, ty0, ntx, rec);
+    k_fts_bbox<<<dim3(ntx, nty), 256, 0, s>>>(table, tstep, ww, wh, dx, dy, tx0, ty0, ntx, sharpness, rec);
     SB_LAUNCHED();
     k_fts_entries<<<dim3(ntx, nty), 256, 0, s>>>(table, tstep, ww, wh, dx, dy, tx0, ty0, ntx, rec, tiles);
     SB_LAUNCHED();
@@ -102,7 +104,7 @@ int launch_fts_camera_tiles(const uint2 *table, size_t tstep, int ww, int wh, in
 }
 
 // pass 3: one 64-byte descriptor per panorama tile: {n_cams, 0, 0, 0} + per camera slot (ascending
-// camera index = feed order) {xlo | ylo << 16, need_end | n_rows << 24, pitch, cam | table block index << 4}.
+// camera index = feed order) {xlo | ylo << 16, need_end | n_rows << 24, pitch, cam | table block index << 4 | full weight << 31}.
 // *status: bit 0 = some tile has more than SB_FTT_MAXC cameras, bit 1 = block index overflow.
 __global__ void k_fts_descriptors(FtsSetup a, uint4 *desc, int *status)
 {
@@ -119,12 +121,14 @@ __global__ void k_fts_descriptors(FtsSetup a, uint4 *desc, int *status)
         uint4 r = a.cam[i].rec[block];
         const unsigned n_rows = r.y >> 24;
         if (n_rows == 0u) continue;
-        if (block >= (1u << 28)) bad |= 2;
+        if (block >= (1u << 27)) bad |= 2;
         if (k == SB_FTT_MAXC) { bad |= 1; break; }
-        r.w = (unsigned)i | (block << 4);
+        r.w = (unsigned)i | (block << 4) | (r.w & 0x80000000u);
         out[1 + k++] = r;
     }
     out[0].x = (unsigned)k;
+    // one camera at full weight over the whole tile, box staged in shared memory: the consumers take the short path
+    out[0].z = (k == 1 && (out[1].w >> 31) && (out[1].y >> 24) != (unsigned)SB_FTS_DIRECT) ? 1u : 0u;
     for (int j = 0; j <= SB_FTT_MAXC; ++j) desc[(size_t)tile * (1 + SB_FTT_MAXC) + j] = out[j];
     if (bad) atomicOr(status, bad);
 }
@@ -174,7 +178,7 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
     const int G = gridDim.x;
     if (tid == 0) {
         for (int s = 0; s < SB_FTT_STAGES; ++s) {
-            mbar_init(&sm.full[s], SB_FTS_PRODUCER_WARPS * 32 + 1);   // every producer lane (cp.async) + the table copies' expect_tx
+            mbar_init(&sm.full[s], 32 + 1);                 // the owning producer warp's lanes (cp.async) + the table copies' expect_tx
             mbar_init(&sm.empty[s], SB_FTS_CONSUMER_WARPS);
         }
         mbar_fence_init();
@@ -184,14 +188,19 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
     if (warp >= SB_FTS_CONSUMER_WARPS) {
         // ------------------------------------------------ producer warps
         const int pw = warp - SB_FTS_CONSUMER_WARPS;
+        // Tile seq (0, 1, 2 ... of this CTA) is fetched by producer warp seq % PRODUCER_WARPS, so the per-tile issue
+        // latency (descriptor shuffles, barrier ops, address arithmetic: ~1.4 us of dependent instructions) overlaps
+        // across warps.  Every warp tracks the slot ring for ALL tiles (it only needs each tile's camera count).
         int stage = 0, head = 0, used = 0;                  // tile entry of this tile; next free slot; slots held by tiles in flight
         int seq = 0, oldest = 0;                            // tiles issued / retired by this CTA
-        uint4 d_next = make_uint4(0u, 0u, 0u, 0u);          // descriptors are fetched one tile ahead of their use
-        if (lane <= SB_FTT_MAXC) d_next = __ldg(a.desc + (size_t)blockIdx.x * (1 + SB_FTT_MAXC) + lane);
+        const uint4 *dbase = a.desc;
+        unsigned nc_next = __ldg(&dbase[(size_t)blockIdx.x * (1 + SB_FTT_MAXC)].x);   // camera count, one tile ahead
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += G, ++seq) {
-            uint4 d = d_next;
-            if (lane <= SB_FTT_MAXC && tile + G < a.n_tiles) d_next = __ldg(a.desc + (size_t)(tile + G) * (1 + SB_FTT_MAXC) + lane);
-            const int nc = (int)__shfl_sync(0xffffffffu, d.x, 0);
+            const int nc = (int)nc_next;
+            if (tile + G < a.n_tiles) nc_next = __ldg(&dbase[(size_t)(tile + G) * (1 + SB_FTT_MAXC)].x);
+            const bool mine = seq % SB_FTS_PRODUCER_WARPS == pw;
+            uint4 d = make_uint4(0u, 0u, 0u, 0u);
+            if (mine && lane <= SB_FTT_MAXC) d = __ldg(dbase + (size_t)tile * (1 + SB_FTT_MAXC) + lane);
             // retire the oldest tiles until a tile entry and nc slots are free (tiles complete in order)
             while (seq - oldest >= SB_FTT_STAGES || used + nc > SB_FTS_SLOTS) {
                 const int e = oldest % SB_FTT_STAGES;
@@ -200,38 +209,42 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
                 ++oldest;
             }
             sm.nc_hist[pw][stage] = nc;                     // (every lane stores the same value)
-            if (lane == 0) d.y = (unsigned)head;
-            if (pw == 0 && lane <= SB_FTT_MAXC) sm.desc[stage][lane] = d;
-            // table blocks: one bulk copy (TMA) per camera slot, completion by expect_tx
-            if (pw == 0 && lane == 0) {
-                if (nc == 0) mbar_arrive(&sm.full[stage]);
-                else mbar_arrive_expect_tx(&sm.full[stage], (unsigned)nc * (unsigned)(SB_FTT_W * SB_FTT_H * sizeof(uint2)));
-            }
-            __syncwarp();
-            for (int k = 0; k < nc; ++k) {
-                const unsigned dx_ = __shfl_sync(0xffffffffu, d.x, k + 1), dy_ = __shfl_sync(0xffffffffu, d.y, k + 1);
-                const unsigned dw_ = __shfl_sync(0xffffffffu, d.w, k + 1), pitch = __shfl_sync(0xffffffffu, d.z, k + 1);
-                const FeatherTmaCam &c = a.cam[dw_ & 15u];
-                const int slot = head + k < SB_FTS_SLOTS ? head + k : head + k - SB_FTS_SLOTS;
-                if (pw == 0 && lane == 0)
-                    bulk_g2s(&sm.slot[slot].tab[0][0], c.tiles + (size_t)(dw_ >> 4) * (SB_FTT_W * SB_FTT_H),
-                             SB_FTT_W * SB_FTT_H * sizeof(uint2), &sm.full[stage]);
-                unsigned n_rows = dy_ >> 24;
-                if (n_rows == (unsigned)SB_FTS_DIRECT) n_rows = 0u;
-                // source box: 16-byte cp.async chunks, all lanes (row length clamped to the pitch of the source image)
-                const unsigned xlo = dx_ & 0xffffu, ylo = dx_ >> 16, need_end = dy_ & 0xffffffu;
-                const unsigned cpr = (min((need_end + 15u) & ~15u, c.sstep) - xlo) >> 4;           // chunks per row
-                const float inv = 1.f / (float)cpr;
-                const unsigned n_chunks = n_rows * cpr;
-                const uint32_t box = smem_u32(&sm.slot[slot].box[0]);
-                const uint8_t *g = c.src + (size_t)ylo * c.sstep + xlo;
-                for (unsigned ch = pw * 32 + lane; ch < n_chunks; ch += 32u * SB_FTS_PRODUCER_WARPS) {
-                    const unsigned r = (unsigned)__float2int_rz(__fmul_rn((float)ch + 0.5f, inv));  // exact: ch < 1024
-                    const unsigned col = ch - r * cpr;
-                    cp_async_16(box + r * pitch + col * 16u, g + (size_t)r * c.sstep + col * 16u);
+            if (mine) {
+                if (lane == 0) d.y = (unsigned)head;
+                if (lane <= SB_FTT_MAXC) sm.desc[stage][lane] = d;
+                // table blocks: one bulk copy (TMA) per camera slot, completion by expect_tx
+                if (lane == 0) {
+                    if (nc == 0) mbar_arrive(&sm.full[stage]);
+                    else mbar_arrive_expect_tx(&sm.full[stage], (unsigned)nc * (unsigned)(SB_FTT_W * SB_FTT_H * sizeof(uint2)));
                 }
+                __syncwarp();
+                for (int k = 0; k < nc; ++k) {
+                    const unsigned dx_ = __shfl_sync(0xffffffffu, d.x, k + 1), dy_ = __shfl_sync(0xffffffffu, d.y, k + 1);
+                    const unsigned dw_ = __shfl_sync(0xffffffffu, d.w, k + 1), pitch = __shfl_sync(0xffffffffu, d.z, k + 1);
+                    const FeatherTmaCam &c = a.cam[dw_ & 15u];
+                    const int slot = head + k < SB_FTS_SLOTS ? head + k : head + k - SB_FTS_SLOTS;
+                    if (lane == 0)
+                        bulk_g2s(&sm.slot[slot].tab[0][0], c.tiles + (size_t)((dw_ >> 4) & 0x7ffffffu) * (SB_FTT_W * SB_FTT_H),
+                                 SB_FTT_W * SB_FTT_H * sizeof(uint2), &sm.full[stage]);
+                    unsigned n_rows = dy_ >> 24;
+                    if (n_rows == (unsigned)SB_FTS_DIRECT) n_rows = 0u;
+                    // source box: 16-byte cp.async chunks, all lanes (row length clamped to the pitch of the source image)
+                    const unsigned xlo = dx_ & 0xffffu, ylo = dx_ >> 16, need_end = dy_ & 0xffffffu;
+                    const unsigned cpr = (min((need_end + 15u) & ~15u, c.sstep) - xlo) >> 4;       // chunks per row
+                    const float inv = __frcp_rn((float)cpr);
+                    const unsigned n_chunks = n_rows * cpr;
+                    const uint32_t box = smem_u32(&sm.slot[slot].box[0]);
+                    const uint8_t *g = c.src + (size_t)ylo * c.sstep + xlo;
+                    for (unsigned ch = lane; ch < n_chunks; ch += 32u) {
+                        unsigned r = (unsigned)__float2int_rz(__fmul_rn((float)ch + 0.5f, inv));    // ch / cpr for ch < 1024 ...
+                        if (r * cpr > ch) --r;                                                      // ... made exact
+                        else if ((r + 1u) * cpr <= ch) ++r;
+                        const unsigned col = ch - r * cpr;
+                        cp_async_16(box + r * pitch + col * 16u, g + (size_t)r * c.sstep + col * 16u);
+                    }
+                }
+                cp_async_mbar_arrive_noinc(&sm.full[stage]);    // one arrival per lane when its chunks have landed
             }
-            cp_async_mbar_arrive_noinc(&sm.full[stage]);    // one arrival per lane when its chunks have landed
             head = head + nc < SB_FTS_SLOTS ? head + nc : head + nc - SB_FTS_SLOTS;
             used += nc;
             if (++stage == SB_FTT_STAGES) stage = 0;
@@ -251,6 +264,57 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
         mbar_wait(&sm.full[stage], parity);
         const int nc = (int)sm.desc[stage][0].x, first = (int)sm.desc[stage][0].y;
         const int X = tx * SB_FTT_W + lx, Y0 = ty * SB_FTT_H + ly;
+        if (sm.desc[stage][0].z) {
+            // Short path (block-uniform; ~80 % of a ring panorama): ONE camera with weight exactly 1.0f on every pixel
+            // of the tile.  Then dst = short(p * 1.0f) = p, dst_w = 1.0f, and normalizeUsingWeightMap gives
+            // short(p / (1.0f + 1e-5f)) = p - 1 for p in 1..255 and 0 for p = 0 (the quotient lies strictly between
+            // p - 1 and p); the mask is 255.  No float op is needed at all.
+            const uint4 rec = sm.desc[stage][1];
+            const unsigned pitch = rec.z;
+            const FtsSlot &sl = sm.slot[first];
+            const uint32_t box = smem_u32(&sl.box[0]);
+            int v[PX][3];
+#pragma unroll
+            for (int p = 0; p < PX; ++p) {
+                const uint2 te = sl.tab[ly + RPP * p][lx];
+                const uint2 bw = __ldg(a.bilin_lut + (te.y & 1023u));
+                const uint32_t r0 = box + (te.x & 0x3ffffu);
+                const uint32_t r1 = (te.x & (1u << 27)) ? r0 : r0 + pitch;
+                unsigned lo0, hi0, lo1, hi1;
+                lds_6bytes(r0, lo0, hi0);
+                lds_6bytes(r1, lo1, hi1);
+                if (te.x & (1u << 26)) {                    // x1 == x0 at the image edge: repeat the pixel
+                    hi0 = lo0 >> 8; lo0 = (lo0 & 0x00ffffffu) | (lo0 << 24);
+                    hi1 = lo1 >> 8; lo1 = (lo1 & 0x00ffffffu) | (lo1 << 24);
+                }
+                bilinear_rgb(lo0, hi0, lo1, hi1, bw, v[p][0], v[p][1], v[p][2]);
+                if (GAIN) {                                 // saturate_cast<uchar>(p * gain)
+                    const float g = a.cam[rec.w & 15u].gain;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) v[p][k] = min(max(__float2int_rn(__fmul_rn((float)v[p][k], g)), 0), 255);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[stage]);
+            unsigned char *orow = reinterpret_cast<unsigned char *>(a.out) + (size_t)Y0 * a.out_step + (size_t)X * (OUT8 ? 3 : 6);
+            uint8_t *mrow_ = a.out_mask ? a.out_mask + (size_t)Y0 * a.mask_step + X : nullptr;
+#pragma unroll
+            for (int p = 0; p < PX; ++p) {
+                const int o0 = v[p][0] - min(v[p][0], 1), o1 = v[p][1] - min(v[p][1], 1), o2 = v[p][2] - min(v[p][2], 1);
+                if (OUT8) {
+                    orow[0] = (uint8_t)o0; orow[1] = (uint8_t)o1; orow[2] = (uint8_t)o2;
+                } else {
+                    short *o = reinterpret_cast<short *>(orow);
+                    o[0] = (short)o0; o[1] = (short)o1; o[2] = (short)o2;
+                }
+                if (mrow_) { *mrow_ = 255; mrow_ += RPP * a.mask_step; }
+                orow += RPP * a.out_step;
+            }
+            tx += gx; ty += gy;
+            if (tx >= a.tiles_x) { tx -= a.tiles_x; ++ty; }
+            if (++stage == SB_FTT_STAGES) { stage = 0; parity ^= 1u; }
+            continue;
+        }
         int acc[PX][3];
         float wsum[PX];
 #pragma unroll

@@ -47,7 +47,7 @@ constexpr int SB_FTS_BOX_BYTES = 12288;          // shared-memory slot for one (
 constexpr int SB_FTS_MAX_ROWS = 64;              // box rows copied by the producer warp (2 per lane)
 constexpr int SB_FTS_DIRECT = 0xff;              // n_rows marker: no box, taps come from global memory
 constexpr int SB_FTS_CONSUMER_WARPS = 16;        // 512 pixel threads
-constexpr int SB_FTS_PRODUCER_WARPS = 2;         // all walk the tile sequence; each issues a quarter of the box chunks
+constexpr int SB_FTS_PRODUCER_WARPS = 4;         // all walk the tile sequence; warp w fetches tiles w, w + 4, ...
 constexpr int SB_FTS_CTAS_PER_SM = 2;
 constexpr int SB_FTS_THREADS = (SB_FTS_CONSUMER_WARPS + SB_FTS_PRODUCER_WARPS) * 32;
 
@@ -80,7 +80,7 @@ struct FtsSetup {
 };
 // setup: box records + tile-major entries of one camera
 int launch_fts_camera_tiles(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int tx0, int ty0, int ntx, int nty,
-                            uint4 *rec, uint2 *tiles, cudaStream_t s);
+                            float sharpness, uint4 *rec, uint2 *tiles, cudaStream_t s);
 // setup: the per-tile descriptors; *status != 0 -> the streaming kernel cannot be used for this calibration
 int launch_fts_descriptors(const FtsSetup &a, uint4 *desc, int *status, cudaStream_t s);
 int launch_feather_stream(const FeatherTmaArgs &a, bool apply_gain, bool out8, int sm_count, cudaStream_t s);
