@@ -28,8 +28,9 @@ extern "C" {
 #endif
 
 /* ---- type / flag codes: numerically identical to OpenCV 2.4.11 ---- */
-enum { SB_8U = 0, SB_16S = 3, SB_32F = 5,
-       SB_8UC1 = 0, SB_8UC3 = 16, SB_16SC1 = 3, SB_16SC3 = 19, SB_32FC1 = 5 };
+enum { SB_8U = 0, SB_16U = 2, SB_16S = 3, SB_32F = 5,
+       SB_8UC1 = 0, SB_8UC3 = 16, SB_16SC1 = 3, SB_16SC3 = 19, SB_32FC1 = 5,
+       SB_16UC1 = 2, SB_16SC2 = 11 };   /* the last two: fixed-point remap maps (cv::convertMaps) only */
 enum { SB_INTER_NEAREST = 0, SB_INTER_LINEAR = 1 };
 enum { SB_BORDER_CONSTANT = 0, SB_BORDER_REPLICATE = 1, SB_BORDER_REFLECT = 2,
        SB_BORDER_WRAP = 3, SB_BORDER_REFLECT_101 = 4 };
@@ -104,10 +105,16 @@ int sb_warper_remap(sb_warper *w, const sb_image *src, int interp_mode, int bord
 int sb_warper_warp_backward(sb_warper *w, const sb_image *src, const float K[9], const float R[9],
                             int interp_mode, int border_mode, sb_size dst_size, sb_image *dst);
 
-/* cv::remap itself (OpenCV 2.4.11 imgproc; call sites warpers_inl.hpp:96,127, APP64:752): 8UC1/8UC3,
- * CV_32FC1 maps, INTER_LINEAR (fixed-point INTER_TAB_SIZE=32) or INTER_NEAREST. */
+/* cv::remap itself (OpenCV 2.4.11 imgproc; call sites warpers_inl.hpp:96,127, APP64:741,752): 8UC1/8UC3,
+ * INTER_LINEAR (fixed-point INTER_TAB_SIZE=32) or INTER_NEAREST.  Maps: CV_32FC1 x / y, or the fixed-point pair the
+ * app's video front end uses (initUndistortRectifyMap(..., CV_16SC2, ...), APP64:201-238): xmap CV_16SC2 integer
+ * coordinates + ymap CV_16UC1 fractions (ymap->data may be NULL for INTER_NEAREST). */
 int sb_remap(const sb_image *src, sb_image *dst, const sb_image *xmap, const sb_image *ymap,
              int interp_mode, int border_mode, const uint8_t border_value[4], int device);
+
+/* cv::convertMaps(xmap, ymap, map1, map2, CV_16SC2, nn_interpolation): float maps -> fixed-point pair, i.e. the map
+ * conversion cv::remap repeats on every call, done once.  map2 is ignored when nn_interpolation. */
+int sb_convert_maps(const sb_image *xmap, const sb_image *ymap, sb_image *map1, sb_image *map2, int nn_interpolation, int device);
 
 /* =====================================================================================
  * ExposureCompensator — INC/detail/exposure_compensate.hpp:51-101.

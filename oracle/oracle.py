@@ -80,6 +80,11 @@ _NP2CV = {np.dtype(np.uint8): CV_8U, np.dtype(np.int16): CV_16S, np.dtype(np.flo
 
 def mat(a):
     """Wrap a C-contiguous-rows numpy array (H,W) or (H,W,C) as so_mat (no copy)."""
+    if a.dtype == np.uint16:                                # CV_16UC1: the fractional part of a fixed-point map pair
+        assert a.ndim == 2 and a.strides[-1] == 2
+        m = SoMat(a.ctypes.data, a.shape[0], a.shape[1], 2, a.strides[0])
+        m._keep = a
+        return m
     assert a.dtype in _NP2CV, a.dtype
     assert a.ndim in (2, 3)
     cn = 1 if a.ndim == 2 else a.shape[2]
@@ -165,6 +170,28 @@ def remap(src, xmap, ymap, interp=INTER_LINEAR, border=BORDER_REFLECT, border_va
     bv = (C.c_uint8 * 4)(*border_value)
     ms, md, mx, my = mat(src), mat(dst), mat(np.ascontiguousarray(xmap)), mat(np.ascontiguousarray(ymap))
     _chk(lib().so_remap(C.byref(ms), C.byref(md), C.byref(mx), C.byref(my), interp, border, bv), "remap")
+    return dst
+
+
+def convert_maps(xmap, ymap, nn_interpolation=False):
+    """cv::convertMaps(xmap, ymap, CV_16SC2) -> (map1 int16 HxWx2, map2 uint16 HxW | None)."""
+    xmap, ymap = np.ascontiguousarray(xmap, np.float32), np.ascontiguousarray(ymap, np.float32)
+    m1 = np.empty(xmap.shape + (2,), np.int16)
+    m2 = None if nn_interpolation else np.empty(xmap.shape, np.uint16)
+    mx, my, a1 = mat(xmap), mat(ymap), mat(m1)
+    a2 = None if m2 is None else mat(m2)
+    _chk(lib().so_convert_maps(C.byref(mx), C.byref(my), C.byref(a1), C.byref(a2) if a2 is not None else None, int(nn_interpolation)), "convertMaps")
+    return m1, m2
+
+
+def remap_fixed(src, map1, map2, interp=INTER_LINEAR, border=BORDER_REFLECT, border_value=(0, 0, 0, 0)):
+    """cv::remap with a CV_16SC2 / CV_16UC1 fixed-point map pair (map2 may be None)."""
+    src = np.ascontiguousarray(src)
+    dst = np.empty(map1.shape[:2] + src.shape[2:], np.uint8)
+    bv = (C.c_uint8 * 4)(*border_value)
+    ms, md, m1 = mat(src), mat(dst), mat(np.ascontiguousarray(map1))
+    m2 = None if map2 is None else mat(np.ascontiguousarray(map2))
+    _chk(lib().so_remap(C.byref(ms), C.byref(md), C.byref(m1), C.byref(m2) if m2 is not None else None, interp, border, bv), "remap")
     return dst
 
 

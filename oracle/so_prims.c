@@ -185,16 +185,29 @@ int so_remap(const so_mat *src, so_mat *dst, const so_mat *xmap, const so_mat *y
     const uint8_t *cval = border_value ? border_value : zero4;
     int cn = SO_CN(src->type);
     if (SO_DEPTH(src->type) != SO_8U || dst->type != src->type) return -1;
-    if (xmap->type != SO_32FC1 || ymap->type != SO_32FC1) return -1;
+    /* fixed-point maps (cv::convertMaps / initUndistortRectifyMap(CV_16SC2), the app's video front end APP64:201-238,
+     * 741): map1 CV_16SC2 = integer coordinates, map2 CV_16UC1 (optional) = fy * 32 + fx */
+    const int fixed = xmap->type == SO_16SC2;
+    if (fixed) {
+        if (ymap && ymap->data && (ymap->type != SO_16UC1 || ymap->rows != xmap->rows || ymap->cols != xmap->cols)) return -1;
+        if (interp != SO_INTER_NEAREST && !(ymap && ymap->data)) return -1;   /* OpenCV needs the fractional map for INTER_LINEAR */
+    } else if (xmap->type != SO_32FC1 || !ymap || ymap->type != SO_32FC1) return -1;
     if (dst->rows != xmap->rows || dst->cols != xmap->cols) return -1;
     int W = src->cols, H = src->rows;
 
     for (int dy = 0; dy < dst->rows; ++dy) {
-        const float *mx = ROW(xmap, const float, dy), *my = ROW(ymap, const float, dy);
+        const float *mx = fixed ? NULL : ROW(xmap, const float, dy), *my = fixed ? NULL : ROW(ymap, const float, dy);
+        const short *m1 = fixed ? ROW(xmap, const short, dy) : NULL;
+        const unsigned short *m2 = (fixed && ymap && ymap->data) ? ROW(ymap, const unsigned short, dy) : NULL;
         uint8_t *D = ROW(dst, uint8_t, dy);
         for (int dx = 0; dx < dst->cols; ++dx, D += cn) {
             if (interp == SO_INTER_NEAREST) {
-                int sx = sat_s16(so_cvround(mx[dx])), sy = sat_s16(so_cvround(my[dx]));
+                int sx = fixed ? m1[2 * dx] : sat_s16(so_cvround(mx[dx])), sy = fixed ? m1[2 * dx + 1] : sat_s16(so_cvround(my[dx]));
+                if (m2) {   /* OpenCV's NNDeltaTab_i[fy * 32 + fx] = {fx < 16, fy < 16} is added to the integer coordinate
+                             * in int16 arithmetic (sic: the table is set up that way in imgwarp.cpp's initInterTab2D) */
+                    const int a = m2[dx] & 1023;
+                    sx = (short)(sx + ((a & 31) < 16)); sy = (short)(sy + ((a >> 5) < 16));
+                }
                 if ((unsigned)sx < (unsigned)W && (unsigned)sy < (unsigned)H) {
                     memcpy(D, ROW(src, const uint8_t, sy) + sx * cn, cn);
                 } else if (border == SO_BORDER_REPLICATE) {
@@ -211,10 +224,16 @@ int so_remap(const so_mat *src, so_mat *dst, const so_mat *xmap, const so_mat *y
                 continue;
             }
             /* INTER_LINEAR: 5 fractional bits, float32 multiply before rounding */
-            int fsx = so_cvround(mx[dx] * 32), fsy = so_cvround(my[dx] * 32);
-            int w[4];
-            remap_weights(fsx & 31, fsy & 31, w);
-            int sx = sat_s16(fsx >> 5), sy = sat_s16(fsy >> 5);
+            int w[4], sx, sy;
+            if (fixed) {
+                const int fxy = m2 ? (m2[dx] & 1023) : 0;
+                remap_weights(fxy & 31, fxy >> 5, w);
+                sx = m1[2 * dx]; sy = m1[2 * dx + 1];
+            } else {
+                int fsx = so_cvround(mx[dx] * 32), fsy = so_cvround(my[dx] * 32);
+                remap_weights(fsx & 31, fsy & 31, w);
+                sx = sat_s16(fsx >> 5); sy = sat_s16(fsy >> 5);
+            }
             int x0, x1, y0, y1;
             if (border == SO_BORDER_CONSTANT && (sx >= W || sx + 1 < 0 || sy >= H || sy + 1 < 0)) {
                 memcpy(D, cval, cn);
@@ -228,6 +247,30 @@ int so_remap(const so_mat *src, so_mat *dst, const so_mat *xmap, const so_mat *y
                 int v2 = (x0 >= 0 && y1 >= 0) ? ROW(src, const uint8_t, y1)[x0 * cn + k] : cval[k];
                 int v3 = (x1 >= 0 && y1 >= 0) ? ROW(src, const uint8_t, y1)[x1 * cn + k] : cval[k];
                 D[k] = sat_u8((v0 * w[0] + v1 * w[1] + v2 * w[2] + v3 * w[3] + (1 << 14)) >> 15);
+            }
+        }
+    }
+    return 0;
+}
+
+/* cv::convertMaps CV_32FC1 x/y -> CV_16SC2 + CV_16UC1 (what remap does internally per call, done once):
+ * nn_interpolation: map1 = saturate_cast<short>(cvRound(x, y)), map2 untouched; else 5 fractional bits. */
+int so_convert_maps(const so_mat *xmap, const so_mat *ymap, so_mat *map1, so_mat *map2, int nn_interpolation)
+{
+    if (xmap->type != SO_32FC1 || ymap->type != SO_32FC1 || map1->type != SO_16SC2) return -1;
+    if (map1->rows != xmap->rows || map1->cols != xmap->cols) return -1;
+    if (!nn_interpolation && (!map2 || map2->type != SO_16UC1 || map2->rows != xmap->rows || map2->cols != xmap->cols)) return -1;
+    for (int y = 0; y < xmap->rows; ++y) {
+        const float *mx = ROW(xmap, const float, y), *my = ROW(ymap, const float, y);
+        short *m1 = ROW(map1, short, y);
+        unsigned short *m2 = nn_interpolation ? NULL : ROW(map2, unsigned short, y);
+        for (int x = 0; x < xmap->cols; ++x) {
+            if (nn_interpolation) {
+                m1[2 * x] = (short)sat_s16(so_cvround(mx[x])); m1[2 * x + 1] = (short)sat_s16(so_cvround(my[x]));
+            } else {
+                const int ix = so_cvround(mx[x] * 32), iy = so_cvround(my[x] * 32);
+                m1[2 * x] = (short)sat_s16(ix >> 5); m1[2 * x + 1] = (short)sat_s16(iy >> 5);
+                m2[x] = (unsigned short)((iy & 31) * 32 + (ix & 31));
             }
         }
     }

@@ -35,7 +35,8 @@ extern "C" {
 /* OpenCV type codes: CV_MAKETYPE(depth, cn) = depth + ((cn-1) << 3) */
 enum {
     SO_8U = 0, SO_16S = 3, SO_32F = 5,
-    SO_8UC1 = 0, SO_8UC3 = 16, SO_16SC1 = 3, SO_16SC3 = 19, SO_32FC1 = 5
+    SO_8UC1 = 0, SO_8UC3 = 16, SO_16SC1 = 3, SO_16SC3 = 19, SO_32FC1 = 5,
+    SO_16UC1 = 2, SO_16SC2 = 11   /* fixed-point remap maps (cv::convertMaps) */
 };
 /* OpenCV interpolation / border codes (imgproc.hpp) */
 enum { SO_INTER_NEAREST = 0, SO_INTER_LINEAR = 1 };

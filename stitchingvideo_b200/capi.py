@@ -84,6 +84,7 @@ API = {
     "sb_warper_remap": (C.c_int, [C.c_void_p, _P(SbImage), C.c_int, C.c_int, _P(SbImage)]),
     "sb_warper_warp_backward": (C.c_int, [C.c_void_p, _P(SbImage), _F9, _F9, C.c_int, C.c_int, SbSize, _P(SbImage)]),
     "sb_remap": (C.c_int, [_P(SbImage), _P(SbImage), _P(SbImage), _P(SbImage), C.c_int, C.c_int, _P(C.c_uint8), C.c_int]),
+    "sb_convert_maps": (C.c_int, [_P(SbImage), _P(SbImage), _P(SbImage), _P(SbImage), C.c_int, C.c_int]),
     "sb_comp_create": (C.c_int, [C.c_int, C.c_int, _P(C.c_void_p)]),
     "sb_comp_destroy": (None, [C.c_void_p]),
     "sb_comp_set_gains": (C.c_int, [C.c_void_p, _P(C.c_double), C.c_int]),
@@ -157,8 +158,9 @@ def _check(rc):
         raise StitchError(rc, lib().sb_last_error().decode("utf-8", "replace"))
 
 
-_NP2CV = {np.dtype(np.uint8): CV_8U, np.dtype(np.int16): CV_16S, np.dtype(np.float32): CV_32F}
-_CV2NP = {CV_8U: np.uint8, CV_16S: np.int16, CV_32F: np.float32}
+CV_16U, CV_16UC1, CV_16SC2 = 2, 2, 11      # fixed-point remap maps (cv::convertMaps)
+_NP2CV = {np.dtype(np.uint8): CV_8U, np.dtype(np.int16): CV_16S, np.dtype(np.float32): CV_32F, np.dtype(np.uint16): CV_16U}
+_CV2NP = {CV_8U: np.uint8, CV_16S: np.int16, CV_32F: np.float32, CV_16U: np.uint16}
 
 
 def _depth(t):
@@ -328,10 +330,33 @@ class SphericalWarper(RotationWarper):
     KIND = WARP_SPHERICAL
 
 
-def remap(src, xmap, ymap, interp_mode=INTER_LINEAR, border_mode=BORDER_CONSTANT, border_value=(0, 0, 0, 0), device=0):
-    isrc, k0 = _image(src)
+def convertMaps(xmap, ymap, nninterpolation=False, device=0):
+    """cv::convertMaps(xmap, ymap, CV_16SC2): float maps -> (map1 int16 HxWx2, map2 uint16 HxW | None)."""
     ix, k1 = _image(np.ascontiguousarray(xmap, np.float32))
     iy, k2 = _image(np.ascontiguousarray(ymap, np.float32))
+    map1 = np.empty((ix.rows, ix.cols, 2), np.int16)
+    map2 = None if nninterpolation else np.empty((ix.rows, ix.cols), np.uint16)
+    i1, k3 = _image(map1)
+    i2 = SbImage(None, 0, 0, CV_16UC1, 0, -1)
+    if map2 is not None:
+        i2, k4 = _image(map2)
+    _check(lib().sb_convert_maps(C.byref(ix), C.byref(iy), C.byref(i1), C.byref(i2), 1 if nninterpolation else 0, device))
+    return map1, map2
+
+
+def remap(src, xmap, ymap, interp_mode=INTER_LINEAR, border_mode=BORDER_CONSTANT, border_value=(0, 0, 0, 0), device=0):
+    """cv::remap.  (xmap, ymap): float32 maps, or the fixed-point pair of convertMaps (int16 HxWx2, uint16 HxW | None)."""
+    isrc, k0 = _image(src)
+    xmap = np.asarray(xmap)
+    if xmap.dtype == np.int16:
+        ix, k1 = _image(np.ascontiguousarray(xmap))
+        if ymap is None:
+            iy = SbImage(None, 0, 0, CV_16UC1, 0, -1)
+        else:
+            iy, k2 = _image(np.ascontiguousarray(ymap, np.uint16))
+    else:
+        ix, k1 = _image(np.ascontiguousarray(xmap, np.float32))
+        iy, k2 = _image(np.ascontiguousarray(ymap, np.float32))
     dst = _empty(ix.rows, ix.cols, isrc.type)
     idst, k3 = _image(dst)
     bv = (C.c_uint8 * 4)(*border_value)

@@ -205,12 +205,38 @@ int sb_remap(const sb_image *src, sb_image *dst, const sb_image *xmap, const sb_
     cudaStream_t s = nullptr;   // legacy default stream: one-shot helper
     SB_TRY(to_device(*src, s_src, s, &dsrc));
     SB_TRY(to_device(*xmap, s_x, s, &dxm));
-    SB_TRY(to_device(*ymap, s_y, s, &dym));
+    if (ymap->data) SB_TRY(to_device(*ymap, s_y, s, &dym));
     SB_ASSERT(dst->rows == dxm.rows && dst->cols == dxm.cols && dst->type == src->type);
     if (dst->device >= 0) { out.data = dst->data; out.rows = dst->rows; out.cols = dst->cols; out.type = dst->type; out.step = dst->step; }
     else { SB_TRY(s_dst.create(dst->rows, dst->cols, dst->type)); out = s_dst.v; }
     SB_TRY(launch_remap(dsrc, out, dxm, dym, interp_mode, border_mode, border_value, s));
     if (dst->device < 0) SB_TRY(from_device(out, dst, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    return SB_OK;
+}
+
+int sb_convert_maps(const sb_image *xmap, const sb_image *ymap, sb_image *map1, sb_image *map2, int nn_interpolation, int device)
+{
+    SB_ASSERT(xmap && ymap && map1 && map1->data);
+    SB_ASSERT(nn_interpolation || (map2 && map2->data));
+    DeviceGuard g(device);
+    if (!g.ok) return SB_ERR_CUDA;
+    DevImage s_x, s_y, s_1, s_2;
+    DImage dx, dy, d1, d2;
+    cudaStream_t s = nullptr;
+    SB_TRY(to_device(*xmap, s_x, s, &dx));
+    SB_TRY(to_device(*ymap, s_y, s, &dy));
+    SB_ASSERT(map1->type == SB_16SC2 && map1->rows == dx.rows && map1->cols == dx.cols);
+    if (map1->device >= 0) { d1.data = map1->data; d1.rows = map1->rows; d1.cols = map1->cols; d1.type = map1->type; d1.step = map1->step; }
+    else { SB_TRY(s_1.create(map1->rows, map1->cols, SB_16SC2)); d1 = s_1.v; }
+    if (!nn_interpolation) {
+        SB_ASSERT(map2->type == SB_16UC1 && map2->rows == dx.rows && map2->cols == dx.cols);
+        if (map2->device >= 0) { d2.data = map2->data; d2.rows = map2->rows; d2.cols = map2->cols; d2.type = map2->type; d2.step = map2->step; }
+        else { SB_TRY(s_2.create(map2->rows, map2->cols, SB_16UC1)); d2 = s_2.v; }
+    }
+    SB_TRY(launch_convert_maps(dx, dy, d1, d2, nn_interpolation != 0, s));
+    if (map1->device < 0) SB_TRY(from_device(d1, map1, s));
+    if (!nn_interpolation && map2->device < 0) SB_TRY(from_device(d2, map2, s));
     SB_CUDA(cudaStreamSynchronize(s));
     return SB_OK;
 }

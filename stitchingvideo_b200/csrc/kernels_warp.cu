@@ -55,14 +55,13 @@ __device__ __forceinline__ void bilinear_weights(int fx, int fy, int &w00, int &
     if ((fx | fy) == 0) { w00 = 32767; w11 = 1; }
 }
 
+// sx, sy: integer tap coordinates (already clamped to int16), fx, fy: the 5 fractional bits
 template <int CN, int BORDER>
-__device__ __forceinline__ void sample_linear(const uint8_t *__restrict__ src, int sw, int sh, size_t sstep, float mx,
-                                              float my, const uint8_t *cval, int out[CN])
+__device__ __forceinline__ void sample_linear_q(const uint8_t *__restrict__ src, int sw, int sh, size_t sstep, int sx, int sy,
+                                                int fx, int fy, const uint8_t *cval, int out[CN])
 {
-    const int fsx = cvround(__fmul_rn(mx, 32.f)), fsy = cvround(__fmul_rn(my, 32.f));
     int w00, w01, w10, w11;
-    bilinear_weights(fsx & 31, fsy & 31, w00, w01, w10, w11);
-    const int sx = sat_s16(fsx >> 5), sy = sat_s16(fsy >> 5);
+    bilinear_weights(fx, fy, w00, w01, w10, w11);
     if (BORDER == BORDER_CONSTANT && (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0)) {
 #pragma unroll
         for (int k = 0; k < CN; ++k) out[k] = cval[k];
@@ -87,10 +86,17 @@ __device__ __forceinline__ void sample_linear(const uint8_t *__restrict__ src, i
 }
 
 template <int CN, int BORDER>
-__device__ __forceinline__ void sample_nearest(const uint8_t *__restrict__ src, int sw, int sh, size_t sstep, float mx,
-                                               float my, const uint8_t *cval, int out[CN])
+__device__ __forceinline__ void sample_linear(const uint8_t *__restrict__ src, int sw, int sh, size_t sstep, float mx,
+                                              float my, const uint8_t *cval, int out[CN])
 {
-    int sx = sat_s16(cvround(mx)), sy = sat_s16(cvround(my));
+    const int fsx = cvround(__fmul_rn(mx, 32.f)), fsy = cvround(__fmul_rn(my, 32.f));
+    sample_linear_q<CN, BORDER>(src, sw, sh, sstep, sat_s16(fsx >> 5), sat_s16(fsy >> 5), fsx & 31, fsy & 31, cval, out);
+}
+
+template <int CN, int BORDER>
+__device__ __forceinline__ void sample_nearest_q(const uint8_t *__restrict__ src, int sw, int sh, size_t sstep, int sx, int sy,
+                                                 const uint8_t *cval, int out[CN])
+{
     if (!((unsigned)sx < (unsigned)sw && (unsigned)sy < (unsigned)sh)) {
         if (BORDER == BORDER_CONSTANT) {
 #pragma unroll
@@ -103,6 +109,13 @@ __device__ __forceinline__ void sample_nearest(const uint8_t *__restrict__ src, 
     const uint8_t *r = src + (size_t)sy * sstep + sx * CN;
 #pragma unroll
     for (int k = 0; k < CN; ++k) out[k] = __ldg(r + k);
+}
+
+template <int CN, int BORDER>
+__device__ __forceinline__ void sample_nearest(const uint8_t *__restrict__ src, int sw, int sh, size_t sstep, float mx,
+                                               float my, const uint8_t *cval, int out[CN])
+{
+    sample_nearest_q<CN, BORDER>(src, sw, sh, sstep, sat_s16(cvround(mx)), sat_s16(cvround(my)), cval, out);
 }
 
 struct CVal { uint8_t v[4]; };
@@ -125,10 +138,75 @@ k_remap(const uint8_t *__restrict__ src, int sw, int sh, size_t sstep, uint8_t *
     for (int k = 0; k < CN; ++k) d[k] = (uint8_t)out[k];
 }
 
+// cv::remap with the fixed-point map pair of cv::convertMaps / initUndistortRectifyMap(CV_16SC2) — the format the
+// app's video front end uses (APP64:201-238, 741): map1 CV_16SC2 = integer coordinates, map2 CV_16UC1 = fy * 32 + fx
+// (may be absent for INTER_NEAREST).  INTER_NEAREST with a fractional map adds OpenCV's NNDeltaTab_i {fx < 16, fy < 16}.
+template <int CN, int BORDER, int INTERP>
+__global__ void __launch_bounds__(256)
+k_remap_fixed(const uint8_t *__restrict__ src, int sw, int sh, size_t sstep, uint8_t *__restrict__ dst, int dw, int dh,
+              size_t dstep, const short2 *__restrict__ map1, size_t m1step, const unsigned short *__restrict__ map2, size_t m2step, CVal cv)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const short2 xy = __ldg(reinterpret_cast<const short2 *>(reinterpret_cast<const char *>(map1) + y * m1step) + x);
+    const int a = map2 ? (__ldg(reinterpret_cast<const unsigned short *>(reinterpret_cast<const char *>(map2) + y * m2step) + x) & 1023) : 0;
+    int out[CN];
+    if (INTERP == SB_INTER_LINEAR) sample_linear_q<CN, BORDER>(src, sw, sh, sstep, xy.x, xy.y, a & 31, a >> 5, cv.v, out);
+    else {
+        int sx = xy.x, sy = xy.y;
+        if (map2) { sx = (short)(sx + ((a & 31) < 16)); sy = (short)(sy + ((a >> 5) < 16)); }
+        sample_nearest_q<CN, BORDER>(src, sw, sh, sstep, sx, sy, cv.v, out);
+    }
+    uint8_t *d = dst + y * dstep + x * CN;
+#pragma unroll
+    for (int k = 0; k < CN; ++k) d[k] = (uint8_t)out[k];
+}
+
+// cv::convertMaps CV_32FC1 x / y -> CV_16SC2 (+ CV_16UC1): the map conversion cv::remap performs on every call, done once
+__global__ void __launch_bounds__(256)
+k_convert_maps(const float *xmap, size_t xstep, const float *ymap, size_t ystep, short2 *map1, size_t m1step, unsigned short *map2,
+               size_t m2step, int w, int h, int nn)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const float mx = reinterpret_cast<const float *>(reinterpret_cast<const char *>(xmap) + y * xstep)[x];
+    const float my = reinterpret_cast<const float *>(reinterpret_cast<const char *>(ymap) + y * ystep)[x];
+    short2 o;
+    if (nn) {
+        o.x = (short)sat_s16(cvround(mx)); o.y = (short)sat_s16(cvround(my));
+    } else {
+        const int ix = cvround(__fmul_rn(mx, 32.f)), iy = cvround(__fmul_rn(my, 32.f));
+        o.x = (short)sat_s16(ix >> 5); o.y = (short)sat_s16(iy >> 5);
+        reinterpret_cast<unsigned short *>(reinterpret_cast<char *>(map2) + y * m2step)[x] = (unsigned short)((iy & 31) * 32 + (ix & 31));
+    }
+    reinterpret_cast<short2 *>(reinterpret_cast<char *>(map1) + y * m1step)[x] = o;
+}
+
+int launch_convert_maps(const DImage &xmap, const DImage &ymap, const DImage &map1, const DImage &map2, bool nn, cudaStream_t s)
+{
+    SB_ASSERT(xmap.type == SB_32FC1 && ymap.type == SB_32FC1 && map1.type == SB_16SC2);
+    SB_ASSERT(map1.rows == xmap.rows && map1.cols == xmap.cols && ymap.rows == xmap.rows && ymap.cols == xmap.cols);
+    SB_ASSERT(nn || (map2.type == SB_16UC1 && map2.rows == xmap.rows && map2.cols == xmap.cols && map2.data));
+    dim3 block(32, 8), grid(div_up(xmap.cols, 32), div_up(xmap.rows, 8));
+    k_convert_maps<<<grid, block, 0, s>>>(xmap.ptr<float>(), xmap.step, ymap.ptr<float>(), ymap.step, map1.ptr<short2>(), map1.step,
+                                          nn ? nullptr : map2.ptr<unsigned short>(), map2.step, xmap.cols, xmap.rows, nn ? 1 : 0);
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
 template <int CN, int BORDER>
 static void remap_dispatch_interp(int interp, dim3 grid, dim3 block, cudaStream_t s, const DImage &src, const DImage &dst,
                                   const DImage &xmap, const DImage &ymap, CVal cv)
 {
+    if (xmap.type == SB_16SC2) {
+        const unsigned short *m2 = ymap.empty() ? nullptr : ymap.ptr<unsigned short>();
+        if (interp == SB_INTER_LINEAR)
+            k_remap_fixed<CN, BORDER, SB_INTER_LINEAR><<<grid, block, 0, s>>>(src.ptr<uint8_t>(), src.cols, src.rows, src.step, dst.ptr<uint8_t>(), dst.cols, dst.rows, dst.step, xmap.ptr<short2>(), xmap.step, m2, ymap.step, cv);
+        else
+            k_remap_fixed<CN, BORDER, SB_INTER_NEAREST><<<grid, block, 0, s>>>(src.ptr<uint8_t>(), src.cols, src.rows, src.step, dst.ptr<uint8_t>(), dst.cols, dst.rows, dst.step, xmap.ptr<short2>(), xmap.step, m2, ymap.step, cv);
+        return;
+    }
     if (interp == SB_INTER_LINEAR)
         k_remap<CN, BORDER, SB_INTER_LINEAR><<<grid, block, 0, s>>>(src.ptr<uint8_t>(), src.cols, src.rows, src.step, dst.ptr<uint8_t>(), dst.cols, dst.rows, dst.step, xmap.ptr<float>(), xmap.step, ymap.ptr<float>(), ymap.step, cv);
     else
@@ -154,9 +232,13 @@ int launch_remap(const DImage &src, const DImage &dst, const DImage &xmap, const
 {
     SB_ASSERT(src.type == SB_8UC1 || src.type == SB_8UC3);
     SB_ASSERT(dst.type == src.type);
-    SB_ASSERT(xmap.type == SB_32FC1 && ymap.type == SB_32FC1);
-    SB_ASSERT(dst.rows == xmap.rows && dst.cols == xmap.cols && ymap.rows == xmap.rows && ymap.cols == xmap.cols);
     SB_ASSERT(interp == SB_INTER_LINEAR || interp == SB_INTER_NEAREST);
+    if (xmap.type == SB_16SC2) {      // fixed-point pair; the fractional map is optional for INTER_NEAREST only (as in OpenCV)
+        SB_ASSERT(ymap.empty() ? interp == SB_INTER_NEAREST : (ymap.type == SB_16UC1 && ymap.rows == xmap.rows && ymap.cols == xmap.cols));
+    } else {
+        SB_ASSERT(xmap.type == SB_32FC1 && ymap.type == SB_32FC1 && ymap.rows == xmap.rows && ymap.cols == xmap.cols);
+    }
+    SB_ASSERT(dst.rows == xmap.rows && dst.cols == xmap.cols);
     SB_ASSERT(src.rows > 0 && src.cols > 0);
     CVal cv;
     for (int i = 0; i < 4; ++i) cv.v[i] = bv ? bv[i] : 0;

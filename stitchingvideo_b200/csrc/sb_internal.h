@@ -45,11 +45,12 @@ int fail(int code, const char *fmt, ...);
 
 inline int type_depth(int type) { return type & 7; }
 inline int type_cn(int type) { return ((type >> 3) & 63) + 1; }
-inline int depth_size(int depth) { return depth == SB_8U ? 1 : depth == SB_16S ? 2 : depth == SB_32F ? 4 : 0; }
+inline int depth_size(int depth) { return depth == SB_8U ? 1 : (depth == SB_16S || depth == SB_16U) ? 2 : depth == SB_32F ? 4 : 0; }
 inline int elem_size(int type) { return depth_size(type_depth(type)) * type_cn(type); }
 inline bool type_supported(int type)
 {
-    return type == SB_8UC1 || type == SB_8UC3 || type == SB_16SC1 || type == SB_16SC3 || type == SB_32FC1;
+    return type == SB_8UC1 || type == SB_8UC3 || type == SB_16SC1 || type == SB_16SC3 || type == SB_32FC1 ||
+           type == SB_16UC1 || type == SB_16SC2;      // (the last two: fixed-point remap maps only)
 }
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 

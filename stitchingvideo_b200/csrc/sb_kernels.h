@@ -14,9 +14,12 @@ struct ProjParams {
 // ---- warp (kernels_warp.cu) -------------------------------------------------------------------
 // a3: buildMaps — one mapBackward per destination pixel of Rect(tl, br)
 int launch_build_maps(const ProjParams &p, int tl_x, int tl_y, const DImage &xmap, const DImage &ymap, cudaStream_t s);
-// a4: cv::remap 8UC1/8UC3 with CV_32FC1 maps
+// a4: cv::remap 8UC1/8UC3 with CV_32FC1 maps, or with the CV_16SC2 (+ CV_16UC1) fixed-point pair of cv::convertMaps
 int launch_remap(const DImage &src, const DImage &dst, const DImage &xmap, const DImage &ymap, int interp, int border,
                  const uint8_t bv[4], cudaStream_t s);
+
+// cv::convertMaps: float maps -> fixed-point pair (map2 unused when nn)
+int launch_convert_maps(const DImage &xmap, const DImage &ymap, const DImage &map1, const DImage &map2, bool nn, cudaStream_t s);
 
 // Fused per-frame warp of the compositor: maps recomputed on the fly from separable trig tables
 // (a3), fixed-point bilinear remap BORDER_REFLECT (a4), gain (a5), convertTo(CV_16S) (a7) and the

@@ -55,6 +55,24 @@ def gen_remap():
     save("remap", **out)
 
 
+def gen_remap_fixed():
+    """Fixed-point map pair (cv::convertMaps) and cv::remap through it: the app's video front-end format."""
+    rng = np.random.default_rng(105)
+    H, W = 45, 61
+    out = {}
+    for cn in (1, 3):
+        src = rng.integers(0, 256, (H, W, cn), dtype=np.uint8) if cn == 3 else rng.integers(0, 256, (H, W), dtype=np.uint8)
+        xm, ym = util.special_maps(rng, 40, 70, W, H)
+        m1, m2 = cv2.convertMaps(xm, ym, cv2.CV_16SC2)
+        n1, _ = cv2.convertMaps(xm, ym, cv2.CV_16SC2, nninterpolation=True)
+        out.update({"src%d" % cn: src, "xmap%d" % cn: xm, "ymap%d" % cn: ym, "map1_%d" % cn: m1, "map2_%d" % cn: m2, "nnmap1_%d" % cn: n1})
+        for border in (0, 1, 2, 3, 4):
+            for interp in (0, 1):
+                out["dst%d_b%d_i%d" % (cn, border, interp)] = cv2.remap(src, m1, m2, interp, borderMode=border, borderValue=(7, 9, 11))
+            out["nndst%d_b%d" % (cn, border)] = cv2.remap(src, n1, None, cv2.INTER_NEAREST, borderMode=border, borderValue=(7, 9, 11))
+    save("remap_fixed", **out)
+
+
 def gen_pyr():
     rng = np.random.default_rng(102)
     out = {}
@@ -109,6 +127,7 @@ def gen_blend():
 if __name__ == "__main__":
     gen_maps()
     gen_remap()
+    gen_remap_fixed()
     gen_pyr()
     gen_misc()
     gen_blend()

@@ -66,6 +66,32 @@ def test_remap_bit_exact(gpu, cn, border, interp):
     assert_same(got, ref, "remap")
 
 
+@pytest.mark.parametrize("cn", [1, 3])
+def test_remap_fixed_point_maps(gpu, cn):
+    """convertMaps + remap through the CV_16SC2 / CV_16UC1 pair: the app's fisheye front-end format (APP64:201-238, 741)."""
+    rng = np.random.default_rng(22 + cn)
+    H, W = 97, 131
+    src = rng.integers(0, 256, (H, W, cn), dtype=np.uint8) if cn == 3 else rng.integers(0, 256, (H, W), dtype=np.uint8)
+    xm, ym = util.special_maps(rng, 120, 173, W, H)
+    m1, m2 = gpu.convertMaps(xm, ym)
+    om1, om2 = O.convert_maps(xm, ym)
+    assert_same(m1, om1, "convertMaps map1")
+    assert_same(m2, om2, "convertMaps map2")
+    n1, _ = gpu.convertMaps(xm, ym, nninterpolation=True)
+    assert_same(n1, O.convert_maps(xm, ym, True)[0], "convertMaps nearest")
+    for border in (O.BORDER_REFLECT, O.BORDER_CONSTANT, O.BORDER_REPLICATE, O.BORDER_REFLECT_101, O.BORDER_WRAP):
+        for interp in (O.INTER_LINEAR, O.INTER_NEAREST):
+            assert_same(gpu.remap(src, m1, m2, interp, border, (7, 9, 11, 0)), O.remap_fixed(src, m1, m2, interp, border, (7, 9, 11, 0)),
+                        "fixed remap b=%d i=%d" % (border, interp))
+        assert_same(gpu.remap(src, n1, None, O.INTER_NEAREST, border, (7, 9, 11, 0)), O.remap_fixed(src, n1, None, O.INTER_NEAREST, border, (7, 9, 11, 0)),
+                    "fixed nearest b=%d" % border)
+        # the fixed-point pair gives what the float maps give (cv::remap converts them the same way internally)
+        assert_same(gpu.remap(src, m1, m2, O.INTER_LINEAR, border, (7, 9, 11, 0)), gpu.remap(src, xm, ym, O.INTER_LINEAR, border, (7, 9, 11, 0)),
+                    "fixed vs float maps b=%d" % border)
+    with pytest.raises(gpu.StitchError):
+        gpu.remap(src, m1, None, O.INTER_LINEAR, O.BORDER_REFLECT)      # OpenCV needs the fractional map for INTER_LINEAR
+
+
 def test_remap_degenerate_sources(gpu):
     rng = np.random.default_rng(21)
     for (H, W) in ((1, 1), (1, 9), (7, 1), (2, 2)):

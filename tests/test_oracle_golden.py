@@ -51,6 +51,23 @@ def test_remap_golden(cn):
             same(got, g["dst%d_b%d_i%d" % (cn, border, interp)], "remap cn=%d border=%d interp=%d" % (cn, border, interp))
 
 
+@pytest.mark.parametrize("cn", [1, 3])
+def test_remap_fixed_point_maps_golden(cn):
+    """cv::convertMaps + cv::remap with the CV_16SC2 / CV_16UC1 pair (SURVEY.md §8f rank 1)."""
+    g = load("remap_fixed")
+    src, xm, ym = g["src%d" % cn], g["xmap%d" % cn], g["ymap%d" % cn]
+    m1, m2 = O.convert_maps(xm, ym)
+    same(m1, g["map1_%d" % cn], "convertMaps map1")
+    same(m2, g["map2_%d" % cn], "convertMaps map2")
+    n1, _ = O.convert_maps(xm, ym, nn_interpolation=True)
+    same(n1, g["nnmap1_%d" % cn], "convertMaps nearest map1")
+    for border in range(5):
+        for interp in (0, 1):
+            same(O.remap_fixed(src, m1, m2, interp, border, (7, 9, 11, 0)), g["dst%d_b%d_i%d" % (cn, border, interp)],
+                 "fixed remap cn=%d border=%d interp=%d" % (cn, border, interp))
+        same(O.remap_fixed(src, n1, None, O.INTER_NEAREST, border, (7, 9, 11, 0)), g["nndst%d_b%d" % (cn, border)], "fixed nearest")
+
+
 def test_pyramids_golden():
     g = load("pyr")
     for name in ("s16", "u8", "s16c1"):
