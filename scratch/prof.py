@@ -5,7 +5,7 @@ import stitchingvideo_b200 as sv
 from stitchingvideo_b200 import rigs, capi
 rig=sys.argv[1] if len(sys.argv)>1 else 'c3'
 Ks,Rs,spec=rigs.cameras(rig); n=spec['n_used']; size=(spec['W'],spec['H'])
-comp=sv.Compositor(size,Ks,Rs,warper=spec['warper'],scale=spec['scale'],blender=spec['blender'],gains=spec['gain_values'])
+comp=sv.Compositor(size,Ks,Rs,warper=spec['warper'],scale=spec['scale'],blender=(sys.argv[2] if len(sys.argv)>2 else spec['blender']),gains=spec['gain_values'])
 sets=[[torch.from_numpy(rigs.frame(rig,s,i,smooth=0)).cuda() for i in range(n)] for s in range(3)]
 dsets=[[capi.DeviceImage.from_torch(t) for t in s] for s in sets]
 for it in range(3): comp.profile_frame(dsets[it%3])

@@ -101,6 +101,7 @@ struct sb_compositor {
     cudaStream_t setup_stream = nullptr;
     cudaEvent_t marks[2] = {nullptr, nullptr};
     bool feather_fast = false;                   // every weighted pixel's taps fit the resolved-tap table
+    float stream_sharpness = 0.02f;              // feather: FeatherBlender::sharpness_; Blender::NO: 1/255 (see setup)
     bool feather_tma = false;                    // <= SB_FTT_MAXC cameras per 128x8 tile: persistent table-streaming kernel
     int feather_variant = 1;                     // 1: k_feather_tma, 0: k_feather_fused_px1
     DevBuf tma_desc;                             // per 128x8 panorama tile: camera slots + source boxes
@@ -393,19 +394,25 @@ int setup(sb_compositor *c)
                 SB_TRY(launch_mb_tile_mask(g, wt == SB_32FC1, g.lw, g.lh, static_cast<uint32_t *>(c->mb_tile_mask[l].p), s));
             }
         }
-    } else if (cfg.blender_kind == SB_BLEND_FEATHER) {
+    } else if (cfg.blender_kind == SB_BLEND_FEATHER || cfg.blender_kind == SB_BLEND_NO) {
+        // Blender::NO rides on the feather tables: the "distance" field carries the mask byte (its OR is dst_mask_,
+        // the last camera with a non-zero mask supplies the pixel, blenders.cpp:81-102), "sharpness" 1/255 marks
+        // the tiles whose mask is 255 throughout
+        const bool noblend = cfg.blender_kind == SB_BLEND_NO;
+        c->stream_sharpness = noblend ? 1.f / 255.f : cfg.sharpness;
         c->wsum.resize(1);
         SB_TRY(c->wsum[0].create_zero(roi.height, roi.width, SB_32FC1, s));
         DevBuf scratch;
         for (int i = 0; i < n; ++i) {
             Camera &cam = c->cams[i];
             SB_TRY(cam.feather_w.create(cam.wh, cam.ww, SB_32FC1));
-            SB_TRY(launch_distance_l1(cam.mask.v, cam.feather_w.v, scratch, s));
+            if (noblend) SB_TRY(launch_convert(cam.mask.v, cam.feather_w.v, s));      // the mask byte as an exact float
+            else SB_TRY(launch_distance_l1(cam.mask.v, cam.feather_w.v, scratch, s));
             cam.feather_tstep = ((size_t)cam.ww * sizeof(uint2) + 255) & ~(size_t)255;
             SB_TRY(cam.feather_table.ensure(cam.feather_tstep * cam.wh));
             SB_TRY(launch_build_feather_table(cam.proj, cam.tl.x, cam.tl.y, cam.feather_w.v, cfg.src_size.width, cfg.src_size.height,
                                               static_cast<uint2 *>(cam.feather_table.p), cam.feather_tstep, s));
-            SB_TRY(launch_weight_from_dist(cam.feather_w.v, cfg.sharpness, s));
+            SB_TRY(launch_weight_from_dist(cam.feather_w.v, c->stream_sharpness, s));
             SB_TRY(launch_weight_accumulate(cam.feather_w.v, c->wsum[0].v, cam.tl.x - roi.x, cam.tl.y - roi.y, s));
             cam.spans.emplace_back();
             SB_TRY(weight_spans(cam.feather_w.v, cam.tl.x - roi.x, scratch, s, &cam.spans.back()));
@@ -439,7 +446,7 @@ int setup(sb_compositor *c)
                 SB_TRY(cam.feather_tiles.ensure(sizeof(uint2) * SB_FTT_W * SB_FTT_H * (size_t)cam.fntx * cam.fnty));
                 SB_TRY(cam.feather_rec.ensure(sizeof(uint4) * (size_t)cam.fntx * cam.fnty));
                 SB_TRY(launch_fts_camera_tiles(static_cast<const uint2 *>(cam.feather_table.p), cam.feather_tstep, cam.ww, cam.wh, dx, dy,
-                                               cam.ftx0, cam.fty0, cam.fntx, cam.fnty, cfg.sharpness, static_cast<uint4 *>(cam.feather_rec.p),
+                                               cam.ftx0, cam.fty0, cam.fntx, cam.fnty, c->stream_sharpness, static_cast<uint4 *>(cam.feather_rec.p),
                                                static_cast<uint2 *>(cam.feather_tiles.p), s));
                 ta.cam[i].rec = static_cast<const uint4 *>(cam.feather_rec.p);
                 ta.cam[i].tx0 = cam.ftx0; ta.cam[i].ty0 = cam.fty0; ta.cam[i].ntx = cam.fntx; ta.cam[i].nty = cam.fnty;
@@ -665,6 +672,9 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
     const bool gain_on = cfg.comp_kind == SB_COMP_GAIN;
     cudaStream_t st = s.stream;
     DImage none;
+    bool stream_ok = c->feather_tma && c->feather_variant == 1;      // the streaming frame kernel (feather / no blending)
+    for (int i = 0; i < n && stream_ok; ++i)      // bulk copies need 16-byte aligned rows
+        stream_ok = src[i].step % 16 == 0 && src[i].step < (1ull << 24) && reinterpret_cast<uintptr_t>(src[i].data) % 16 == 0;
     // Blender::prepare zeroes the accumulators (blenders.cpp:71-78, 227-232): only the unfused
     // (camera-by-camera) path has accumulators in HBM; the weight sums are resident either way
     if (cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused && c->mb_fast && c->mb_variant == 1) {
@@ -717,7 +727,8 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
             PROF(fin ? "band_fused_final" : "band_fused", bytes,
                  launch_band_fused(a, cfg.weight_type == SB_32F, l < nb, fin, s.out.v.type == SB_8UC3, st));
         }
-    } else if (cfg.blender_kind == SB_BLEND_FEATHER && c->fused && c->feather_fast && cfg.sharpness > 0.f) {
+    } else if ((cfg.blender_kind == SB_BLEND_FEATHER || cfg.blender_kind == SB_BLEND_NO) && c->fused && c->feather_fast &&
+               c->stream_sharpness > 0.f && (cfg.blender_kind == SB_BLEND_FEATHER || stream_ok)) {
         double bytes = 0;
         for (int i = 0; i < n; ++i) {
             const auto &sp = c->cams[i].spans[0];
@@ -725,10 +736,7 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
             bytes += img_bytes(src[i]) + 8.0 * c->cams[i].wh * ((sp[1] - sp[0]) + (sp[3] - sp[2]));
         }
         bytes += img_bytes(s.out.v) + (s.want_mask ? img_bytes(s.out_mask.v) : 0);
-        bool tma = c->feather_tma && c->feather_variant == 1;
-        for (int i = 0; i < n && tma; ++i)      // bulk copies need 16-byte aligned rows
-            tma = src[i].step % 16 == 0 && src[i].step < (1ull << 24) && reinterpret_cast<uintptr_t>(src[i].data) % 16 == 0;
-        if (tma) {
+        if (stream_ok) {
             FeatherTmaArgs a{};
             a.n = n;
             for (int i = 0; i < n; ++i) {
@@ -739,12 +747,13 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
             }
             a.desc = static_cast<const uint4 *>(c->tma_desc.p);
             a.bilin_lut = static_cast<const uint2 *>(c->bilin_lut.p);
-            a.sharpness = cfg.sharpness;
+            a.sharpness = c->stream_sharpness;
+            a.no_blend = cfg.blender_kind == SB_BLEND_NO;
             a.out = s.out.v.data; a.out_step = s.out.v.step;
             a.out_mask = s.want_mask ? s.out_mask.v.ptr<uint8_t>() : nullptr; a.mask_step = s.out_mask.v.step;
             a.pw = s.out.v.cols; a.ph = s.out.v.rows;
             a.tiles_x = div_up(a.pw, SB_FTT_W); a.n_tiles = a.tiles_x * div_up(a.ph, SB_FTT_H);
-            PROF("feather_stream", bytes, launch_feather_stream(a, gain_on, s.out.v.type == SB_8UC3, c->sm_count, st));
+            PROF(a.no_blend ? "noblend_stream" : "feather_stream", bytes, launch_feather_stream(a, gain_on, s.out.v.type == SB_8UC3, c->sm_count, st));
         } else {
             FeatherFusedArgs a{};
             a.n = n;

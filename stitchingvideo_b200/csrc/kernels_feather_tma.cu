@@ -168,7 +168,9 @@ __device__ __forceinline__ void lds_6bytes(uint32_t a, unsigned &lo, unsigned &h
     hi = __funnelshift_r(w1, w2, o * 8);
 }
 
-template <bool GAIN, bool OUT8>
+// NOBLEND: Blender::feed / blend without blending (blenders.cpp:81-112): the pixel of the LAST camera (feed order)
+// whose mask is non-zero, dst_mask = OR of the mask bytes, 0 where no camera has a mask.
+template <bool GAIN, bool OUT8, bool NOBLEND>
 __global__ void __launch_bounds__(SB_FTS_THREADS, SB_FTS_CTAS_PER_SM)
 k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
 {
@@ -300,7 +302,8 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
             uint8_t *mrow_ = a.out_mask ? a.out_mask + (size_t)Y0 * a.mask_step + X : nullptr;
 #pragma unroll
             for (int p = 0; p < PX; ++p) {
-                const int o0 = v[p][0] - min(v[p][0], 1), o1 = v[p][1] - min(v[p][1], 1), o2 = v[p][2] - min(v[p][2], 1);
+                const int o0 = NOBLEND ? v[p][0] : v[p][0] - min(v[p][0], 1), o1 = NOBLEND ? v[p][1] : v[p][1] - min(v[p][1], 1),
+                          o2 = NOBLEND ? v[p][2] : v[p][2] - min(v[p][2], 1);
                 if (OUT8) {
                     orow[0] = (uint8_t)o0; orow[1] = (uint8_t)o1; orow[2] = (uint8_t)o2;
                 } else {
@@ -319,6 +322,77 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
         float wsum[PX];
 #pragma unroll
         for (int p = 0; p < PX; ++p) { acc[p][0] = acc[p][1] = acc[p][2] = 0; wsum[p] = 0.f; }
+        if (NOBLEND) {
+            // which camera slot supplies each pixel (the last one in feed order with a non-zero mask), OR of the masks
+            int sel[PX];
+            unsigned mor[PX];
+#pragma unroll
+            for (int p = 0; p < PX; ++p) { sel[p] = -1; mor[p] = 0u; }
+            for (int k = 0; k < nc; ++k) {
+                const FtsSlot &sl = sm.slot[first + k < SB_FTS_SLOTS ? first + k : first + k - SB_FTS_SLOTS];
+#pragma unroll
+                for (int p = 0; p < PX; ++p) {
+                    const unsigned m = sl.tab[ly + RPP * p][lx].y >> 16;
+                    mor[p] |= m;
+                    if (m) sel[p] = k;
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < PX; ++p) {
+                if (sel[p] < 0) continue;
+                const uint4 rec = sm.desc[stage][1 + sel[p]];
+                const FtsSlot &sl = sm.slot[first + sel[p] < SB_FTS_SLOTS ? first + sel[p] : first + sel[p] - SB_FTS_SLOTS];
+                const uint2 te = sl.tab[ly + RPP * p][lx];
+                const uint2 bw = __ldg(a.bilin_lut + (te.y & 1023u));
+                unsigned lo0, hi0, lo1, hi1;
+                if ((rec.y >> 24) != (unsigned)SB_FTS_DIRECT) {
+                    const uint32_t r0 = smem_u32(&sl.box[0]) + (te.x & 0x3ffffu);
+                    const uint32_t r1 = (te.x & (1u << 27)) ? r0 : r0 + rec.z;
+                    lds_6bytes(r0, lo0, hi0);
+                    lds_6bytes(r1, lo1, hi1);
+                    if (te.x & (1u << 26)) {
+                        hi0 = lo0 >> 8; lo0 = (lo0 & 0x00ffffffu) | (lo0 << 24);
+                        hi1 = lo1 >> 8; lo1 = (lo1 & 0x00ffffffu) | (lo1 << 24);
+                    }
+                } else {
+                    const FeatherTmaCam &c = a.cam[rec.w & 15u];
+                    const unsigned x0 = te.x & 0x1fffu, y0 = (te.x >> 13) & 0x1fffu;
+                    const uint8_t *g0 = c.src + (size_t)(y0 * c.sstep);
+                    const uint8_t *g1 = (te.x & (1u << 27)) ? g0 : g0 + c.sstep;
+                    const unsigned x1 = x0 + 1u - ((te.x >> 26) & 1u);
+                    load_tap_row(g0, x0, x1, lo0, hi0);
+                    load_tap_row(g1, x0, x1, lo1, hi1);
+                }
+                bilinear_rgb(lo0, hi0, lo1, hi1, bw, acc[p][0], acc[p][1], acc[p][2]);
+                if (GAIN) {
+                    const float g = a.cam[rec.w & 15u].gain;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) acc[p][k] = min(max(__float2int_rn(__fmul_rn((float)acc[p][k], g)), 0), 255);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[stage]);
+            if (X < a.pw) {
+                unsigned char *orow = reinterpret_cast<unsigned char *>(a.out) + (size_t)Y0 * a.out_step + (size_t)X * (OUT8 ? 3 : 6);
+                uint8_t *mrow_ = a.out_mask ? a.out_mask + (size_t)Y0 * a.mask_step + X : nullptr;
+#pragma unroll
+                for (int p = 0; p < PX; ++p) {
+                    if (Y0 + RPP * p >= a.ph) break;
+                    if (OUT8) {
+                        orow[0] = (uint8_t)acc[p][0]; orow[1] = (uint8_t)acc[p][1]; orow[2] = (uint8_t)acc[p][2];
+                    } else {
+                        short *o = reinterpret_cast<short *>(orow);
+                        o[0] = (short)acc[p][0]; o[1] = (short)acc[p][1]; o[2] = (short)acc[p][2];
+                    }
+                    if (mrow_) { *mrow_ = (uint8_t)mor[p]; mrow_ += RPP * a.mask_step; }
+                    orow += RPP * a.out_step;
+                }
+            }
+            tx += gx; ty += gy;
+            if (tx >= a.tiles_x) { tx -= a.tiles_x; ++ty; }
+            if (++stage == SB_FTT_STAGES) { stage = 0; parity ^= 1u; }
+            continue;
+        }
         for (int k = 0; k < nc; ++k) {                      // ascending camera index = feed order (float weight sums)
             const uint4 rec = sm.desc[stage][1 + k];
             const unsigned pitch = rec.z;
@@ -404,21 +478,19 @@ int launch_feather_stream(const FeatherTmaArgs &a, bool apply_gain, bool out8, i
 {
     SB_ASSERT(a.sharpness > 0.f && a.bilin_lut && a.desc && a.n_tiles > 0 && a.n <= 16);
     const size_t smem = sizeof(FtsSmem);
-    static bool configured[4] = {false, false, false, false};
-    const void *fn[4] = {(const void *)k_feather_stream<false, false>, (const void *)k_feather_stream<false, true>,
-                         (const void *)k_feather_stream<true, false>, (const void *)k_feather_stream<true, true>};
-    const int v = (apply_gain ? 2 : 0) + (out8 ? 1 : 0);
+    static bool configured[8] = {false, false, false, false, false, false, false, false};
+    const void *fn[8] = {(const void *)k_feather_stream<false, false, false>, (const void *)k_feather_stream<false, true, false>,
+                         (const void *)k_feather_stream<true, false, false>, (const void *)k_feather_stream<true, true, false>,
+                         (const void *)k_feather_stream<false, false, true>, (const void *)k_feather_stream<false, true, true>,
+                         (const void *)k_feather_stream<true, false, true>, (const void *)k_feather_stream<true, true, true>};
+    const int v = (a.no_blend ? 4 : 0) + (apply_gain ? 2 : 0) + (out8 ? 1 : 0);
     if (!configured[v]) {
         SB_CUDA(cudaFuncSetAttribute(fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[v] = true;
     }
     const int grid = std::min(a.n_tiles, SB_FTS_CTAS_PER_SM * sm_count);
-    switch (v) {
-    case 0: k_feather_stream<false, false><<<grid, SB_FTS_THREADS, smem, s>>>(a); break;
-    case 1: k_feather_stream<false, true><<<grid, SB_FTS_THREADS, smem, s>>>(a); break;
-    case 2: k_feather_stream<true, false><<<grid, SB_FTS_THREADS, smem, s>>>(a); break;
-    default: k_feather_stream<true, true><<<grid, SB_FTS_THREADS, smem, s>>>(a); break;
-    }
+    void *params[] = {const_cast<FeatherTmaArgs *>(&a)};
+    SB_CUDA(cudaLaunchKernel(fn[v], dim3(grid), dim3(SB_FTS_THREADS), params, smem, s));
     SB_LAUNCHED();
     return SB_OK;
 }

@@ -124,6 +124,8 @@ int launch_convert(const DImage &src, const DImage &dst, cudaStream_t s)
         k_convert<uint8_t, short><<<grid, block, 0, s>>>(src.ptr<uint8_t>(), src.step, dst.ptr<short>(), dst.step, n, src.rows);
     else if (sd == SB_16S && dd == SB_8U)
         k_convert<short, uint8_t><<<grid, block, 0, s>>>(src.ptr<short>(), src.step, dst.ptr<uint8_t>(), dst.step, n, src.rows);
+    else if (sd == SB_8U && dd == SB_32F)
+        k_convert<uint8_t, float><<<grid, block, 0, s>>>(src.ptr<uint8_t>(), src.step, dst.ptr<float>(), dst.step, n, src.rows);
     else
         return fail(SB_ERR_NOT_IMPL, "convert %d -> %d not on the compositing path", src.type, dst.type);
     SB_LAUNCHED();

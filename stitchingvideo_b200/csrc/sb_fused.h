@@ -63,6 +63,7 @@ struct FeatherTmaArgs {
     const uint4 *desc;           // per panorama tile: 1 + SB_FTT_MAXC records (kernels_feather_tma.cu)
     const uint2 *bilin_lut;
     float sharpness;
+    int no_blend;                // Blender::NO: the table's distance field is the mask byte; last camera with a non-zero mask wins
     void *out;
     size_t out_step;
     uint8_t *out_mask;

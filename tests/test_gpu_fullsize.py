@@ -108,3 +108,19 @@ def test_sharded_stream_equals_unsharded(gpu):
         per_rank.append([sharding.checksum(shard.compose([rigs.frame("mini_cyl", f, i) for i in range(n)])[0])
                          for f in sharding.frames_for_rank(n_frames, g, G)])
     assert sharding.interleave(per_rank) == whole
+
+
+def test_full_size_no_blend_matches_oracle(gpu):
+    """The live app's shape (APP64:724-770): cylindrical warp + gain + Blender::NO composite of 5 x 1080p, one fused launch."""
+    Ks, Rs, spec = rigs.cameras("c2")
+    size, n = (spec["W"], spec["H"]), spec["n_used"]
+    gains = [0.95, 1.02, 1.0, 0.98, 1.05]
+    comp = gpu.Compositor(size, Ks, Rs, warper="cylindrical", scale=spec["scale"], blender="no", gains=gains)
+    cal = P.Calibration(size, Ks, Rs, "cylindrical", spec["scale"])
+    frames = [rigs.frame("c2", 4, i, smooth=1) for i in range(n)]
+    ref, rmask = P.compose(cal, frames, blender="no", gains=gains)
+    for fused in (11, 10, 0):
+        comp.set_fused(fused)
+        pano, mask = comp.compose(frames)
+        same(pano, ref, "no-blend panorama (variant %d)" % fused)
+        same(mask, rmask, "no-blend mask (variant %d)" % fused)
