@@ -186,12 +186,16 @@ typedef struct sb_compositor_config {
     int      num_bands;           /* multi-band */
     int      weight_type;         /* SB_32F or SB_16S (multi-band) */
     float    sharpness;           /* feather */
-    int      comp_kind;           /* SB_COMP_NO or SB_COMP_GAIN */
+    int      comp_kind;           /* SB_COMP_NO, SB_COMP_GAIN or SB_COMP_GAIN_BLOCKS */
     const double *gains;          /* n gains (SB_COMP_GAIN) */
     /* optional n seam masks in warped coordinates (host CV_8UC1, size of each camera's warped
      * image), ANDed with the warped all-255 mask exactly as stitcher.cpp:278-294; NULL = none */
     const sb_image *seam_masks;
     int      output_type;         /* SB_8UC3 (result.convertTo(CV_8U), stitcher.cpp:313) or SB_16SC3 */
+    /* SB_COMP_GAIN_BLOCKS: n host CV_32FC1 block gain maps (BlocksGainCompensator::gain_maps_,
+     * exposure_compensate.cpp:203-221), resized to each warped image with INTER_LINEAR once, as apply() does
+     * on every call (:225-246; the live app's BlockApply, APP64:310-331).  Fused paths only. */
+    const sb_image *gain_maps;
 } sb_compositor_config;
 
 int  sb_compositor_create(const sb_compositor_config *cfg, int device, sb_compositor **out);

@@ -353,6 +353,7 @@ public:
         int weight_type = SB_32F;
         float sharpness = 0.02f;
         std::vector<double> gains;            // empty: no exposure compensation
+        std::vector<Mat> gain_maps;           // BlocksGainCompensator: one CV_32FC1 block gain map per camera (instead of gains)
         std::vector<Mat> seam_masks;          // empty: none
         int output_type = SB_8UC3;
     };
@@ -367,8 +368,11 @@ public:
         c.warper_kind = cfg.warper_kind; c.warper_scale = cfg.warper_scale;
         c.K = cfg.K.data(); c.R = cfg.R.data();
         c.blender_kind = cfg.blender_kind; c.num_bands = cfg.num_bands; c.weight_type = cfg.weight_type; c.sharpness = cfg.sharpness;
-        c.comp_kind = cfg.gains.empty() ? SB_COMP_NO : SB_COMP_GAIN;
+        std::vector<sb_image> gm;
+        for (const Mat &m : cfg.gain_maps) gm.push_back(m.c());
+        c.comp_kind = !cfg.gains.empty() ? SB_COMP_GAIN : !gm.empty() ? SB_COMP_GAIN_BLOCKS : SB_COMP_NO;
         c.gains = cfg.gains.empty() ? nullptr : cfg.gains.data();
+        c.gain_maps = gm.empty() ? nullptr : gm.data();
         std::vector<sb_image> sm;
         for (const Mat &m : cfg.seam_masks) sm.push_back(m.c());
         c.seam_masks = sm.empty() ? nullptr : sm.data();

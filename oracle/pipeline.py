@@ -30,7 +30,7 @@ class Calibration:
 
 
 def compose(cal, frames, blender="multiband", num_bands=5, weight_type=O.CV_32F, sharpness=0.02, gains=None,
-            output_8u=True, use_ref=False):
+            output_8u=True, use_ref=False, gain_maps=None):
     """One frame set through warp -> gain -> convertTo(16S) -> feed -> blend -> convertTo(8U).
     use_ref: blend with the reference's own blenders.cpp (oracle/_ref) instead of the oracle's restatement."""
     if use_ref:
@@ -44,6 +44,8 @@ def compose(cal, frames, blender="multiband", num_bands=5, weight_type=O.CV_32F,
         warped = O.remap(f, xmap, ymap, O.INTER_LINEAR, O.BORDER_REFLECT)      # stitcher.cpp:275
         if gains is not None:
             warped = O.gain_apply(warped, gains[i])                            # stitcher.cpp:283
+        elif gain_maps is not None:
+            warped = O.blocks_gain_apply(warped, gain_maps[i])                 # BlocksGainCompensator::apply, exposure_compensate.cpp:225-246
         b.feed(warped.astype(np.int16), cal.masks[i], cal.corners[i])          # stitcher.cpp:285, 303
     dst, dmask = b.blend()                                                     # stitcher.cpp:307
     if output_8u:

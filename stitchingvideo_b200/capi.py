@@ -58,7 +58,8 @@ class SbCompositorConfig(C.Structure):
     _fields_ = [("n_cameras", C.c_int), ("src_size", SbSize), ("warper_kind", C.c_int), ("warper_scale", C.c_float),
                 ("K", C.POINTER(C.c_float)), ("R", C.POINTER(C.c_float)), ("blender_kind", C.c_int),
                 ("num_bands", C.c_int), ("weight_type", C.c_int), ("sharpness", C.c_float), ("comp_kind", C.c_int),
-                ("gains", C.POINTER(C.c_double)), ("seam_masks", C.POINTER(SbImage)), ("output_type", C.c_int)]
+                ("gains", C.POINTER(C.c_double)), ("seam_masks", C.POINTER(SbImage)), ("output_type", C.c_int),
+                ("gain_maps", C.POINTER(SbImage))]
 
 
 # every symbol include/stitchb200.h declares: name -> (restype, argtypes)
@@ -540,7 +541,8 @@ class Compositor:
     """The per-frame loop of Stitcher::composePanorama (stitcher.cpp:221-313) with calibration fixed."""
 
     def __init__(self, src_size, Ks, Rs, warper="spherical", scale=None, blender="multiband", num_bands=5,
-                 weight_type=CV_32F, sharpness=0.02, gains=None, seam_masks=None, output_type=CV_8UC3, device=0):
+                 weight_type=CV_32F, sharpness=0.02, gains=None, seam_masks=None, output_type=CV_8UC3, device=0,
+                 gain_maps=None):
         n = len(Ks)
         self.n = n
         self.device = device
@@ -563,6 +565,11 @@ class Compositor:
             g = np.ascontiguousarray(gains, np.float64)
             cfg.comp_kind = COMP_GAIN
             cfg.gains = g.ctypes.data_as(_P(C.c_double))
+        elif gain_maps is not None:          # BlocksGainCompensator: one float32 block gain map per camera
+            gkeep = [np.ascontiguousarray(m, np.float32) for m in gain_maps]
+            garr = (SbImage * n)(*[_image(m)[0] for m in gkeep])
+            cfg.comp_kind = COMP_GAIN_BLOCKS
+            cfg.gain_maps = garr
         else:
             cfg.comp_kind = COMP_NO
         keep = None

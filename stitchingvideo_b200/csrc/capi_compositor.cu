@@ -28,6 +28,8 @@ struct Camera {
     sb_point tl;                 // corner of the warped image in panorama coordinates
     int ww = 0, wh = 0;          // warped size (br - tl + 1)
     float gain = 1.f;
+    DevImage gain_full;          // SB_COMP_GAIN_BLOCKS: block gain map resized to the warped image (sequence-constant)
+    DevImage gain_rect;          // ... and laid out over the padded feed rect (BORDER_REFLECT, multi-band fast path)
     DevBuf tables;               // col_sin | col_cos | row_a | row_b
     WarpTables wt{};
     DevImage mask;               // warped (and seam-ANDed) mask, 8UC1 ww x wh
@@ -287,6 +289,17 @@ int setup(sb_compositor *c)
         if (ww <= 0 || wh <= 0 || ww * wh > (1LL << 31)) return fail(SB_ERR_ASSERT, "camera %d: degenerate warped ROI", i);
         cam.ww = (int)ww; cam.wh = (int)wh;
         cam.gain = (cfg.comp_kind == SB_COMP_GAIN && cfg.gains) ? (float)cfg.gains[i] : 1.f;
+        if (cfg.comp_kind == SB_COMP_GAIN_BLOCKS) {
+            // BlocksGainCompensator::apply: resize(gain_maps_[index], gain_map, image.size(), 0, 0, INTER_LINEAR) (exposure_compensate.cpp:233)
+            const sb_image &gm = cfg.gain_maps[i];
+            SB_ASSERT(gm.type == SB_32FC1 && gm.data && gm.rows > 0 && gm.cols > 0);
+            DevImage st;
+            DImage dgm;
+            SB_TRY(to_device(gm, st, s, &dgm));
+            SB_TRY(cam.gain_full.create(cam.wh, cam.ww, SB_32FC1));
+            SB_TRY(launch_resize_linear_32f(dgm, cam.gain_full.v, s));
+            SB_CUDA(cudaStreamSynchronize(s));
+        }
         tlx = std::min(tlx, cam.tl.x); tly = std::min(tly, cam.tl.y);
         brx = std::max(brx, cam.tl.x + cam.ww); bry = std::max(bry, cam.tl.y + cam.wh);
         // separable trig tables
@@ -374,6 +387,10 @@ int setup(sb_compositor *c)
         if (c->mb_fast) {
             for (int i = 0; i < n; ++i) {
                 Camera &cam = c->cams[i];
+                if (cfg.comp_kind == SB_COMP_GAIN_BLOCKS) {      // the gain seen by each padded-rect pixel (copyMakeBorder REFLECT)
+                    SB_TRY(cam.gain_rect.create(cam.rh, cam.rw, SB_32FC1));
+                    SB_TRY(launch_copy_make_border(cam.gain_full.v, cam.gain_rect.v, cam.top, cam.left, SB_BORDER_REFLECT, s));
+                }
                 cam.mb_tstep = ((size_t)cam.rw * sizeof(uint2) + 255) & ~(size_t)255;
                 SB_TRY(cam.mb_table.ensure(cam.mb_tstep * cam.rh));
                 SB_TRY(launch_mb_tap_table(cam.proj, cam.tl.x, cam.tl.y, cam.ww, cam.wh, cam.left, cam.top, cfg.src_size.width,
@@ -500,6 +517,7 @@ int mb_warp_stage(sb_compositor *c, Slot &s, const std::vector<DImage> &src, int
         wc.table = static_cast<const uint2 *>(cam.mb_table.p); wc.tstep = cam.mb_tstep;
         wc.g0 = static_cast<uint32_t *>(s.grgbx[i][0].buf.p); wc.gstep = s.grgbx[i][0].step;
         wc.rw = cam.rw; wc.rh = cam.rh; wc.gain = cam.gain;
+        if (c->cfg.comp_kind == SB_COMP_GAIN_BLOCKS) { wc.gmap = cam.gain_rect.v.ptr<float>(); wc.gmstep = cam.gain_rect.v.step; }
         double cols = 0;
         int cmax = 0;
         clip_runs(cam.g_runs[0], cam.rx, x0, x1, wc.cx, &cmax, &cols);
@@ -509,7 +527,7 @@ int mb_warp_stage(sb_compositor *c, Slot &s, const std::vector<DImage> &src, int
         bytes += img_bytes(src[i]) * std::min(1.0, cols / (double)std::min(cam.ww, src[i].cols)) + cols * cam.rh * (8 + 4);
     }
     if (mw == 0) return SB_OK;
-    PROF("mb_warp", bytes, launch_mb_warp(a, c->cfg.comp_kind == SB_COMP_GAIN, mw, mh, st));
+    PROF("mb_warp", bytes, launch_mb_warp(a, c->cfg.comp_kind != SB_COMP_NO, mw, mh, st));
     return SB_OK;
 }
 
@@ -669,12 +687,17 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
 {
     const sb_compositor_config &cfg = c->cfg;
     const int n = cfg.n_cameras;
-    const bool gain_on = cfg.comp_kind == SB_COMP_GAIN;
+    const bool gain_on = cfg.comp_kind != SB_COMP_NO, blocks = cfg.comp_kind == SB_COMP_GAIN_BLOCKS;
+
     cudaStream_t st = s.stream;
     DImage none;
     bool stream_ok = c->feather_tma && c->feather_variant == 1;      // the streaming frame kernel (feather / no blending)
     for (int i = 0; i < n && stream_ok; ++i)      // bulk copies need 16-byte aligned rows
         stream_ok = src[i].step % 16 == 0 && src[i].step < (1ull << 24) && reinterpret_cast<uintptr_t>(src[i].data) % 16 == 0;
+    if (blocks && !((cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused && c->mb_fast && c->mb_variant == 1) ||
+                    (cfg.blender_kind == SB_BLEND_FEATHER && c->fused && c->feather_fast) ||
+                    (cfg.blender_kind == SB_BLEND_NO && c->fused && c->feather_fast && stream_ok)))
+        return fail(SB_ERR_NOT_IMPL, "block gain maps are applied by the fused fast paths only");
     // Blender::prepare zeroes the accumulators (blenders.cpp:71-78, 227-232): only the unfused
     // (camera-by-camera) path has accumulators in HBM; the weight sums are resident either way
     if (cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused && c->mb_fast && c->mb_variant == 1) {
@@ -743,6 +766,8 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
                 const Camera &cam = c->cams[i];
                 FeatherTmaCam &fc = a.cam[i];
                 fc.src = src[i].ptr<uint8_t>(); fc.sstep = (unsigned)src[i].step; fc.gain = cam.gain;
+                fc.dx = cam.tl.x - c->dst_roi.x; fc.dy = cam.tl.y - c->dst_roi.y;
+                if (blocks) { fc.gmap = cam.gain_full.v.ptr<float>(); fc.gmstep = (unsigned)cam.gain_full.v.step; }
                 fc.tiles = static_cast<const uint2 *>(cam.feather_tiles.p);
             }
             a.desc = static_cast<const uint4 *>(c->tma_desc.p);
@@ -764,6 +789,7 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
                 fc.table = static_cast<const uint2 *>(cam.feather_table.p); fc.tstep = cam.feather_tstep;
                 fc.ww = cam.ww; fc.wh = cam.wh; fc.dx = cam.tl.x - c->dst_roi.x; fc.dy = cam.tl.y - c->dst_roi.y;
                 fc.gain = cam.gain;
+                if (blocks) { fc.gmap = cam.gain_full.v.ptr<float>(); fc.gmstep = cam.gain_full.v.step; }
             }
             a.tiles_x = div_up(s.out.v.cols, SB_FT_W);
             a.sharpness = cfg.sharpness;
@@ -841,8 +867,9 @@ int sb_compositor_create(const sb_compositor_config *cfg, int device, sb_composi
         return fail(SB_ERR_BAD_ARG, "unsupported warper kind %d", cfg->warper_kind);
     if (cfg->blender_kind != SB_BLEND_NO && cfg->blender_kind != SB_BLEND_FEATHER && cfg->blender_kind != SB_BLEND_MULTI_BAND)
         return fail(SB_ERR_BAD_ARG, "unsupported blending method");
-    if (cfg->comp_kind != SB_COMP_NO && cfg->comp_kind != SB_COMP_GAIN)
-        return fail(SB_ERR_BAD_ARG, "compositor supports SB_COMP_NO and SB_COMP_GAIN");
+    if (cfg->comp_kind != SB_COMP_NO && cfg->comp_kind != SB_COMP_GAIN && cfg->comp_kind != SB_COMP_GAIN_BLOCKS)
+        return fail(SB_ERR_BAD_ARG, "unsupported exposure compensation method");
+    SB_ASSERT(cfg->comp_kind != SB_COMP_GAIN_BLOCKS || cfg->gain_maps);
     if (cfg->blender_kind == SB_BLEND_MULTI_BAND) SB_ASSERT(cfg->weight_type == SB_32F || cfg->weight_type == SB_16S);
     SB_ASSERT(cfg->output_type == SB_8UC3 || cfg->output_type == SB_16SC3);
     SB_ASSERT(cfg->comp_kind != SB_COMP_GAIN || cfg->gains);
@@ -860,7 +887,7 @@ int sb_compositor_create(const sb_compositor_config *cfg, int device, sb_composi
         rc = make_slot(c, c->slots[0]);
     }
     // the config's pointers are not retained
-    c->cfg.K = c->cfg.R = nullptr; c->cfg.gains = nullptr; c->cfg.seam_masks = nullptr;
+    c->cfg.K = c->cfg.R = nullptr; c->cfg.gains = nullptr; c->cfg.seam_masks = nullptr; c->cfg.gain_maps = nullptr;
     if (rc != SB_OK) { sb_compositor_destroy(c); return rc; }
     *out = c;
     return SB_OK;

@@ -155,6 +155,12 @@ struct FtsSmem {
     int nc_hist[SB_FTS_PRODUCER_WARPS][SB_FTT_STAGES];      // per producer warp: cameras of its tiles in flight
 };
 
+// exposure gain of camera `c` at panorama pixel (X, Y): the scalar of GainCompensator or the resized block map
+__device__ __forceinline__ float fts_gain(const FeatherTmaCam &c, int X, int Y)
+{
+    return c.gmap ? __ldg(reinterpret_cast<const float *>(reinterpret_cast<const char *>(c.gmap) + (size_t)(Y - c.dy) * c.gmstep) + (X - c.dx)) : c.gain;
+}
+
 // lo = bytes 0..3, hi = bytes 4..7 of the 6 tap bytes at shared-memory byte address `a`
 __device__ __forceinline__ void lds_6bytes(uint32_t a, unsigned &lo, unsigned &hi)
 {
@@ -291,7 +297,7 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
                 }
                 bilinear_rgb(lo0, hi0, lo1, hi1, bw, v[p][0], v[p][1], v[p][2]);
                 if (GAIN) {                                 // saturate_cast<uchar>(p * gain)
-                    const float g = a.cam[rec.w & 15u].gain;
+                    const float g = fts_gain(a.cam[rec.w & 15u], X, Y0 + RPP * p);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) v[p][k] = min(max(__float2int_rn(__fmul_rn((float)v[p][k], g)), 0), 255);
                 }
@@ -365,7 +371,7 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
                 }
                 bilinear_rgb(lo0, hi0, lo1, hi1, bw, acc[p][0], acc[p][1], acc[p][2]);
                 if (GAIN) {
-                    const float g = a.cam[rec.w & 15u].gain;
+                    const float g = fts_gain(a.cam[rec.w & 15u], X, Y0 + RPP * p);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) acc[p][k] = min(max(__float2int_rn(__fmul_rn((float)acc[p][k], g)), 0), 255);
                 }
@@ -434,8 +440,8 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
                 wsum[p] = __fadd_rn(wsum[p], w);
                 int v0, v1, v2;
                 bilinear_rgb(lo0[p], hi0[p], lo1[p], hi1[p], bw[p], v0, v1, v2);
-                if (GAIN) {                                 // saturate_cast<uchar>(p * gain)
-                    const float g = a.cam[rec.w & 15u].gain;
+                if (GAIN && dist != 0u) {                   // saturate_cast<uchar>(p * gain)
+                    const float g = fts_gain(a.cam[rec.w & 15u], X, Y0 + RPP * p);
                     v0 = min(max(__float2int_rn(__fmul_rn((float)v0, g)), 0), 255);
                     v1 = min(max(__float2int_rn(__fmul_rn((float)v1, g)), 0), 255);
                     v2 = min(max(__float2int_rn(__fmul_rn((float)v2, g)), 0), 255);

@@ -170,9 +170,10 @@ k_feather_fused_px1(const __grid_constant__ FeatherFusedArgs a)
         int v0, v1, v2;
         bilinear_rgb(lo0, hi0, lo1, hi1, bw, v0, v1, v2);
         if (GAIN) {                                                           // saturate_cast<uchar>(p * gain)
-            v0 = min(max(__float2int_rn(__fmul_rn((float)v0, c.gain)), 0), 255);
-            v1 = min(max(__float2int_rn(__fmul_rn((float)v1, c.gain)), 0), 255);
-            v2 = min(max(__float2int_rn(__fmul_rn((float)v2, c.gain)), 0), 255);
+            const float g = c.gmap ? __ldg(reinterpret_cast<const float *>(reinterpret_cast<const char *>(c.gmap) + (size_t)(Y - c.dy) * c.gmstep) + (X - c.dx)) : c.gain;
+            v0 = min(max(__float2int_rn(__fmul_rn((float)v0, g)), 0), 255);
+            v1 = min(max(__float2int_rn(__fmul_rn((float)v1, g)), 0), 255);
+            v2 = min(max(__float2int_rn(__fmul_rn((float)v2, g)), 0), 255);
         }
         acc0 += __float2int_rz(__fmul_rn((float)v0, w));                      // static_cast<short>(src * w)
         acc1 += __float2int_rz(__fmul_rn((float)v1, w));

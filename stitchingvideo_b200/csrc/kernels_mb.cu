@@ -137,10 +137,11 @@ __global__ void __launch_bounds__(256) k_mb_warp(const __grid_constant__ MbWarpA
         if (py >= c.rh) break;
         int v0, v1, v2;
         bilinear_rgb(tap[r][0], tap[r][1], tap[r][2], tap[r][3], bw[r], v0, v1, v2);
-        if (GAIN) {                                         // saturate_cast<uchar>(p * gain)
-            v0 = min(max(__float2int_rn(__fmul_rn((float)v0, c.gain)), 0), 255);
-            v1 = min(max(__float2int_rn(__fmul_rn((float)v1, c.gain)), 0), 255);
-            v2 = min(max(__float2int_rn(__fmul_rn((float)v2, c.gain)), 0), 255);
+        if (GAIN) {                                         // saturate_cast<uchar>(p * gain): GainCompensator / BlocksGainCompensator
+            const float g = c.gmap ? __ldg(rowp<float>(c.gmap, c.gmstep, py) + px) : c.gain;
+            v0 = min(max(__float2int_rn(__fmul_rn((float)v0, g)), 0), 255);
+            v1 = min(max(__float2int_rn(__fmul_rn((float)v1, g)), 0), 255);
+            v2 = min(max(__float2int_rn(__fmul_rn((float)v2, g)), 0), 255);
         }
         rowp<uint32_t>(c.g0, c.gstep, py)[px] = (unsigned)v0 | ((unsigned)v1 << 8) | ((unsigned)v2 << 16);
     }

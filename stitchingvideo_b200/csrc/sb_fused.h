@@ -20,6 +20,8 @@ struct FeatherCam {
     int ww, wh;            // warped size
     int dx, dy;            // warped corner in panorama coordinates
     float gain;
+    const float *gmap;     // SB_COMP_GAIN_BLOCKS: gain per warped pixel (null: the scalar gain)
+    size_t gmstep;
 };
 
 constexpr int SB_FT_W = 32, SB_FT_H = 8;         // panorama pixels per block of k_feather_fused_px1 = camera-mask tile
@@ -55,6 +57,9 @@ struct FeatherTmaCam {
     const uint8_t *src;    // 16-byte aligned, sstep a multiple of 16
     unsigned sstep;
     float gain;
+    const float *gmap;     // SB_COMP_GAIN_BLOCKS: gain per warped pixel (null: the scalar gain)
+    unsigned gmstep;
+    int dx, dy;            // warped corner in panorama coordinates (gain map lookup)
     const uint2 *tiles;    // tile-major table blocks of this camera
 };
 struct FeatherTmaArgs {

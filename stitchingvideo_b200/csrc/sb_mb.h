@@ -13,6 +13,8 @@ struct MbWarpCam {
     size_t gstep;
     int rw, rh;            // padded feed rect (blenders.cpp:241-269)
     float gain;
+    const float *gmap;     // SB_COMP_GAIN_BLOCKS: per padded-rect pixel gain (null: the scalar gain)
+    size_t gmstep;
     int cx[4];             // columns of the rect to produce: [cx[0], cx[1]) and [cx[2], cx[3]) (empty runs have lo >= hi)
 };
 struct MbWarpArgs {

@@ -363,3 +363,31 @@ def test_frame_set_in_one_host_block(gpu):
         got, gmask = comp.compose([block[i] for i in range(n)])
         assert_same(got, want, rig + " one-block frame set")
         assert_same(gmask, wmask, rig + " one-block mask")
+
+
+@pytest.mark.parametrize("rig,blender", [("mini", "multiband"), ("mini_cyl", "feather"), ("mini_cyl", "no")])
+def test_compositor_blocks_gain(gpu, rig, blender):
+    """BlocksGainCompensator::apply inside the fused frame kernels (the live app's BlockApply, APP64:310-331, 754):
+    per-camera block gain maps, resized once with INTER_LINEAR, multiplied in per pixel."""
+    from stitchingvideo_b200 import rigs
+    Ks, Rs, spec = rigs.cameras(rig)
+    size, n = (spec["W"], spec["H"]), spec["n_used"]
+    rng = np.random.default_rng(70)
+    comp0 = gpu.Compositor(size, Ks, Rs, warper=spec["warper"], scale=spec["scale"], blender=blender)
+    gmaps = []
+    for i in range(n):
+        x, y, w, h = comp0.camera_roi(i)
+        gmaps.append(rng.uniform(0.7, 1.4, ((h + 31) // 32, (w + 31) // 32)).astype(np.float32))     # 32x32 blocks (exposure_compensate.cpp:165-170)
+    comp = gpu.Compositor(size, Ks, Rs, warper=spec["warper"], scale=spec["scale"], blender=blender, gain_maps=gmaps)
+    cal = P.Calibration(size, Ks, Rs, spec["warper"], spec["scale"])
+    frames = [rigs.frame(rig, 5, i) for i in range(n)]
+    ref, rmask = P.compose(cal, frames, blender=blender, gain_maps=gmaps)
+    for fused in ((11, 12, 13) if blender == "multiband" else (11, 10) if blender == "feather" else (11,)):
+        comp.set_fused(fused)
+        pano, mask = comp.compose(frames)
+        assert_same(pano, ref, "%s/%s blocks gain (variant %d)" % (rig, blender, fused))
+        assert_same(mask, rmask, "%s/%s blocks gain mask (variant %d)" % (rig, blender, fused))
+    comp.set_fused(0)
+    with pytest.raises(gpu.StitchError) as e:
+        comp.compose(frames)
+    assert e.value.code == -213                  # the staged path applies scalar gains only
