@@ -70,9 +70,18 @@ void sb_host_free(void *ptr);
  * RotationWarper — INC/detail/warpers.hpp:53-72 (interface), :102-125 (RotationWarperBase),
  * factories INC/warpers.hpp:50-167.  kind selects the projector.
  * ===================================================================================== */
-enum { SB_WARP_PLANE = 0,        /* PlaneWarper      INC/detail/warpers.hpp:135-161 */
-       SB_WARP_CYLINDRICAL = 1,  /* CylindricalWarper INC/detail/warpers.hpp:352-364 */
-       SB_WARP_SPHERICAL = 2 };  /* SphericalWarper   INC/detail/warpers.hpp:330-340 */
+enum { SB_WARP_PLANE = 0,        /* PlaneWarper      INC/detail/warpers.hpp:129-147 */
+       SB_WARP_CYLINDRICAL = 1,  /* CylindricalWarper INC/detail/warpers.hpp:177-187 */
+       SB_WARP_SPHERICAL = 2,    /* SphericalWarper   INC/detail/warpers.hpp:159-166 */
+       /* The remaining projectors of INC/detail/warpers.hpp:190-503.  Their maps use
+        * atan2f/asinf/tanf/logf/sinhf... of the host libm, exactly like the reference's host code, and are
+        * built on the HOST once per calibration (buildMaps) and uploaded; the per-frame remap is the same CUDA
+        * kernel.  Object API only (not the fused compositor). */
+       SB_WARP_FISHEYE = 3, SB_WARP_STEREOGRAPHIC = 4,
+       SB_WARP_COMPRESSED_RECTILINEAR = 5, SB_WARP_COMPRESSED_RECTILINEAR_PORTRAIT = 6,   /* parameters a, b */
+       SB_WARP_PANINI = 7, SB_WARP_PANINI_PORTRAIT = 8,                                   /* parameters a, b */
+       SB_WARP_MERCATOR = 9, SB_WARP_TRANSVERSE_MERCATOR = 10,
+       SB_WARP_SPHERICAL_PORTRAIT = 11, SB_WARP_CYLINDRICAL_PORTRAIT = 12, SB_WARP_PLANE_PORTRAIT = 13 };
 typedef struct sb_warper sb_warper;
 
 /* WarperCreator::create(scale) (INC/warpers.hpp:50-83) */
@@ -82,6 +91,8 @@ float sb_warper_get_scale(const sb_warper *w);                       /* warpers.
 int   sb_warper_set_scale(sb_warper *w, float scale);                /* warpers.hpp:119 */
 /* PlaneWarper's T overloads (warpers.cpp:81-137): translation used by subsequent calls (default 0) */
 int   sb_warper_set_translation(sb_warper *w, const float T[3]);
+/* the (A, B) constructor arguments of the CompressedRectilinear / Panini warpers (warpers.hpp:227-299; default 1, 1) */
+int   sb_warper_set_ab(sb_warper *w, float a, float b);
 
 /* RotationWarper::warpPoint (warpers_inl.hpp:52-59).  K, R: row-major 3x3 float32 (warpers.cpp:52-54) */
 int sb_warper_warp_point(sb_warper *w, const float pt[2], const float K[9], const float R[9], float uv[2]);

@@ -176,6 +176,34 @@ public:
     explicit SphericalWarper(float scale, int device = 0) : RotationWarper(SB_WARP_SPHERICAL, scale, device) {}
 };
 
+// the remaining projectors of detail/warpers.hpp:190-503: maps are built on the host (libm), the remap runs on the device
+#define SB200_SIMPLE_WARPER(NAME, KIND)                                                                  \
+    class NAME : public RotationWarper {                                                                  \
+    public:                                                                                               \
+        explicit NAME(float scale, int device = 0) : RotationWarper(KIND, scale, device) {}               \
+    }
+#define SB200_AB_WARPER(NAME, KIND)                                                                      \
+    class NAME : public RotationWarper {                                                                  \
+    public:                                                                                               \
+        explicit NAME(float scale, float A = 1.f, float B = 1.f, int device = 0) : RotationWarper(KIND, scale, device) \
+        {                                                                                                 \
+            check(sb_warper_set_ab(h_, A, B));                                                            \
+        }                                                                                                 \
+    }
+SB200_SIMPLE_WARPER(FisheyeWarper, SB_WARP_FISHEYE);
+SB200_SIMPLE_WARPER(StereographicWarper, SB_WARP_STEREOGRAPHIC);
+SB200_AB_WARPER(CompressedRectilinearWarper, SB_WARP_COMPRESSED_RECTILINEAR);
+SB200_AB_WARPER(CompressedRectilinearPortraitWarper, SB_WARP_COMPRESSED_RECTILINEAR_PORTRAIT);
+SB200_AB_WARPER(PaniniWarper, SB_WARP_PANINI);
+SB200_AB_WARPER(PaniniPortraitWarper, SB_WARP_PANINI_PORTRAIT);
+SB200_SIMPLE_WARPER(MercatorWarper, SB_WARP_MERCATOR);
+SB200_SIMPLE_WARPER(TransverseMercatorWarper, SB_WARP_TRANSVERSE_MERCATOR);
+SB200_SIMPLE_WARPER(SphericalPortraitWarper, SB_WARP_SPHERICAL_PORTRAIT);
+SB200_SIMPLE_WARPER(CylindricalPortraitWarper, SB_WARP_CYLINDRICAL_PORTRAIT);
+SB200_SIMPLE_WARPER(PlanePortraitWarper, SB_WARP_PLANE_PORTRAIT);
+#undef SB200_SIMPLE_WARPER
+#undef SB200_AB_WARPER
+
 // cv::WarperCreator and its subclasses (INC/warpers.hpp:50-83)
 struct WarperCreator {
     virtual ~WarperCreator() {}

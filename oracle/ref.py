@@ -31,6 +31,7 @@ def lib():
         L.ref_blender_feed.argtypes = [C.c_void_p, C.POINTER(O.SoMat), C.POINTER(O.SoMat), C.c_int, C.c_int]
         L.ref_blender_blend.argtypes = [C.c_void_p, C.POINTER(O.SoMat), C.POINTER(O.SoMat)]
         L.ref_create_weight_map.argtypes = [C.POINTER(O.SoMat), C.c_float, C.POINTER(O.SoMat)]
+        L.ref_set_ab.argtypes = [C.c_float, C.c_float]
         L.ref_warp_roi.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         L.ref_warp_point.argtypes = [C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_build_maps.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int),
@@ -46,7 +47,9 @@ def _chk(rc, what):
         raise RuntimeError("reference %s failed rc=%d" % (what, rc))
 
 
-_KIND = {"plane": O.WARP_PLANE, "cylindrical": O.WARP_CYLINDRICAL, "spherical": O.WARP_SPHERICAL}
+_KIND = {"plane": 0, "cylindrical": 1, "spherical": 2, "fisheye": 3, "stereographic": 4, "compressedRectilinear": 5,
+         "compressedRectilinearPortrait": 6, "panini": 7, "paniniPortrait": 8, "mercator": 9, "transverseMercator": 10,
+         "sphericalPortrait": 11, "cylindricalPortrait": 12, "planePortrait": 13}
 
 
 def _f9(m):
@@ -56,15 +59,20 @@ def _f9(m):
 class Warper:
     """detail::RotationWarper through the reference's RotationWarperBase<P> (warpers_inl.hpp / warpers.cpp)."""
 
-    def __init__(self, kind, scale):
-        self.kind, self.scale = _KIND.get(kind, kind), float(scale)
+    def __init__(self, kind, scale, a=1.0, b=1.0):
+        self.kind, self.scale, self.a, self.b = _KIND.get(kind, kind), float(scale), float(a), float(b)
+
+    def _ab(self):
+        lib().ref_set_ab(C.c_float(self.a), C.c_float(self.b))
 
     def warp_roi(self, src_size, K, R):
+        self._ab()
         K, R, roi = _f9(K), _f9(R), (C.c_int * 4)()
         _chk(lib().ref_warp_roi(self.kind, self.scale, src_size[0], src_size[1], K.ctypes.data, R.ctypes.data, roi), "warpRoi")
         return tuple(roi)
 
     def warp_point(self, pt, K, R):
+        self._ab()
         K, R = _f9(K), _f9(R)
         p, uv = np.asarray(pt, np.float32), np.zeros(2, np.float32)
         _chk(lib().ref_warp_point(self.kind, self.scale, p.ctypes.data, K.ctypes.data, R.ctypes.data, uv.ctypes.data), "warpPoint")

@@ -39,13 +39,26 @@ static int copy_out(const Mat &src, so_mat *dst)
         std::memcpy((char *)dst->data + (size_t)y * dst->step, src.ptr<unsigned char>(y), (size_t)src.cols * src.elemSize());
     return 0;
 }
+static float g_a = 1.f, g_b = 1.f;      // (A, B) of the CompressedRectilinear / Panini warpers
 static cv::Ptr<cv::detail::RotationWarper> make_warper(int kind, float scale)
 {
-    switch (kind) {
-    case SO_WARP_PLANE: return new cv::detail::PlaneWarper(scale);
-    case SO_WARP_CYLINDRICAL: return new cv::detail::CylindricalWarper(scale);
-    case SO_WARP_SPHERICAL: return new cv::detail::SphericalWarper(scale);
+    switch (kind) {      // kind numbers = SB_WARP_* of include/stitchb200.h
+    case 0: return new cv::detail::PlaneWarper(scale);
+    case 1: return new cv::detail::CylindricalWarper(scale);
+    case 2: return new cv::detail::SphericalWarper(scale);
+    case 3: return new cv::detail::FisheyeWarper(scale);
+    case 4: return new cv::detail::StereographicWarper(scale);
+    case 5: return new cv::detail::CompressedRectilinearWarper(scale, g_a, g_b);
+    case 6: return new cv::detail::CompressedRectilinearPortraitWarper(scale, g_a, g_b);
+    case 7: return new cv::detail::PaniniWarper(scale, g_a, g_b);
+    case 8: return new cv::detail::PaniniPortraitWarper(scale, g_a, g_b);
+    case 9: return new cv::detail::MercatorWarper(scale);
+    case 10: return new cv::detail::TransverseMercatorWarper(scale);
+    case 11: return new cv::detail::SphericalPortraitWarper(scale);
+    case 12: return new cv::detail::CylindricalPortraitWarper(scale);
+    case 13: return new cv::detail::PlanePortraitWarper(scale);
     }
+    CV_Error(CV_StsBadArg, "unknown warper kind");
     return cv::Ptr<cv::detail::RotationWarper>();
 }
 static Mat mat3(const float *m)
@@ -62,6 +75,7 @@ struct ref_blender {
 
 extern "C" {
 
+void ref_set_ab(float a, float b) { g_a = a; g_b = b; }
 const char *ref_version(void) { return "reference sources (blenders.cpp, warpers.cpp, util.cpp) on the OpenCV shim"; }
 
 ref_blender *ref_blender_create(int kind, int num_bands, int weight_type, float sharpness)

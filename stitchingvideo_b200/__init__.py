@@ -12,6 +12,8 @@ from .capi import (  # noqa: F401
     CV_16SC1, CV_16SC3, CV_32F, CV_32FC1, INTER_LINEAR, INTER_NEAREST, Blender, BlocksGainCompensator,
     Compositor, CylindricalWarper, DeviceImage, ExposureCompensator, FeatherBlender, GainCompensator,
     MultiBandBlender, NoExposureCompensator, PlaneWarper, RotationWarper, SphericalWarper, StitchError,
+    CompressedRectilinearPortraitWarper, CompressedRectilinearWarper, CylindricalPortraitWarper, FisheyeWarper, MercatorWarper,
+    PaniniPortraitWarper, PaniniWarper, PlanePortraitWarper, SphericalPortraitWarper, StereographicWarper, TransverseMercatorWarper,
     convertMaps, createLaplacePyr, createWeightMap, device_count, kernel_launch_count, lib, normalizeUsingWeightMap, remap,
     restoreImageFromLaplacePyr,
 )

@@ -24,6 +24,8 @@ CV_8UC1, CV_8UC3, CV_16SC1, CV_16SC3, CV_32FC1 = 0, 16, 3, 19, 5
 INTER_NEAREST, INTER_LINEAR = 0, 1
 BORDER_CONSTANT, BORDER_REPLICATE, BORDER_REFLECT, BORDER_WRAP, BORDER_REFLECT_101 = 0, 1, 2, 3, 4
 WARP_PLANE, WARP_CYLINDRICAL, WARP_SPHERICAL = 0, 1, 2
+(WARP_FISHEYE, WARP_STEREOGRAPHIC, WARP_COMPRESSED_RECTILINEAR, WARP_COMPRESSED_RECTILINEAR_PORTRAIT, WARP_PANINI, WARP_PANINI_PORTRAIT,
+ WARP_MERCATOR, WARP_TRANSVERSE_MERCATOR, WARP_SPHERICAL_PORTRAIT, WARP_CYLINDRICAL_PORTRAIT, WARP_PLANE_PORTRAIT) = range(3, 14)
 COMP_NO, COMP_GAIN, COMP_GAIN_BLOCKS = 0, 1, 2
 BLEND_NO, BLEND_FEATHER, BLEND_MULTI_BAND = 0, 1, 2
 SB_OK, SB_ERR_NO_MEM, SB_ERR_BAD_ARG, SB_ERR_ASSERT, SB_ERR_NOT_IMPL, SB_ERR_CUDA = 0, -4, -5, -215, -213, -217
@@ -78,6 +80,7 @@ API = {
     "sb_warper_get_scale": (C.c_float, [C.c_void_p]),
     "sb_warper_set_scale": (C.c_int, [C.c_void_p, C.c_float]),
     "sb_warper_set_translation": (C.c_int, [C.c_void_p, _F9]),
+    "sb_warper_set_ab": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
     "sb_warper_warp_point": (C.c_int, [C.c_void_p, _F9, _F9, _F9, _F9]),
     "sb_warper_warp_roi": (C.c_int, [C.c_void_p, SbSize, _F9, _F9, _P(SbRect)]),
     "sb_warper_build_maps": (C.c_int, [C.c_void_p, SbSize, _F9, _F9, _P(SbImage), _P(SbImage), _P(SbRect)]),
@@ -321,6 +324,58 @@ class PlaneWarper(RotationWarper):
     def setTranslation(self, T):
         t = np.ascontiguousarray(T, np.float32).reshape(3)
         _check(lib().sb_warper_set_translation(self._h, _fp(t)))
+
+
+class _ABWarper(RotationWarper):
+    """CompressedRectilinear / Panini warpers: (scale, A = 1, B = 1) (warpers.hpp:227-299)."""
+
+    def __init__(self, scale=1.0, A=1.0, B=1.0, device=0):
+        super().__init__(scale, device)
+        _check(lib().sb_warper_set_ab(self._h, C.c_float(A), C.c_float(B)))
+
+
+class FisheyeWarper(RotationWarper):
+    KIND = WARP_FISHEYE
+
+
+class StereographicWarper(RotationWarper):
+    KIND = WARP_STEREOGRAPHIC
+
+
+class CompressedRectilinearWarper(_ABWarper):
+    KIND = WARP_COMPRESSED_RECTILINEAR
+
+
+class CompressedRectilinearPortraitWarper(_ABWarper):
+    KIND = WARP_COMPRESSED_RECTILINEAR_PORTRAIT
+
+
+class PaniniWarper(_ABWarper):
+    KIND = WARP_PANINI
+
+
+class PaniniPortraitWarper(_ABWarper):
+    KIND = WARP_PANINI_PORTRAIT
+
+
+class MercatorWarper(RotationWarper):
+    KIND = WARP_MERCATOR
+
+
+class TransverseMercatorWarper(RotationWarper):
+    KIND = WARP_TRANSVERSE_MERCATOR
+
+
+class SphericalPortraitWarper(RotationWarper):
+    KIND = WARP_SPHERICAL_PORTRAIT
+
+
+class CylindricalPortraitWarper(RotationWarper):
+    KIND = WARP_CYLINDRICAL_PORTRAIT
+
+
+class PlanePortraitWarper(RotationWarper):
+    KIND = WARP_PLANE_PORTRAIT
 
 
 class CylindricalWarper(RotationWarper):

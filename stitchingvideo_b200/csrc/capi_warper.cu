@@ -6,6 +6,7 @@
 // (SURVEY.md §8a a1, a2); per-pixel work (a3, a4) is CUDA.
 #include <cfloat>
 #include <cmath>
+#include <vector>
 
 #include "sb_kernels.h"
 #include "sb_host_projector.h"
@@ -17,6 +18,7 @@ struct sb_warper {
     int kind = 0;
     float scale = 1.f;
     float t[3] = {0, 0, 0};
+    float a = 1.f, b = 1.f;      // CompressedRectilinear / Panini parameters
     cudaStream_t stream = nullptr;
     // maps cached by the last build_maps (the app's xmap1/ymap1, APP64:188-198)
     DevImage xmap, ymap;
@@ -26,21 +28,35 @@ struct sb_warper {
 };
 
 namespace {
-int kind_ok(int kind) { return kind == SB_WARP_PLANE || kind == SB_WARP_CYLINDRICAL || kind == SB_WARP_SPHERICAL; }
+int kind_ok(int kind) { return kind >= SB_WARP_PLANE && kind <= SB_WARP_PLANE_PORTRAIT; }
+bool device_maps(int kind) { return kind == SB_WARP_PLANE || kind == SB_WARP_CYLINDRICAL || kind == SB_WARP_SPHERICAL; }
+void set_params(const sb_warper *w, ProjParams &p, const float K[9], const float R[9])
+{
+    projector_set(p, w->kind, w->scale, K, R, w->t);
+    p.a = w->a; p.b = w->b;
+}
 
 int build_maps_dev(sb_warper *w, sb_size src_size, const float K[9], const float R[9], sb_point *tl, sb_point *br)
 {
     SB_ASSERT(K && R);
     SB_ASSERT(src_size.width > 0 && src_size.height > 0);
     ProjParams p;
-    projector_set(p, w->kind, w->scale, K, R, w->t);
+    set_params(w, p, K, R);
     projector_detect_result_roi(p, src_size.width, src_size.height, tl, br);
     long long mw = (long long)br->x - tl->x + 1, mh = (long long)br->y - tl->y + 1;
     if (mw <= 0 || mh <= 0 || mw * mh > (1LL << 31))
         return fail(SB_ERR_ASSERT, "degenerate warped ROI %lld x %lld (check K, R, scale)", mw, mh);
     SB_TRY(w->xmap.create((int)mh, (int)mw, SB_32FC1));
     SB_TRY(w->ymap.create((int)mh, (int)mw, SB_32FC1));
-    SB_TRY(launch_build_maps(p, tl->x, tl->y, w->xmap.v, w->ymap.v, w->stream));
+    if (device_maps(w->kind)) {
+        SB_TRY(launch_build_maps(p, tl->x, tl->y, w->xmap.v, w->ymap.v, w->stream));
+    } else {      // libm-heavy projectors: maps built on the host once per calibration (as the reference does), uploaded
+        std::vector<float> hx((size_t)mw * mh), hy(hx.size());
+        projector_build_maps_host(p, *tl, *br, hx.data(), hy.data());
+        SB_CUDA(cudaMemcpy2DAsync(w->xmap.v.data, w->xmap.v.step, hx.data(), (size_t)mw * 4, (size_t)mw * 4, (size_t)mh, cudaMemcpyHostToDevice, w->stream));
+        SB_CUDA(cudaMemcpy2DAsync(w->ymap.v.data, w->ymap.v.step, hy.data(), (size_t)mw * 4, (size_t)mw * 4, (size_t)mh, cudaMemcpyHostToDevice, w->stream));
+        SB_CUDA(cudaStreamSynchronize(w->stream));
+    }
     w->have_maps = true;
     return SB_OK;
 }
@@ -103,11 +119,18 @@ int sb_warper_set_translation(sb_warper *w, const float T[3])
     return SB_OK;
 }
 
+int sb_warper_set_ab(sb_warper *w, float a, float b)
+{
+    SB_ASSERT(w);
+    w->a = a; w->b = b;
+    return SB_OK;
+}
+
 int sb_warper_warp_point(sb_warper *w, const float pt[2], const float K[9], const float R[9], float uv[2])
 {
     SB_ASSERT(w && pt && K && R && uv);
     ProjParams p;
-    projector_set(p, w->kind, w->scale, K, R, w->t);
+    set_params(w, p, K, R);
     projector_map_forward(p, pt[0], pt[1], &uv[0], &uv[1]);
     return SB_OK;
 }
@@ -116,7 +139,7 @@ int sb_warper_warp_roi(sb_warper *w, sb_size src_size, const float K[9], const f
 {
     SB_ASSERT(w && K && R && roi);
     ProjParams p;
-    projector_set(p, w->kind, w->scale, K, R, w->t);
+    set_params(w, p, K, R);
     sb_point tl, br;
     projector_detect_result_roi(p, src_size.width, src_size.height, &tl, &br);
     roi->x = tl.x; roi->y = tl.y; roi->width = br.x + 1 - tl.x; roi->height = br.y + 1 - tl.y;
@@ -171,7 +194,7 @@ int sb_warper_warp_backward(sb_warper *w, const sb_image *src, const float K[9],
     DeviceGuard g(w->device);
     if (!g.ok) return SB_ERR_CUDA;
     ProjParams p;
-    projector_set(p, w->kind, w->scale, K, R, w->t);
+    set_params(w, p, K, R);
     sb_point tl, br;
     projector_detect_result_roi(p, dst_size.width, dst_size.height, &tl, &br);
     SB_ASSERT(br.x - tl.x + 1 == src->cols && br.y - tl.y + 1 == src->rows);

@@ -9,6 +9,7 @@ struct ProjParams {
     int kind;
     float scale;
     float k[9], rinv[9], r_kinv[9], k_rinv[9], t[3];
+    float a, b;      // CompressedRectilinear / Panini parameters
 };
 
 // ---- warp (kernels_warp.cu) -------------------------------------------------------------------

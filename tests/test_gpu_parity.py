@@ -391,3 +391,36 @@ def test_compositor_blocks_gain(gpu, rig, blender):
     with pytest.raises(gpu.StitchError) as e:
         comp.compose(frames)
     assert e.value.code == -213                  # the staged path applies scalar gains only
+
+
+@pytest.mark.parametrize("name,ab", [("fisheye", None), ("stereographic", None), ("compressedRectilinear", (1.5, 1.0)),
+                                     ("compressedRectilinearPortrait", (2.0, 1.0)), ("panini", (1.5, 1.0)), ("paniniPortrait", (2.0, 1.0)),
+                                     ("mercator", None), ("transverseMercator", None), ("sphericalPortrait", None),
+                                     ("cylindricalPortrait", None), ("planePortrait", None)])
+def test_remaining_projectors_against_reference_sources(gpu, name, ab):
+    """The other projectors of detail/warpers.hpp: host-built maps + the CUDA remap, against the
+    reference's own RotationWarperBase<P> code compiled into oracle/_ref."""
+    from oracle import ref as RF
+    if not RF.available():
+        pytest.skip("oracle/_ref not built")
+    cls = getattr(gpu, name[0].upper() + name[1:] + "Warper")
+    rng = np.random.default_rng(80)
+    for trial in range(3):
+        W, H = int(rng.integers(120, 260)), int(rng.integers(90, 200))
+        K, R = util.random_camera(rng, W, H, yaw=float(rng.uniform(-0.5, 0.5)))
+        scale = float(rng.uniform(150, 400))
+        w = cls(scale, *ab) if ab else cls(scale)
+        rw = RF.Warper(name, scale, *(ab or (1.0, 1.0)))
+        assert w.warpRoi((W, H), K, R) == rw.warp_roi((W, H), K, R), "%s warpRoi" % name
+        u, v = w.warpPoint((W / 3.0, H / 5.0), K, R)
+        ru, rv = rw.warp_point((W / 3.0, H / 5.0), K, R)
+        assert (np.float32(u), np.float32(v)) == (np.float32(ru), np.float32(rv)), "%s warpPoint" % name
+        roi, xm, ym = w.buildMaps((W, H), K, R)
+        rroi, rxm, rym = rw.build_maps((W, H), K, R)
+        assert tuple(roi) == tuple(rroi)
+        assert_same(xm, rxm, name + " xmap")
+        assert_same(ym, rym, name + " ymap")
+        img = util.smooth_image(rng, H, W)
+        (tl, dst), (rtl, rdst) = w.warp(img, K, R), rw.warp(img, K, R)
+        assert tuple(tl) == tuple(rtl)
+        assert_same(dst, rdst, name + " warp")
