@@ -566,7 +566,8 @@ int mb_down_stage(sb_compositor *c, Slot &s, int l, int ox0, int ox1)
     int tx[SB_MAX_CAMERAS], t[SB_MAX_CAMERAS], mw, mh;
     double bytes = 0;
     if (!fill_down(c, s, l, ox0, ox1, a, tx, t, mw, mh, bytes)) return SB_OK;
-    PROF("mb_pyr_down", bytes, launch_mb_pyr_down(a, mw, mh, st));
+    static const char *const names[] = {"mb_pyr_down_L0", "mb_pyr_down_L1", "mb_pyr_down_L2", "mb_pyr_down_L3", "mb_pyr_down_L4", "mb_pyr_down_L5+"};
+    PROF(names[std::min(l, 5)], bytes, launch_mb_pyr_down(a, mw, mh, st));
     return SB_OK;
 }
 
@@ -638,7 +639,8 @@ int mb_band_stage(sb_compositor *c, Slot &s, int l, int bx0, int bx1)
     double bytes = 0;
     if (!fill_band(c, s, l, bx0, bx1, a, bytes)) return SB_OK;
     const bool fin = l == 0;
-    PROF(fin ? "mb_band_final" : "mb_band", bytes,
+    static const char *const names[] = {"mb_band_final", "mb_band_L1", "mb_band_L2", "mb_band_L3", "mb_band_L4", "mb_band_L5+"};
+    PROF(names[std::min(l, 5)], bytes,
          launch_mb_band(a, c->cfg.weight_type == SB_32F, l < c->num_bands, fin, s.out.v.type == SB_8UC3, st));
     return SB_OK;
 }

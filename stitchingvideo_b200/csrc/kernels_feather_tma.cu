@@ -484,7 +484,10 @@ int launch_feather_stream(const FeatherTmaArgs &a, bool apply_gain, bool out8, i
 {
     SB_ASSERT(a.sharpness > 0.f && a.bilin_lut && a.desc && a.n_tiles > 0 && a.n <= 16);
     const size_t smem = sizeof(FtsSmem);
-    static bool configured[8] = {false, false, false, false, false, false, false, false};
+    static bool configured_dev[64][8] = {};                  // the attribute is per device (context)
+    int dev = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    bool *configured = configured_dev[dev & 63];
     const void *fn[8] = {(const void *)k_feather_stream<false, false, false>, (const void *)k_feather_stream<false, true, false>,
                          (const void *)k_feather_stream<true, false, false>, (const void *)k_feather_stream<true, true, false>,
                          (const void *)k_feather_stream<false, false, true>, (const void *)k_feather_stream<false, true, true>,
