@@ -408,7 +408,7 @@ int setup(sb_compositor *c)
                     g.cam[i].rw = cam.w_pyr[l].v.cols; g.cam[i].rh = cam.w_pyr[l].v.rows;
                 }
                 SB_TRY(c->mb_tile_mask[l].ensure(sizeof(uint32_t) * (size_t)div_up(g.lw, 32) * div_up(g.lh, 8)));
-                SB_TRY(launch_mb_tile_mask(g, wt == SB_32FC1, g.lw, g.lh, static_cast<uint32_t *>(c->mb_tile_mask[l].p), s));
+                SB_TRY(launch_mb_tile_mask(g, wt == SB_32FC1, g.lw, g.lh, c->wsum[l].v.data, c->wsum[l].v.step, static_cast<uint32_t *>(c->mb_tile_mask[l].p), s));
             }
         }
     } else if (cfg.blender_kind == SB_BLEND_FEATHER || cfg.blender_kind == SB_BLEND_NO) {

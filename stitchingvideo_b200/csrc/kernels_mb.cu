@@ -78,27 +78,37 @@ int launch_mb_tap_table(const ProjParams &p, int tl_x, int tl_y, int ww, int wh,
 }
 
 // ------------------------------------------------------------------------------------ setup: tile masks
-// mask[tile] bit i set when camera i has a non-zero weight inside the 32x8 tile of band l
+// mask[tile] bit i set when camera i has a non-zero weight inside the 32x8 tile of band l.  Bit 31 (float weights):
+// the tile is "plain" — exactly one camera carries weight, that weight is exactly 1.0f on every pixel of the tile and
+// so is the weight sum; the band kernel then needs no float arithmetic there (see mb_band_thread).
 template <typename WT>
-__global__ void __launch_bounds__(256) k_mb_tile_mask(MbBandGeom g, uint32_t *mask, int tiles_x)
+__global__ void __launch_bounds__(256) k_mb_tile_mask(MbBandGeom g, const WT *wsum, size_t wsum_step, uint32_t *mask, int tiles_x)
 {
     const int X = blockIdx.x * 32 + threadIdx.x, Y = blockIdx.y * 8 + threadIdx.y;
+    const bool inside = X < g.lw && Y < g.lh;
     uint32_t m = 0;
+    int n_nz = 0;
+    bool one = inside;
     for (int i = 0; i < g.n; ++i) {
         const int x = X - g.cam[i].rx, y = Y - g.cam[i].ry;
         bool nz = false;
-        if ((unsigned)x < (unsigned)g.cam[i].rw && (unsigned)y < (unsigned)g.cam[i].rh)
-            nz = rowp<WT>(g.cam[i].weight, g.cam[i].wstep, y)[x] != (WT)0;
+        if (inside && (unsigned)x < (unsigned)g.cam[i].rw && (unsigned)y < (unsigned)g.cam[i].rh) {
+            const WT w = rowp<WT>(g.cam[i].weight, g.cam[i].wstep, y)[x];
+            nz = w != (WT)0;
+            if (nz) { ++n_nz; one = one && sizeof(WT) == 4 && (float)w == 1.f; }
+        }
         if (__syncthreads_or(nz)) m |= 1u << i;
     }
-    if (threadIdx.x == 0 && threadIdx.y == 0) mask[blockIdx.y * tiles_x + blockIdx.x] = m;
+    one = one && n_nz == 1 && (float)rowp<WT>(wsum, wsum_step, inside ? Y : 0)[inside ? X : 0] == 1.f;
+    const bool plain = __syncthreads_and(one) && __popc(m) == 1 && sizeof(WT) == 4;
+    if (threadIdx.x == 0 && threadIdx.y == 0) mask[blockIdx.y * tiles_x + blockIdx.x] = m | (plain ? 0x80000000u : 0u);
 }
 
-int launch_mb_tile_mask(const MbBandGeom &g, bool float_weights, int lw, int lh, uint32_t *mask, cudaStream_t s)
+int launch_mb_tile_mask(const MbBandGeom &g, bool float_weights, int lw, int lh, const void *wsum, size_t wsum_step, uint32_t *mask, cudaStream_t s)
 {
     dim3 block(32, 8), grid(div_up(lw, 32), div_up(lh, 8));
-    if (float_weights) k_mb_tile_mask<float><<<grid, block, 0, s>>>(g, mask, grid.x);
-    else k_mb_tile_mask<short><<<grid, block, 0, s>>>(g, mask, grid.x);
+    if (float_weights) k_mb_tile_mask<float><<<grid, block, 0, s>>>(g, static_cast<const float *>(wsum), wsum_step, mask, grid.x);
+    else k_mb_tile_mask<short><<<grid, block, 0, s>>>(g, static_cast<const short *>(wsum), wsum_step, mask, grid.x);
     SB_LAUNCHED();
     return SB_OK;
 }
@@ -244,6 +254,11 @@ __device__ __forceinline__ void mb_band_thread(const MbBandArgs &a, int X0, int 
     const int lw = FINAL ? a.out_w : a.g.lw, lh = FINAL ? a.out_h : a.g.lh;       // band 0 is cropped to dst_roi_final_
     if (X0 >= lw || Y0 >= lh || X0 + 1 < a.x_begin || X0 >= a.x_end) return;
     uint32_t cams = __ldg(a.tile_mask + (Y0 >> 3) * a.tiles_x + (X0 >> 5));       // the 2x2 block lies inside one 32x8 mask tile
+    // "plain" tile: one camera, weight and weight sum exactly 1.0f everywhere.  Then short(lap * 1.0f) = lap and
+    // normalizeUsingWeightMap's short(lap / (1.0f + 1e-5f)) = lap - sign(lap) (the quotient lies strictly between
+    // |lap| - 1 and |lap| for 1 <= |lap| < 65536): no weight loads, no float arithmetic.
+    const bool plain = sizeof(WT) == 4 && (cams >> 31) != 0u;
+    cams &= 0x7fffffffu;
 
     int acc[2][2][3];
 #pragma unroll
@@ -260,9 +275,10 @@ __device__ __forceinline__ void mb_band_thread(const MbBandArgs &a, int X0, int 
         if (NOT_TOP) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const WT *wr = rowp<WT>(c.weight, c.wstep, y + j) + x;
                 const uint2 gg = __ldg(reinterpret_cast<const uint2 *>(rowp<uint32_t>(c.fine, c.fstep, y + j) + x));
                 g[j][0] = gg.x; g[j][1] = gg.y;
+                if (plain) { w[j][0] = w[j][1] = (WT)1; continue; }
+                const WT *wr = rowp<WT>(c.weight, c.wstep, y + j) + x;
                 w[j][0] = __ldg(wr); w[j][1] = __ldg(wr + 1);
             }
         } else {     // top level: rect corners may be odd, sizes may be odd
@@ -308,6 +324,7 @@ __device__ __forceinline__ void mb_band_thread(const MbBandArgs &a, int X0, int 
                 const int l0 = (int)(g[j][i] & 0xff) - (int)(u02[j][i] & 0xffffu);
                 const int l1 = (int)((g[j][i] >> 8) & 0xff) - (int)u1[j][i];
                 const int l2 = (int)((g[j][i] >> 16) & 0xff) - (int)(u02[j][i] >> 16);
+                if (plain) { acc[j][i][0] = l0; acc[j][i][1] = l1; acc[j][i][2] = l2; continue; }
                 acc[j][i][0] += mb_weighted(l0, w[j][i]); acc[j][i][1] += mb_weighted(l1, w[j][i]); acc[j][i][2] += mb_weighted(l2, w[j][i]);
             }
     }
@@ -346,6 +363,11 @@ __device__ __forceinline__ void mb_band_thread(const MbBandArgs &a, int X0, int 
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const int X = X0 + i;
+            if (plain) {
+                masked[i] = X < lw;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { const int p = acc[j][i][k]; v[i][k] = p - (p > 0) + (p < 0); }
+            } else {
             const WT ws = X < lw ? __ldg(rowp<WT>(a.wsum, a.wsum_step, Y) + X) : (WT)0;
             if (sizeof(WT) == 4) {
                 const float wf = (float)ws;
@@ -358,6 +380,7 @@ __device__ __forceinline__ void mb_band_thread(const MbBandArgs &a, int X0, int 
                 masked[i] = (int)ws > 0;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) v[i][k] = wi ? (short)((((int)(short)acc[j][i][k]) << 8) / wi) : 0;
+            }
             }
             if (NOT_TOP) {   // restoreImageFromLaplacePyr: add(pyrUp(pyr[i+1]), pyr[i]) saturates
 #pragma unroll
