@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstitchb200.so")
+# STITCHB200_LIB: an alternative build of the same library (kernel-shape experiments); never a fallback
+LIB_PATH = os.environ.get("STITCHB200_LIB") or os.path.join(_HERE, "libstitchb200.so")
 
 # OpenCV-numbered constants
 CV_8U, CV_16S, CV_32F = 0, 3, 5

@@ -5,15 +5,17 @@
 // is how the bytes move.  In the one-pixel-per-thread kernel every warp waits for its tile mask, then
 // for its table entries, then for its taps: three dependent DRAM round trips, and the profile is
 // latency-bound (long-scoreboard stalls, < 20 % of HBM bandwidth).  Here
-//   * the panorama is cut into 32x16 tiles; per (tile, camera) the sequence-constant table is stored
-//     TILE-MAJOR as one contiguous 4 KB block, and the bounding box of the source pixels the tile
+//   * the panorama is cut into 32 x SB_FTT_H tiles; per (tile, camera) the sequence-constant table is
+//     stored TILE-MAJOR as one contiguous block, and the bounding box of the source pixels the tile
 //     samples is known per calibration (a 64-byte descriptor per tile);
-//   * each CTA is persistent (one per SM) and walks tiles round-robin; a PRODUCER warp streams, three
-//     tiles ahead, the table blocks (one cp.async.bulk / TMA each, mbarrier complete_tx) and the source
-//     boxes (16-byte cp.async chunks, lanes in parallel, mbarrier arrive.noinc) into a 4-stage ring;
-//   * 16 CONSUMER warps compute pixels purely from shared memory (table entry -> box-relative tap
-//     offset -> aligned LDS + funnel shift -> byte dot products) and hand the stage back through an
-//     "empty" mbarrier.  No thread ever waits on a global load.
+//   * each CTA is persistent and walks tiles round-robin; PRODUCER warps stream, many tiles ahead, the
+//     table blocks (one cp.async.bulk / TMA each, mbarrier complete_tx) and the source boxes (16-byte
+//     cp.async chunks, lanes in parallel, mbarrier arrive.noinc) into a BYTE-GRANULAR shared-memory
+//     ring (a tile takes what its boxes need, ~7 KB per camera instead of a fixed 16 KB slot);
+//   * the CONSUMER warps compute pixels purely from shared memory (table entry -> box-relative word
+//     offset + byte shift -> aligned LDS + funnel shift -> byte dot products against a shared-memory
+//     copy of the bilinear weight table) and hand the stage back through an "empty" mbarrier.
+//     No consumer thread ever waits on a global load.
 #include <algorithm>
 #include <climits>
 
@@ -58,7 +60,7 @@ k_fts_bbox(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int
         uint4 r = make_uint4(0u, 0u, 0u, 0u);                // n_rows == 0: the camera carries no weight in this tile
         if (mxx >= mnx) {
             const unsigned xlo = ((unsigned)mnx * 3u) & ~15u;             // box start, 16-byte aligned
-            const unsigned need_end = (unsigned)(mxx + 1) * 3u + 3u;      // last needed byte + the aligned-word slack of load_6bytes
+            const unsigned need_end = (unsigned)(mxx + 1) * 3u + 3u;      // last needed byte + the aligned-word slack of the 6-byte tap read
             const unsigned pitch = ((need_end + 15u) & ~15u) - xlo;
             unsigned n_rows = (unsigned)(mxy - mny + 1);
             if (n_rows > (unsigned)SB_FTS_MAX_ROWS || n_rows * pitch > (unsigned)SB_FTS_BOX_BYTES) n_rows = SB_FTS_DIRECT;
@@ -69,8 +71,14 @@ k_fts_bbox(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int
 }
 
 // pass 2: tile-major entries, tap position relative to the tile's source box:
-//   x = box byte offset of tap (y0, x0) | (x1 == x0) << 26 | (y1 == y0) << 27     y = fx | fy << 5 | dist << 16
-// (boxes too large for a shared-memory slot: x = x0 | y0 << 13 | flags, the row-major format, taps gathered directly)
+//   x = (box byte offset of tap (y0, x0) & 3) << 3 | (that offset >> 2) << 5 | (y1 == y0) << 27
+//       (low 5 bits = the funnel-shift amount of the aligned-word tap read; box rows are 16-byte pitched, so the
+//        second tap row shares it)
+//   y = (fx | fy << 5) << 3 | dist << 16       (byte offset into the 8-byte bilinear weight table)
+// An x-folded pair (x1 == x0 at the source edge) is stored with fx = 0: the weights of the second column are then
+// zero, sum w*p is the same integer, and the consumer needs no special case (the bytes it multiplies by zero are
+// inside the box pitch).
+// Boxes too large for shared memory: x = x0 | y0 << 13 | flags, the row-major format, taps gathered directly.
 __global__ void __launch_bounds__(256)
 k_fts_entries(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int tx0, int ty0, int ntx, const uint4 *rec, uint2 *tiles)
 {
@@ -85,8 +93,15 @@ k_fts_entries(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, 
             const uint2 s = reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(table) + (size_t)y * tstep)[x];
             if ((s.y >> 16) != 0u) {
                 const unsigned x0 = s.x & 0x1fffu, y0 = (s.x >> 13) & 0x1fffu;
-                t.x = (r.y >> 24) == (unsigned)SB_FTS_DIRECT ? s.x : (((y0 - ylo) * pitch + x0 * 3u - xlo) | (s.x & (3u << 26)));
-                t.y = s.y;
+                unsigned fxy = s.y & 1023u;
+                if ((r.y >> 24) == (unsigned)SB_FTS_DIRECT) {
+                    t.x = s.x;
+                } else {
+                    const unsigned off = (y0 - ylo) * pitch + x0 * 3u - xlo;
+                    t.x = ((off & 3u) << 3) | ((off >> 2) << 5) | (s.x & (1u << 27));
+                    if (s.x & (1u << 26)) fxy &= ~31u;
+                }
+                t.y = (fxy << 3) | (s.y & 0xffff0000u);
             }
         }
         dst[e] = t;
@@ -103,8 +118,11 @@ int launch_fts_camera_tiles(const uint2 *table, size_t tstep, int ww, int wh, in
     return SB_OK;
 }
 
-// pass 3: one 64-byte descriptor per panorama tile: {n_cams, 0, 0, 0} + per camera slot (ascending
-// camera index = feed order) {xlo | ylo << 16, need_end | n_rows << 24, pitch, cam | table block index << 4 | full weight << 31}.
+// pass 3: one 64-byte descriptor per panorama tile:
+//   [0]     = {n_cams | short path << 2 | ring units << 8, tile origin X0 | Y0 << 16, 0, 0}     (ring unit = 128 bytes)
+//   [1 + k] = per camera slot (ascending camera index = feed order)
+//             {xlo | ylo << 16, need_end | n_rows << 24, pitch | ring unit offset inside the tile << 16,
+//              cam | table block index << 4 | full weight << 31}
 // *status: bit 0 = some tile has more than SB_FTT_MAXC cameras, bit 1 = block index overflow.
 __global__ void k_fts_descriptors(FtsSetup a, uint4 *desc, int *status)
 {
@@ -114,6 +132,7 @@ __global__ void k_fts_descriptors(FtsSetup a, uint4 *desc, int *status)
     uint4 out[1 + SB_FTT_MAXC];
     for (int k = 0; k <= SB_FTT_MAXC; ++k) out[k] = make_uint4(0u, 0u, 0u, 0u);
     int k = 0, bad = 0;
+    unsigned units = 0;
     for (int i = 0; i < a.n; ++i) {
         const int rx = tx - a.cam[i].tx0, ry = ty - a.cam[i].ty0;
         if ((unsigned)rx >= (unsigned)a.cam[i].ntx || (unsigned)ry >= (unsigned)a.cam[i].nty) continue;
@@ -123,12 +142,16 @@ __global__ void k_fts_descriptors(FtsSetup a, uint4 *desc, int *status)
         if (n_rows == 0u) continue;
         if (block >= (1u << 27)) bad |= 2;
         if (k == SB_FTT_MAXC) { bad |= 1; break; }
+        const unsigned box_bytes = n_rows == (unsigned)SB_FTS_DIRECT ? 0u : n_rows * r.z;
+        r.z |= units << 16;
+        units += ((unsigned)SB_FTT_TAB_BYTES + box_bytes + 127u) >> 7;
         r.w = (unsigned)i | (block << 4) | (r.w & 0x80000000u);
         out[1 + k++] = r;
     }
-    out[0].x = (unsigned)k;
     // one camera at full weight over the whole tile, box staged in shared memory: the consumers take the short path
-    out[0].z = (k == 1 && (out[1].w >> 31) && (out[1].y >> 24) != (unsigned)SB_FTS_DIRECT) ? 1u : 0u;
+    const unsigned short_path = (k == 1 && (out[1].w >> 31) && (out[1].y >> 24) != (unsigned)SB_FTS_DIRECT) ? 1u : 0u;
+    out[0].x = (unsigned)k | (short_path << 2) | (units << 8);
+    out[0].y = (unsigned)(tx * SB_FTT_W) | ((unsigned)(ty * SB_FTT_H) << 16);
     for (int j = 0; j <= SB_FTT_MAXC; ++j) desc[(size_t)tile * (1 + SB_FTT_MAXC) + j] = out[j];
     if (bad) atomicOr(status, bad);
 }
@@ -141,18 +164,15 @@ int launch_fts_descriptors(const FtsSetup &a, uint4 *desc, int *status, cudaStre
 }
 
 // ------------------------------------------------------------------------------------ frame kernel
-// Shared memory: a ring of SB_FTS_SLOTS camera slots (table block + source box) allocated to tiles in
-// order, as many as the tile has cameras (0..SB_FTT_MAXC; 1.2 on average), and a ring of SB_FTT_STAGES
-// tile entries (descriptor + full/empty barriers).  ~10 tiles are in flight per CTA.
-struct FtsSlot {
-    uint2 tab[SB_FTT_H][SB_FTT_W];                          // 4 KB
-    unsigned char box[SB_FTS_BOX_BYTES];
-};
+// Shared memory: a byte ring (128-byte units) that holds, per (tile, camera) in flight, the table block followed by
+// the source box; a ring of SB_FTT_STAGES tile entries (descriptor + full/empty barriers); the bilinear weight table.
+constexpr int FTS_RING_UNITS = SB_FTS_RING_BYTES / 128;
 struct FtsSmem {
-    FtsSlot slot[SB_FTS_SLOTS];
-    uint4 desc[SB_FTT_STAGES][1 + SB_FTT_MAXC];             // [0] = {n_cams, first slot, 0, 0}
+    unsigned char ring[SB_FTS_RING_BYTES];
+    uint2 lut[1024];                                        // bilin_lut (sb_device.cuh): 8 KB, read once per camera pixel
+    uint4 desc[SB_FTT_STAGES][1 + SB_FTT_MAXC];             // [0] = {n_cams | short << 2, tile origin, ., .}; [1 + k].x = shared address of slot k
     uint64_t full[SB_FTT_STAGES], empty[SB_FTT_STAGES];
-    int nc_hist[SB_FTS_PRODUCER_WARPS][SB_FTT_STAGES];      // per producer warp: cameras of its tiles in flight
+    int start_hist[SB_FTS_PRODUCER_WARPS][SB_FTT_STAGES];   // per producer warp: ring start unit of the tiles in flight
 };
 
 // exposure gain of camera `c` at panorama pixel (X, Y): the scalar of GainCompensator or the resized block map
@@ -161,17 +181,59 @@ __device__ __forceinline__ float fts_gain(const FeatherTmaCam &c, int X, int Y)
     return c.gmap ? __ldg(reinterpret_cast<const float *>(reinterpret_cast<const char *>(c.gmap) + (size_t)(Y - c.dy) * c.gmstep) + (X - c.dx)) : c.gain;
 }
 
-// lo = bytes 0..3, hi = bytes 4..7 of the 6 tap bytes at shared-memory byte address `a`
-__device__ __forceinline__ void lds_6bytes(uint32_t a, unsigned &lo, unsigned &hi)
+__device__ __forceinline__ uint2 lds_u2(uint32_t a)
 {
-    const unsigned o = a & 3u;
-    const uint32_t b = a - o;
-    unsigned w0, w1, w2;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(b));
-    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(b));
-    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(b));
-    lo = __funnelshift_r(w0, w1, o * 8);
-    hi = __funnelshift_r(w1, w2, o * 8);
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+// The two tap rows of one boxed table entry: lo = bytes 0..3, hi = bytes 4..7 of the 6 tap bytes of each row.
+// tex = byte shift (bits 0-4) | word offset in the box (bits 5-20) | (y1 == y0) << 27
+__device__ __forceinline__ void fts_taps(uint32_t box, unsigned pitch, unsigned tex, unsigned &lo0, unsigned &hi0, unsigned &lo1, unsigned &hi1)
+{
+    const uint32_t r0 = box + ((tex >> 3) & 0x3fffcu);
+    const uint32_t r1 = (tex & (1u << 27)) ? r0 : r0 + pitch;
+    unsigned a0, a1, a2, b0, b1, b2;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a0) : "r"(r0));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(a1) : "r"(r0));
+    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(a2) : "r"(r0));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(b0) : "r"(r1));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(b1) : "r"(r1));
+    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(b2) : "r"(r1));
+    lo0 = __funnelshift_r(a0, a1, tex); hi0 = __funnelshift_r(a1, a2, tex);      // (shift amount = tex mod 32)
+    lo1 = __funnelshift_r(b0, b1, tex); hi1 = __funnelshift_r(b1, b2, tex);
+}
+// the taps of a row-major entry (box too large for shared memory), gathered from global memory
+__device__ __forceinline__ void fts_taps_direct(const FeatherTmaCam &c, unsigned tex, unsigned &lo0, unsigned &hi0, unsigned &lo1, unsigned &hi1)
+{
+    const unsigned x0 = tex & 0x1fffu, y0 = (tex >> 13) & 0x1fffu;
+    const uint8_t *g0 = c.src + (size_t)(y0 * c.sstep);
+    const uint8_t *g1 = (tex & (1u << 27)) ? g0 : g0 + c.sstep;
+    const unsigned x1 = x0 + 1u - ((tex >> 26) & 1u);
+    load_tap_row(g0, x0, x1, lo0, hi0);
+    load_tap_row(g1, x0, x1, lo1, hi1);
+}
+// bilinear_rgb (sb_device.cuh); MINUS1: max(v - 1, 0) instead of v, folded into the rounding bias:
+// v = (s + 512) >> 10 with s >= 0, so max(v - 1, 0) = max(s - 512, 0) >> 10.
+template <bool MINUS1>
+__device__ __forceinline__ void fts_bilinear(unsigned lo0, unsigned hi0, unsigned lo1, unsigned hi1, uint2 w, int &v0, int &v1, int &v2)
+{
+    if (!MINUS1) { bilinear_rgb(lo0, hi0, lo1, hi1, w, v0, v1, v2); return; }
+    const unsigned m0 = __byte_perm(lo0, hi0, 0x5241), m1 = __byte_perm(lo1, hi1, 0x5241);
+    const unsigned p0 = __byte_perm(lo0, lo1, 0x7430), p1 = __byte_perm(m0, m1, 0x5410), p2 = __byte_perm(m0, m1, 0x7632);
+    v0 = max((int)(__dp4a(p0, w.x, 0u) * 8u + __dp4a(p0, w.y, 0xfffffe00u)), 0) >> 10;
+    v1 = max((int)(__dp4a(p1, w.x, 0u) * 8u + __dp4a(p1, w.y, 0xfffffe00u)), 0) >> 10;
+    v2 = max((int)(__dp4a(p2, w.x, 0u) * 8u + __dp4a(p2, w.y, 0xfffffe00u)), 0) >> 10;
+}
+template <bool OUT8>
+__device__ __forceinline__ void fts_store(unsigned char *o, int v0, int v1, int v2)
+{
+    if (OUT8) {
+        o[0] = (uint8_t)v0; o[1] = (uint8_t)v1; o[2] = (uint8_t)v2;
+    } else {
+        short *q = reinterpret_cast<short *>(o);
+        q[0] = (short)v0; q[1] = (short)v1; q[2] = (short)v2;
+    }
 }
 
 // NOBLEND: Blender::feed / blend without blending (blenders.cpp:81-112): the pixel of the LAST camera (feed order)
@@ -191,143 +253,159 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
         }
         mbar_fence_init();
     }
+    for (int i = tid; i < 1024; i += SB_FTS_THREADS) sm.lut[i] = __ldg(a.bilin_lut + i);
     __syncthreads();
 
     if (warp >= SB_FTS_CONSUMER_WARPS) {
         // ------------------------------------------------ producer warps
-        const int pw = warp - SB_FTS_CONSUMER_WARPS;
         // Tile seq (0, 1, 2 ... of this CTA) is fetched by producer warp seq % PRODUCER_WARPS, so the per-tile issue
-        // latency (descriptor shuffles, barrier ops, address arithmetic: ~1.4 us of dependent instructions) overlaps
-        // across warps.  Every warp tracks the slot ring for ALL tiles (it only needs each tile's camera count).
-        int stage = 0, head = 0, used = 0;                  // tile entry of this tile; next free slot; slots held by tiles in flight
+        // latency (descriptor shuffles, barrier ops, address arithmetic) overlaps across warps.  Every warp replays the
+        // ring allocation for ALL tiles (it only needs each tile's size, one word fetched a tile ahead): a tile takes
+        // `units` contiguous 128-byte units at the head, wrapping to 0 when the end of the ring is too short; tiles
+        // retire in order, which moves the tail to the start of the oldest tile still in flight.
+        const int pw = warp - SB_FTS_CONSUMER_WARPS;
+        int stage = 0, head = 0, tail = 0;
         int seq = 0, oldest = 0;                            // tiles issued / retired by this CTA
         const uint4 *dbase = a.desc;
-        unsigned nc_next = __ldg(&dbase[(size_t)blockIdx.x * (1 + SB_FTT_MAXC)].x);   // camera count, one tile ahead
+        const uint32_t ring0 = smem_u32(&sm.ring[0]);
+        unsigned w_next = __ldg(&dbase[(size_t)blockIdx.x * (1 + SB_FTT_MAXC)].x);   // n_cams | .. | units << 8, one tile ahead
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += G, ++seq) {
-            const int nc = (int)nc_next;
-            if (tile + G < a.n_tiles) nc_next = __ldg(&dbase[(size_t)(tile + G) * (1 + SB_FTT_MAXC)].x);
+            const unsigned w0 = w_next;
+            if (tile + G < a.n_tiles) w_next = __ldg(&dbase[(size_t)(tile + G) * (1 + SB_FTT_MAXC)].x);
+            const int nc = (int)(w0 & 3u), units = (int)(w0 >> 8);
             const bool mine = seq % SB_FTS_PRODUCER_WARPS == pw;
             uint4 d = make_uint4(0u, 0u, 0u, 0u);
             if (mine && lane <= SB_FTT_MAXC) d = __ldg(dbase + (size_t)tile * (1 + SB_FTT_MAXC) + lane);
-            // retire the oldest tiles until a tile entry and nc slots are free (tiles complete in order)
-            while (seq - oldest >= SB_FTT_STAGES || used + nc > SB_FTS_SLOTS) {
+            int start;
+            for (;;) {
+                if (seq - oldest < SB_FTT_STAGES) {
+                    if (seq == oldest) head = tail = 0;     // nothing in flight
+                    if (head >= tail) {                     // in use: [tail, head)
+                        if (head + units <= FTS_RING_UNITS) { start = head; break; }
+                        if (units < tail) { start = 0; break; }
+                    } else if (head + units < tail) {       // in use: [tail, end) and [0, head)
+                        start = head; break;
+                    }
+                }
                 const int e = oldest % SB_FTT_STAGES;
-                mbar_wait(&sm.empty[e], (unsigned)(oldest / SB_FTT_STAGES) & 1u);   // every consumer warp is done with it
-                used -= sm.nc_hist[pw][e];
+                mbar_wait(&sm.empty[e], (unsigned)(oldest / SB_FTT_STAGES) & 1u);   // every consumer warp is done with the oldest tile
                 ++oldest;
+                tail = oldest < seq ? sm.start_hist[pw][oldest % SB_FTT_STAGES] : head;
             }
-            sm.nc_hist[pw][stage] = nc;                     // (every lane stores the same value)
+            head = start + units;
+            sm.start_hist[pw][stage] = start;               // (every lane stores the same value)
             if (mine) {
-                if (lane == 0) d.y = (unsigned)head;
-                if (lane <= SB_FTT_MAXC) sm.desc[stage][lane] = d;
+                const uint32_t tile_base = ring0 + (uint32_t)start * 128u;
+                uint4 ds = d;
+                if (lane != 0) ds.x = tile_base + ((d.z >> 16) << 7);
+                if (lane <= SB_FTT_MAXC) sm.desc[stage][lane] = ds;
+                __syncwarp();
                 // table blocks: one bulk copy (TMA) per camera slot, completion by expect_tx
                 if (lane == 0) {
                     if (nc == 0) mbar_arrive(&sm.full[stage]);
-                    else mbar_arrive_expect_tx(&sm.full[stage], (unsigned)nc * (unsigned)(SB_FTT_W * SB_FTT_H * sizeof(uint2)));
+                    else mbar_arrive_expect_tx(&sm.full[stage], (unsigned)nc * (unsigned)SB_FTT_TAB_BYTES);
                 }
                 __syncwarp();
                 for (int k = 0; k < nc; ++k) {
                     const unsigned dx_ = __shfl_sync(0xffffffffu, d.x, k + 1), dy_ = __shfl_sync(0xffffffffu, d.y, k + 1);
-                    const unsigned dw_ = __shfl_sync(0xffffffffu, d.w, k + 1), pitch = __shfl_sync(0xffffffffu, d.z, k + 1);
+                    const unsigned dw_ = __shfl_sync(0xffffffffu, d.w, k + 1), dz_ = __shfl_sync(0xffffffffu, d.z, k + 1);
                     const FeatherTmaCam &c = a.cam[dw_ & 15u];
-                    const int slot = head + k < SB_FTS_SLOTS ? head + k : head + k - SB_FTS_SLOTS;
+                    const uint32_t slot = tile_base + ((dz_ >> 16) << 7);
+                    const unsigned pitch = dz_ & 0xffffu;
                     if (lane == 0)
-                        bulk_g2s(&sm.slot[slot].tab[0][0], c.tiles + (size_t)((dw_ >> 4) & 0x7ffffffu) * (SB_FTT_W * SB_FTT_H),
-                                 SB_FTT_W * SB_FTT_H * sizeof(uint2), &sm.full[stage]);
+                        bulk_g2s_addr(slot, c.tiles + (size_t)((dw_ >> 4) & 0x7ffffffu) * (SB_FTT_W * SB_FTT_H), SB_FTT_TAB_BYTES, &sm.full[stage]);
                     unsigned n_rows = dy_ >> 24;
                     if (n_rows == (unsigned)SB_FTS_DIRECT) n_rows = 0u;
                     // source box: 16-byte cp.async chunks, all lanes (row length clamped to the pitch of the source image)
                     const unsigned xlo = dx_ & 0xffffu, ylo = dx_ >> 16, need_end = dy_ & 0xffffffu;
                     const unsigned cpr = (min((need_end + 15u) & ~15u, c.sstep) - xlo) >> 4;       // chunks per row
-                    const float inv = __frcp_rn((float)cpr);
-                    const unsigned n_chunks = n_rows * cpr;
-                    const uint32_t box = smem_u32(&sm.slot[slot].box[0]);
+                    const uint32_t box = slot + (uint32_t)SB_FTT_TAB_BYTES;
                     const uint8_t *g = c.src + (size_t)ylo * c.sstep + xlo;
-                    for (unsigned ch = lane; ch < n_chunks; ch += 32u) {
-                        unsigned r = (unsigned)__float2int_rz(__fmul_rn((float)ch + 0.5f, inv));    // ch / cpr for ch < 1024 ...
-                        if (r * cpr > ch) --r;                                                      // ... made exact
-                        else if ((r + 1u) * cpr <= ch) ++r;
-                        const unsigned col = ch - r * cpr;
-                        cp_async_16(box + r * pitch + col * 16u, g + (size_t)r * c.sstep + col * 16u);
+                    if (cpr <= 32u) {
+                        // lanes = (32 / cw rows) x (cw chunk columns), cw = the power of two >= cpr
+                        const unsigned sh = cpr > 1u ? 32u - (unsigned)__clz((int)(cpr - 1u)) : 0u;
+                        const unsigned col = (unsigned)lane & ((1u << sh) - 1u), rstep = 32u >> sh;
+                        unsigned r = (unsigned)lane >> sh;
+                        uint32_t dst = box + r * pitch + col * 16u;
+                        const uint8_t *src = g + (size_t)r * c.sstep + col * 16u;
+                        if (col < cpr)
+                            for (; r < n_rows; r += rstep, dst += rstep * pitch, src += (size_t)rstep * c.sstep) cp_async_16(dst, src);
+                    } else {
+                        const float inv = __frcp_rn((float)cpr);
+                        const unsigned n_chunks = n_rows * cpr;
+                        for (unsigned ch = lane; ch < n_chunks; ch += 32u) {
+                            unsigned r = (unsigned)__float2int_rz(__fmul_rn((float)ch + 0.5f, inv));    // ch / cpr for ch < 1024 ...
+                            if (r * cpr > ch) --r;                                                      // ... made exact
+                            else if ((r + 1u) * cpr <= ch) ++r;
+                            const unsigned col = ch - r * cpr;
+                            cp_async_16(box + r * pitch + col * 16u, g + (size_t)r * c.sstep + col * 16u);
+                        }
                     }
                 }
                 cp_async_mbar_arrive_noinc(&sm.full[stage]);    // one arrival per lane when its chunks have landed
             }
-            head = head + nc < SB_FTS_SLOTS ? head + nc : head + nc - SB_FTS_SLOTS;
-            used += nc;
             if (++stage == SB_FTT_STAGES) stage = 0;
         }
         return;
     }
 
     // ---------------------------------------------------- consumer warps
-    // warp w covers columns (w % SEGS) * 32 .. +31 of tile rows (w / SEGS) + RPP * p, p = 0 .. PX-1
-    constexpr int SEGS = SB_FTT_W / 32, RPP = SB_FTS_CONSUMER_WARPS / SEGS, PX = SB_FTT_H / RPP;
-    const int lx = (warp % SEGS) * 32 + lane, ly = warp / SEGS;
-    const int gx = G % a.tiles_x, gy = G / a.tiles_x;       // tile -> (tx, ty) advanced incrementally
-    int tx = blockIdx.x % a.tiles_x, ty = blockIdx.x / a.tiles_x;
+    // warp w covers the 32 columns of tile rows w + RPP * p, p = 0 .. PX-1
+    constexpr int RPP = SB_FTS_CONSUMER_WARPS, PX = SB_FTT_H / RPP;
+    static_assert(SB_FTT_W == 32 && SB_FTT_H % RPP == 0, "one warp per tile row");
+    constexpr uint32_t ROW_STRIDE = (uint32_t)RPP * SB_FTT_W * 8u;        // table bytes between a thread's pixels
+    const int lx = lane, ly = warp;
+    const uint32_t lut0 = smem_u32(&sm.lut[0]);
+    const uint32_t tab_off = (uint32_t)(ly * SB_FTT_W + lx) * 8u;
+    const unsigned ostep = (unsigned)a.out_step, mstep = (unsigned)a.mask_step;      // (the launcher checks the panorama is < 4 GB)
     int stage = 0;
     unsigned parity = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += G) {
         mbar_wait(&sm.full[stage], parity);
-        const int nc = (int)sm.desc[stage][0].x, first = (int)sm.desc[stage][0].y;
-        const int X = tx * SB_FTT_W + lx, Y0 = ty * SB_FTT_H + ly;
-        if (sm.desc[stage][0].z) {
+        const uint4 d0 = sm.desc[stage][0];
+        const int nc = (int)(d0.x & 3u);
+        const int X = (int)(d0.y & 0xffffu) + lx, Y0 = (int)(d0.y >> 16) + ly;
+        unsigned char *orow = reinterpret_cast<unsigned char *>(a.out) + ((unsigned)Y0 * ostep + (unsigned)X * (OUT8 ? 3u : 6u));
+        uint8_t *mrow_ = a.out_mask ? a.out_mask + ((unsigned)Y0 * mstep + (unsigned)X) : nullptr;
+        if (d0.x & 4u) {
             // Short path (block-uniform; ~80 % of a ring panorama): ONE camera with weight exactly 1.0f on every pixel
             // of the tile.  Then dst = short(p * 1.0f) = p, dst_w = 1.0f, and normalizeUsingWeightMap gives
             // short(p / (1.0f + 1e-5f)) = p - 1 for p in 1..255 and 0 for p = 0 (the quotient lies strictly between
             // p - 1 and p); the mask is 255.  No float op is needed at all.
             const uint4 rec = sm.desc[stage][1];
-            const unsigned pitch = rec.z;
-            const FtsSlot &sl = sm.slot[first];
-            const uint32_t box = smem_u32(&sl.box[0]);
+            const unsigned pitch = rec.z & 0xffffu;
+            const uint32_t tab = rec.x + tab_off, box = rec.x + (uint32_t)SB_FTT_TAB_BYTES;
             int v[PX][3];
 #pragma unroll
             for (int p = 0; p < PX; ++p) {
-                const uint2 te = sl.tab[ly + RPP * p][lx];
-                const uint2 bw = __ldg(a.bilin_lut + (te.y & 1023u));
-                const uint32_t r0 = box + (te.x & 0x3ffffu);
-                const uint32_t r1 = (te.x & (1u << 27)) ? r0 : r0 + pitch;
+                const uint2 te = lds_u2(tab + (uint32_t)p * ROW_STRIDE);
+                const uint2 bw = lds_u2(lut0 + (te.y & 0x1ff8u));
                 unsigned lo0, hi0, lo1, hi1;
-                lds_6bytes(r0, lo0, hi0);
-                lds_6bytes(r1, lo1, hi1);
-                if (te.x & (1u << 26)) {                    // x1 == x0 at the image edge: repeat the pixel
-                    hi0 = lo0 >> 8; lo0 = (lo0 & 0x00ffffffu) | (lo0 << 24);
-                    hi1 = lo1 >> 8; lo1 = (lo1 & 0x00ffffffu) | (lo1 << 24);
-                }
-                bilinear_rgb(lo0, hi0, lo1, hi1, bw, v[p][0], v[p][1], v[p][2]);
+                fts_taps(box, pitch, te.x, lo0, hi0, lo1, hi1);
+                fts_bilinear<!GAIN && !NOBLEND>(lo0, hi0, lo1, hi1, bw, v[p][0], v[p][1], v[p][2]);
                 if (GAIN) {                                 // saturate_cast<uchar>(p * gain)
                     const float g = fts_gain(a.cam[rec.w & 15u], X, Y0 + RPP * p);
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) v[p][k] = min(max(__float2int_rn(__fmul_rn((float)v[p][k], g)), 0), 255);
+                    for (int k = 0; k < 3; ++k) {
+                        v[p][k] = min(max(__float2int_rn(__fmul_rn((float)v[p][k], g)), 0), 255);
+                        if (!NOBLEND) v[p][k] -= min(v[p][k], 1);
+                    }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty[stage]);
-            unsigned char *orow = reinterpret_cast<unsigned char *>(a.out) + (size_t)Y0 * a.out_step + (size_t)X * (OUT8 ? 3 : 6);
-            uint8_t *mrow_ = a.out_mask ? a.out_mask + (size_t)Y0 * a.mask_step + X : nullptr;
 #pragma unroll
             for (int p = 0; p < PX; ++p) {
-                const int o0 = NOBLEND ? v[p][0] : v[p][0] - min(v[p][0], 1), o1 = NOBLEND ? v[p][1] : v[p][1] - min(v[p][1], 1),
-                          o2 = NOBLEND ? v[p][2] : v[p][2] - min(v[p][2], 1);
-                if (OUT8) {
-                    orow[0] = (uint8_t)o0; orow[1] = (uint8_t)o1; orow[2] = (uint8_t)o2;
-                } else {
-                    short *o = reinterpret_cast<short *>(orow);
-                    o[0] = (short)o0; o[1] = (short)o1; o[2] = (short)o2;
-                }
-                if (mrow_) { *mrow_ = 255; mrow_ += RPP * a.mask_step; }
-                orow += RPP * a.out_step;
+                fts_store<OUT8>(orow, v[p][0], v[p][1], v[p][2]);
+                if (mrow_) { *mrow_ = 255; mrow_ += RPP * mstep; }
+                orow += RPP * ostep;
             }
-            tx += gx; ty += gy;
-            if (tx >= a.tiles_x) { tx -= a.tiles_x; ++ty; }
             if (++stage == SB_FTT_STAGES) { stage = 0; parity ^= 1u; }
             continue;
         }
         int acc[PX][3];
-        float wsum[PX];
 #pragma unroll
-        for (int p = 0; p < PX; ++p) { acc[p][0] = acc[p][1] = acc[p][2] = 0; wsum[p] = 0.f; }
+        for (int p = 0; p < PX; ++p) acc[p][0] = acc[p][1] = acc[p][2] = 0;
         if (NOBLEND) {
             // which camera slot supplies each pixel (the last one in feed order with a non-zero mask), OR of the masks
             int sel[PX];
@@ -335,10 +413,10 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
 #pragma unroll
             for (int p = 0; p < PX; ++p) { sel[p] = -1; mor[p] = 0u; }
             for (int k = 0; k < nc; ++k) {
-                const FtsSlot &sl = sm.slot[first + k < SB_FTS_SLOTS ? first + k : first + k - SB_FTS_SLOTS];
+                const uint32_t tab = sm.desc[stage][1 + k].x + tab_off;
 #pragma unroll
                 for (int p = 0; p < PX; ++p) {
-                    const unsigned m = sl.tab[ly + RPP * p][lx].y >> 16;
+                    const unsigned m = lds_u2(tab + (uint32_t)p * ROW_STRIDE).y >> 16;
                     mor[p] |= m;
                     if (m) sel[p] = k;
                 }
@@ -347,28 +425,11 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
             for (int p = 0; p < PX; ++p) {
                 if (sel[p] < 0) continue;
                 const uint4 rec = sm.desc[stage][1 + sel[p]];
-                const FtsSlot &sl = sm.slot[first + sel[p] < SB_FTS_SLOTS ? first + sel[p] : first + sel[p] - SB_FTS_SLOTS];
-                const uint2 te = sl.tab[ly + RPP * p][lx];
-                const uint2 bw = __ldg(a.bilin_lut + (te.y & 1023u));
+                const uint2 te = lds_u2(rec.x + tab_off + (uint32_t)p * ROW_STRIDE);
+                const uint2 bw = lds_u2(lut0 + (te.y & 0x1ff8u));
                 unsigned lo0, hi0, lo1, hi1;
-                if ((rec.y >> 24) != (unsigned)SB_FTS_DIRECT) {
-                    const uint32_t r0 = smem_u32(&sl.box[0]) + (te.x & 0x3ffffu);
-                    const uint32_t r1 = (te.x & (1u << 27)) ? r0 : r0 + rec.z;
-                    lds_6bytes(r0, lo0, hi0);
-                    lds_6bytes(r1, lo1, hi1);
-                    if (te.x & (1u << 26)) {
-                        hi0 = lo0 >> 8; lo0 = (lo0 & 0x00ffffffu) | (lo0 << 24);
-                        hi1 = lo1 >> 8; lo1 = (lo1 & 0x00ffffffu) | (lo1 << 24);
-                    }
-                } else {
-                    const FeatherTmaCam &c = a.cam[rec.w & 15u];
-                    const unsigned x0 = te.x & 0x1fffu, y0 = (te.x >> 13) & 0x1fffu;
-                    const uint8_t *g0 = c.src + (size_t)(y0 * c.sstep);
-                    const uint8_t *g1 = (te.x & (1u << 27)) ? g0 : g0 + c.sstep;
-                    const unsigned x1 = x0 + 1u - ((te.x >> 26) & 1u);
-                    load_tap_row(g0, x0, x1, lo0, hi0);
-                    load_tap_row(g1, x0, x1, lo1, hi1);
-                }
+                if ((rec.y >> 24) != (unsigned)SB_FTS_DIRECT) fts_taps(rec.x + (uint32_t)SB_FTT_TAB_BYTES, rec.z & 0xffffu, te.x, lo0, hi0, lo1, hi1);
+                else fts_taps_direct(a.cam[rec.w & 15u], te.x, lo0, hi0, lo1, hi1);
                 bilinear_rgb(lo0, hi0, lo1, hi1, bw, acc[p][0], acc[p][1], acc[p][2]);
                 if (GAIN) {
                     const float g = fts_gain(a.cam[rec.w & 15u], X, Y0 + RPP * p);
@@ -379,58 +440,36 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty[stage]);
             if (X < a.pw) {
-                unsigned char *orow = reinterpret_cast<unsigned char *>(a.out) + (size_t)Y0 * a.out_step + (size_t)X * (OUT8 ? 3 : 6);
-                uint8_t *mrow_ = a.out_mask ? a.out_mask + (size_t)Y0 * a.mask_step + X : nullptr;
 #pragma unroll
                 for (int p = 0; p < PX; ++p) {
                     if (Y0 + RPP * p >= a.ph) break;
-                    if (OUT8) {
-                        orow[0] = (uint8_t)acc[p][0]; orow[1] = (uint8_t)acc[p][1]; orow[2] = (uint8_t)acc[p][2];
-                    } else {
-                        short *o = reinterpret_cast<short *>(orow);
-                        o[0] = (short)acc[p][0]; o[1] = (short)acc[p][1]; o[2] = (short)acc[p][2];
-                    }
-                    if (mrow_) { *mrow_ = (uint8_t)mor[p]; mrow_ += RPP * a.mask_step; }
-                    orow += RPP * a.out_step;
+                    fts_store<OUT8>(orow, acc[p][0], acc[p][1], acc[p][2]);
+                    if (mrow_) { *mrow_ = (uint8_t)mor[p]; mrow_ += RPP * mstep; }
+                    orow += RPP * ostep;
                 }
             }
-            tx += gx; ty += gy;
-            if (tx >= a.tiles_x) { tx -= a.tiles_x; ++ty; }
             if (++stage == SB_FTT_STAGES) { stage = 0; parity ^= 1u; }
             continue;
         }
+        float wsum[PX];
+#pragma unroll
+        for (int p = 0; p < PX; ++p) wsum[p] = 0.f;
         for (int k = 0; k < nc; ++k) {                      // ascending camera index = feed order (float weight sums)
             const uint4 rec = sm.desc[stage][1 + k];
-            const unsigned pitch = rec.z;
+            const unsigned pitch = rec.z & 0xffffu;
             const bool direct = (rec.y >> 24) == (unsigned)SB_FTS_DIRECT;    // block-uniform
-            const FtsSlot &sl = sm.slot[first + k < SB_FTS_SLOTS ? first + k : first + k - SB_FTS_SLOTS];
-            const uint32_t box = smem_u32(&sl.box[0]);
+            const uint32_t tab = rec.x + tab_off, box = rec.x + (uint32_t)SB_FTT_TAB_BYTES;
             uint2 te[PX], bw[PX];
             unsigned lo0[PX], hi0[PX], lo1[PX], hi1[PX];
 #pragma unroll
             for (int p = 0; p < PX; ++p) {
-                te[p] = sl.tab[ly + RPP * p][lx];
-                bw[p] = __ldg(a.bilin_lut + (te[p].y & 1023u));
+                te[p] = lds_u2(tab + (uint32_t)p * ROW_STRIDE);
+                bw[p] = lds_u2(lut0 + (te[p].y & 0x1ff8u));
                 if (!direct) {
-                    const uint32_t r0 = box + (te[p].x & 0x3ffffu);
-                    const uint32_t r1 = (te[p].x & (1u << 27)) ? r0 : r0 + pitch;
-                    lds_6bytes(r0, lo0[p], hi0[p]);
-                    lds_6bytes(r1, lo1[p], hi1[p]);
-                    if (te[p].x & (1u << 26)) {             // x1 == x0 at the image edge: repeat the pixel
-                        hi0[p] = lo0[p] >> 8; lo0[p] = (lo0[p] & 0x00ffffffu) | (lo0[p] << 24);
-                        hi1[p] = lo1[p] >> 8; lo1[p] = (lo1[p] & 0x00ffffffu) | (lo1[p] << 24);
-                    }
-                } else {                                    // box too large for the slot: gather from global memory
+                    fts_taps(box, pitch, te[p].x, lo0[p], hi0[p], lo1[p], hi1[p]);
+                } else {                                    // box too large for the ring: gather from global memory
                     lo0[p] = hi0[p] = lo1[p] = hi1[p] = 0u;
-                    if ((te[p].y >> 16) != 0u) {
-                        const FeatherTmaCam &c = a.cam[rec.w & 15u];
-                        const unsigned x0 = te[p].x & 0x1fffu, y0 = (te[p].x >> 13) & 0x1fffu;
-                        const uint8_t *g0 = c.src + (size_t)(y0 * c.sstep);
-                        const uint8_t *g1 = (te[p].x & (1u << 27)) ? g0 : g0 + c.sstep;
-                        const unsigned x1 = x0 + 1u - ((te[p].x >> 26) & 1u);
-                        load_tap_row(g0, x0, x1, lo0[p], hi0[p]);
-                        load_tap_row(g1, x0, x1, lo1[p], hi1[p]);
-                    }
+                    if ((te[p].y >> 16) != 0u) fts_taps_direct(a.cam[rec.w & 15u], te[p].x, lo0[p], hi0[p], lo1[p], hi1[p]);
                 }
             }
 #pragma unroll
@@ -455,8 +494,6 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
         if (lane == 0) mbar_arrive(&sm.empty[stage]);       // this warp no longer reads the stage
         // FeatherBlender::blend: normalizeUsingWeightMap, mask = weight > eps, zero unmasked, convertTo(8U)
         if (X < a.pw) {
-            unsigned char *orow = reinterpret_cast<unsigned char *>(a.out) + (size_t)Y0 * a.out_step + (size_t)X * (OUT8 ? 3 : 6);
-            uint8_t *mrow_ = a.out_mask ? a.out_mask + (size_t)Y0 * a.mask_step + X : nullptr;
 #pragma unroll
             for (int p = 0; p < PX; ++p) {
                 if (Y0 + RPP * p >= a.ph) break;
@@ -464,18 +501,11 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
                 const SharedDiv div(__fadd_rn(wsum[p], SB_WEIGHT_EPS));            // in [1e-5, n + 1e-5]: fast-path range
                 const int o0 = m ? __float2int_rz(div((float)acc[p][0])) : 0, o1 = m ? __float2int_rz(div((float)acc[p][1])) : 0,
                           o2 = m ? __float2int_rz(div((float)acc[p][2])) : 0;
-                if (OUT8) {
-                    orow[0] = (uint8_t)o0; orow[1] = (uint8_t)o1; orow[2] = (uint8_t)o2;
-                } else {
-                    short *o = reinterpret_cast<short *>(orow);
-                    o[0] = (short)o0; o[1] = (short)o1; o[2] = (short)o2;
-                }
-                if (mrow_) { *mrow_ = (uint8_t)m; mrow_ += RPP * a.mask_step; }
-                orow += RPP * a.out_step;
+                fts_store<OUT8>(orow, o0, o1, o2);
+                if (mrow_) { *mrow_ = (uint8_t)m; mrow_ += RPP * mstep; }
+                orow += RPP * ostep;
             }
         }
-        tx += gx; ty += gy;
-        if (tx >= a.tiles_x) { tx -= a.tiles_x; ++ty; }
         if (++stage == SB_FTT_STAGES) { stage = 0; parity ^= 1u; }
     }
 }
@@ -483,6 +513,7 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
 int launch_feather_stream(const FeatherTmaArgs &a, bool apply_gain, bool out8, int sm_count, cudaStream_t s)
 {
     SB_ASSERT(a.sharpness > 0.f && a.bilin_lut && a.desc && a.n_tiles > 0 && a.n <= 16);
+    SB_ASSERT(a.pw < 65536 && a.ph < 65536 && (unsigned long long)a.ph * a.out_step < (1ull << 32) && (unsigned long long)a.ph * a.mask_step < (1ull << 32));
     const size_t smem = sizeof(FtsSmem);
     static bool configured_dev[64][8] = {};                  // the attribute is per device (context)
     int dev = 0;

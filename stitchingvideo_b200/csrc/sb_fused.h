@@ -41,16 +41,34 @@ struct FeatherFusedArgs {
 };
 
 // ---- persistent, warp-specialised streaming feather kernel (kernels_feather_tma.cu) ----
-constexpr int SB_FTT_W = 32, SB_FTT_H = 16;      // panorama tile: one contiguous 4 KB table block per camera
+// Shape knobs (compile-time; -DSB_CFG_* builds the variants scratch/feather_variants.sh times against each other)
+#ifndef SB_CFG_FTT_H
+#define SB_CFG_FTT_H 32
+#endif
+#ifndef SB_CFG_FTS_CONSUMER_WARPS
+#define SB_CFG_FTS_CONSUMER_WARPS 16
+#endif
+#ifndef SB_CFG_FTS_PRODUCER_WARPS
+#define SB_CFG_FTS_PRODUCER_WARPS 4
+#endif
+#ifndef SB_CFG_FTS_CTAS_PER_SM
+#define SB_CFG_FTS_CTAS_PER_SM 2
+#endif
+#ifndef SB_CFG_FTS_RING_KB
+#define SB_CFG_FTS_RING_KB 100
+#endif
+constexpr int SB_FTT_W = 32, SB_FTT_H = SB_CFG_FTT_H;   // panorama tile: one contiguous table block (8 B per pixel) per camera
+constexpr int SB_FTT_TAB_BYTES = SB_FTT_W * SB_FTT_H * 8;
 constexpr int SB_FTT_MAXC = 3;                   // cameras with weight inside one tile (more -> k_feather_fused_px1)
-constexpr int SB_FTT_STAGES = 8;                 // tile entries (descriptor + barriers) in flight per CTA
-constexpr int SB_FTS_SLOTS = 6;                  // shared-memory ring of camera slots (16 KB each)
-constexpr int SB_FTS_BOX_BYTES = 12288;          // shared-memory slot for one (tile, camera) source box; larger boxes are gathered directly
-constexpr int SB_FTS_MAX_ROWS = 64;              // box rows copied by the producer warp (2 per lane)
+constexpr int SB_FTT_STAGES = 16;                // tile entries (descriptor + barriers) in flight per CTA
+constexpr int SB_FTS_RING_BYTES = SB_CFG_FTS_RING_KB * 1024;   // shared-memory ring: per (tile, camera) table block + source box, byte-granular
+constexpr int SB_FTS_BOX_BYTES = 12288;          // largest source box staged in shared memory; larger boxes are gathered directly
+constexpr int SB_FTS_MAX_ROWS = 96;              // box rows (< SB_FTS_DIRECT)
 constexpr int SB_FTS_DIRECT = 0xff;              // n_rows marker: no box, taps come from global memory
-constexpr int SB_FTS_CONSUMER_WARPS = 16;        // 512 pixel threads
-constexpr int SB_FTS_PRODUCER_WARPS = 4;         // all walk the tile sequence; warp w fetches tiles w, w + 4, ...
-constexpr int SB_FTS_CTAS_PER_SM = 2;
+constexpr int SB_FTS_CONSUMER_WARPS = SB_CFG_FTS_CONSUMER_WARPS;   // pixel threads = 32 x this
+constexpr int SB_FTS_PRODUCER_WARPS = SB_CFG_FTS_PRODUCER_WARPS;   // all walk the tile sequence; warp w fetches tiles w, w + P, ...
+constexpr int SB_FTS_CTAS_PER_SM = SB_CFG_FTS_CTAS_PER_SM;
+static_assert(SB_FTT_MAXC * (SB_FTT_TAB_BYTES + SB_FTS_BOX_BYTES) <= SB_FTS_RING_BYTES, "one tile must fit the ring");
 constexpr int SB_FTS_THREADS = (SB_FTS_CONSUMER_WARPS + SB_FTS_PRODUCER_WARPS) * 32;
 
 struct FeatherTmaCam {
