@@ -471,7 +471,7 @@ int setup(sb_compositor *c)
             SB_TRY(c->tma_desc.ensure(sizeof(uint4) * (1 + SB_FTT_MAXC) * (size_t)ta.n_tiles + 16));
             int *status = reinterpret_cast<int *>(static_cast<uint4 *>(c->tma_desc.p) + (size_t)(1 + SB_FTT_MAXC) * ta.n_tiles);
             SB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), s));
-            SB_TRY(launch_fts_descriptors(ta, static_cast<uint4 *>(c->tma_desc.p), status, s));
+            SB_TRY(launch_fts_descriptors(ta, static_cast<uint4 *>(c->tma_desc.p), status, fts_grid(ta.n_tiles, c->sm_count), s));
             int h_status = 1;
             SB_CUDA(cudaMemcpyAsync(&h_status, status, sizeof h_status, cudaMemcpyDeviceToHost, s));
             SB_CUDA(cudaStreamSynchronize(s));

@@ -18,6 +18,8 @@
 //     No consumer thread ever waits on a global load.
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
+#include <vector>
 
 #include "sb_device.cuh"
 #include "sb_fused.h"
@@ -119,7 +121,8 @@ int launch_fts_camera_tiles(const uint2 *table, size_t tstep, int ww, int wh, in
 }
 
 // pass 3: one 64-byte descriptor per panorama tile:
-//   [0]     = {n_cams | short path << 2 | ring units << 8, tile origin X0 | Y0 << 16, 0, 0}     (ring unit = 128 bytes)
+//   [0]     = {n_cams | short path << 2 | ring units << 8, tile origin X0 | Y0 << 16, ring start unit, tiles to retire first}
+//             (ring unit = 128 bytes; .z and .w are filled by k_fts_ring_plan)
 //   [1 + k] = per camera slot (ascending camera index = feed order)
 //             {xlo | ylo << 16, need_end | n_rows << 24, pitch | ring unit offset inside the tile << 16,
 //              cam | table block index << 4 | full weight << 31}
@@ -156,12 +159,72 @@ __global__ void k_fts_descriptors(FtsSetup a, uint4 *desc, int *status)
     if (bad) atomicOr(status, bad);
 }
 
-int launch_fts_descriptors(const FtsSetup &a, uint4 *desc, int *status, cudaStream_t s)
+// pass 4 (after the host has put the tiles in schedule order): the shared-memory ring plan.  CTA b of a grid of G
+// walks tiles b, b + G, ...; a tile takes `units` contiguous 128-byte ring units at the head, wrapping to 0 when the
+// end of the ring is too short, and tiles retire in order.  Both are a pure function of the tile sizes, so the start
+// unit of every tile and the number of the CTA's tiles that must have been consumed before its copies may land are
+// computed once per calibration: [0].z = start unit, [0].w = tiles to retire first (also covers the reuse of the tile's
+// stage entry).  The producer warps then need no shared bookkeeping at all.
+__global__ void k_fts_ring_plan(uint4 *desc, int n_tiles, int G)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= G) return;
+    int hist[SB_FTT_STAGES];
+    int head = 0, tail = 0, oldest = 0, seq = 0;
+    for (int tile = b; tile < n_tiles; tile += G, ++seq) {
+        uint4 d0 = desc[(size_t)tile * (1 + SB_FTT_MAXC)];
+        const int units = (int)(d0.x >> 8);
+        int start;
+        for (;;) {
+            if (seq - oldest < SB_FTT_STAGES) {
+                if (seq == oldest) head = tail = 0;     // nothing in flight
+                if (head >= tail) {                     // in use: [tail, head)
+                    if (head + units <= SB_FTS_RING_BYTES / 128) { start = head; break; }
+                    if (units < tail) { start = 0; break; }
+                } else if (head + units < tail) {       // in use: [tail, end) and [0, head)
+                    start = head; break;
+                }
+            }
+            ++oldest;
+            tail = oldest < seq ? hist[oldest % SB_FTT_STAGES] : head;
+        }
+        head = start + units;
+        hist[seq % SB_FTT_STAGES] = start;
+        d0.z = (unsigned)start;
+        d0.w = (unsigned)oldest;
+        desc[(size_t)tile * (1 + SB_FTT_MAXC)] = d0;
+    }
+}
+
+// Schedule order: CTA b takes positions b, b + G, ... of the descriptor array, so listing the tiles by descending cost
+// (blended tiles with 3, 2, 1 cameras, then the single-camera short-path tiles, then empty ones; row-major inside a
+// class) deals every CTA the same number of tiles of each class, the expensive ones first.
+int launch_fts_descriptors(const FtsSetup &a, uint4 *desc, int *status, int grid, cudaStream_t s)
 {
     k_fts_descriptors<<<div_up(a.n_tiles, 128), 128, 0, s>>>(a, desc, status);
     SB_LAUNCHED();
+    const size_t per = 1 + SB_FTT_MAXC;
+    std::vector<uint4> h((size_t)a.n_tiles * per), o((size_t)a.n_tiles * per);
+    SB_CUDA(cudaMemcpyAsync(h.data(), desc, h.size() * sizeof(uint4), cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    std::vector<int> order(a.n_tiles);
+    for (int t = 0; t < a.n_tiles; ++t) order[t] = t;
+    auto cost = [&](int t) {
+        const unsigned x = h[(size_t)t * per].x;
+        const int nc = (int)(x & 3u);
+        return nc == 0 ? 0 : (x & 4u) ? 1 : 1 + nc;
+    };
+    if (!getenv("SB_FTS_NO_SORT"))                          // (measurement knob: row-major tile order)
+        std::stable_sort(order.begin(), order.end(), [&](int l, int r) { return cost(l) > cost(r); });
+    for (int t = 0; t < a.n_tiles; ++t)
+        for (size_t j = 0; j < per; ++j) o[(size_t)t * per + j] = h[(size_t)order[t] * per + j];
+    SB_CUDA(cudaMemcpyAsync(desc, o.data(), o.size() * sizeof(uint4), cudaMemcpyHostToDevice, s));
+    k_fts_ring_plan<<<div_up(grid, 64), 64, 0, s>>>(desc, a.n_tiles, grid);
+    SB_LAUNCHED();
+    SB_CUDA(cudaStreamSynchronize(s));                      // (o goes out of scope)
     return SB_OK;
 }
+int fts_grid(int n_tiles, int sm_count) { return std::min(n_tiles, SB_FTS_CTAS_PER_SM * sm_count); }
 
 // ------------------------------------------------------------------------------------ frame kernel
 // Shared memory: a byte ring (128-byte units) that holds, per (tile, camera) in flight, the table block followed by
@@ -170,9 +233,8 @@ constexpr int FTS_RING_UNITS = SB_FTS_RING_BYTES / 128;
 struct FtsSmem {
     unsigned char ring[SB_FTS_RING_BYTES];
     uint2 lut[1024];                                        // bilin_lut (sb_device.cuh): 8 KB, read once per camera pixel
-    uint4 desc[SB_FTT_STAGES][1 + SB_FTT_MAXC];             // [0] = {n_cams | short << 2, tile origin, ., .}; [1 + k].x = shared address of slot k
+    uint4 desc[SB_FTT_STAGES][1 + SB_FTT_MAXC];             // [0] = {n_cams | short << 2, tile origin, output byte offset, mask byte offset}; [1 + k].x = shared address of slot k
     uint64_t full[SB_FTT_STAGES], empty[SB_FTT_STAGES];
-    int start_hist[SB_FTS_PRODUCER_WARPS][SB_FTT_STAGES];   // per producer warp: ring start unit of the tiles in flight
 };
 
 // exposure gain of camera `c` at panorama pixel (X, Y): the scalar of GainCompensator or the resized block map
@@ -258,46 +320,37 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
 
     if (warp >= SB_FTS_CONSUMER_WARPS) {
         // ------------------------------------------------ producer warps
-        // Tile seq (0, 1, 2 ... of this CTA) is fetched by producer warp seq % PRODUCER_WARPS, so the per-tile issue
-        // latency (descriptor shuffles, barrier ops, address arithmetic) overlaps across warps.  Every warp replays the
-        // ring allocation for ALL tiles (it only needs each tile's size, one word fetched a tile ahead): a tile takes
-        // `units` contiguous 128-byte units at the head, wrapping to 0 when the end of the ring is too short; tiles
-        // retire in order, which moves the tail to the start of the oldest tile still in flight.
+        // Producer warp w fetches tiles w, w + P, ... of this CTA's sequence (seq = 0, 1, 2 ...; tile = blockIdx + seq * G),
+        // so the per-tile issue latency overlaps across warps.  Where a tile lands in the ring and how many of the CTA's
+        // tiles must have been consumed first come from the ring plan in the descriptor (k_fts_ring_plan).
         const int pw = warp - SB_FTS_CONSUMER_WARPS;
-        int stage = 0, head = 0, tail = 0;
-        int seq = 0, oldest = 0;                            // tiles issued / retired by this CTA
         const uint4 *dbase = a.desc;
         const uint32_t ring0 = smem_u32(&sm.ring[0]);
-        unsigned w_next = __ldg(&dbase[(size_t)blockIdx.x * (1 + SB_FTT_MAXC)].x);   // n_cams | .. | units << 8, one tile ahead
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += G, ++seq) {
-            const unsigned w0 = w_next;
-            if (tile + G < a.n_tiles) w_next = __ldg(&dbase[(size_t)(tile + G) * (1 + SB_FTT_MAXC)].x);
-            const int nc = (int)(w0 & 3u), units = (int)(w0 >> 8);
-            const bool mine = seq % SB_FTS_PRODUCER_WARPS == pw;
-            uint4 d = make_uint4(0u, 0u, 0u, 0u);
-            if (mine && lane <= SB_FTT_MAXC) d = __ldg(dbase + (size_t)tile * (1 + SB_FTT_MAXC) + lane);
-            int start;
-            for (;;) {
-                if (seq - oldest < SB_FTT_STAGES) {
-                    if (seq == oldest) head = tail = 0;     // nothing in flight
-                    if (head >= tail) {                     // in use: [tail, head)
-                        if (head + units <= FTS_RING_UNITS) { start = head; break; }
-                        if (units < tail) { start = 0; break; }
-                    } else if (head + units < tail) {       // in use: [tail, end) and [0, head)
-                        start = head; break;
-                    }
-                }
-                const int e = oldest % SB_FTT_STAGES;
-                mbar_wait(&sm.empty[e], (unsigned)(oldest / SB_FTT_STAGES) & 1u);   // every consumer warp is done with the oldest tile
-                ++oldest;
-                tail = oldest < seq ? sm.start_hist[pw][oldest % SB_FTT_STAGES] : head;
+        const unsigned ostep = (unsigned)a.out_step, mstep = (unsigned)a.mask_step;
+        int tile = blockIdx.x + pw * G;
+        uint4 d_next = make_uint4(0u, 0u, 0u, 0u);
+        if (tile < a.n_tiles && lane <= SB_FTT_MAXC) d_next = __ldg(dbase + (size_t)tile * (1 + SB_FTT_MAXC) + lane);
+        for (int seq = pw; tile < a.n_tiles; tile += SB_FTS_PRODUCER_WARPS * G, seq += SB_FTS_PRODUCER_WARPS) {
+            const uint4 d = d_next;
+            if (tile + SB_FTS_PRODUCER_WARPS * G < a.n_tiles && lane <= SB_FTT_MAXC)       // one of this warp's tiles ahead
+                d_next = __ldg(dbase + (size_t)(tile + SB_FTS_PRODUCER_WARPS * G) * (1 + SB_FTT_MAXC) + lane);
+            const int stage = seq % SB_FTT_STAGES;
+            const int nc = (int)(__shfl_sync(0xffffffffu, d.x, 0) & 3u);
+            const uint32_t tile_base = ring0 + __shfl_sync(0xffffffffu, d.z, 0) * 128u;
+            const int need = max((int)__shfl_sync(0xffffffffu, d.w, 0), seq - SB_FTT_STAGES + 1);
+            if (need > 0) {                                 // tiles retire in order: waiting for tile need - 1 covers all before it
+                const int t = need - 1;                     // (t >= seq - STAGES, so the barrier is at most one phase ahead)
+                mbar_wait(&sm.empty[t % SB_FTT_STAGES], (unsigned)(t / SB_FTT_STAGES) & 1u);
             }
-            head = start + units;
-            sm.start_hist[pw][stage] = start;               // (every lane stores the same value)
-            if (mine) {
-                const uint32_t tile_base = ring0 + (uint32_t)start * 128u;
+            {
                 uint4 ds = d;
-                if (lane != 0) ds.x = tile_base + ((d.z >> 16) << 7);
+                if (lane == 0) {                            // tile origin -> byte offsets of its first pixel in the panorama and the mask
+                    const unsigned X0 = d.y & 0xffffu, Y0 = d.y >> 16;
+                    ds.z = Y0 * ostep + X0 * (OUT8 ? 3u : 6u);
+                    ds.w = Y0 * mstep + X0;
+                } else {
+                    ds.x = tile_base + ((d.z >> 16) << 7);
+                }
                 if (lane <= SB_FTT_MAXC) sm.desc[stage][lane] = ds;
                 __syncwarp();
                 // table blocks: one bulk copy (TMA) per camera slot, completion by expect_tx
@@ -344,7 +397,6 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
                 }
                 cp_async_mbar_arrive_noinc(&sm.full[stage]);    // one arrival per lane when its chunks have landed
             }
-            if (++stage == SB_FTT_STAGES) stage = 0;
         }
         return;
     }
@@ -358,15 +410,17 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
     const uint32_t lut0 = smem_u32(&sm.lut[0]);
     const uint32_t tab_off = (uint32_t)(ly * SB_FTT_W + lx) * 8u;
     const unsigned ostep = (unsigned)a.out_step, mstep = (unsigned)a.mask_step;      // (the launcher checks the panorama is < 4 GB)
+    unsigned char *const out_t = reinterpret_cast<unsigned char *>(a.out) + ((unsigned)ly * ostep + (unsigned)lx * (OUT8 ? 3u : 6u));
+    uint8_t *const mask_t = a.out_mask ? a.out_mask + ((unsigned)ly * mstep + (unsigned)lx) : nullptr;
     int stage = 0;
     unsigned parity = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += G) {
         mbar_wait(&sm.full[stage], parity);
         const uint4 d0 = sm.desc[stage][0];
         const int nc = (int)(d0.x & 3u);
-        const int X = (int)(d0.y & 0xffffu) + lx, Y0 = (int)(d0.y >> 16) + ly;
-        unsigned char *orow = reinterpret_cast<unsigned char *>(a.out) + ((unsigned)Y0 * ostep + (unsigned)X * (OUT8 ? 3u : 6u));
-        uint8_t *mrow_ = a.out_mask ? a.out_mask + ((unsigned)Y0 * mstep + (unsigned)X) : nullptr;
+        const int X = (int)(d0.y & 0xffffu) + lx, Y0 = (int)(d0.y >> 16) + ly;       // (only the gain map and the edge tiles use them)
+        unsigned char *orow = out_t + d0.z;
+        uint8_t *mrow_ = mask_t ? mask_t + d0.w : nullptr;
         if (d0.x & 4u) {
             // Short path (block-uniform; ~80 % of a ring panorama): ONE camera with weight exactly 1.0f on every pixel
             // of the tile.  Then dst = short(p * 1.0f) = p, dst_w = 1.0f, and normalizeUsingWeightMap gives
@@ -528,7 +582,7 @@ int launch_feather_stream(const FeatherTmaArgs &a, bool apply_gain, bool out8, i
         SB_CUDA(cudaFuncSetAttribute(fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[v] = true;
     }
-    const int grid = std::min(a.n_tiles, SB_FTS_CTAS_PER_SM * sm_count);
+    const int grid = fts_grid(a.n_tiles, sm_count);           // the schedule order and ring plan in a.desc were made for this grid
     void *params[] = {const_cast<FeatherTmaArgs *>(&a)};
     SB_CUDA(cudaLaunchKernel(fn[v], dim3(grid), dim3(SB_FTS_THREADS), params, smem, s));
     SB_LAUNCHED();

@@ -106,7 +106,8 @@ struct FtsSetup {
 int launch_fts_camera_tiles(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int tx0, int ty0, int ntx, int nty,
                             float sharpness, uint4 *rec, uint2 *tiles, cudaStream_t s);
 // setup: the per-tile descriptors; *status != 0 -> the streaming kernel cannot be used for this calibration
-int launch_fts_descriptors(const FtsSetup &a, uint4 *desc, int *status, cudaStream_t s);
+int launch_fts_descriptors(const FtsSetup &a, uint4 *desc, int *status, int grid, cudaStream_t s);   // grid = fts_grid(): the schedule and ring plan are per grid size
+int fts_grid(int n_tiles, int sm_count);
 int launch_feather_stream(const FeatherTmaArgs &a, bool apply_gain, bool out8, int sm_count, cudaStream_t s);
 
 // one camera as seen by k_band_fused at one pyramid level
