@@ -315,7 +315,6 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
         }
         mbar_fence_init();
     }
-    for (int i = tid; i < 1024; i += SB_FTS_THREADS) sm.lut[i] = __ldg(a.bilin_lut + i);
     __syncthreads();
 
     if (warp >= SB_FTS_CONSUMER_WARPS) {
@@ -407,6 +406,9 @@ k_feather_stream(const __grid_constant__ FeatherTmaArgs a)
     static_assert(SB_FTT_W == 32 && SB_FTT_H % RPP == 0, "one warp per tile row");
     constexpr uint32_t ROW_STRIDE = (uint32_t)RPP * SB_FTT_W * 8u;        // table bytes between a thread's pixels
     const int lx = lane, ly = warp;
+    // the weight table is loaded by the consumer warps while the producers already fetch the first tiles
+    for (int i = tid; i < 1024; i += SB_FTS_CONSUMER_WARPS * 32) sm.lut[i] = __ldg(a.bilin_lut + i);
+    asm volatile("bar.sync 1, %0;" ::"n"(SB_FTS_CONSUMER_WARPS * 32) : "memory");
     const uint32_t lut0 = smem_u32(&sm.lut[0]);
     const uint32_t tab_off = (uint32_t)(ly * SB_FTT_W + lx) * 8u;
     const unsigned ostep = (unsigned)a.out_step, mstep = (unsigned)a.mask_step;      // (the launcher checks the panorama is < 4 GB)
