@@ -129,8 +129,9 @@ int sb_convert_maps(const sb_image *xmap, const sb_image *ymap, sb_image *map1, 
 
 /* =====================================================================================
  * ExposureCompensator — INC/detail/exposure_compensate.hpp:51-101.
- * feed() (gain estimation) is calibration and stays on the host (north_star); its result is
- * handed in with sb_comp_set_gains / sb_comp_set_gain_maps.
+ * feed() (gain estimation) is calibration, once per sequence (north_star): its result is either
+ * handed in (sb_comp_set_gains / sb_comp_set_gain_maps) or estimated by sb_comp_feed, which reduces
+ * the overlap statistics on the device and solves the normal equations on the host.
  * ===================================================================================== */
 enum { SB_COMP_NO = 0, SB_COMP_GAIN = 1, SB_COMP_GAIN_BLOCKS = 2 };   /* exposure_compensate.hpp:56 */
 typedef struct sb_comp sb_comp;
@@ -142,8 +143,30 @@ int  sb_comp_set_gains(sb_comp *c, const double *gains, int n);
 int  sb_comp_get_gains(const sb_comp *c, double *gains, int n);
 /* BlocksGainCompensator::gain_maps_ (exposure_compensate.cpp:203-221): n host CV_32FC1 maps */
 int  sb_comp_set_gain_maps(sb_comp *c, const sb_image *maps, int n);
+/* ExposureCompensator::feed(corners, images, masks) (exposure_compensate.cpp:64-71): GainCompensator::feed (:76-147) or
+ * BlocksGainCompensator::feed (:165-222).  images CV_8UC3, masks CV_8UC1 (level 255), host or device.  The pair
+ * statistics N(i,j) (exact) and I(i,j) = sum sqrt(r^2+g^2+b^2) / N are reduced on the device; the sums are accumulated
+ * as exact 128-bit integers (order independent, rounded once), where the reference adds doubles in scan order — gains
+ * agree with the reference to ~1e-12 relative, not bit for bit.  A = n x n is dense as in the reference (blocks: n =
+ * total block count; the LU is the reference's O(n^3)). */
+int  sb_comp_feed(sb_comp *c, const sb_point *corners, const sb_image *images, const sb_image *masks, int n);
+/* BlocksGainCompensator(bl_width = 32, bl_height = 32) ctor arguments (exposure_compensate.hpp:92) */
+int  sb_comp_set_block_size(sb_comp *c, int bl_width, int bl_height);
+/* number of gains / gain maps the compensator holds after feed or set */
+int  sb_comp_num_gains(const sb_comp *c);
+/* BlocksGainCompensator::gain_maps_[index] as estimated by sb_comp_feed: size, then a copy into a host CV_32FC1 image */
+int  sb_comp_gain_map_size(const sb_comp *c, int index, sb_size *size);
+int  sb_comp_get_gain_map(const sb_comp *c, int index, sb_image *map);
 /* ExposureCompensator::apply (exposure_compensate.cpp:150-153, 225-246): in place on 8UC3 */
 int  sb_comp_apply(sb_comp *c, int index, sb_point corner, sb_image *image, const sb_image *mask);
+
+/* The seam-mask refinement every compose loop of the reference runs per camera (stitcher.cpp:291-294; SAMPLE:731-735):
+ *     dilate(masks_warped[i], dilated, Mat());  resize(dilated, seam_mask, mask_warped.size());  out = seam_mask & mask_warped
+ * seam_mask: CV_8UC1 at seam-estimation scale; mask_warped, out: CV_8UC1 at compose scale.  Bit-exact. */
+int sb_refine_seam_mask(const sb_image *seam_mask, const sb_image *mask_warped, sb_image *out, int device);
+/* its two OpenCV primitives on CV_8UC1: cv::dilate(src, dst, Mat()) and cv::resize(src, dst, dst.size(), 0, 0, INTER_LINEAR) */
+int sb_dilate3x3(const sb_image *src, sb_image *dst, int device);
+int sb_resize_linear_8u(const sb_image *src, sb_image *dst, int device);
 
 /* =====================================================================================
  * Blender / FeatherBlender / MultiBandBlender — INC/detail/blenders.hpp:53-117, blenders.cpp

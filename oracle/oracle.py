@@ -241,6 +241,86 @@ def resize_linear(src, dsize_wh):
     return dst
 
 
+
+# ---- once-per-calibration steps (so_calib.c) -------------------------------------------------
+def _mat_array(arrs):
+    ms = [mat(a) for a in arrs]
+    arr = (SoMat * len(ms))(*ms)
+    arr._keep = ms
+    return arr
+
+
+def gain_overlap_stats(corners, images, masks, mask_vals=None):
+    """exposure_compensate.cpp:93-126 -> (N int32 n x n, I float64 n x n)"""
+    n = len(images)
+    images = [np.ascontiguousarray(a, np.uint8) for a in images]
+    masks = [np.ascontiguousarray(a, np.uint8) for a in masks]
+    vals = (C.c_ubyte * n)(*([255] * n if mask_vals is None else mask_vals))
+    cxy = np.ascontiguousarray(np.asarray(corners, np.int32).reshape(-1))
+    N, I = np.zeros((n, n), np.int32), np.zeros((n, n), np.float64)
+    lib().so_gain_overlap_stats(n, cxy.ctypes.data_as(C.c_void_p), _mat_array(images), _mat_array(masks), vals,
+                                N.ctypes.data_as(C.c_void_p), I.ctypes.data_as(C.c_void_p))
+    return N, I
+
+
+def gain_feed(corners, images, masks, mask_vals=None):
+    """GainCompensator::feed (exposure_compensate.cpp:76-147) -> gains (float64)"""
+    n = len(images)
+    images = [np.ascontiguousarray(a, np.uint8) for a in images]
+    masks = [np.ascontiguousarray(a, np.uint8) for a in masks]
+    vals = (C.c_ubyte * n)(*([255] * n if mask_vals is None else mask_vals))
+    cxy = np.ascontiguousarray(np.asarray(corners, np.int32).reshape(-1))
+    gains = np.zeros(n, np.float64)
+    _chk(lib().so_gain_feed(n, cxy.ctypes.data_as(C.c_void_p), _mat_array(images), _mat_array(masks), vals,
+                            gains.ctypes.data_as(C.c_void_p)), "gain_feed")
+    return gains
+
+
+def blocks_gain_feed(corners, images, masks, bl_width=32, bl_height=32):
+    """BlocksGainCompensator::feed (exposure_compensate.cpp:165-222) -> list of float32 block gain maps"""
+    n = len(images)
+    images = [np.ascontiguousarray(a, np.uint8) for a in images]
+    masks = [np.ascontiguousarray(a, np.uint8) for a in masks]
+    vals = (C.c_ubyte * n)(*([255] * n))
+    cxy = np.ascontiguousarray(np.asarray(corners, np.int32).reshape(-1))
+    maps = [np.zeros(((a.shape[0] + bl_height - 1) // bl_height, (a.shape[1] + bl_width - 1) // bl_width), np.float32) for a in images]
+    _chk(lib().so_blocks_gain_feed(n, cxy.ctypes.data_as(C.c_void_p), _mat_array(images), _mat_array(masks), vals,
+                                   bl_width, bl_height, _mat_array(maps)), "blocks_gain_feed")
+    return maps
+
+
+def sep_filter3(src, k0=0.5, k1=0.25):
+    src = np.ascontiguousarray(src, np.float32)
+    dst = np.empty_like(src)
+    ms, md = mat(src), mat(dst)
+    _chk(lib().so_sep_filter3_f32(C.byref(ms), C.byref(md), C.c_float(k0), C.c_float(k1)), "sepFilter2D")
+    return dst
+
+
+def dilate3x3(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    ms, md = mat(src), mat(dst)
+    _chk(lib().so_dilate3x3_8u(C.byref(ms), C.byref(md)), "dilate")
+    return dst
+
+
+def resize_linear_8u(src, dsize_wh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dsize_wh[1], dsize_wh[0]), np.uint8)
+    ms, md = mat(src), mat(dst)
+    _chk(lib().so_resize_linear_8u(C.byref(ms), C.byref(md)), "resize 8u")
+    return dst
+
+
+def refine_seam_mask(seam_mask, mask_warped):
+    """stitcher.cpp:291-294"""
+    seam_mask, mask_warped = np.ascontiguousarray(seam_mask, np.uint8), np.ascontiguousarray(mask_warped, np.uint8)
+    dst = np.empty_like(mask_warped)
+    a, b, d = mat(seam_mask), mat(mask_warped), mat(dst)
+    _chk(lib().so_refine_seam_mask(C.byref(a), C.byref(b), C.byref(d)), "refine_seam_mask")
+    return dst
+
 def distance_l1(mask):
     mask = np.ascontiguousarray(mask, np.uint8)
     dst = np.empty(mask.shape, np.float32)

@@ -123,6 +123,19 @@ int  so_blender_blend(so_blender *b, so_mat *dst, so_mat *dst_mask);
 void so_set_float_pyrdown_order(int mode);
 
 /* version string / self-identification */
+/* ---- once-per-calibration steps next to the path (so_calib.c) ---- */
+int  so_solve_lu(int n, double *A, double *b);                              /* cv::solve DECOMP_LU, in place */
+void so_gain_overlap_stats(int n, const int *corners_xy, const so_mat *images, const so_mat *masks, const unsigned char *mask_vals,
+                           int *N, double *I);                              /* exposure_compensate.cpp:93-126 */
+int  so_gain_solve(int n, const int *N, const double *I, double *gains);    /* :128-144 */
+int  so_gain_feed(int n, const int *corners_xy, const so_mat *images, const so_mat *masks, const unsigned char *mask_vals, double *gains);
+int  so_sep_filter3_f32(const so_mat *src, so_mat *dst, float k0, float k1);
+int  so_blocks_gain_feed(int n, const int *corners_xy, const so_mat *images, const so_mat *masks, const unsigned char *mask_vals,
+                         int bl_width, int bl_height, so_mat *gain_maps);   /* :165-222 */
+int  so_dilate3x3_8u(const so_mat *src, so_mat *dst);
+int  so_resize_linear_8u(const so_mat *src, so_mat *dst);
+int  so_refine_seam_mask(const so_mat *seam_mask, const so_mat *mask_warped, so_mat *out);   /* stitcher.cpp:291-294 */
+
 const char *so_version(void);
 
 #ifdef __cplusplus

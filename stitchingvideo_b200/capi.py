@@ -96,6 +96,14 @@ API = {
     "sb_comp_get_gains": (C.c_int, [C.c_void_p, _P(C.c_double), C.c_int]),
     "sb_comp_set_gain_maps": (C.c_int, [C.c_void_p, _P(SbImage), C.c_int]),
     "sb_comp_apply": (C.c_int, [C.c_void_p, C.c_int, SbPoint, _P(SbImage), _P(SbImage)]),
+    "sb_comp_feed": (C.c_int, [C.c_void_p, _P(SbPoint), _P(SbImage), _P(SbImage), C.c_int]),
+    "sb_comp_set_block_size": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "sb_comp_num_gains": (C.c_int, [C.c_void_p]),
+    "sb_comp_gain_map_size": (C.c_int, [C.c_void_p, C.c_int, _P(SbSize)]),
+    "sb_comp_get_gain_map": (C.c_int, [C.c_void_p, C.c_int, _P(SbImage)]),
+    "sb_refine_seam_mask": (C.c_int, [_P(SbImage), _P(SbImage), _P(SbImage), C.c_int]),
+    "sb_dilate3x3": (C.c_int, [_P(SbImage), _P(SbImage), C.c_int]),
+    "sb_resize_linear_8u": (C.c_int, [_P(SbImage), _P(SbImage), C.c_int]),
     "sb_blender_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P(C.c_void_p)]),
     "sb_blender_destroy": (None, [C.c_void_p]),
     "sb_blender_num_bands": (C.c_int, [C.c_void_p]),
@@ -423,7 +431,8 @@ def remap(src, xmap, ymap, interp_mode=INTER_LINEAR, border_mode=BORDER_CONSTANT
 
 # ======================================================================================= exposure
 class ExposureCompensator:
-    """detail::ExposureCompensator (exposure_compensate.hpp:51-64).  feed() is calibration (host)."""
+    """detail::ExposureCompensator (exposure_compensate.hpp:51-64).  feed() is calibration: hand its result in
+    (setGains / setGainMaps) or let feed() estimate it (overlap statistics on the device)."""
     NO, GAIN, GAIN_BLOCKS = COMP_NO, COMP_GAIN, COMP_GAIN_BLOCKS
     KIND = COMP_NO
 
@@ -443,6 +452,18 @@ class ExposureCompensator:
         if getattr(self, "_h", None) and _lib is not None:
             _lib.sb_comp_destroy(self._h)
             self._h = None
+
+    def feed(self, corners, images, masks):
+        """ExposureCompensator::feed(corners, images, masks) (exposure_compensate.cpp:64-71, 76-147, 165-222):
+        images uint8 HxWx3, masks uint8 HxW (level 255), host arrays or DeviceImages."""
+        n = len(images)
+        if not (len(corners) == n and len(masks) == n):
+            raise StitchError(SB_ERR_ASSERT, "corners.size() == images.size() && images.size() == masks.size()")
+        im, mk = [_image(a) for a in images], [_image(a) for a in masks]
+        ai, am = (SbImage * max(n, 1))(*[x[0] for x in im]), (SbImage * max(n, 1))(*[x[0] for x in mk])
+        pts = (SbPoint * max(n, 1))(*[SbPoint(int(c[0]), int(c[1])) for c in corners])
+        _check(lib().sb_comp_feed(self._h, pts, ai, am, n))
+        self._n = n
 
     def apply(self, index, corner, image, mask=None):
         """In place on a host uint8 array or a DeviceImage (exposure_compensate.cpp:150-153, 225-246)."""
@@ -478,6 +499,50 @@ class BlocksGainCompensator(ExposureCompensator):
         keep = [np.ascontiguousarray(m, np.float32) for m in maps]
         arr = (SbImage * len(keep))(*[_image(m)[0] for m in keep])
         _check(lib().sb_comp_set_gain_maps(self._h, arr, len(keep)))
+
+    def setBlockSize(self, bl_width, bl_height):
+        """BlocksGainCompensator(bl_width = 32, bl_height = 32) (exposure_compensate.hpp:92)"""
+        _check(lib().sb_comp_set_block_size(self._h, bl_width, bl_height))
+
+    def gainMaps(self):
+        """gain_maps_ as estimated by feed(): list of float32 arrays (block grid of every image)"""
+        out = []
+        for i in range(lib().sb_comp_num_gains(self._h)):
+            sz = SbSize()
+            _check(lib().sb_comp_gain_map_size(self._h, i, C.byref(sz)))
+            m = np.empty((sz.height, sz.width), np.float32)
+            im, _ = _image(m)
+            _check(lib().sb_comp_get_gain_map(self._h, i, C.byref(im)))
+            out.append(m)
+        return out
+
+
+def refine_seam_mask(seam_mask, mask_warped, device=0):
+    """stitcher.cpp:291-294: dilate(seam_mask) -> resize to mask_warped.size() (INTER_LINEAR) -> & mask_warped"""
+    a, k0 = _image(np.ascontiguousarray(seam_mask, np.uint8))
+    b, k1 = _image(np.ascontiguousarray(mask_warped, np.uint8))
+    out = np.empty((b.rows, b.cols), np.uint8)
+    o, k2 = _image(out)
+    _check(lib().sb_refine_seam_mask(C.byref(a), C.byref(b), C.byref(o), device))
+    return out
+
+
+def dilate3x3(src, device=0):
+    """cv::dilate(src, dst, Mat()) on uint8 HxW"""
+    a, k0 = _image(np.ascontiguousarray(src, np.uint8))
+    out = np.empty((a.rows, a.cols), np.uint8)
+    o, k1 = _image(out)
+    _check(lib().sb_dilate3x3(C.byref(a), C.byref(o), device))
+    return out
+
+
+def resize_linear_8u(src, dsize_wh, device=0):
+    """cv::resize(src, dsize, INTER_LINEAR) on uint8 HxW"""
+    a, k0 = _image(np.ascontiguousarray(src, np.uint8))
+    out = np.empty((dsize_wh[1], dsize_wh[0]), np.uint8)
+    o, k1 = _image(out)
+    _check(lib().sb_resize_linear_8u(C.byref(a), C.byref(o), device))
+    return out
 
 
 # ======================================================================================= blenders

@@ -46,6 +46,19 @@ int launch_convert(const DImage &src, const DImage &dst, cudaStream_t s);       
 int launch_copy_make_border(const DImage &src, const DImage &dst, int top, int left, int border, cudaStream_t s);  // a10
 int launch_set_zero(const DImage &img, cudaStream_t s);
 
+// ---- once-per-calibration steps (kernels_calib.cu) -----------------------
+struct OverlapPair {            // one overlap of GainCompensator::feed (exposure_compensate.cpp:99-124), already cropped
+    const uint8_t *img1, *img2;     // 8UC3 rows of the overlap in image i / j
+    const uint8_t *mask1, *mask2;   // 8UC1
+    unsigned istep1, istep2, mstep1, mstep2;
+    int w, h;
+    int val1, val2;                 // masks[i].second / masks[j].second
+};
+// out[pair] = {count, sum1 low, sum1 high, sum2 low, sum2 high}: sums of sqrt(r^2+g^2+b^2) * 2^52 as exact integers
+int launch_overlap_stats(const OverlapPair *pairs_dev, int n_pairs, int max_h, unsigned long long *out_dev, cudaStream_t s);
+int launch_dilate3x3(const DImage &src, const DImage &dst, cudaStream_t s);               // cv::dilate(src, dst, Mat())
+int launch_resize_linear_8u(const DImage &src, const DImage &dst, const DImage *and_mask, cudaStream_t s);   // cv::resize 8UC1 (& mask)
+
 // ---- pyramids (kernels_pyr.cu) ----------------------------------------------------------------
 int launch_pyr_down(const DImage &src, const DImage &dst, cudaStream_t s);                // A2 (8U/16S/32F, cn 1|3)
 int launch_pyr_up(const DImage &src, const DImage &dst, cudaStream_t s);                  // A3 (8U/16S)

@@ -124,6 +124,37 @@ def gen_blend():
     save("blend", **out)
 
 
+def gen_calib():
+    """ExposureCompensator::feed and the seam-mask refinement (SURVEY.md 8f rank 4) from cv2."""
+    rng = np.random.default_rng(106)
+    out = {}
+    for k, (shp, ds) in enumerate((((37, 53), (106, 74)), ((40, 64), (32, 20)), ((64, 2), (5, 100)), ((50, 70), (70, 50)),
+                                   ((31, 45), (100, 77)), ((1, 9), (20, 3)))):
+        a = (rng.random(shp) > 0.7).astype(np.uint8) * 255
+        a[rng.random(shp) > 0.9] = rng.integers(1, 255)
+        out["m%d" % k] = a
+        out["m%d_dilate" % k] = cv2.dilate(a, None)
+        out["m%d_resize" % k] = cv2.resize(a, ds, interpolation=cv2.INTER_LINEAR)
+        mw = (rng.random((ds[1], ds[0])) > 0.2).astype(np.uint8) * 255
+        out["m%d_warped" % k] = mw
+        out["m%d_refined" % k] = cv2.resize(cv2.dilate(a, None), ds) & mw          # stitcher.cpp:291-294
+    for n, w, h in ((2, 120, 90), (3, 160, 100), (5, 200, 120)):
+        corners, imgs, masks = util.exposure_scene(n, w, h, seed=n)
+        masks = [np.where(m == 255, 255, 0).astype(np.uint8) for m in masks]        # cv2 4.x tests mask != 0, 2.4.11 mask == 255
+        c = cv2.detail_GainCompensator(1)
+        c.feed(corners, [cv2.UMat(i) for i in imgs], [cv2.UMat(m) for m in masks])
+        out["gains%d" % n] = np.array(c.getMatGains(), np.float64).reshape(-1)
+        bc = cv2.detail_BlocksGainCompensator(32, 32, 1)
+        bc.setNrGainsFilteringIterations(2)
+        bc.feed(corners, [cv2.UMat(i) for i in imgs], [cv2.UMat(m) for m in masks])
+        for i, m in enumerate(bc.getMatGains()):
+            out["blocks%d_%d" % (n, i)] = np.array(m, np.float32)
+    g = rng.uniform(0.8, 1.2, (9, 13)).astype(np.float32)
+    ker = np.array([[0.25, 0.5, 0.25]], np.float32)
+    out["gmap"], out["gmap_smooth"] = g, cv2.sepFilter2D(g, cv2.CV_32F, ker, ker)
+    save("calib", **out)
+
+
 if __name__ == "__main__":
     gen_maps()
     gen_remap()
@@ -131,3 +162,4 @@ if __name__ == "__main__":
     gen_pyr()
     gen_misc()
     gen_blend()
+    gen_calib()

@@ -424,3 +424,68 @@ def test_remaining_projectors_against_reference_sources(gpu, name, ab):
         (tl, dst), (rtl, rdst) = w.warp(img, K, R), rw.warp(img, K, R)
         assert tuple(tl) == tuple(rtl)
         assert_same(dst, rdst, name + " warp")
+
+
+# ---- once-per-calibration steps --------------------------------------------------------------
+@pytest.mark.parametrize("n,w,h", [(2, 120, 90), (3, 160, 100), (5, 200, 120), (4, 333, 251)])
+def test_gain_compensator_feed(gpu, n, w, h):
+    """GainCompensator::feed (exposure_compensate.cpp:76-147): N exact, sums exact-then-rounded on the device vs the
+    reference's sequential double sums -> gains to 1e-11 relative (the tolerance of a double sum over <= 1e5 terms)."""
+    corners, imgs, masks = util.exposure_scene(n, w, h, seed=10 + n)
+    ref = O.gain_feed(corners, imgs, masks)
+    c = gpu.GainCompensator()
+    c.feed(corners, imgs, masks)
+    got = np.array(c.gains())
+    np.testing.assert_allclose(got, ref, rtol=1e-11, atol=0)
+    c2 = gpu.GainCompensator()                                       # deterministic run to run (integer accumulation)
+    c2.feed(corners, imgs, masks)
+    assert c2.gains() == c.gains()
+    # the estimated gains drive apply() like handed-in ones
+    img = imgs[1].copy()
+    c.apply(1, corners[1], img)
+    assert np.array_equal(img, O.gain_apply(imgs[1], ref[1])) or np.float32(ref[1]) != np.float32(got[1])
+
+
+def test_gain_compensator_feed_disjoint_and_errors(gpu):
+    corners, imgs, masks = util.exposure_scene(3, 64, 48, seed=3)
+    corners = [(0, 0), (1000, 0), (2000, 500)]                       # no overlaps: every gain is exactly 1
+    c = gpu.GainCompensator()
+    c.feed(corners, imgs, masks)
+    assert c.gains() == [1.0, 1.0, 1.0]
+    assert list(O.gain_feed(corners, imgs, masks)) == [1.0, 1.0, 1.0]
+    with pytest.raises(gpu.StitchError):                             # CV_Assert(corners.size() == images.size() && ...)
+        c.feed(corners[:2], imgs, masks)
+    with pytest.raises(gpu.StitchError):
+        c.feed(corners, [im[:, :, 0] for im in imgs], masks)
+
+
+@pytest.mark.parametrize("n,w,h,bl", [(2, 120, 90, 32), (3, 160, 100, 32), (3, 150, 97, 20)])
+def test_blocks_gain_compensator_feed(gpu, n, w, h, bl):
+    """BlocksGainCompensator::feed (exposure_compensate.cpp:165-222): block lists, one gain solve over all blocks, two
+    smoothing passes; float32 gain maps within 2 ulp of the oracle's (the double gains agree to 1e-11)."""
+    corners, imgs, masks = util.exposure_scene(n, w, h, seed=20 + n)
+    ref = O.blocks_gain_feed(corners, imgs, masks, bl, bl)
+    c = gpu.BlocksGainCompensator()
+    c.setBlockSize(bl, bl)
+    c.feed(corners, imgs, masks)
+    got = c.gainMaps()
+    assert [m.shape for m in got] == [m.shape for m in ref]
+    for a, b in zip(got, ref):
+        np.testing.assert_allclose(a, b, rtol=3e-7, atol=0)
+    img = imgs[0].copy()                                             # and apply() uses them
+    c.apply(0, corners[0], img)
+    assert np.abs(img.astype(int) - O.blocks_gain_apply(imgs[0], ref[0]).astype(int)).max() <= 1
+
+
+@pytest.mark.parametrize("shape,dsize", [((37, 53), (106, 74)), ((40, 64), (32, 20)), ((64, 2), (5, 100)), ((50, 70), (70, 50)),
+                                         ((31, 45), (100, 77)), ((1, 9), (20, 3)), ((249, 389), (1555, 998))])
+def test_seam_mask_refinement_bit_exact(gpu, shape, dsize):
+    """stitcher.cpp:291-294: dilate -> resize(INTER_LINEAR) -> & ; and the two primitives on their own."""
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    a = (rng.random(shape) > 0.6).astype(np.uint8) * 255
+    a[rng.random(shape) > 0.9] = rng.integers(1, 255)
+    mw = (rng.random((dsize[1], dsize[0])) > 0.2).astype(np.uint8) * 255
+    from stitchingvideo_b200 import capi
+    assert_same(capi.dilate3x3(a), O.dilate3x3(a), "dilate")
+    assert_same(capi.resize_linear_8u(a, dsize), O.resize_linear_8u(a, dsize), "resize")
+    assert_same(capi.refine_seam_mask(a, mw), O.refine_seam_mask(a, mw), "refined seam mask")

@@ -144,3 +144,23 @@ def test_sinf_cosf_match_host_libm():
     hc = np.array([m.cosf(float(v)) for v in xs], np.float32)
     assert (s.view(np.uint32) == hs.view(np.uint32)).all()
     assert (c.view(np.uint32) == hc.view(np.uint32)).all()
+
+
+def test_calibration_side_steps_golden():
+    """ExposureCompensator::feed (exposure_compensate.cpp:76-147, 165-222) and the seam-mask refinement
+    (stitcher.cpp:291-294) against cv2: the integer steps bit for bit, block gain maps bit for bit, scalar gains to
+    1e-12 (cv::solve takes a closed form for n <= 3)."""
+    from tests import util
+    g = load("calib")
+    for k, ds in enumerate(((106, 74), (32, 20), (5, 100), (70, 50), (100, 77), (20, 3))):
+        a = g["m%d" % k]
+        same(O.dilate3x3(a), g["m%d_dilate" % k], "dilate %d" % k)
+        same(O.resize_linear_8u(a, ds), g["m%d_resize" % k], "resize %d" % k)
+        same(O.refine_seam_mask(a, g["m%d_warped" % k]), g["m%d_refined" % k], "refine %d" % k)
+    same(O.sep_filter3(g["gmap"]), g["gmap_smooth"], "sepFilter2D")
+    for n, w, h in ((2, 120, 90), (3, 160, 100), (5, 200, 120)):
+        corners, imgs, masks = util.exposure_scene(n, w, h, seed=n)
+        gains = O.gain_feed(corners, imgs, masks)
+        np.testing.assert_allclose(gains, g["gains%d" % n], rtol=1e-12, atol=0)
+        for i, m in enumerate(O.blocks_gain_feed(corners, imgs, masks)):
+            same(m, g["blocks%d_%d" % (n, i)], "block gain map %d/%d" % (i, n))

@@ -62,3 +62,25 @@ def blend_scene(rng, n, H, W, spread, nonbinary=True, dtype=np.int16):
         masks.append(m)
         tls.append((int(rng.integers(-spread, spread)), int(rng.integers(-20, 20))))
     return imgs, masks, tls
+
+
+def exposure_scene(n, w, h, seed, overlap=0.3):
+    """n overlapping 8UC3 views of one smooth scene with different exposure, masks with holes, corners (some negative):
+    the input shape of ExposureCompensator::feed (exposure_compensate.cpp:64-71)."""
+    r = np.random.default_rng(seed)
+    step = int(w * (1 - overlap))
+    base = r.integers(0, 256, (h + 40, step * n + w, 3), dtype=np.uint8).astype(np.float32)
+    for _ in range(3):                                       # cheap smoothing without cv2 (the GPU box may lack it)
+        base = (base + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, -1, 0) + np.roll(base, -1, 1)) / 5
+    imgs, masks, corners = [], [], []
+    for i in range(n):
+        x0, y0 = i * step, (7 * i) % 30
+        g = 0.75 + 0.12 * i
+        im = np.clip(base[y0:y0 + h, x0:x0 + w] * g, 0, 255).astype(np.uint8)
+        m = np.full((h, w), 255, np.uint8)
+        m[:4] = 0
+        m[:, :3] = 0
+        m[r.random((h, w)) > 0.97] = 0
+        m[r.random((h, w)) > 0.995] = 128                    # not the level value: excluded like 0
+        imgs.append(np.ascontiguousarray(im)); masks.append(m); corners.append((x0 - 60, y0 - 11))
+    return corners, imgs, masks
