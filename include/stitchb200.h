@@ -233,6 +233,19 @@ typedef struct sb_compositor_config {
 } sb_compositor_config;
 
 int  sb_compositor_create(const sb_compositor_config *cfg, int device, sb_compositor **out);
+
+/* Calibration-table serialization: everything a (re)calibration hands to the per-frame path —
+ * the sb_compositor_config with its K, R, gains / block gain maps and seam masks (host images) — in one checksummed
+ * file, written atomically.  The reference keeps these only in process memory (APP64:334-346 PreStitchingStruct), so a
+ * restart pays the 1-2 s calibration again (APP64:696-722); with the file a process (or another rank) resumes by
+ * sb_calibration_load + sb_compositor_create(sb_calibration_config(cal), ...), which rebuilds the device tables in
+ * milliseconds, bit-identical.  Host-only: works without a device. */
+typedef struct sb_calibration sb_calibration;
+int  sb_calibration_save(const sb_compositor_config *cfg, const char *path);
+int  sb_calibration_load(const char *path, sb_calibration **out);
+/* the loaded configuration; pointers inside stay valid until sb_calibration_free */
+const sb_compositor_config *sb_calibration_config(const sb_calibration *cal);
+void sb_calibration_free(sb_calibration *cal);
 void sb_compositor_destroy(sb_compositor *c);
 /* geometry fixed by the calibration: per-camera warped corner/size and the panorama rect */
 int  sb_compositor_pano_size(const sb_compositor *c, sb_size *size);

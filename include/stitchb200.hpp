@@ -231,8 +231,18 @@ public:
     {
         return std::unique_ptr<ExposureCompensator>(new ExposureCompensator(type, device));
     }
-    // feed() (gain estimation, exposure_compensate.cpp:73-147,165-222) is calibration and stays on the
-    // host (north_star); hand its result in with setGains / setGainMaps.
+    // feed() (gain estimation, exposure_compensate.cpp:64-147,165-222) is calibration, once per sequence: either hand
+    // its result in with setGains / setGainMaps, or call feed — the overlap statistics are reduced on the device.
+    void feed(const std::vector<Point> &corners, const std::vector<Mat> &images, const std::vector<Mat> &masks)
+    {
+        if (corners.size() != images.size() || images.size() != masks.size())
+            throw Exception(SB_ERR_ASSERT, "corners.size() == images.size() && images.size() == masks.size()");
+        std::vector<sb_point> c;
+        std::vector<sb_image> im, mk;
+        for (size_t i = 0; i < images.size(); ++i) { c.push_back(sb_point{corners[i].x, corners[i].y}); im.push_back(images[i].c()); mk.push_back(masks[i].c()); }
+        check(sb_comp_feed(h_, c.data(), im.data(), mk.data(), (int)images.size()));
+        n_ = (int)images.size();
+    }
     void setGains(const std::vector<double> &g) { check(sb_comp_set_gains(h_, g.data(), (int)g.size())); n_ = (int)g.size(); }
     std::vector<double> gains() const
     {
@@ -269,7 +279,11 @@ public:
 };
 class BlocksGainCompensator : public ExposureCompensator {
 public:
-    explicit BlocksGainCompensator(int device = 0) : ExposureCompensator(SB_COMP_GAIN_BLOCKS, device) {}
+    // BlocksGainCompensator(int bl_width = 32, int bl_height = 32) (exposure_compensate.hpp:92)
+    explicit BlocksGainCompensator(int bl_width = 32, int bl_height = 32, int device = 0) : ExposureCompensator(SB_COMP_GAIN_BLOCKS, device)
+    {
+        check(sb_comp_set_block_size(h_, bl_width, bl_height));
+    }
 };
 
 // ------------------------------------------------------------------------------------ blenders

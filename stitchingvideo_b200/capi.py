@@ -101,6 +101,10 @@ API = {
     "sb_comp_num_gains": (C.c_int, [C.c_void_p]),
     "sb_comp_gain_map_size": (C.c_int, [C.c_void_p, C.c_int, _P(SbSize)]),
     "sb_comp_get_gain_map": (C.c_int, [C.c_void_p, C.c_int, _P(SbImage)]),
+    "sb_calibration_save": (C.c_int, [_P(SbCompositorConfig), C.c_char_p]),
+    "sb_calibration_load": (C.c_int, [C.c_char_p, _P(C.c_void_p)]),
+    "sb_calibration_config": (_P(SbCompositorConfig), [C.c_void_p]),
+    "sb_calibration_free": (None, [C.c_void_p]),
     "sb_refine_seam_mask": (C.c_int, [_P(SbImage), _P(SbImage), _P(SbImage), C.c_int]),
     "sb_dilate3x3": (C.c_int, [_P(SbImage), _P(SbImage), C.c_int]),
     "sb_resize_linear_8u": (C.c_int, [_P(SbImage), _P(SbImage), C.c_int]),
@@ -658,6 +662,34 @@ def restoreImageFromLaplacePyr(pyr, device=0):
 
 
 # ======================================================================================= compositor
+def save_calibration(cfg, path):
+    """sb_calibration_save of an SbCompositorConfig (or a pointer to one)"""
+    _check(lib().sb_calibration_save(cfg if isinstance(cfg, _P(SbCompositorConfig)) else C.byref(cfg), os.fsencode(path)))
+
+
+def load_calibration(path):
+    """sb_calibration_load -> dict of plain numpy values (the file's content; no device needed)"""
+    cal = C.c_void_p()
+    _check(lib().sb_calibration_load(os.fsencode(path), C.byref(cal)))
+    try:
+        c = lib().sb_calibration_config(cal).contents
+        n = c.n_cameras
+
+        def img(im):
+            dt = np.uint8 if im.type == CV_8UC1 else np.float32
+            a = np.ctypeslib.as_array(C.cast(im.data, _P(C.c_uint8)), shape=(im.rows, im.step))
+            return a[:, :im.cols * np.dtype(dt).itemsize].copy().view(dt)
+        return {"n_cameras": n, "src_size": (c.src_size.width, c.src_size.height), "warper_kind": c.warper_kind,
+                "warper_scale": c.warper_scale, "K": np.ctypeslib.as_array(c.K, shape=(n, 3, 3)).copy(),
+                "R": np.ctypeslib.as_array(c.R, shape=(n, 3, 3)).copy(), "blender_kind": c.blender_kind, "num_bands": c.num_bands,
+                "weight_type": c.weight_type, "sharpness": c.sharpness, "comp_kind": c.comp_kind, "output_type": c.output_type,
+                "gains": np.ctypeslib.as_array(c.gains, shape=(n,)).copy() if c.gains else None,
+                "seam_masks": [img(c.seam_masks[i]) for i in range(n)] if c.seam_masks else None,
+                "gain_maps": [img(c.gain_maps[i]) for i in range(n)] if c.gain_maps else None}
+    finally:
+        lib().sb_calibration_free(cal)
+
+
 class Compositor:
     """The per-frame loop of Stitcher::composePanorama (stitcher.cpp:221-313) with calibration fixed."""
 
@@ -699,17 +731,43 @@ class Compositor:
             arr = (SbImage * n)(*[_image(m)[0] for m in keep])
             cfg.seam_masks = arr
         cfg.output_type = output_type
-        self.output_type = output_type
+        self._cal = None
+        self._cfg, self._cfg_keep = C.pointer(cfg), (K, R, g, keep, locals().get("gkeep"), locals().get("garr"), locals().get("arr"))
+        self._create(device)
+
+    def _create(self, device):
+        cfg = self._cfg.contents
+        self.n, self.device, self.src_size = cfg.n_cameras, device, (cfg.src_size.width, cfg.src_size.height)
+        self.output_type = cfg.output_type
         self._h = C.c_void_p()
-        _check(lib().sb_compositor_create(C.byref(cfg), device, C.byref(self._h)))
+        _check(lib().sb_compositor_create(self._cfg, device, C.byref(self._h)))
         s = SbSize()
         _check(lib().sb_compositor_pano_size(self._h, C.byref(s)))
         self.pano_size = (s.width, s.height)
+
+    def save_calibration(self, path):
+        """Everything the calibration handed to this compositor (K, R, scale, blender settings, gains / gain maps,
+        seam masks) into one checksummed file (sb_calibration_save)."""
+        save_calibration(self._cfg, path)
+
+    @classmethod
+    def from_calibration(cls, path, device=0):
+        """Resume from a file written by save_calibration: the device tables are rebuilt, bit-identical."""
+        self = cls.__new__(cls)
+        self._h = None
+        self._cal = C.c_void_p()
+        _check(lib().sb_calibration_load(os.fsencode(path), C.byref(self._cal)))
+        self._cfg, self._cfg_keep = lib().sb_calibration_config(self._cal), None
+        self._create(device)
+        return self
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:
             _lib.sb_compositor_destroy(self._h)
             self._h = None
+        if getattr(self, "_cal", None) and _lib is not None:
+            _lib.sb_calibration_free(self._cal)
+            self._cal = None
 
     def camera_roi(self, i):
         r = SbRect()

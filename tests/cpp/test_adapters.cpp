@@ -114,6 +114,17 @@ int main(int argc, char **argv)
                 for (int y = 0; y < warped[i].rows; ++y)
                     for (int x = 0; x < warped[i].cols * 3; ++x) warped_s[i].ptr<short>(y)[x] = warped[i].ptr<unsigned char>(y)[x];
             }
+            if (wt == 0) {   // ExposureCompensator::feed as stitcher.cpp:209 calls it, on the warped images (exposure_compensate.cpp:76-147)
+                GainCompensator est;
+                est.feed(corners, warped, masks);
+                std::vector<so_mat> si, sm;
+                std::vector<int> c2;
+                std::vector<unsigned char> vals(N, 255);
+                for (int i = 0; i < N; ++i) { si.push_back(so(warped[i])); sm.push_back(so(masks[i])); c2.push_back(corners[i].x); c2.push_back(corners[i].y); }
+                std::vector<double> og(N), gg = est.gains();
+                EXPECT(so_gain_feed(N, c2.data(), si.data(), sm.data(), vals.data(), og.data()) == 0, "oracle gain feed");
+                for (int i = 0; i < N; ++i) EXPECT(std::fabs(gg[i] - og[i]) <= 1e-11 * std::fabs(og[i]), "estimated gain %d: %.17g vs %.17g", i, gg[i], og[i]);
+            }
             blender.prepare(corners, sizes);                                                                     // :296-300
             std::vector<int> cxy, swh;
             for (int i = 0; i < N; ++i) { cxy.push_back(corners[i].x); cxy.push_back(corners[i].y); swh.push_back(sizes[i].width); swh.push_back(sizes[i].height); }
