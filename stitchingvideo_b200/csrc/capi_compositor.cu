@@ -40,6 +40,8 @@ struct Camera {
     DevBuf feather_table;        // fixed-point map + distance, 8 B per warped pixel (sequence-constant)
     DevBuf mb_table;             // multi-band fast path: resolved bilinear taps per padded-rect pixel (8 B)
     size_t mb_tstep = 0;
+    DevBuf mbs_tiles, mbs_rec;   // the same taps tile-major + per-tile source boxes (streaming warp stage, kernels_mb_stream.cu)
+    int mbs_ntx = 0, mbs_nty = 0;
     size_t feather_tstep = 0;
     DevBuf feather_tiles;        // the same table tile-major (one 8 KB block per 128x8 panorama tile) for the streaming kernel
     DevBuf feather_rec;          // per tile block: source box record
@@ -117,6 +119,10 @@ struct sb_compositor {
     // flight: lowest latency; off when frames are pipelined over several slots: the small per-level launches of one
     // frame then overlap with the big kernels of the others, which is worth more than the saved launches), 0 / 1 = forced
     int mb_multilevel = -1;
+    bool mbs_ok = false;                         // streaming warp stage usable (whole-frame launches)
+    bool mbs_enabled = true;                     // tuning hook (set_fused 12 keeps the gather kernel)
+    DevBuf mbs_desc;                             // tile descriptors in schedule order with the ring plan
+    int mbs_n_tiles = 0;
     bool fused = true;                           // panorama-centric fused kernels (default); false = staged reference-shaped path
     // latency ("strip") mode: this handle produces padded-panorama columns [strip_x0, strip_x1)
     int strip_rank = 0, strip_world = 1, strip_x0 = 0, strip_x1 = 0;
@@ -396,6 +402,45 @@ int setup(sb_compositor *c)
                 SB_TRY(launch_mb_tap_table(cam.proj, cam.tl.x, cam.tl.y, cam.ww, cam.wh, cam.left, cam.top, cfg.src_size.width,
                                            cfg.src_size.height, static_cast<uint2 *>(cam.mb_table.p), cam.mb_tstep, cam.rw, cam.rh, s));
             }
+            // streaming warp stage: tile-major taps + source boxes per camera, descriptors of the tiles that intersect the
+            // level-0 column runs the pyramid needs (whole-frame launches)
+            {
+                const int full_w = c->wsum[0].v.cols;
+                std::vector<unsigned> list;
+                MbsSetup ms{};
+                bool ok = cfg.src_size.width * 3 <= 65535 && n <= 16;
+                for (int i = 0; i < n && ok; ++i) {
+                    Camera &cam = c->cams[i];
+                    cam.mbs_ntx = div_up(cam.rw, SB_FTT_W); cam.mbs_nty = div_up(cam.rh, SB_FTT_H);
+                    const size_t nt = (size_t)cam.mbs_ntx * cam.mbs_nty;
+                    if (nt >= (1u << 27)) { ok = false; break; }
+                    SB_TRY(cam.mbs_rec.ensure(sizeof(uint4) * nt));
+                    SB_TRY(cam.mbs_tiles.ensure(sizeof(uint2) * SB_FTT_W * SB_FTT_H * nt));
+                    SB_TRY(launch_mbs_camera_tiles(static_cast<const uint2 *>(cam.mb_table.p), cam.mb_tstep, cam.rw, cam.rh, cam.mbs_ntx, cam.mbs_nty,
+                                                   static_cast<uint4 *>(cam.mbs_rec.p), static_cast<uint2 *>(cam.mbs_tiles.p), s));
+                    ms.rec[i] = static_cast<const uint4 *>(cam.mbs_rec.p); ms.ntx[i] = cam.mbs_ntx;
+                    int cx[4], cmax = 0;
+                    double cols = 0;
+                    clip_runs(cam.g_runs[0], cam.rx, 0, full_w, cx, &cmax, &cols);
+                    for (int ty = 0; ty < cam.mbs_nty; ++ty)
+                        for (int tx = 0; tx < cam.mbs_ntx; ++tx) {
+                            const int a0 = tx * SB_FTT_W, a1 = a0 + SB_FTT_W;
+                            if ((a0 < cx[1] && a1 > cx[0]) || (a0 < cx[3] && a1 > cx[2])) list.push_back((unsigned)i | ((unsigned)(ty * cam.mbs_ntx + tx) << 4));
+                        }
+                }
+                c->mbs_ok = false;
+                if (ok && !list.empty()) {
+                    DevBuf dl;
+                    SB_TRY(dl.ensure(sizeof(unsigned) * list.size()));
+                    SB_CUDA(cudaMemcpyAsync(dl.p, list.data(), sizeof(unsigned) * list.size(), cudaMemcpyHostToDevice, s));
+                    c->mbs_n_tiles = (int)list.size();
+                    SB_TRY(c->mbs_desc.ensure(sizeof(uint4) * (1 + SB_FTT_MAXC) * list.size()));
+                    SB_TRY(launch_mbs_descriptors(ms, static_cast<const unsigned *>(dl.p), c->mbs_n_tiles, static_cast<uint4 *>(c->mbs_desc.p),
+                                                  fts_grid(c->mbs_n_tiles, c->sm_count), s));
+                    SB_CUDA(cudaStreamSynchronize(s));
+                    c->mbs_ok = true;
+                }
+            }
             c->mb_tile_mask.resize(nb + 1);
             for (int l = 0; l <= nb; ++l) {
                 MbBandGeom g{};
@@ -527,6 +572,26 @@ int mb_warp_stage(sb_compositor *c, Slot &s, const std::vector<DImage> &src, int
         bytes += img_bytes(src[i]) * std::min(1.0, cols / (double)std::min(cam.ww, src[i].cols)) + cols * cam.rh * (8 + 4);
     }
     if (mw == 0) return SB_OK;
+    bool aligned = true;                                     // cp.async source boxes: 16-byte aligned rows
+    for (int i = 0; i < n; ++i) aligned = aligned && (reinterpret_cast<uintptr_t>(src[i].data) & 15) == 0 && (src[i].step & 15) == 0;
+    if (c->mbs_ok && c->mbs_enabled && aligned && x0 <= 0 && x1 >= c->wsum[0].v.cols) {
+        MbStreamArgs sa{};
+        sa.n = n;
+        for (int i = 0; i < n; ++i) {
+            const Camera &cam = c->cams[i];
+            MbStreamCam &wc = sa.cam[i];
+            wc.src = src[i].ptr<uint8_t>(); wc.sstep = (unsigned)src[i].step;
+            wc.tiles = static_cast<const uint2 *>(cam.mbs_tiles.p);
+            wc.g0 = a.cam[i].g0; wc.gstep = (unsigned)a.cam[i].gstep;
+            wc.rw = cam.rw; wc.rh = cam.rh; wc.gain = cam.gain;
+            wc.gmap = a.cam[i].gmap; wc.gmstep = (unsigned)a.cam[i].gmstep;
+        }
+        sa.desc = static_cast<const uint4 *>(c->mbs_desc.p);
+        sa.bilin_lut = a.bilin_lut;
+        sa.n_tiles = c->mbs_n_tiles;
+        PROF("mb_warp", bytes, launch_mb_warp_stream(sa, c->cfg.comp_kind != SB_COMP_NO, c->sm_count, st));
+        return SB_OK;
+    }
     PROF("mb_warp", bytes, launch_mb_warp(a, c->cfg.comp_kind != SB_COMP_NO, mw, mh, st));
     return SB_OK;
 }
@@ -927,6 +992,7 @@ int sb_compositor_set_fused(sb_compositor *c, int fused)
         // pyramid level / with the multi-level launches forced
         c->feather_variant = fused == 10 ? 0 : 1; c->mb_variant = fused == 10 ? 0 : 1;
         c->mb_multilevel = fused == 12 ? 0 : fused == 13 ? 1 : -1;
+        c->mbs_enabled = fused != 12;                        // 12 also keeps the gather form of the warp stage
     }   // test/tuning hook: 10 / 11 select the kernel variant
     return SB_OK;
 }

@@ -108,6 +108,8 @@ int launch_fts_camera_tiles(const uint2 *table, size_t tstep, int ww, int wh, in
 // setup: the per-tile descriptors; *status != 0 -> the streaming kernel cannot be used for this calibration
 int launch_fts_descriptors(const FtsSetup &a, uint4 *desc, int *status, int grid, cudaStream_t s);   // grid = fts_grid(): the schedule and ring plan are per grid size
 int fts_grid(int n_tiles, int sm_count);
+// schedule order (descending cost) + ring plan of a descriptor array, in place
+int fts_schedule(uint4 *desc, int n_tiles, int grid, cudaStream_t s);
 int launch_feather_stream(const FeatherTmaArgs &a, bool apply_gain, bool out8, int sm_count, cudaStream_t s);
 
 // one camera as seen by k_band_fused at one pyramid level

@@ -85,6 +85,34 @@ struct MbBandHeadArgs {
 int launch_mb_pyr_tail(const MbPyrTailArgs &a, int sm_count, cudaStream_t s);
 int launch_mb_band_head(const MbBandHeadArgs &a, bool float_weights, int sm_count, cudaStream_t s);
 
+// ---- streaming form of the warp stage (kernels_mb_stream.cu, machinery of sb_stream.cuh) ----
+struct MbStreamCam {
+    const uint8_t *src;    // 8UC3 source frame, 16-byte aligned, sstep a multiple of 16
+    unsigned sstep;
+    const uint2 *tiles;    // tile-major tap entries of this camera's padded rect
+    uint32_t *g0;          // Gaussian level 0 of the padded warped image, RGBX bytes
+    unsigned gstep;
+    int rw, rh;
+    float gain;
+    const float *gmap;     // SB_COMP_GAIN_BLOCKS: per padded-rect pixel gain (null: the scalar gain)
+    unsigned gmstep;
+};
+struct MbStreamArgs {
+    int n;
+    MbStreamCam cam[SB_MAX_CAMERAS];
+    const uint4 *desc;     // per listed tile: 1 + SB_FTT_MAXC records, in schedule order, with the ring plan
+    const uint2 *bilin_lut;
+    int n_tiles;
+};
+struct MbsSetup {
+    const uint4 *rec[SB_MAX_CAMERAS];   // per camera, per tile of its padded rect: source box record
+    int ntx[SB_MAX_CAMERAS];
+};
+int launch_mbs_camera_tiles(const uint2 *table, size_t tstep, int rw, int rh, int ntx, int nty, uint4 *rec, uint2 *tiles, cudaStream_t s);
+// list_dev[t] = camera | tile block index << 4 for the tiles that have to be produced; grid = fts_grid()
+int launch_mbs_descriptors(const MbsSetup &a, const unsigned *list_dev, int n_tiles, uint4 *desc, int grid, cudaStream_t s);
+int launch_mb_warp_stream(const MbStreamArgs &a, bool apply_gain, int sm_count, cudaStream_t s);
+
 int launch_mb_tap_table(const ProjParams &p, int tl_x, int tl_y, int ww, int wh, int left, int top, int sw, int sh,
                         uint2 *table, size_t tstep, int rw, int rh, cudaStream_t s);
 int launch_mb_tile_mask(const MbBandGeom &g, bool float_weights, int lw, int lh, const void *wsum, size_t wsum_step, uint32_t *mask, cudaStream_t s);

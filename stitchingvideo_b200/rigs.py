@@ -18,6 +18,13 @@ RIGS = {
     # small rigs for fast parity tests (same construction, scaled down)
     "mini": dict(n=5, W=240, H=136, f=131.0, warper="spherical", scale=131.0, blender="multiband", gains=True),
     "mini_cyl": dict(n=5, W=240, H=136, f=131.0, warper="cylindrical", scale=131.0, blender="feather", gains=False),
+    # shape coverage of the streaming frame kernel: warper scale far below / above the focal length (source boxes too
+    # large for shared memory -> direct gathers; large boxes; tiny boxes) and heavy overlap (3+ cameras per tile)
+    "mini_cyl_s3": dict(n=5, W=480, H=272, f=262.0, warper="cylindrical", scale=262.0 / 3.0, blender="feather", gains=False),
+    "mini_cyl_s17": dict(n=5, W=480, H=272, f=262.0, warper="cylindrical", scale=262.0 / 1.7, blender="feather", gains=True),
+    "mini_cyl_up": dict(n=5, W=240, H=136, f=131.0, warper="cylindrical", scale=131.0 * 1.6, blender="feather", gains=False),
+    "mini_cyl_n9": dict(n=9, W=240, H=136, f=100.0, warper="cylindrical", scale=100.0, blender="feather", gains=True),
+    "mini_sph_n7": dict(n=7, W=240, H=136, f=110.0, warper="spherical", scale=140.0, blender="feather", gains=False),
 }
 GAINS = [0.95, 1.02, 1.00, 0.98, 1.05, 0.97, 1.03, 0.99]
 

@@ -282,7 +282,7 @@ def _compositor_case(gpu, rig, blender, weight_type=O.CV_32F, seams=False, gains
     Ks, Rs, spec = rigs.cameras(rig)
     size = (spec["W"], spec["H"])
     n = spec["n_used"]
-    g = [0.95, 1.02, 1.0, 0.98, 1.05][:n] if gains else None
+    g = ([0.95, 1.02, 1.0, 0.98, 1.05] * 2)[:n] if gains else None
     cal0 = P.Calibration(size, Ks, Rs, spec["warper"], spec["scale"])
     seam = None
     if seams:
@@ -317,6 +317,15 @@ def _compositor_case(gpu, rig, blender, weight_type=O.CV_32F, seams=False, gains
     dict(rig="mini_cyl", blender="feather", seams=True),
     dict(rig="mini_cyl", blender="no", gains=False),
     dict(rig="mini", blender="no", seams=True),
+    # streaming frame kernel shapes: direct gathers (boxes beyond shared memory), large / tiny boxes, 3 cameras per tile
+    dict(rig="mini_cyl_s3", blender="feather", gains=False),
+    dict(rig="mini_cyl_s3", blender="no", gains=False),
+    dict(rig="mini_cyl_s17", blender="feather", seams=True),
+    dict(rig="mini_cyl_s17", blender="multiband"),
+    dict(rig="mini_cyl_up", blender="feather", gains=False),
+    dict(rig="mini_cyl_n9", blender="feather"),
+    dict(rig="mini_cyl_n9", blender="no", gains=False),
+    dict(rig="mini_sph_n7", blender="feather", out16=True),
 ])
 def test_compositor_matches_reference_loop(gpu, case):
     _compositor_case(gpu, **case)
