@@ -62,9 +62,9 @@ __device__ __forceinline__ void fts_bilinear(unsigned lo0, unsigned hi0, unsigne
     if (!MINUS1) { bilinear_rgb(lo0, hi0, lo1, hi1, w, v0, v1, v2); return; }
     const unsigned m0 = __byte_perm(lo0, hi0, 0x5241), m1 = __byte_perm(lo1, hi1, 0x5241);
     const unsigned p0 = __byte_perm(lo0, lo1, 0x7430), p1 = __byte_perm(m0, m1, 0x5410), p2 = __byte_perm(m0, m1, 0x7632);
-    v0 = max((int)(__dp4a(p0, w.x, 0u) * 8u + __dp4a(p0, w.y, 0xfffffe00u)), 0) >> 10;
-    v1 = max((int)(__dp4a(p1, w.x, 0u) * 8u + __dp4a(p1, w.y, 0xfffffe00u)), 0) >> 10;
-    v2 = max((int)(__dp4a(p2, w.x, 0u) * 8u + __dp4a(p2, w.y, 0xfffffe00u)), 0) >> 10;
+    v0 = max((int)bilin_sum(p0, w, 0xfffffe00u), 0) >> 10;
+    v1 = max((int)bilin_sum(p1, w, 0xfffffe00u), 0) >> 10;
+    v2 = max((int)bilin_sum(p2, w, 0xfffffe00u), 0) >> 10;
 }
 // The producer side of a streaming frame kernel; called by every producer warp (pw = 0 .. SB_FTS_PRODUCER_WARPS-1) of a
 // persistent CTA of a grid of G.  Args: .desc, .n_tiles, .cam[i].{src, sstep, tiles}.  (ostep, obpp, mstep): the stage
