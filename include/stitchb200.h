@@ -257,7 +257,8 @@ int  sb_compositor_compose(sb_compositor *c, const sb_image *srcs, sb_image *pan
  * fused == 0: the staged, camera-by-camera path shaped like the reference's feed/blend calls.
  * Both give identical results; the staged path is kept as a cross-check.  Values >= 10 are tuning hooks that pick a
  * kernel variant of the fused path (10: CV_16S band kernels / one-pixel-per-thread feather, 11: default fast paths,
- * 12 / 13: multi-band fast path with one launch per pyramid level / with the multi-level launches forced). */
+ * 12 / 13: multi-band fast path with one launch per pyramid level / with the multi-level launches forced,
+ * 14: multi-band fast path with the direct-gather form of the warp stage instead of the streaming one). */
 int  sb_compositor_set_fused(sb_compositor *c, int fused);
 /* Pipelined form for throughput: up to `depth` frame sets in flight, each on its own stream/slot.
  * enqueue returns a slot id; wait blocks until that slot's pano has landed in the buffers given

@@ -989,10 +989,10 @@ int sb_compositor_set_fused(sb_compositor *c, int fused)
     SB_ASSERT(c);
     c->fused = fused != 0;
     if (fused >= 10) {   // 10: CV_16S band kernels / px1 feather; 11: fast paths (default); 12 / 13: fast paths with one launch per
-        // pyramid level / with the multi-level launches forced
+        // pyramid level / with the multi-level launches forced; 14: fast paths with the gather warp stage
         c->feather_variant = fused == 10 ? 0 : 1; c->mb_variant = fused == 10 ? 0 : 1;
         c->mb_multilevel = fused == 12 ? 0 : fused == 13 ? 1 : -1;
-        c->mbs_enabled = fused != 12;                        // 12 also keeps the gather form of the warp stage
+        c->mbs_enabled = fused != 14;                        // 14: default fast paths with the gather form of the multi-band warp stage
     }   // test/tuning hook: 10 / 11 select the kernel variant
     return SB_OK;
 }

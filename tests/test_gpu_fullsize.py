@@ -37,7 +37,7 @@ def test_full_size_frame_matches_oracle(gpu, rig):
         assert (roi[0], roi[1]) == cal.corners[i] and (roi[2], roi[3]) == cal.sizes[i]
     frames = [rigs.frame(rig, 1, i, smooth=1) for i in range(n)]
     ref, rmask = P.compose(cal, frames, blender=spec["blender"], num_bands=5, gains=spec["gain_values"])
-    for fused in (11, 12, 13, 10):
+    for fused in (11, 12, 13, 14, 10):
         comp.set_fused(fused)
         pano, mask = comp.compose(frames)
         same(pano, ref, "%s panorama (variant %d)" % (rig, fused))
