@@ -119,7 +119,9 @@ struct sb_compositor {
     // flight: lowest latency; off when frames are pipelined over several slots: the small per-level launches of one
     // frame then overlap with the big kernels of the others, which is worth more than the saved launches), 0 / 1 = forced
     int mb_multilevel = -1;
-    bool mbs_ok = false;                         // streaming warp stage usable (whole-frame launches)
+    bool mbs_tables = false;                     // tile-major taps + source boxes built
+    bool mbs_ok = false;                         // streaming warp stage usable for panorama columns [mbs_x0, mbs_x1)
+    int mbs_x0 = 0, mbs_x1 = 0;
     bool mbs_enabled = true;                     // tuning hook (set_fused 12 keeps the gather kernel)
     DevBuf mbs_desc;                             // tile descriptors in schedule order with the ring plan
     int mbs_n_tiles = 0;
@@ -271,6 +273,42 @@ void clip_runs(const std::array<int, 4> &g, int rx, int x0, int x1, int out[4], 
     }
 }
 
+// Tile schedule of the streaming warp stage (kernels_mb_stream.cu) for the panorama columns [x0, x1): the tiles of every
+// camera's padded rect that intersect the level-0 column runs the pyramid needs there, their descriptors in schedule
+// order with the shared-memory ring plan.  Whole frame at setup; a rank's strip (+ halo) in latency mode.
+int build_mbs_schedule(sb_compositor *c, int x0, int x1, cudaStream_t s)
+{
+    c->mbs_ok = false;
+    if (!c->mbs_tables) return SB_OK;
+    const int n = c->cfg.n_cameras;
+    std::vector<unsigned> list;
+    MbsSetup ms{};
+    for (int i = 0; i < n; ++i) {
+        const Camera &cam = c->cams[i];
+        ms.rec[i] = static_cast<const uint4 *>(cam.mbs_rec.p); ms.ntx[i] = cam.mbs_ntx;
+        int cx[4], cmax = 0;
+        double cols = 0;
+        clip_runs(cam.g_runs[0], cam.rx, x0, x1, cx, &cmax, &cols);
+        for (int ty = 0; ty < cam.mbs_nty; ++ty)
+            for (int tx = 0; tx < cam.mbs_ntx; ++tx) {
+                const int a0 = tx * SB_FTT_W, a1 = a0 + SB_FTT_W;
+                if ((a0 < cx[1] && a1 > cx[0]) || (a0 < cx[3] && a1 > cx[2])) list.push_back((unsigned)i | ((unsigned)(ty * cam.mbs_ntx + tx) << 4));
+            }
+    }
+    if (list.empty()) return SB_OK;
+    DevBuf dl;
+    SB_TRY(dl.ensure(sizeof(unsigned) * list.size()));
+    SB_CUDA(cudaMemcpyAsync(dl.p, list.data(), sizeof(unsigned) * list.size(), cudaMemcpyHostToDevice, s));
+    c->mbs_n_tiles = (int)list.size();
+    SB_TRY(c->mbs_desc.ensure(sizeof(uint4) * (1 + SB_FTT_MAXC) * list.size()));
+    SB_TRY(launch_mbs_descriptors(ms, static_cast<const unsigned *>(dl.p), c->mbs_n_tiles, static_cast<uint4 *>(c->mbs_desc.p),
+                                  fts_grid(c->mbs_n_tiles, c->sm_count), s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    c->mbs_x0 = x0; c->mbs_x1 = x1;
+    c->mbs_ok = true;
+    return SB_OK;
+}
+
 // calibration-time work: geometry, tables, masks, weights
 int setup(sb_compositor *c)
 {
@@ -402,12 +440,8 @@ int setup(sb_compositor *c)
                 SB_TRY(launch_mb_tap_table(cam.proj, cam.tl.x, cam.tl.y, cam.ww, cam.wh, cam.left, cam.top, cfg.src_size.width,
                                            cfg.src_size.height, static_cast<uint2 *>(cam.mb_table.p), cam.mb_tstep, cam.rw, cam.rh, s));
             }
-            // streaming warp stage: tile-major taps + source boxes per camera, descriptors of the tiles that intersect the
-            // level-0 column runs the pyramid needs (whole-frame launches)
+            // streaming warp stage: tile-major taps + source boxes per camera, then the tile schedule for whole-frame launches
             {
-                const int full_w = c->wsum[0].v.cols;
-                std::vector<unsigned> list;
-                MbsSetup ms{};
                 bool ok = cfg.src_size.width * 3 <= 65535 && n <= 16;
                 for (int i = 0; i < n && ok; ++i) {
                     Camera &cam = c->cams[i];
@@ -418,28 +452,9 @@ int setup(sb_compositor *c)
                     SB_TRY(cam.mbs_tiles.ensure(sizeof(uint2) * SB_FTT_W * SB_FTT_H * nt));
                     SB_TRY(launch_mbs_camera_tiles(static_cast<const uint2 *>(cam.mb_table.p), cam.mb_tstep, cam.rw, cam.rh, cam.mbs_ntx, cam.mbs_nty,
                                                    static_cast<uint4 *>(cam.mbs_rec.p), static_cast<uint2 *>(cam.mbs_tiles.p), s));
-                    ms.rec[i] = static_cast<const uint4 *>(cam.mbs_rec.p); ms.ntx[i] = cam.mbs_ntx;
-                    int cx[4], cmax = 0;
-                    double cols = 0;
-                    clip_runs(cam.g_runs[0], cam.rx, 0, full_w, cx, &cmax, &cols);
-                    for (int ty = 0; ty < cam.mbs_nty; ++ty)
-                        for (int tx = 0; tx < cam.mbs_ntx; ++tx) {
-                            const int a0 = tx * SB_FTT_W, a1 = a0 + SB_FTT_W;
-                            if ((a0 < cx[1] && a1 > cx[0]) || (a0 < cx[3] && a1 > cx[2])) list.push_back((unsigned)i | ((unsigned)(ty * cam.mbs_ntx + tx) << 4));
-                        }
                 }
-                c->mbs_ok = false;
-                if (ok && !list.empty()) {
-                    DevBuf dl;
-                    SB_TRY(dl.ensure(sizeof(unsigned) * list.size()));
-                    SB_CUDA(cudaMemcpyAsync(dl.p, list.data(), sizeof(unsigned) * list.size(), cudaMemcpyHostToDevice, s));
-                    c->mbs_n_tiles = (int)list.size();
-                    SB_TRY(c->mbs_desc.ensure(sizeof(uint4) * (1 + SB_FTT_MAXC) * list.size()));
-                    SB_TRY(launch_mbs_descriptors(ms, static_cast<const unsigned *>(dl.p), c->mbs_n_tiles, static_cast<uint4 *>(c->mbs_desc.p),
-                                                  fts_grid(c->mbs_n_tiles, c->sm_count), s));
-                    SB_CUDA(cudaStreamSynchronize(s));
-                    c->mbs_ok = true;
-                }
+                c->mbs_tables = ok;
+                SB_TRY(build_mbs_schedule(c, 0, c->wsum[0].v.cols, s));
             }
             c->mb_tile_mask.resize(nb + 1);
             for (int l = 0; l <= nb; ++l) {
@@ -574,7 +589,7 @@ int mb_warp_stage(sb_compositor *c, Slot &s, const std::vector<DImage> &src, int
     if (mw == 0) return SB_OK;
     bool aligned = true;                                     // cp.async source boxes: 16-byte aligned rows
     for (int i = 0; i < n; ++i) aligned = aligned && (reinterpret_cast<uintptr_t>(src[i].data) & 15) == 0 && (src[i].step & 15) == 0;
-    if (c->mbs_ok && c->mbs_enabled && aligned && x0 <= 0 && x1 >= c->wsum[0].v.cols) {
+    if (c->mbs_ok && c->mbs_enabled && aligned && c->mbs_x0 <= std::max(x0, 0) && std::min(x1, c->wsum[0].v.cols) <= c->mbs_x1) {
         MbStreamArgs sa{};
         sa.n = n;
         for (int i = 0; i < n; ++i) {
@@ -1272,7 +1287,9 @@ int sb_compositor_set_strip(sb_compositor *c, int rank, int world)
     strip_bounds(c, rank, world, &c->strip_x0, &c->strip_x1);
     c->fused = true; c->mb_variant = 1;
     strip_plan(c);
-    return SB_OK;
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    return build_mbs_schedule(c, c->g_lo[0], c->g_hi[0], c->setup_stream);
 }
 
 int sb_compositor_set_strip_halo(sb_compositor *c, int recompute)
@@ -1281,7 +1298,9 @@ int sb_compositor_set_strip_halo(sb_compositor *c, int recompute)
     for (auto &s : c->slots) if (s.busy) return fail(SB_ERR_ASSERT, "set_strip_halo with frames in flight");
     c->strip_recompute = recompute != 0;
     strip_plan(c);
-    return SB_OK;
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    return build_mbs_schedule(c, c->g_lo[0], c->g_hi[0], c->setup_stream);
 }
 
 int sb_compositor_strip_compose(sb_compositor *c, const sb_image *srcs)
