@@ -17,6 +17,7 @@ collective on the data path ("scaling": "weak").
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -70,6 +71,20 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self.stop_flag = index, [], False
 
     def run(self):
+        try:                                             # NVML directly (what nvidia-smi reads): no process spawn per sample
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            bits = [("hw_slowdown", pynvml.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", pynvml.nvmlClocksThrottleReasonSwPowerCap)]
+            while not self.stop_flag:
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                  "%.1f" % (pynvml.nvmlDeviceGetPowerUsage(h) / 1e3)] + ["Active" if r & b else "Not Active" for _, b in bits])
+                time.sleep(0.05)
+            return
+        except Exception:                                # noqa: BLE001 - fall back to the nvidia-smi command line of the recipe
+            pass
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
@@ -97,12 +112,14 @@ def make_frames(rig, n_sets, n_cams, rank):
 
 def pipelined(comp, frame_sets, outs, steps, depth):
     """steps frames through `depth` in-flight slots; returns the slot list (all waited)."""
+    # (a video loop cycles through a few input / output buffers: their argument blocks are built once)
+    period = len(frame_sets) * len(outs) // math.gcd(len(frame_sets), len(outs))
+    calls = [comp.prepare_call(frame_sets[k % len(frame_sets)], *outs[k % len(outs)]) for k in range(min(period, steps))]
     slots = []
     for k in range(steps):
         if k >= depth:
             comp.wait(slots[k - depth])
-        pano, mask = outs[k % len(outs)]
-        slots.append(comp.enqueue(frame_sets[k % len(frame_sets)], pano, mask))
+        slots.append(comp.enqueue_prepared(calls[k % len(calls)]))
     for s in slots[-depth:]:
         comp.wait(s)
     return slots

@@ -818,6 +818,25 @@ class Compositor:
         _check(lib().sb_compositor_enqueue(self._h, arr, C.byref(ip), C.byref(im) if im is not None else None, C.byref(slot)))
         return slot.value
 
+    def prepare_call(self, frames, pano, pano_mask=None):
+        """The argument block of enqueue(frames, pano, pano_mask), built once for buffers that are reused frame after
+        frame (a video loop cycles through a few input / output buffers): enqueue_prepared then costs one C call."""
+        arr, keep = self._srcs(frames)
+        if pano is None:
+            ip, k0 = SbImage(None, 0, 0, self.output_type, 0, -1), None
+        else:
+            ip, k0 = _image(pano)
+        im, k1 = _image(pano_mask) if pano_mask is not None else (None, None)
+        return (arr, C.byref(ip), C.byref(im) if im is not None else None, C.c_int(-1), ip if pano is None else None, (keep, ip, im, k0, k1))
+
+    def enqueue_prepared(self, call):
+        lent = call[4]
+        if lent is not None:                         # pano=None: the library lends the slot's buffer through this struct every time
+            lent.data, lent.rows, lent.cols, lent.step, lent.device = None, 0, 0, 0, -1
+            self.last_lent = lent
+        _check(_lib.sb_compositor_enqueue(self._h, call[0], call[1], call[2], C.byref(call[3])))
+        return call[3].value
+
     def wait(self, slot):
         _check(lib().sb_compositor_wait(self._h, slot))
 
