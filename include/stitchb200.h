@@ -150,6 +150,12 @@ int  sb_comp_set_gain_maps(sb_comp *c, const sb_image *maps, int n);
  * agree with the reference to ~1e-12 relative, not bit for bit.  A = n x n is dense as in the reference (blocks: n =
  * total block count; the LU is the reference's O(n^3)). */
 int  sb_comp_feed(sb_comp *c, const sb_point *corners, const sb_image *images, const sb_image *masks, int n);
+/* The host half of feed on its own (exposure_compensate.cpp:128-144): gains from the pair statistics.  Pairs (i <= j)
+ * each once, N = max(1, overlap count), Iij / Iji = mean intensity of image i / j inside the overlap.  Up to 512 unknowns
+ * it is the reference's dense LU (cv::solve); larger systems (the block compensator: one unknown per block) are solved
+ * sparse by preconditioned conjugate gradients to 1e-15 relative residual instead of a dense O(n^3) factorisation.
+ * Needs no device. */
+int  sb_gain_solve(int n, int n_pairs, const int *pi, const int *pj, const double *N, const double *Iij, const double *Iji, double *gains);
 /* BlocksGainCompensator(bl_width = 32, bl_height = 32) ctor arguments (exposure_compensate.hpp:92) */
 int  sb_comp_set_block_size(sb_comp *c, int bl_width, int bl_height);
 /* number of gains / gain maps the compensator holds after feed or set */

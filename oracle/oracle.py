@@ -263,6 +263,14 @@ def gain_overlap_stats(corners, images, masks, mask_vals=None):
     return N, I
 
 
+def gain_solve(N, I):
+    """exposure_compensate.cpp:128-144 on dense N (int32 n x n) and I (float64 n x n) -> gains"""
+    N, I = np.ascontiguousarray(N, np.int32), np.ascontiguousarray(I, np.float64)
+    g = np.zeros(N.shape[0], np.float64)
+    _chk(lib().so_gain_solve(N.shape[0], N.ctypes.data_as(C.c_void_p), I.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p)), "gain_solve")
+    return g
+
+
 def gain_feed(corners, images, masks, mask_vals=None):
     """GainCompensator::feed (exposure_compensate.cpp:76-147) -> gains (float64)"""
     n = len(images)

@@ -97,6 +97,7 @@ API = {
     "sb_comp_set_gain_maps": (C.c_int, [C.c_void_p, _P(SbImage), C.c_int]),
     "sb_comp_apply": (C.c_int, [C.c_void_p, C.c_int, SbPoint, _P(SbImage), _P(SbImage)]),
     "sb_comp_feed": (C.c_int, [C.c_void_p, _P(SbPoint), _P(SbImage), _P(SbImage), C.c_int]),
+    "sb_gain_solve": (C.c_int, [C.c_int, C.c_int, _P(C.c_int), _P(C.c_int), _P(C.c_double), _P(C.c_double), _P(C.c_double), _P(C.c_double)]),
     "sb_comp_set_block_size": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "sb_comp_num_gains": (C.c_int, [C.c_void_p]),
     "sb_comp_gain_map_size": (C.c_int, [C.c_void_p, C.c_int, _P(SbSize)]),
@@ -519,6 +520,17 @@ class BlocksGainCompensator(ExposureCompensator):
             _check(lib().sb_comp_get_gain_map(self._h, i, C.byref(im)))
             out.append(m)
         return out
+
+
+def gain_solve(n, pi, pj, N, Iij, Iji):
+    """sb_gain_solve: the normal equations of GainCompensator::feed (exposure_compensate.cpp:128-144) from pair statistics"""
+    pi, pj = np.ascontiguousarray(pi, np.int32), np.ascontiguousarray(pj, np.int32)
+    N, Iij, Iji = (np.ascontiguousarray(a, np.float64) for a in (N, Iij, Iji))
+    g = np.zeros(n, np.float64)
+    d = _P(C.c_double)
+    _check(lib().sb_gain_solve(n, len(pi), pi.ctypes.data_as(_P(C.c_int)), pj.ctypes.data_as(_P(C.c_int)), N.ctypes.data_as(d),
+                               Iij.ctypes.data_as(d), Iji.ctypes.data_as(d), g.ctypes.data_as(d)))
+    return g
 
 
 def refine_seam_mask(seam_mask, mask_warped, device=0):

@@ -99,3 +99,27 @@ def test_compositor_resumes_from_calibration_file(gpu, tmp_path, rig):
     assert np.array_equal(pano, pano2) and np.array_equal(mask, mask2)
     again.save_calibration(path + "2")                               # and the resumed one saves the same file
     assert open(path, "rb").read() == open(path + "2", "rb").read()
+
+
+@pytest.mark.parametrize("n,deg", [(5, 2), (40, 3), (512, 4), (513, 4), (3000, 6)])
+def test_gain_solve_matches_the_reference_dense_solve(n, deg):
+    """sb_gain_solve (host-only): the reference's normal equations + dense LU up to 512 unknowns, sparse conjugate gradients
+    beyond (the block compensator's sizes) — against the oracle's dense cv::solve restatement on a random overlap graph."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(n)
+    pairs = {(i, i) for i in range(n)}
+    for i in range(n):
+        for j in rng.integers(0, n, deg):
+            if i != j:
+                pairs.add((min(i, int(j)), max(i, int(j))))
+    pi, pj = np.array(sorted(pairs), np.int32).T
+    cnt = rng.integers(0, 1024, len(pi))
+    cnt[rng.random(len(pi)) < 0.1] = 0                                   # empty intersections count as 1 (max(1, countNonZero))
+    Nk = np.maximum(cnt, 1).astype(np.float64)
+    Iij, Iji = rng.uniform(20, 300, len(pi)), rng.uniform(20, 300, len(pi))
+    N, I = np.zeros((n, n), np.int32), np.zeros((n, n), np.float64)
+    N[pi, pj] = Nk; N[pj, pi] = Nk
+    I[pi, pj] = Iij; I[pj, pi] = Iji
+    ref = O.gain_solve(N, I)
+    got = capi.gain_solve(n, pi, pj, Nk, Iij, Iji)
+    np.testing.assert_allclose(got, ref, rtol=1e-11, atol=0)
