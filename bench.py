@@ -435,7 +435,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=32, help="frame sets per step")
-    ap.add_argument("--depth", type=int, default=4, help="frame sets in flight (slots)")
+    ap.add_argument("--depth", type=int, default=None, help="frame sets in flight (slots); default 4 for the one-kernel feather workload, 8 for the "
+                    "multi-band ones (lets the launch-latency-bound coarse pyramid levels of several frames overlap: C3 +9 %)")
     ap.add_argument("--frame-sets", type=int, default=8, help="distinct synthetic frame sets rotated through (8 x 31 MB > L2)")
     ap.add_argument("--profile-frames", type=int, default=5)
     ap.add_argument("--cpu-frames", type=int, default=4)
@@ -443,6 +444,8 @@ def main():
     ap.add_argument("--variant", type=int, default=None, choices=[0, 1, 2], help="fused kernel variant: 10 + v is passed to set_fused (default: library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.depth is None:
+        args.depth = 4 if args.workload == "c2" else 8
     if args.impl == "reference":
         if args.steps == 20:
             args.steps, args.warmup = 4, 3
