@@ -43,7 +43,7 @@ struct Camera {
     DevBuf mbs_tiles, mbs_rec;   // the same taps tile-major + per-tile source boxes (streaming warp stage, kernels_mb_stream.cu)
     int mbs_ntx = 0, mbs_nty = 0;
     size_t feather_tstep = 0;
-    DevBuf feather_tiles;        // the same table tile-major (one 8 KB block per 128x8 panorama tile) for the streaming kernel
+    DevBuf feather_tiles;        // the same table tile-major (one 8 KB block per 32x32 panorama tile) for the streaming kernel
     DevBuf feather_rec;          // per tile block: source box record
     int ftx0 = 0, fty0 = 0, fntx = 0, fnty = 0;
     // panorama(-level) column ranges that hold non-zero weights, per level: [s0,s1) U [s2,s3)
@@ -106,9 +106,9 @@ struct sb_compositor {
     cudaEvent_t marks[2] = {nullptr, nullptr};
     bool feather_fast = false;                   // every weighted pixel's taps fit the resolved-tap table
     float stream_sharpness = 0.02f;              // feather: FeatherBlender::sharpness_; Blender::NO: 1/255 (see setup)
-    bool feather_tma = false;                    // <= SB_FTT_MAXC cameras per 128x8 tile: persistent table-streaming kernel
+    bool feather_tma = false;                    // <= SB_FTT_MAXC cameras per 32x32 tile: persistent table-streaming kernel
     int feather_variant = 1;                     // 1: k_feather_tma, 0: k_feather_fused_px1
-    DevBuf tma_desc;                             // per 128x8 panorama tile: camera slots + source boxes
+    DevBuf tma_desc;                             // per 32x32 panorama tile: camera slots + source boxes, schedule order, ring plan
     int sm_count = 148;
     DevBuf bilin_lut;                            // 1024 x uint2 bilinear product weights (sb_device.cuh)
     int mb_variant = 1;                          // 1: RGBX fast path, 0: CV_16S band kernels
