@@ -18,7 +18,6 @@
 //     No consumer thread ever waits on a global load.
 #include <algorithm>
 #include <climits>
-#include <cstdlib>
 #include <vector>
 
 #include "sb_stream.cuh"
@@ -208,12 +207,10 @@ int fts_schedule(uint4 *desc, int n_tiles, int grid, cudaStream_t s)
         const int nc = (int)(x & 3u);
         return nc == 0 ? 0 : (x & 4u) ? 1 : 1 + nc;
     };
-    if (!getenv("SB_FTS_NO_SORT")) {                        // (measurement knob: row-major tile order)
-        std::stable_sort(order.begin(), order.end(), [&](int l, int r) { return cost(l) > cost(r); });
-        // ... except that every CTA's FIRST tile is a cheap one: the first wave of copies (grid x producer warps tiles at
-        // once) is what the consumers wait for at kernel start, and a one-camera tile is 2-3x fewer bytes
-        if (n_tiles >= 2 * grid && !getenv("SB_FTS_NO_ROTATE")) std::rotate(order.begin(), order.end() - grid, order.end());
-    }
+    std::stable_sort(order.begin(), order.end(), [&](int l, int r) { return cost(l) > cost(r); });
+    // ... except that every CTA's FIRST tile is a cheap one: the first wave of copies (grid x producer warps tiles at once)
+    // is what the consumers wait for at kernel start, and a one-camera tile is 2-3x fewer bytes
+    if (n_tiles >= 2 * grid) std::rotate(order.begin(), order.end() - grid, order.end());
     for (int t = 0; t < n_tiles; ++t)
         for (size_t j = 0; j < per; ++j) o[(size_t)t * per + j] = h[(size_t)order[t] * per + j];
     SB_CUDA(cudaMemcpyAsync(desc, o.data(), o.size() * sizeof(uint4), cudaMemcpyHostToDevice, s));

@@ -41,7 +41,7 @@ struct FeatherFusedArgs {
 };
 
 // ---- persistent, warp-specialised streaming feather kernel (kernels_feather_tma.cu) ----
-// Shape knobs (compile-time; -DSB_CFG_* builds the variants scratch/feather_variants.sh times against each other)
+// Shape knobs (compile-time, -DSB_CFG_*: round 1 timed 32x16 / 32x32 / 32x64 tiles with 8 or 16 consumer warps; 32x32 x 16 won)
 #ifndef SB_CFG_FTT_H
 #define SB_CFG_FTT_H 32
 #endif
