@@ -187,6 +187,11 @@ int  sb_blender_num_bands(const sb_blender *b);                      /* blenders
 int  sb_blender_set_num_bands(sb_blender *b, int n);                 /* blenders.hpp:102 */
 float sb_blender_sharpness(const sb_blender *b);                     /* blenders.hpp:77 */
 int  sb_blender_set_sharpness(sb_blender *b, float s);               /* blenders.hpp:78 */
+/* FeatherBlender::createWeightMaps(masks, corners, weight_maps) (blenders.hpp:80-81, blenders.cpp:158-186): the feather
+ * weights of a fixed set of images normalised by their sum over the result ROI ("final image can be obtained by simple
+ * weighting of the source images").  masks CV_8UC1; weight_maps: n caller-allocated CV_32FC1 images of the masks' sizes
+ * (host or device); *dst_roi = resultRoi(corners, masks).  Feather blenders only.  Bit-exact. */
+int  sb_blender_create_weight_maps(sb_blender *b, const sb_image *masks, const sb_point *corners, int n, sb_image *weight_maps, sb_rect *dst_roi);
 /* Blender::prepare(corners, sizes) (blenders.cpp:65-68) / virtual prepare(Rect) (:71-78,115-120,203-233) */
 int  sb_blender_prepare(sb_blender *b, const sb_point *corners, const sb_size *sizes, int n);
 int  sb_blender_prepare_rect(sb_blender *b, sb_rect dst_roi);

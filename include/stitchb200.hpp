@@ -340,6 +340,21 @@ public:
     explicit FeatherBlender(float sharpness = 0.02f, int device = 0) : Blender(SB_BLEND_FEATHER, 5, SB_32F, sharpness, device) {}
     float sharpness() const { return sb_blender_sharpness(h_); }
     void setSharpness(float v) { check(sb_blender_set_sharpness(h_, v)); }
+    // blenders.hpp:80-81: weight maps for a fixed set of source images by their masks and top-left corners
+    Rect createWeightMaps(const std::vector<Mat> &masks, const std::vector<Point> &corners, std::vector<Mat> &weight_maps)
+    {
+        if (masks.size() != corners.size() || masks.empty()) throw Exception(SB_ERR_ASSERT, "masks.size() == corners.size()");
+        std::vector<sb_image> m, w;
+        std::vector<sb_point> c;
+        weight_maps.resize(masks.size());
+        for (size_t i = 0; i < masks.size(); ++i) {
+            weight_maps[i].create(masks[i].rows, masks[i].cols, SB_32FC1);
+            m.push_back(masks[i].c()); w.push_back(weight_maps[i].c()); c.push_back(sb_point{corners[i].x, corners[i].y});
+        }
+        sb_rect r;
+        check(sb_blender_create_weight_maps(h_, m.data(), c.data(), (int)masks.size(), w.data(), &r));
+        return Rect(r.x, r.y, r.width, r.height);
+    }
 };
 class MultiBandBlender : public Blender {
 public:

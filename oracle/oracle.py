@@ -297,6 +297,17 @@ def blocks_gain_feed(corners, images, masks, bl_width=32, bl_height=32):
     return maps
 
 
+def feather_create_weight_maps(masks, corners, sharpness=0.02):
+    """FeatherBlender::createWeightMaps (blenders.cpp:158-186) -> (dst_roi (x, y, w, h), list of float32 weight maps)"""
+    masks = [np.ascontiguousarray(m, np.uint8) for m in masks]
+    maps = [np.zeros(m.shape, np.float32) for m in masks]
+    cxy = np.ascontiguousarray(np.asarray(corners, np.int32).reshape(-1))
+    roi = (C.c_int * 4)()
+    _chk(lib().so_feather_create_weight_maps(len(masks), _mat_array(masks), cxy.ctypes.data_as(C.c_void_p), C.c_float(sharpness),
+                                             _mat_array(maps), roi), "createWeightMaps")
+    return tuple(roi), maps
+
+
 def sep_filter3(src, k0=0.5, k1=0.25):
     src = np.ascontiguousarray(src, np.float32)
     dst = np.empty_like(src)

@@ -283,3 +283,40 @@ int so_refine_seam_mask(const so_mat *seam_mask, const so_mat *mask_warped, so_m
     free(dil.data); free(rs.data);
     return rc;
 }
+
+/* FeatherBlender::createWeightMaps (blenders.cpp:158-186): per-image feather weights normalised by their sum over the
+ * result ROI, so that the final image is a plain weighting of the sources.  Note that `tmp` in the reference is a VIEW
+ * of weights_sum: setTo(1, tmp < eps) writes the 1 back into the shared sum before the next image is divided.
+ * cv::divide on CV_32F: src2 != 0 ? src1 / src2 : 0 (computed in double and rounded once = the IEEE float quotient). */
+int so_feather_create_weight_maps(int n, const so_mat *masks, const int *corners_xy, float sharpness, so_mat *weight_maps, int roi_xywh[4])
+{
+    int *sizes = (int *)malloc(sizeof(int) * 2 * n);
+    for (int i = 0; i < n; ++i) {
+        if (so_create_weight_map(&masks[i], sharpness, &weight_maps[i]) != 0) { free(sizes); return -1; }
+        sizes[2 * i] = masks[i].cols; sizes[2 * i + 1] = masks[i].rows;
+    }
+    so_result_roi(corners_xy, sizes, n, roi_xywh);
+    free(sizes);
+    int W = roi_xywh[2], H = roi_xywh[3];
+    float *sum = (float *)calloc((size_t)W * H, sizeof(float));
+    for (int i = 0; i < n; ++i) {
+        int ox = corners_xy[2 * i] - roi_xywh[0], oy = corners_xy[2 * i + 1] - roi_xywh[1];
+        for (int y = 0; y < weight_maps[i].rows; ++y) {
+            const float *w = ROW(&weight_maps[i], const float, y);
+            for (int x = 0; x < weight_maps[i].cols; ++x) sum[(size_t)(oy + y) * W + ox + x] += w[x];
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        int ox = corners_xy[2 * i] - roi_xywh[0], oy = corners_xy[2 * i + 1] - roi_xywh[1];
+        for (int y = 0; y < weight_maps[i].rows; ++y) {
+            float *w = ROW(&weight_maps[i], float, y);
+            for (int x = 0; x < weight_maps[i].cols; ++x) {
+                float *t = &sum[(size_t)(oy + y) * W + ox + x];
+                if (*t < 1.1920928955078125e-07f) *t = 1.f;
+                w[x] = *t != 0 ? w[x] / *t : 0.f;
+            }
+        }
+    }
+    free(sum);
+    return 0;
+}

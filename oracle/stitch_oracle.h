@@ -134,6 +134,7 @@ int  so_blocks_gain_feed(int n, const int *corners_xy, const so_mat *images, con
                          int bl_width, int bl_height, so_mat *gain_maps);   /* :165-222 */
 int  so_dilate3x3_8u(const so_mat *src, so_mat *dst);
 int  so_resize_linear_8u(const so_mat *src, so_mat *dst);
+int  so_feather_create_weight_maps(int n, const so_mat *masks, const int *corners_xy, float sharpness, so_mat *weight_maps, int roi_xywh[4]);   /* blenders.cpp:158-186 */
 int  so_refine_seam_mask(const so_mat *seam_mask, const so_mat *mask_warped, so_mat *out);   /* stitcher.cpp:291-294 */
 
 const char *so_version(void);

@@ -115,6 +115,7 @@ API = {
     "sb_blender_set_num_bands": (C.c_int, [C.c_void_p, C.c_int]),
     "sb_blender_sharpness": (C.c_float, [C.c_void_p]),
     "sb_blender_set_sharpness": (C.c_int, [C.c_void_p, C.c_float]),
+    "sb_blender_create_weight_maps": (C.c_int, [C.c_void_p, _P(SbImage), _P(SbPoint), C.c_int, _P(SbImage), _P(SbRect)]),
     "sb_blender_prepare": (C.c_int, [C.c_void_p, _P(SbPoint), _P(SbSize), C.c_int]),
     "sb_blender_prepare_rect": (C.c_int, [C.c_void_p, SbRect]),
     "sb_blender_feed": (C.c_int, [C.c_void_p, _P(SbImage), _P(SbImage), SbPoint]),
@@ -625,6 +626,20 @@ class FeatherBlender(Blender):
 
     def setSharpness(self, v):
         _check(lib().sb_blender_set_sharpness(self._h, C.c_float(v)))
+
+    def createWeightMaps(self, masks, corners):
+        """FeatherBlender::createWeightMaps (blenders.hpp:80-81, blenders.cpp:158-186) -> (dst_roi (x, y, w, h), weight_maps)"""
+        n = len(masks)
+        if len(corners) != n or n == 0:
+            raise StitchError(SB_ERR_ASSERT, "masks.size() == corners.size()")
+        mk = [_image(np.ascontiguousarray(m, np.uint8)) for m in masks]
+        maps = [np.empty((m[0].rows, m[0].cols), np.float32) for m in mk]
+        wm = [_image(w) for w in maps]
+        am, aw = (SbImage * n)(*[x[0] for x in mk]), (SbImage * n)(*[x[0] for x in wm])
+        pts = (SbPoint * n)(*[SbPoint(int(c[0]), int(c[1])) for c in corners])
+        roi = SbRect()
+        _check(lib().sb_blender_create_weight_maps(self._h, am, pts, n, aw, C.byref(roi)))
+        return (roi.x, roi.y, roi.width, roi.height), maps
 
 
 class MultiBandBlender(Blender):

@@ -291,6 +291,48 @@ int sb_create_weight_map(const sb_image *mask, float sharpness, sb_image *weight
     return SB_OK;
 }
 
+// FeatherBlender::createWeightMaps (blenders.hpp:80-81, blenders.cpp:158-186)
+int sb_blender_create_weight_maps(sb_blender *b, const sb_image *masks, const sb_point *corners, int n, sb_image *weight_maps, sb_rect *dst_roi)
+{
+    SB_ASSERT(b && masks && corners && weight_maps && dst_roi && n > 0);
+    SB_ASSERT(b->kind == SB_BLEND_FEATHER);
+    DeviceGuard g(b->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    std::vector<sb_size> sizes(n);
+    for (int i = 0; i < n; ++i) {
+        SB_TRY(check_image(&masks[i], "mask"));
+        SB_ASSERT(masks[i].type == SB_8UC1);                            // blenders.cpp:429
+        SB_ASSERT(weight_maps[i].data && weight_maps[i].type == SB_32FC1 && weight_maps[i].rows == masks[i].rows && weight_maps[i].cols == masks[i].cols);
+        sizes[i] = sb_size{masks[i].cols, masks[i].rows};
+    }
+    int tlx = INT32_MAX, tly = INT32_MAX, brx = INT32_MIN, bry = INT32_MIN;       // resultRoi(corners, masks), util.cpp:118-140
+    for (int i = 0; i < n; ++i) {
+        tlx = std::min(tlx, corners[i].x); tly = std::min(tly, corners[i].y);
+        brx = std::max(brx, corners[i].x + sizes[i].width); bry = std::max(bry, corners[i].y + sizes[i].height);
+    }
+    const sb_rect roi = {tlx, tly, brx - tlx, bry - tly};
+    std::vector<DevImage> stage(n), wown(n);
+    std::vector<DImage> w(n);
+    DevImage sum;
+    SB_TRY(sum.create_zero(roi.height, roi.width, SB_32FC1, b->stream));
+    for (int i = 0; i < n; ++i) {
+        DImage dm;
+        SB_TRY(to_device(masks[i], stage[i], b->stream, &dm));
+        if (weight_maps[i].device >= 0) { w[i].data = weight_maps[i].data; w[i].rows = dm.rows; w[i].cols = dm.cols; w[i].type = SB_32FC1; w[i].step = weight_maps[i].step; }
+        else { SB_TRY(wown[i].create(dm.rows, dm.cols, SB_32FC1)); w[i] = wown[i].v; }
+        SB_TRY(launch_distance_l1(dm, w[i], b->dist_scratch, b->stream));              // createWeightMap (blenders.cpp:427-432)
+        SB_TRY(launch_weight_from_dist(w[i], b->sharpness, b->stream));
+        SB_TRY(launch_weight_accumulate(w[i], sum.v, corners[i].x - roi.x, corners[i].y - roi.y, b->stream));   // weights_sum(roi) += weight_maps[i]
+    }
+    for (int i = 0; i < n; ++i) {
+        SB_TRY(launch_weight_normalize(w[i], sum.v, corners[i].x - roi.x, corners[i].y - roi.y, b->stream));
+        if (weight_maps[i].device < 0) SB_TRY(from_device(w[i], &weight_maps[i], b->stream));
+    }
+    SB_CUDA(cudaStreamSynchronize(b->stream));
+    *dst_roi = roi;
+    return SB_OK;
+}
+
 int sb_create_laplace_pyr(const sb_image *img, int num_levels, sb_image *pyr, int device)
 {
     SB_ASSERT(img && pyr && num_levels >= 0);

@@ -92,6 +92,30 @@ int launch_weight_accumulate(const DImage &w, const DImage &dst_w, int ox, int o
     return SB_OK;
 }
 
+// FeatherBlender::createWeightMaps (blenders.cpp:176-183): tmp = weights_sum(roi) is a VIEW, so setTo(1, tmp < eps) writes
+// back into the shared sum; then divide(weight, tmp, weight) with cv::divide's "x / 0 = 0"
+__global__ void __launch_bounds__(256)
+k_weight_normalize(float *w, size_t wstep, int ww, int wh, float *sum, size_t sstep, int ox, int oy)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= ww || y >= wh) return;
+    float *t = mrow<float>(sum, sstep, oy + y) + (ox + x);
+    float d = *t;
+    if (d < 1.1920928955078125e-07f) { d = 1.f; *t = 1.f; }
+    float *p = mrow<float>(w, wstep, y) + x;
+    *p = d != 0.f ? __fdiv_rn(*p, d) : 0.f;
+}
+
+int launch_weight_normalize(const DImage &w, const DImage &sum, int ox, int oy, cudaStream_t s)
+{
+    SB_ASSERT(w.type == SB_32FC1 && sum.type == SB_32FC1);
+    SB_ASSERT(ox >= 0 && oy >= 0 && ox + w.cols <= sum.cols && oy + w.rows <= sum.rows);
+    dim3 block(32, 8), grid(div_up(w.cols, 32), div_up(w.rows, 8));
+    k_weight_normalize<<<grid, block, 0, s>>>(w.ptr<float>(), w.step, w.cols, w.rows, sum.ptr<float>(), sum.step, ox, oy);
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
 int launch_lap_accumulate(const DImage &fine, const DImage &coarse, const DImage &w, const DImage &dst,
                           const DImage &dst_w, int ox, int oy, cudaStream_t s)
 {

@@ -77,6 +77,8 @@ int launch_lap_accumulate(const DImage &fine, const DImage &coarse, const DImage
                           const DImage &dst_w, int ox, int oy, cudaStream_t s);
 // dst_w(x+ox, y+oy) += w : the weight-sum half of a13 alone (built once per calibration by the compositor)
 int launch_weight_accumulate(const DImage &w, const DImage &dst_w, int ox, int oy, cudaStream_t s);
+// w /= sum(roi) with sum(roi) < eps set to 1 in place (FeatherBlender::createWeightMaps, blenders.cpp:176-183)
+int launch_weight_normalize(const DImage &w, const DImage &sum, int ox, int oy, cudaStream_t s);
 // a14 normalizeUsingWeightMap in place
 int launch_normalize(const DImage &weight, const DImage &src, cudaStream_t s);
 // a14+a15 fused: fine = saturate(pyrUp(coarse) + normalize(fine, w))

@@ -498,3 +498,19 @@ def test_seam_mask_refinement_bit_exact(gpu, shape, dsize):
     assert_same(capi.dilate3x3(a), O.dilate3x3(a), "dilate")
     assert_same(capi.resize_linear_8u(a, dsize), O.resize_linear_8u(a, dsize), "resize")
     assert_same(capi.refine_seam_mask(a, mw), O.refine_seam_mask(a, mw), "refined seam mask")
+
+
+@pytest.mark.parametrize("n,w,h,sharp", [(2, 120, 90, 0.02), (3, 160, 100, 0.05), (4, 90, 70, 0.3)])
+def test_feather_create_weight_maps(gpu, n, w, h, sharp):
+    """FeatherBlender::createWeightMaps (blenders.cpp:158-186) incl. an all-zero mask (sum < eps -> 1, written back into
+    the shared sum) — bit for bit; the oracle is pinned against cv2 in tests/test_oracle_vs_cv2.py."""
+    corners, _, masks = util.exposure_scene(n, w, h, seed=30 + n)
+    if n == 4:
+        masks[2][:] = 0
+    oroi, omaps = O.feather_create_weight_maps(masks, corners, sharp)
+    roi, maps = gpu.FeatherBlender(sharp).createWeightMaps(masks, corners)
+    assert tuple(roi) == tuple(oroi)
+    for a, b in zip(maps, omaps):
+        assert_same(a, b, "normalised weight map")
+    with pytest.raises(gpu.StitchError):
+        gpu.FeatherBlender().createWeightMaps(masks, corners[:1])

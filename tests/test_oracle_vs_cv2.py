@@ -108,3 +108,17 @@ def test_frame_loop_against_cv2_pipeline():
     ref, rmask = _cv_blend(cv2.detail_MultiBandBlender(0, 5, cv2.CV_16S), warped, masks, corners)
     same(got, np.clip(ref, 0, 255).astype(np.uint8), "panorama")
     same(gmask, rmask, "panorama mask")
+
+
+@pytest.mark.parametrize("n,w,h", [(2, 120, 90), (3, 160, 100), (4, 90, 70)])
+def test_feather_create_weight_maps_against_cv2(n, w, h):
+    """FeatherBlender::createWeightMaps (blenders.cpp:158-186), incl. an all-zero mask"""
+    corners, _, masks = util.exposure_scene(n, w, h, seed=n)
+    masks = [np.where(m == 255, 255, 0).astype(np.uint8) for m in masks]
+    if n == 4:
+        masks[2][:] = 0
+    roi, maps = cv2.detail_FeatherBlender(0.05).createWeightMaps([cv2.UMat(m) for m in masks], corners, None)
+    oroi, omaps = O.feather_create_weight_maps(masks, corners, 0.05)
+    assert tuple(roi) == tuple(oroi)
+    for a, b in zip(maps, omaps):
+        same(b, a.get(), "normalised weight map")
