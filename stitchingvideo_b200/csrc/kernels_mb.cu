@@ -168,7 +168,7 @@ int launch_mb_warp(const MbWarpArgs &a, bool apply_gain, int max_rw, int max_rh,
 // ------------------------------------------------------------------------------------ K2: pyrDown on RGBX
 // channels 0 and 2 ride in the 16-bit lanes of one register, channel 1 in another
 __device__ __forceinline__ unsigned lanes02(unsigned v) { return v & 0x00ff00ffu; }
-__device__ __forceinline__ unsigned lane1(unsigned v) { return (v >> 8) & 0xffu; }
+__device__ __forceinline__ unsigned lane1(unsigned v) { return __byte_perm(v, 0u, 0x4441); }   // (v >> 8) & 0xff in one PRMT
 
 // Each thread produces a 2x2 block of outputs from a 7x7 window of inputs.  With x2 the thread's
 // column, the window starts at input column 4*x2 - 2: per input row one 8-byte, one 16-byte and one
@@ -321,9 +321,9 @@ __device__ __forceinline__ void mb_band_thread(const MbBandArgs &a, int X0, int 
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 if (w[j][i] == (WT)0) continue;              // short(lap * 0) == 0 and (lap * 0) >> 8 == 0
-                const int l0 = (int)(g[j][i] & 0xff) - (int)(u02[j][i] & 0xffffu);
-                const int l1 = (int)((g[j][i] >> 8) & 0xff) - (int)u1[j][i];
-                const int l2 = (int)((g[j][i] >> 16) & 0xff) - (int)(u02[j][i] >> 16);
+                const int l0 = (int)__byte_perm(g[j][i], 0u, 0x4440) - (int)(u02[j][i] & 0xffffu);
+                const int l1 = (int)__byte_perm(g[j][i], 0u, 0x4441) - (int)u1[j][i];
+                const int l2 = (int)__byte_perm(g[j][i], 0u, 0x4442) - (int)(u02[j][i] >> 16);
                 if (plain) { acc[j][i][0] = l0; acc[j][i][1] = l1; acc[j][i][2] = l2; continue; }
                 acc[j][i][0] += mb_weighted(l0, w[j][i]); acc[j][i][1] += mb_weighted(l1, w[j][i]); acc[j][i][2] += mb_weighted(l2, w[j][i]);
             }
@@ -384,7 +384,8 @@ __device__ __forceinline__ void mb_band_thread(const MbBandArgs &a, int X0, int 
             }
             if (NOT_TOP) {   // restoreImageFromLaplacePyr: add(pyrUp(pyr[i+1]), pyr[i]) saturates
 #pragma unroll
-                for (int k = 0; k < 3; ++k) v[i][k] = sat_s16(up[j][i][k] + v[i][k]);
+                for (int k = 0; k < 3; ++k)      // (8-bit output clamps to [0, 255] right after: the 16-bit clamp is subsumed)
+                    v[i][k] = (FINAL && OUT8) ? up[j][i][k] + v[i][k] : sat_s16(up[j][i][k] + v[i][k]);
             }
             if (FINAL && !masked[i]) v[i][0] = v[i][1] = v[i][2] = 0;   // Blender::blend: dst_.setTo(0, dst_mask_ == 0)
         }
