@@ -34,7 +34,12 @@ WORKLOADS = {
     "c2": "C2: 5-camera 1080p 360deg, CylindricalWarper + FeatherBlender(0.02), fixed calibration (BASELINE.json configs[1])",
     "c3": "C3: 5-camera 1080p 360deg, SphericalWarper + GainCompensator + MultiBandBlender(5 bands, CV_32F weights) (configs[2])",
     "c4": "C4: 8-camera 4K VR, SphericalWarper + GainCompensator + MultiBandBlender(5 bands) (configs[3])",
+    "app6": "APP6: the live app's own per-frame case (BASELINE.md 1): 6-camera 1920x1088, cached-map cylindrical remap + composite "
+            "without blending or gain (Blender::NO), panorama ~8040x1088",
 }
+# the only per-frame figure the reference publishes (REL32/resultTime-at.txt, mean 43.6 ms per frame set,
+# hardware unknown): frames/s for exactly the APP6 workload
+PUBLISHED_FPS = {"app6": 1000.0 / 43.6}
 
 
 # SURVEY.md §8d "ALGORITHMIC bytes per frame" of the reference-shaped (fused-by-stage) dataflow, GB
@@ -276,7 +281,8 @@ def run_ours(args):
         return
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": (value / PUBLISHED_FPS[args.workload]) if args.workload in PUBLISHED_FPS else None,
         "dtype": "u8/s16 integer + f32 weights", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload], "frame_sets_per_step": args.batch, "frame_sets_per_rank": steps_f, "cameras": n,
                    "frame": "%dx%d" % size,
@@ -356,7 +362,8 @@ def cv2_baseline(workload, frames=3):
     for it in range(frames + 1):
         fr = [rigs.frame(workload, it, i, smooth=0) for i in range(spec["n_used"])]
         t = time.perf_counter()
-        b = cv2.detail_MultiBandBlender(0, 5, cv2.CV_32F) if spec["blender"] == "multiband" else cv2.detail_FeatherBlender(0.02)
+        b = (cv2.detail_MultiBandBlender(0, 5, cv2.CV_32F) if spec["blender"] == "multiband" else
+             cv2.detail_FeatherBlender(0.02) if spec["blender"] == "feather" else cv2.detail.Blender_createDefault(cv2.detail.Blender_NO))
         from oracle import oracle as O
         b.prepare(O.result_roi(cal.corners, cal.sizes))
         for i, f in enumerate(fr):
@@ -445,7 +452,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.depth is None:
-        args.depth = 4 if args.workload == "c2" else 8
+        args.depth = 8 if args.workload in ("c3", "c4") else 4
     if args.impl == "reference":
         if args.steps == 20:
             args.steps, args.warmup = 4, 3

@@ -15,6 +15,9 @@ RIGS = {
     "c3": dict(n=5, W=1920, H=1080, f=1050.0, warper="spherical", scale=1050.0, blender="multiband", gains=True),
     "c4": dict(n=8, W=3840, H=2160, f=2900.0, warper="spherical", scale=2900.0, blender="multiband", gains=True),
     "c5": dict(n=8, W=3840, H=2160, f=2900.0, warper="spherical", scale=16384.0 / (2.0 * math.pi), blender="multiband", gains=True),
+    # the live app's published per-frame case: 6 x 1920x1088, cached-map
+    # cylindrical remap + composite without blending or gain, panorama ~8040 x 1105 (2 pi f = 8040 -> f = 1280)
+    "app6": dict(n=6, W=1920, H=1088, f=1280.0, warper="cylindrical", scale=1280.0, blender="no", gains=False),
     # small rigs for fast parity tests (same construction, scaled down)
     "mini": dict(n=5, W=240, H=136, f=131.0, warper="spherical", scale=131.0, blender="multiband", gains=True),
     "mini_cyl": dict(n=5, W=240, H=136, f=131.0, warper="cylindrical", scale=131.0, blender="feather", gains=False),
