@@ -90,6 +90,12 @@ __device__ __forceinline__ void stream_producer(const Args &a, FtsSmem &sm, int 
         const int need = max((int)__shfl_sync(0xffffffffu, d.w, 0), seq - SB_FTT_STAGES + 1);
         if (need > 0) {                                 // tiles retire in order: waiting for tile need - 1 covers all before it
             const int t = need - 1;                     // (t >= seq - STAGES, so the barrier is at most one phase ahead)
+            // A parity wait is only meaningful when the barrier is in the awaited phase or the one after it: this warp
+            // must already know tile t - STAGES (the barrier's previous phase) consumed.  What it knows from its previous
+            // tile (seq - P) is that tile seq - P - STAGES was consumed; if the plan lets t run ahead of seq - P, step
+            // through that tile first (its barrier is then at most one phase behind, and t - STAGES <= seq - P).
+            const int w = seq - SB_FTS_PRODUCER_WARPS;
+            if (w >= 0 && t > w) mbar_wait(&sm.empty[w % SB_FTT_STAGES], (unsigned)(w / SB_FTT_STAGES) & 1u);
             mbar_wait(&sm.empty[t % SB_FTT_STAGES], (unsigned)(t / SB_FTT_STAGES) & 1u);
         }
         {
