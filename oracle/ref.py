@@ -38,6 +38,10 @@ def lib():
                                      C.POINTER(O.SoMat), C.POINTER(O.SoMat)]
         L.ref_warp.argtypes = [C.c_int, C.c_float, C.POINTER(O.SoMat), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                C.POINTER(C.c_int), C.POINTER(O.SoMat)]
+        L.ref_gain_feed.argtypes = [C.c_int, C.c_void_p, C.POINTER(O.SoMat), C.POINTER(O.SoMat), C.c_void_p]
+        L.ref_blocks_gain_feed.argtypes = [C.c_int, C.c_void_p, C.POINTER(O.SoMat), C.POINTER(O.SoMat), C.c_int, C.c_int,
+                                           C.POINTER(O.SoMat), C.POINTER(O.SoMat)]
+        L.ref_gain_apply.argtypes = [C.POINTER(O.SoMat), C.c_double]
         _lib = L
     return _lib
 
@@ -164,3 +168,37 @@ def normalize_using_weight_map(weight, src):
     mw, ms = O.mat(np.ascontiguousarray(weight)), O.mat(src)
     _chk(lib().ref_normalize_using_weight_map(C.byref(mw), C.byref(ms)), "normalizeUsingWeightMap")
     return src
+
+
+# ---- ExposureCompensator through the reference's own exposure_compensate.cpp ---------------------------------------
+def gain_feed(corners, images, masks):
+    """GainCompensator::feed(corners, images, masks) + gains() (exposure_compensate.cpp:64-162)"""
+    n = len(images)
+    images = [np.ascontiguousarray(a, np.uint8) for a in images]
+    masks = [np.ascontiguousarray(a, np.uint8) for a in masks]
+    cxy = np.ascontiguousarray(np.asarray(corners, np.int32).reshape(-1))
+    g = np.zeros(n, np.float64)
+    _chk(lib().ref_gain_feed(n, cxy.ctypes.data_as(C.c_void_p), O._mat_array(images), O._mat_array(masks), g.ctypes.data_as(C.c_void_p)), "GainCompensator::feed")
+    return g
+
+
+def blocks_gain_feed(corners, images, masks, bl_width=32, bl_height=32, apply_first=False):
+    """BlocksGainCompensator(bl_width, bl_height)::feed -> gain_maps_ (and, optionally, images[0] after apply(0, ...))"""
+    n = len(images)
+    images = [np.ascontiguousarray(a, np.uint8) for a in images]
+    masks = [np.ascontiguousarray(a, np.uint8) for a in masks]
+    cxy = np.ascontiguousarray(np.asarray(corners, np.int32).reshape(-1))
+    maps = [np.zeros(((a.shape[0] + bl_height - 1) // bl_height, (a.shape[1] + bl_width - 1) // bl_width), np.float32) for a in images]
+    out0 = np.zeros_like(images[0]) if apply_first else None
+    m0 = O.mat(out0) if apply_first else None
+    _chk(lib().ref_blocks_gain_feed(n, cxy.ctypes.data_as(C.c_void_p), O._mat_array(images), O._mat_array(masks), bl_width, bl_height,
+                                    O._mat_array(maps), C.byref(m0) if apply_first else None), "BlocksGainCompensator::feed")
+    return (maps, out0) if apply_first else maps
+
+
+def gain_apply(img, gain):
+    """GainCompensator::apply with gains_(0, 0) = gain (exposure_compensate.cpp:150-153)"""
+    out = np.ascontiguousarray(img).copy()
+    m = O.mat(out)
+    _chk(lib().ref_gain_apply(C.byref(m), C.c_double(gain)), "GainCompensator::apply")
+    return out

@@ -44,6 +44,8 @@
 #define CV_16SC1 CV_MAKETYPE(CV_16S, 1)
 #define CV_16SC3 CV_MAKETYPE(CV_16S, 3)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
+#define CV_32SC1 CV_MAKETYPE(CV_32S, 1)
+#define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
 
 enum { CV_StsNoMem = -4, CV_StsBadArg = -5, CV_StsNotImplemented = -213, CV_StsAssert = -215 };
 enum { CV_DIST_L1 = 1, CV_DIST_L2 = 2 };
@@ -51,6 +53,9 @@ enum { CV_DIST_L1 = 1, CV_DIST_L2 = 2 };
 namespace cv {
 
 typedef unsigned char uchar;
+typedef long long int64;
+inline int64 getTickCount() { return 0; }                   // (only feeds the reference's LOGLN timing lines)
+inline double getTickFrequency() { return 1.0; }
 
 class Exception : public std::runtime_error {
 public:
@@ -67,6 +72,8 @@ template <typename T> struct Point_ {
 };
 typedef Point_<int> Point;
 typedef Point_<float> Point2f;
+template <typename T> inline Point_<T> operator-(const Point_<T> &a, const Point_<T> &b) { return Point_<T>(a.x - b.x, a.y - b.y); }
+template <typename T> inline Point_<T> operator+(const Point_<T> &a, const Point_<T> &b) { return Point_<T>(a.x + b.x, a.y + b.y); }
 template <typename T> struct Point3_ {
     T x, y, z;
     Point3_() : x(0), y(0), z(0) {}
@@ -200,6 +207,13 @@ public:
     Mat &setTo(const Scalar &s, const Mat &mask = Mat());
     Mat &setTo(double v, const Mat &mask = Mat()) { return setTo(Scalar::all(v), mask); }
     Mat &operator+=(const Mat &o);
+    Mat &operator*=(double v)                               // image *= gain: convertTo(image, -1, gain) on 8U (exposure_compensate.cpp:152)
+    {
+        CV_Assert(depth() == CV_8U);
+        so_mat s = so();
+        CV_Assert(so_scale_8u(&s, v) == 0);
+        return *this;
+    }
     Mat t() const;
     Mat inv() const;
     Mat reshape(int cn, int new_rows) const
@@ -231,10 +245,21 @@ private:
     std::shared_ptr<uchar> owner_;
 };
 
+template <typename T> struct DataType_;
+template <> struct DataType_<uchar> { enum { type = CV_8UC1 }; };
+template <> struct DataType_<short> { enum { type = CV_16SC1 }; };
+template <> struct DataType_<int> { enum { type = CV_32SC1 }; };
+template <> struct DataType_<float> { enum { type = CV_32FC1 }; };
+template <> struct DataType_<double> { enum { type = CV_64FC1 }; };
+
 template <typename T> class Mat_ : public Mat {
 public:
     Mat_() {}
+    Mat_(int r, int c) : Mat(r, c, DataType_<T>::type) {}
     Mat_(const Mat &m) : Mat(m) { CV_Assert(m.empty() || m.elemSize() == sizeof(T)); }
+    Mat_ &operator=(const Mat &m) { CV_Assert(m.empty() || m.elemSize() == sizeof(T)); Mat::operator=(m); return *this; }
+    void create(int r, int c) { Mat::create(r, c, DataType_<T>::type); }
+    void create(Size s) { Mat::create(s.height, s.width, DataType_<T>::type); }
     T &operator()(int y, int x) { return this->template at<T>(y, x); }
     const T &operator()(int y, int x) const { return this->template at<T>(y, x); }
 };
@@ -268,6 +293,35 @@ inline Mat operator==(const Mat &a, double v) { return compare_scalar(a, v, CMP_
 inline Mat operator!=(const Mat &a, double v) { return compare_scalar(a, v, CMP_NE); }
 inline Mat operator>(const Mat &a, double v) { return compare_scalar(a, v, CMP_GT); }
 inline Mat operator<(const Mat &a, double v) { return compare_scalar(a, v, CMP_LT); }
+
+// (submask1 == v) & (submask2 == w): bitwise AND of two CV_8U masks (exposure_compensate.cpp:104)
+inline Mat operator&(const Mat &a, const Mat &b)
+{
+    CV_Assert(a.type() == CV_8U && b.type() == CV_8U && a.rows == b.rows && a.cols == b.cols);
+    Mat d(a.rows, a.cols, CV_8U);
+    for (int y = 0; y < a.rows; ++y)
+        for (int x = 0; x < a.cols; ++x) d.ptr<uchar>(y)[x] = a.ptr<uchar>(y)[x] & b.ptr<uchar>(y)[x];
+    return d;
+}
+inline int countNonZero(const Mat &m)
+{
+    CV_Assert(m.type() == CV_8U);
+    int n = 0;
+    for (int y = 0; y < m.rows; ++y)
+        for (int x = 0; x < m.cols; ++x) n += m.ptr<uchar>(y)[x] != 0;
+    return n;
+}
+// cv::solve(A, b, x) with the default DECOMP_LU on CV_64F: the oracle's restatement of OpenCV's LU (so_calib.c)
+inline bool solve(const Mat &A, const Mat &b, Mat &x)
+{
+    CV_Assert(A.type() == CV_64FC1 && b.type() == CV_64FC1 && A.rows == A.cols && b.rows == A.rows && b.cols == 1);
+    Mat a = A.clone(), r = b.clone();
+    const bool ok = so_solve_lu(A.rows, a.ptr<double>(), r.ptr<double>()) != 0;
+    x = r;
+    return ok;
+}
+template <typename T> inline T saturate_cast(float v);
+template <> inline uchar saturate_cast<uchar>(float v) { const int i = so_cvround(v); return (uchar)(i < 0 ? 0 : i > 255 ? 255 : i); }
 
 // MatExpr `weight * sharpness` (CV_32F): evaluated by convertTo-style scaling, float(src * alpha)
 inline Mat operator*(const Mat &a, double s)
@@ -321,6 +375,8 @@ inline Mat &Mat::setTo(const Scalar &s, const Mat &mask)
                 case CV_8U: ptr<uchar>(y)[x * cn + c] = (uchar)v; break;
                 case CV_16S: ptr<short>(y)[x * cn + c] = (short)v; break;
                 case CV_32F: ptr<float>(y)[x * cn + c] = (float)v; break;
+                case CV_32S: ptr<int>(y)[x * cn + c] = (int)v; break;
+                case CV_64F: ptr<double>(y)[x * cn + c] = v; break;
                 default: CV_Error(CV_StsNotImplemented, "shim: setTo depth");
                 }
             }
@@ -451,6 +507,25 @@ inline double threshold(const Mat &src, Mat &dst, double thresh, double, int typ
         }
     dst = out;
     return thresh;
+}
+// cv::sepFilter2D with a symmetric 3-tap row/column kernel on CV_32F, BORDER_DEFAULT (exposure_compensate.cpp:217-218)
+inline void sepFilter2D(const Mat &src, Mat &dst, int ddepth, const Mat &kx, const Mat &ky)
+{
+    CV_Assert(src.type() == CV_32F && ddepth == CV_32F && kx.type() == CV_32F && kx.rows == 1 && kx.cols == 3 && ky.data == kx.data);
+    CV_Assert(kx.at<float>(0, 0) == kx.at<float>(0, 2));
+    Mat out(src.rows, src.cols, CV_32F);
+    so_mat s = src.so(), d = out.so();
+    CV_Assert(so_sep_filter3_f32(&s, &d, kx.at<float>(0, 1), kx.at<float>(0, 0)) == 0);
+    dst = out;
+}
+// cv::resize INTER_LINEAR on CV_32FC1 (exposure_compensate.cpp:233)
+inline void resize(const Mat &src, Mat &dst, Size dsize, double = 0, double = 0, int interpolation = INTER_LINEAR)
+{
+    CV_Assert(src.type() == CV_32F && interpolation == INTER_LINEAR && dsize.width > 0 && dsize.height > 0);
+    Mat out(dsize.height, dsize.width, CV_32F);
+    so_mat s = src.so(), d = out.so();
+    CV_Assert(so_resize_linear_32f(&s, &d) == 0);
+    dst = out;
 }
 template <typename T> inline T randu() { return (T)std::rand(); }
 

@@ -2,8 +2,7 @@
 // (/root/reference/.../src/{blenders,warpers,util}.cpp + the detail/*.hpp headers they include), unmodified,
 // against the OpenCV stand-in of include/opencv2 (primitives = the oracle's restatement of OpenCV 2.4.11).
 // TEST INFRASTRUCTURE: tests/test_ref_shim.py compares the oracle (oracle/so_stitch.c) with this library.
-// Not built: exposure_compensate.cpp (its feed() needs solve/sepFilter2D/resize; the per-frame apply() is the
-// two-line `image *= gain` / `multiply by the resized gain map`, exposure_compensate.cpp:150-153,225-246).
+// exposure_compensate.cpp is built too (feed() of GainCompensator / BlocksGainCompensator and both apply()).
 //
 // precomp.hpp pulls in every OpenCV module (features2d, calib3d, ...); its include guard is defined here so that
 // only the headers the three sources really need are seen.
@@ -21,6 +20,9 @@
 #include <vector>
 
 #include "opencv2/core/core.hpp"
+#define private public                                      // read BlocksGainCompensator::gain_maps_ (no accessor in 2.4.11); the sources stay untouched
+#include "opencv2/stitching/detail/exposure_compensate.hpp"
+#undef private
 #include "opencv2/stitching/detail/blenders.hpp"
 #include "opencv2/stitching/detail/util.hpp"
 #include "opencv2/stitching/detail/warpers.hpp"
@@ -28,6 +30,7 @@
 #include REF_SRC(blenders.cpp)
 #include REF_SRC(util.cpp)
 #include REF_SRC(warpers.cpp)
+#include REF_SRC(exposure_compensate.cpp)
 
 // ------------------------------------------------------------------------------------ C API (ctypes)
 using cv::Mat;
@@ -175,6 +178,57 @@ int ref_warp(int kind, float scale, const so_mat *src, const float K[9], const f
         cv::Point p = make_warper(kind, scale)->warp(wrap(src), mat3(K), mat3(R), interp, border, d);
         tl[0] = p.x; tl[1] = p.y;
         return copy_out(d, dst);
+    } catch (const cv::Exception &e) { return e.code; }
+}
+
+// ---- ExposureCompensator (exposure_compensate.cpp): feed / gains / apply through the reference's own classes
+static void feed_args(int n, const int *corners_xy, const so_mat *images, const so_mat *masks,
+                      std::vector<cv::Point> &c, std::vector<Mat> &im, std::vector<Mat> &mk)
+{
+    for (int i = 0; i < n; ++i) { c.push_back(cv::Point(corners_xy[2 * i], corners_xy[2 * i + 1])); im.push_back(wrap(&images[i])); mk.push_back(wrap(&masks[i])); }
+}
+int ref_gain_feed(int n, const int *corners_xy, const so_mat *images, const so_mat *masks, double *gains)
+{
+    try {
+        cv::detail::stitchingLogLevel() = 2;               // silence the LOGLN timing lines
+        std::vector<cv::Point> c; std::vector<Mat> im, mk;
+        feed_args(n, corners_xy, images, masks, c, im, mk);
+        cv::detail::GainCompensator comp;
+        static_cast<cv::detail::ExposureCompensator &>(comp).feed(c, im, mk);      // the (corners, images, masks) overload, level 255
+        std::vector<double> g = comp.gains();
+        for (int i = 0; i < n; ++i) gains[i] = g[i];
+        return 0;
+    } catch (const cv::Exception &e) { return e.code; }
+}
+// gain_maps[i]: CV_32FC1 of the block grid size; image0_out (may be null): images[0] after apply(0, ...)
+int ref_blocks_gain_feed(int n, const int *corners_xy, const so_mat *images, const so_mat *masks, int bl_width, int bl_height,
+                         so_mat *gain_maps, so_mat *image0_out)
+{
+    try {
+        cv::detail::stitchingLogLevel() = 2;
+        std::vector<cv::Point> c; std::vector<Mat> im, mk;
+        feed_args(n, corners_xy, images, masks, c, im, mk);
+        cv::detail::BlocksGainCompensator comp(bl_width, bl_height);
+        static_cast<cv::detail::ExposureCompensator &>(comp).feed(c, im, mk);
+        int rc = 0;
+        for (int i = 0; i < n; ++i) rc |= copy_out(comp.gain_maps_[i], &gain_maps[i]);
+        if (image0_out) {
+            Mat img = im[0].clone();
+            comp.apply(0, c[0], img, mk[0]);
+            rc |= copy_out(img, image0_out);
+        }
+        return rc;
+    } catch (const cv::Exception &e) { return e.code; }
+}
+int ref_gain_apply(so_mat *image, double gain)
+{
+    try {
+        cv::detail::GainCompensator comp;
+        comp.gains_.create(1, 1);
+        comp.gains_(0, 0) = gain;
+        Mat img = wrap(image);
+        comp.apply(0, cv::Point(0, 0), img, Mat());
+        return 0;
     } catch (const cv::Exception &e) { return e.code; }
 }
 

@@ -139,3 +139,27 @@ def test_remaining_projectors_reference_sources_equal_cv2(name, cv_name, ab):
         assert tuple(roi) == tuple(croi)
         same(xm, cxm, name + " xmap")
         same(ym, cym, name + " ymap")
+
+
+# ---- exposure_compensate.cpp, compiled where it lies -------------------------------------------
+@pytest.mark.parametrize("n,w,h", [(2, 120, 90), (3, 160, 100), (5, 200, 120), (4, 97, 61)])
+def test_gain_compensator_feed_is_the_reference_code(n, w, h):
+    """The oracle's restatement of GainCompensator::feed (so_calib.c) against the reference's own exposure_compensate.cpp
+    (:76-147): same overlap loops, same sequential double sums, same normal equations -> the gains are EQUAL doubles."""
+    corners, imgs, masks = util.exposure_scene(n, w, h, seed=40 + n)
+    assert np.array_equal(RF.gain_feed(corners, imgs, masks), O.gain_feed(corners, imgs, masks))
+    img = imgs[0]
+    for g in (0.95, 1.02, 1.5, 2.5):
+        assert np.array_equal(RF.gain_apply(img, g), O.gain_apply(img, g))
+
+
+@pytest.mark.parametrize("n,w,h,bl", [(2, 120, 90, 32), (3, 160, 100, 32), (3, 150, 97, 20), (2, 64, 40, 64)])
+def test_blocks_gain_compensator_feed_is_the_reference_code(n, w, h, bl):
+    """BlocksGainCompensator::feed (:165-222) and ::apply (:225-246): block lists, one gain solve over all blocks, two
+    smoothing passes, resize + multiply — gain maps and the compensated image bit for bit."""
+    corners, imgs, masks = util.exposure_scene(n, w, h, seed=50 + n)
+    ref_maps, ref_img0 = RF.blocks_gain_feed(corners, imgs, masks, bl, bl, apply_first=True)
+    maps = O.blocks_gain_feed(corners, imgs, masks, bl, bl)
+    for a, b in zip(maps, ref_maps):
+        assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.array_equal(O.blocks_gain_apply(imgs[0], maps[0]), ref_img0)
