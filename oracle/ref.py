@@ -42,6 +42,7 @@ def lib():
         L.ref_blocks_gain_feed.argtypes = [C.c_int, C.c_void_p, C.POINTER(O.SoMat), C.POINTER(O.SoMat), C.c_int, C.c_int,
                                            C.POINTER(O.SoMat), C.POINTER(O.SoMat)]
         L.ref_gain_apply.argtypes = [C.POINTER(O.SoMat), C.c_double]
+        L.ref_feather_create_weight_maps.argtypes = [C.c_int, C.POINTER(O.SoMat), C.c_void_p, C.c_float, C.POINTER(O.SoMat), C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
@@ -202,3 +203,14 @@ def gain_apply(img, gain):
     m = O.mat(out)
     _chk(lib().ref_gain_apply(C.byref(m), C.c_double(gain)), "GainCompensator::apply")
     return out
+
+
+def feather_create_weight_maps(masks, corners, sharpness=0.02):
+    """FeatherBlender(sharpness)::createWeightMaps (blenders.cpp:158-186) -> (dst_roi, weight maps)"""
+    masks = [np.ascontiguousarray(m, np.uint8) for m in masks]
+    maps = [np.zeros(m.shape, np.float32) for m in masks]
+    cxy = np.ascontiguousarray(np.asarray(corners, np.int32).reshape(-1))
+    roi = (C.c_int * 4)()
+    _chk(lib().ref_feather_create_weight_maps(len(masks), O._mat_array(masks), cxy.ctypes.data_as(C.c_void_p), C.c_float(sharpness),
+                                              O._mat_array(maps), roi), "FeatherBlender::createWeightMaps")
+    return tuple(roi), maps

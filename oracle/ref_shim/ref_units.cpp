@@ -181,6 +181,22 @@ int ref_warp(int kind, float scale, const so_mat *src, const float K[9], const f
     } catch (const cv::Exception &e) { return e.code; }
 }
 
+// FeatherBlender::createWeightMaps (blenders.cpp:158-186); weight_maps[i]: CV_32FC1 of masks[i]'s size
+int ref_feather_create_weight_maps(int n, const so_mat *masks, const int *corners_xy, float sharpness, so_mat *weight_maps, int roi_xywh[4])
+{
+    try {
+        std::vector<Mat> mk, wm;
+        std::vector<cv::Point> c;
+        for (int i = 0; i < n; ++i) { mk.push_back(wrap(&masks[i])); c.push_back(cv::Point(corners_xy[2 * i], corners_xy[2 * i + 1])); }
+        cv::detail::FeatherBlender fb(sharpness);
+        const cv::Rect r = fb.createWeightMaps(mk, c, wm);
+        roi_xywh[0] = r.x; roi_xywh[1] = r.y; roi_xywh[2] = r.width; roi_xywh[3] = r.height;
+        int rc = 0;
+        for (int i = 0; i < n; ++i) rc |= copy_out(wm[i], &weight_maps[i]);
+        return rc;
+    } catch (const cv::Exception &e) { return e.code; }
+}
+
 // ---- ExposureCompensator (exposure_compensate.cpp): feed / gains / apply through the reference's own classes
 static void feed_args(int n, const int *corners_xy, const so_mat *images, const so_mat *masks,
                       std::vector<cv::Point> &c, std::vector<Mat> &im, std::vector<Mat> &mk)

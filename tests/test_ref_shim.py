@@ -163,3 +163,16 @@ def test_blocks_gain_compensator_feed_is_the_reference_code(n, w, h, bl):
     for a, b in zip(maps, ref_maps):
         assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert np.array_equal(O.blocks_gain_apply(imgs[0], maps[0]), ref_img0)
+
+
+@pytest.mark.parametrize("n,w,h,sharp", [(2, 120, 90, 0.02), (3, 160, 100, 0.05), (4, 90, 70, 0.3)])
+def test_feather_create_weight_maps_is_the_reference_code(n, w, h, sharp):
+    """FeatherBlender::createWeightMaps (blenders.cpp:158-186), incl. an all-zero mask (the `tmp` VIEW write-back)"""
+    corners, _, masks = util.exposure_scene(n, w, h, seed=60 + n)
+    if n == 4:
+        masks[2][:] = 0
+    rroi, rmaps = RF.feather_create_weight_maps(masks, corners, sharp)
+    oroi, omaps = O.feather_create_weight_maps(masks, corners, sharp)
+    assert tuple(rroi) == tuple(oroi)
+    for a, b in zip(omaps, rmaps):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
