@@ -122,3 +122,26 @@ def test_feather_create_weight_maps_against_cv2(n, w, h):
     assert tuple(roi) == tuple(oroi)
     for a, b in zip(maps, omaps):
         same(b, a.get(), "normalised weight map")
+
+
+def test_mask_refinement_primitives_random_shapes():
+    """cv::dilate (3x3 default) and cv::resize INTER_LINEAR on 8UC1 over random shapes and scale factors: up, down, exact
+    2x decimation in both / one dimension (INTER_AREA rerouting only when both are 2), degenerate 1-pixel sizes."""
+    rng = np.random.default_rng(2026)
+    for k in range(60):
+        h, w = int(rng.integers(1, 90)), int(rng.integers(1, 120))
+        a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        a[rng.random((h, w)) < 0.5] = 0
+        same(O.dilate3x3(a), cv2.dilate(a, None), "dilate %dx%d" % (w, h))
+        mode = k % 4
+        if mode == 0 and h % 2 == 0 and w % 2 == 0:
+            ds = (w // 2, h // 2)
+        elif mode == 1 and w % 2 == 0:
+            ds = (w // 2, int(rng.integers(1, 200)))
+        elif mode == 2:
+            ds = (int(w * rng.uniform(1.0, 4.0)) + 1, int(h * rng.uniform(1.0, 4.0)) + 1)
+        else:
+            ds = (int(rng.integers(1, 200)), int(rng.integers(1, 150)))
+        same(O.resize_linear_8u(a, ds), cv2.resize(a, ds, interpolation=cv2.INTER_LINEAR), "resize %dx%d -> %dx%d" % (w, h, ds[0], ds[1]))
+        mw = (rng.random((ds[1], ds[0])) > 0.3).astype(np.uint8) * 255
+        same(O.refine_seam_mask(a, mw), cv2.resize(cv2.dilate(a, None), ds) & mw, "refine")
