@@ -514,3 +514,27 @@ def test_feather_create_weight_maps(gpu, n, w, h, sharp):
         assert_same(a, b, "normalised weight map")
     with pytest.raises(gpu.StitchError):
         gpu.FeatherBlender().createWeightMaps(masks, corners[:1])
+
+
+def test_seam_mask_refinement_random_shapes(gpu):
+    """dilate / 8U linear resize / refine over random shapes and scale factors (up, down, exact 2x in one or both
+    dimensions, 1-pixel sizes) — bit for bit against the oracle (which test_oracle_vs_cv2 fuzzes against OpenCV)."""
+    from stitchingvideo_b200 import capi
+    rng = np.random.default_rng(77)
+    for k in range(40):
+        h, w = int(rng.integers(1, 90)), int(rng.integers(1, 120))
+        a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        a[rng.random((h, w)) < 0.5] = 0
+        mode = k % 4
+        if mode == 0 and h % 2 == 0 and w % 2 == 0:
+            ds = (w // 2, h // 2)
+        elif mode == 1 and w % 2 == 0:
+            ds = (w // 2, int(rng.integers(1, 200)))
+        elif mode == 2:
+            ds = (int(w * rng.uniform(1.0, 4.0)) + 1, int(h * rng.uniform(1.0, 4.0)) + 1)
+        else:
+            ds = (int(rng.integers(1, 200)), int(rng.integers(1, 150)))
+        mw = (rng.random((ds[1], ds[0])) > 0.3).astype(np.uint8) * 255
+        assert_same(capi.dilate3x3(a), O.dilate3x3(a), "dilate %dx%d" % (w, h))
+        assert_same(capi.resize_linear_8u(a, ds), O.resize_linear_8u(a, ds), "resize %dx%d -> %dx%d" % (w, h, ds[0], ds[1]))
+        assert_same(capi.refine_seam_mask(a, mw), O.refine_seam_mask(a, mw), "refine")
