@@ -740,7 +740,7 @@ class Compositor:
         cfg.num_bands = num_bands
         cfg.weight_type = weight_type
         cfg.sharpness = sharpness
-        g = None
+        g = gkeep = garr = arr = None
         if gains is not None:
             g = np.ascontiguousarray(gains, np.float64)
             cfg.comp_kind = COMP_GAIN
@@ -759,7 +759,7 @@ class Compositor:
             cfg.seam_masks = arr
         cfg.output_type = output_type
         self._cal = None
-        self._cfg, self._cfg_keep = C.pointer(cfg), (K, R, g, keep, locals().get("gkeep"), locals().get("garr"), locals().get("arr"))
+        self._cfg, self._cfg_keep = C.pointer(cfg), (K, R, g, keep, gkeep, garr, arr)      # (the config points into these)
         self._create(device)
 
     def _create(self, device):
