@@ -448,7 +448,7 @@ def main():
     ap.add_argument("--profile-frames", type=int, default=5)
     ap.add_argument("--cpu-frames", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--variant", type=int, default=None, choices=[0, 1, 2], help="fused kernel variant: 10 + v is passed to set_fused (default: library default)")
+    ap.add_argument("--variant", type=int, default=None, choices=[0, 1, 2, 3, 4, 5], help="fused kernel variant: 10 + v is passed to set_fused (default: library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.depth is None:

@@ -269,8 +269,13 @@ int  sb_compositor_compose(sb_compositor *c, const sb_image *srcs, sb_image *pan
  * Both give identical results; the staged path is kept as a cross-check.  Values >= 10 are tuning hooks that pick a
  * kernel variant of the fused path (10: CV_16S band kernels / one-pixel-per-thread feather, 11: default fast paths,
  * 12 / 13: multi-band fast path with one launch per pyramid level / with the multi-level launches forced,
- * 14: multi-band fast path with the direct-gather form of the warp stage instead of the streaming one). */
+ * 14: multi-band fast path with the direct-gather form of the warp stage instead of the streaming one,
+ * 15: feather / no-blend with the round-1 streaming kernel instead of its successor). */
 int  sb_compositor_set_fused(sb_compositor *c, int fused);
+/* Which frame kernel this calibration was planned for (tests assert that the fast path really is the one that runs):
+ * feather / no blending: 2 = tensor-TMA streaming kernel (k_fs2), 1 = round-1 streaming kernel, 0 = gather kernel;
+ * multi-band: 2 = RGBX fast path with the streaming warp stage, 1 = RGBX fast path, 0 = CV_16S band kernels. */
+int  sb_compositor_kernel_plan(const sb_compositor *c);
 /* Pipelined form for throughput: up to `depth` frame sets in flight, each on its own stream/slot.
  * enqueue returns a slot id; wait blocks until that slot's pano has landed in the buffers given
  * to enqueue. */

@@ -132,6 +132,7 @@ API = {
     "sb_compositor_compose": (C.c_int, [C.c_void_p, _P(SbImage), _P(SbImage), _P(SbImage)]),
     "sb_compositor_set_depth": (C.c_int, [C.c_void_p, C.c_int]),
     "sb_compositor_set_fused": (C.c_int, [C.c_void_p, C.c_int]),
+    "sb_compositor_kernel_plan": (C.c_int, [C.c_void_p]),
     "sb_compositor_enqueue": (C.c_int, [C.c_void_p, _P(SbImage), _P(SbImage), _P(SbImage), _P(C.c_int)]),
     "sb_compositor_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "sb_compositor_last_gpu_ms": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_float)]),
@@ -826,6 +827,10 @@ class Compositor:
     def set_fused(self, fused):
         """True/1: fused kernels; False/0: staged feed/blend-shaped path; 10/11: fused with kernel variant 0/1."""
         _check(lib().sb_compositor_set_fused(self._h, int(fused)))
+
+    def kernel_plan(self):
+        """2 / 1 / 0: which generation of the frame kernels this calibration runs on (sb_compositor_kernel_plan)."""
+        return int(lib().sb_compositor_kernel_plan(self._h))
 
     def set_depth(self, depth):
         _check(lib().sb_compositor_set_depth(self._h, depth))

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <string>
 
+#include "sb_fs2.h"
 #include "sb_fused.h"
 #include "sb_host_projector.h"
 #include "sb_mb.h"
@@ -46,6 +47,11 @@ struct Camera {
     DevBuf feather_tiles;        // the same table tile-major (one 8 KB block per 32x32 panorama tile) for the streaming kernel
     DevBuf feather_rec;          // per tile block: source box record
     int ftx0 = 0, fty0 = 0, fntx = 0, fnty = 0;
+    DevBuf fs2_blocks;           // second-generation streaming kernel: tile-major 4-byte tap entries + weight-index plane
+    // the source image as tensor maps (one per box width class), keyed on the frame buffer: video pipelines cycle through
+    // a few input buffers, so after the first lap every frame is a cache hit
+    struct TmapSet { const void *p; size_t step; unsigned long long stamp; CUtensorMap m[FS2_NCLS]; };
+    std::vector<TmapSet> tmaps;
     // panorama(-level) column ranges that hold non-zero weights, per level: [s0,s1) U [s2,s3)
     std::vector<std::array<int, 4>> spans;
     // rect-local columns of Gaussian level l that the weighted pixels can see through the pyramid taps (two runs):
@@ -107,8 +113,11 @@ struct sb_compositor {
     bool feather_fast = false;                   // every weighted pixel's taps fit the resolved-tap table
     float stream_sharpness = 0.02f;              // feather: FeatherBlender::sharpness_; Blender::NO: 1/255 (see setup)
     bool feather_tma = false;                    // <= SB_FTT_MAXC cameras per 32x32 tile: persistent table-streaming kernel
-    int feather_variant = 1;                     // 1: k_feather_tma, 0: k_feather_fused_px1
+    int feather_variant = 1;                     // 1: k_fs2 (else the next that applies), 3: k_feather_stream, 0: k_feather_fused_px1
     DevBuf tma_desc;                             // per 32x32 panorama tile: camera slots + source boxes, schedule order, ring plan
+    Fs2Plan fs2;                                 // second-generation streaming kernel (kernels_fstream2.cu): usable when fs2.ok
+    DevBuf fs2_desc;
+    unsigned long long tmap_clock = 0;
     int sm_count = 148;
     DevBuf bilin_lut;                            // 1024 x uint2 bilinear product weights (sb_device.cuh)
     int mb_variant = 1;                          // 1: RGBX fast path, 0: CV_16S band kernels
@@ -180,7 +189,8 @@ int make_slot(sb_compositor *c, Slot &s)
     }
     // packed rows: the device->host copy of the panorama into a contiguous host image is one linear DMA
     SB_TRY(s.out.create(c->dst_roi_final.height, c->dst_roi_final.width, c->cfg.output_type));
-    if (((size_t)c->dst_roi_final.width * elem_size(c->cfg.output_type)) % 4 == 0) {
+    // (the frame kernels store 4 pixels per thread: 32-bit words of 8UC3, 64-bit words of 16SC3 - keep the rows so aligned)
+    if (((size_t)c->dst_roi_final.width * elem_size(c->cfg.output_type)) % (c->cfg.output_type == SB_8UC3 ? 4 : 8) == 0) {
         s.out.v.step = (size_t)c->dst_roi_final.width * elem_size(c->cfg.output_type);
     }
     SB_TRY(s.out_mask.create(c->dst_roi_final.height, c->dst_roi_final.width, SB_8UC1));
@@ -536,6 +546,16 @@ int setup(sb_compositor *c)
             SB_CUDA(cudaMemcpyAsync(&h_status, status, sizeof h_status, cudaMemcpyDeviceToHost, s));
             SB_CUDA(cudaStreamSynchronize(s));
             c->feather_tma = h_status == 0 && n <= 16;
+            // ... and for its successor (4-byte entries, tensor-TMA source boxes)
+            std::vector<Fs2CamSetup> fc(n);
+            for (int i = 0; i < n; ++i) {
+                Camera &cam = c->cams[i];
+                SB_TRY(cam.fs2_blocks.ensure((size_t)FS2_BLOCK_BYTES * cam.fntx * cam.fnty));
+                fc[i] = Fs2CamSetup{static_cast<const uint2 *>(cam.feather_table.p), cam.feather_tstep, cam.ww, cam.wh, cam.tl.x - roi.x, cam.tl.y - roi.y,
+                                    cam.ftx0, cam.fty0, cam.fntx, cam.fnty, static_cast<unsigned char *>(cam.fs2_blocks.p)};
+                cam.tmaps.clear();
+            }
+            SB_TRY(fs2_build(fc.data(), n, roi.width, roi.height, c->stream_sharpness, c->sm_count, c->fs2_desc, &c->fs2, s));
         }
         SB_CUDA(cudaStreamSynchronize(s));
     }
@@ -773,9 +793,12 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
 
     cudaStream_t st = s.stream;
     DImage none;
-    bool stream_ok = c->feather_tma && c->feather_variant == 1;      // the streaming frame kernel (feather / no blending)
-    for (int i = 0; i < n && stream_ok; ++i)      // bulk copies need 16-byte aligned rows
-        stream_ok = src[i].step % 16 == 0 && src[i].step < (1ull << 24) && reinterpret_cast<uintptr_t>(src[i].data) % 16 == 0;
+    static_assert(FS2_W == SB_FTT_W && FS2_H == SB_FTT_H, "both streaming kernels use the same panorama tile grid");
+    bool aligned_src = true;                      // bulk / tensor copies need 16-byte aligned rows
+    for (int i = 0; i < n && aligned_src; ++i)
+        aligned_src = src[i].step % 16 == 0 && src[i].step < (1ull << 24) && reinterpret_cast<uintptr_t>(src[i].data) % 16 == 0;
+    const bool fs2_ok = c->fs2.ok && c->feather_variant == 1 && aligned_src;                       // the streaming frame kernel (feather / no blending)
+    const bool stream_ok = fs2_ok || (c->feather_tma && (c->feather_variant == 1 || c->feather_variant == 3) && aligned_src);   // ... or its round-1 predecessor
     if (blocks && !((cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused && c->mb_fast && c->mb_variant == 1) ||
                     (cfg.blender_kind == SB_BLEND_FEATHER && c->fused && c->feather_fast) ||
                     (cfg.blender_kind == SB_BLEND_NO && c->fused && c->feather_fast && stream_ok)))
@@ -841,7 +864,43 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
             bytes += img_bytes(src[i]) + 8.0 * c->cams[i].wh * ((sp[1] - sp[0]) + (sp[3] - sp[2]));
         }
         bytes += img_bytes(s.out.v) + (s.want_mask ? img_bytes(s.out_mask.v) : 0);
-        if (stream_ok) {
+        if (fs2_ok) {
+            Fs2Args a{};
+            a.n = n;
+            double fs2_bytes = c->fs2.table_bytes + img_bytes(s.out.v) + (s.want_mask ? img_bytes(s.out_mask.v) : 0);
+            for (int i = 0; i < n; ++i) {
+                Camera &cam = c->cams[i];
+                Fs2Cam &fc = a.cam[i];
+                fc.blocks = static_cast<const unsigned char *>(cam.fs2_blocks.p);
+                fc.gain = cam.gain;
+                fc.dx = cam.tl.x - c->dst_roi.x; fc.dy = cam.tl.y - c->dst_roi.y;
+                if (blocks) { fc.gmap = cam.gain_full.v.ptr<float>(); fc.gmstep = (unsigned)cam.gain_full.v.step; }
+                fs2_bytes += img_bytes(src[i]);
+                // tensor maps of this frame buffer (encoded on first sight, then cached)
+                Camera::TmapSet *hit = nullptr, *lru = nullptr;
+                for (auto &t : cam.tmaps) {
+                    if (t.p == src[i].data && t.step == src[i].step) { hit = &t; break; }
+                    if (!lru || t.stamp < lru->stamp) lru = &t;
+                }
+                if (!hit) {
+                    if (cam.tmaps.size() < 32) { cam.tmaps.emplace_back(); hit = &cam.tmaps.back(); }
+                    else hit = lru;
+                    hit->p = src[i].data; hit->step = src[i].step;
+                    SB_TRY(fs2_encode_tmaps(src[i].data, src[i].step, src[i].cols, src[i].rows, c->fs2.cls_w, hit->m));
+                }
+                hit->stamp = ++c->tmap_clock;
+                std::memcpy(&a.tmap[i * FS2_NCLS], hit->m, sizeof hit->m);
+            }
+            a.desc = static_cast<const uint4 *>(c->fs2_desc.p);
+            for (int k = 0; k < FS2_NCLS; ++k) a.cls_w[k] = c->fs2.cls_w[k];
+            a.sharpness = c->stream_sharpness;
+            a.no_blend = cfg.blender_kind == SB_BLEND_NO;
+            a.out = s.out.v.data; a.out_step = (unsigned)s.out.v.step;
+            a.out_mask = s.want_mask ? s.out_mask.v.ptr<uint8_t>() : nullptr; a.mask_step = (unsigned)s.out_mask.v.step;
+            a.pw = s.out.v.cols; a.ph = s.out.v.rows;
+            a.n_tiles = c->fs2.n_tiles;
+            PROF(a.no_blend ? "noblend_stream" : "feather_stream", fs2_bytes, launch_fs2(a, gain_on, s.out.v.type == SB_8UC3, c->fs2.grid, st));
+        } else if (stream_ok) {
             FeatherTmaArgs a{};
             a.n = n;
             for (int i = 0; i < n; ++i) {
@@ -1005,11 +1064,18 @@ int sb_compositor_set_fused(sb_compositor *c, int fused)
     c->fused = fused != 0;
     if (fused >= 10) {   // 10: CV_16S band kernels / px1 feather; 11: fast paths (default); 12 / 13: fast paths with one launch per
         // pyramid level / with the multi-level launches forced; 14: fast paths with the gather warp stage
-        c->feather_variant = fused == 10 ? 0 : 1; c->mb_variant = fused == 10 ? 0 : 1;
+        c->feather_variant = fused == 10 ? 0 : fused == 15 ? 3 : 1; c->mb_variant = fused == 10 ? 0 : 1;   // 15: the round-1 feather streaming kernel
         c->mb_multilevel = fused == 12 ? 0 : fused == 13 ? 1 : -1;
         c->mbs_enabled = fused != 14;                        // 14: default fast paths with the gather form of the multi-band warp stage
     }   // test/tuning hook: 10 / 11 select the kernel variant
     return SB_OK;
+}
+
+int sb_compositor_kernel_plan(const sb_compositor *c)
+{
+    if (!c) return SB_ERR_ASSERT;
+    if (c->cfg.blender_kind == SB_BLEND_MULTI_BAND) return c->mb_fast ? (c->mbs_ok ? 2 : 1) : 0;
+    return c->feather_fast ? (c->fs2.ok ? 2 : c->feather_tma ? 1 : 0) : 0;
 }
 
 int sb_compositor_set_depth(sb_compositor *c, int depth)

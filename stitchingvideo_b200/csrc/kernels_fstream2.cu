@@ -1,0 +1,662 @@
+// kernels_fstream2.cu — the feather / no-blend frame kernel, second generation (design notes: sb_fs2.h).
+//
+// Reference semantics replaced by ONE launch per frame set:
+//   RotationWarperBase::warp -> cv::remap INTER_LINEAR BORDER_REFLECT      warpers_inl.hpp:88-99
+//   GainCompensator::apply / BlocksGainCompensator::apply                  exposure_compensate.cpp:150-153, 225-246
+//   convertTo(CV_16S), FeatherBlender::feed x n, FeatherBlender::blend     blenders.cpp:136-155, 383-424
+//   Blender::feed / Blender::blend (no blending)                           blenders.cpp:81-112
+//   result.convertTo(CV_8U)                                                stitcher.cpp:313
+#include <algorithm>
+#include <climits>
+#include <vector>
+
+#include "sb_device.cuh"
+#include "sb_fs2.h"
+#include "sb_tma.cuh"
+
+namespace sb {
+using namespace sbd;
+using namespace sbt;
+
+#define SB_WEIGHT_EPS 1e-5f
+
+// ------------------------------------------------------------------------------------ setup kernels
+// pass 1: per (camera, tile) the source bounding box of the weighted entries of the row-major feather table
+//   table.x = x0 | y0 << 13 | (x1 == x0) << 26 | (y1 == y0) << 27 | unrepresentable << 28,  table.y = fx | fy << 5 | dist << 16
+__global__ void __launch_bounds__(256)
+k_fs2_bbox(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int tx0, int ty0, int ntx, float sharpness, Fs2Box *boxes)
+{
+    __shared__ int red[4][8];
+    bool all_one = true;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
+    for (int e = tid; e < FS2_W * FS2_H; e += blockDim.x) {
+        const int lx = e % FS2_W, ly = e / FS2_W;
+        const int x = (tx0 + (int)blockIdx.x) * FS2_W + lx - dx, y = (ty0 + (int)blockIdx.y) * FS2_H + ly - dy;
+        if ((unsigned)x >= (unsigned)ww || (unsigned)y >= (unsigned)wh) { all_one = false; continue; }
+        const uint2 t = reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(table) + (size_t)y * tstep)[x];
+        all_one = all_one && fminf(__fmul_rn((float)(t.y >> 16), sharpness), 1.f) == 1.f;
+        if ((t.y >> 16) == 0u) continue;
+        const int x0 = t.x & 0x1fff, y0 = (t.x >> 13) & 0x1fff;
+        const int x1 = x0 + 1 - (int)((t.x >> 26) & 1u), y1 = y0 + 1 - (int)((t.x >> 27) & 1u);
+        mnx = min(mnx, x0); mxx = max(mxx, x1); mny = min(mny, y0); mxy = max(mxy, y1);
+    }
+    mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
+    mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+    if (lane == 0) { red[0][warp] = mnx; red[1][warp] = mny; red[2][warp] = mxx; red[3][warp] = mxy; }
+    const int every = __syncthreads_and(all_one);
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w) {
+            mnx = min(mnx, red[0][w]); mny = min(mny, red[1][w]); mxx = max(mxx, red[2][w]); mxy = max(mxy, red[3][w]);
+        }
+        Fs2Box b{};
+        b.mnx = mnx; b.mny = mny; b.mxx = mxx; b.mxy = mxy; b.all_one = every;
+        boxes[blockIdx.y * ntx + blockIdx.x] = b;
+    }
+}
+
+// pass 2: the tile-major block of every (camera, tile): 1024 tap entries (sb_fs2.h) + 1024 weight-index bytes.
+// An x-folded pair (x1 == x0 at the source edge) is stored with fx = 0, a y-folded one with fy = 0: the weights of the
+// second column / row are then zero, sum w*p is the same integer, and the consumer has one code path (the bytes it
+// multiplies by zero lie inside the staged box or right behind it in shared memory).
+__global__ void __launch_bounds__(256)
+k_fs2_entries(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int tx0, int ty0, int ntx, const Fs2Place *place,
+              unsigned dist_cap, unsigned char *blocks)
+{
+    const Fs2Place pl = place[blockIdx.y * ntx + blockIdx.x];
+    unsigned char *blk = blocks + ((size_t)blockIdx.y * ntx + blockIdx.x) * FS2_BLOCK_BYTES;
+    uint32_t *ent = reinterpret_cast<uint32_t *>(blk);
+    unsigned char *plane = blk + FS2_ENT_BYTES;
+    for (int e = threadIdx.x; e < FS2_W * FS2_H; e += blockDim.x) {
+        const int lx = e % FS2_W, ly = e / FS2_W;
+        const int x = (tx0 + (int)blockIdx.x) * FS2_W + lx - dx, y = (ty0 + (int)blockIdx.y) * FS2_H + ly - dy;
+        uint32_t t = 0u;
+        unsigned d = 0u;
+        if (pl.valid && (unsigned)x < (unsigned)ww && (unsigned)y < (unsigned)wh) {
+            const uint2 s = reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(table) + (size_t)y * tstep)[x];
+            d = min(s.y >> 16, dist_cap);
+            if (d != 0u) {
+                const unsigned x0 = s.x & 0x1fffu, y0 = (s.x >> 13) & 0x1fffu;
+                unsigned fxy = s.y & 1023u;
+                if (s.x & (1u << 26)) fxy &= ~31u;
+                if (s.x & (1u << 27)) fxy &= 31u;
+                const unsigned off = (y0 - (unsigned)pl.ylo) * (unsigned)pl.pitch + x0 * 3u - (unsigned)pl.xlo;
+                t = (fxy << 22) | ((off >> 2) << 5) | ((off & 3u) << 3);
+            }
+        }
+        ent[e] = t;
+        plane[e] = (unsigned char)d;
+    }
+}
+
+int launch_fs2_bbox(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int tx0, int ty0, int ntx, int nty,
+                    float sharpness, Fs2Box *boxes, cudaStream_t s)
+{
+    k_fs2_bbox<<<dim3(ntx, nty), 256, 0, s>>>(table, tstep, ww, wh, dx, dy, tx0, ty0, ntx, sharpness, boxes);
+    SB_LAUNCHED();
+    return SB_OK;
+}
+int launch_fs2_entries(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int tx0, int ty0, int ntx, int nty,
+                       const Fs2Place *place, unsigned dist_cap, unsigned char *blocks, cudaStream_t s)
+{
+    k_fs2_entries<<<dim3(ntx, nty), 256, 0, s>>>(table, tstep, ww, wh, dx, dy, tx0, ty0, ntx, place, dist_cap, blocks);
+    SB_LAUNCHED();
+    return SB_OK;
+}
+int fs2_grid(int n_tiles, int sm_count) { return std::min(n_tiles, FS2_CTAS_PER_SM * sm_count); }
+
+// ------------------------------------------------------------------------------------ host-side setup
+// Per calibration: boxes of every (camera, tile) -> box width classes -> tile-major blocks -> per-tile descriptors in
+// schedule order with the shared-memory ring plan.
+//   descriptor (64 bytes per panorama tile):
+//   [0]     = {n_cams | short path << 2 | edge tile << 3 | ring units << 8, X0 | Y0 << 16, ring start unit,
+//              tiles of the CTA to retire first | (bytes the copies deliver >> 4) << 16}
+//   [1 + k] = per camera slot (ascending camera index = feed order)
+//             {box x (byte) | box y << 16, table block index, class | tensor copies << 4 | block KB << 8 | ring unit
+//              offset inside the tile << 16, camera}
+int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, int sm_count, DevBuf &desc_out, Fs2Plan *plan, cudaStream_t s)
+{
+    *plan = Fs2Plan{};
+    const unsigned cls_w[FS2_NCLS] = {96u, 160u, 224u, 256u};      // pitches of 32 (mod 128) bytes keep the 4 tile rows of a warp on distinct banks
+    for (int c = 0; c < FS2_NCLS; ++c) plan->cls_w[c] = cls_w[c];
+    // the weight index is one byte: the weight must saturate by distance 255 (Blender::NO: the mask byte itself)
+    if (!(sharpness > 0.f) || fminf((float)(255.f * sharpness), 1.f) != 1.f) return SB_OK;
+    const int tiles_x = div_up(pw, FS2_W), tiles_y = div_up(ph, FS2_H), n_tiles = tiles_x * tiles_y;
+    std::vector<std::vector<Fs2Box>> boxes(n);
+    std::vector<std::vector<Fs2Place>> places(n);
+    DevBuf tmp;
+    for (int i = 0; i < n; ++i) {
+        const Fs2CamSetup &c = cams[i];
+        const size_t nt = (size_t)c.ntx * c.nty;
+        boxes[i].resize(nt);
+        SB_TRY(tmp.ensure(nt * sizeof(Fs2Box)));
+        SB_TRY(launch_fs2_bbox(c.table, c.tstep, c.ww, c.wh, c.dx, c.dy, c.tx0, c.ty0, c.ntx, c.nty, sharpness, static_cast<Fs2Box *>(tmp.p), s));
+        SB_CUDA(cudaMemcpyAsync(boxes[i].data(), tmp.p, nt * sizeof(Fs2Box), cudaMemcpyDeviceToHost, s));
+        SB_CUDA(cudaStreamSynchronize(s));
+        places[i].assign(nt, Fs2Place{0, 0, 0, 0});
+        for (size_t t = 0; t < nt; ++t) {
+            const Fs2Box &b = boxes[i][t];
+            if (b.mxx < b.mnx) continue;
+            const int xlo = (b.mnx * 3) & ~15, need_w = (b.mxx + 1) * 3 - xlo, rows = b.mxy - b.mny + 1;
+            int cls = 0;
+            while (cls < FS2_NCLS && (int)cls_w[cls] < need_w) ++cls;
+            if (cls == FS2_NCLS || rows > FS2_ROWS * FS2_MAX_OPS) return SB_OK;       // a box the ring cannot stage: plan->ok stays false
+            places[i][t] = Fs2Place{xlo, b.mny, (int)cls_w[cls], 1 | (cls << 4) | (div_up(rows, FS2_ROWS) << 8)};
+        }
+        SB_TRY(tmp.ensure(nt * sizeof(Fs2Place)));
+        SB_CUDA(cudaMemcpyAsync(tmp.p, places[i].data(), nt * sizeof(Fs2Place), cudaMemcpyHostToDevice, s));
+        SB_TRY(launch_fs2_entries(c.table, c.tstep, c.ww, c.wh, c.dx, c.dy, c.tx0, c.ty0, c.ntx, c.nty, static_cast<const Fs2Place *>(tmp.p),
+                                  255u, c.blocks, s));
+        SB_CUDA(cudaStreamSynchronize(s));
+    }
+    const size_t per = 1 + FS2_MAXC;
+    std::vector<uint4> d((size_t)n_tiles * per, make_uint4(0u, 0u, 0u, 0u));
+    double table_bytes = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+        const int tx = t % tiles_x, ty = t / tiles_x;
+        uint4 *o = &d[(size_t)t * per];
+        int k = 0, one = 0;
+        int slot_cam[FS2_MAXC];
+        size_t slot_blk[FS2_MAXC];
+        for (int i = 0; i < n; ++i) {
+            const int rx = tx - cams[i].tx0, ry = ty - cams[i].ty0;
+            if ((unsigned)rx >= (unsigned)cams[i].ntx || (unsigned)ry >= (unsigned)cams[i].nty) continue;
+            const size_t blk = (size_t)ry * cams[i].ntx + rx;
+            if (!(places[i][blk].valid & 1)) continue;
+            if (k == FS2_MAXC) return SB_OK;                                          // more cameras than slots: plan->ok stays false
+            slot_cam[k] = i; slot_blk[k] = blk; one = boxes[i][blk].all_one;
+            ++k;
+        }
+        const unsigned short_path = (k == 1 && one) ? 1u : 0u;
+        const unsigned blk_kb = short_path ? FS2_ENT_BYTES / 1024 : FS2_BLOCK_BYTES / 1024;
+        unsigned units = 0, tx_bytes = 0;
+        for (int j = 0; j < k; ++j) {
+            const Fs2Place &pl = places[slot_cam[j]][slot_blk[j]];
+            const unsigned cls = (unsigned)(pl.valid >> 4) & 15u, nops = (unsigned)pl.valid >> 8;
+            const unsigned bytes = blk_kb * 1024u + nops * FS2_ROWS * (unsigned)pl.pitch;
+            o[1 + j] = make_uint4((unsigned)pl.xlo | ((unsigned)pl.ylo << 16), (unsigned)slot_blk[j], cls | (nops << 4) | (blk_kb << 8) | (units << 16),
+                                  (unsigned)slot_cam[j]);
+            units += (bytes + 127u) >> 7;
+            tx_bytes += bytes;
+            table_bytes += blk_kb * 1024.0;
+        }
+        const unsigned X0 = (unsigned)(tx * FS2_W), Y0 = (unsigned)(ty * FS2_H);
+        const unsigned edge = ((int)X0 + FS2_W > pw || (int)Y0 + FS2_H > ph) ? 1u : 0u;
+        o[0] = make_uint4((unsigned)k | (short_path << 2) | (edge << 3) | (units << 8), X0 | (Y0 << 16), 0u, (tx_bytes >> 4) << 16);
+    }
+    // Schedule order: CTA b takes positions b, b + G, ... of the descriptor array, so listing the tiles by descending cost
+    // (blended tiles with 3, 2, 1 cameras, then the single-camera short-path tiles, then empty ones; row-major inside a
+    // class) deals every CTA the same number of tiles of each class, the expensive ones first ...
+    const int grid = fs2_grid(n_tiles, sm_count);
+    std::vector<int> order(n_tiles);
+    for (int t = 0; t < n_tiles; ++t) order[t] = t;
+    auto cost = [&](int t) {
+        const unsigned x = d[(size_t)t * per].x;
+        const int nc = (int)(x & 3u);
+        return nc == 0 ? 0 : (x & 4u) ? 1 : 1 + nc;
+    };
+    std::stable_sort(order.begin(), order.end(), [&](int l, int r) { return cost(l) > cost(r); });
+    // ... except that every CTA's FIRST tiles are cheap ones: the first wave of copies is what the consumers wait for at
+    // kernel start, and a one-camera tile is 2-3x fewer bytes
+    if (n_tiles >= 2 * grid * FS2_GROUPS) std::rotate(order.begin(), order.end() - (size_t)grid * FS2_GROUPS, order.end());
+    std::vector<uint4> o((size_t)n_tiles * per);
+    for (int t = 0; t < n_tiles; ++t)
+        for (size_t j = 0; j < per; ++j) o[(size_t)t * per + j] = d[(size_t)order[t] * per + j];
+    // The shared-memory ring plan.  CTA b walks positions b, b + G, ...; a tile takes `units` contiguous 128-byte ring units
+    // at the head, wrapping to 0 when the end of the ring is too short; space is handed back in tile order.  Both are a pure
+    // function of the tile sizes, so the start unit of every tile and the number of the CTA's tiles that must have been
+    // consumed before its copies may land are computed here, once: [0].z = start unit, [0].w low half = tiles to retire first
+    // (also covers the reuse of the tile's stage entry).  The producer warp then needs no bookkeeping at all.
+    constexpr int RING_UNITS = FS2_RING_BYTES / 128;
+    for (int b = 0; b < grid; ++b) {
+        int hist[FS2_STAGES];
+        int head = 0, tail = 0, oldest = 0, seq = 0;
+        for (int tile = b; tile < n_tiles; tile += grid, ++seq) {
+            uint4 &d0 = o[(size_t)tile * per];
+            const int units = (int)(d0.x >> 8);
+            int start;
+            for (;;) {
+                if (seq - oldest < FS2_STAGES) {
+                    if (seq == oldest) head = tail = 0;     // nothing in flight
+                    if (head >= tail) {                     // in use: [tail, head)
+                        if (head + units <= RING_UNITS) { start = head; break; }
+                        if (units < tail) { start = 0; break; }
+                    } else if (head + units < tail) {       // in use: [tail, end) and [0, head)
+                        start = head; break;
+                    }
+                }
+                ++oldest;
+                tail = oldest < seq ? hist[oldest % FS2_STAGES] : head;
+            }
+            head = start + units;
+            hist[seq % FS2_STAGES] = start;
+            d0.z = (unsigned)start;
+            d0.w |= (unsigned)oldest;
+        }
+    }
+    SB_TRY(desc_out.ensure(o.size() * sizeof(uint4)));
+    SB_CUDA(cudaMemcpyAsync(desc_out.p, o.data(), o.size() * sizeof(uint4), cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    plan->n_tiles = n_tiles; plan->grid = grid; plan->table_bytes = table_bytes; plan->ok = true;
+    return SB_OK;
+}
+
+// ------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*PFN_tmap_encode)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmap_encode tmap_encoder()
+{
+    static PFN_tmap_encode fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_tmap_encode>(p);
+    }
+    return fn;
+}
+// The 8UC3 source image as a 2-D tensor of bytes {row bytes, rows}; a copy brings cls_w[c] x FS2_ROWS bytes densely
+// packed into shared memory, out-of-range bytes read as zero (they are only ever multiplied by zero weights).
+int fs2_encode_tmaps(const void *src, size_t sstep, int sw, int sh, const unsigned cls_w[FS2_NCLS], CUtensorMap out[FS2_NCLS])
+{
+    PFN_tmap_encode enc = tmap_encoder();
+    if (!enc) return fail(SB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t gdim[2] = {(cuuint64_t)sw * 3u, (cuuint64_t)sh};
+    const cuuint64_t gstride[1] = {(cuuint64_t)sstep};
+    const cuuint32_t estr[2] = {1u, 1u};
+    for (int c = 0; c < FS2_NCLS; ++c) {
+        const cuuint32_t box[2] = {cls_w[c], (cuuint32_t)FS2_ROWS};
+        const CUresult r = enc(&out[c], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2u, const_cast<void *>(src), gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(SB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %dx%d source, pitch %zu, box %u", (int)r, sw, sh, sstep, cls_w[c]);
+    }
+    return SB_OK;
+}
+
+// ------------------------------------------------------------------------------------ frame kernel
+struct Fs2Smem {
+    unsigned char ring[FS2_RING_BYTES];
+    uint2 lut[1024];                                        // bilinear product weights x 64 (see fs2_lut_entry)
+    uint4 desc[FS2_STAGES][1 + FS2_MAXC];                   // stage copy of the tile descriptor, rewritten by the producer:
+                                                            //   [0] = {flags, X0 | Y0 << 16, output byte offset, mask byte offset}
+                                                            //   [1 + k] = {slot offset in the ring, box pitch, -, camera}
+    uint64_t full[FS2_STAGES], empty[FS2_STAGES];
+};
+static_assert(sizeof(Fs2Smem) * FS2_CTAS_PER_SM + 1024 * FS2_CTAS_PER_SM <= 232448, "shared memory of one SM");
+
+// 2-D tensor copy global -> shared (UTMALDG), completion on `bar`
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap *map, int x, int y, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+// mbarrier wait without polling instructions: try_wait suspends the warp in hardware until the phase completes or a
+// time limit passes (only then does the loop go round)
+__device__ __forceinline__ void mbar_wait_hw(uint64_t *bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
+}
+
+// Bilinear product weights of table index fx | fy << 5, times 64: {w00 | w01 << 16, w10 | w11 << 16}, w = a*b*64 with
+// a*b <= 1024 (sb_device.cuh: bilin_weights).  The factor 64 puts the result byte of (sum ab*p + 512) >> 10 into
+// byte 2 of the 32-bit dot product.  Entry (0, 0) would need 1024 * 64 = 2^16: it is stored as 1023 * 64, which gives
+// the same byte for every 8-bit p, with and without the "- 1" of the full-weight path:
+//   (1023 p + 512) >> 10 == p   and   (1023 p - 512) >> 10 == p - 1   for p in 1..255  (0 <= 512 - p <= 1023).
+__device__ __forceinline__ uint2 fs2_lut_entry(int i)
+{
+    uint2 w = bilin_weights(i & 31, i >> 5);
+    if (i == 0) w.x = 1023u;
+    return make_uint2(w.x << 6, w.y << 6);
+}
+
+// One output pixel of one camera: three 32-bit sums s_c = 64 * (sum ab*p_c) + BIAS; the pixel value is byte 2.
+// e = table entry (sb_fs2.h), box = byte offset of the staged source box in shared memory, pitch = its row pitch.
+template <int BIAS>
+__device__ __forceinline__ void fs2_pixel(const unsigned char *sm, uint32_t box, uint32_t pitch, uint32_t e, unsigned &s0, unsigned &s1, unsigned &s2)
+{
+    const uint2 bw = *reinterpret_cast<const uint2 *>(sm + FS2_RING_BYTES + (e >> 19));
+    const unsigned char *r0 = sm + box + ((e >> 3) & 0x3ffcu);
+    const unsigned char *r1 = r0 + pitch;
+    const unsigned a0 = *reinterpret_cast<const uint32_t *>(r0), a1 = *reinterpret_cast<const uint32_t *>(r0 + 4),
+                   a2 = *reinterpret_cast<const uint32_t *>(r0 + 8);
+    const unsigned b0 = *reinterpret_cast<const uint32_t *>(r1), b1 = *reinterpret_cast<const uint32_t *>(r1 + 4),
+                   b2 = *reinterpret_cast<const uint32_t *>(r1 + 8);
+    const unsigned lo0 = __funnelshift_r(a0, a1, e), hi0 = __funnelshift_r(a1, a2, e);     // (shift amount = e mod 32 = 8 * byte shift)
+    const unsigned lo1 = __funnelshift_r(b0, b1, e), hi1 = __funnelshift_r(b1, b2, e);
+    const unsigned m0 = __byte_perm(lo0, hi0, 0x5241), m1 = __byte_perm(lo1, hi1, 0x5241);     // [G0 G1 B0 B1] per row
+    const unsigned p0 = __byte_perm(lo0, lo1, 0x7430), p1 = __byte_perm(m0, m1, 0x5410), p2 = __byte_perm(m0, m1, 0x7632);
+    s0 = __dp2a_hi(bw.y, p0, __dp2a_lo(bw.x, p0, (unsigned)BIAS));
+    s1 = __dp2a_hi(bw.y, p1, __dp2a_lo(bw.x, p1, (unsigned)BIAS));
+    s2 = __dp2a_hi(bw.y, p2, __dp2a_lo(bw.x, p2, (unsigned)BIAS));
+}
+
+// exposure gain of camera `c` at panorama pixel (X, Y): the scalar of GainCompensator or the resized block map
+__device__ __forceinline__ float fs2_gain(const Fs2Cam &c, int X, int Y)
+{
+    return c.gmap ? __ldg(reinterpret_cast<const float *>(reinterpret_cast<const char *>(c.gmap) + (size_t)(Y - c.dy) * c.gmstep) + (X - c.dx)) : c.gain;
+}
+// saturate_cast<uchar>(v * gain)
+__device__ __forceinline__ unsigned fs2_apply_gain(unsigned v, float g)
+{
+    return (unsigned)min(max(__float2int_rn(__fmul_rn((float)v, g)), 0), 255);
+}
+
+// The 4 pixels x 3 channels of one thread, each value in byte B of its register (the byte above it zero), as the 12 (8UC3)
+// or 24 (16SC3) output bytes.  Full tiles: vector stores; edge tiles: per pixel, guarded.
+template <bool OUT8, int B>
+__device__ __forceinline__ void fs2_store_quad(unsigned char *o, const unsigned (&v)[4][3], bool edge, int nx, bool row_ok)
+{
+    if (!edge) {
+        if (OUT8) {
+            constexpr unsigned S = (unsigned)B | ((unsigned)(B + 4) << 4);
+            uint32_t *q = reinterpret_cast<uint32_t *>(o);
+            q[0] = __byte_perm(__byte_perm(v[0][0], v[0][1], S), __byte_perm(v[0][2], v[1][0], S), 0x5410);
+            q[1] = __byte_perm(__byte_perm(v[1][1], v[1][2], S), __byte_perm(v[2][0], v[2][1], S), 0x5410);
+            q[2] = __byte_perm(__byte_perm(v[2][2], v[3][0], S), __byte_perm(v[3][1], v[3][2], S), 0x5410);
+        } else {
+            constexpr unsigned S = (unsigned)B | ((unsigned)(B + 1) << 4) | ((unsigned)(B + 4) << 8) | ((unsigned)(B + 5) << 12);
+            uint2 *q = reinterpret_cast<uint2 *>(o);
+            q[0] = make_uint2(__byte_perm(v[0][0], v[0][1], S), __byte_perm(v[0][2], v[1][0], S));
+            q[1] = make_uint2(__byte_perm(v[1][1], v[1][2], S), __byte_perm(v[2][0], v[2][1], S));
+            q[2] = make_uint2(__byte_perm(v[2][2], v[3][0], S), __byte_perm(v[3][1], v[3][2], S));
+        }
+        return;
+    }
+    if (!row_ok) return;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        if (p >= nx) break;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const unsigned val = (v[p][k] >> (8 * B)) & 0xffu;
+            if (OUT8) o[p * 3 + k] = (unsigned char)val;
+            else reinterpret_cast<short *>(o)[p * 3 + k] = (short)val;
+        }
+    }
+}
+__device__ __forceinline__ void fs2_store_mask(uint8_t *m, unsigned word, bool edge, int nx, bool row_ok)
+{
+    if (!edge) { *reinterpret_cast<uint32_t *>(m) = word; return; }
+    if (!row_ok) return;
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+        if (p < nx) m[p] = (uint8_t)(word >> (8 * p));
+}
+
+#ifdef SB_FS2_TRACE
+__device__ __forceinline__ unsigned long long fs2_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define FS2_TRACE(SLOT, SEQ)                                                                        \
+    do {                                                                                            \
+        if (a.trace && (SEQ) < 64) a.trace[((size_t)blockIdx.x * 64 + (SEQ)) * 4 + (SLOT)] = fs2_now(); \
+    } while (0)
+#else
+#define FS2_TRACE(SLOT, SEQ) do { } while (0)
+#endif
+
+// NOBLEND: Blender::feed / blend without blending (blenders.cpp:81-112): the pixel of the LAST camera (feed order)
+// whose mask is non-zero, dst_mask = OR of the mask bytes, 0 where no camera has a mask.
+template <bool GAIN, bool OUT8, bool NOBLEND>
+__global__ void __launch_bounds__(FS2_THREADS, FS2_CTAS_PER_SM)
+k_fs2(const __grid_constant__ Fs2Args a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Fs2Smem &sm = *reinterpret_cast<Fs2Smem *>(smem_raw);
+    const unsigned char *const smb = smem_raw;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x;
+    if (tid == 0) {
+        for (int s = 0; s < FS2_STAGES; ++s) {
+            mbar_init(&sm.full[s], 1);                      // the producer's arrive (+ the copies' expect_tx)
+            mbar_init(&sm.empty[s], FS2_GROUP_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == FS2_GROUPS * FS2_GROUP_WARPS) {
+        // ------------------------------------------------ producer warp
+        // Tiles blockIdx.x, + G, + 2G ... in order.  Where a tile lands in the ring and how many of the CTA's tiles must
+        // have been consumed before its copies may land come from the per-calibration ring plan in the descriptor.
+        // Lane l issues copy l of the tile: per camera one bulk copy (table block) and one tensor copy per 8 box rows.
+        const uint32_t ring0 = smem_u32(&sm.ring[0]);
+        const uint4 *dp = a.desc + (size_t)blockIdx.x * (1 + FS2_MAXC);
+        const size_t dstride = (size_t)G * (1 + FS2_MAXC);
+        uint4 nx0 = make_uint4(0u, 0u, 0u, 0u), nx1 = nx0, nx2 = nx0, nx3 = nx0;
+        if ((int)blockIdx.x < a.n_tiles) { nx0 = __ldg(dp); nx1 = __ldg(dp + 1); nx2 = __ldg(dp + 2); nx3 = __ldg(dp + 3); }
+        int retired = 0;
+        int seq = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += G, ++seq) {
+            const uint4 d0 = nx0, d1 = nx1, d2 = nx2, d3 = nx3;
+            dp += dstride;
+            if (tile + G < a.n_tiles) { nx0 = __ldg(dp); nx1 = __ldg(dp + 1); nx2 = __ldg(dp + 2); nx3 = __ldg(dp + 3); }
+            const int stage = seq % FS2_STAGES;
+            const int nc = (int)(d0.x & 3u);
+            const int need = max((int)(d0.w & 0xffffu), seq - FS2_STAGES + 1);
+            for (; retired < need; ++retired)              // groups finish tiles out of order: every tile is awaited once, in order
+                mbar_wait_hw(&sm.empty[retired % FS2_STAGES], (unsigned)(retired / FS2_STAGES) & 1u);
+            const uint32_t tile_off = d0.z * 128u;          // ring byte offset of the tile
+            if (lane <= FS2_MAXC) {
+                uint4 ds;
+                if (lane == 0) {                            // tile origin -> byte offsets of its first pixel in the panorama and the mask
+                    const unsigned X0 = d0.y & 0xffffu, Y0 = d0.y >> 16;
+                    ds = make_uint4(d0.x, d0.y, Y0 * a.out_step + X0 * (OUT8 ? 3u : 6u), Y0 * a.mask_step + X0);
+                } else {
+                    const uint4 r = lane == 1 ? d1 : lane == 2 ? d2 : d3;
+                    ds = make_uint4(tile_off + (r.z >> 16) * 128u, a.cls_w[r.z & 3u], 0u, r.w);
+                }
+                sm.desc[stage][lane] = ds;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (nc == 0) mbar_arrive(&sm.full[stage]);
+                else mbar_arrive_expect_tx(&sm.full[stage], (d0.w >> 16) << 4);
+                FS2_TRACE(0, seq);
+            }
+            __syncwarp();
+            // copies: lane -> (camera slot k, copy j of it)
+            const int n0 = nc > 0 ? 1 + (int)((d1.z >> 4) & 15u) : 0, n1 = nc > 1 ? 1 + (int)((d2.z >> 4) & 15u) : 0,
+                      n2 = nc > 2 ? 1 + (int)((d3.z >> 4) & 15u) : 0;
+            if (lane < n0 + n1 + n2) {
+                const int k = (lane >= n0) + (lane >= n0 + n1);
+                const int j = lane - (k == 0 ? 0 : k == 1 ? n0 : n0 + n1);
+                const uint4 r = k == 0 ? d1 : k == 1 ? d2 : d3;
+                const unsigned cam = r.w & 15u, cls = r.z & 3u, blk_bytes = ((r.z >> 8) & 15u) << 10;
+                const uint32_t slot = ring0 + tile_off + (r.z >> 16) * 128u;
+                if (j == 0) {
+                    bulk_g2s_addr(slot, a.cam[cam].blocks + (size_t)r.y * FS2_BLOCK_BYTES, blk_bytes, &sm.full[stage]);
+                } else {
+                    const unsigned wb = a.cls_w[cls];
+                    tma_load_2d(slot + blk_bytes + (unsigned)(j - 1) * wb * FS2_ROWS, &a.tmap[cam * FS2_NCLS + cls],
+                                (int)(r.x & 0xffffu), (int)(r.x >> 16) + (j - 1) * FS2_ROWS, &sm.full[stage]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------- consumer warps
+    // group g = warp / 8 works on tiles seq = g, g + GROUPS, ... of the CTA's sequence; inside a group warp w covers tile
+    // rows 4w .. 4w+3, lane = (row << 3 | quad), a thread owns pixels 4*quad .. 4*quad+3 of its row
+    for (int i = tid; i < 1024; i += FS2_GROUPS * FS2_GROUP_WARPS * 32) sm.lut[i] = fs2_lut_entry(i);
+    asm volatile("bar.sync 1, %0;" ::"n"(FS2_GROUPS * FS2_GROUP_WARPS * 32) : "memory");
+    const int grp = warp / FS2_GROUP_WARPS, slab = warp % FS2_GROUP_WARPS;
+    const int ty = slab * 4 + (lane >> 3), tx = (lane & 7) * 4;
+    const uint32_t tab_off = (uint32_t)(ty * FS2_W + tx) * 4u, plane_off = (uint32_t)FS2_ENT_BYTES + (uint32_t)(ty * FS2_W + tx);
+    unsigned char *const out_t = reinterpret_cast<unsigned char *>(a.out) + ((unsigned)ty * a.out_step + (unsigned)tx * (OUT8 ? 3u : 6u));
+    uint8_t *const mask_t = a.out_mask ? a.out_mask + ((unsigned)ty * a.mask_step + (unsigned)tx) : nullptr;
+    int seq = grp;
+    for (int tile = blockIdx.x + grp * G; tile < a.n_tiles; tile += FS2_GROUPS * G, seq += FS2_GROUPS) {
+        const int stage = seq % FS2_STAGES;
+        mbar_wait_hw(&sm.full[stage], (unsigned)(seq / FS2_STAGES) & 1u);
+        if (tid % (FS2_GROUP_WARPS * 32) == 0) FS2_TRACE(1, seq);
+        const uint4 d0 = sm.desc[stage][0];
+        const int nc = (int)(d0.x & 3u);
+        const bool edge = (d0.x & 8u) != 0u;                // block-uniform: the tile crosses the panorama's right / bottom edge
+        const int X = (int)(d0.y & 0xffffu) + tx, Y = (int)(d0.y >> 16) + ty;
+        const int nx = edge ? min(max(a.pw - X, 0), 4) : 4;
+        const bool row_ok = !edge || Y < a.ph;
+        unsigned char *const o = out_t + d0.z;
+        uint8_t *const mo = mask_t ? mask_t + d0.w : nullptr;
+        unsigned v[4][3];
+        if (d0.x & 4u) {
+            // Short path (block-uniform; ~2/3 of a ring panorama): ONE camera with weight exactly 1.0f on every pixel of
+            // the tile.  Then dst = short(p * 1.0f) = p, dst_w = 1.0f, and normalizeUsingWeightMap gives
+            // short(p / (1.0f + 1e-5f)) = p - 1 for p in 1..255 and 0 for p = 0 (the quotient lies strictly between
+            // p - 1 and p); the mask is 255.  No float op at all: max(64 * sum ab*p - 64 * 512, 0), byte 2.
+            const uint4 rec = sm.desc[stage][1];
+            const uint4 e4 = *reinterpret_cast<const uint4 *>(smb + rec.x + tab_off);
+            const uint32_t box = rec.x + (uint32_t)FS2_ENT_BYTES;
+            const uint32_t ee[4] = {e4.x, e4.y, e4.z, e4.w};
+            constexpr int BIAS = (!GAIN && !NOBLEND) ? -32768 : 32768;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                fs2_pixel<BIAS>(smb, box, rec.y, ee[p], v[p][0], v[p][1], v[p][2]);
+                if (!GAIN && !NOBLEND) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) v[p][k] = (unsigned)max((int)v[p][k], 0);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[stage]);   // this warp no longer reads the stage
+            if (GAIN) {
+                const Fs2Cam &c = a.cam[rec.w & 15u];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float g = (c.gmap && p >= nx) ? 1.f : fs2_gain(c, X + p, Y);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        unsigned q = fs2_apply_gain(v[p][k] >> 16, g);
+                        if (!NOBLEND) q -= min(q, 1u);
+                        v[p][k] = q;
+                    }
+                }
+                fs2_store_quad<OUT8, 0>(o, v, edge, nx, row_ok);
+            } else {
+                fs2_store_quad<OUT8, 2>(o, v, edge, nx, row_ok);
+            }
+            if (mo) fs2_store_mask(mo, 0xffffffffu, edge, nx, row_ok);
+        } else if (NOBLEND) {
+            // which camera slot supplies each pixel (the last one in feed order with a non-zero mask), OR of the masks
+            int sel[4] = {-1, -1, -1, -1};
+            unsigned mor = 0u;
+            for (int k = 0; k < nc; ++k) {
+                const unsigned m4 = *reinterpret_cast<const uint32_t *>(smb + sm.desc[stage][1 + k].x + plane_off);
+                mor |= m4;
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    if ((m4 >> (8 * p)) & 0xffu) sel[p] = k;
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                v[p][0] = v[p][1] = v[p][2] = 0u;
+                if (sel[p] < 0) continue;
+                const uint4 rec = sm.desc[stage][1 + sel[p]];
+                const uint32_t e = *reinterpret_cast<const uint32_t *>(smb + rec.x + tab_off + 4u * p);
+                fs2_pixel<32768>(smb, rec.x + (uint32_t)FS2_BLOCK_BYTES, rec.y, e, v[p][0], v[p][1], v[p][2]);
+                if (GAIN) {
+                    const float g = fs2_gain(a.cam[rec.w & 15u], X + p, Y);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) v[p][k] = fs2_apply_gain(v[p][k] >> 16, g) << 16;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[stage]);
+            fs2_store_quad<OUT8, 2>(o, v, edge, nx, row_ok);
+            if (mo) fs2_store_mask(mo, mor, edge, nx, row_ok);
+        } else {
+            // FeatherBlender::feed over the cameras of the tile in feed order (ascending camera index): per channel
+            // dst += short(src * w) as integers, dst_w += w in float.  float(v): byte 2 of the sum under the exponent of
+            // 2^23, minus 2^23; short(t): bits of (t + 2^23) rounded toward zero, summed as integers.
+            float wsum[4] = {0.f, 0.f, 0.f, 0.f};
+            unsigned acc[4][3];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[p][0] = acc[p][1] = acc[p][2] = 0u;
+            for (int k = 0; k < nc; ++k) {
+                const uint4 rec = sm.desc[stage][1 + k];
+                const uint4 e4 = *reinterpret_cast<const uint4 *>(smb + rec.x + tab_off);
+                const unsigned d4 = *reinterpret_cast<const uint32_t *>(smb + rec.x + plane_off);
+                const uint32_t box = rec.x + (uint32_t)FS2_BLOCK_BYTES;
+                const uint32_t ee[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const unsigned dist = (d4 >> (8 * p)) & 0xffu;      // 0: short(p * 0) == 0 and dst_w += 0 -> contributes nothing
+                    const float w = fminf(__fmul_rn((float)dist, a.sharpness), 1.f);       // createWeightMap
+                    wsum[p] = __fadd_rn(wsum[p], w);
+                    unsigned s0, s1, s2;
+                    fs2_pixel<32768>(smb, box, rec.y, ee[p], s0, s1, s2);
+                    float f0, f1, f2;
+                    if (GAIN) {                             // saturate_cast<uchar>(p * gain)
+                        const float g = (dist != 0u) ? fs2_gain(a.cam[rec.w & 15u], X + p, Y) : 1.f;
+                        f0 = (float)fs2_apply_gain(s0 >> 16, g); f1 = (float)fs2_apply_gain(s1 >> 16, g); f2 = (float)fs2_apply_gain(s2 >> 16, g);
+                    } else {
+                        f0 = __fsub_rn(__uint_as_float(__byte_perm(s0, 0x4b000000u, 0x7442)), 8388608.f);
+                        f1 = __fsub_rn(__uint_as_float(__byte_perm(s1, 0x4b000000u, 0x7442)), 8388608.f);
+                        f2 = __fsub_rn(__uint_as_float(__byte_perm(s2, 0x4b000000u, 0x7442)), 8388608.f);
+                    }
+                    acc[p][0] += __float_as_uint(__fadd_rz(__fmul_rn(f0, w), 8388608.f));      // static_cast<short>(src * w)
+                    acc[p][1] += __float_as_uint(__fadd_rz(__fmul_rn(f1, w), 8388608.f));
+                    acc[p][2] += __float_as_uint(__fadd_rz(__fmul_rn(f2, w), 8388608.f));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[stage]);
+            // FeatherBlender::blend: normalizeUsingWeightMap, mask = weight > eps, zero unmasked (the sums are already
+            // zero there: every w <= 1e-5 makes every short(src * w) zero), convertTo(8U)
+            unsigned mword = 0u;
+            const unsigned magic = (unsigned)nc * 0x4b000000u;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                if (wsum[p] > SB_WEIGHT_EPS) mword |= 0xffu << (8 * p);
+                const SharedDiv div(__fadd_rn(wsum[p], SB_WEIGHT_EPS));                    // in [1e-5, n + 1e-5]: fast-path range
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float s = __fsub_rn(__uint_as_float((acc[p][k] - magic) | 0x4b000000u), 8388608.f);
+                    v[p][k] = __float_as_uint(__fadd_rz(div(s), 8388608.f));
+                }
+            }
+            fs2_store_quad<OUT8, 0>(o, v, edge, nx, row_ok);
+            if (mo) fs2_store_mask(mo, mword, edge, nx, row_ok);
+        }
+        if (tid % (FS2_GROUP_WARPS * 32) == 0) FS2_TRACE(2, seq);
+    }
+}
+
+int launch_fs2(const Fs2Args &a, bool apply_gain, bool out8, int grid, cudaStream_t s)
+{
+    SB_ASSERT(a.sharpness > 0.f && a.desc && a.n_tiles > 0 && a.n <= SB_MAX_CAMERAS);
+    SB_ASSERT(a.pw < 65536 && a.ph < 65536 && (unsigned long long)a.ph * a.out_step < (1ull << 32) && (unsigned long long)a.ph * a.mask_step < (1ull << 32));
+    SB_ASSERT(reinterpret_cast<uintptr_t>(a.out) % 8 == 0 && a.out_step % (out8 ? 4 : 8) == 0);
+    SB_ASSERT(!a.out_mask || (reinterpret_cast<uintptr_t>(a.out_mask) % 4 == 0 && a.mask_step % 4 == 0));
+    const size_t smem = sizeof(Fs2Smem);
+    static bool configured_dev[64][8] = {};                  // the attribute is per device (context)
+    int dev = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    bool *configured = configured_dev[dev & 63];
+    const void *fn[8] = {(const void *)k_fs2<false, false, false>, (const void *)k_fs2<false, true, false>,
+                         (const void *)k_fs2<true, false, false>, (const void *)k_fs2<true, true, false>,
+                         (const void *)k_fs2<false, false, true>, (const void *)k_fs2<false, true, true>,
+                         (const void *)k_fs2<true, false, true>, (const void *)k_fs2<true, true, true>};
+    const int v = (a.no_blend ? 4 : 0) + (apply_gain ? 2 : 0) + (out8 ? 1 : 0);
+    if (!configured[v]) {
+        SB_CUDA(cudaFuncSetAttribute(fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[v] = true;
+    }
+    void *params[] = {const_cast<Fs2Args *>(&a)};
+    SB_CUDA(cudaLaunchKernel(fn[v], dim3(grid), dim3(FS2_THREADS), params, smem, s));
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
+}  // namespace sb

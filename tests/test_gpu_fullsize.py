@@ -32,12 +32,13 @@ def test_full_size_frame_matches_oracle(gpu, rig):
     comp = gpu.Compositor(size, Ks, Rs, warper=spec["warper"], scale=spec["scale"], blender=spec["blender"], num_bands=5,
                           gains=spec["gain_values"])
     cal = P.Calibration(size, Ks, Rs, spec["warper"], spec["scale"])
+    assert comp.kernel_plan() == 2, "the BASELINE configs must run on the newest frame kernels, not on a fallback"
     for i in range(n):
         roi = comp.camera_roi(i)
         assert (roi[0], roi[1]) == cal.corners[i] and (roi[2], roi[3]) == cal.sizes[i]
     frames = [rigs.frame(rig, 1, i, smooth=1) for i in range(n)]
     ref, rmask = P.compose(cal, frames, blender=spec["blender"], num_bands=5, gains=spec["gain_values"])
-    for fused in (11, 12, 13, 14, 10):
+    for fused in (11, 15, 12, 13, 14, 10):
         comp.set_fused(fused)
         pano, mask = comp.compose(frames)
         same(pano, ref, "%s panorama (variant %d)" % (rig, fused))
@@ -88,7 +89,7 @@ def test_c4_properties(gpu):
     base = rng.integers(0, 256, (size[1] // 8, size[0] // 8, 3), dtype=np.uint8)
     tex = [np.ascontiguousarray(np.roll(np.kron(base, np.ones((8, 8, 1), np.uint8)), 97 * i, axis=1)) for i in range(n)]
     outs = []
-    for fused in (11, 10, 0):
+    for fused in (11, 15, 10, 0):
         comp.set_fused(fused)
         outs.append(comp.compose(tex)[0].copy())
     same(outs[1], outs[0], "C4 fused CV_16S path vs fast path")
@@ -117,9 +118,10 @@ def test_full_size_no_blend_matches_oracle(gpu):
     gains = [0.95, 1.02, 1.0, 0.98, 1.05]
     comp = gpu.Compositor(size, Ks, Rs, warper="cylindrical", scale=spec["scale"], blender="no", gains=gains)
     cal = P.Calibration(size, Ks, Rs, "cylindrical", spec["scale"])
+    assert comp.kernel_plan() == 2
     frames = [rigs.frame("c2", 4, i, smooth=1) for i in range(n)]
     ref, rmask = P.compose(cal, frames, blender="no", gains=gains)
-    for fused in (11, 10, 0):
+    for fused in (11, 15, 10, 0):
         comp.set_fused(fused)
         pano, mask = comp.compose(frames)
         same(pano, ref, "no-blend panorama (variant %d)" % fused)

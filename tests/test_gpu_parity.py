@@ -301,7 +301,7 @@ def _compositor_case(gpu, rig, blender, weight_type=O.CV_32F, seams=False, gains
         # 11: fused fast kernels (RGBX pyramid with multi-level launches / streaming feather); 12 / 13: the same with one
         # launch per pyramid level / with the multi-level launches forced; 14: the same with the gather warp stage; 10: fused CV_16S band kernels / one-pixel-per-thread feather; 0: the staged,
         # camera-by-camera path shaped like the reference's feed/blend calls
-        for fused in (11, 12, 13, 14, 10, 0):
+        for fused in (11, 15, 12, 13, 14, 10, 0):
             comp.set_fused(fused)
             pano, mask = comp.compose(frames)
             assert_same(pano, ref, "%s/%s pano frame %d fused=%s" % (rig, blender, fi, fused))
