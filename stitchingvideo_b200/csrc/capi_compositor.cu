@@ -898,7 +898,7 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
             a.out = s.out.v.data; a.out_step = (unsigned)s.out.v.step;
             a.out_mask = s.want_mask ? s.out_mask.v.ptr<uint8_t>() : nullptr; a.mask_step = (unsigned)s.out_mask.v.step;
             a.pw = s.out.v.cols; a.ph = s.out.v.rows;
-            a.n_tiles = c->fs2.n_tiles;
+            a.n_tiles = c->fs2.n_tiles; a.per_cta = c->fs2.per_cta;
             PROF(a.no_blend ? "noblend_stream" : "feather_stream", fs2_bytes, launch_fs2(a, gain_on, s.out.v.type == SB_8UC3, c->fs2.grid, st));
         } else if (stream_ok) {
             FeatherTmaArgs a{};

@@ -199,9 +199,12 @@ int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, i
     // ... except that every CTA's FIRST tiles are cheap ones: the first wave of copies is what the consumers wait for at
     // kernel start, and a one-camera tile is 2-3x fewer bytes
     if (n_tiles >= 2 * grid * FS2_GROUPS) std::rotate(order.begin(), order.end() - (size_t)grid * FS2_GROUPS, order.end());
-    std::vector<uint4> o((size_t)n_tiles * per);
+    // position t of the schedule belongs to CTA t % grid as its tile number t / grid; the CTA's descriptors are contiguous
+    const int per_cta = div_up(n_tiles, grid);
+    std::vector<uint4> o((size_t)grid * per_cta * per, make_uint4(0u, 0u, 0u, 0u));
+    auto at = [&](int t) -> uint4 * { return &o[((size_t)(t % grid) * per_cta + (size_t)(t / grid)) * per]; };
     for (int t = 0; t < n_tiles; ++t)
-        for (size_t j = 0; j < per; ++j) o[(size_t)t * per + j] = d[(size_t)order[t] * per + j];
+        for (size_t j = 0; j < per; ++j) at(t)[j] = d[(size_t)order[t] * per + j];
     // The shared-memory ring plan.  CTA b walks positions b, b + G, ...; a tile takes `units` contiguous 128-byte ring units
     // at the head, wrapping to 0 when the end of the ring is too short; space is handed back in tile order.  Both are a pure
     // function of the tile sizes, so the start unit of every tile and the number of the CTA's tiles that must have been
@@ -212,7 +215,7 @@ int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, i
         int hist[FS2_STAGES];
         int head = 0, tail = 0, oldest = 0, seq = 0;
         for (int tile = b; tile < n_tiles; tile += grid, ++seq) {
-            uint4 &d0 = o[(size_t)tile * per];
+            uint4 &d0 = *at(tile);
             const int units = (int)(d0.x >> 8);
             int start;
             for (;;) {
@@ -237,7 +240,7 @@ int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, i
     SB_TRY(desc_out.ensure(o.size() * sizeof(uint4)));
     SB_CUDA(cudaMemcpyAsync(desc_out.p, o.data(), o.size() * sizeof(uint4), cudaMemcpyHostToDevice, s));
     SB_CUDA(cudaStreamSynchronize(s));
-    plan->n_tiles = n_tiles; plan->grid = grid; plan->table_bytes = table_bytes; plan->ok = true;
+    plan->n_tiles = n_tiles; plan->grid = grid; plan->per_cta = per_cta; plan->table_bytes = table_bytes; plan->ok = true;
     return SB_OK;
 }
 
@@ -280,7 +283,6 @@ int fs2_encode_tmaps(const void *src, size_t sstep, int sw, int sh, const unsign
 // ------------------------------------------------------------------------------------ frame kernel
 struct Fs2Smem {
     unsigned char ring[FS2_RING_BYTES];
-    uint2 lut[1024];                                        // bilinear product weights x 64 (see fs2_lut_entry)
     uint4 desc[FS2_STAGES][1 + FS2_MAXC];                   // stage copy of the tile descriptor, rewritten by the producer:
                                                             //   [0] = {flags, X0 | Y0 << 16, output byte offset, mask byte offset}
                                                             //   [1 + k] = {slot offset in the ring, box pitch, -, camera}
@@ -304,16 +306,22 @@ __device__ __forceinline__ void mbar_wait_hw(uint64_t *bar, unsigned parity)
                  ::"r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
 }
 
-// Bilinear product weights of table index fx | fy << 5, times 64: {w00 | w01 << 16, w10 | w11 << 16}, w = a*b*64 with
-// a*b <= 1024 (sb_device.cuh: bilin_weights).  The factor 64 puts the result byte of (sum ab*p + 512) >> 10 into
-// byte 2 of the 32-bit dot product.  Entry (0, 0) would need 1024 * 64 = 2^16: it is stored as 1023 * 64, which gives
-// the same byte for every 8-bit p, with and without the "- 1" of the full-weight path:
-//   (1023 p + 512) >> 10 == p   and   (1023 p - 512) >> 10 == p - 1   for p in 1..255  (0 <= 512 - p <= 1023).
-__device__ __forceinline__ uint2 fs2_lut_entry(int i)
+// Bilinear product weights of a table entry (fx = bits 22-26, fy = bits 27-31), times 64, as the two operands of the
+// 16-bit x 8-bit dot products: wx = w00 | w01 << 16, wy = w10 | w11 << 16 with w = a*b*64, a in {32 - fx, fx},
+// b in {32 - fy, fy} (sb_device.cuh: bilin_weights).  The factor 64 puts the result byte of (sum ab*p + 512) >> 10 into
+// byte 2 of the 32-bit sum.  They are computed, not looked up: a 1024-entry table in shared memory costs 3.4 bank
+// conflicts per load (the index is as good as random across a warp), a third of the kernel's shared-memory traffic.
+//   t = (32 - fx) * 64 | fx * 64 << 16 = fx * (0xffff * 64) + 2048;   wx = t * (32 - fy);   wy = t * fy
+// (fx, fy) = (0, 0) would need w00 = 2^16: it becomes 0xffff, which gives the same byte for every 8-bit p, with and
+// without the "- 1" of the full-weight path:  (65535 p + 32768) >> 16 == p  and  (65535 p - 32768) >> 16 == p - 1 for
+// p in 1..255.
+__device__ __forceinline__ void fs2_weights(uint32_t e, unsigned &wx, unsigned &wy)
 {
-    uint2 w = bilin_weights(i & 31, i >> 5);
-    if (i == 0) w.x = 1023u;
-    return make_uint2(w.x << 6, w.y << 6);
+    const unsigned fy = e >> 27, fx = (e >> 22) & 31u;
+    const unsigned t = fx * (0xffffu * 64u) + 2048u;
+    wx = t * (32u - fy);
+    wy = t * fy;
+    if (wx == 0x10000u) wx = 0xffffu;
 }
 
 // One output pixel of one camera: three 32-bit sums s_c = 64 * (sum ab*p_c) + BIAS; the pixel value is byte 2.
@@ -321,7 +329,8 @@ __device__ __forceinline__ uint2 fs2_lut_entry(int i)
 template <int BIAS>
 __device__ __forceinline__ void fs2_pixel(const unsigned char *sm, uint32_t box, uint32_t pitch, uint32_t e, unsigned &s0, unsigned &s1, unsigned &s2)
 {
-    const uint2 bw = *reinterpret_cast<const uint2 *>(sm + FS2_RING_BYTES + (e >> 19));
+    uint2 bw;
+    fs2_weights(e, bw.x, bw.y);
     const unsigned char *r0 = sm + box + ((e >> 3) & 0x3ffcu);
     const unsigned char *r1 = r0 + pitch;
     const unsigned a0 = *reinterpret_cast<const uint32_t *>(r0), a1 = *reinterpret_cast<const uint32_t *>(r0 + 4),
@@ -425,26 +434,29 @@ k_fs2(const __grid_constant__ Fs2Args a)
     }
     __syncthreads();
 
-    if (warp == FS2_GROUPS * FS2_GROUP_WARPS) {
-        // ------------------------------------------------ producer warp
-        // Tiles blockIdx.x, + G, + 2G ... in order.  Where a tile lands in the ring and how many of the CTA's tiles must
+    if (warp >= FS2_GROUPS * FS2_GROUP_WARPS) {
+        // ------------------------------------------------ producer warps
+        // The CTA walks its tiles (schedule positions blockIdx.x, + G, + 2G ...; their descriptors are contiguous) in order;
+        // producer warp w fetches tiles w, w + P, ...  Where a tile lands in the ring and how many of the CTA's tiles must
         // have been consumed before its copies may land come from the per-calibration ring plan in the descriptor.
-        // Lane l issues copy l of the tile: per camera one bulk copy (table block) and one tensor copy per 8 box rows.
+        // Lane l issues copy l of the tile: per camera one bulk copy (table block) and one tensor copy per FS2_ROWS box
+        // rows.  A TMA instruction is warp-uniform, so the lanes' copies leave one after the other (~70 cycles each):
+        // the parallelism that keeps the ring full comes from the P warps.
+        const int pw = warp - FS2_GROUPS * FS2_GROUP_WARPS;
         const uint32_t ring0 = smem_u32(&sm.ring[0]);
-        const uint4 *dp = a.desc + (size_t)blockIdx.x * (1 + FS2_MAXC);
-        const size_t dstride = (size_t)G * (1 + FS2_MAXC);
+        const uint4 *dp = a.desc + ((size_t)blockIdx.x * a.per_cta + pw) * (1 + FS2_MAXC);
+        const int n_mine = (a.n_tiles - (int)blockIdx.x + G - 1) / G;
         uint4 nx0 = make_uint4(0u, 0u, 0u, 0u), nx1 = nx0, nx2 = nx0, nx3 = nx0;
-        if ((int)blockIdx.x < a.n_tiles) { nx0 = __ldg(dp); nx1 = __ldg(dp + 1); nx2 = __ldg(dp + 2); nx3 = __ldg(dp + 3); }
+        if (pw < n_mine) { nx0 = __ldg(dp); nx1 = __ldg(dp + 1); nx2 = __ldg(dp + 2); nx3 = __ldg(dp + 3); }
         int retired = 0;
-        int seq = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += G, ++seq) {
+        for (int seq = pw; seq < n_mine; seq += FS2_PRODUCERS) {
             const uint4 d0 = nx0, d1 = nx1, d2 = nx2, d3 = nx3;
-            dp += dstride;
-            if (tile + G < a.n_tiles) { nx0 = __ldg(dp); nx1 = __ldg(dp + 1); nx2 = __ldg(dp + 2); nx3 = __ldg(dp + 3); }
+            dp += FS2_PRODUCERS * (1 + FS2_MAXC);
+            if (seq + FS2_PRODUCERS < n_mine) { nx0 = __ldg(dp); nx1 = __ldg(dp + 1); nx2 = __ldg(dp + 2); nx3 = __ldg(dp + 3); }
             const int stage = seq % FS2_STAGES;
             const int nc = (int)(d0.x & 3u);
             const int need = max((int)(d0.w & 0xffffu), seq - FS2_STAGES + 1);
-            for (; retired < need; ++retired)              // groups finish tiles out of order: every tile is awaited once, in order
+            for (; retired < need; ++retired)              // groups finish tiles out of order: every warp awaits every tile once, in order
                 mbar_wait_hw(&sm.empty[retired % FS2_STAGES], (unsigned)(retired / FS2_STAGES) & 1u);
             const uint32_t tile_off = d0.z * 128u;          // ring byte offset of the tile
             if (lane <= FS2_MAXC) {
@@ -489,15 +501,13 @@ k_fs2(const __grid_constant__ Fs2Args a)
     // ---------------------------------------------------- consumer warps
     // group g = warp / 8 works on tiles seq = g, g + GROUPS, ... of the CTA's sequence; inside a group warp w covers tile
     // rows 4w .. 4w+3, lane = (row << 3 | quad), a thread owns pixels 4*quad .. 4*quad+3 of its row
-    for (int i = tid; i < 1024; i += FS2_GROUPS * FS2_GROUP_WARPS * 32) sm.lut[i] = fs2_lut_entry(i);
-    asm volatile("bar.sync 1, %0;" ::"n"(FS2_GROUPS * FS2_GROUP_WARPS * 32) : "memory");
     const int grp = warp / FS2_GROUP_WARPS, slab = warp % FS2_GROUP_WARPS;
     const int ty = slab * 4 + (lane >> 3), tx = (lane & 7) * 4;
     const uint32_t tab_off = (uint32_t)(ty * FS2_W + tx) * 4u, plane_off = (uint32_t)FS2_ENT_BYTES + (uint32_t)(ty * FS2_W + tx);
     unsigned char *const out_t = reinterpret_cast<unsigned char *>(a.out) + ((unsigned)ty * a.out_step + (unsigned)tx * (OUT8 ? 3u : 6u));
     uint8_t *const mask_t = a.out_mask ? a.out_mask + ((unsigned)ty * a.mask_step + (unsigned)tx) : nullptr;
-    int seq = grp;
-    for (int tile = blockIdx.x + grp * G; tile < a.n_tiles; tile += FS2_GROUPS * G, seq += FS2_GROUPS) {
+    const int n_mine = (a.n_tiles - (int)blockIdx.x + G - 1) / G;
+    for (int seq = grp; seq < n_mine; seq += FS2_GROUPS) {
         const int stage = seq % FS2_STAGES;
         mbar_wait_hw(&sm.full[stage], (unsigned)(seq / FS2_STAGES) & 1u);
         if (tid % (FS2_GROUP_WARPS * 32) == 0) FS2_TRACE(1, seq);

@@ -29,14 +29,20 @@ namespace sb {
 #ifndef SB_CFG_FS2_CTAS_PER_SM
 #define SB_CFG_FS2_CTAS_PER_SM 1
 #endif
+#ifndef SB_CFG_FS2_PRODUCERS
+#define SB_CFG_FS2_PRODUCERS 4
+#endif
+#ifndef SB_CFG_FS2_ROWS
+#define SB_CFG_FS2_ROWS 16
+#endif
 #ifndef SB_CFG_FS2_RING_KB
 #define SB_CFG_FS2_RING_KB 200
 #endif
 
 constexpr int FS2_W = 32, FS2_H = 32;                 // panorama tile
 constexpr int FS2_NCLS = 4;                           // source-box width classes (one tensor map per camera and class)
-constexpr int FS2_ROWS = 8;                           // box rows per tensor copy
-constexpr int FS2_MAX_OPS = 8;                        // <= 64 box rows
+constexpr int FS2_ROWS = SB_CFG_FS2_ROWS;             // box rows per tensor copy
+constexpr int FS2_MAX_OPS = 64 / FS2_ROWS;            // <= 64 box rows
 constexpr int FS2_MAX_BOX_W = 256;                    // TMA box dimension limit
 constexpr int FS2_ENT_BYTES = FS2_W * FS2_H * 4;      // tap entries of one (tile, camera)
 constexpr int FS2_BLOCK_BYTES = FS2_ENT_BYTES + FS2_W * FS2_H;   // + the weight-index plane (fetched only where cameras blend)
@@ -46,7 +52,8 @@ constexpr int FS2_GROUP_WARPS = 8;
 constexpr int FS2_STAGES = 8 * FS2_GROUPS;            // tile entries (descriptor + barriers) in flight per CTA
 constexpr int FS2_CTAS_PER_SM = SB_CFG_FS2_CTAS_PER_SM;
 constexpr int FS2_RING_BYTES = SB_CFG_FS2_RING_KB * 1024;
-constexpr int FS2_THREADS = (FS2_GROUPS * FS2_GROUP_WARPS + 1) * 32;
+constexpr int FS2_PRODUCERS = SB_CFG_FS2_PRODUCERS;   // producer warps, each on its own tile
+constexpr int FS2_THREADS = (FS2_GROUPS * FS2_GROUP_WARPS + FS2_PRODUCERS) * 32;
 static_assert(FS2_MAXC * (FS2_BLOCK_BYTES + FS2_MAX_BOX_W * FS2_ROWS * FS2_MAX_OPS) <= FS2_RING_BYTES, "one tile must fit the ring");
 
 struct Fs2Cam {
@@ -68,6 +75,7 @@ struct alignas(64) Fs2Args {
     uint8_t *out_mask;
     unsigned mask_step;
     int pw, ph, n_tiles, n;
+    int per_cta;                   // descriptors of CTA b start at desc + b * per_cta * (1 + FS2_MAXC)
     unsigned long long *trace;     // SB_FS2_TRACE builds: per CTA and tile {issue, full, done} timestamps
 };
 
@@ -83,7 +91,7 @@ struct Fs2Place {
 };
 struct Fs2Plan {                    // host-side result of the setup: what the compositor keeps per calibration
     unsigned cls_w[FS2_NCLS];
-    int n_tiles = 0, grid = 0;
+    int n_tiles = 0, grid = 0, per_cta = 0;
     double table_bytes = 0;         // bytes of table blocks one frame fetches (algorithmic bytes of the table stream)
     bool ok = false;
 };
