@@ -47,12 +47,13 @@ SURVEY_DATAFLOW_GB = {"c2": 0.71, "c3": 1.30}
 
 
 def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` ("workload:name", else "name") from the
+    committed ncu capture."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         with open(p) as f:
             t = json.load(f)
-        e = t[kernel]
+        e = t.get(kernel) or t[kernel.split(":", 1)[-1]]
         return e["dram_bytes_per_launch"], e["source"]
     except (OSError, KeyError, ValueError):
         return None, None
@@ -115,21 +116,6 @@ def make_frames(rig, n_sets, n_cams, rank):
     return [[rigs.frame(rig, rank * 1000 + s, i) for i in range(n_cams)] for s in range(n_sets)]
 
 
-def pipelined(comp, frame_sets, outs, steps, depth):
-    """steps frames through `depth` in-flight slots; returns the slot list (all waited)."""
-    # (a video loop cycles through a few input / output buffers: their argument blocks are built once)
-    period = len(frame_sets) * len(outs) // math.gcd(len(frame_sets), len(outs))
-    calls = [comp.prepare_call(frame_sets[k % len(frame_sets)], *outs[k % len(outs)]) for k in range(min(period, steps))]
-    slots = []
-    for k in range(steps):
-        if k >= depth:
-            comp.wait(slots[k - depth])
-        slots.append(comp.enqueue_prepared(calls[k % len(calls)]))
-    for s in slots[-depth:]:
-        comp.wait(s)
-    return slots
-
-
 def bind_to_gpu_numa_node(index):
     """Run this rank (and allocate its pinned buffers) on the CPU cores of the NUMA node its GPU hangs off, so that
     the host<->device copies of N ranks do not all cross the socket interconnect.  Best effort; returns a note."""
@@ -158,85 +144,106 @@ def bind_to_gpu_numa_node(index):
         return "unavailable (%s)" % type(e).__name__
 
 
-def run_ours(args):
+LAP = 32      # frame sets per recorded lap (one CUDA graph launch = one host call)
+
+
+def measure(workload, args, rank, world, local, barrier, max_over_ranks, sampler=None):
+    """All the numbers of one workload on this rank's GPU: value (device-resident), e2e (host buffers), roofline."""
     import torch
-    import torch.distributed as dist
     import stitchingvideo_b200 as sv
     from stitchingvideo_b200 import capi, rigs
 
-    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    Ks, Rs, spec = rigs.cameras(args.workload)
+    Ks, Rs, spec = rigs.cameras(workload)
     n, size = spec["n_used"], (spec["W"], spec["H"])
     comp = sv.Compositor(size, Ks, Rs, warper=spec["warper"], scale=spec["scale"], blender=spec["blender"], num_bands=5,
                          weight_type=sv.CV_32F, sharpness=0.02, gains=spec["gain_values"], output_type=sv.CV_8UC3, device=local)
     if args.variant is not None:
         comp.set_fused(10 + args.variant)      # kernel variant of the fused path (tuning hook)
     pw, ph = comp.pano_size
+    depth = args.depth if args.depth is not None else (8 if workload in ("c3", "c4") else 4)
     n_sets = args.frame_sets
-    host_sets = make_frames(args.workload, n_sets, n, rank)
+    host_sets = make_frames(workload, n_sets, n, rank)
+    laps = max(1, args.batch // LAP)                        # graph launches per step
+    frames_per_step = laps * LAP
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    steps_f, warm_f = args.steps * args.batch, args.warmup * args.batch      # frame sets in the timed / warm-up regions
     # ---------------- value: inputs resident in HBM, output stays on the device ----------------
+    # One lap of the input ring (LAP frame sets over `depth` in-flight slots) is recorded once as a CUDA graph and
+    # replayed: one host call per lap (sb_compositor_batch_*), the way a capture loop with a fixed buffer ring runs.
     dev_tensors = [[torch.from_numpy(f).cuda() for f in s] for s in host_sets]
     dev_sets = [[capi.DeviceImage.from_torch(t) for t in s] for s in dev_tensors]
-    comp.set_depth(args.depth)
-    dev_outs = [(None, None)]            # panorama stays in the slot's device buffer (lent, no copy)
-    pipelined(comp, dev_sets, dev_outs, warm_f, args.depth)
+    comp.set_depth(depth)
+    # every frame set of the lap has its own device panorama (row pitch aligned for the kernel's vector stores): with device
+    # sources AND device outputs a feather / no-blend lap is ONE persistent launch of the frame kernel (sb_batch_mode 1)
+    wp = (pw + 7) & ~7
+    out_t = [torch.empty((ph, wp, 3), dtype=torch.uint8, device="cuda") for _ in range(LAP)]
+    dev_out = [capi.DeviceImage(t.data_ptr(), ph, pw, sv.CV_8UC3, wp * 3, local, owner=t) for t in out_t]
+    lap = comp.batch([dev_sets[f % n_sets] for f in range(LAP)], dev_out)
+    lap_mode = lap.mode
+    for _ in range(args.warmup * laps):
+        lap.launch()
+    lap.wait()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    if sampler is not None:
+        sampler.start()
     launches0 = sv.kernel_launch_count()
     comp.mark(0)
-    pipelined(comp, dev_sets, dev_outs, steps_f, args.depth)
+    for _ in range(args.steps * laps):
+        lap.launch()
     comp.mark(1)
     ms_dev = comp.marked_ms()
     launches = sv.kernel_launch_count() - launches0
     barrier()
     ms_dev = max_over_ranks(ms_dev)
-    value = world * steps_f / (ms_dev / 1e3)
+    value = world * args.steps * frames_per_step / (ms_dev / 1e3)
+    lap.close()
 
-    # ---------------- e2e: host buffers through the C ABI (H2D + kernels + D2H per step) ----------------
+    # ... and one frame set at a time on ONE stream (depth 1, a lap of single launches back to back, never overlapping):
+    # frame time here = the sum of the frame's kernel durations as the launching stream sees them (inputs still rotate over
+    # n_sets frame sets > L2), the denominator of the per-kernel roofline below.
+    comp.set_depth(1)
+    lap1 = comp.batch([dev_sets[f % n_sets] for f in range(LAP)], [None] * LAP)
+    for _ in range(3):
+        lap1.launch()
+    lap1.wait()
+    comp.mark(0)
+    for _ in range(max(2, laps // 2)):
+        lap1.launch()
+    comp.mark(1)
+    serial_frame_ms = comp.marked_ms() / (max(2, laps // 2) * LAP)
+    lap1.close()
+    del out_t, dev_out
+
+    # ---------------- e2e: host buffers through the C ABI (H2D + kernels + D2H per frame set) ----------------
     # each frame set lives in one pinned block (n x H x W x 3), the way a capture pipeline delivers it; the library
     # recognises the contiguous set and moves it with a single DMA
+    comp.set_depth(depth)
     pin_in = [torch.from_numpy(np.stack(s)).pin_memory() for s in host_sets]
     pin_sets = [[t[i].numpy() for i in range(n)] for t in pin_in]
-    pin_out = [torch.empty((ph, pw, 3), dtype=torch.uint8).pin_memory() for _ in range(args.depth + 1)]
-    pin_outs = [(t.numpy(), None) for t in pin_out]
-    pipelined(comp, pin_sets, pin_outs, warm_f, args.depth)
+    pin_out = [torch.empty((ph, pw, 3), dtype=torch.uint8).pin_memory() for _ in range(depth + 1)]
+    e2e_steps, e2e_laps = args.steps, max(1, laps // args.e2e_divisor)     # (PCIe-bound: fewer laps per step keep the run short)
+    elap = comp.batch([pin_sets[f % n_sets] for f in range(LAP)], [pin_out[f % (depth + 1)].numpy() for f in range(LAP)])
+    for _ in range(min(args.warmup, 3) * e2e_laps):
+        elap.launch()
+    elap.wait()
     barrier()
     comp.mark(0)
     t0 = time.perf_counter()
-    pipelined(comp, pin_sets, pin_outs, steps_f, args.depth)
+    for _ in range(e2e_steps * e2e_laps):
+        elap.launch()
     comp.mark(1)
     ms_e2e = comp.marked_ms()
     wall_e2e = (time.perf_counter() - t0) * 1e3
     barrier()
     ms_e2e = max_over_ranks(max(ms_e2e, wall_e2e))
-    clocks = sampler.summary()
-    e2e_value = world * steps_f / (ms_e2e / 1e3)
-    h2d = n * size[0] * size[1] * 3 * args.batch
-    d2h = pw * ph * 3 * args.batch
+    clocks = sampler.summary() if sampler is not None else None
+    e2e_frames_per_step = e2e_laps * LAP
+    e2e_value = world * e2e_steps * e2e_frames_per_step / (ms_e2e / 1e3)
+    h2d_frame, d2h_frame = n * size[0] * size[1] * 3, pw * ph * 3
+    elap.close()
 
     # ---------------- roofline: per-kernel CUDA-event timing (separate pass, never the reported fps) ----------------
     comp.set_depth(1)
-    if args.variant is None and args.depth > 1:
+    if args.variant is None and depth > 1 and workload in ("c3", "c4"):
         comp.set_fused(12)      # profile the kernels the pipelined timed region launched (one launch per pyramid level)
     agg = {}
     for it in range(args.profile_frames + 1):
@@ -250,50 +257,109 @@ def run_ours(args):
     total_ms = sum(a["ms"] for a in agg.values())
     kernels = []
     for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
-        gbs = a["bytes"] / (a["ms"] * 1e-3) / 1e9 if a["ms"] > 0 else 0.0
-        kernels.append({"name": name, "launches_per_step": a["launches"] / args.profile_frames,
-                        "ms_per_step": a["ms"] / args.profile_frames, "share": a["ms"] / total_ms if total_ms else 0.0,
-                        "algorithmic_mb_per_step": a["bytes"] / args.profile_frames / 1e6, "achieved_gbs": gbs, "frac": gbs / peak})
+        share = a["ms"] / total_ms if total_ms else 0.0
+        per_frame_launches = a["launches"] / args.profile_frames
+        # isolated: events around ONE launch with nothing else in flight (carries ~5-10 us of event / launch latency);
+        # in_stream: the kernel's share of the frame x the frame time of the back-to-back single-stream lap above
+        iso_ms = a["ms"] / args.profile_frames
+        ins_ms = share * serial_frame_ms
+        mb = a["bytes"] / args.profile_frames / 1e6
+        kernels.append({"name": name, "launches_per_frame": per_frame_launches, "share": share, "algorithmic_mb_per_frame": mb,
+                        "isolated_ms_per_frame": iso_ms, "in_stream_ms_per_frame": ins_ms,
+                        "achieved_gbs": mb / 1e3 / (ins_ms / 1e3) if ins_ms > 0 else 0.0,
+                        "frac": (mb / 1e3 / (ins_ms / 1e3) / peak) if ins_ms > 0 else 0.0,
+                        "frac_isolated": (mb / 1e3 / (iso_ms / 1e3) / peak) if iso_ms > 0 else 0.0})
     dom = kernels[0]
-    traffic, traffic_src = ncu_traffic(dom["name"])
-    survey_gb = SURVEY_DATAFLOW_GB.get(args.workload)
-    frame_ms = ms_dev / steps_f
+    traffic, traffic_src = ncu_traffic(workload + ":" + dom["name"])
+    survey_gb = SURVEY_DATAFLOW_GB.get(workload)
+    frame_ms = ms_dev / (args.steps * frames_per_step)
+    total_mb = sum(k["algorithmic_mb_per_frame"] for k in kernels)
     roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "share_of_step": dom["share"],
+                "how": "achieved = the kernel's algorithmic bytes per launch / its average launch duration when %d frame sets are launched one "
+                       "kernel at a time, back to back on ONE stream (CUDA events around the laps; inputs rotate over %d frame sets = %.0f MB > L2); a frame of "
+                       "several kernels is split by the per-kernel CUDA-event shares of the isolated pass" % (LAP, n_sets, n_sets * h2d_frame / 1e6),
+                "avg_launch_us": dom["in_stream_ms_per_frame"] / dom["launches_per_frame"] * 1e3,
+                "isolated_launch_us": dom["isolated_ms_per_frame"] / dom["launches_per_frame"] * 1e3,
+                "frac_isolated": dom["frac_isolated"],
+                "algorithmic_bytes_per_launch": dom["algorithmic_mb_per_frame"] * 1e6 / dom["launches_per_frame"],
                 # SURVEY.md §8d's reference-shaped dataflow (accumulators in HBM) over the measured frame time, for
                 # comparison with the survey's 60 % bar; the fused kernels move far fewer bytes than that
                 "survey_dataflow": None if survey_gb is None else {
                     "gb_per_frame": survey_gb, "achieved_gbs": survey_gb / (frame_ms / 1e3), "frac": survey_gb / (frame_ms / 1e3) / peak},
-                "avg_launch_us": dom["ms_per_step"] / dom["launches_per_step"] * 1e3,
-                "algorithmic_bytes_per_launch": dom["algorithmic_mb_per_step"] * 1e6 / dom["launches_per_step"],
                 # The timed region itself (frame sets in flight on several streams, launches overlap): all algorithmic
-                # bytes of the frame over the device time per frame.  The per-launch figure above is taken with ONE frame
-                # in flight and so carries each launch's ramp-up and tail; this one is the sustained rate.
-                "timed_region": {"algorithmic_mb_per_frame": sum(k["algorithmic_mb_per_step"] for k in kernels),
-                                 "us_per_frame": frame_ms * 1e3,
-                                 "achieved_gbs": sum(k["algorithmic_mb_per_step"] for k in kernels) / 1e3 / (frame_ms / 1e3),
-                                 "frac": sum(k["algorithmic_mb_per_step"] for k in kernels) / 1e3 / (frame_ms / 1e3) / peak},
-                "whole_step": {"algorithmic_mb": sum(k["algorithmic_mb_per_step"] for k in kernels),
-                               "serial_kernel_ms": total_ms / args.profile_frames,
-                               "achieved_gbs": sum(k["algorithmic_mb_per_step"] for k in kernels) / 1e3 / (total_ms / args.profile_frames / 1e3) if total_ms else 0.0}}
-
-    if rank != 0:
-        return
-    line = {
-        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": (value / PUBLISHED_FPS[args.workload]) if args.workload in PUBLISHED_FPS else None,
-        "dtype": "u8/s16 integer + f32 weights", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "frame_sets_per_step": args.batch, "frame_sets_per_rank": steps_f, "cameras": n,
-                   "frame": "%dx%d" % size,
-                   "panorama": "%dx%d" % (pw, ph), "in_flight_slots": args.depth,
-                   "l2_policy": "inputs rotate over %d frame sets (%.0f MB) and each step streams >400 MB of intermediates; "
-                                "working set exceeds the 126 MB L2" % (n_sets, n_sets * h2d / 1e6)},
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps, "host_buffers": "pinned, one block per frame set", "numa_binding_rank0": numa,
-                "pcie_gbs": {"h2d": h2d / (ms_e2e / args.steps) / 1e6, "d2h": d2h / (ms_e2e / args.steps) / 1e6}},
+                # bytes of the frame over the device time per frame.
+                "timed_region": {"algorithmic_mb_per_frame": total_mb, "us_per_frame": frame_ms * 1e3,
+                                 "achieved_gbs": total_mb / 1e3 / (frame_ms / 1e3), "frac": total_mb / 1e3 / (frame_ms / 1e3) / peak},
+                "single_stream": {"us_per_frame": serial_frame_ms * 1e3, "achieved_gbs": total_mb / 1e3 / (serial_frame_ms / 1e3),
+                                  "frac": total_mb / 1e3 / (serial_frame_ms / 1e3) / peak}}
+    out = {
+        "value": value, "unit": "frames/s", "ms_per_step": ms_dev / args.steps,
+        "config": {"workload": WORKLOADS[workload], "frame_sets_per_step": frames_per_step, "frame_sets_per_rank": args.steps * frames_per_step,
+                   "cameras": n, "frame": "%dx%d" % size, "panorama": "%dx%d" % (pw, ph), "in_flight_slots": depth,
+                   "host_calls": "one per lap of %d frame sets (sb_compositor_batch_*: %s)" % (
+                       LAP, "one persistent launch of the frame kernel per lap" if lap_mode == 1 else "frame sets enqueued back to back on the slots' streams"),
+                   "kernel_plan": comp.kernel_plan(),
+                   "l2_policy": "inputs rotate over %d frame sets (%.0f MB) and every frame set streams its tables; the working set "
+                                "exceeds the 126 MB L2" % (n_sets, n_sets * h2d_frame / 1e6)},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_frame * e2e_frames_per_step,
+                "d2h_bytes_per_step": d2h_frame * e2e_frames_per_step, "frame_sets_per_step": e2e_frames_per_step,
+                "ms_per_step": ms_e2e / e2e_steps, "host_buffers": "pinned, one block per frame set",
+                "pcie_gbs": {"h2d": h2d_frame * e2e_frames_per_step / (ms_e2e / e2e_steps) / 1e6,
+                             "d2h": d2h_frame * e2e_frames_per_step / (ms_e2e / e2e_steps) / 1e6}},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
     }
+    del comp
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    head = measure(args.workload, args, rank, world, local, barrier, max_over_ranks, ClockSampler(local))
+    # the other workloads of BASELINE.json in the same run (N=1 by default): multi-band C3 and the live app's own case
+    extra = {}
+    for w in args.also:
+        m = measure(w, args, rank, world, local, barrier, max_over_ranks, ClockSampler(local))
+        extra[w] = {"metric": METRIC if w != "app6" else "6x1088p->composite frame sets/s", "value": m["value"], "unit": m["unit"],
+                    "ms_per_step": m["ms_per_step"], "vs_baseline": (m["value"] / PUBLISHED_FPS[w]) if w in PUBLISHED_FPS else None,
+                    "config": m["config"], "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "clocks": m["clocks"],
+                    "roofline": m["roofline"], "kernels": m["kernels"]}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    head["e2e"]["numa_binding_rank0"] = numa
+    line = {
+        "metric": METRIC, "value": head["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": (head["value"] / PUBLISHED_FPS[args.workload]) if args.workload in PUBLISHED_FPS else None,
+        "dtype": "u8/s16 integer + f32 weights", "data": "synthetic", "config": head["config"], "e2e": head["e2e"],
+        "gpu_launches": head["gpu_launches"], "clocks": head["clocks"], "roofline": head["roofline"], "kernels": head["kernels"],
+    }
+    if extra:
+        line["workloads"] = extra
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.workload, sample_frames=args.cpu_frames)
     print(json.dumps(line))
@@ -441,7 +507,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=32, help="frame sets per step")
+    ap.add_argument("--batch", type=int, default=960, help="frame sets per step (a multiple of the 32-frame lap; 20 steps x 960 = 19 200 frame sets, "
+                    "~0.5 s of device time for the one-kernel feather workload)")
+    ap.add_argument("--also", default=None, help="comma-separated extra workloads measured in the same run and reported under \"workloads\" "
+                    "(default: c3,app6 at N=1, none for N>1)")
+    ap.add_argument("--e2e-divisor", type=int, default=8, help="the PCIe-bound end-to-end leg runs batch / this many frame sets per step")
     ap.add_argument("--depth", type=int, default=None, help="frame sets in flight (slots); default 4 for the one-kernel feather workload, 8 for the "
                     "multi-band ones (lets the launch-latency-bound coarse pyramid levels of several frames overlap: C3 +9 %)")
     ap.add_argument("--frame-sets", type=int, default=8, help="distinct synthetic frame sets rotated through (8 x 31 MB > L2)")
@@ -451,11 +521,12 @@ def main():
     ap.add_argument("--variant", type=int, default=None, choices=[0, 1, 2, 3, 4, 5], help="fused kernel variant: 10 + v is passed to set_fused (default: library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.depth is None:
-        args.depth = 8 if args.workload in ("c3", "c4") else 4
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.also is None:
+        args.also = [w for w in ("c3", "app6") if w != args.workload] if (world == 1 and args.workload == "c2") else []
+    else:
+        args.also = [w for w in args.also.split(",") if w and w != args.workload]
     if args.impl == "reference":
-        if args.steps == 20:
-            args.steps, args.warmup = 4, 3
         run_reference(args)
     else:
         run_ours(args)

@@ -276,12 +276,33 @@ int  sb_compositor_set_fused(sb_compositor *c, int fused);
  * feather / no blending: 2 = tensor-TMA streaming kernel (k_fs2), 1 = round-1 streaming kernel, 0 = gather kernel;
  * multi-band: 2 = RGBX fast path with the streaming warp stage, 1 = RGBX fast path, 0 = CV_16S band kernels. */
 int  sb_compositor_kernel_plan(const sb_compositor *c);
+/* Debugging aid: with the environment variable SB_FS2_TRACE=<file> set, the feather / no-blend frame kernel records per-CTA
+ * pipeline timestamps; this writes them out (scripts/fs2_trace.py reads the file).  Returns the number of launches dumped. */
+int  sb_debug_fs2_trace_dump(void);
 /* Pipelined form for throughput: up to `depth` frame sets in flight, each on its own stream/slot.
  * enqueue returns a slot id; wait blocks until that slot's pano has landed in the buffers given
  * to enqueue. */
 int  sb_compositor_set_depth(sb_compositor *c, int depth);
 int  sb_compositor_enqueue(sb_compositor *c, const sb_image *srcs, sb_image *pano, sb_image *pano_mask, int *slot);
 int  sb_compositor_wait(sb_compositor *c, int slot);
+/* Batches: one lap of a video pipeline's buffer ring (n_frames frame sets; srcs[f * n_cameras + i], panos[f], pano_masks[f]
+ * or NULL) run with ONE host call per lap.  Results are identical to n_frames calls of sb_compositor_enqueue (the reference's
+ * per-frame loop, LIB/src/stitcher.cpp:221-313, APP64:724-770).  How a lap runs (sb_batch_mode):
+ *   1 = one persistent launch of the frame kernel walks all the lap's frame sets - feather / no blending with every source and
+ *       every panorama (and mask) a device image: no kernel boundary, ramp-up or tail between frame sets;
+ *   0 = the frame sets are enqueued back to back on the slots' streams (frame f on slot f % depth): host buffers, multi-band;
+ *   2 = as 0 but recorded as a CUDA graph (environment SB_BATCH_GRAPH=1; slower on B200, kept for comparison).
+ * sb_batch_launch is asynchronous (stream order after earlier launches of any batch of the handle); do not mix it with
+ * enqueue/wait while a batch is in flight.  panos[f].data == NULL: the panorama stays in the slot's device buffer (lent),
+ * as with enqueue (mode 0 / 2). */
+typedef struct sb_batch sb_batch;
+int  sb_compositor_batch_create(sb_compositor *c, int n_frames, const sb_image *srcs, sb_image *panos, sb_image *pano_masks, sb_batch **batch);
+int  sb_batch_launch(sb_batch *b);
+int  sb_batch_wait(sb_batch *b);
+int  sb_batch_last_gpu_ms(sb_batch *b, float *ms);       /* device time of the last launch (CUDA events around the graph) */
+int  sb_batch_frames(const sb_batch *b);
+int  sb_batch_mode(const sb_batch *b);
+void sb_batch_destroy(sb_batch *b);
 /* device-resident timing of the last compose on a slot, ms (CUDA events on the slot's stream) */
 int  sb_compositor_last_gpu_ms(sb_compositor *c, int slot, float *ms);
 /* Device-side timing of a region spanning every slot: mark(0) before the first enqueue, mark(1)

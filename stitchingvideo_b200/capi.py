@@ -133,8 +133,16 @@ API = {
     "sb_compositor_set_depth": (C.c_int, [C.c_void_p, C.c_int]),
     "sb_compositor_set_fused": (C.c_int, [C.c_void_p, C.c_int]),
     "sb_compositor_kernel_plan": (C.c_int, [C.c_void_p]),
+    "sb_debug_fs2_trace_dump": (C.c_int, []),
     "sb_compositor_enqueue": (C.c_int, [C.c_void_p, _P(SbImage), _P(SbImage), _P(SbImage), _P(C.c_int)]),
     "sb_compositor_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "sb_compositor_batch_create": (C.c_int, [C.c_void_p, C.c_int, _P(SbImage), _P(SbImage), _P(SbImage), _P(C.c_void_p)]),
+    "sb_batch_launch": (C.c_int, [C.c_void_p]),
+    "sb_batch_wait": (C.c_int, [C.c_void_p]),
+    "sb_batch_last_gpu_ms": (C.c_int, [C.c_void_p, _P(C.c_float)]),
+    "sb_batch_frames": (C.c_int, [C.c_void_p]),
+    "sb_batch_mode": (C.c_int, [C.c_void_p]),
+    "sb_batch_destroy": (None, [C.c_void_p]),
     "sb_compositor_last_gpu_ms": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_float)]),
     "sb_compositor_mark": (C.c_int, [C.c_void_p, C.c_int]),
     "sb_compositor_marked_ms": (C.c_int, [C.c_void_p, _P(C.c_float)]),
@@ -210,8 +218,9 @@ class DeviceImage:
         return SbImage(self.ptr, self.rows, self.cols, self.type, self.step, self.device)
 
 
-def _image(a):
-    """numpy array | DeviceImage -> (SbImage, keepalive)."""
+def _image(a, output=False):
+    """numpy array | DeviceImage -> (SbImage, keepalive).  An input whose pixels are not contiguous is copied; an OUTPUT
+    must be written in place, so a view with non-contiguous pixels or a negative row stride is an error."""
     if isinstance(a, DeviceImage):
         return a.sb(), a
     a = np.asarray(a)
@@ -220,7 +229,9 @@ def _image(a):
     if a.ndim not in (2, 3):
         raise StitchError(SB_ERR_ASSERT, "image must be 2-D or 3-D")
     cn = 1 if a.ndim == 2 else a.shape[2]
-    if a.strides[-1] != a.itemsize or (a.ndim == 3 and a.strides[1] != a.itemsize * cn):
+    if a.strides[-1] != a.itemsize or (a.ndim == 3 and a.strides[1] != a.itemsize * cn) or a.strides[0] < 0:
+        if output:
+            raise StitchError(SB_ERR_ASSERT, "output array must have contiguous pixels and a non-negative row stride (got strides %s)" % (a.strides,))
         a = np.ascontiguousarray(a)
     return SbImage(a.ctypes.data, a.shape[0], a.shape[1], _NP2CV[a.dtype] + ((cn - 1) << 3), a.strides[0], -1), a
 
@@ -309,7 +320,7 @@ class RotationWarper:
         isrc, keep = _image(src)
         roi = self.warpRoi((isrc.cols, isrc.rows), K, R)
         dst = _empty(roi[3], roi[2], isrc.type)
-        idst, _k = _image(dst)
+        idst, _k = _image(dst, output=True)
         tl = SbPoint()
         _check(lib().sb_warper_warp(self._h, C.byref(isrc), _fp(K), _fp(R), interp_mode, border_mode, C.byref(idst), C.byref(tl)))
         return (tl.x, tl.y), dst
@@ -320,7 +331,7 @@ class RotationWarper:
         if getattr(self, "_map_shape", None) is None:
             raise StitchError(SB_ERR_ASSERT, "remap: no cached maps; call buildMaps first")
         dst = _empty(self._map_shape[0], self._map_shape[1], isrc.type)
-        idst, _k = _image(dst)
+        idst, _k = _image(dst, output=True)
         _check(lib().sb_warper_remap(self._h, C.byref(isrc), interp_mode, border_mode, C.byref(idst)))
         return dst
 
@@ -328,7 +339,7 @@ class RotationWarper:
         K, R = _f9(K), _f9(R)
         isrc, keep = _image(src)
         dst = _empty(dst_size[1], dst_size[0], isrc.type)
-        idst, _k = _image(dst)
+        idst, _k = _image(dst, output=True)
         _check(lib().sb_warper_warp_backward(self._h, C.byref(isrc), _fp(K), _fp(R), interp_mode, border_mode,
                                              SbSize(*dst_size), C.byref(idst)))
         return dst
@@ -430,7 +441,7 @@ def remap(src, xmap, ymap, interp_mode=INTER_LINEAR, border_mode=BORDER_CONSTANT
         ix, k1 = _image(np.ascontiguousarray(xmap, np.float32))
         iy, k2 = _image(np.ascontiguousarray(ymap, np.float32))
     dst = _empty(ix.rows, ix.cols, isrc.type)
-    idst, k3 = _image(dst)
+    idst, k3 = _image(dst, output=True)
     bv = (C.c_uint8 * 4)(*border_value)
     _check(lib().sb_remap(C.byref(isrc), C.byref(idst), C.byref(ix), C.byref(iy), interp_mode, border_mode, bv, device))
     return dst
@@ -540,7 +551,7 @@ def refine_seam_mask(seam_mask, mask_warped, device=0):
     a, k0 = _image(np.ascontiguousarray(seam_mask, np.uint8))
     b, k1 = _image(np.ascontiguousarray(mask_warped, np.uint8))
     out = np.empty((b.rows, b.cols), np.uint8)
-    o, k2 = _image(out)
+    o, k2 = _image(out, output=True)
     _check(lib().sb_refine_seam_mask(C.byref(a), C.byref(b), C.byref(o), device))
     return out
 
@@ -549,7 +560,7 @@ def dilate3x3(src, device=0):
     """cv::dilate(src, dst, Mat()) on uint8 HxW"""
     a, k0 = _image(np.ascontiguousarray(src, np.uint8))
     out = np.empty((a.rows, a.cols), np.uint8)
-    o, k1 = _image(out)
+    o, k1 = _image(out, output=True)
     _check(lib().sb_dilate3x3(C.byref(a), C.byref(o), device))
     return out
 
@@ -558,7 +569,7 @@ def resize_linear_8u(src, dsize_wh, device=0):
     """cv::resize(src, dsize, INTER_LINEAR) on uint8 HxW"""
     a, k0 = _image(np.ascontiguousarray(src, np.uint8))
     out = np.empty((dsize_wh[1], dsize_wh[0]), np.uint8)
-    o, k1 = _image(out)
+    o, k1 = _image(out, output=True)
     _check(lib().sb_resize_linear_8u(C.byref(a), C.byref(o), device))
     return out
 
@@ -610,8 +621,8 @@ class Blender:
         _check(lib().sb_blender_result_size(self._h, C.byref(s)))
         dst = np.empty((s.height, s.width, 3), np.int16)
         dmask = np.empty((s.height, s.width), np.uint8)
-        i, k0 = _image(dst)
-        m, k1 = _image(dmask)
+        i, k0 = _image(dst, output=True)
+        m, k1 = _image(dmask, output=True)
         _check(lib().sb_blender_blend(self._h, C.byref(i), C.byref(m)))
         return dst, dmask
 
@@ -658,7 +669,7 @@ class MultiBandBlender(Blender):
 
 def normalizeUsingWeightMap(weight, src, device=0):
     w, k0 = _image(weight)
-    s, k1 = _image(src)
+    s, k1 = _image(src, output=True)      # normalised in place
     _check(lib().sb_normalize_using_weight_map(C.byref(w), C.byref(s), device))
     return src
 
@@ -666,7 +677,7 @@ def normalizeUsingWeightMap(weight, src, device=0):
 def createWeightMap(mask, sharpness, device=0):
     m, k0 = _image(mask)
     out = np.empty((m.rows, m.cols), np.float32)
-    o, k1 = _image(out)
+    o, k1 = _image(out, output=True)
     _check(lib().sb_create_weight_map(C.byref(m), C.c_float(sharpness), C.byref(o), device))
     return out
 
@@ -716,6 +727,65 @@ def load_calibration(path):
                 "gain_maps": [img(c.gain_maps[i]) for i in range(n)] if c.gain_maps else None}
     finally:
         lib().sb_calibration_free(cal)
+
+
+class Batch:
+    """sb_batch: a recorded lap of frame sets, replayed with one host call (see Compositor.batch)."""
+
+    def __init__(self, comp, frame_sets, panos, pano_masks=None):
+        n, nf = comp.n, len(frame_sets)
+        assert nf > 0 and len(panos) == nf and (pano_masks is None or len(pano_masks) == nf)
+        self._keep = [comp]
+        srcs = (SbImage * (nf * n))()
+        for f, frames in enumerate(frame_sets):
+            arr, keep = comp._srcs(frames)
+            self._keep.append(keep)
+            for i in range(n):
+                srcs[f * n + i] = arr[i]
+        self.panos = (SbImage * nf)()
+        for f, pano in enumerate(panos):
+            if pano is None:
+                self.panos[f] = SbImage(None, 0, 0, comp.output_type, 0, -1)
+            else:
+                self.panos[f], k = _image(pano, output=True)
+                self._keep.append(k)
+        self.masks = None
+        if pano_masks is not None:
+            self.masks = (SbImage * nf)()
+            for f, m in enumerate(pano_masks):
+                if m is None:
+                    self.masks[f] = SbImage(None, 0, 0, CV_8UC1, 0, -1)
+                else:
+                    self.masks[f], k = _image(m, output=True)
+                    self._keep.append(k)
+        self._srcs_arr = srcs
+        h = C.c_void_p()
+        _check(lib().sb_compositor_batch_create(comp._h, nf, srcs, self.panos, self.masks, C.byref(h)))
+        self._h = h
+        self.n_frames = nf
+        self.mode = int(lib().sb_batch_mode(h))       # 1: one persistent launch per lap, 0: stream replay, 2: CUDA graph
+
+    def launch(self):
+        _check(_lib.sb_batch_launch(self._h))
+
+    def wait(self):
+        _check(_lib.sb_batch_wait(self._h))
+
+    def last_gpu_ms(self):
+        ms = C.c_float()
+        _check(lib().sb_batch_last_gpu_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().sb_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # noqa: BLE001 - interpreter shutdown
+            pass
 
 
 class Compositor:
@@ -817,10 +887,10 @@ class Compositor:
         if pano is None:
             pano, pano_mask = self.new_output()
         arr, keep = self._srcs(frames)
-        ip, k0 = _image(pano)
+        ip, k0 = _image(pano, output=True)
         im = None
         if pano_mask is not None:
-            im, k1 = _image(pano_mask)
+            im, k1 = _image(pano_mask, output=True)
         _check(lib().sb_compositor_compose(self._h, arr, C.byref(ip), C.byref(im) if im is not None else None))
         return pano, pano_mask
 
@@ -842,10 +912,10 @@ class Compositor:
             ip = SbImage(None, 0, 0, self.output_type, 0, -1)
             self.last_lent = ip
         else:
-            ip, k0 = _image(pano)
+            ip, k0 = _image(pano, output=True)
         im = None
         if pano_mask is not None:
-            im, k1 = _image(pano_mask)
+            im, k1 = _image(pano_mask, output=True)
         slot = C.c_int(-1)
         _check(lib().sb_compositor_enqueue(self._h, arr, C.byref(ip), C.byref(im) if im is not None else None, C.byref(slot)))
         return slot.value
@@ -857,8 +927,8 @@ class Compositor:
         if pano is None:
             ip, k0 = SbImage(None, 0, 0, self.output_type, 0, -1), None
         else:
-            ip, k0 = _image(pano)
-        im, k1 = _image(pano_mask) if pano_mask is not None else (None, None)
+            ip, k0 = _image(pano, output=True)
+        im, k1 = _image(pano_mask, output=True) if pano_mask is not None else (None, None)
         return (arr, C.byref(ip), C.byref(im) if im is not None else None, C.c_int(-1), ip if pano is None else None, (keep, ip, im, k0, k1))
 
     def enqueue_prepared(self, call):
@@ -871,6 +941,12 @@ class Compositor:
 
     def wait(self, slot):
         _check(lib().sb_compositor_wait(self._h, slot))
+
+    def batch(self, frame_sets, panos, pano_masks=None):
+        """One lap of a buffer ring as a CUDA graph (sb_compositor_batch_create): frame_sets[f] = the n source images of
+        frame f (numpy arrays or DeviceImage), panos[f] = the output array of frame f or None (stays in the slot's device
+        buffer), pano_masks likewise or None for no masks at all.  -> Batch (launch / wait / last_gpu_ms)."""
+        return Batch(self, frame_sets, panos, pano_masks)
 
     def mark(self, which):
         _check(lib().sb_compositor_mark(self._h, which))
@@ -939,12 +1015,13 @@ class Compositor:
     def strip_band(self, level):
         _check(lib().sb_compositor_strip_band(self._h, level))
 
-    def strip_result(self, rank, world):
-        """-> (strip, strip_mask) host arrays holding this rank's columns of the panorama."""
+    def strip_result(self, rank, world, pano=None, pano_mask=None):
+        """-> (strip, strip_mask) host arrays holding this rank's columns of the panorama; with `pano` / `pano_mask` (full
+        panorama-sized arrays) the columns are written straight into them and the returned arrays are views."""
         x0, x1 = self.strip_range(rank, world)
-        strip = _empty(self.pano_size[1], x1 - x0, self.output_type)
-        smask = np.empty((self.pano_size[1], x1 - x0), np.uint8)
-        i0, k0 = _image(strip)
-        i1, k1 = _image(smask)
+        strip = _empty(self.pano_size[1], x1 - x0, self.output_type) if pano is None else pano[:, x0:x1]
+        smask = np.empty((self.pano_size[1], x1 - x0), np.uint8) if pano_mask is None else pano_mask[:, x0:x1]
+        i0, k0 = _image(strip, output=True)
+        i1, k1 = _image(smask, output=True)
         _check(lib().sb_compositor_strip_result(self._h, C.byref(i0), C.byref(i1)))
         return strip, smask

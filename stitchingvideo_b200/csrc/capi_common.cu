@@ -83,8 +83,8 @@ int to_device(const sb_image &img, DevImage &stage, cudaStream_t s, DImage *out)
     }
     SB_TRY(stage.create_packed(img.rows, img.cols, img.type));
     if (img.rows > 0 && img.cols > 0) {
-        if (img.step == stage.v.step)       // contiguous on both sides: one linear DMA
-            SB_CUDA(cudaMemcpyAsync(stage.v.data, img.data, img.step * (size_t)(img.rows - 1) + (size_t)img.cols * elem_size(img.type), cudaMemcpyHostToDevice, s));
+        if (img.step == stage.v.step && img.step == (size_t)img.cols * elem_size(img.type))      // packed on both sides: one linear DMA
+            SB_CUDA(cudaMemcpyAsync(stage.v.data, img.data, img.step * (size_t)img.rows, cudaMemcpyHostToDevice, s));
         else
             SB_CUDA(cudaMemcpy2DAsync(stage.v.data, stage.v.step, img.data, img.step, (size_t)img.cols * elem_size(img.type), img.rows, cudaMemcpyHostToDevice, s));
     }
@@ -100,8 +100,10 @@ int from_device(const DImage &src, sb_image *dst, cudaStream_t s)
         return fail(SB_ERR_ASSERT, "output image is %dx%d type %d, expected %dx%d type %d", dst->rows, dst->cols, dst->type, src.rows, src.cols, src.type);
     if (src.rows > 0 && src.cols > 0) {
         const cudaMemcpyKind kind = dst->device >= 0 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-        if (dst->step == src.step)          // same pitch on both sides: one linear DMA
-            SB_CUDA(cudaMemcpyAsync(dst->data, src.data, src.step * (size_t)(src.rows - 1) + (size_t)src.cols * elem_size(src.type), kind, s));
+        // rows packed back to back on both sides: one linear DMA.  (Equal pitches alone are not enough: a column view of a
+        // wider image has the wide image's pitch, and a linear copy would run over the columns next to the view.)
+        if (dst->step == src.step && src.step == (size_t)src.cols * elem_size(src.type))
+            SB_CUDA(cudaMemcpyAsync(dst->data, src.data, src.step * (size_t)src.rows, kind, s));
         else
             SB_CUDA(cudaMemcpy2DAsync(dst->data, dst->step, src.data, src.step, (size_t)src.cols * elem_size(src.type), src.rows, kind, s));
     }

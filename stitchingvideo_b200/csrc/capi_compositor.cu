@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstdlib>
 #include <string>
 
 #include "sb_fs2.h"
@@ -785,6 +786,46 @@ int mb_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src, const in
     return SB_OK;
 }
 
+// k_fs2 arguments that depend on the calibration only
+void fs2_static_args(sb_compositor *c, Fs2Args &a)
+{
+    const int n = c->cfg.n_cameras;
+    a.n = n;
+    for (int i = 0; i < n; ++i) {
+        Camera &cam = c->cams[i];
+        Fs2Cam &fc = a.cam[i];
+        fc.blocks = static_cast<const unsigned char *>(cam.fs2_blocks.p);
+        fc.gain = cam.gain;
+        fc.dx = cam.tl.x - c->dst_roi.x; fc.dy = cam.tl.y - c->dst_roi.y;
+        if (c->cfg.comp_kind == SB_COMP_GAIN_BLOCKS) { fc.gmap = cam.gain_full.v.ptr<float>(); fc.gmstep = (unsigned)cam.gain_full.v.step; }
+    }
+    a.desc = static_cast<const uint4 *>(c->fs2_desc.p);
+    for (int k = 0; k < FS2_NCLS; ++k) a.cls_w[k] = c->fs2.cls_w[k];
+    a.sharpness = c->stream_sharpness;
+    a.no_blend = c->cfg.blender_kind == SB_BLEND_NO;
+    a.n_tiles = c->fs2.n_tiles; a.per_cta = c->fs2.per_cta; a.steady = c->fs2.steady ? 1 : 0;
+}
+
+// the tensor maps of one camera's frame buffer (encoded on first sight, then cached)
+int fs2_tmaps(sb_compositor *c, int i, const DImage &src, CUtensorMap *out)
+{
+    Camera &cam = c->cams[i];
+    Camera::TmapSet *hit = nullptr, *lru = nullptr;
+    for (auto &t : cam.tmaps) {
+        if (t.p == src.data && t.step == src.step) { hit = &t; break; }
+        if (!lru || t.stamp < lru->stamp) lru = &t;
+    }
+    if (!hit) {
+        if (cam.tmaps.size() < 32) { cam.tmaps.emplace_back(); hit = &cam.tmaps.back(); }
+        else hit = lru;
+        hit->p = src.data; hit->step = src.step;
+        SB_TRY(fs2_encode_tmaps(src.data, src.step, src.cols, src.rows, c->fs2.cls_w, hit->m));
+    }
+    hit->stamp = ++c->tmap_clock;
+    std::memcpy(out, hit->m, sizeof hit->m);
+    return SB_OK;
+}
+
 int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
 {
     const sb_compositor_config &cfg = c->cfg;
@@ -866,39 +907,15 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
         bytes += img_bytes(s.out.v) + (s.want_mask ? img_bytes(s.out_mask.v) : 0);
         if (fs2_ok) {
             Fs2Args a{};
-            a.n = n;
+            fs2_static_args(c, a);
             double fs2_bytes = c->fs2.table_bytes + img_bytes(s.out.v) + (s.want_mask ? img_bytes(s.out_mask.v) : 0);
             for (int i = 0; i < n; ++i) {
-                Camera &cam = c->cams[i];
-                Fs2Cam &fc = a.cam[i];
-                fc.blocks = static_cast<const unsigned char *>(cam.fs2_blocks.p);
-                fc.gain = cam.gain;
-                fc.dx = cam.tl.x - c->dst_roi.x; fc.dy = cam.tl.y - c->dst_roi.y;
-                if (blocks) { fc.gmap = cam.gain_full.v.ptr<float>(); fc.gmstep = (unsigned)cam.gain_full.v.step; }
                 fs2_bytes += img_bytes(src[i]);
-                // tensor maps of this frame buffer (encoded on first sight, then cached)
-                Camera::TmapSet *hit = nullptr, *lru = nullptr;
-                for (auto &t : cam.tmaps) {
-                    if (t.p == src[i].data && t.step == src[i].step) { hit = &t; break; }
-                    if (!lru || t.stamp < lru->stamp) lru = &t;
-                }
-                if (!hit) {
-                    if (cam.tmaps.size() < 32) { cam.tmaps.emplace_back(); hit = &cam.tmaps.back(); }
-                    else hit = lru;
-                    hit->p = src[i].data; hit->step = src[i].step;
-                    SB_TRY(fs2_encode_tmaps(src[i].data, src[i].step, src[i].cols, src[i].rows, c->fs2.cls_w, hit->m));
-                }
-                hit->stamp = ++c->tmap_clock;
-                std::memcpy(&a.tmap[i * FS2_NCLS], hit->m, sizeof hit->m);
+                SB_TRY(fs2_tmaps(c, i, src[i], &a.tmap[i * FS2_NCLS]));
             }
-            a.desc = static_cast<const uint4 *>(c->fs2_desc.p);
-            for (int k = 0; k < FS2_NCLS; ++k) a.cls_w[k] = c->fs2.cls_w[k];
-            a.sharpness = c->stream_sharpness;
-            a.no_blend = cfg.blender_kind == SB_BLEND_NO;
             a.out = s.out.v.data; a.out_step = (unsigned)s.out.v.step;
             a.out_mask = s.want_mask ? s.out_mask.v.ptr<uint8_t>() : nullptr; a.mask_step = (unsigned)s.out_mask.v.step;
             a.pw = s.out.v.cols; a.ph = s.out.v.rows;
-            a.n_tiles = c->fs2.n_tiles; a.per_cta = c->fs2.per_cta;
             PROF(a.no_blend ? "noblend_stream" : "feather_stream", fs2_bytes, launch_fs2(a, gain_on, s.out.v.type == SB_8UC3, c->fs2.grid, st));
         } else if (stream_ok) {
             FeatherTmaArgs a{};
@@ -1071,6 +1088,8 @@ int sb_compositor_set_fused(sb_compositor *c, int fused)
     return SB_OK;
 }
 
+int sb_debug_fs2_trace_dump(void) { return fs2_trace_dump(); }
+
 int sb_compositor_kernel_plan(const sb_compositor *c)
 {
     if (!c) return SB_ERR_ASSERT;
@@ -1093,17 +1112,16 @@ int sb_compositor_set_depth(sb_compositor *c, int depth)
     return SB_OK;
 }
 
-int sb_compositor_enqueue(sb_compositor *c, const sb_image *srcs, sb_image *pano, sb_image *pano_mask, int *slot)
+// One frame set on slot `s`: host->device staging of host sources, the frame kernels, the copy of the panorama (and mask)
+// into the caller's buffers - everything asynchronous on the slot's stream.
+static int enqueue_on_slot(sb_compositor *c, Slot &s, const sb_image *srcs, sb_image *pano, sb_image *pano_mask, bool timing)
 {
-    SB_ASSERT(c && srcs && pano && slot);
-    DeviceGuard g(c->device);
-    if (!g.ok) return SB_ERR_CUDA;
-    const int si = c->next_slot;
-    Slot &s = c->slots[si];
-    if (s.busy) return fail(SB_ERR_ASSERT, "slot %d still in flight: call sb_compositor_wait first", si);
     const int n = c->cfg.n_cameras;
-    SB_CUDA(cudaEventRecord(s.ev_start, s.stream));
-    std::vector<DImage> src(n);
+    if (timing) SB_CUDA(cudaEventRecord(s.ev_start, s.stream));
+    DImage src_local[SB_MAX_CAMERAS];
+    std::vector<DImage> src_heap;
+    DImage *srcp = src_local;
+    if (n > SB_MAX_CAMERAS) { src_heap.resize(n); srcp = src_heap.data(); }
     // A frame set delivered as ONE host block (camera i+1 starts where camera i ends, rows packed) crosses PCIe as a
     // single DMA: n separate 6 MB copies cost ~20 % of the link's throughput in per-copy overhead.
     bool one_block = n > 1;
@@ -1117,13 +1135,14 @@ int sb_compositor_enqueue(sb_compositor *c, const sb_image *srcs, sb_image *pano
         SB_TRY(s.src_all.ensure(img_bytes_ * n + 16));
         SB_CUDA(cudaMemcpyAsync(s.src_all.p, srcs[0].data, img_bytes_ * n, cudaMemcpyHostToDevice, s.stream));
         for (int i = 0; i < n; ++i) {
-            src[i].data = static_cast<char *>(s.src_all.p) + img_bytes_ * i;
-            src[i].rows = srcs[i].rows; src[i].cols = srcs[i].cols; src[i].type = SB_8UC3; src[i].step = row_bytes;
+            srcp[i].data = static_cast<char *>(s.src_all.p) + img_bytes_ * i;
+            srcp[i].rows = srcs[i].rows; srcp[i].cols = srcs[i].cols; srcp[i].type = SB_8UC3; srcp[i].step = row_bytes;
         }
     } else {
-        for (int i = 0; i < n; ++i) SB_TRY(to_device(srcs[i], s.src[i], s.stream, &src[i]));
+        for (int i = 0; i < n; ++i) SB_TRY(to_device(srcs[i], s.src[i], s.stream, &srcp[i]));
     }
     s.want_mask = pano_mask != nullptr;
+    const std::vector<DImage> src(srcp, srcp + n);
     SB_TRY(run_frame(c, s, src));
     if (!pano->data) lend(s.out.v, c->device, pano);
     else SB_TRY(from_device(s.out.v, pano, s.stream));
@@ -1131,11 +1150,238 @@ int sb_compositor_enqueue(sb_compositor *c, const sb_image *srcs, sb_image *pano
         if (!pano_mask->data) lend(s.out_mask.v, c->device, pano_mask);
         else SB_TRY(from_device(s.out_mask.v, pano_mask, s.stream));
     }
-    SB_CUDA(cudaEventRecord(s.ev_stop, s.stream));
+    if (timing) SB_CUDA(cudaEventRecord(s.ev_stop, s.stream));
+    return SB_OK;
+}
+
+int sb_compositor_enqueue(sb_compositor *c, const sb_image *srcs, sb_image *pano, sb_image *pano_mask, int *slot)
+{
+    SB_ASSERT(c && srcs && pano && slot);
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    const int si = c->next_slot;
+    Slot &s = c->slots[si];
+    if (s.busy) return fail(SB_ERR_ASSERT, "slot %d still in flight: call sb_compositor_wait first", si);
+    SB_TRY(enqueue_on_slot(c, s, srcs, pano, pano_mask, true));
     s.busy = true;
     *slot = si;
     c->next_slot = (si + 1) % (int)c->slots.size();
     return SB_OK;
+}
+
+// ---- batches: one lap of a video pipeline's buffer ring as ONE host call -------------------------------------------------
+// A video pipeline cycles through a ring of input and output buffers.  At 20-25 us of device time per frame set the per-frame
+// host work of enqueue / wait (two C calls, event records, a launch) and, worse, the launch / ramp-up / tail of one kernel per
+// frame set are what limit a GPU (round-1 SCALE: 0.87 efficiency at N=8 from host launch issue alone).  A batch runs a lap as
+//   PERSISTENT  one launch of the frame kernel that walks all the lap's frame sets (feather / no blending, sources and
+//               panoramas resident on the device): no kernel boundary between frame sets, the tile pipeline never drains;
+//   STREAMS     the frame sets enqueued back to back on the slots' streams by one C call (host buffers, multi-band);
+//   GRAPH       the same recorded as a CUDA graph (SB_BATCH_GRAPH=1; measured slower on B200: a dependent kernel node
+//               starts ~14 us after its predecessor ends).
+struct sb_batch {
+    sb_compositor *c = nullptr;
+    enum Mode { STREAMS, PERSISTENT, GRAPH } mode = STREAMS;
+    int n_frames = 0;
+    std::vector<sb_image> srcs, panos, masks;     // STREAMS: the lap's argument blocks
+    DevBuf frames;                                // PERSISTENT: Fs2Frame[n_frames]
+    Fs2Args args{};
+    bool out8 = true;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int kernel_nodes = 0;        // kernel launches one replay performs (sb_kernel_launch_count)
+    bool launched = false;
+};
+
+// PERSISTENT applies when the frame kernel can read every source and write every panorama in place
+static bool batch_can_persist(sb_compositor *c, int n_frames, const sb_image *srcs, const sb_image *panos, const sb_image *masks)
+{
+    const sb_compositor_config &cfg = c->cfg;
+    if (!(cfg.blender_kind == SB_BLEND_FEATHER || cfg.blender_kind == SB_BLEND_NO) || !c->fused || !c->feather_fast || !c->fs2.ok ||
+        c->feather_variant != 1 || !(c->stream_sharpness > 0.f) || cfg.n_cameras > FS2_TMAP_CAMS)
+        return false;
+    const int n = cfg.n_cameras;
+    const size_t px = (size_t)elem_size(cfg.output_type);
+    for (int f = 0; f < n_frames; ++f) {
+        for (int i = 0; i < n; ++i) {
+            const sb_image &im = srcs[(size_t)f * n + i];
+            if (im.device != c->device || !im.data || im.step % 16 || im.step >= (1ull << 24) || reinterpret_cast<uintptr_t>(im.data) % 16) return false;
+        }
+        const sb_image &p = panos[f];
+        if (p.device != c->device || !p.data || p.step != panos[0].step || p.step % (cfg.output_type == SB_8UC3 ? 4 : 8) ||
+            reinterpret_cast<uintptr_t>(p.data) % 8 || p.rows != c->dst_roi_final.height || p.cols != c->dst_roi_final.width ||
+            p.type != cfg.output_type || (unsigned long long)p.rows * p.step >= (1ull << 32) || p.step < p.cols * px)
+            return false;
+        if (masks) {
+            const sb_image &m = masks[f];
+            if (m.device != c->device || !m.data || m.step != masks[0].step || m.step % 4 || reinterpret_cast<uintptr_t>(m.data) % 4 ||
+                m.rows != p.rows || m.cols != p.cols || m.type != SB_8UC1)
+                return false;
+        }
+    }
+    return true;
+}
+
+int sb_compositor_batch_create(sb_compositor *c, int n_frames, const sb_image *srcs, sb_image *panos, sb_image *pano_masks, sb_batch **out)
+{
+    SB_ASSERT(c && srcs && panos && out && n_frames > 0);
+    *out = nullptr;
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    if (c->external_stream) return fail(SB_ERR_NOT_IMPL, "batches run on the handle's own streams");
+    for (auto &s : c->slots) if (s.busy) return fail(SB_ERR_ASSERT, "batch_create with frames in flight");
+    const int n = c->cfg.n_cameras, depth = (int)c->slots.size();
+    for (int f = 0; f < n_frames; ++f)
+        for (int i = 0; i < n; ++i) {
+            const sb_image &im = srcs[(size_t)f * n + i];
+            SB_ASSERT(im.type == SB_8UC3 && im.rows == c->cfg.src_size.height && im.cols == c->cfg.src_size.width);
+        }
+    sb_batch *b = new sb_batch();
+    b->c = c; b->n_frames = n_frames;
+    int rc = SB_OK;
+    auto cuda_ok = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && rc == SB_OK) rc = fail(SB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+        return e == cudaSuccess;
+    };
+    static const bool want_graph = getenv("SB_BATCH_GRAPH") != nullptr && atoi(getenv("SB_BATCH_GRAPH")) != 0;
+    if (!want_graph && batch_can_persist(c, n_frames, srcs, panos, pano_masks)) {
+        // ---- one launch for the whole lap
+        b->mode = sb_batch::PERSISTENT;
+        std::vector<Fs2Frame> h(n_frames);
+        for (int f = 0; f < n_frames && rc == SB_OK; ++f) {
+            std::memset(&h[f], 0, sizeof(Fs2Frame));
+            for (int i = 0; i < n && rc == SB_OK; ++i) {
+                const sb_image &im = srcs[(size_t)f * n + i];
+                DImage d; d.data = im.data; d.rows = im.rows; d.cols = im.cols; d.type = im.type; d.step = im.step;
+                rc = fs2_tmaps(c, i, d, &h[f].tmap[i * FS2_NCLS]);
+            }
+            h[f].out = panos[f].data;
+            h[f].out_mask = pano_masks ? static_cast<uint8_t *>(pano_masks[f].data) : nullptr;
+        }
+        if (rc == SB_OK) rc = b->frames.ensure(sizeof(Fs2Frame) * (size_t)n_frames);
+        if (rc == SB_OK) cuda_ok(cudaMemcpy(b->frames.p, h.data(), sizeof(Fs2Frame) * (size_t)n_frames, cudaMemcpyHostToDevice), "cudaMemcpy");
+        fs2_static_args(c, b->args);
+        b->args.frames = static_cast<const Fs2Frame *>(b->frames.p);
+        b->args.n_frames = n_frames;
+        b->args.out_step = (unsigned)panos[0].step;
+        b->args.mask_step = pano_masks ? (unsigned)pano_masks[0].step : 0u;
+        b->args.out_mask = pano_masks ? static_cast<uint8_t *>(pano_masks[0].data) : nullptr;       // (non-null = masks wanted)
+        b->args.out = panos[0].data;
+        b->args.pw = c->dst_roi_final.width; b->args.ph = c->dst_roi_final.height;
+        b->out8 = c->cfg.output_type == SB_8UC3;
+        b->kernel_nodes = 1;
+    } else {
+        b->mode = want_graph ? sb_batch::GRAPH : sb_batch::STREAMS;
+        b->srcs.assign(srcs, srcs + (size_t)n_frames * n);
+        b->panos.assign(panos, panos + n_frames);
+        if (pano_masks) b->masks.assign(pano_masks, pano_masks + n_frames);
+        // eager pass first: every buffer the lap needs is allocated, every tensor map encoded, every kernel configured;
+        // it also fills in the lent panoramas (data == NULL) of the caller's array
+        const uint64_t l0 = g_launches.load();
+        for (int f = 0; f < n_frames && rc == SB_OK; ++f)
+            rc = enqueue_on_slot(c, c->slots[f % depth], srcs + (size_t)f * n, &panos[f], pano_masks ? &pano_masks[f] : nullptr, false);
+        for (auto &s : c->slots) cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+        b->kernel_nodes = (int)(g_launches.load() - l0);
+        if (b->mode == sb_batch::GRAPH && rc == SB_OK) {
+            cudaStream_t origin = c->setup_stream;
+            cudaEvent_t fork = nullptr;
+            std::vector<cudaEvent_t> joins(depth, nullptr);
+            cuda_ok(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming), "cudaEventCreate");
+            for (auto &j : joins) cuda_ok(cudaEventCreateWithFlags(&j, cudaEventDisableTiming), "cudaEventCreate");
+            if (rc == SB_OK && cuda_ok(cudaStreamBeginCapture(origin, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture")) {
+                cuda_ok(cudaEventRecord(fork, origin), "fork");
+                for (auto &s : c->slots) cuda_ok(cudaStreamWaitEvent(s.stream, fork, 0), "fork wait");
+                for (int f = 0; f < n_frames && rc == SB_OK; ++f) {
+                    sb_image p = b->panos[f], m = pano_masks ? b->masks[f] : sb_image{};
+                    rc = enqueue_on_slot(c, c->slots[f % depth], b->srcs.data() + (size_t)f * n, &p, pano_masks ? &m : nullptr, false);
+                }
+                for (int k = 0; k < depth; ++k) {
+                    cuda_ok(cudaEventRecord(joins[k], c->slots[k].stream), "join");
+                    cuda_ok(cudaStreamWaitEvent(origin, joins[k], 0), "join wait");
+                }
+                cuda_ok(cudaStreamEndCapture(origin, &b->graph), "cudaStreamEndCapture");      // (always ends the capture, also after an error)
+                if (rc == SB_OK) cuda_ok(cudaGraphInstantiate(&b->exec, b->graph, 0), "cudaGraphInstantiate");
+            }
+            if (fork) cudaEventDestroy(fork);
+            for (auto j : joins) if (j) cudaEventDestroy(j);
+        }
+    }
+    if (rc == SB_OK) { cuda_ok(cudaEventCreate(&b->e0), "cudaEventCreate"); cuda_ok(cudaEventCreate(&b->e1), "cudaEventCreate"); }
+    if (rc != SB_OK) { sb_batch_destroy(b); return rc; }
+    *out = b;
+    return SB_OK;
+}
+
+int sb_batch_launch(sb_batch *b)
+{
+    SB_ASSERT(b);
+    sb_compositor *c = b->c;
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    cudaStream_t origin = c->setup_stream;
+    const int n = c->cfg.n_cameras, depth = (int)c->slots.size();
+    if (b->mode == sb_batch::STREAMS) {
+        // the lap on the slots' streams, bracketed on the origin stream: fork (slots wait for e0), frames, join (e1 waits for slots)
+        SB_CUDA(cudaEventRecord(b->e0, origin));
+        for (auto &s : c->slots) SB_CUDA(cudaStreamWaitEvent(s.stream, b->e0, 0));
+        for (int f = 0; f < b->n_frames; ++f) {
+            sb_image p = b->panos[f], m = b->masks.empty() ? sb_image{} : b->masks[f];
+            SB_TRY(enqueue_on_slot(c, c->slots[f % depth], b->srcs.data() + (size_t)f * n, &p, b->masks.empty() ? nullptr : &m, false));
+        }
+        for (auto &s : c->slots) {
+            SB_CUDA(cudaEventRecord(s.ev_stop, s.stream));
+            SB_CUDA(cudaStreamWaitEvent(origin, s.ev_stop, 0));
+        }
+        SB_CUDA(cudaEventRecord(b->e1, origin));
+    } else if (b->mode == sb_batch::PERSISTENT) {
+        SB_CUDA(cudaEventRecord(b->e0, origin));
+        SB_TRY(launch_fs2(b->args, c->cfg.comp_kind != SB_COMP_NO, b->out8, c->fs2.grid, origin));
+        SB_CUDA(cudaEventRecord(b->e1, origin));
+    } else {
+        SB_ASSERT(b->exec);
+        SB_CUDA(cudaEventRecord(b->e0, origin));
+        SB_CUDA(cudaGraphLaunch(b->exec, origin));
+        g_launches.fetch_add((uint64_t)b->kernel_nodes, std::memory_order_relaxed);
+        SB_CUDA(cudaEventRecord(b->e1, origin));
+    }
+    b->launched = true;
+    return SB_OK;
+}
+
+int sb_batch_mode(const sb_batch *b) { return b ? (int)b->mode : -1; }
+
+int sb_batch_wait(sb_batch *b)
+{
+    SB_ASSERT(b);
+    if (!b->launched) return SB_OK;
+    DeviceGuard g(b->c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    SB_CUDA(cudaEventSynchronize(b->e1));
+    return SB_OK;
+}
+
+int sb_batch_last_gpu_ms(sb_batch *b, float *ms)
+{
+    SB_ASSERT(b && ms && b->launched);
+    DeviceGuard g(b->c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    SB_CUDA(cudaEventSynchronize(b->e1));
+    SB_CUDA(cudaEventElapsedTime(ms, b->e0, b->e1));
+    return SB_OK;
+}
+
+int sb_batch_frames(const sb_batch *b) { return b ? b->n_frames : 0; }
+
+void sb_batch_destroy(sb_batch *b)
+{
+    if (!b) return;
+    DeviceGuard g(b->c->device);
+    if (b->launched && b->e1) cudaEventSynchronize(b->e1);
+    if (b->exec) cudaGraphExecDestroy(b->exec);
+    if (b->graph) cudaGraphDestroy(b->graph);
+    if (b->e0) cudaEventDestroy(b->e0);
+    if (b->e1) cudaEventDestroy(b->e1);
+    delete b;
 }
 
 int sb_compositor_wait(sb_compositor *c, int slot)

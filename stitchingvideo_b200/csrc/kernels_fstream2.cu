@@ -8,6 +8,7 @@
 //   result.convertTo(CV_8U)                                                stitcher.cpp:313
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 #include <vector>
 
 #include "sb_device.cuh"
@@ -108,12 +109,14 @@ int fs2_grid(int n_tiles, int sm_count) { return std::min(n_tiles, FS2_CTAS_PER_
 // ------------------------------------------------------------------------------------ host-side setup
 // Per calibration: boxes of every (camera, tile) -> box width classes -> tile-major blocks -> per-tile descriptors in
 // schedule order with the shared-memory ring plan.
-//   descriptor (64 bytes per panorama tile):
-//   [0]     = {n_cams | short path << 2 | edge tile << 3 | ring units << 8, X0 | Y0 << 16, ring start unit,
-//              tiles of the CTA to retire first | (bytes the copies deliver >> 4) << 16}
-//   [1 + k] = per camera slot (ascending camera index = feed order)
-//             {box x (byte) | box y << 16, table block index, class | tensor copies << 4 | block KB << 8 | ring unit
-//              offset inside the tile << 16, camera}
+//   descriptor (FS2_DESC_RECS x 16 bytes per panorama tile): everything the producer warp needs, ready to issue
+//   [0]     = {n_cams | short path << 2 | edge tile << 3 | copies << 4 | ring units << 8, X0 | Y0 << 16, ring start unit,
+//              lag behind the consumed tiles | (bytes the copies deliver >> 4) << 16}   (see the ring plan below)
+//   [1 + k] = per camera slot (ascending camera index = feed order), for the consumers
+//             {byte offset of the slot inside the tile's ring space, box pitch, -, camera}
+//   [4 + j] = copy j of the tile: {destination byte offset inside the tile's ring space,
+//             bulk copy: byte offset of the table block in the camera's blocks, bytes, camera
+//             tensor copy: box x (byte) | box y << 16, tensor map index (camera * FS2_NCLS + class), bit 31 set}
 int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, int sm_count, DevBuf &desc_out, Fs2Plan *plan, cudaStream_t s)
 {
     *plan = Fs2Plan{};
@@ -149,7 +152,7 @@ int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, i
                                   255u, c.blocks, s));
         SB_CUDA(cudaStreamSynchronize(s));
     }
-    const size_t per = 1 + FS2_MAXC;
+    const size_t per = FS2_DESC_RECS;
     std::vector<uint4> d((size_t)n_tiles * per, make_uint4(0u, 0u, 0u, 0u));
     double table_bytes = 0;
     for (int t = 0; t < n_tiles; ++t) {
@@ -168,21 +171,27 @@ int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, i
             ++k;
         }
         const unsigned short_path = (k == 1 && one) ? 1u : 0u;
-        const unsigned blk_kb = short_path ? FS2_ENT_BYTES / 1024 : FS2_BLOCK_BYTES / 1024;
-        unsigned units = 0, tx_bytes = 0;
+        const unsigned blk_bytes = short_path ? FS2_ENT_BYTES : FS2_BLOCK_BYTES;
+        unsigned units = 0, tx_bytes = 0, n_ops = 0;
         for (int j = 0; j < k; ++j) {
             const Fs2Place &pl = places[slot_cam[j]][slot_blk[j]];
             const unsigned cls = (unsigned)(pl.valid >> 4) & 15u, nops = (unsigned)pl.valid >> 8;
-            const unsigned bytes = blk_kb * 1024u + nops * FS2_ROWS * (unsigned)pl.pitch;
-            o[1 + j] = make_uint4((unsigned)pl.xlo | ((unsigned)pl.ylo << 16), (unsigned)slot_blk[j], cls | (nops << 4) | (blk_kb << 8) | (units << 16),
-                                  (unsigned)slot_cam[j]);
+            const unsigned bytes = blk_bytes + nops * FS2_ROWS * (unsigned)pl.pitch, slot_off = units * 128u;
+            if (slot_blk[j] * (size_t)FS2_BLOCK_BYTES >= (1ull << 32)) return SB_OK;
+            o[1 + j] = make_uint4(slot_off, (unsigned)pl.pitch, 0u, (unsigned)slot_cam[j]);
+            // copy list: the table block (bulk copy), then the source box, FS2_ROWS rows per tensor copy
+            o[1 + FS2_MAXC + n_ops++] = make_uint4(slot_off, (unsigned)(slot_blk[j] * FS2_BLOCK_BYTES), blk_bytes, (unsigned)slot_cam[j]);
+            for (unsigned q = 0; q < nops; ++q)
+                o[1 + FS2_MAXC + n_ops++] = make_uint4(slot_off + blk_bytes + q * FS2_ROWS * (unsigned)pl.pitch,
+                                                       ((unsigned)pl.xlo & 0xffffu) | ((unsigned)(pl.ylo + (int)(q * FS2_ROWS)) << 16),
+                                                       (unsigned)slot_cam[j] * FS2_NCLS + cls, 0x80000000u);
             units += (bytes + 127u) >> 7;
             tx_bytes += bytes;
-            table_bytes += blk_kb * 1024.0;
+            table_bytes += blk_bytes;
         }
         const unsigned X0 = (unsigned)(tx * FS2_W), Y0 = (unsigned)(ty * FS2_H);
         const unsigned edge = ((int)X0 + FS2_W > pw || (int)Y0 + FS2_H > ph) ? 1u : 0u;
-        o[0] = make_uint4((unsigned)k | (short_path << 2) | (edge << 3) | (units << 8), X0 | (Y0 << 16), 0u, (tx_bytes >> 4) << 16);
+        o[0] = make_uint4((unsigned)k | (short_path << 2) | (edge << 3) | (n_ops << 4) | (units << 8), X0 | (Y0 << 16), 0u, (tx_bytes >> 4) << 16);
     }
     // Schedule order: CTA b takes positions b, b + G, ... of the descriptor array, so listing the tiles by descending cost
     // (blended tiles with 3, 2, 1 cameras, then the single-camera short-path tiles, then empty ones; row-major inside a
@@ -207,36 +216,49 @@ int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, i
         for (size_t j = 0; j < per; ++j) at(t)[j] = d[(size_t)order[t] * per + j];
     // The shared-memory ring plan.  CTA b walks positions b, b + G, ...; a tile takes `units` contiguous 128-byte ring units
     // at the head, wrapping to 0 when the end of the ring is too short; space is handed back in tile order.  Both are a pure
-    // function of the tile sizes, so the start unit of every tile and the number of the CTA's tiles that must have been
-    // consumed before its copies may land are computed here, once: [0].z = start unit, [0].w low half = tiles to retire first
-    // (also covers the reuse of the tile's stage entry).  The producer warp then needs no bookkeeping at all.
+    // function of the tile sizes, so the start unit of every tile and how far behind it the CTA's consumed tiles must be
+    // before its copies may land are computed here, once.  A multi-frame launch walks the same tile sequence frame after
+    // frame without emptying the ring, so the plan is made for three frames in a row: frame 0 starts from an empty ring
+    // (plan 0), and if frames 1 and 2 come out the same the ring has reached its cycle (plan 1, for every later frame).
+    //   [0].z = start unit (plan 0) | start unit (plan 1) << 16
+    //   [0].w = lag (plan 0) | lag (plan 1) << 8 | bytes >> 4 << 16;  lag: copies of tile number s (counted over the frames)
+    //           may land once the CTA's tiles up to number s - lag - 1 are consumed (also covers the reuse of the stage entry)
+    // The producer warps then need no bookkeeping at all.
     constexpr int RING_UNITS = FS2_RING_BYTES / 128;
+    bool steady = true;
     for (int b = 0; b < grid; ++b) {
+        const int mine = (n_tiles - b + grid - 1) / grid;
+        std::vector<int> start(3 * (size_t)mine), lag(3 * (size_t)mine);
         int hist[FS2_STAGES];
-        int head = 0, tail = 0, oldest = 0, seq = 0;
-        for (int tile = b; tile < n_tiles; tile += grid, ++seq) {
-            uint4 &d0 = *at(tile);
-            const int units = (int)(d0.x >> 8);
-            int start;
+        int head = 0, tail = 0, oldest = 0;
+        for (int g = 0; g < 3 * mine; ++g) {
+            const int units = (int)(at(b + (g % mine) * grid)->x >> 8);
+            int st;
             for (;;) {
-                if (seq - oldest < FS2_STAGES) {
-                    if (seq == oldest) head = tail = 0;     // nothing in flight
+                if (g - oldest < FS2_STAGES) {
+                    if (g == oldest) head = tail = 0;       // nothing in flight
                     if (head >= tail) {                     // in use: [tail, head)
-                        if (head + units <= RING_UNITS) { start = head; break; }
-                        if (units < tail) { start = 0; break; }
+                        if (head + units <= RING_UNITS) { st = head; break; }
+                        if (units < tail) { st = 0; break; }
                     } else if (head + units < tail) {       // in use: [tail, end) and [0, head)
-                        start = head; break;
+                        st = head; break;
                     }
                 }
                 ++oldest;
-                tail = oldest < seq ? hist[oldest % FS2_STAGES] : head;
+                tail = oldest < g ? hist[oldest % FS2_STAGES] : head;
             }
-            head = start + units;
-            hist[seq % FS2_STAGES] = start;
-            d0.z = (unsigned)start;
-            d0.w |= (unsigned)oldest;
+            head = st + units;
+            hist[g % FS2_STAGES] = st;
+            start[g] = st; lag[g] = g - oldest;
+        }
+        for (int q = 0; q < mine; ++q) {
+            uint4 &d0 = *at(b + q * grid);
+            steady = steady && start[mine + q] == start[2 * mine + q] && lag[mine + q] == lag[2 * mine + q];
+            d0.z = (unsigned)start[q] | ((unsigned)start[mine + q] << 16);
+            d0.w |= (unsigned)lag[q] | ((unsigned)lag[mine + q] << 8);
         }
     }
+    plan->steady = steady;
     SB_TRY(desc_out.ensure(o.size() * sizeof(uint4)));
     SB_CUDA(cudaMemcpyAsync(desc_out.p, o.data(), o.size() * sizeof(uint4), cudaMemcpyHostToDevice, s));
     SB_CUDA(cudaStreamSynchronize(s));
@@ -329,9 +351,12 @@ __device__ __forceinline__ void fs2_weights(uint32_t e, unsigned &wx, unsigned &
 template <int BIAS>
 __device__ __forceinline__ void fs2_pixel(const unsigned char *sm, uint32_t box, uint32_t pitch, uint32_t e, unsigned &s0, unsigned &s1, unsigned &s2)
 {
+#ifdef SB_FS2_EXPERIMENT_NOCONFLICT
+    e &= ~0x7ffe0u;                                          // tuning experiment: every tap at box offset 0 (broadcast, no bank conflicts; results are garbage)
+#endif
     uint2 bw;
     fs2_weights(e, bw.x, bw.y);
-    const unsigned char *r0 = sm + box + ((e >> 3) & 0x3ffcu);
+    const unsigned char *r0 = sm + box + ((e >> 3) & 0xfffcu);
     const unsigned char *r1 = r0 + pitch;
     const unsigned a0 = *reinterpret_cast<const uint32_t *>(r0), a1 = *reinterpret_cast<const uint32_t *>(r0 + 4),
                    a2 = *reinterpret_cast<const uint32_t *>(r0 + 8);
@@ -358,10 +383,15 @@ __device__ __forceinline__ unsigned fs2_apply_gain(unsigned v, float g)
 }
 
 // The 4 pixels x 3 channels of one thread, each value in byte B of its register (the byte above it zero), as the 12 (8UC3)
-// or 24 (16SC3) output bytes.  Full tiles: vector stores; edge tiles: per pixel, guarded.
+// or 24 (16SC3) output bytes.  Full tiles: three 32-bit (64-bit) stores per thread; edge tiles: per pixel, guarded.
+// (Tried in round 2: staging the warp's 4 rows in shared memory so that consecutive lanes store consecutive words made the
+// C2 frame 1.7 us SLOWER - the extra shared-memory traffic costs more than the partial-sector stores.)
 template <bool OUT8, int B>
 __device__ __forceinline__ void fs2_store_quad(unsigned char *o, const unsigned (&v)[4][3], bool edge, int nx, bool row_ok)
 {
+#ifdef SB_FS2_EXPERIMENT_NOSTORE
+    if (nx >= 0) return;                                     // tuning experiment: no output stores at all
+#endif
     if (!edge) {
         if (OUT8) {
             constexpr unsigned S = (unsigned)B | ((unsigned)(B + 4) << 4);
@@ -392,6 +422,9 @@ __device__ __forceinline__ void fs2_store_quad(unsigned char *o, const unsigned 
 }
 __device__ __forceinline__ void fs2_store_mask(uint8_t *m, unsigned word, bool edge, int nx, bool row_ok)
 {
+#ifdef SB_FS2_EXPERIMENT_NOSTORE
+    if (nx >= 0) return;
+#endif
     if (!edge) { *reinterpret_cast<uint32_t *>(m) = word; return; }
     if (!row_ok) return;
 #pragma unroll
@@ -399,20 +432,19 @@ __device__ __forceinline__ void fs2_store_mask(uint8_t *m, unsigned word, bool e
         if (p < nx) m[p] = (uint8_t)(word >> (8 * p));
 }
 
-#ifdef SB_FS2_TRACE
+// Pipeline trace (debugging aid, off unless the environment variable SB_FS2_TRACE names a file): per CTA and tile four
+// timestamps - copies issued, consumer group starts waiting, data landed, tile finished.
 __device__ __forceinline__ unsigned long long fs2_now()
 {
     unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
 #define FS2_TRACE(SLOT, SEQ)                                                                        \
     do {                                                                                            \
-        if (a.trace && (SEQ) < 64) a.trace[((size_t)blockIdx.x * 64 + (SEQ)) * 4 + (SLOT)] = fs2_now(); \
+        if (a.trace && (SEQ) < FS2_TRACE_TILES) a.trace[((size_t)blockIdx.x * FS2_TRACE_TILES + (SEQ)) * 8 + (SLOT)] = fs2_now(); \
     } while (0)
-#else
-#define FS2_TRACE(SLOT, SEQ) do { } while (0)
-#endif
+constexpr int FS2_TRACE_TILES = 64;
 
 // NOBLEND: Blender::feed / blend without blending (blenders.cpp:81-112): the pixel of the LAST camera (feed order)
 // whose mask is non-zero, dst_mask = OR of the mask bytes, 0 where no camera has a mask.
@@ -444,56 +476,58 @@ k_fs2(const __grid_constant__ Fs2Args a)
         // the parallelism that keeps the ring full comes from the P warps.
         const int pw = warp - FS2_GROUPS * FS2_GROUP_WARPS;
         const uint32_t ring0 = smem_u32(&sm.ring[0]);
-        const uint4 *dp = a.desc + ((size_t)blockIdx.x * a.per_cta + pw) * (1 + FS2_MAXC);
+        const uint4 *const dp0 = a.desc + (size_t)blockIdx.x * a.per_cta * FS2_DESC_RECS;
         const int n_mine = (a.n_tiles - (int)blockIdx.x + G - 1) / G;
-        uint4 nx0 = make_uint4(0u, 0u, 0u, 0u), nx1 = nx0, nx2 = nx0, nx3 = nx0;
-        if (pw < n_mine) { nx0 = __ldg(dp); nx1 = __ldg(dp + 1); nx2 = __ldg(dp + 2); nx3 = __ldg(dp + 3); }
+        const int total = n_mine * max(a.n_frames, 1);      // a multi-frame launch walks the same tiles once per frame set
+        // lane l holds record l of the tile's descriptor (one coalesced 256-byte load, a tile ahead of its use)
+        auto load_rec = [&](int g) { return lane < FS2_DESC_RECS ? __ldg(dp0 + (size_t)(g % n_mine) * FS2_DESC_RECS + lane) : make_uint4(0u, 0u, 0u, 0u); };
+        uint4 nx = make_uint4(0u, 0u, 0u, 0u);
+        if (pw < total) nx = load_rec(pw);
         int retired = 0;
-        for (int seq = pw; seq < n_mine; seq += FS2_PRODUCERS) {
-            const uint4 d0 = nx0, d1 = nx1, d2 = nx2, d3 = nx3;
-            dp += FS2_PRODUCERS * (1 + FS2_MAXC);
-            if (seq + FS2_PRODUCERS < n_mine) { nx0 = __ldg(dp); nx1 = __ldg(dp + 1); nx2 = __ldg(dp + 2); nx3 = __ldg(dp + 3); }
-            const int stage = seq % FS2_STAGES;
-            const int nc = (int)(d0.x & 3u);
-            const int need = max((int)(d0.w & 0xffffu), seq - FS2_STAGES + 1);
+        for (int gs = pw; gs < total; gs += FS2_PRODUCERS) {     // gs: tile number counted over the frames
+            const uint4 d = nx;
+            if (gs + FS2_PRODUCERS < total) nx = load_rec(gs + FS2_PRODUCERS);
+            const int f = gs / n_mine, seq = gs - f * n_mine;
+            const int stage = gs % FS2_STAGES;
+            if (lane == 0) FS2_TRACE(4, gs);
+            const unsigned d0x = __shfl_sync(0xffffffffu, d.x, 0), d0z = __shfl_sync(0xffffffffu, d.z, 0), d0w = __shfl_sync(0xffffffffu, d.w, 0);
+            // plan 0: the ring was empty when this frame started (first frame; every frame when the plan is not cyclic and
+            // the ring is drained in between); plan 1: the cyclic plan of the frames after the first
+            const bool cyc = f > 0 && a.steady;
+            int need = gs - (int)((cyc ? d0w >> 8 : d0w) & 0xffu);
+            if (f > 0 && !a.steady) need = max(need, f * n_mine);
             for (; retired < need; ++retired)              // groups finish tiles out of order: every warp awaits every tile once, in order
                 mbar_wait_hw(&sm.empty[retired % FS2_STAGES], (unsigned)(retired / FS2_STAGES) & 1u);
-            const uint32_t tile_off = d0.z * 128u;          // ring byte offset of the tile
+            const Fs2Frame *fr = a.frames ? a.frames + f : nullptr;
+            const CUtensorMap *tmaps = fr ? fr->tmap : a.tmap;
+            if (fr && seq < FS2_PRODUCERS && lane < a.n * FS2_NCLS)      // first use of this frame's tensor maps by this warp: they were
+                asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmaps + lane) : "memory");   // written through the generic proxy
+            const uint32_t tile_off = ((cyc ? d0z >> 16 : d0z) & 0xffffu) * 128u;          // ring byte offset of the tile
             if (lane <= FS2_MAXC) {
-                uint4 ds;
+                uint4 ds = d;
                 if (lane == 0) {                            // tile origin -> byte offsets of its first pixel in the panorama and the mask
-                    const unsigned X0 = d0.y & 0xffffu, Y0 = d0.y >> 16;
-                    ds = make_uint4(d0.x, d0.y, Y0 * a.out_step + X0 * (OUT8 ? 3u : 6u), Y0 * a.mask_step + X0);
+                    const unsigned X0 = d.y & 0xffffu, Y0 = d.y >> 16;
+                    ds.z = Y0 * a.out_step + X0 * (OUT8 ? 3u : 6u); ds.w = Y0 * a.mask_step + X0;
                 } else {
-                    const uint4 r = lane == 1 ? d1 : lane == 2 ? d2 : d3;
-                    ds = make_uint4(tile_off + (r.z >> 16) * 128u, a.cls_w[r.z & 3u], 0u, r.w);
+                    ds.x += tile_off;                       // the slot's byte offset in the ring
                 }
                 sm.desc[stage][lane] = ds;
             }
             __syncwarp();
+            const int n_ops = (int)((d0x >> 4) & 15u);
             if (lane == 0) {
-                if (nc == 0) mbar_arrive(&sm.full[stage]);
-                else mbar_arrive_expect_tx(&sm.full[stage], (d0.w >> 16) << 4);
-                FS2_TRACE(0, seq);
+                if (n_ops == 0) mbar_arrive(&sm.full[stage]);
+                else mbar_arrive_expect_tx(&sm.full[stage], (d0w >> 16) << 4);
+                FS2_TRACE(0, gs);
             }
             __syncwarp();
-            // copies: lane -> (camera slot k, copy j of it)
-            const int n0 = nc > 0 ? 1 + (int)((d1.z >> 4) & 15u) : 0, n1 = nc > 1 ? 1 + (int)((d2.z >> 4) & 15u) : 0,
-                      n2 = nc > 2 ? 1 + (int)((d3.z >> 4) & 15u) : 0;
-            if (lane < n0 + n1 + n2) {
-                const int k = (lane >= n0) + (lane >= n0 + n1);
-                const int j = lane - (k == 0 ? 0 : k == 1 ? n0 : n0 + n1);
-                const uint4 r = k == 0 ? d1 : k == 1 ? d2 : d3;
-                const unsigned cam = r.w & 15u, cls = r.z & 3u, blk_bytes = ((r.z >> 8) & 15u) << 10;
-                const uint32_t slot = ring0 + tile_off + (r.z >> 16) * 128u;
-                if (j == 0) {
-                    bulk_g2s_addr(slot, a.cam[cam].blocks + (size_t)r.y * FS2_BLOCK_BYTES, blk_bytes, &sm.full[stage]);
-                } else {
-                    const unsigned wb = a.cls_w[cls];
-                    tma_load_2d(slot + blk_bytes + (unsigned)(j - 1) * wb * FS2_ROWS, &a.tmap[cam * FS2_NCLS + cls],
-                                (int)(r.x & 0xffffu), (int)(r.x >> 16) + (j - 1) * FS2_ROWS, &sm.full[stage]);
-                }
+            // copies: lane 1 + FS2_MAXC + j issues copy j of the tile's list
+            if (lane > FS2_MAXC && lane <= FS2_MAXC + n_ops) {
+                const uint32_t dst = ring0 + tile_off + d.x;
+                if (d.w & 0x80000000u) tma_load_2d(dst, tmaps + d.z, (int)(d.y & 0xffffu), (int)(d.y >> 16), &sm.full[stage]);
+                else bulk_g2s_addr(dst, a.cam[d.w].blocks + d.y, d.z, &sm.full[stage]);
             }
+            if (lane == 0) FS2_TRACE(5, gs);
         }
         return;
     }
@@ -504,21 +538,35 @@ k_fs2(const __grid_constant__ Fs2Args a)
     const int grp = warp / FS2_GROUP_WARPS, slab = warp % FS2_GROUP_WARPS;
     const int ty = slab * 4 + (lane >> 3), tx = (lane & 7) * 4;
     const uint32_t tab_off = (uint32_t)(ty * FS2_W + tx) * 4u, plane_off = (uint32_t)FS2_ENT_BYTES + (uint32_t)(ty * FS2_W + tx);
-    unsigned char *const out_t = reinterpret_cast<unsigned char *>(a.out) + ((unsigned)ty * a.out_step + (unsigned)tx * (OUT8 ? 3u : 6u));
-    uint8_t *const mask_t = a.out_mask ? a.out_mask + ((unsigned)ty * a.mask_step + (unsigned)tx) : nullptr;
+    const unsigned out_t = (unsigned)ty * a.out_step + (unsigned)tx * (OUT8 ? 3u : 6u), mask_t = (unsigned)ty * a.mask_step + (unsigned)tx;
     const int n_mine = (a.n_tiles - (int)blockIdx.x + G - 1) / G;
-    for (int seq = grp; seq < n_mine; seq += FS2_GROUPS) {
+    const int total = n_mine * max(a.n_frames, 1);
+    unsigned char *out_f = reinterpret_cast<unsigned char *>(a.out);
+    uint8_t *mask_f = a.out_mask;
+    int next_frame_at = a.frames ? 0 : total;               // tile number at which the next frame set's output pointers are due
+    for (int seq = grp; seq < total; seq += FS2_GROUPS) {   // seq: tile number counted over the frames
+        if (seq >= next_frame_at) {
+            const Fs2Frame *fr = a.frames + seq / n_mine;
+            out_f = reinterpret_cast<unsigned char *>(fr->out); mask_f = fr->out_mask;
+            next_frame_at = (seq / n_mine + 1) * n_mine;
+        }
         const int stage = seq % FS2_STAGES;
-        mbar_wait_hw(&sm.full[stage], (unsigned)(seq / FS2_STAGES) & 1u);
         if (tid % (FS2_GROUP_WARPS * 32) == 0) FS2_TRACE(1, seq);
+        mbar_wait_hw(&sm.full[stage], (unsigned)(seq / FS2_STAGES) & 1u);
+        if (tid % (FS2_GROUP_WARPS * 32) == 0) FS2_TRACE(2, seq);
+        if (a.debug == 1) {                                  // tuning experiment: the supply side alone (results are garbage)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[stage]);
+            continue;
+        }
         const uint4 d0 = sm.desc[stage][0];
         const int nc = (int)(d0.x & 3u);
         const bool edge = (d0.x & 8u) != 0u;                // block-uniform: the tile crosses the panorama's right / bottom edge
         const int X = (int)(d0.y & 0xffffu) + tx, Y = (int)(d0.y >> 16) + ty;
         const int nx = edge ? min(max(a.pw - X, 0), 4) : 4;
         const bool row_ok = !edge || Y < a.ph;
-        unsigned char *const o = out_t + d0.z;
-        uint8_t *const mo = mask_t ? mask_t + d0.w : nullptr;
+        unsigned char *const o = out_f + (out_t + d0.z);
+        uint8_t *const mo = mask_f ? mask_f + (mask_t + d0.w) : nullptr;
         unsigned v[4][3];
         if (d0.x & 4u) {
             // Short path (block-uniform; ~2/3 of a ring panorama): ONE camera with weight exactly 1.0f on every pixel of
@@ -639,13 +687,56 @@ k_fs2(const __grid_constant__ Fs2Args a)
             fs2_store_quad<OUT8, 0>(o, v, edge, nx, row_ok);
             if (mo) fs2_store_mask(mo, mword, edge, nx, row_ok);
         }
-        if (tid % (FS2_GROUP_WARPS * 32) == 0) FS2_TRACE(2, seq);
+        if (tid % (FS2_GROUP_WARPS * 32) == 0) FS2_TRACE(3, seq);
     }
+}
+
+// ---- pipeline trace plumbing (SB_FS2_TRACE=file): a pool of 64 buffers, one per launch, dumped on request
+static constexpr int FS2_TRACE_POOL = 64;
+static unsigned long long *g_trace_pool[FS2_TRACE_POOL] = {};
+static int g_trace_grid = 0, g_trace_next = 0;
+static bool fs2_trace_enabled()
+{
+    static const bool on = getenv("SB_FS2_TRACE") != nullptr;
+    return on;
+}
+static int fs2_debug_mode()
+{
+    static const int m = getenv("SB_FS2_DEBUG") ? atoi(getenv("SB_FS2_DEBUG")) : 0;
+    return m;
+}
+static unsigned long long *fs2_trace_buffer(int grid)
+{
+    if (!g_trace_pool[0]) {                                  // (first launch: never inside a stream capture, batches warm up eagerly)
+        g_trace_grid = grid;
+        const size_t bytes = (size_t)grid * FS2_TRACE_TILES * 8 * sizeof(unsigned long long);
+        for (auto &p : g_trace_pool) { cudaMalloc(&p, bytes); cudaMemset(p, 0, bytes); }
+    }
+    return g_trace_pool[g_trace_next++ % FS2_TRACE_POOL];
+}
+// writes the pool (launch-major) to the file SB_FS2_TRACE names; returns the number of launches since the last dump
+int fs2_trace_dump()
+{
+    if (!fs2_trace_enabled() || !g_trace_pool[0]) return 0;
+    cudaDeviceSynchronize();
+    const size_t bytes = (size_t)g_trace_grid * FS2_TRACE_TILES * 8 * sizeof(unsigned long long);
+    std::vector<unsigned long long> h(bytes / 8);
+    FILE *f = fopen(getenv("SB_FS2_TRACE"), "wb");
+    if (!f) return -1;
+    const int n = std::min(g_trace_next, FS2_TRACE_POOL);
+    for (int k = 0; k < n; ++k) {
+        cudaMemcpy(h.data(), g_trace_pool[k], bytes, cudaMemcpyDeviceToHost);
+        fwrite(h.data(), 1, bytes, f);
+        cudaMemset(g_trace_pool[k], 0, bytes);
+    }
+    fclose(f);
+    g_trace_next = 0;
+    return n;
 }
 
 int launch_fs2(const Fs2Args &a, bool apply_gain, bool out8, int grid, cudaStream_t s)
 {
-    SB_ASSERT(a.sharpness > 0.f && a.desc && a.n_tiles > 0 && a.n <= SB_MAX_CAMERAS);
+    SB_ASSERT(a.sharpness > 0.f && a.desc && a.n_tiles > 0 && a.n <= FS2_TMAP_CAMS);
     SB_ASSERT(a.pw < 65536 && a.ph < 65536 && (unsigned long long)a.ph * a.out_step < (1ull << 32) && (unsigned long long)a.ph * a.mask_step < (1ull << 32));
     SB_ASSERT(reinterpret_cast<uintptr_t>(a.out) % 8 == 0 && a.out_step % (out8 ? 4 : 8) == 0);
     SB_ASSERT(!a.out_mask || (reinterpret_cast<uintptr_t>(a.out_mask) % 4 == 0 && a.mask_step % 4 == 0));
@@ -662,6 +753,23 @@ int launch_fs2(const Fs2Args &a, bool apply_gain, bool out8, int grid, cudaStrea
     if (!configured[v]) {
         SB_CUDA(cudaFuncSetAttribute(fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[v] = true;
+    }
+    if (fs2_trace_enabled()) {                               // debugging aid: launch k writes its timestamps to trace buffer k % 64
+        Fs2Args at = a;
+        at.trace = fs2_trace_buffer(grid);
+        at.debug = fs2_debug_mode();
+        void *params[] = {&at};
+        SB_CUDA(cudaLaunchKernel(fn[v], dim3(grid), dim3(FS2_THREADS), params, smem, s));
+        SB_LAUNCHED();
+        return SB_OK;
+    }
+    if (fs2_debug_mode()) {
+        Fs2Args ad = a;
+        ad.debug = fs2_debug_mode();
+        void *params[] = {&ad};
+        SB_CUDA(cudaLaunchKernel(fn[v], dim3(grid), dim3(FS2_THREADS), params, smem, s));
+        SB_LAUNCHED();
+        return SB_OK;
     }
     void *params[] = {const_cast<Fs2Args *>(&a)};
     SB_CUDA(cudaLaunchKernel(fn[v], dim3(grid), dim3(FS2_THREADS), params, smem, s));

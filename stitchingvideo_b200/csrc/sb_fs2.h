@@ -33,20 +33,26 @@ namespace sb {
 #define SB_CFG_FS2_PRODUCERS 4
 #endif
 #ifndef SB_CFG_FS2_ROWS
-#define SB_CFG_FS2_ROWS 16
+#define SB_CFG_FS2_ROWS 48
 #endif
 #ifndef SB_CFG_FS2_RING_KB
 #define SB_CFG_FS2_RING_KB 200
 #endif
 
+#ifndef SB_CFG_FS2_TMAP_CAMS
+#define SB_CFG_FS2_TMAP_CAMS 12
+#endif
+constexpr int FS2_TMAP_CAMS = SB_CFG_FS2_TMAP_CAMS;
 constexpr int FS2_W = 32, FS2_H = 32;                 // panorama tile
 constexpr int FS2_NCLS = 4;                           // source-box width classes (one tensor map per camera and class)
 constexpr int FS2_ROWS = SB_CFG_FS2_ROWS;             // box rows per tensor copy
-constexpr int FS2_MAX_OPS = 64 / FS2_ROWS;            // <= 64 box rows
+constexpr int FS2_MAX_OPS = 96 / FS2_ROWS;            // <= 96 box rows
+static_assert(1 + 3 + 3 * (1 + FS2_MAX_OPS) <= 16, "a tile's copy list must fit its descriptor");
 constexpr int FS2_MAX_BOX_W = 256;                    // TMA box dimension limit
 constexpr int FS2_ENT_BYTES = FS2_W * FS2_H * 4;      // tap entries of one (tile, camera)
 constexpr int FS2_BLOCK_BYTES = FS2_ENT_BYTES + FS2_W * FS2_H;   // + the weight-index plane (fetched only where cameras blend)
-constexpr int FS2_MAXC = 3;                           // cameras with weight inside one tile (more -> k_feather_fused_px1)
+constexpr int FS2_MAXC = 3;
+constexpr int FS2_DESC_RECS = 16;                      // 16-byte records per tile descriptor: 1 + FS2_MAXC + the tile's copy list                           // cameras with weight inside one tile (more -> k_feather_fused_px1)
 constexpr int FS2_GROUPS = SB_CFG_FS2_GROUPS;         // consumer groups (8 warps each) per CTA, each on its own tile
 constexpr int FS2_GROUP_WARPS = 8;
 constexpr int FS2_STAGES = 8 * FS2_GROUPS;            // tile entries (descriptor + barriers) in flight per CTA
@@ -63,10 +69,16 @@ struct Fs2Cam {
     float gain;
     int dx, dy;                    // warped corner in panorama coordinates (gain map lookup)
 };
+// one frame set of a multi-frame launch (global memory, written by the host before the launch)
+struct alignas(128) Fs2Frame {
+    CUtensorMap tmap[FS2_TMAP_CAMS * FS2_NCLS];
+    void *out;
+    uint8_t *out_mask;
+};
 struct alignas(64) Fs2Args {
-    CUtensorMap tmap[SB_MAX_CAMERAS * FS2_NCLS];     // source image of camera i as a 2-D byte tensor, box = cls_w[c] x FS2_ROWS
+    CUtensorMap tmap[FS2_TMAP_CAMS * FS2_NCLS];     // source image of camera i as a 2-D byte tensor, box = cls_w[c] x FS2_ROWS
     Fs2Cam cam[SB_MAX_CAMERAS];
-    const uint4 *desc;             // per tile in schedule order: 1 + FS2_MAXC records (kernels_fstream2.cu)
+    const uint4 *desc;             // per tile in schedule order, CTA-major: FS2_DESC_RECS records (kernels_fstream2.cu)
     unsigned cls_w[FS2_NCLS];
     float sharpness;
     int no_blend;
@@ -75,8 +87,12 @@ struct alignas(64) Fs2Args {
     uint8_t *out_mask;
     unsigned mask_step;
     int pw, ph, n_tiles, n;
-    int per_cta;                   // descriptors of CTA b start at desc + b * per_cta * (1 + FS2_MAXC)
-    unsigned long long *trace;     // SB_FS2_TRACE builds: per CTA and tile {issue, full, done} timestamps
+    int per_cta;                   // descriptors of CTA b start at desc + b * per_cta * FS2_DESC_RECS
+    const Fs2Frame *frames;        // multi-frame launch: n_frames frame sets (tmap / out / out_mask above are then unused)
+    int n_frames;                  // 0 or 1: the single frame set described by this block
+    int steady;                    // Fs2Plan::steady
+    int debug;                     // tuning experiments (SB_FS2_DEBUG): 1 = supply side only (no pixel work)
+    unsigned long long *trace;     // null, or (SB_FS2_TRACE=file) per CTA and tile {issued, wait, landed, done} timestamps
 };
 
 // one (camera, tile) of the setup pass: the source bounding box of the weighted entries
@@ -94,6 +110,7 @@ struct Fs2Plan {                    // host-side result of the setup: what the c
     int n_tiles = 0, grid = 0, per_cta = 0;
     double table_bytes = 0;         // bytes of table blocks one frame fetches (algorithmic bytes of the table stream)
     bool ok = false;
+    bool steady = false;            // the ring plan of frames >= 1 of a multi-frame launch is cyclic (else the ring is drained between frames)
 };
 
 struct Fs2CamSetup {               // one camera as the setup sees it
@@ -116,5 +133,6 @@ int launch_fs2_entries(const uint2 *table, size_t tstep, int ww, int wh, int dx,
 // the source image of one camera as FS2_NCLS tensor maps
 int fs2_encode_tmaps(const void *src, size_t sstep, int sw, int sh, const unsigned cls_w[FS2_NCLS], CUtensorMap out[FS2_NCLS]);
 int launch_fs2(const Fs2Args &a, bool apply_gain, bool out8, int grid, cudaStream_t s);
+int fs2_trace_dump();           // debugging aid (SB_FS2_TRACE): see kernels_fstream2.cu
 
 }  // namespace sb

@@ -1,0 +1,108 @@
+"""sb_compositor_batch_*: a lap of frame sets recorded as a CUDA graph gives the panoramas enqueue/wait gives (and the
+oracle gives), replay after replay, for host and device buffers."""
+import numpy as np
+import pytest
+
+from oracle import pipeline as P
+from stitchingvideo_b200 import rigs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rig,blender", [("mini_cyl", "feather"), ("mini", "multiband"), ("mini_cyl", "no")])
+def test_batch_equals_per_frame_calls(gpu, rig, blender):
+    Ks, Rs, spec = rigs.cameras(rig)
+    size, n = (spec["W"], spec["H"]), spec["n_used"]
+    gains = ([0.95, 1.02, 1.0, 0.98, 1.05] * 2)[:n]
+    comp = gpu.Compositor(size, Ks, Rs, warper=spec["warper"], scale=spec["scale"], blender=blender, gains=gains)
+    comp.set_depth(3)
+    cal = P.Calibration(size, Ks, Rs, spec["warper"], spec["scale"])
+    sets = [[rigs.frame(rig, f, i) for i in range(n)] for f in range(4)]
+    refs = [P.compose(cal, s, blender=blender, gains=gains) for s in sets]
+    lap = [sets[f % 4] for f in range(7)]                       # 7 frame sets over 3 slots: slots are reused inside the lap
+    w, h = comp.pano_size
+    panos = [np.zeros((h, w, 3), np.uint8) for _ in lap]
+    masks = [np.zeros((h, w), np.uint8) for _ in lap]
+    b = comp.batch(lap, panos, masks)
+    assert b.n_frames == 7
+    for rep in range(3):
+        for p in panos:
+            p[:] = 0
+        b.launch()
+        b.wait()
+        for f in range(7):
+            assert np.array_equal(panos[f], refs[f % 4][0]), "replay %d frame %d" % (rep, f)
+            assert np.array_equal(masks[f], refs[f % 4][1])
+    assert b.last_gpu_ms() > 0
+    b.close()
+    # the handle still serves per-frame calls afterwards
+    pano, mask = comp.compose(sets[1])
+    assert np.array_equal(pano, refs[1][0]) and np.array_equal(mask, refs[1][1])
+
+
+@pytest.mark.parametrize("rig,blender,out16", [("mini_cyl", "feather", False), ("mini_cyl", "no", False), ("mini_cyl_n9", "feather", True),
+                                               ("mini_sph_n7", "feather", False)])
+def test_persistent_lap_on_device_buffers(gpu, rig, blender, out16):
+    """Device sources + device panoramas: the whole lap is ONE launch of the frame kernel (sb_batch_mode 1), bit-exact per
+    frame set against the oracle, replay after replay."""
+    import torch
+    from stitchingvideo_b200 import capi
+    Ks, Rs, spec = rigs.cameras(rig)
+    size, n = (spec["W"], spec["H"]), spec["n_used"]
+    gains = ([0.95, 1.02, 1.0, 0.98, 1.05] * 2)[:n]
+    comp = gpu.Compositor(size, Ks, Rs, warper=spec["warper"], scale=spec["scale"], blender=blender, gains=gains,
+                          output_type=gpu.CV_16SC3 if out16 else gpu.CV_8UC3)
+    cal = P.Calibration(size, Ks, Rs, spec["warper"], spec["scale"])
+    sets = [[rigs.frame(rig, f, i) for i in range(n)] for f in range(3)]
+    refs = [P.compose(cal, s, blender=blender, gains=gains, output_8u=not out16) for s in sets]
+    dev = [[capi.DeviceImage.from_torch(torch.from_numpy(a).cuda()) for a in s] for s in sets]
+    w, h = comp.pano_size
+    wp = (w + 7) & ~7                                                     # row pitch aligned for the kernel's vector stores
+    F = 5
+    pt = [torch.zeros((h, wp, 3), dtype=torch.int16 if out16 else torch.uint8, device="cuda") for _ in range(F)]
+    mt = [torch.zeros((h, wp), dtype=torch.uint8, device="cuda") for _ in range(F)]
+    esz = 6 if out16 else 3
+    panos = [capi.DeviceImage(t.data_ptr(), h, w, gpu.CV_16SC3 if out16 else gpu.CV_8UC3, wp * esz, 0, owner=t) for t in pt]
+    masks = [capi.DeviceImage(t.data_ptr(), h, w, gpu.CV_8UC1, wp, 0, owner=t) for t in mt]
+    b = comp.batch([dev[f % 3] for f in range(F)], panos, masks)
+    assert comp.kernel_plan() == 2 and b.mode == 1, "expected the persistent multi-frame launch"
+    for rep in range(2):
+        for t in pt:
+            t.zero_()
+        before = gpu.kernel_launch_count()
+        b.launch()
+        b.wait()
+        assert gpu.kernel_launch_count() - before == 1
+        for f in range(F):
+            assert np.array_equal(pt[f][:, :w].cpu().numpy(), refs[f % 3][0]), "replay %d frame %d" % (rep, f)
+            assert np.array_equal(mt[f][:, :w].cpu().numpy(), refs[f % 3][1])
+    b.close()
+
+
+def test_batch_counts_its_kernel_launches(gpu):
+    Ks, Rs, spec = rigs.cameras("mini_cyl")
+    n = spec["n_used"]
+    comp = gpu.Compositor((spec["W"], spec["H"]), Ks, Rs, warper="cylindrical", scale=spec["scale"], blender="feather")
+    comp.set_depth(2)
+    frames = [rigs.frame("mini_cyl", 0, i) for i in range(n)]
+    b = comp.batch([frames] * 4, [None] * 4)
+    before = gpu.kernel_launch_count()
+    b.launch(); b.launch()
+    b.wait()
+    assert gpu.kernel_launch_count() - before == 2 * 4          # one frame kernel per frame set and replay
+
+
+def test_output_views_must_be_writable_in_place(gpu):
+    """an output array with non-contiguous pixels used to be replaced by a temporary and never filled."""
+    Ks, Rs, spec = rigs.cameras("mini_cyl")
+    n = spec["n_used"]
+    comp = gpu.Compositor((spec["W"], spec["H"]), Ks, Rs, warper="cylindrical", scale=spec["scale"], blender="feather")
+    frames = [rigs.frame("mini_cyl", 0, i) for i in range(n)]
+    w, h = comp.pano_size
+    wide = np.zeros((h, w, 4), np.uint8)
+    with pytest.raises(gpu.StitchError):
+        comp.compose(frames, wide[:, :, :3])                     # pixel stride 4, 3 channels: cannot be written in place
+    good = np.zeros((h, 2 * w, 3), np.uint8)[:, :w]              # a column view with contiguous pixels is fine
+    pano, _ = comp.compose(frames)
+    comp.compose(frames, good)
+    assert np.array_equal(good, pano)

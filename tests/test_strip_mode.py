@@ -55,6 +55,26 @@ def test_strips_reassemble_the_panorama(gpu, world, weight_type):
 
 
 @pytest.mark.gpu
+def test_strips_written_into_views_of_one_panorama(gpu):
+    """strip results copied into column VIEWS of one full-size panorama buffer (pitch = the panorama's) must
+    only touch their own columns - a linear copy over such a view would overwrite the neighbouring strips."""
+    Ks, Rs, spec = rigs.cameras("mini")
+    size, n, world = (spec["W"], spec["H"]), spec["n_used"], 3
+    mk = lambda: gpu.Compositor(size, Ks, Rs, warper="spherical", scale=spec["scale"], blender="multiband", num_bands=5, gains=spec["gain_values"])
+    whole = mk()
+    frames = [rigs.frame("mini", 1, i) for i in range(n)]
+    pano, mask = whole.compose(frames)
+    got, gmask = np.full_like(pano, 77), np.full_like(mask, 77)
+    for r in reversed(range(world)):                      # last strip first: an overrun to the right would be seen
+        c = mk()
+        c.set_strip(r, world)
+        c.set_strip_halo(True)
+        c.strip_compose(frames)
+        c.strip_result(r, world, got, gmask)
+    assert np.array_equal(got, pano) and np.array_equal(gmask, mask)
+
+
+@pytest.mark.gpu
 def test_strips_full_size_c3(gpu):
     Ks, Rs, spec = rigs.cameras("c3")
     size, n = (spec["W"], spec["H"]), spec["n_used"]
