@@ -241,7 +241,28 @@ typedef struct sb_compositor_config {
      * exposure_compensate.cpp:203-221), resized to each warped image with INTER_LINEAR once, as apply() does
      * on every call (:225-246; the live app's BlockApply, APP64:310-331).  Fused paths only. */
     const sb_image *gain_maps;
+    /* ---- round-2 additions; all zero = off (a zero-initialised struct behaves as before) ---- */
+    /* CompressedRectilinear* / Panini* projector parameters (detail/warpers.hpp:300-420); 0, 0 means the default 1, 1 */
+    float    warper_a, warper_b;
+    /* Fisheye-undistort stage in front of the warp, the live app's first remap (APP64:201-238, 736-745):
+     * n pairs of host maps as initUndistortRectifyMap(..., CV_16SC2, map1, map2) makes them - undistort_map1[i] CV_16SC2,
+     * undistort_map2[i] CV_16UC1, both of the frame size.  Per frame and camera: remap(frame, INTER_LINEAR,
+     * BORDER_CONSTANT 0) with cv::remap's fixed-point arithmetic, THEN the warp of the 8-bit result - two roundings, exactly
+     * as the reference (a single composed map would not be bit-exact).  NULL = no stage. */
+    const sb_image *undistort_map1;
+    const sb_image *undistort_map2;
+    /* Crop margins of the live app's composite (APP64:47, 150-177, 702): the panorama handed back is
+     *   (width - crop_left - crop_right) x int(height * (1 - crop_up - crop_down)),
+     * its pixel (x, y) = composite(x + crop_left, y + yy), yy = int(rows / (1 - crop_up - crop_down) * crop_up) in float
+     * arithmetic as APP64:153.  Cropped-away tiles are never computed.  SB_BLEND_NO and SB_BLEND_FEATHER.
+     * crop_app_fill != 0 reproduces feedSizeRemap's unconditional gather (APP64:165-172, SB_BLEND_NO only): a pixel no camera
+     * covers takes camera 0's warped pixel (0, 0) - its look-up entries are all zero - instead of 0; the mask is unaffected. */
+    float    crop_up, crop_down;          /* fractions of the height */
+    int      crop_left, crop_right;       /* pixels */
+    int      crop_app_fill;
 } sb_compositor_config;
+/* At most SB_MAX_COMPOSITOR_CAMERAS cameras per compositor (and per calibration file). */
+#define SB_MAX_COMPOSITOR_CAMERAS 12
 
 int  sb_compositor_create(const sb_compositor_config *cfg, int device, sb_compositor **out);
 

@@ -38,6 +38,14 @@ def lib():
                                      C.POINTER(O.SoMat), C.POINTER(O.SoMat)]
         L.ref_warp.argtypes = [C.c_int, C.c_float, C.POINTER(O.SoMat), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                C.POINTER(C.c_int), C.POINTER(O.SoMat)]
+        L.ref_warp_backward.argtypes = [C.c_int, C.c_float, C.POINTER(O.SoMat), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.POINTER(O.SoMat)]
+        L.ref_plane_warp_roi_t.argtypes = [C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.ref_plane_warp_point_t.argtypes = [C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_plane_build_maps_t.argtypes = [C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int),
+                                             C.POINTER(O.SoMat), C.POINTER(O.SoMat)]
+        L.ref_plane_warp_t.argtypes = [C.c_float, C.POINTER(O.SoMat), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                       C.POINTER(C.c_int), C.POINTER(O.SoMat)]
         L.ref_gain_feed.argtypes = [C.c_int, C.c_void_p, C.POINTER(O.SoMat), C.POINTER(O.SoMat), C.c_void_p]
         L.ref_blocks_gain_feed.argtypes = [C.c_int, C.c_void_p, C.POINTER(O.SoMat), C.POINTER(O.SoMat), C.c_int, C.c_int,
                                            C.POINTER(O.SoMat), C.POINTER(O.SoMat)]

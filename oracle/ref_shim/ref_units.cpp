@@ -181,6 +181,61 @@ int ref_warp(int kind, float scale, const so_mat *src, const float K[9], const f
     } catch (const cv::Exception &e) { return e.code; }
 }
 
+// RotationWarperBase<P>::warpBackward (warpers_inl.hpp:102-128): dst is dst_h x dst_w of src's type
+int ref_warp_backward(int kind, float scale, const so_mat *src, const float K[9], const float R[9], int interp, int border, int dst_w, int dst_h, so_mat *dst)
+{
+    try {
+        Mat d;
+        make_warper(kind, scale)->warpBackward(wrap(src), mat3(K), mat3(R), interp, border, cv::Size(dst_w, dst_h), d);
+        return copy_out(d, dst);
+    } catch (const cv::Exception &e) { return e.code; }
+}
+// PlaneWarper's overloads with a translation T (warpers.cpp:81-137)
+static Mat mat31(const float *t)
+{
+    Mat r(3, 1, CV_32F);
+    for (int i = 0; i < 3; ++i) r.at<float>(i, 0) = t[i];
+    return r;
+}
+int ref_plane_warp_roi_t(float scale, int src_w, int src_h, const float K[9], const float R[9], const float T[3], int roi_xywh[4])
+{
+    try {
+        cv::detail::PlaneWarper w(scale);
+        cv::Rect r = w.warpRoi(cv::Size(src_w, src_h), mat3(K), mat3(R), mat31(T));
+        roi_xywh[0] = r.x; roi_xywh[1] = r.y; roi_xywh[2] = r.width; roi_xywh[3] = r.height;
+        return 0;
+    } catch (const cv::Exception &e) { return e.code; }
+}
+int ref_plane_warp_point_t(float scale, const float pt[2], const float K[9], const float R[9], const float T[3], float uv[2])
+{
+    try {
+        cv::detail::PlaneWarper w(scale);
+        cv::Point2f p = w.warpPoint(cv::Point2f(pt[0], pt[1]), mat3(K), mat3(R), mat31(T));
+        uv[0] = p.x; uv[1] = p.y;
+        return 0;
+    } catch (const cv::Exception &e) { return e.code; }
+}
+int ref_plane_build_maps_t(float scale, int src_w, int src_h, const float K[9], const float R[9], const float T[3], int roi_xywh[4], so_mat *xmap, so_mat *ymap)
+{
+    try {
+        cv::detail::PlaneWarper w(scale);
+        Mat xm, ym;
+        cv::Rect r = w.buildMaps(cv::Size(src_w, src_h), mat3(K), mat3(R), mat31(T), xm, ym);
+        roi_xywh[0] = r.x; roi_xywh[1] = r.y; roi_xywh[2] = r.width; roi_xywh[3] = r.height;
+        return copy_out(xm, xmap) | copy_out(ym, ymap);
+    } catch (const cv::Exception &e) { return e.code; }
+}
+int ref_plane_warp_t(float scale, const so_mat *src, const float K[9], const float R[9], const float T[3], int interp, int border, int tl[2], so_mat *dst)
+{
+    try {
+        cv::detail::PlaneWarper w(scale);
+        Mat d;
+        cv::Point p = w.warp(wrap(src), mat3(K), mat3(R), mat31(T), interp, border, d);
+        tl[0] = p.x; tl[1] = p.y;
+        return copy_out(d, dst);
+    } catch (const cv::Exception &e) { return e.code; }
+}
+
 // FeatherBlender::createWeightMaps (blenders.cpp:158-186); weight_maps[i]: CV_32FC1 of masks[i]'s size
 int ref_feather_create_weight_maps(int n, const so_mat *masks, const int *corners_xy, float sharpness, so_mat *weight_maps, int roi_xywh[4])
 {

@@ -62,7 +62,10 @@ class SbCompositorConfig(C.Structure):
                 ("K", C.POINTER(C.c_float)), ("R", C.POINTER(C.c_float)), ("blender_kind", C.c_int),
                 ("num_bands", C.c_int), ("weight_type", C.c_int), ("sharpness", C.c_float), ("comp_kind", C.c_int),
                 ("gains", C.POINTER(C.c_double)), ("seam_masks", C.POINTER(SbImage)), ("output_type", C.c_int),
-                ("gain_maps", C.POINTER(SbImage))]
+                ("gain_maps", C.POINTER(SbImage)),
+                ("warper_a", C.c_float), ("warper_b", C.c_float),
+                ("undistort_map1", C.POINTER(SbImage)), ("undistort_map2", C.POINTER(SbImage)),
+                ("crop_up", C.c_float), ("crop_down", C.c_float), ("crop_left", C.c_int), ("crop_right", C.c_int), ("crop_app_fill", C.c_int)]
 
 
 # every symbol include/stitchb200.h declares: name -> (restype, argtypes)
@@ -788,12 +791,23 @@ class Batch:
             pass
 
 
+_WARPER_KINDS = {"plane": WARP_PLANE, "cylindrical": WARP_CYLINDRICAL, "spherical": WARP_SPHERICAL, "fisheye": WARP_FISHEYE,
+                 "stereographic": WARP_STEREOGRAPHIC, "compressedRectilinear": WARP_COMPRESSED_RECTILINEAR,
+                 "compressedRectilinearPortrait": WARP_COMPRESSED_RECTILINEAR_PORTRAIT, "panini": WARP_PANINI, "paniniPortrait": WARP_PANINI_PORTRAIT,
+                 "mercator": WARP_MERCATOR, "transverseMercator": WARP_TRANSVERSE_MERCATOR, "sphericalPortrait": WARP_SPHERICAL_PORTRAIT,
+                 "cylindricalPortrait": WARP_CYLINDRICAL_PORTRAIT, "planePortrait": WARP_PLANE_PORTRAIT}
+
+
 class Compositor:
     """The per-frame loop of Stitcher::composePanorama (stitcher.cpp:221-313) with calibration fixed."""
 
     def __init__(self, src_size, Ks, Rs, warper="spherical", scale=None, blender="multiband", num_bands=5,
                  weight_type=CV_32F, sharpness=0.02, gains=None, seam_masks=None, output_type=CV_8UC3, device=0,
-                 gain_maps=None):
+                 gain_maps=None, warper_ab=None, undistort_maps=None, crop=None, crop_app_fill=False):
+        """warper: "plane" / "cylindrical" / "spherical" or any WARP_* kind (warper_ab = (a, b) for the compressed-rectilinear /
+        Panini projectors); undistort_maps: per camera the (map1 CV_16SC2, map2 CV_16UC1) pair of initUndistortRectifyMap
+        (the app's fisheye front end, APP64:201-238); crop = (up, down, left, right): the live app's crop margins
+        (fractions of the height, pixels; APP64:47, 150-177, 702), crop_app_fill its unconditional gather for uncovered pixels."""
         n = len(Ks)
         self.n = n
         self.device = device
@@ -803,8 +817,21 @@ class Compositor:
         cfg = SbCompositorConfig()
         cfg.n_cameras = n
         cfg.src_size = SbSize(*self.src_size)
-        cfg.warper_kind = {"plane": WARP_PLANE, "cylindrical": WARP_CYLINDRICAL, "spherical": WARP_SPHERICAL}.get(warper, warper)
+        cfg.warper_kind = _WARPER_KINDS.get(warper, warper)
         cfg.warper_scale = float(scale)
+        if warper_ab is not None:
+            cfg.warper_a, cfg.warper_b = float(warper_ab[0]), float(warper_ab[1])
+        ukeep = None
+        if undistort_maps is not None:
+            u1 = [np.ascontiguousarray(m[0], np.int16) for m in undistort_maps]
+            u2 = [np.ascontiguousarray(m[1], np.uint16) for m in undistort_maps]
+            a1 = (SbImage * n)(*[_image(m)[0] for m in u1])
+            a2 = (SbImage * n)(*[_image(m)[0] for m in u2])
+            cfg.undistort_map1, cfg.undistort_map2 = a1, a2
+            ukeep = (u1, u2, a1, a2)
+        if crop is not None:
+            cfg.crop_up, cfg.crop_down, cfg.crop_left, cfg.crop_right = float(crop[0]), float(crop[1]), int(crop[2]), int(crop[3])
+        cfg.crop_app_fill = int(bool(crop_app_fill))
         cfg.K = K.ctypes.data_as(_F9)
         cfg.R = R.ctypes.data_as(_F9)
         cfg.blender_kind = {"no": BLEND_NO, "feather": BLEND_FEATHER, "multiband": BLEND_MULTI_BAND}.get(blender, blender)
@@ -830,7 +857,7 @@ class Compositor:
             cfg.seam_masks = arr
         cfg.output_type = output_type
         self._cal = None
-        self._cfg, self._cfg_keep = C.pointer(cfg), (K, R, g, keep, gkeep, garr, arr)      # (the config points into these)
+        self._cfg, self._cfg_keep = C.pointer(cfg), (K, R, g, keep, gkeep, garr, arr, ukeep)      # (the config points into these)
         self._create(device)
 
     def _create(self, device):

@@ -15,13 +15,14 @@ struct sb_calibration {
     sb_compositor_config cfg{};
     std::vector<float> K, R;
     std::vector<double> gains;
-    std::vector<sb_image> seam_masks, gain_maps;
+    std::vector<sb_image> seam_masks, gain_maps, umap1, umap2;
     std::vector<std::vector<uint8_t>> blobs;        // pixel storage of the images above
 };
 
 namespace {
 
-const char kMagic[8] = {'S', 'B', 'C', 'A', 'L', '0', '0', '1'};
+const char kMagic[8] = {'S', 'B', 'C', 'A', 'L', '0', '0', '2'};       // 002: + projector a/b, undistort maps, crop margins
+const char kMagic1[8] = {'S', 'B', 'C', 'A', 'L', '0', '0', '1'};      // (round-1 files still load)
 
 struct Writer {
     std::vector<uint8_t> buf;
@@ -65,7 +66,7 @@ extern "C" {
 
 int sb_calibration_save(const sb_compositor_config *cfg, const char *path)
 {
-    SB_ASSERT(cfg && path && cfg->n_cameras > 0 && cfg->n_cameras <= 64 && cfg->K && cfg->R);
+    SB_ASSERT(cfg && path && cfg->n_cameras > 0 && cfg->n_cameras <= SB_MAX_COMPOSITOR_CAMERAS && cfg->K && cfg->R);
     const int n = cfg->n_cameras;
     Writer w;
     w.put(kMagic, 8);
@@ -84,6 +85,20 @@ int sb_calibration_save(const sb_compositor_config *cfg, const char *path)
     for (int i = 0; cfg->gain_maps && i < n; ++i) {
         SB_ASSERT(cfg->gain_maps[i].data && cfg->gain_maps[i].device < 0 && cfg->gain_maps[i].type == SB_32FC1);
         w.image(cfg->gain_maps[i]);
+    }
+    // format 002
+    w.pod(cfg->warper_a); w.pod(cfg->warper_b);
+    w.pod(cfg->crop_up); w.pod(cfg->crop_down);
+    const int32_t crop[3] = {cfg->crop_left, cfg->crop_right, cfg->crop_app_fill};
+    w.put(crop, sizeof crop);
+    SB_ASSERT((cfg->undistort_map1 != nullptr) == (cfg->undistort_map2 != nullptr));
+    const int32_t has_u = cfg->undistort_map1 ? 1 : 0;
+    w.pod(has_u);
+    for (int i = 0; has_u && i < n; ++i) {
+        SB_ASSERT(cfg->undistort_map1[i].data && cfg->undistort_map1[i].device < 0 && cfg->undistort_map1[i].type == SB_16SC2);
+        SB_ASSERT(cfg->undistort_map2[i].data && cfg->undistort_map2[i].device < 0 && cfg->undistort_map2[i].type == SB_16UC1);
+        w.image(cfg->undistort_map1[i]);
+        w.image(cfg->undistort_map2[i]);
     }
     w.pod(fnv1a(w.buf.data(), w.buf.size()));
     const std::string tmp = std::string(path) + ".tmp";      // write-then-rename: a crash never leaves a torn file behind
@@ -104,7 +119,8 @@ int sb_calibration_load(const char *path, sb_calibration **out)
     uint8_t chunk[65536];
     for (size_t k; (k = std::fread(chunk, 1, sizeof chunk, f)) > 0;) buf.insert(buf.end(), chunk, chunk + k);
     std::fclose(f);
-    if (buf.size() < 8 + 40 + 8 + 8 || std::memcmp(buf.data(), kMagic, 8) != 0) return fail(SB_ERR_BAD_ARG, "%s is not a calibration file", path);
+    const bool v2 = buf.size() >= 8 && std::memcmp(buf.data(), kMagic, 8) == 0, v1 = buf.size() >= 8 && std::memcmp(buf.data(), kMagic1, 8) == 0;
+    if (buf.size() < 8 + 40 + 8 + 8 || !(v1 || v2)) return fail(SB_ERR_BAD_ARG, "%s is not a calibration file", path);
     uint64_t sum;
     std::memcpy(&sum, buf.data() + buf.size() - 8, 8);
     if (sum != fnv1a(buf.data(), buf.size() - 8)) return fail(SB_ERR_BAD_ARG, "%s: checksum mismatch (truncated or corrupt)", path);
@@ -113,7 +129,7 @@ int sb_calibration_load(const char *path, sb_calibration **out)
     int32_t head[10];
     r.get(head, sizeof head);
     const int n = head[0];
-    if (!r.ok || n <= 0 || n > 64) return fail(SB_ERR_BAD_ARG, "%s: bad header", path);
+    if (!r.ok || n <= 0 || n > SB_MAX_COMPOSITOR_CAMERAS) return fail(SB_ERR_BAD_ARG, "%s: bad header", path);
     sb_compositor_config &g = c->cfg;
     g.n_cameras = n; g.src_size = sb_size{head[1], head[2]}; g.warper_kind = head[3]; g.blender_kind = head[4]; g.num_bands = head[5];
     g.weight_type = head[6]; g.comp_kind = head[7]; g.output_type = head[8];
@@ -122,11 +138,26 @@ int sb_calibration_load(const char *path, sb_calibration **out)
     r.get(c->K.data(), sizeof(float) * 9 * n); r.get(c->R.data(), sizeof(float) * 9 * n);
     int32_t has[3] = {0, 0, 0};
     r.get(has, sizeof has);
-    c->blobs.reserve(2 * (size_t)n);                          // (sb_image::data points into the blobs: no reallocation later)
+    c->blobs.reserve(4 * (size_t)n);                          // (sb_image::data points into the blobs: no reallocation later)
     if (has[0]) { c->gains.resize(n); r.get(c->gains.data(), sizeof(double) * n); }
     if (has[1]) { c->seam_masks.resize(n); for (int i = 0; i < n && r.ok; ++i) read_image(r, SB_8UC1, *c, &c->seam_masks[i]); }
     if (has[2]) { c->gain_maps.resize(n); for (int i = 0; i < n && r.ok; ++i) read_image(r, SB_32FC1, *c, &c->gain_maps[i]); }
+    int32_t has_u = 0;
+    if (v2) {
+        g.warper_a = r.pod<float>(); g.warper_b = r.pod<float>();
+        g.crop_up = r.pod<float>(); g.crop_down = r.pod<float>();
+        int32_t crop[3] = {0, 0, 0};
+        r.get(crop, sizeof crop);
+        g.crop_left = crop[0]; g.crop_right = crop[1]; g.crop_app_fill = crop[2];
+        has_u = r.pod<int32_t>();
+        if (has_u) {
+            c->umap1.resize(n); c->umap2.resize(n);
+            for (int i = 0; i < n && r.ok; ++i) { read_image(r, SB_16SC2, *c, &c->umap1[i]); read_image(r, SB_16UC1, *c, &c->umap2[i]); }
+        }
+    }
     if (!r.ok || r.p != r.end) return fail(SB_ERR_BAD_ARG, "%s: malformed body", path);
+    g.undistort_map1 = has_u ? c->umap1.data() : nullptr;
+    g.undistort_map2 = has_u ? c->umap2.data() : nullptr;
     g.K = c->K.data(); g.R = c->R.data();
     g.gains = has[0] ? c->gains.data() : nullptr;
     g.seam_masks = has[1] ? c->seam_masks.data() : nullptr;

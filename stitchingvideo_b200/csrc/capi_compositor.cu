@@ -48,6 +48,9 @@ struct Camera {
     DevBuf feather_tiles;        // the same table tile-major (one 8 KB block per 32x32 panorama tile) for the streaming kernel
     DevBuf feather_rec;          // per tile block: source box record
     int ftx0 = 0, fty0 = 0, fntx = 0, fnty = 0;
+    DevImage xmap, ymap;         // projectors evaluated on the host (kinds beyond plane / cylindrical / spherical): the float maps, kept for the table builders
+    DevImage umap1, umap2;       // fisheye-undistort stage: initUndistortRectifyMap's CV_16SC2 / CV_16UC1 pair (APP64:201-238)
+    int f2tx0 = 0, f2ty0 = 0, f2ntx = 0, f2nty = 0;   // k_fs2: the (cropped) output tiles this camera's warped rect touches
     DevBuf fs2_blocks;           // second-generation streaming kernel: tile-major 4-byte tap entries + weight-index plane
     // the source image as tensor maps (one per box width class), keyed on the frame buffer: video pipelines cycle through
     // a few input buffers, so after the first lap every frame is a cache hit
@@ -89,6 +92,7 @@ struct Slot {
     bool want_mask = true;                       // the caller asked for dst_mask (else it is never materialised)
     std::vector<DevImage> src;                   // staged source frames (host input)
     DevBuf src_all;                              // one staging block for a frame set that is contiguous in host memory
+    std::vector<DevImage> undist;                // fisheye-undistort stage: the undistorted frames (what the warp reads)
     std::vector<std::vector<DevImage>> gpyr;     // per camera Gaussian pyramid of the padded warped image
     DevImage warped;                             // feather / no-blend: one warped image at a time
     std::vector<std::vector<RawImage>> grgbx;    // fast path: per camera Gaussian pyramid as RGBX bytes
@@ -116,6 +120,11 @@ struct sb_compositor {
     bool feather_tma = false;                    // <= SB_FTT_MAXC cameras per 32x32 tile: persistent table-streaming kernel
     int feather_variant = 1;                     // 1: k_fs2 (else the next that applies), 3: k_feather_stream, 0: k_feather_fused_px1
     DevBuf tma_desc;                             // per 32x32 panorama tile: camera slots + source boxes, schedule order, ring plan
+    bool host_maps = false;                      // projector kind whose maps are built on the host (fused fast paths only)
+    bool undistort = false;                      // fisheye-undistort stage in front of the warp
+    sb_rect out_rect{};                          // what compose hands back, in dst_roi_final coordinates (crop margins; else all of it)
+    bool crop = false;
+    unsigned fill_tex[2] = {0, 0};               // crop_app_fill: camera 0's table entry of warped pixel (0, 0)
     Fs2Plan fs2;                                 // second-generation streaming kernel (kernels_fstream2.cu): usable when fs2.ok
     DevBuf fs2_desc;
     unsigned long long tmap_clock = 0;
@@ -189,13 +198,17 @@ int make_slot(sb_compositor *c, Slot &s)
         for (int l = 1; l <= levels; ++l) SB_TRY(s.rband[l].create(s.acc[l].v.rows, s.acc[l].v.cols, 8));
     }
     // packed rows: the device->host copy of the panorama into a contiguous host image is one linear DMA
-    SB_TRY(s.out.create(c->dst_roi_final.height, c->dst_roi_final.width, c->cfg.output_type));
+    SB_TRY(s.out.create(c->out_rect.height, c->out_rect.width, c->cfg.output_type));
     // (the frame kernels store 4 pixels per thread: 32-bit words of 8UC3, 64-bit words of 16SC3 - keep the rows so aligned)
-    if (((size_t)c->dst_roi_final.width * elem_size(c->cfg.output_type)) % (c->cfg.output_type == SB_8UC3 ? 4 : 8) == 0) {
-        s.out.v.step = (size_t)c->dst_roi_final.width * elem_size(c->cfg.output_type);
+    if (((size_t)c->out_rect.width * elem_size(c->cfg.output_type)) % (c->cfg.output_type == SB_8UC3 ? 4 : 8) == 0) {
+        s.out.v.step = (size_t)c->out_rect.width * elem_size(c->cfg.output_type);
     }
-    SB_TRY(s.out_mask.create(c->dst_roi_final.height, c->dst_roi_final.width, SB_8UC1));
-    if (c->dst_roi_final.width % 4 == 0) s.out_mask.v.step = (size_t)c->dst_roi_final.width;
+    SB_TRY(s.out_mask.create(c->out_rect.height, c->out_rect.width, SB_8UC1));
+    if (c->out_rect.width % 4 == 0) s.out_mask.v.step = (size_t)c->out_rect.width;
+    if (c->undistort) {
+        s.undist.resize(n);
+        for (int i = 0; i < n; ++i) SB_TRY(s.undist[i].create_packed(c->cfg.src_size.height, c->cfg.src_size.width, SB_8UC3));
+    }
     return SB_OK;
 }
 
@@ -327,6 +340,8 @@ int setup(sb_compositor *c)
     cudaStream_t s = c->setup_stream;
     const int n = cfg.n_cameras;
     c->cams.resize(n);
+    c->host_maps = cfg.warper_kind > SB_WARP_SPHERICAL;
+    c->undistort = cfg.undistort_map1 != nullptr;
     int tlx = INT32_MAX, tly = INT32_MAX, brx = INT32_MIN, bry = INT32_MIN;
     SB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
     SB_TRY(c->bilin_lut.ensure(1024 * sizeof(uint2)));
@@ -338,6 +353,7 @@ int setup(sb_compositor *c)
     for (int i = 0; i < n; ++i) {
         Camera &cam = c->cams[i];
         projector_set(cam.proj, cfg.warper_kind, cfg.warper_scale, cfg.K + 9 * i, cfg.R + 9 * i, zeroT);
+        cam.proj.a = cfg.warper_a != 0.f ? cfg.warper_a : 1.f; cam.proj.b = cfg.warper_b != 0.f ? cfg.warper_b : 1.f;
         sb_point br;
         projector_detect_result_roi(cam.proj, cfg.src_size.width, cfg.src_size.height, &cam.tl, &br);
         long long ww = (long long)br.x - cam.tl.x + 1, wh = (long long)br.y - cam.tl.y + 1;
@@ -357,17 +373,39 @@ int setup(sb_compositor *c)
         }
         tlx = std::min(tlx, cam.tl.x); tly = std::min(tly, cam.tl.y);
         brx = std::max(brx, cam.tl.x + cam.ww); bry = std::max(bry, cam.tl.y + cam.wh);
-        // separable trig tables
-        SB_TRY(cam.tables.ensure(sizeof(float) * 2 * (size_t)(cam.ww + cam.wh)));
-        float *t = static_cast<float *>(cam.tables.p);
-        SB_TRY(launch_build_warp_tables(cam.proj, cam.tl.x, cam.tl.y, cam.ww, cam.wh, t, t + cam.ww, t + 2 * cam.ww, t + 2 * cam.ww + cam.wh, s));
-        cam.wt.col_sin = t; cam.wt.col_cos = t + cam.ww; cam.wt.row_a = t + 2 * cam.ww; cam.wt.row_b = t + 2 * cam.ww + cam.wh;
         // warped mask: w->warp(mask, K, R, INTER_NEAREST, BORDER_CONSTANT) (stitcher.cpp:278-280)
-        SB_TRY(xmap.create(cam.wh, cam.ww, SB_32FC1));
-        SB_TRY(ymap.create(cam.wh, cam.ww, SB_32FC1));
-        SB_TRY(launch_build_maps(cam.proj, cam.tl.x, cam.tl.y, xmap.v, ymap.v, s));
         SB_TRY(cam.mask.create(cam.wh, cam.ww, SB_8UC1));
-        SB_TRY(launch_remap(ones.v, cam.mask.v, xmap.v, ymap.v, SB_INTER_NEAREST, SB_BORDER_CONSTANT, nullptr, s));
+        if (!c->host_maps) {
+            // separable trig tables
+            SB_TRY(cam.tables.ensure(sizeof(float) * 2 * (size_t)(cam.ww + cam.wh)));
+            float *t = static_cast<float *>(cam.tables.p);
+            SB_TRY(launch_build_warp_tables(cam.proj, cam.tl.x, cam.tl.y, cam.ww, cam.wh, t, t + cam.ww, t + 2 * cam.ww, t + 2 * cam.ww + cam.wh, s));
+            cam.wt.col_sin = t; cam.wt.col_cos = t + cam.ww; cam.wt.row_a = t + 2 * cam.ww; cam.wt.row_b = t + 2 * cam.ww + cam.wh;
+            SB_TRY(xmap.create(cam.wh, cam.ww, SB_32FC1));
+            SB_TRY(ymap.create(cam.wh, cam.ww, SB_32FC1));
+            SB_TRY(launch_build_maps(cam.proj, cam.tl.x, cam.tl.y, xmap.v, ymap.v, s));
+            SB_TRY(launch_remap(ones.v, cam.mask.v, xmap.v, ymap.v, SB_INTER_NEAREST, SB_BORDER_CONSTANT, nullptr, s));
+        } else {
+            // the libm-heavy projectors (warpers_inl.hpp:302-759): mapBackward on the host once per calibration, exactly as the
+            // reference evaluates it; the maps stay on the device for the table builders below, no frame ever sees the host
+            std::vector<float> hx((size_t)cam.ww * cam.wh), hy(hx.size());
+            projector_build_maps_host(cam.proj, cam.tl, br, hx.data(), hy.data());
+            SB_TRY(cam.xmap.create(cam.wh, cam.ww, SB_32FC1));
+            SB_TRY(cam.ymap.create(cam.wh, cam.ww, SB_32FC1));
+            SB_CUDA(cudaMemcpy2DAsync(cam.xmap.v.data, cam.xmap.v.step, hx.data(), (size_t)cam.ww * 4, (size_t)cam.ww * 4, (size_t)cam.wh, cudaMemcpyHostToDevice, s));
+            SB_CUDA(cudaMemcpy2DAsync(cam.ymap.v.data, cam.ymap.v.step, hy.data(), (size_t)cam.ww * 4, (size_t)cam.ww * 4, (size_t)cam.wh, cudaMemcpyHostToDevice, s));
+            SB_CUDA(cudaStreamSynchronize(s));
+            SB_TRY(launch_remap(ones.v, cam.mask.v, cam.xmap.v, cam.ymap.v, SB_INTER_NEAREST, SB_BORDER_CONSTANT, nullptr, s));
+        }
+        if (cfg.undistort_map1) {   // the app's fisheye front end (APP64:201-238): fixed-point maps of the frame size
+            const sb_image &m1 = cfg.undistort_map1[i], &m2 = cfg.undistort_map2[i];
+            SB_ASSERT(m1.type == SB_16SC2 && m2.type == SB_16UC1 && m1.data && m2.data && m1.rows == cfg.src_size.height && m1.cols == cfg.src_size.width &&
+                      m2.rows == m1.rows && m2.cols == m1.cols);
+            DImage v;
+            SB_TRY(to_device(m1, cam.umap1, s, &v));
+            SB_TRY(to_device(m2, cam.umap2, s, &v));
+            SB_CUDA(cudaStreamSynchronize(s));
+        }
         if (cfg.seam_masks) {   // mask_warped = seam_mask & mask_warped (stitcher.cpp:294)
             const sb_image &sm = cfg.seam_masks[i];
             SB_ASSERT(sm.type == SB_8UC1 && sm.rows == cam.wh && sm.cols == cam.ww && sm.data);
@@ -381,6 +419,17 @@ int setup(sb_compositor *c)
     // Blender::prepare(corners, sizes) -> resultRoi (util.cpp:127-140) -> prepare(Rect)
     sb_rect roi = {tlx, tly, brx - tlx, bry - tly};
     c->dst_roi_final = roi;
+    c->out_rect = sb_rect{0, 0, roi.width, roi.height};
+    c->crop = cfg.crop_up != 0.f || cfg.crop_down != 0.f || cfg.crop_left != 0 || cfg.crop_right != 0;
+    if (c->crop) {
+        // UpdateMat / feedSizeRemap (APP64:702, 153): float arithmetic exactly as written there, truncating conversions
+        const float keep = 1 - cfg.crop_up - cfg.crop_down;
+        const int out_w = (int)((float)roi.width - (float)cfg.crop_left - (float)cfg.crop_right), out_h = (int)((float)roi.height * keep);
+        const int yy = (int)((float)out_h / keep * cfg.crop_up);
+        if (out_w <= 0 || out_h <= 0 || yy + out_h > roi.height || cfg.crop_left + out_w > roi.width)
+            return fail(SB_ERR_BAD_ARG, "crop margins leave no panorama (%d x %d at %d, %d of %d x %d)", out_w, out_h, cfg.crop_left, yy, roi.width, roi.height);
+        c->out_rect = sb_rect{cfg.crop_left, yy, out_w, out_h};
+    }
     c->num_bands = 0;
     if (cfg.blender_kind == SB_BLEND_MULTI_BAND) {
         double max_len = static_cast<double>(std::max(roi.width, roi.height));
@@ -449,7 +498,8 @@ int setup(sb_compositor *c)
                 cam.mb_tstep = ((size_t)cam.rw * sizeof(uint2) + 255) & ~(size_t)255;
                 SB_TRY(cam.mb_table.ensure(cam.mb_tstep * cam.rh));
                 SB_TRY(launch_mb_tap_table(cam.proj, cam.tl.x, cam.tl.y, cam.ww, cam.wh, cam.left, cam.top, cfg.src_size.width,
-                                           cfg.src_size.height, static_cast<uint2 *>(cam.mb_table.p), cam.mb_tstep, cam.rw, cam.rh, s));
+                                           cfg.src_size.height, static_cast<uint2 *>(cam.mb_table.p), cam.mb_tstep, cam.rw, cam.rh, s,
+                                           c->host_maps ? &cam.xmap.v : nullptr, c->host_maps ? &cam.ymap.v : nullptr));
             }
             // streaming warp stage: tile-major taps + source boxes per camera, then the tile schedule for whole-frame launches
             {
@@ -499,7 +549,8 @@ int setup(sb_compositor *c)
             cam.feather_tstep = ((size_t)cam.ww * sizeof(uint2) + 255) & ~(size_t)255;
             SB_TRY(cam.feather_table.ensure(cam.feather_tstep * cam.wh));
             SB_TRY(launch_build_feather_table(cam.proj, cam.tl.x, cam.tl.y, cam.feather_w.v, cfg.src_size.width, cfg.src_size.height,
-                                              static_cast<uint2 *>(cam.feather_table.p), cam.feather_tstep, s));
+                                              static_cast<uint2 *>(cam.feather_table.p), cam.feather_tstep, s,
+                                              c->host_maps ? &cam.xmap.v : nullptr, c->host_maps ? &cam.ymap.v : nullptr));
             SB_TRY(launch_weight_from_dist(cam.feather_w.v, c->stream_sharpness, s));
             SB_TRY(launch_weight_accumulate(cam.feather_w.v, c->wsum[0].v, cam.tl.x - roi.x, cam.tl.y - roi.y, s));
             cam.spans.emplace_back();
@@ -547,16 +598,30 @@ int setup(sb_compositor *c)
             SB_CUDA(cudaMemcpyAsync(&h_status, status, sizeof h_status, cudaMemcpyDeviceToHost, s));
             SB_CUDA(cudaStreamSynchronize(s));
             c->feather_tma = h_status == 0 && n <= 16;
-            // ... and for its successor (4-byte entries, tensor-TMA source boxes)
+            // ... and for its successor (4-byte entries, tensor-TMA source boxes).  Its tiles cover what compose hands back:
+            // with crop margins (APP64:150-177) the cropped-away part of the composite is never scheduled.
             std::vector<Fs2CamSetup> fc(n);
+            const int otx = div_up(c->out_rect.width, FS2_W), oty = div_up(c->out_rect.height, FS2_H);
             for (int i = 0; i < n; ++i) {
                 Camera &cam = c->cams[i];
-                SB_TRY(cam.fs2_blocks.ensure((size_t)FS2_BLOCK_BYTES * cam.fntx * cam.fnty));
-                fc[i] = Fs2CamSetup{static_cast<const uint2 *>(cam.feather_table.p), cam.feather_tstep, cam.ww, cam.wh, cam.tl.x - roi.x, cam.tl.y - roi.y,
-                                    cam.ftx0, cam.fty0, cam.fntx, cam.fnty, static_cast<unsigned char *>(cam.fs2_blocks.p)};
+                const int dx = cam.tl.x - roi.x - c->out_rect.x, dy = cam.tl.y - roi.y - c->out_rect.y;
+                auto fdiv = [](int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); };
+                cam.f2tx0 = std::max(0, fdiv(dx, FS2_W)); cam.f2ty0 = std::max(0, fdiv(dy, FS2_H));
+                cam.f2ntx = std::max(0, std::min(otx, div_up(dx + cam.ww, FS2_W)) - cam.f2tx0);
+                cam.f2nty = std::max(0, std::min(oty, div_up(dy + cam.wh, FS2_H)) - cam.f2ty0);
+                if (cam.f2ntx == 0 || cam.f2nty == 0) cam.f2ntx = cam.f2nty = 0;
+                SB_TRY(cam.fs2_blocks.ensure((size_t)FS2_BLOCK_BYTES * std::max(1, cam.f2ntx * cam.f2nty)));
+                fc[i] = Fs2CamSetup{static_cast<const uint2 *>(cam.feather_table.p), cam.feather_tstep, cam.ww, cam.wh, dx, dy,
+                                    cam.f2tx0, cam.f2ty0, cam.f2ntx, cam.f2nty, static_cast<unsigned char *>(cam.fs2_blocks.p)};
                 cam.tmaps.clear();
             }
-            SB_TRY(fs2_build(fc.data(), n, roi.width, roi.height, c->stream_sharpness, c->sm_count, c->fs2_desc, &c->fs2, s));
+            SB_TRY(fs2_build(fc.data(), n, c->out_rect.width, c->out_rect.height, c->stream_sharpness, c->sm_count, c->fs2_desc, &c->fs2, s));
+            if (cfg.crop_app_fill) {   // camera 0's table entry of warped pixel (0, 0): what an uncovered pixel gathers (APP64:165-172)
+                uint2 e;
+                SB_CUDA(cudaMemcpyAsync(&e, c->cams[0].feather_table.p, sizeof e, cudaMemcpyDeviceToHost, s));
+                SB_CUDA(cudaStreamSynchronize(s));
+                c->fill_tex[0] = e.x; c->fill_tex[1] = e.y;
+            }
         }
         SB_CUDA(cudaStreamSynchronize(s));
     }
@@ -804,6 +869,7 @@ void fs2_static_args(sb_compositor *c, Fs2Args &a)
     a.sharpness = c->stream_sharpness;
     a.no_blend = c->cfg.blender_kind == SB_BLEND_NO;
     a.n_tiles = c->fs2.n_tiles; a.per_cta = c->fs2.per_cta; a.steady = c->fs2.steady ? 1 : 0;
+    a.fill_on = c->cfg.crop_app_fill ? 1 : 0; a.fill_tex[0] = c->fill_tex[0]; a.fill_tex[1] = c->fill_tex[1];
 }
 
 // the tensor maps of one camera's frame buffer (encoded on first sight, then cached)
@@ -840,6 +906,11 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
         aligned_src = src[i].step % 16 == 0 && src[i].step < (1ull << 24) && reinterpret_cast<uintptr_t>(src[i].data) % 16 == 0;
     const bool fs2_ok = c->fs2.ok && c->feather_variant == 1 && aligned_src;                       // the streaming frame kernel (feather / no blending)
     const bool stream_ok = fs2_ok || (c->feather_tma && (c->feather_variant == 1 || c->feather_variant == 3) && aligned_src);   // ... or its round-1 predecessor
+    if ((c->crop || cfg.crop_app_fill) && !fs2_ok)
+        return fail(SB_ERR_NOT_IMPL, "crop margins are applied by the streaming frame kernel only (16-byte aligned sources, default kernel variant)");
+    if (c->host_maps && !((cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused && c->mb_fast && c->mb_variant == 1) ||
+                          (cfg.blender_kind != SB_BLEND_MULTI_BAND && c->fused && c->feather_fast)))
+        return fail(SB_ERR_NOT_IMPL, "projectors beyond plane / cylindrical / spherical run on the fused fast paths only");
     if (blocks && !((cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused && c->mb_fast && c->mb_variant == 1) ||
                     (cfg.blender_kind == SB_BLEND_FEATHER && c->fused && c->feather_fast) ||
                     (cfg.blender_kind == SB_BLEND_NO && c->fused && c->feather_fast && stream_ok)))
@@ -916,6 +987,7 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
             a.out = s.out.v.data; a.out_step = (unsigned)s.out.v.step;
             a.out_mask = s.want_mask ? s.out_mask.v.ptr<uint8_t>() : nullptr; a.mask_step = (unsigned)s.out_mask.v.step;
             a.pw = s.out.v.cols; a.ph = s.out.v.rows;
+            a.src0 = src[0].ptr<uint8_t>(); a.sstep0 = (unsigned)src[0].step;
             PROF(a.no_blend ? "noblend_stream" : "feather_stream", fs2_bytes, launch_fs2(a, gain_on, s.out.v.type == SB_8UC3, c->fs2.grid, st));
         } else if (stream_ok) {
             FeatherTmaArgs a{};
@@ -1021,8 +1093,16 @@ int sb_compositor_create(const sb_compositor_config *cfg, int device, sb_composi
     *out = nullptr;
     SB_ASSERT(cfg && cfg->n_cameras > 0 && cfg->K && cfg->R);
     SB_ASSERT(cfg->src_size.width > 0 && cfg->src_size.height > 0);
-    if (cfg->warper_kind != SB_WARP_PLANE && cfg->warper_kind != SB_WARP_CYLINDRICAL && cfg->warper_kind != SB_WARP_SPHERICAL)
+    if (cfg->warper_kind < SB_WARP_PLANE || cfg->warper_kind > SB_WARP_PLANE_PORTRAIT)
         return fail(SB_ERR_BAD_ARG, "unsupported warper kind %d", cfg->warper_kind);
+    if ((cfg->undistort_map1 != nullptr) != (cfg->undistort_map2 != nullptr))
+        return fail(SB_ERR_BAD_ARG, "the undistort stage needs both maps of initUndistortRectifyMap (CV_16SC2 + CV_16UC1)");
+    const bool crop = cfg->crop_up != 0.f || cfg->crop_down != 0.f || cfg->crop_left != 0 || cfg->crop_right != 0;
+    if (crop || cfg->crop_app_fill) {
+        SB_ASSERT(cfg->crop_up >= 0.f && cfg->crop_down >= 0.f && cfg->crop_up + cfg->crop_down < 1.f && cfg->crop_left >= 0 && cfg->crop_right >= 0);
+        if (cfg->blender_kind == SB_BLEND_MULTI_BAND) return fail(SB_ERR_NOT_IMPL, "crop margins apply to the Blender::NO / FeatherBlender composite");
+        if (cfg->crop_app_fill && cfg->blender_kind != SB_BLEND_NO) return fail(SB_ERR_BAD_ARG, "crop_app_fill is the Blender::NO look-up composite's behaviour");
+    }
     if (cfg->blender_kind != SB_BLEND_NO && cfg->blender_kind != SB_BLEND_FEATHER && cfg->blender_kind != SB_BLEND_MULTI_BAND)
         return fail(SB_ERR_BAD_ARG, "unsupported blending method");
     if (cfg->comp_kind != SB_COMP_NO && cfg->comp_kind != SB_COMP_GAIN && cfg->comp_kind != SB_COMP_GAIN_BLOCKS)
@@ -1046,6 +1126,7 @@ int sb_compositor_create(const sb_compositor_config *cfg, int device, sb_composi
     }
     // the config's pointers are not retained
     c->cfg.K = c->cfg.R = nullptr; c->cfg.gains = nullptr; c->cfg.seam_masks = nullptr; c->cfg.gain_maps = nullptr;
+    c->cfg.undistort_map1 = c->cfg.undistort_map2 = nullptr;
     if (rc != SB_OK) { sb_compositor_destroy(c); return rc; }
     *out = c;
     return SB_OK;
@@ -1063,7 +1144,7 @@ void sb_compositor_destroy(sb_compositor *c)
 int sb_compositor_pano_size(const sb_compositor *c, sb_size *size)
 {
     SB_ASSERT(c && size);
-    size->width = c->dst_roi_final.width; size->height = c->dst_roi_final.height;
+    size->width = c->out_rect.width; size->height = c->out_rect.height;       // (the composite's ROI, less the crop margins)
     return SB_OK;
 }
 
@@ -1112,6 +1193,21 @@ int sb_compositor_set_depth(sb_compositor *c, int depth)
     return SB_OK;
 }
 
+// The live app's first remap (APP64:736-745): remap(frame, img3, mapEye1, mapEye2, INTER_LINEAR) - fixed-point maps, constant
+// zero border - per camera; the warp then reads the 8-bit result, as in the reference (two roundings).
+static int undistort_stage(sb_compositor *c, Slot &s, DImage *src)
+{
+    if (!c->undistort) return SB_OK;
+    cudaStream_t st = s.stream;
+    for (int i = 0; i < c->cfg.n_cameras; ++i) {
+        const Camera &cam = c->cams[i];
+        PROF("undistort", img_bytes(src[i]) + img_bytes(s.undist[i].v) + img_bytes(cam.umap1.v) + img_bytes(cam.umap2.v),
+             launch_remap(src[i], s.undist[i].v, cam.umap1.v, cam.umap2.v, SB_INTER_LINEAR, SB_BORDER_CONSTANT, nullptr, st));
+        src[i] = s.undist[i].v;
+    }
+    return SB_OK;
+}
+
 // One frame set on slot `s`: host->device staging of host sources, the frame kernels, the copy of the panorama (and mask)
 // into the caller's buffers - everything asynchronous on the slot's stream.
 static int enqueue_on_slot(sb_compositor *c, Slot &s, const sb_image *srcs, sb_image *pano, sb_image *pano_mask, bool timing)
@@ -1142,6 +1238,7 @@ static int enqueue_on_slot(sb_compositor *c, Slot &s, const sb_image *srcs, sb_i
         for (int i = 0; i < n; ++i) SB_TRY(to_device(srcs[i], s.src[i], s.stream, &srcp[i]));
     }
     s.want_mask = pano_mask != nullptr;
+    SB_TRY(undistort_stage(c, s, srcp));
     const std::vector<DImage> src(srcp, srcp + n);
     SB_TRY(run_frame(c, s, src));
     if (!pano->data) lend(s.out.v, c->device, pano);
@@ -1198,7 +1295,7 @@ static bool batch_can_persist(sb_compositor *c, int n_frames, const sb_image *sr
 {
     const sb_compositor_config &cfg = c->cfg;
     if (!(cfg.blender_kind == SB_BLEND_FEATHER || cfg.blender_kind == SB_BLEND_NO) || !c->fused || !c->feather_fast || !c->fs2.ok ||
-        c->feather_variant != 1 || !(c->stream_sharpness > 0.f) || cfg.n_cameras > FS2_TMAP_CAMS)
+        c->feather_variant != 1 || !(c->stream_sharpness > 0.f) || cfg.n_cameras > FS2_TMAP_CAMS || c->undistort)
         return false;
     const int n = cfg.n_cameras;
     const size_t px = (size_t)elem_size(cfg.output_type);
@@ -1209,7 +1306,7 @@ static bool batch_can_persist(sb_compositor *c, int n_frames, const sb_image *sr
         }
         const sb_image &p = panos[f];
         if (p.device != c->device || !p.data || p.step != panos[0].step || p.step % (cfg.output_type == SB_8UC3 ? 4 : 8) ||
-            reinterpret_cast<uintptr_t>(p.data) % 8 || p.rows != c->dst_roi_final.height || p.cols != c->dst_roi_final.width ||
+            reinterpret_cast<uintptr_t>(p.data) % 8 || p.rows != c->out_rect.height || p.cols != c->out_rect.width ||
             p.type != cfg.output_type || (unsigned long long)p.rows * p.step >= (1ull << 32) || p.step < p.cols * px)
             return false;
         if (masks) {
@@ -1257,6 +1354,7 @@ int sb_compositor_batch_create(sb_compositor *c, int n_frames, const sb_image *s
             }
             h[f].out = panos[f].data;
             h[f].out_mask = pano_masks ? static_cast<uint8_t *>(pano_masks[f].data) : nullptr;
+            h[f].src0 = static_cast<const uint8_t *>(srcs[(size_t)f * n].data); h[f].sstep0 = (unsigned)srcs[(size_t)f * n].step;
         }
         if (rc == SB_OK) rc = b->frames.ensure(sizeof(Fs2Frame) * (size_t)n_frames);
         if (rc == SB_OK) cuda_ok(cudaMemcpy(b->frames.p, h.data(), sizeof(Fs2Frame) * (size_t)n_frames, cudaMemcpyHostToDevice), "cudaMemcpy");
@@ -1267,7 +1365,7 @@ int sb_compositor_batch_create(sb_compositor *c, int n_frames, const sb_image *s
         b->args.mask_step = pano_masks ? (unsigned)pano_masks[0].step : 0u;
         b->args.out_mask = pano_masks ? static_cast<uint8_t *>(pano_masks[0].data) : nullptr;       // (non-null = masks wanted)
         b->args.out = panos[0].data;
-        b->args.pw = c->dst_roi_final.width; b->args.ph = c->dst_roi_final.height;
+        b->args.pw = c->out_rect.width; b->args.ph = c->out_rect.height;
         b->out8 = c->cfg.output_type == SB_8UC3;
         b->kernel_nodes = 1;
     } else {
@@ -1452,7 +1550,8 @@ int sb_compositor_profile_frame(sb_compositor *c, const sb_image *srcs, char *bu
     std::vector<ProfRec> recs;
     s.prof = &recs;
     s.want_mask = false;
-    int rc = run_frame(c, s, src);
+    int rc = undistort_stage(c, s, src.data());
+    if (rc == SB_OK) rc = run_frame(c, s, src);
     s.prof = nullptr;
     cudaError_t e = cudaStreamSynchronize(s.stream);
     std::string out = "[";
@@ -1591,6 +1690,7 @@ int sb_compositor_set_strip(sb_compositor *c, int rank, int world)
     SB_ASSERT(c && world >= 1 && rank >= 0 && rank < world);
     if (c->cfg.blender_kind != SB_BLEND_MULTI_BAND || !c->mb_fast)
         return fail(SB_ERR_NOT_IMPL, "strip mode is implemented for the multi-band fast path (MultiBandBlender, sources <= 4096 px)");
+    if (c->undistort) return fail(SB_ERR_NOT_IMPL, "strip mode does not run the undistort stage");
     const int m = 1 << c->num_bands;
     if (world > 1 && c->dst_roi.width / m / world < 2)
         return fail(SB_ERR_ASSERT, "panorama too narrow for %d strips: every strip needs at least 2 * 2^num_bands columns", world);

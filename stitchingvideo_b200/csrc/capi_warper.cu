@@ -6,6 +6,7 @@
 // (SURVEY.md §8a a1, a2); per-pixel work (a3, a4) is CUDA.
 #include <cfloat>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "sb_kernels.h"
@@ -23,6 +24,13 @@ struct sb_warper {
     // maps cached by the last build_maps (the app's xmap1/ymap1, APP64:188-198)
     DevImage xmap, ymap;
     bool have_maps = false;
+    // what those maps were built for: a repeated warp() / buildMaps with the same (size, K, R, scale, T, a, b) reuses them
+    // (warpers_inl.hpp:88-99 rebuilds every call; for the projectors evaluated on the host that is a per-pixel libm loop)
+    struct Key { int kind, w, h; float scale, t[3], a, b, K[9], R[9]; } key{};
+    sb_point key_tl{}, key_br{};
+    DevImage bxmap, bymap;       // warpBackward's forward maps, cached the same way
+    Key bkey{};
+    bool have_bmaps = false;
     // staging / outputs
     DevImage src_stage, dst_out;
 };
@@ -36,10 +44,22 @@ void set_params(const sb_warper *w, ProjParams &p, const float K[9], const float
     p.a = w->a; p.b = w->b;
 }
 
+sb_warper::Key make_key(const sb_warper *w, sb_size size, const float K[9], const float R[9])
+{
+    sb_warper::Key k;
+    std::memset(&k, 0, sizeof k);
+    k.kind = w->kind; k.w = size.width; k.h = size.height; k.scale = w->scale; k.a = w->a; k.b = w->b;
+    std::memcpy(k.t, w->t, sizeof k.t); std::memcpy(k.K, K, sizeof k.K); std::memcpy(k.R, R, sizeof k.R);
+    return k;
+}
+
 int build_maps_dev(sb_warper *w, sb_size src_size, const float K[9], const float R[9], sb_point *tl, sb_point *br)
 {
     SB_ASSERT(K && R);
     SB_ASSERT(src_size.width > 0 && src_size.height > 0);
+    const sb_warper::Key key = make_key(w, src_size, K, R);
+    if (w->have_maps && std::memcmp(&key, &w->key, sizeof key) == 0) { *tl = w->key_tl; *br = w->key_br; return SB_OK; }
+    w->have_maps = false;
     ProjParams p;
     set_params(w, p, K, R);
     projector_detect_result_roi(p, src_size.width, src_size.height, tl, br);
@@ -58,6 +78,7 @@ int build_maps_dev(sb_warper *w, sb_size src_size, const float K[9], const float
         SB_CUDA(cudaStreamSynchronize(w->stream));
     }
     w->have_maps = true;
+    w->key = key; w->key_tl = *tl; w->key_br = *br;
     return SB_OK;
 }
 
@@ -198,20 +219,26 @@ int sb_warper_warp_backward(sb_warper *w, const sb_image *src, const float K[9],
     sb_point tl, br;
     projector_detect_result_roi(p, dst_size.width, dst_size.height, &tl, &br);
     SB_ASSERT(br.x - tl.x + 1 == src->cols && br.y - tl.y + 1 == src->rows);
-    std::vector<float> hx((size_t)dst_size.width * dst_size.height), hy(hx.size());
-    for (int y = 0; y < dst_size.height; ++y)
-        for (int x = 0; x < dst_size.width; ++x) {
-            float u, v;
-            projector_map_forward(p, (float)x, (float)y, &u, &v);
-            hx[(size_t)y * dst_size.width + x] = u - tl.x;
-            hy[(size_t)y * dst_size.width + x] = v - tl.y;
-        }
-    DevImage dx, dy;
-    sb_image ix = {hx.data(), dst_size.height, dst_size.width, SB_32FC1, (size_t)dst_size.width * 4, -1};
-    sb_image iy = {hy.data(), dst_size.height, dst_size.width, SB_32FC1, (size_t)dst_size.width * 4, -1};
-    DImage vx, vy;
-    SB_TRY(to_device(ix, dx, w->stream, &vx));
-    SB_TRY(to_device(iy, dy, w->stream, &vy));
+    const sb_warper::Key key = make_key(w, dst_size, K, R);
+    if (!(w->have_bmaps && std::memcmp(&key, &w->bkey, sizeof key) == 0)) {
+        w->have_bmaps = false;
+        std::vector<float> hx((size_t)dst_size.width * dst_size.height), hy(hx.size());
+        for (int y = 0; y < dst_size.height; ++y)
+            for (int x = 0; x < dst_size.width; ++x) {
+                float u, v;
+                projector_map_forward(p, (float)x, (float)y, &u, &v);
+                hx[(size_t)y * dst_size.width + x] = u - tl.x;
+                hy[(size_t)y * dst_size.width + x] = v - tl.y;
+            }
+        sb_image ix = {hx.data(), dst_size.height, dst_size.width, SB_32FC1, (size_t)dst_size.width * 4, -1};
+        sb_image iy = {hy.data(), dst_size.height, dst_size.width, SB_32FC1, (size_t)dst_size.width * 4, -1};
+        DImage t;
+        SB_TRY(to_device(ix, w->bxmap, w->stream, &t));
+        SB_TRY(to_device(iy, w->bymap, w->stream, &t));
+        SB_CUDA(cudaStreamSynchronize(w->stream));           // (hx / hy go out of scope)
+        w->bkey = key; w->have_bmaps = true;
+    }
+    const DImage vx = w->bxmap.v, vy = w->bymap.v;
     int rc = remap_out(w, src, vx, vy, interp_mode, border_mode, dst);
     cudaStreamSynchronize(w->stream);
     return rc;

@@ -382,6 +382,27 @@ __device__ __forceinline__ unsigned fs2_apply_gain(unsigned v, float g)
     return (unsigned)min(max(__float2int_rn(__fmul_rn((float)v, g)), 0), 255);
 }
 
+// crop_app_fill: camera 0's warped pixel (0, 0), sampled from its frame in global memory (rare: only pixels no camera covers)
+template <bool GAIN>
+__device__ __noinline__ void fs2_fill_pixel(const Fs2Args &a, const uint8_t *src0, unsigned sstep0, unsigned &s0, unsigned &s1, unsigned &s2)
+{
+    const unsigned tex = a.fill_tex[0], fxy = a.fill_tex[1] & 1023u;
+    const unsigned x0 = tex & 0x1fffu, y0 = (tex >> 13) & 0x1fffu;
+    const uint8_t *g0 = src0 + (size_t)y0 * sstep0;
+    const uint8_t *g1 = (tex & (1u << 27)) ? g0 : g0 + sstep0;
+    const unsigned x1 = x0 + 1u - ((tex >> 26) & 1u);
+    unsigned lo0, hi0, lo1, hi1;
+    load_tap_row(g0, x0, x1, lo0, hi0);
+    load_tap_row(g1, x0, x1, lo1, hi1);
+    int v0, v1, v2;
+    bilinear_rgb(lo0, hi0, lo1, hi1, bilin_weights((int)(fxy & 31u), (int)(fxy >> 5)), v0, v1, v2);
+    if (GAIN) {
+        const float g = fs2_gain(a.cam[0], a.cam[0].dx, a.cam[0].dy);
+        v0 = (int)fs2_apply_gain((unsigned)v0, g); v1 = (int)fs2_apply_gain((unsigned)v1, g); v2 = (int)fs2_apply_gain((unsigned)v2, g);
+    }
+    s0 = (unsigned)v0 << 16; s1 = (unsigned)v1 << 16; s2 = (unsigned)v2 << 16;
+}
+
 // The 4 pixels x 3 channels of one thread, each value in byte B of its register (the byte above it zero), as the 12 (8UC3)
 // or 24 (16SC3) output bytes.  Full tiles: three 32-bit (64-bit) stores per thread; edge tiles: per pixel, guarded.
 // (Tried in round 2: staging the warp's 4 rows in shared memory so that consecutive lanes store consecutive words made the
@@ -543,11 +564,14 @@ k_fs2(const __grid_constant__ Fs2Args a)
     const int total = n_mine * max(a.n_frames, 1);
     unsigned char *out_f = reinterpret_cast<unsigned char *>(a.out);
     uint8_t *mask_f = a.out_mask;
+    const uint8_t *src0 = a.src0;
+    unsigned sstep0 = a.sstep0;
     int next_frame_at = a.frames ? 0 : total;               // tile number at which the next frame set's output pointers are due
     for (int seq = grp; seq < total; seq += FS2_GROUPS) {   // seq: tile number counted over the frames
         if (seq >= next_frame_at) {
             const Fs2Frame *fr = a.frames + seq / n_mine;
             out_f = reinterpret_cast<unsigned char *>(fr->out); mask_f = fr->out_mask;
+            src0 = fr->src0; sstep0 = fr->sstep0;
             next_frame_at = (seq / n_mine + 1) * n_mine;
         }
         const int stage = seq % FS2_STAGES;
@@ -619,7 +643,12 @@ k_fs2(const __grid_constant__ Fs2Args a)
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 v[p][0] = v[p][1] = v[p][2] = 0u;
-                if (sel[p] < 0) continue;
+                if (sel[p] < 0) {
+                    // feedSizeRemap gathers unconditionally (APP64:165-172): where no camera feeds the look-up tables are
+                    // zero, i.e. image 0, pixel (0, 0) of its warped, gain-compensated image
+                    if (a.fill_on) fs2_fill_pixel<GAIN>(a, src0, sstep0, v[p][0], v[p][1], v[p][2]);
+                    continue;
+                }
                 const uint4 rec = sm.desc[stage][1 + sel[p]];
                 const uint32_t e = *reinterpret_cast<const uint32_t *>(smb + rec.x + tab_off + 4u * p);
                 fs2_pixel<32768>(smb, rec.x + (uint32_t)FS2_BLOCK_BYTES, rec.y, e, v[p][0], v[p][1], v[p][2]);

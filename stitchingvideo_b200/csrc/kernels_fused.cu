@@ -57,14 +57,18 @@ int launch_build_bilin_lut(uint2 *lut, cudaStream_t s)
 // coordinate rounds into the image (sx in [-1, sw-1], sy in [-1, sh-1]): there x1 is x0 or x0 + 1.
 // Pixels whose taps are folded any other way are given distance 0 only if the mask is 0 there, so the
 // kernel asserts nothing: entries with dist == 0 are skipped, exactly (short(p * 0) == 0, w += 0).
+// KIND < 0: the projector's maps were built on the host (the libm-heavy projectors of warpers_inl.hpp:302-759) and are read
+// from xm / ym instead of being recomputed
 template <int KIND>
 __global__ void __launch_bounds__(256)
-k_build_feather_table(ProjParams p, int tl_x, int tl_y, const float *dist, size_t dstep, int w, int h, int sw, int sh, uint2 *table, size_t tstep)
+k_build_feather_table(ProjParams p, int tl_x, int tl_y, const float *dist, size_t dstep, int w, int h, int sw, int sh, uint2 *table, size_t tstep,
+                      const float *xm, const float *ym, size_t mstep)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
     float mx, my;
-    map_backward<KIND>(p, (float)(tl_x + x), (float)(tl_y + y), mx, my);
+    if (KIND < 0) { mx = crow<float>(xm, mstep, y)[x]; my = crow<float>(ym, mstep, y)[x]; }
+    else map_backward<(KIND < 0 ? 0 : KIND)>(p, (float)(tl_x + x), (float)(tl_y + y), mx, my);
     const int fsx = cvround(__fmul_rn(mx, 32.f)), fsy = cvround(__fmul_rn(my, 32.f));
     const int sx = sat_s16(fsx >> 5), sy = sat_s16(fsy >> 5);
     const float d = crow<float>(dist, dstep, y)[x];
@@ -80,17 +84,22 @@ k_build_feather_table(ProjParams p, int tl_x, int tl_y, const float *dist, size_
     reinterpret_cast<uint2 *>(reinterpret_cast<char *>(table) + (size_t)y * tstep)[x] = t;
 }
 
-int launch_build_feather_table(const ProjParams &p, int tl_x, int tl_y, const DImage &dist, int sw, int sh, uint2 *table, size_t tstep, cudaStream_t s)
+int launch_build_feather_table(const ProjParams &p, int tl_x, int tl_y, const DImage &dist, int sw, int sh, uint2 *table, size_t tstep, cudaStream_t s,
+                               const DImage *xmap, const DImage *ymap)
 {
     SB_ASSERT(dist.type == SB_32FC1);
     SB_ASSERT(sw <= 8192 && sh <= 8192);
     dim3 block(32, 8), grid(div_up(dist.cols, 32), div_up(dist.rows, 8));
-#define SB_FT(K) k_build_feather_table<K><<<grid, block, 0, s>>>(p, tl_x, tl_y, dist.ptr<float>(), dist.step, dist.cols, dist.rows, sw, sh, table, tstep)
-    switch (p.kind) {
+    const float *xm = xmap ? xmap->ptr<float>() : nullptr, *ym = ymap ? ymap->ptr<float>() : nullptr;
+    const size_t mstep = xmap ? xmap->step : 0;
+    if (xmap) SB_ASSERT(ymap && xmap->type == SB_32FC1 && ymap->type == SB_32FC1 && xmap->rows == dist.rows && xmap->cols == dist.cols && ymap->step == xmap->step);
+#define SB_FT(K) k_build_feather_table<K><<<grid, block, 0, s>>>(p, tl_x, tl_y, dist.ptr<float>(), dist.step, dist.cols, dist.rows, sw, sh, table, tstep, xm, ym, mstep)
+    if (xmap) SB_FT(-1);
+    else switch (p.kind) {
     case SB_WARP_PLANE: SB_FT(SB_WARP_PLANE); break;
     case SB_WARP_CYLINDRICAL: SB_FT(SB_WARP_CYLINDRICAL); break;
     case SB_WARP_SPHERICAL: SB_FT(SB_WARP_SPHERICAL); break;
-    default: return fail(SB_ERR_BAD_ARG, "unsupported projector kind %d", p.kind);
+    default: return fail(SB_ERR_BAD_ARG, "projector kind %d needs host-built maps", p.kind);
     }
 #undef SB_FT
     SB_LAUNCHED();

@@ -40,16 +40,18 @@ template <typename T> __device__ __forceinline__ T *rowp(void *base, size_t step
 
 // ------------------------------------------------------------------------------------ setup: tap table
 // entry.x = x0 | x1 << 12 | fx << 24      entry.y = y0 | y1 << 12 | fy << 24   (source size <= 4096)
-template <int KIND>
+template <int KIND>      // KIND < 0: the warped image's maps come from xm / ym (projectors evaluated on the host)
 __global__ void __launch_bounds__(256)
-k_mb_tap_table(ProjParams p, int tl_x, int tl_y, int ww, int wh, int left, int top, int sw, int sh, uint2 *table, size_t tstep, int rw, int rh)
+k_mb_tap_table(ProjParams p, int tl_x, int tl_y, int ww, int wh, int left, int top, int sw, int sh, uint2 *table, size_t tstep, int rw, int rh,
+               const float *xm, const float *ym, size_t mstep)
 {
     const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
     if (px >= rw || py >= rh) return;
     // copyMakeBorder(BORDER_REFLECT) of the warped image (blenders.cpp:272-274)
     const int wx = border_interp<BORDER_REFLECT>(px - left, ww), wy = border_interp<BORDER_REFLECT>(py - top, wh);
     float mx, my;
-    map_backward<KIND>(p, (float)(tl_x + wx), (float)(tl_y + wy), mx, my);
+    if (KIND < 0) { mx = rowp<float>(xm, mstep, wy)[wx]; my = rowp<float>(ym, mstep, wy)[wx]; }
+    else map_backward<(KIND < 0 ? 0 : KIND)>(p, (float)(tl_x + wx), (float)(tl_y + wy), mx, my);
     const int fsx = cvround(__fmul_rn(mx, 32.f)), fsy = cvround(__fmul_rn(my, 32.f));
     const int sx = sat_s16(fsx >> 5), sy = sat_s16(fsy >> 5);
     const unsigned x0 = border_interp<BORDER_REFLECT>(sx, sw), x1 = border_interp<BORDER_REFLECT>(sx + 1, sw);
@@ -61,12 +63,16 @@ k_mb_tap_table(ProjParams p, int tl_x, int tl_y, int ww, int wh, int left, int t
 }
 
 int launch_mb_tap_table(const ProjParams &p, int tl_x, int tl_y, int ww, int wh, int left, int top, int sw, int sh,
-                        uint2 *table, size_t tstep, int rw, int rh, cudaStream_t s)
+                        uint2 *table, size_t tstep, int rw, int rh, cudaStream_t s, const DImage *xmap, const DImage *ymap)
 {
     SB_ASSERT(sw <= 4096 && sh <= 4096);
     dim3 block(32, 8), grid(div_up(rw, 32), div_up(rh, 8));
-#define SB_TT(K) k_mb_tap_table<K><<<grid, block, 0, s>>>(p, tl_x, tl_y, ww, wh, left, top, sw, sh, table, tstep, rw, rh)
-    switch (p.kind) {
+    const float *xm = xmap ? xmap->ptr<float>() : nullptr, *ym = ymap ? ymap->ptr<float>() : nullptr;
+    const size_t mstep = xmap ? xmap->step : 0;
+    if (xmap) SB_ASSERT(ymap && xmap->rows == wh && xmap->cols == ww && ymap->step == xmap->step);
+#define SB_TT(K) k_mb_tap_table<K><<<grid, block, 0, s>>>(p, tl_x, tl_y, ww, wh, left, top, sw, sh, table, tstep, rw, rh, xm, ym, mstep)
+    if (xmap) SB_TT(-1);
+    else switch (p.kind) {
     case SB_WARP_PLANE: SB_TT(SB_WARP_PLANE); break;
     case SB_WARP_CYLINDRICAL: SB_TT(SB_WARP_CYLINDRICAL); break;
     case SB_WARP_SPHERICAL: SB_TT(SB_WARP_SPHERICAL); break;

@@ -74,6 +74,8 @@ struct alignas(128) Fs2Frame {
     CUtensorMap tmap[FS2_TMAP_CAMS * FS2_NCLS];
     void *out;
     uint8_t *out_mask;
+    const uint8_t *src0;           // camera 0's frame (crop_app_fill)
+    unsigned sstep0;
 };
 struct alignas(64) Fs2Args {
     CUtensorMap tmap[FS2_TMAP_CAMS * FS2_NCLS];     // source image of camera i as a 2-D byte tensor, box = cls_w[c] x FS2_ROWS
@@ -91,6 +93,10 @@ struct alignas(64) Fs2Args {
     const Fs2Frame *frames;        // multi-frame launch: n_frames frame sets (tmap / out / out_mask above are then unused)
     int n_frames;                  // 0 or 1: the single frame set described by this block
     int steady;                    // Fs2Plan::steady
+    int fill_on;                   // Blender::NO with crop_app_fill: an uncovered pixel takes camera 0's warped pixel (0, 0) (APP64:165-172)
+    unsigned fill_tex[2];          // ... whose row-major table entry (sb_fused.h: FeatherCam) this is
+    const uint8_t *src0;           // ... sampled from camera 0's frame
+    unsigned sstep0;
     int debug;                     // tuning experiments (SB_FS2_DEBUG): 1 = supply side only (no pixel work)
     unsigned long long *trace;     // null, or (SB_FS2_TRACE=file) per CTA and tile {issued, wait, landed, done} timestamps
 };

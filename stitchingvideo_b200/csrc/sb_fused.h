@@ -4,7 +4,7 @@
 
 namespace sb {
 
-constexpr int SB_MAX_CAMERAS = 12;
+constexpr int SB_MAX_CAMERAS = SB_MAX_COMPOSITOR_CAMERAS;
 
 // Per-camera, per-warped-pixel table of the feather path (sequence-constant, 8 bytes/pixel): the
 // resolved taps of cv::remap's fixed-point map entry (A1) and the L1 distance createWeightMap turns
@@ -144,7 +144,9 @@ int launch_build_bilin_lut(uint2 *lut, cudaStream_t s);
 int launch_feather_tile_cams(const FeatherCam &c, int cam_index, int pw, int ph, uint32_t *tile_cams, unsigned *bad, cudaStream_t s);
 int launch_feather_fused(const FeatherFusedArgs &a, bool apply_gain, bool out8, cudaStream_t s);
 // setup: resolved-tap + distance table of one camera (dist: CV_32FC1 output of distanceTransform)
-int launch_build_feather_table(const ProjParams &p, int tl_x, int tl_y, const DImage &dist, int sw, int sh, uint2 *table, size_t tstep, cudaStream_t s);
+// (xmap / ymap: the warped image's float maps for the projectors whose mapBackward is evaluated on the host; null: recomputed)
+int launch_build_feather_table(const ProjParams &p, int tl_x, int tl_y, const DImage &dist, int sw, int sh, uint2 *table, size_t tstep, cudaStream_t s,
+                               const DImage *xmap = nullptr, const DImage *ymap = nullptr);
 // device self-test of SharedDiv against __fdiv_rn; returns the number of mismatching quotients
 int selftest_division(unsigned long long n, unsigned seed, unsigned long long *mismatches);
 int launch_band_fused(const BandFusedArgs &a, bool float_weights, bool not_top, bool final_band, bool out8, cudaStream_t s);

@@ -114,7 +114,7 @@ int launch_mbs_descriptors(const MbsSetup &a, const unsigned *list_dev, int n_ti
 int launch_mb_warp_stream(const MbStreamArgs &a, bool apply_gain, int sm_count, cudaStream_t s);
 
 int launch_mb_tap_table(const ProjParams &p, int tl_x, int tl_y, int ww, int wh, int left, int top, int sw, int sh,
-                        uint2 *table, size_t tstep, int rw, int rh, cudaStream_t s);
+                        uint2 *table, size_t tstep, int rw, int rh, cudaStream_t s, const DImage *xmap = nullptr, const DImage *ymap = nullptr);
 int launch_mb_tile_mask(const MbBandGeom &g, bool float_weights, int lw, int lh, const void *wsum, size_t wsum_step, uint32_t *mask, cudaStream_t s);
 int launch_mb_warp(const MbWarpArgs &a, bool apply_gain, int max_rw, int max_rh, cudaStream_t s);
 int launch_mb_pyr_down(const MbPyrArgs &a, int max_dw, int max_dh, cudaStream_t s);
