@@ -110,6 +110,54 @@ class Warper:
         return (tl[0], tl[1]), dst
 
 
+    def warp_backward(self, src, K, R, dst_size, interp=O.INTER_LINEAR, border=O.BORDER_REFLECT):
+        """RotationWarperBase<P>::warpBackward (warpers_inl.hpp:102-128) -> dst of dst_size (w, h)."""
+        self._ab()
+        src = np.ascontiguousarray(src)
+        K, R = _f9(K), _f9(R)
+        dst = np.empty((dst_size[1], dst_size[0]) + src.shape[2:], np.uint8)
+        ms, md = O.mat(src), O.mat(dst)
+        _chk(lib().ref_warp_backward(self.kind, self.scale, C.byref(ms), K.ctypes.data, R.ctypes.data, interp, border,
+                                     dst_size[0], dst_size[1], C.byref(md)), "warpBackward")
+        return dst
+
+
+class PlaneWarperT:
+    """detail::PlaneWarper's overloads with a translation T (warpers.cpp:81-137) through the reference's own code."""
+
+    def __init__(self, scale, T):
+        self.scale, self.T = float(scale), np.ascontiguousarray(T, np.float32).reshape(3)
+
+    def warp_roi(self, src_size, K, R):
+        K, R, roi = _f9(K), _f9(R), (C.c_int * 4)()
+        _chk(lib().ref_plane_warp_roi_t(self.scale, src_size[0], src_size[1], K.ctypes.data, R.ctypes.data, self.T.ctypes.data, roi), "warpRoi(T)")
+        return tuple(roi)
+
+    def warp_point(self, pt, K, R):
+        K, R = _f9(K), _f9(R)
+        p, uv = np.asarray(pt, np.float32), np.zeros(2, np.float32)
+        _chk(lib().ref_plane_warp_point_t(self.scale, p.ctypes.data, K.ctypes.data, R.ctypes.data, self.T.ctypes.data, uv.ctypes.data), "warpPoint(T)")
+        return float(uv[0]), float(uv[1])
+
+    def build_maps(self, src_size, K, R):
+        x, y, w, h = self.warp_roi(src_size, K, R)
+        K, R, roi = _f9(K), _f9(R), (C.c_int * 4)()
+        xmap, ymap = np.empty((h, w), np.float32), np.empty((h, w), np.float32)
+        mx, my = O.mat(xmap), O.mat(ymap)
+        _chk(lib().ref_plane_build_maps_t(self.scale, src_size[0], src_size[1], K.ctypes.data, R.ctypes.data, self.T.ctypes.data, roi,
+                                          C.byref(mx), C.byref(my)), "buildMaps(T)")
+        return tuple(roi), xmap, ymap
+
+    def warp(self, src, K, R, interp=O.INTER_LINEAR, border=O.BORDER_REFLECT):
+        src = np.ascontiguousarray(src)
+        x, y, w, h = self.warp_roi((src.shape[1], src.shape[0]), K, R)
+        K, R, tl = _f9(K), _f9(R), (C.c_int * 2)()
+        dst = np.empty((h, w) + src.shape[2:], np.uint8)
+        ms, md = O.mat(src), O.mat(dst)
+        _chk(lib().ref_plane_warp_t(self.scale, C.byref(ms), K.ctypes.data, R.ctypes.data, self.T.ctypes.data, interp, border, tl, C.byref(md)), "warp(T)")
+        return (tl[0], tl[1]), dst
+
+
 class Blender:
     """detail::Blender / FeatherBlender / MultiBandBlender: the reference's blenders.cpp itself."""
 

@@ -861,7 +861,7 @@ void fs2_static_args(sb_compositor *c, Fs2Args &a)
         Fs2Cam &fc = a.cam[i];
         fc.blocks = static_cast<const unsigned char *>(cam.fs2_blocks.p);
         fc.gain = cam.gain;
-        fc.dx = cam.tl.x - c->dst_roi.x; fc.dy = cam.tl.y - c->dst_roi.y;
+        fc.dx = cam.tl.x - c->dst_roi.x - c->out_rect.x; fc.dy = cam.tl.y - c->dst_roi.y - c->out_rect.y;      // (in the coordinates of what compose hands back)
         if (c->cfg.comp_kind == SB_COMP_GAIN_BLOCKS) { fc.gmap = cam.gain_full.v.ptr<float>(); fc.gmstep = (unsigned)cam.gain_full.v.step; }
     }
     a.desc = static_cast<const uint4 *>(c->fs2_desc.p);
