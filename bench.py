@@ -34,8 +34,8 @@ WORKLOADS = {
     "c2": "C2: 5-camera 1080p 360deg, CylindricalWarper + FeatherBlender(0.02), fixed calibration (BASELINE.json configs[1])",
     "c3": "C3: 5-camera 1080p 360deg, SphericalWarper + GainCompensator + MultiBandBlender(5 bands, CV_32F weights) (configs[2])",
     "c4": "C4: 8-camera 4K VR, SphericalWarper + GainCompensator + MultiBandBlender(5 bands) (configs[3])",
-    "app6": "APP6: the live app's own per-frame case (BASELINE.md 1): 6-camera 1920x1088, cached-map cylindrical remap + composite "
-            "without blending or gain (Blender::NO), panorama ~8040x1088",
+    "app6": "APP6: the live app's own per-frame case (BASELINE.md 1; APP64:748-759): 6-camera 1920x1088, cached-map cylindrical remap + BlockApply "
+            "(block gain maps) + look-up composite without blending, cropped by the app's margins (0.1 / 0.1 / 10 / 10), panorama ~8020x883",
 }
 # the only per-frame figure the reference publishes (REL32/resultTime-at.txt, mean 43.6 ms per frame set,
 # hardware unknown): frames/s for exactly the APP6 workload
@@ -155,8 +155,15 @@ def measure(workload, args, rank, world, local, barrier, max_over_ranks, sampler
 
     Ks, Rs, spec = rigs.cameras(workload)
     n, size = spec["n_used"], (spec["W"], spec["H"])
+    kw = {}
+    if spec.get("block_gains"):          # the live app's BlockApply (APP64:310-331): block gain maps sized from the warped images
+        probe = sv.Compositor(size, Ks, Rs, warper=spec["warper"], scale=spec["scale"], blender=spec["blender"], device=local)
+        kw["gain_maps"] = rigs.block_gain_maps(workload, [probe.camera_roi(i)[2:] for i in range(n)])
+        del probe
+    if spec.get("crop"):
+        kw["crop"], kw["crop_app_fill"] = spec["crop"], spec.get("crop_app_fill", False)
     comp = sv.Compositor(size, Ks, Rs, warper=spec["warper"], scale=spec["scale"], blender=spec["blender"], num_bands=5,
-                         weight_type=sv.CV_32F, sharpness=0.02, gains=spec["gain_values"], output_type=sv.CV_8UC3, device=local)
+                         weight_type=sv.CV_32F, sharpness=0.02, gains=spec["gain_values"], output_type=sv.CV_8UC3, device=local, **kw)
     if args.variant is not None:
         comp.set_fused(10 + args.variant)      # kernel variant of the fused path (tuning hook)
     pw, ph = comp.pano_size
@@ -394,6 +401,11 @@ def _oracle_frame(cal, spec, workload, idx):
     from stitchingvideo_b200 import rigs
     from oracle import pipeline as P
     frames = [rigs.frame(workload, idx, i, smooth=0) for i in range(spec["n_used"])]
+    if spec.get("crop"):                 # the live app's loop: warp + BlockApply + feedSizeRemap (APP64:748-759)
+        gm = rigs.block_gain_maps(workload, cal.sizes) if spec.get("block_gains") else None
+        t = time.perf_counter()
+        P.compose_app(cal, frames, gain_maps=gm, crop=spec["crop"], fill=spec.get("crop_app_fill", False))
+        return time.perf_counter() - t
     t = time.perf_counter()
     P.compose(cal, frames, blender=spec["blender"], num_bands=5, gains=spec["gain_values"], use_ref=_have_ref())
     return time.perf_counter() - t

@@ -17,7 +17,10 @@ RIGS = {
     "c5": dict(n=8, W=3840, H=2160, f=2900.0, warper="spherical", scale=16384.0 / (2.0 * math.pi), blender="multiband", gains=True),
     # the live app's published per-frame case: 6 x 1920x1088, cached-map
     # cylindrical remap + composite without blending or gain, panorama ~8040 x 1105 (2 pi f = 8040 -> f = 1280)
-    "app6": dict(n=6, W=1920, H=1088, f=1280.0, warper="cylindrical", scale=1280.0, blender="no", gains=False),
+    # Round 2: as the app runs it (APP64:748-759) - BlockApply with per-camera block gain maps, the composite cropped by the
+    # app's margins (upblack = downblack = 0.1, leftblack = rightblack = 10, APP64:47) with feedSizeRemap's unconditional gather
+    "app6": dict(n=6, W=1920, H=1088, f=1280.0, warper="cylindrical", scale=1280.0, blender="no", gains=False,
+                 block_gains=True, crop=(0.1, 0.1, 10, 10), crop_app_fill=True),
     # small rigs for fast parity tests (same construction, scaled down)
     "mini": dict(n=5, W=240, H=136, f=131.0, warper="spherical", scale=131.0, blender="multiband", gains=True),
     "mini_cyl": dict(n=5, W=240, H=136, f=131.0, warper="cylindrical", scale=131.0, blender="feather", gains=False),
@@ -49,6 +52,12 @@ def cameras(name):
     spec["n_used"] = len(idx)
     spec["gain_values"] = [GAINS[i % len(GAINS)] for i in range(len(idx))] if spec["gains"] else None
     return Ks, Rs, spec
+
+
+def block_gain_maps(name, warped_sizes):
+    """Deterministic BlocksGainCompensator::gain_maps_ for a rig (32x32 blocks of each warped image, gains in 0.85..1.15)."""
+    rng = np.random.default_rng(7)
+    return [rng.uniform(0.85, 1.15, ((h + 31) // 32, (w + 31) // 32)).astype(np.float32) for (w, h) in warped_sizes]
 
 
 def _blur121(a, passes):

@@ -126,3 +126,27 @@ def test_full_size_no_blend_matches_oracle(gpu):
         pano, mask = comp.compose(frames)
         same(pano, ref, "no-blend panorama (variant %d)" % fused)
         same(mask, rmask, "no-blend mask (variant %d)" % fused)
+
+
+def test_app6_as_the_app_runs_it(gpu):
+    """BASELINE.md §1's case at full size: 6 x 1920x1088, cylindrical cached-map remap + BlockApply + the look-up composite
+    cropped by the app's margins with its unconditional gather (APP64:47, 150-177, 310-331, 748-759) - one launch, bit-exact."""
+    Ks, Rs, spec = rigs.cameras("app6")
+    size, n = (spec["W"], spec["H"]), spec["n_used"]
+    cal = P.Calibration(size, Ks, Rs, "cylindrical", spec["scale"])
+    gm = rigs.block_gain_maps("app6", cal.sizes)
+    comp = gpu.Compositor(size, Ks, Rs, warper="cylindrical", scale=spec["scale"], blender="no", gain_maps=gm, crop=spec["crop"],
+                          crop_app_fill=True)
+    assert comp.kernel_plan() == 2
+    frames = [rigs.frame("app6", 2, i, smooth=1) for i in range(n)]
+    ref, rmask = P.compose_app(cal, frames, gain_maps=gm, crop=spec["crop"], fill=True)
+    before = gpu.kernel_launch_count()
+    pano, mask = comp.compose(frames)
+    assert gpu.kernel_launch_count() - before == 1
+    same(pano, ref, "app6 composite")
+    w, h = comp.pano_size
+    from oracle import oracle as O
+    roi = O.result_roi(cal.corners, cal.sizes)
+    ow, oh, xx, yy = P.crop_geometry(roi[2], roi[3], *spec["crop"])
+    assert (w, h) == (ow, oh)
+    same(mask, rmask[yy:yy + oh, xx:xx + ow], "app6 mask")
