@@ -92,6 +92,8 @@ struct Slot {
     bool want_mask = true;                       // the caller asked for dst_mask (else it is never materialised)
     std::vector<DevImage> src;                   // staged source frames (host input)
     DevBuf src_all;                              // one staging block for a frame set that is contiguous in host memory
+    DevBuf mb_sync;                              // k_mb_coarse: this slot's work / stage counters (only ever grow)
+    std::vector<unsigned long long> mb_totals;   // ... and their running totals on the host
     std::vector<DevImage> undist;                // fisheye-undistort stage: the undistorted frames (what the warp reads)
     std::vector<std::vector<DevImage>> gpyr;     // per camera Gaussian pyramid of the padded warped image
     DevImage warped;                             // feather / no-blend: one warped image at a time
@@ -833,12 +835,59 @@ int mb_band_head(sb_compositor *c, Slot &s, int l_hi, int l_lo, const int *lo, c
     return SB_OK;
 }
 
+// Gaussian levels l0 -> ... -> nb and bands nb ... l_lo in ONE launch (k_mb_coarse): with the warp stage, the level-0
+// pyrDown and the final band a multi-band frame is 4 launches instead of 12
+int mb_coarse(sb_compositor *c, Slot &s, int l0, int l_lo, const int *g_lo, const int *g_hi, const int *b_lo, const int *b_hi)
+{
+    cudaStream_t st = s.stream;
+    const int nb = c->num_bands;
+    MbCoarseArgs a{};
+    double bytes = 0;
+    for (int l = l0; l < nb; ++l) {
+        const int k = a.down.n_levels;
+        int tx[SB_MAX_CAMERAS], t[SB_MAX_CAMERAS], mw, mh;
+        if (!fill_down(c, s, l, g_lo[l + 1], g_hi[l + 1], a.down.level[k], tx, t, mw, mh, bytes)) continue;
+        int first = 0;
+        for (int i = 0; i < c->cfg.n_cameras; ++i) { a.down.first_item[k][i] = first; a.down.tiles_x[k][i] = std::max(1, tx[i]); first += t[i]; }
+        if (first == 0) continue;
+        a.down.items[k] = first;
+        ++a.down.n_levels;
+    }
+    a.band.top_is_top = 1;
+    for (int l = nb; l >= l_lo; --l) {
+        const int k = a.band.n_levels;
+        if (!fill_band(c, s, l, b_lo[l], b_hi[l], a.band.level[k], bytes)) {
+            if (k == 0) a.band.top_is_top = 0;
+            continue;
+        }
+        a.band.tiles_x[k] = div_up(a.band.level[k].g.lw, 64);
+        a.band.items[k] = a.band.tiles_x[k] * div_up(a.band.level[k].g.lh, 16);
+        ++a.band.n_levels;
+    }
+    if (a.down.n_levels + a.band.n_levels == 0) return SB_OK;
+    if (!s.mb_sync.p) {
+        SB_TRY(s.mb_sync.ensure(sizeof(unsigned long long) * (2 + 2 * SB_MB_MAX_FUSED_LEVELS)));
+        SB_CUDA(cudaMemsetAsync(s.mb_sync.p, 0, sizeof(unsigned long long) * (2 + 2 * SB_MB_MAX_FUSED_LEVELS), st));
+        s.mb_totals.assign(2 + 2 * SB_MB_MAX_FUSED_LEVELS, 0ull);
+    }
+    a.sync = static_cast<unsigned long long *>(s.mb_sync.p);
+    PROF("mb_coarse", bytes, launch_mb_coarse(a, s.mb_totals.data(), c->cfg.weight_type == SB_32F, c->sm_count, c->slots.size() == 1, st));
+    return SB_OK;
+}
+
 // the whole multi-band fast path for the column ranges g_lo/g_hi (Gaussian levels) and b_lo/b_hi (bands)
 int mb_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src, const int *g_lo, const int *g_hi, const int *b_lo, const int *b_hi)
 {
     const int nb = c->num_bands;
     SB_TRY(mb_warp_stage(c, s, src, g_lo[0], g_hi[0]));
-    const bool multilevel = c->mb_multilevel < 0 ? c->slots.size() == 1 : c->mb_multilevel != 0;
+    if (c->mb_multilevel < 0 && nb >= 2 && nb <= SB_MB_MAX_FUSED_LEVELS && c->strip_world == 1) {
+        // default: warp, pyrDown 0 -> 1, every coarser level and every band but the last in one launch, the final band
+        SB_TRY(mb_down_stage(c, s, 0, g_lo[1], g_hi[1]));
+        SB_TRY(mb_coarse(c, s, 1, 1, g_lo, g_hi, b_lo, b_hi));
+        SB_TRY(mb_band_stage(c, s, 0, b_lo[0], b_hi[0]));
+        return SB_OK;
+    }
+    const bool multilevel = c->mb_multilevel > 0;
     if (multilevel && nb >= 3 && nb <= SB_MB_MAX_FUSED_LEVELS) {
         SB_TRY(mb_down_stage(c, s, 0, g_lo[1], g_hi[1]));
         SB_TRY(mb_down_tail(c, s, 1, nb, g_lo, g_hi));
@@ -1340,7 +1389,9 @@ int sb_compositor_batch_create(sb_compositor *c, int n_frames, const sb_image *s
         if (e != cudaSuccess && rc == SB_OK) rc = fail(SB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
         return e == cudaSuccess;
     };
-    static const bool want_graph = getenv("SB_BATCH_GRAPH") != nullptr && atoi(getenv("SB_BATCH_GRAPH")) != 0;
+    // (a recorded graph would replay k_mb_coarse with the counter values of the recording: multi-band laps are never graphs)
+    static const bool graph_env = getenv("SB_BATCH_GRAPH") != nullptr && atoi(getenv("SB_BATCH_GRAPH")) != 0;
+    const bool want_graph = graph_env && c->cfg.blender_kind != SB_BLEND_MULTI_BAND;
     if (!want_graph && batch_can_persist(c, n_frames, srcs, panos, pano_masks)) {
         // ---- one launch for the whole lap
         b->mode = sb_batch::PERSISTENT;

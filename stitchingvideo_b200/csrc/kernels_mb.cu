@@ -15,6 +15,7 @@
 // a few 32-byte sectors; per-tile camera bitmasks keep the per-pixel camera loop to the 1-3 cameras
 // that matter; all of a pixel's independent loads are issued before the first is consumed.
 #include <algorithm>
+#include <cstdlib>
 #include <climits>
 
 #include <cooperative_groups.h>
@@ -523,6 +524,95 @@ int launch_mb_band_head(const MbBandHeadArgs &a, bool float_weights, int sm_coun
     void *params[] = {const_cast<MbBandHeadArgs *>(&a)};
     if (float_weights) SB_CUDA(cudaLaunchCooperativeKernel((const void *)k_mb_band_head<float>, grid, block, params, 0, s));
     else SB_CUDA(cudaLaunchCooperativeKernel((const void *)k_mb_band_head<short>, grid, block, params, 0, s));
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
+// ------------------------------------------------------------------------------------ all the coarse levels, one launch
+// Gaussian levels l0 -> ... -> top, then bands top ... l_lo, as ONE ordinary (non-cooperative) launch.  The stages depend on
+// each other only through global memory; instead of a grid-wide barrier (which needs the whole grid co-resident and so
+// serialises frames that are in flight on other streams) the CTAs draw work items from one counter IN STAGE ORDER and an
+// item of stage s waits until every item of stage s - 1 has been counted done.  Whoever waits holds a later item than all
+// the items it waits for, and those have been drawn by CTAs that are running: progress never depends on co-residency.
+// The counters only ever grow (64-bit, one set per in-flight slot; the host keeps their running totals): a launch owns the
+// item numbers [base, base + total) of its slot's work counter, nothing is reset between frames.
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename WT> __global__ void __launch_bounds__(256) k_mb_coarse(const __grid_constant__ MbCoarseArgs a)
+{
+    __shared__ unsigned long long s_item;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n_down = a.down.n_levels, n_stage = n_down + a.band.n_levels;
+    const unsigned long long base = a.base;
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(a.sync, 1ull) - base;
+        __syncthreads();
+        const unsigned long long item_g = s_item;
+        if (item_g >= (unsigned long long)a.total) break;
+        int st = 0;
+        while (st + 1 < n_stage && item_g >= (unsigned long long)a.first[st + 1]) ++st;
+        const int item = (int)item_g - a.first[st];
+        if (st > 0) {                                        // every item of the stage before must be done
+            if (threadIdx.x == 0) {
+                const unsigned long long want = a.want[st - 1];
+                while (ld_acquire_u64(a.sync + 1 + (st - 1)) < want) __nanosleep(64);
+            }
+            __syncthreads();
+        }
+        if (st < n_down) {
+            const MbPyrArgs &L = a.down.level[st];
+            int i = 0;
+            while (i + 1 < L.n && item >= a.down.first_item[st][i + 1]) ++i;
+            const int local = item - a.down.first_item[st][i], bx = local % a.down.tiles_x[st][i], by = local / a.down.tiles_x[st][i];
+            mb_pyr_down_thread(L.cam[i], bx * 32 + tx, by * 8 + ty);
+        } else {
+            const int lv = st - n_down;
+            const MbBandArgs &L = a.band.level[lv];
+            const int bx = item % a.band.tiles_x[lv], by = item / a.band.tiles_x[lv];
+            const int X0 = (bx * 32 + tx) * 2, Y0 = (by * 8 + ty) * 2;
+            if (lv == 0 && a.band.top_is_top) mb_band_thread<WT, false, false, false>(L, X0, Y0);
+            else mb_band_thread<WT, true, false, false>(L, X0, Y0);
+        }
+        __threadfence();                                     // this CTA's results before its count
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(a.sync + 1 + st, 1ull);
+    }
+}
+
+// totals: the slot's running counter values (work counter, then one per stage), advanced here for the next launch
+int launch_mb_coarse(MbCoarseArgs &a, unsigned long long *totals, bool float_weights, int sm_count, bool alone, cudaStream_t s)
+{
+    const int n_down = a.down.n_levels, n_stage = n_down + a.band.n_levels;
+    if (n_stage == 0) return SB_OK;
+    SB_ASSERT(n_stage <= 2 * SB_MB_MAX_FUSED_LEVELS && a.sync);
+    int total = 0, most = 0;
+    for (int st = 0; st < n_stage; ++st) {
+        const int items = st < n_down ? a.down.items[st] : a.band.items[st - n_down];
+        SB_ASSERT(items > 0);                                // (an empty stage would never be counted done)
+        a.first[st] = total;
+        total += items;
+        most = std::max(most, items);
+    }
+    a.first[n_stage] = total;
+    a.total = total;
+    // a frame alone on the GPU wants the stages over as fast as possible (4 CTAs per SM: C3 217 us per frame against 276);
+    // with frames in flight on other streams one CTA per SM leaves the SMs to their big kernels (136 us per frame against 179)
+    static const int forced = getenv("SB_MB_COARSE_CTAS") ? atoi(getenv("SB_MB_COARSE_CTAS")) : 0;      // tuning hook
+    const int per_sm = forced > 0 ? forced : alone ? 4 : 1;
+    dim3 grid(std::min(most, per_sm * sm_count)), block(256);
+    a.base = totals[0];
+    totals[0] += (unsigned long long)total + grid.x;        // (every CTA draws once past the end)
+    for (int st = 0; st < n_stage; ++st) {
+        totals[1 + st] += (unsigned long long)(a.first[st + 1] - a.first[st]);
+        a.want[st] = totals[1 + st];
+    }
+    if (float_weights) k_mb_coarse<float><<<grid, block, 0, s>>>(a);
+    else k_mb_coarse<short><<<grid, block, 0, s>>>(a);
     SB_LAUNCHED();
     return SB_OK;
 }

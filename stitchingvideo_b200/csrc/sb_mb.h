@@ -82,6 +82,17 @@ struct MbBandHeadArgs {
     int items[SB_MB_MAX_FUSED_LEVELS];
     int tiles_x[SB_MB_MAX_FUSED_LEVELS];
 };
+// every coarse level in ONE ordinary launch: stages drawn from a work counter in order, stage s waits for stage s - 1's count
+struct MbCoarseArgs {
+    MbPyrTailArgs down;                                    // Gaussian levels l0 -> ... (n_levels may be 0)
+    MbBandHeadArgs band;                                   // then the bands, coarsest first
+    int first[2 * SB_MB_MAX_FUSED_LEVELS + 1];             // first work item of each stage (filled by the launcher)
+    int total;
+    unsigned long long *sync;                              // per slot: [0] work counter, [1 + s] items of stage s done; only ever grow
+    unsigned long long base;                               // value of the work counter when this launch starts
+    unsigned long long want[2 * SB_MB_MAX_FUSED_LEVELS];   // value of stage s's counter when all its items of this launch are done
+};
+int launch_mb_coarse(MbCoarseArgs &a, unsigned long long *totals, bool float_weights, int sm_count, bool alone, cudaStream_t s);
 int launch_mb_pyr_tail(const MbPyrTailArgs &a, int sm_count, cudaStream_t s);
 int launch_mb_band_head(const MbBandHeadArgs &a, bool float_weights, int sm_count, cudaStream_t s);
 
