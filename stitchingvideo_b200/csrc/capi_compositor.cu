@@ -97,6 +97,7 @@ struct Slot {
     std::vector<DevImage> undist;                // fisheye-undistort stage: the undistorted frames (what the warp reads)
     std::vector<std::vector<DevImage>> gpyr;     // per camera Gaussian pyramid of the padded warped image
     DevImage warped;                             // feather / no-blend: one warped image at a time
+    DevImage warped_pad;                         // staged multi-band with block gains: the padded 8UC3 image before convertTo(16S)
     std::vector<std::vector<RawImage>> grgbx;    // fast path: per camera Gaussian pyramid as RGBX bytes
     std::vector<RawImage> rband;                 // fast path: restored bands 1..n as short4 pixels
     std::vector<DevImage> acc;                   // dst_pyr_laplace_ (level 0 = dst_)
@@ -730,12 +731,12 @@ int mb_down_stage(sb_compositor *c, Slot &s, int l, int ox0, int ox1)
 {
     // K2: Gaussian level l -> l+1 for every camera, one launch
     cudaStream_t st = s.stream;
-    MbPyrArgs a;
+    MbPyrListArgs a;
     int tx[SB_MAX_CAMERAS], t[SB_MAX_CAMERAS], mw, mh;
     double bytes = 0;
-    if (!fill_down(c, s, l, ox0, ox1, a, tx, t, mw, mh, bytes)) return SB_OK;
+    if (!fill_down(c, s, l, ox0, ox1, a.p, tx, t, mw, mh, bytes)) return SB_OK;
     static const char *const names[] = {"mb_pyr_down_L0", "mb_pyr_down_L1", "mb_pyr_down_L2", "mb_pyr_down_L3", "mb_pyr_down_L4", "mb_pyr_down_L5+"};
-    PROF(names[std::min(l, 5)], bytes, launch_mb_pyr_down(a, mw, mh, st));
+    PROF(names[std::min(l, 5)], bytes, launch_mb_pyr_down_list(a, st));
     return SB_OK;
 }
 
@@ -941,6 +942,25 @@ int fs2_tmaps(sb_compositor *c, int i, const DImage &src, CUtensorMap *out)
     return SB_OK;
 }
 
+// Staged (reference-shaped) warp of camera i with BlocksGainCompensator::apply (exposure_compensate.cpp:225-246): warp to 8UC3,
+// multiply by the resized gain map with uchar saturation, then - multi-band - copyMakeBorder(BORDER_REFLECT) and
+// convertTo(CV_16S) into the padded feed rect `dst16` (blenders.cpp:272-274).  dst16 == nullptr: the 8UC3 result stays in s.warped.
+int staged_warp_blocks(sb_compositor *c, Slot &s, int i, const DImage &src, const DImage *dst16)
+{
+    const Camera &cam = c->cams[i];
+    cudaStream_t st = s.stream;
+    SB_TRY(s.warped.create(cam.wh, cam.ww, SB_8UC3));
+    PROF("warp_fused", img_bytes(src) + img_bytes(s.warped.v),
+         launch_warp_fused(cam.proj, cam.wt, src, cam.ww, cam.wh, 0, 0, 1.f, false, s.warped.v, st));
+    PROF("gain_blocks", img_bytes(s.warped.v) * 2 + img_bytes(cam.gain_full.v), launch_mul_map_8u(s.warped.v, cam.gain_full.v, st));
+    if (!dst16) return SB_OK;
+    SB_TRY(s.warped_pad.create(dst16->rows, dst16->cols, SB_8UC3));
+    PROF("copy_make_border", img_bytes(s.warped.v) + img_bytes(s.warped_pad.v),
+         launch_copy_make_border(s.warped.v, s.warped_pad.v, cam.top, cam.left, SB_BORDER_REFLECT, st));
+    PROF("convert_16s", img_bytes(s.warped_pad.v) * 3, launch_convert(s.warped_pad.v, *dst16, st));
+    return SB_OK;
+}
+
 int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
 {
     const sb_compositor_config &cfg = c->cfg;
@@ -960,10 +980,6 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
     if (c->host_maps && !((cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused && c->mb_fast && c->mb_variant == 1) ||
                           (cfg.blender_kind != SB_BLEND_MULTI_BAND && c->fused && c->feather_fast)))
         return fail(SB_ERR_NOT_IMPL, "projectors beyond plane / cylindrical / spherical run on the fused fast paths only");
-    if (blocks && !((cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused && c->mb_fast && c->mb_variant == 1) ||
-                    (cfg.blender_kind == SB_BLEND_FEATHER && c->fused && c->feather_fast) ||
-                    (cfg.blender_kind == SB_BLEND_NO && c->fused && c->feather_fast && stream_ok)))
-        return fail(SB_ERR_NOT_IMPL, "block gain maps are applied by the fused fast paths only");
     // Blender::prepare zeroes the accumulators (blenders.cpp:71-78, 227-232): only the unfused
     // (camera-by-camera) path has accumulators in HBM; the weight sums are resident either way
     if (cfg.blender_kind == SB_BLEND_MULTI_BAND && c->fused && c->mb_fast && c->mb_variant == 1) {
@@ -976,6 +992,8 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
         for (int i = 0; i < n; ++i) {
             const Camera &cam = c->cams[i];
             auto &g = s.gpyr[i];
+            if (blocks) SB_TRY(staged_warp_blocks(c, s, i, src[i], &g[0].v));
+            else
             PROF("warp_fused", img_bytes(src[i]) + img_bytes(g[0].v),
                  launch_warp_fused(cam.proj, cam.wt, src[i], cam.ww, cam.wh, cam.left, cam.top, cam.gain, gain_on, g[0].v, st));
             for (int l = 0; l < nb; ++l)
@@ -1087,6 +1105,8 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
             auto &g = s.gpyr[i];
             // warp + gain + convertTo(16S) + copyMakeBorder(REFLECT) -> Gaussian level 0
             // source is gathered (each pixel read ~once), output written once
+            if (blocks) SB_TRY(staged_warp_blocks(c, s, i, src[i], &g[0].v));
+            else
             PROF("warp_fused", img_bytes(src[i]) + img_bytes(g[0].v),
                  launch_warp_fused(cam.proj, cam.wt, src[i], cam.ww, cam.wh, cam.left, cam.top, cam.gain, gain_on, g[0].v, st));
             for (int l = 0; l < nb; ++l)
@@ -1110,9 +1130,12 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
         if (cfg.blender_kind == SB_BLEND_NO) PROF("zero_fill", img_bytes(s.acc_mask.v), launch_set_zero(s.acc_mask.v, st));
         for (int i = 0; i < n; ++i) {
             const Camera &cam = c->cams[i];
+            if (blocks) SB_TRY(staged_warp_blocks(c, s, i, src[i], nullptr));
+            else {
             SB_TRY(s.warped.create(cam.wh, cam.ww, SB_8UC3));
             PROF("warp_fused", img_bytes(src[i]) + img_bytes(s.warped.v),
                  launch_warp_fused(cam.proj, cam.wt, src[i], cam.ww, cam.wh, 0, 0, cam.gain, gain_on, s.warped.v, st));
+            }
             const int dx = cam.tl.x - c->dst_roi.x, dy = cam.tl.y - c->dst_roi.y;
             if (cfg.blender_kind == SB_BLEND_FEATHER)
                 PROF("feather_accumulate", img_bytes(s.warped.v) * (1 + 4.0 / 3 + 2 * 2), 

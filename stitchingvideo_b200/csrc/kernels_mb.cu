@@ -230,6 +230,44 @@ __global__ void __launch_bounds__(256) k_mb_pyr_down(const __grid_constant__ MbP
     mb_pyr_down_thread(a.cam[blockIdx.z], blockIdx.x * 32 + threadIdx.x, blockIdx.y * 8 + threadIdx.y);
 }
 
+// The same over a compacted tile list: only the 64-column tiles that intersect a camera's wanted output runs are launched.
+// (One camera of a ring straddles the panorama seam: its rect is panorama-wide but only both ends are wanted, and the
+// other cameras are a quarter as wide - a rectangular grid sized for the widest camera had 73 % of its warps exit at once.)
+__global__ void __launch_bounds__(256) k_mb_pyr_down_list(const __grid_constant__ MbPyrListArgs a)
+{
+    int k = 0;
+    while (k + 1 < a.n_seg && (int)blockIdx.x >= a.seg[k + 1].first) ++k;
+    const MbPyrSeg sg = a.seg[k];
+    const int local = (int)blockIdx.x - sg.first, bx = local % sg.ntx, by = local / sg.ntx;
+    mb_pyr_down_thread(a.p.cam[sg.cam], (sg.tx0 + bx) * 32 + (int)(threadIdx.x & 31), by * 8 + (int)(threadIdx.x >> 5));
+}
+
+int launch_mb_pyr_down_list(MbPyrListArgs &a, cudaStream_t s)
+{
+    a.n_seg = 0;
+    int total = 0;
+    for (int i = 0; i < a.p.n; ++i) {
+        const MbPyrCam &c = a.p.cam[i];
+        const int dw = (c.sw + 1) >> 1, dh = (c.sh + 1) >> 1;
+        const int rows = div_up(div_up(dh, 2), 8);
+        int t0[2], t1[2], nr = 0;
+        for (int r = 0; r < 2; ++r) {
+            const int lo = std::max(0, c.ox[2 * r]), hi = std::min(dw, c.ox[2 * r + 1]);
+            if (hi <= lo) continue;
+            t0[nr] = lo / 64; t1[nr] = div_up(hi, 64); ++nr;
+        }
+        if (nr == 2 && t0[1] <= t1[0]) { t1[0] = std::max(t1[0], t1[1]); nr = 1; }      // (runs are ascending)
+        for (int r = 0; r < nr; ++r) {
+            a.seg[a.n_seg++] = MbPyrSeg{i, t0[r], t1[r] - t0[r], total};
+            total += (t1[r] - t0[r]) * rows;
+        }
+    }
+    if (total == 0) return SB_OK;
+    k_mb_pyr_down_list<<<total, 256, 0, s>>>(a);
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
 int launch_mb_pyr_down(const MbPyrArgs &a, int max_dw, int max_dh, cudaStream_t s)
 {
     dim3 block(32, 8), grid(div_up(div_up(max_dw, 2), 32), div_up(div_up(max_dh, 2), 8), a.n);

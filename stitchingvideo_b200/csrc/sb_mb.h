@@ -36,6 +36,13 @@ struct MbPyrArgs {
     MbPyrCam cam[SB_MAX_CAMERAS];
 };
 
+struct MbPyrSeg { int cam, tx0, ntx, first; };          // tiles tx0 .. tx0 + ntx - 1 (64 output columns each) of one camera, all tile rows
+struct MbPyrListArgs {
+    MbPyrArgs p;
+    int n_seg;
+    MbPyrSeg seg[2 * SB_MAX_CAMERAS];
+};
+
 struct MbBandCam {
     const uint32_t *fine;    // Gaussian level l (RGBX), rect-local
     size_t fstep;
@@ -129,6 +136,7 @@ int launch_mb_tap_table(const ProjParams &p, int tl_x, int tl_y, int ww, int wh,
 int launch_mb_tile_mask(const MbBandGeom &g, bool float_weights, int lw, int lh, const void *wsum, size_t wsum_step, uint32_t *mask, cudaStream_t s);
 int launch_mb_warp(const MbWarpArgs &a, bool apply_gain, int max_rw, int max_rh, cudaStream_t s);
 int launch_mb_pyr_down(const MbPyrArgs &a, int max_dw, int max_dh, cudaStream_t s);
+int launch_mb_pyr_down_list(MbPyrListArgs &a, cudaStream_t s);      // the same over the compacted tile list (fills a.seg)
 int launch_mb_band(const MbBandArgs &a, bool float_weights, bool not_top, bool final_band, bool out8, cudaStream_t s);
 
 }  // namespace sb
