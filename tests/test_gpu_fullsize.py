@@ -150,3 +150,26 @@ def test_app6_as_the_app_runs_it(gpu):
     ow, oh, xx, yy = P.crop_geometry(roi[2], roi[3], *spec["crop"])
     assert (w, h) == (ow, oh)
     same(mask, rmask[yy:yy + oh, xx:xx + ow], "app6 mask")
+
+
+def test_c5_strips_match_the_oracle(gpu):
+    """BASELINE.json configs[4] against the ORACLE (round 1 only compared strips with the unsplit GPU panorama): the 16K-wide
+    panorama of 8 x 4K cameras composed as 8 column strips - both halo policies - equals the CPU oracle's panorama bit for bit."""
+    from stitchingvideo_b200 import strips
+    Ks, Rs, spec = rigs.cameras("c5")
+    size, n = (spec["W"], spec["H"]), spec["n_used"]
+    cal = P.Calibration(size, Ks, Rs, spec["warper"], spec["scale"])
+    frames = [rigs.frame("c5", 0, i, smooth=1) for i in range(n)]
+    ref, rmask = P.compose(cal, frames, blender="multiband", num_bands=5, gains=spec["gain_values"])
+    assert ref.shape[1] > 16000
+    mk = lambda: gpu.Compositor(size, Ks, Rs, warper=spec["warper"], scale=spec["scale"], blender="multiband", num_bands=5, gains=spec["gain_values"])
+    whole = mk()
+    pano, mask = whole.compose(frames)
+    same(pano, ref, "c5 unsplit panorama")
+    same(mask, rmask, "c5 unsplit mask")
+    del whole
+    comps = [mk() for _ in range(8)]
+    for run in (strips.run_local_recompute, strips.run_local):
+        parts = run(comps, frames)
+        same(np.concatenate([p[0] for p in parts], axis=1), ref, "c5 strips %s" % run.__name__)
+        same(np.concatenate([p[1] for p in parts], axis=1), rmask, "c5 strip masks %s" % run.__name__)
