@@ -266,6 +266,18 @@ typedef struct sb_compositor_config {
 
 int  sb_compositor_create(const sb_compositor_config *cfg, int device, sb_compositor **out);
 
+/* One process, several GPUs (SURVEY.md 8e throughput mode, as C++ host code): frame f of a sequence runs on devices[f % n];
+ * every device gets its own compositor built from `cfg` (tables replicated), `depth` frame sets in flight per device, one
+ * host thread per device inside sb_multi_run, no data-path collective.  sb_multi_run blocks until all n_frames panoramas
+ * (srcs[f * n_cameras + i] -> panos[f], pano_masks[f] or NULL) have landed; results equal n_frames calls of
+ * sb_compositor_compose.  sb_multi_handle gives the per-device compositor (e.g. to build an sb_batch per device). */
+typedef struct sb_multi sb_multi;
+int  sb_multi_create(const sb_compositor_config *cfg, int n_devices, const int *devices, int depth, sb_multi **out);
+int  sb_multi_size(const sb_multi *m);
+sb_compositor *sb_multi_handle(sb_multi *m, int k);
+int  sb_multi_run(sb_multi *m, int n_frames, const sb_image *srcs, sb_image *panos, sb_image *pano_masks);
+void sb_multi_destroy(sb_multi *m);
+
 /* Calibration-table serialization: everything a (re)calibration hands to the per-frame path —
  * the sb_compositor_config with its K, R, gains / block gain maps and seam masks (host images) — in one checksummed
  * file, written atomically.  The reference keeps these only in process memory (APP64:334-346 PreStitchingStruct), so a
@@ -370,6 +382,16 @@ int  sb_compositor_strip_down(sb_compositor *c, int level);
 int  sb_compositor_strip_band(sb_compositor *c, int level);
 /* this rank's columns of the panorama (and mask); data == NULL lends a view of the device buffer */
 int  sb_compositor_strip_result(sb_compositor *c, sb_image *strip, sb_image *strip_mask);
+/* Halo exchange WITHOUT the host in the loop (exchange halo mode): every rank keeps one receive area per side in its own HBM;
+ * the neighbour maps it (CUDA IPC handle from another process, the plain pointer inside one process) and its kernels write
+ * their edge columns straight into it over NVLink, then store the step's sequence number into the area's flag word; the
+ * receiving rank's kernel waits for that number and moves the columns into place.  Setup once per calibration:
+ *     peer_export(side) on every rank -> exchange the 64-byte handles -> peer_connect(side, handle of that neighbour's
+ *     OPPOSITE side);   then per frame ONE call: strip_frame_peer(srcs) (+ strip_result).
+ * The reference has no counterpart. */
+int  sb_compositor_strip_peer_export(sb_compositor *c, int side, void *ipc_handle_64, void **local_ptr, size_t *bytes);
+int  sb_compositor_strip_peer_connect(sb_compositor *c, int side, const void *ipc_handle_64, void *same_process_ptr);
+int  sb_compositor_strip_frame_peer(sb_compositor *c, const sb_image *srcs);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,7 @@ def main():
     ap.add_argument("--rig", default="c5")
     ap.add_argument("--frames", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--halo", default="exchange", choices=["exchange", "recompute"])
+    ap.add_argument("--halo", default="exchange", choices=["exchange", "recompute", "peer"])
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -87,7 +87,7 @@ def main():
         print(json.dumps({"mode": "strip", "halo": args.halo, "rig": args.rig, "n_gpus": world, "panorama": "%dx%d" % (pw, ph), "bit_exact_vs_unsplit": ok,
                           "strip_latency_ms": {"median": float(np.median(lat)), "min": float(np.min(lat))},
                           "single_gpu_latency_ms": single_ms, "halo_bytes_per_frame_rank0": {"sent": sent, "received": recvd},
-                          "exchanges_per_frame": sum(1 for s in sc.steps if s[0] == "exchange") if args.halo == "exchange" else 0, "frames": args.frames}))
+                          "exchanges_per_frame": sum(1 for s in sc.steps if s[0] == "exchange") if args.halo in ("exchange", "peer") else 0, "frames": args.frames}))
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
 

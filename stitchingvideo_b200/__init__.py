@@ -10,7 +10,7 @@ from .capi import (  # noqa: F401
     BLEND_FEATHER, BLEND_MULTI_BAND, BLEND_NO, BORDER_CONSTANT, BORDER_REFLECT, BORDER_REFLECT_101,
     BORDER_REPLICATE, BORDER_WRAP, COMP_GAIN, COMP_GAIN_BLOCKS, COMP_NO, CV_8U, CV_8UC1, CV_8UC3, CV_16S,
     CV_16SC1, CV_16SC3, CV_32F, CV_32FC1, INTER_LINEAR, INTER_NEAREST, Blender, BlocksGainCompensator,
-    Compositor, CylindricalWarper, DeviceImage, ExposureCompensator, FeatherBlender, GainCompensator,
+    Batch, Compositor, CylindricalWarper, DeviceImage, MultiCompositor, ExposureCompensator, FeatherBlender, GainCompensator,
     MultiBandBlender, NoExposureCompensator, PlaneWarper, RotationWarper, SphericalWarper, StitchError,
     CompressedRectilinearPortraitWarper, CompressedRectilinearWarper, CylindricalPortraitWarper, FisheyeWarper, MercatorWarper,
     PaniniPortraitWarper, PaniniWarper, PlanePortraitWarper, SphericalPortraitWarper, StereographicWarper, TransverseMercatorWarper,

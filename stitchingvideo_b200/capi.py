@@ -136,6 +136,11 @@ API = {
     "sb_compositor_set_depth": (C.c_int, [C.c_void_p, C.c_int]),
     "sb_compositor_set_fused": (C.c_int, [C.c_void_p, C.c_int]),
     "sb_compositor_kernel_plan": (C.c_int, [C.c_void_p]),
+    "sb_multi_create": (C.c_int, [_P(SbCompositorConfig), C.c_int, _P(C.c_int), C.c_int, _P(C.c_void_p)]),
+    "sb_multi_size": (C.c_int, [C.c_void_p]),
+    "sb_multi_handle": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "sb_multi_run": (C.c_int, [C.c_void_p, C.c_int, _P(SbImage), _P(SbImage), _P(SbImage)]),
+    "sb_multi_destroy": (None, [C.c_void_p]),
     "sb_debug_fs2_trace_dump": (C.c_int, []),
     "sb_compositor_enqueue": (C.c_int, [C.c_void_p, _P(SbImage), _P(SbImage), _P(SbImage), _P(C.c_int)]),
     "sb_compositor_wait": (C.c_int, [C.c_void_p, C.c_int]),
@@ -152,6 +157,9 @@ API = {
     "sb_compositor_profile_frame": (C.c_int, [C.c_void_p, _P(SbImage), C.c_char_p, C.c_size_t]),
     "sb_compositor_num_bands": (C.c_int, [C.c_void_p]),
     "sb_compositor_set_strip": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "sb_compositor_strip_peer_export": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, _P(C.c_void_p), _P(C.c_size_t)]),
+    "sb_compositor_strip_peer_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "sb_compositor_strip_frame_peer": (C.c_int, [C.c_void_p, _P(SbImage)]),
     "sb_compositor_set_strip_halo": (C.c_int, [C.c_void_p, C.c_int]),
     "sb_compositor_strip_compose": (C.c_int, [C.c_void_p, _P(SbImage)]),
     "sb_compositor_strip_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(C.c_int), _P(C.c_int)]),
@@ -791,6 +799,44 @@ class Batch:
             pass
 
 
+class MultiCompositor:
+    """sb_multi: one process driving several GPUs, frame f on devices[f % n] (SURVEY.md §8e throughput mode)."""
+
+    def __init__(self, devices, depth, *args, **kw):
+        proto = Compositor.__new__(Compositor)
+        proto._h = None
+        proto._build_config(*args, **kw)
+        self._proto = proto                                   # keeps the config's arrays alive
+        self.n = proto.n
+        self.output_type = proto._cfg.contents.output_type
+        devs = (C.c_int * len(devices))(*devices)
+        self._h = C.c_void_p()
+        _check(lib().sb_multi_create(proto._cfg, len(devices), devs, depth, C.byref(self._h)))
+        s = SbSize()
+        _check(lib().sb_compositor_pano_size(lib().sb_multi_handle(self._h, 0), C.byref(s)))
+        self.pano_size = (s.width, s.height)
+
+    def run(self, frame_sets, with_masks=True):
+        """frame_sets[f] = the n frames of frame set f (host arrays) -> list of (pano, mask) in frame order."""
+        nf, w, h = len(frame_sets), self.pano_size[0], self.pano_size[1]
+        srcs = (SbImage * (nf * self.n))()
+        keep = []
+        for f, frames in enumerate(frame_sets):
+            for i, fr in enumerate(frames):
+                srcs[f * self.n + i], k = _image(fr)
+                keep.append(k)
+        panos, masks = [_empty(h, w, self.output_type) for _ in range(nf)], [np.empty((h, w), np.uint8) for _ in range(nf)]
+        ip = (SbImage * nf)(*[_image(p, output=True)[0] for p in panos])
+        im = (SbImage * nf)(*[_image(m, output=True)[0] for m in masks]) if with_masks else None
+        _check(lib().sb_multi_run(self._h, nf, srcs, ip, im))
+        return list(zip(panos, masks))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.sb_multi_destroy(self._h)
+            self._h = None
+
+
 _WARPER_KINDS = {"plane": WARP_PLANE, "cylindrical": WARP_CYLINDRICAL, "spherical": WARP_SPHERICAL, "fisheye": WARP_FISHEYE,
                  "stereographic": WARP_STEREOGRAPHIC, "compressedRectilinear": WARP_COMPRESSED_RECTILINEAR,
                  "compressedRectilinearPortrait": WARP_COMPRESSED_RECTILINEAR_PORTRAIT, "panini": WARP_PANINI, "paniniPortrait": WARP_PANINI_PORTRAIT,
@@ -804,6 +850,13 @@ class Compositor:
     def __init__(self, src_size, Ks, Rs, warper="spherical", scale=None, blender="multiband", num_bands=5,
                  weight_type=CV_32F, sharpness=0.02, gains=None, seam_masks=None, output_type=CV_8UC3, device=0,
                  gain_maps=None, warper_ab=None, undistort_maps=None, crop=None, crop_app_fill=False):
+        self._build_config(src_size, Ks, Rs, warper, scale, blender, num_bands, weight_type, sharpness, gains, seam_masks, output_type,
+                           device, gain_maps, warper_ab, undistort_maps, crop, crop_app_fill)
+        self._create(device)
+
+    def _build_config(self, src_size, Ks, Rs, warper="spherical", scale=None, blender="multiband", num_bands=5,
+                      weight_type=CV_32F, sharpness=0.02, gains=None, seam_masks=None, output_type=CV_8UC3, device=0,
+                      gain_maps=None, warper_ab=None, undistort_maps=None, crop=None, crop_app_fill=False):
         """warper: "plane" / "cylindrical" / "spherical" or any WARP_* kind (warper_ab = (a, b) for the compressed-rectilinear /
         Panini projectors); undistort_maps: per camera the (map1 CV_16SC2, map2 CV_16UC1) pair of initUndistortRectifyMap
         (the app's fisheye front end, APP64:201-238); crop = (up, down, left, right): the live app's crop margins
@@ -858,7 +911,6 @@ class Compositor:
         cfg.output_type = output_type
         self._cal = None
         self._cfg, self._cfg_keep = C.pointer(cfg), (K, R, g, keep, gkeep, garr, arr, ukeep)      # (the config points into these)
-        self._create(device)
 
     def _create(self, device):
         cfg = self._cfg.contents
@@ -1012,6 +1064,22 @@ class Compositor:
         """Recompute-halo mode: every stage of one frame on this rank's columns, no exchange; asynchronous."""
         arr, keep = self._srcs(frames)
         _check(lib().sb_compositor_strip_compose(self._h, arr))
+
+    def strip_peer_export(self, side):
+        """This rank's receive area of `side` for the peer-memory halo exchange -> (64-byte CUDA IPC handle, device pointer)."""
+        h, ptr, n = C.create_string_buffer(64), C.c_void_p(), C.c_size_t()
+        _check(lib().sb_compositor_strip_peer_export(self._h, side, h, C.byref(ptr), C.byref(n)))
+        return h.raw, ptr.value
+
+    def strip_peer_connect(self, side, ipc_handle=None, same_process_ptr=None):
+        """Map the neighbour's receive area (of ITS opposite side): its IPC handle, or its pointer inside one process."""
+        hb = C.create_string_buffer(ipc_handle, 64) if ipc_handle is not None else None
+        _check(lib().sb_compositor_strip_peer_connect(self._h, side, hb, C.c_void_p(same_process_ptr) if same_process_ptr is not None else None))
+
+    def strip_frame_peer(self, frames):
+        """Exchange-halo mode with peer-memory exchange: every stage and exchange of one frame, ONE call; asynchronous."""
+        arr, keep = self._srcs(frames)
+        _check(lib().sb_compositor_strip_frame_peer(self._h, arr))
 
     def strip_range(self, rank, world):
         x0, x1 = C.c_int(), C.c_int()

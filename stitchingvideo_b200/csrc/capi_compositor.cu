@@ -155,6 +155,12 @@ struct sb_compositor {
     std::vector<int> g_lo, g_hi, b_lo, b_hi;
     bool external_stream = false;
     std::vector<DImage> strip_src;               // device views of the current frame's sources
+    // peer-memory halo exchange: this rank's receive areas (one per side), the neighbours' as mapped here, step layout
+    DevBuf peer_mine[2], peer_done;
+    char *peer_theirs[2] = {nullptr, nullptr};
+    bool peer_ipc[2] = {false, false};
+    std::vector<unsigned long long> peer_region_mine[2], peer_region_theirs[2];   // per exchange step
+    unsigned long long peer_frames = 0;
 };
 
 namespace {
@@ -1750,6 +1756,73 @@ void strip_plan(sb_compositor *c)
     }
 }
 
+// ---- halo exchange without the host in the loop -----------------------------------------------------------------------
+// Each rank owns, per side, one receive area in its own HBM (a 128-byte flag block + one region per exchange step) that the
+// neighbour on that side maps (CUDA IPC between processes, the plain pointer inside one process).  An exchange step is two
+// small kernels on the rank's stream: k_halo_push copies this rank's edge columns STRAIGHT into both neighbours' receive areas
+// over NVLink and, when its last block is done, stores the step's sequence number into their flag words (release at system
+// scope); k_halo_pull waits for the sequence number in its own flag words (acquire) and moves the received columns into place.
+// No packing buffers, no collective library call, no host synchronisation: the whole frame is enqueued at once.
+struct HaloCopy {                     // one column run of one buffer
+    char *base; unsigned long long step;
+    int esz, rows, col, ncols;
+    unsigned long long off;           // byte offset inside the step's region of the receive area
+    int side;
+};
+constexpr int SB_HALO_MAX_COPIES = 2 * (SB_MAX_CAMERAS + 1);
+struct HaloXferArgs {
+    int n;
+    HaloCopy c[SB_HALO_MAX_COPIES];
+    char *area[2];                    // push: the neighbours' receive areas (peer memory); pull: this rank's own
+    unsigned long long region[2];     // byte offset of this step's region inside the area of each side
+    unsigned long long seq;           // sequence number of this step (monotonic over steps and frames)
+    unsigned *done;                   // push: block counter for "last block signals"
+};
+__global__ void __launch_bounds__(128) k_halo_push(const __grid_constant__ HaloXferArgs a)
+{
+    for (int k = 0; k < a.n; ++k) {
+        const HaloCopy &h = a.c[k];
+        char *dst = a.area[h.side] + 128 + a.region[h.side] + h.off;
+        const int row_bytes = h.ncols * h.esz, words = row_bytes / 4;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h.rows * words; i += gridDim.x * blockDim.x) {
+            const int r = i / words, w = i - r * words;
+            reinterpret_cast<uint32_t *>(dst + (size_t)r * row_bytes)[w] =
+                reinterpret_cast<const uint32_t *>(h.base + (size_t)r * h.step + (size_t)h.col * h.esz)[w];
+        }
+    }
+    __threadfence_system();                                 // this block's columns before its count
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(a.done, 1u) == gridDim.x - 1) {
+        *a.done = 0u;                                       // (the next push on this stream starts from zero)
+        __threadfence_system();
+        for (int side = 0; side < 2; ++side)
+            if (a.area[side]) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.area[side]), "l"(a.seq) : "memory");
+    }
+}
+__global__ void __launch_bounds__(128) k_halo_pull(const __grid_constant__ HaloXferArgs a)
+{
+    if (threadIdx.x == 0)
+        for (int side = 0; side < 2; ++side) {
+            if (!a.area[side]) continue;
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.area[side]) : "memory");
+                if (v < a.seq) __nanosleep(200);
+            } while (v < a.seq);
+        }
+    __syncthreads();
+    for (int k = 0; k < a.n; ++k) {
+        const HaloCopy &h = a.c[k];
+        const char *src = a.area[h.side] + 128 + a.region[h.side] + h.off;
+        const int row_bytes = h.ncols * h.esz, words = row_bytes / 4;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h.rows * words; i += gridDim.x * blockDim.x) {
+            const int r = i / words, w = i - r * words;
+            reinterpret_cast<uint32_t *>(h.base + (size_t)r * h.step + (size_t)h.col * h.esz)[w] =
+                *reinterpret_cast<const volatile uint32_t *>(src + (size_t)r * row_bytes + (size_t)w * 4);
+        }
+    }
+}
+
 int strip_ready(sb_compositor *c)
 {
     SB_ASSERT(c);
@@ -1911,6 +1984,132 @@ int sb_compositor_strip_band(sb_compositor *c, int level)
     DeviceGuard g(c->device);
     if (!g.ok) return SB_ERR_CUDA;
     return mb_band_stage(c, c->slots[0], level, c->b_lo[level], c->b_hi[level]);
+}
+
+// The exchange steps of a frame, in schedule order (strips.py: schedule): Gaussian level l before the pyrDown that reads it
+// (l = 0 .. num_bands), restored band l right after its band (l = num_bands .. 1).
+static void peer_steps(const sb_compositor *c, std::vector<std::pair<int, int>> *steps)
+{
+    steps->clear();
+    for (int l = 0; l <= c->num_bands; ++l) steps->emplace_back(SB_HALO_GAUSS, l);
+    for (int l = c->num_bands; l >= 1; --l) steps->emplace_back(SB_HALO_RESTORED, l);
+}
+
+// Receive area of `side`: 128 bytes of flags, then one region per exchange step, each the size of what arrives from that side.
+int sb_compositor_strip_peer_export(sb_compositor *c, int side, void *ipc_handle_64, void **local_ptr, size_t *bytes)
+{
+    SB_TRY(strip_ready(c));
+    SB_ASSERT(side == SB_SIDE_LEFT || side == SB_SIDE_RIGHT);
+    if (c->strip_recompute) return fail(SB_ERR_ASSERT, "the peer exchange belongs to the exchange halo mode");
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    std::vector<std::pair<int, int>> steps;
+    peer_steps(c, &steps);
+    size_t total = 0;
+    c->peer_region_mine[side].clear();
+    for (auto &st : steps) {
+        size_t sb = 0, rb = 0;
+        SB_TRY(sb_compositor_strip_halo_bytes(c, st.first, st.second, side, &sb, &rb));
+        c->peer_region_mine[side].push_back(total);
+        total += (rb + 127) & ~(size_t)127;
+    }
+    // what this rank SENDS to that side lands in the neighbour's area of the opposite side, laid out by the same rule
+    size_t ttotal = 0;
+    c->peer_region_theirs[side].clear();
+    for (auto &st : steps) {
+        size_t sb = 0, rb = 0;
+        SB_TRY(sb_compositor_strip_halo_bytes(c, st.first, st.second, side, &sb, &rb));
+        c->peer_region_theirs[side].push_back(ttotal);
+        ttotal += (sb + 127) & ~(size_t)127;
+    }
+    SB_TRY(c->peer_mine[side].ensure(128 + total + 128));
+    SB_CUDA(cudaMemset(c->peer_mine[side].p, 0, 128 + total + 128));
+    if (!c->peer_done.p) { SB_TRY(c->peer_done.ensure(64)); SB_CUDA(cudaMemset(c->peer_done.p, 0, 64)); }
+    c->peer_frames = 0;
+    if (ipc_handle_64) {
+        cudaIpcMemHandle_t h;
+        SB_CUDA(cudaIpcGetMemHandle(&h, c->peer_mine[side].p));
+        static_assert(sizeof h == 64, "cudaIpcMemHandle_t is 64 bytes");
+        std::memcpy(ipc_handle_64, &h, 64);
+    }
+    if (local_ptr) *local_ptr = c->peer_mine[side].p;
+    if (bytes) *bytes = 128 + total + 128;
+    return SB_OK;
+}
+
+// Map the neighbour's receive area: its IPC handle (another process) or its plain device pointer (same process).
+int sb_compositor_strip_peer_connect(sb_compositor *c, int side, const void *ipc_handle_64, void *same_process_ptr)
+{
+    SB_TRY(strip_ready(c));
+    SB_ASSERT(side == SB_SIDE_LEFT || side == SB_SIDE_RIGHT);
+    SB_ASSERT((ipc_handle_64 != nullptr) != (same_process_ptr != nullptr));
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    if (c->peer_theirs[side] && c->peer_ipc[side]) cudaIpcCloseMemHandle(c->peer_theirs[side]);
+    c->peer_theirs[side] = nullptr; c->peer_ipc[side] = false;
+    if (ipc_handle_64) {
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, ipc_handle_64, 64);
+        void *p = nullptr;
+        SB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_theirs[side] = static_cast<char *>(p); c->peer_ipc[side] = true;
+    } else {
+        c->peer_theirs[side] = static_cast<char *>(same_process_ptr);
+    }
+    return SB_OK;
+}
+
+static int peer_exchange(sb_compositor *c, int step, int what, int level, unsigned long long seq)
+{
+    cudaStream_t st = c->slots[0].stream;
+    HaloXferArgs push{}, pull{};
+    push.seq = pull.seq = seq;
+    push.done = static_cast<unsigned *>(c->peer_done.p);
+    for (int side = 0; side < 2; ++side) {
+        std::vector<HaloSeg> segs;
+        SB_TRY(halo_segments(c, what, level, side, &segs));
+        if (segs.empty()) continue;
+        if (!c->peer_theirs[side] || !c->peer_mine[side].p) return fail(SB_ERR_ASSERT, "strip_frame_peer: side %d is not connected (peer_export / peer_connect)", side);
+        push.area[side] = c->peer_theirs[side]; push.region[side] = c->peer_region_theirs[side][step];
+        pull.area[side] = static_cast<char *>(c->peer_mine[side].p); pull.region[side] = c->peer_region_mine[side][step];
+        unsigned long long so = 0, ro = 0;
+        for (const HaloSeg &h : segs) {
+            if (h.ncols_send) { SB_ASSERT(push.n < SB_HALO_MAX_COPIES); push.c[push.n++] = HaloCopy{h.base, h.step, h.esz, h.rows, h.send_col, h.ncols_send, so, side}; }
+            if (h.ncols_recv) { SB_ASSERT(pull.n < SB_HALO_MAX_COPIES); pull.c[pull.n++] = HaloCopy{h.base, h.step, h.esz, h.rows, h.recv_col, h.ncols_recv, ro, side}; }
+            so += (unsigned long long)h.rows * h.ncols_send * h.esz;
+            ro += (unsigned long long)h.rows * h.ncols_recv * h.esz;
+        }
+    }
+    if (!push.area[0] && !push.area[1]) return SB_OK;       // a single strip: nothing to exchange
+    k_halo_push<<<8, 128, 0, st>>>(push);
+    SB_LAUNCHED();
+    k_halo_pull<<<8, 128, 0, st>>>(pull);
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
+// One frame of this rank's strip, every stage and every halo exchange enqueued by this ONE call (exchange halo mode).
+int sb_compositor_strip_frame_peer(sb_compositor *c, const sb_image *srcs)
+{
+    SB_TRY(strip_ready(c));
+    if (c->strip_recompute) return fail(SB_ERR_ASSERT, "strip_frame_peer runs the exchange halo mode");
+    SB_TRY(sb_compositor_strip_warp(c, srcs));
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    Slot &s = c->slots[0];
+    const int nb = c->num_bands;
+    const unsigned long long n_steps = 2ull * nb + 1, base = c->peer_frames * n_steps;
+    int step = 0;
+    for (int l = 0; l <= nb; ++l) {
+        SB_TRY(peer_exchange(c, step, SB_HALO_GAUSS, l, base + step + 1)); ++step;
+        if (l < nb) SB_TRY(mb_down_stage(c, s, l, c->g_lo[l + 1], c->g_hi[l + 1]));
+    }
+    for (int l = nb; l >= 0; --l) {
+        SB_TRY(mb_band_stage(c, s, l, c->b_lo[l], c->b_hi[l]));
+        if (l >= 1) { SB_TRY(peer_exchange(c, step, SB_HALO_RESTORED, l, base + step + 1)); ++step; }
+    }
+    ++c->peer_frames;
+    return SB_OK;
 }
 
 int sb_compositor_strip_result(sb_compositor *c, sb_image *strip, sb_image *strip_mask)

@@ -98,6 +98,34 @@ class TorchTransport:
                 self.comp.strip_unpack(what, level, side, rb.data_ptr())
 
 
+def connect_peers_distributed(comp, rank, world):
+    """Peer-memory halo exchange between processes: every rank exports its two receive areas as CUDA IPC handles, the handles
+    travel once through torch.distributed (control plane), each rank maps its neighbours' areas.  After this no collective
+    library call and no host synchronisation is on the frame path."""
+    import torch.distributed as dist
+    mine = {}
+    for side in (LEFT, RIGHT):
+        if neighbour(rank, world, side) is not None:
+            mine[side] = comp.strip_peer_export(side)[0]
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine)
+    for side in (LEFT, RIGHT):
+        nbr = neighbour(rank, world, side)
+        if nbr is not None:
+            comp.strip_peer_connect(side, ipc_handle=everyone[nbr][RIGHT if side == LEFT else LEFT])
+
+
+def connect_peers_local(comps):
+    """The same inside one process (all handles on one device or on peer-accessible devices): plain pointers."""
+    world = len(comps)
+    areas = [{side: c.strip_peer_export(side)[1] for side in (LEFT, RIGHT) if neighbour(r, world, side) is not None} for r, c in enumerate(comps)]
+    for r, c in enumerate(comps):
+        for side in (LEFT, RIGHT):
+            nbr = neighbour(r, world, side)
+            if nbr is not None:
+                c.strip_peer_connect(side, same_process_ptr=areas[nbr][RIGHT if side == LEFT else LEFT])
+
+
 class StripCompositor:
     """One rank of the strip-mode panorama: a Compositor restricted to its columns + a transport.
 
@@ -107,10 +135,18 @@ class StripCompositor:
     when strips are wide compared with the halo."""
 
     def __init__(self, comp, rank, world, transport=None, device=None, halo="exchange"):
+        """halo="peer": the exchange mode with the halo columns written straight into the neighbours' HBM by this rank's
+        kernels (sb_compositor_strip_frame_peer) - no collective call, no host in the loop, one C call per frame."""
         comp.set_strip(rank, world)
         self.comp, self.rank, self.world, self.halo = comp, rank, world, halo
         comp.set_strip_halo(halo == "recompute")
-        if halo == "recompute":
+        if halo == "peer":
+            self.transport = None
+            if device is not None and str(device) != "cpu":
+                import torch
+                comp.set_stream(torch.cuda.current_stream(device).cuda_stream)
+            connect_peers_distributed(comp, rank, world)
+        elif halo == "recompute":
             self.transport = None
             if device is not None and str(device) != "cpu":
                 import torch
@@ -123,6 +159,9 @@ class StripCompositor:
         """All stages of one frame, asynchronous on the compositor's stream."""
         if self.halo == "recompute":
             self.comp.strip_compose(frames)
+            return
+        if self.halo == "peer":
+            self.comp.strip_frame_peer(frames)
             return
         for step in self.steps:
             if step[0] == "exchange":
@@ -145,6 +184,26 @@ class StripCompositor:
         pano = np.concatenate([p[0] for p in parts], axis=1)
         pmask = None if mask is None else np.concatenate([p[1] for p in parts], axis=1)
         return pano, pmask
+
+
+def run_local_peer(comps, frames, connected=False):
+    """Peer-memory exchange on one device: every handle runs its whole frame on its own stream; the ranks meet only through
+    the flag words in each other's receive areas."""
+    world = len(comps)
+    if not connected:
+        for r, c in enumerate(comps):
+            c.set_strip(r, world)
+            c.set_strip_halo(False)
+        connect_peers_local(comps)
+        # Inside ONE process the ranks share a device: a cudaMalloc by one handle (first-frame staging buffers) synchronises
+        # the whole device and would wait for ever behind another handle's kernel that is waiting for its neighbour's flag.
+        # So every handle stages a frame once, alone, before the ranks start to depend on each other.
+        for r, c in enumerate(comps):
+            c.strip_warp(frames)
+            c.strip_result(r, world)
+    for c in comps:
+        c.strip_frame_peer(frames)
+    return [c.strip_result(r, world) for r, c in enumerate(comps)]
 
 
 def run_local_recompute(comps, frames):

@@ -106,3 +106,19 @@ def test_output_views_must_be_writable_in_place(gpu):
     pano, _ = comp.compose(frames)
     comp.compose(frames, good)
     assert np.array_equal(good, pano)
+
+
+def test_multi_device_driver(gpu):
+    """sb_multi_*: one process, one host thread per device, frame f on devices[f % n] (here two handles on device 0 - a box
+    with several GPUs passes their indices): the panoramas come back in frame order and equal the oracle's."""
+    Ks, Rs, spec = rigs.cameras("mini_cyl")
+    size, n = (spec["W"], spec["H"]), spec["n_used"]
+    cal = P.Calibration(size, Ks, Rs, "cylindrical", spec["scale"])
+    m = gpu.MultiCompositor([0, 0], 2, size, Ks, Rs, warper="cylindrical", scale=spec["scale"], blender="feather")
+    sets = [[rigs.frame("mini_cyl", f, i) for i in range(n)] for f in range(7)]
+    out = m.run(sets)
+    for f, (pano, mask) in enumerate(out):
+        ref, rmask = P.compose(cal, sets[f], blender="feather")
+        assert np.array_equal(pano, ref) and np.array_equal(mask, rmask), "frame %d" % f
+    with pytest.raises(gpu.StitchError):
+        gpu.MultiCompositor([0, 99], 1, size, Ks, Rs, warper="cylindrical", scale=spec["scale"], blender="feather")     # no such device: an error, not a downgrade

@@ -55,6 +55,27 @@ def test_strips_reassemble_the_panorama(gpu, world, weight_type):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_peer_memory_halo_exchange(gpu, world):
+    """the halo exchange without the host in the loop - each handle's kernels write its edge columns into the
+    neighbours' receive areas and raise their flag words; one C call per rank and frame.  Here the "ranks" are handles on one
+    device (plain pointers instead of IPC handles); frame after frame the strips reassemble the unsplit panorama bit for bit."""
+    Ks, Rs, spec = rigs.cameras("mini")
+    size, n = (spec["W"], spec["H"]), spec["n_used"]
+    mk = lambda: gpu.Compositor(size, Ks, Rs, warper="spherical", scale=spec["scale"], blender="multiband", num_bands=5, gains=spec["gain_values"])
+    whole = mk()
+    comps = [mk() for _ in range(world)]
+    for fi in range(3):                                      # the sequence numbers keep counting over the frames
+        frames = [rigs.frame("mini", fi, i) for i in range(n)]
+        pano, mask = whole.compose(frames)
+        before = gpu.kernel_launch_count()
+        parts = strips.run_local_peer(comps, frames, connected=fi > 0)
+        assert gpu.kernel_launch_count() > before
+        assert np.array_equal(np.concatenate([p[0] for p in parts], axis=1), pano), "frame %d" % fi
+        assert np.array_equal(np.concatenate([p[1] for p in parts], axis=1), mask)
+
+
+@pytest.mark.gpu
 def test_strips_written_into_views_of_one_panorama(gpu):
     """strip results copied into column VIEWS of one full-size panorama buffer (pitch = the panorama's) must
     only touch their own columns - a linear copy over such a view would overwrite the neighbouring strips."""
