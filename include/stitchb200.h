@@ -392,6 +392,9 @@ int  sb_compositor_strip_result(sb_compositor *c, sb_image *strip, sb_image *str
 int  sb_compositor_strip_peer_export(sb_compositor *c, int side, void *ipc_handle_64, void **local_ptr, size_t *bytes);
 int  sb_compositor_strip_peer_connect(sb_compositor *c, int side, const void *ipc_handle_64, void *same_process_ptr);
 int  sb_compositor_strip_frame_peer(sb_compositor *c, const sb_image *srcs);
+/* the two halves of one exchange step (for a process that plays several ranks on one device: all pushes of a step first) */
+int  sb_compositor_strip_peer_push(sb_compositor *c, int what, int level);
+int  sb_compositor_strip_peer_pull(sb_compositor *c, int what, int level);
 
 #ifdef __cplusplus
 }

@@ -160,6 +160,8 @@ API = {
     "sb_compositor_strip_peer_export": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, _P(C.c_void_p), _P(C.c_size_t)]),
     "sb_compositor_strip_peer_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "sb_compositor_strip_frame_peer": (C.c_int, [C.c_void_p, _P(SbImage)]),
+    "sb_compositor_strip_peer_push": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "sb_compositor_strip_peer_pull": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "sb_compositor_set_strip_halo": (C.c_int, [C.c_void_p, C.c_int]),
     "sb_compositor_strip_compose": (C.c_int, [C.c_void_p, _P(SbImage)]),
     "sb_compositor_strip_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(C.c_int), _P(C.c_int)]),
@@ -1075,6 +1077,12 @@ class Compositor:
         """Map the neighbour's receive area (of ITS opposite side): its IPC handle, or its pointer inside one process."""
         hb = C.create_string_buffer(ipc_handle, 64) if ipc_handle is not None else None
         _check(lib().sb_compositor_strip_peer_connect(self._h, side, hb, C.c_void_p(same_process_ptr) if same_process_ptr is not None else None))
+
+    def strip_peer_push(self, what, level):
+        _check(lib().sb_compositor_strip_peer_push(self._h, what, level))
+
+    def strip_peer_pull(self, what, level):
+        _check(lib().sb_compositor_strip_peer_pull(self._h, what, level))
 
     def strip_frame_peer(self, frames):
         """Exchange-halo mode with peer-memory exchange: every stage and exchange of one frame, ONE call; asynchronous."""

@@ -2059,9 +2059,16 @@ int sb_compositor_strip_peer_connect(sb_compositor *c, int side, const void *ipc
     return SB_OK;
 }
 
-static int peer_exchange(sb_compositor *c, int step, int what, int level, unsigned long long seq)
+// which = 1: push this rank's edge columns of (what, level) into both neighbours' receive areas and raise their flags;
+// which = 2: wait for this rank's flags and move what arrived into place;  3: both (push first)
+static int peer_exchange(sb_compositor *c, int what, int level, int which)
 {
     cudaStream_t st = c->slots[0].stream;
+    const int nb = c->num_bands;
+    const int step = what == SB_HALO_GAUSS ? level : nb + 1 + (nb - level);
+    if (step == 0 && (which & 1)) ++c->peer_frames;         // a frame's first push opens its block of sequence numbers
+    SB_ASSERT(c->peer_frames > 0);
+    const unsigned long long seq = (c->peer_frames - 1) * (2ull * nb + 1) + step + 1;
     HaloXferArgs push{}, pull{};
     push.seq = pull.seq = seq;
     push.done = static_cast<unsigned *>(c->peer_done.p);
@@ -2069,7 +2076,7 @@ static int peer_exchange(sb_compositor *c, int step, int what, int level, unsign
         std::vector<HaloSeg> segs;
         SB_TRY(halo_segments(c, what, level, side, &segs));
         if (segs.empty()) continue;
-        if (!c->peer_theirs[side] || !c->peer_mine[side].p) return fail(SB_ERR_ASSERT, "strip_frame_peer: side %d is not connected (peer_export / peer_connect)", side);
+        if (!c->peer_theirs[side] || !c->peer_mine[side].p) return fail(SB_ERR_ASSERT, "peer exchange: side %d is not connected (peer_export / peer_connect)", side);
         push.area[side] = c->peer_theirs[side]; push.region[side] = c->peer_region_theirs[side][step];
         pull.area[side] = static_cast<char *>(c->peer_mine[side].p); pull.region[side] = c->peer_region_mine[side][step];
         unsigned long long so = 0, ro = 0;
@@ -2081,11 +2088,27 @@ static int peer_exchange(sb_compositor *c, int step, int what, int level, unsign
         }
     }
     if (!push.area[0] && !push.area[1]) return SB_OK;       // a single strip: nothing to exchange
-    k_halo_push<<<8, 128, 0, st>>>(push);
-    SB_LAUNCHED();
-    k_halo_pull<<<8, 128, 0, st>>>(pull);
-    SB_LAUNCHED();
+    if (which & 1) { k_halo_push<<<8, 128, 0, st>>>(push); SB_LAUNCHED(); }
+    if (which & 2) { k_halo_pull<<<8, 128, 0, st>>>(pull); SB_LAUNCHED(); }
     return SB_OK;
+}
+
+// The two halves of one exchange step on their own (a single process that plays several ranks on ONE device must enqueue every
+// rank's push of a step before any rank's pull: streams of one process can share a hardware queue, and a pull that waits for a
+// push queued behind it would wait for ever).  One rank per process / GPU: sb_compositor_strip_frame_peer.
+int sb_compositor_strip_peer_push(sb_compositor *c, int what, int level)
+{
+    SB_TRY(strip_ready(c));
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    return peer_exchange(c, what, level, 1);
+}
+int sb_compositor_strip_peer_pull(sb_compositor *c, int what, int level)
+{
+    SB_TRY(strip_ready(c));
+    DeviceGuard g(c->device);
+    if (!g.ok) return SB_ERR_CUDA;
+    return peer_exchange(c, what, level, 2);
 }
 
 // One frame of this rank's strip, every stage and every halo exchange enqueued by this ONE call (exchange halo mode).
@@ -2098,17 +2121,14 @@ int sb_compositor_strip_frame_peer(sb_compositor *c, const sb_image *srcs)
     if (!g.ok) return SB_ERR_CUDA;
     Slot &s = c->slots[0];
     const int nb = c->num_bands;
-    const unsigned long long n_steps = 2ull * nb + 1, base = c->peer_frames * n_steps;
-    int step = 0;
     for (int l = 0; l <= nb; ++l) {
-        SB_TRY(peer_exchange(c, step, SB_HALO_GAUSS, l, base + step + 1)); ++step;
+        SB_TRY(peer_exchange(c, SB_HALO_GAUSS, l, 3));
         if (l < nb) SB_TRY(mb_down_stage(c, s, l, c->g_lo[l + 1], c->g_hi[l + 1]));
     }
     for (int l = nb; l >= 0; --l) {
         SB_TRY(mb_band_stage(c, s, l, c->b_lo[l], c->b_hi[l]));
-        if (l >= 1) { SB_TRY(peer_exchange(c, step, SB_HALO_RESTORED, l, base + step + 1)); ++step; }
+        if (l >= 1) SB_TRY(peer_exchange(c, SB_HALO_RESTORED, l, 3));
     }
-    ++c->peer_frames;
     return SB_OK;
 }
 

@@ -201,8 +201,17 @@ def run_local_peer(comps, frames, connected=False):
         for r, c in enumerate(comps):
             c.strip_warp(frames)
             c.strip_result(r, world)
-    for c in comps:
-        c.strip_frame_peer(frames)
+    # (one process, one device: the streams of the handles may share a hardware queue, so every rank's push of a step is
+    # enqueued before any rank's pull of it; with one rank per process / GPU each rank simply calls strip_frame_peer)
+    for step in schedule(comps[0].num_bands):
+        if step[0] != "exchange":
+            for c in comps:
+                run_stage(c, step, frames)
+        else:
+            for c in comps:
+                c.strip_peer_push(step[1], step[2])
+            for c in comps:
+                c.strip_peer_pull(step[1], step[2])
     return [c.strip_result(r, world) for r, c in enumerate(comps)]
 
 
