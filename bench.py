@@ -243,6 +243,27 @@ def measure(workload, args, rank, world, local, barrier, max_over_ranks, sampler
     barrier()
     ms_e2e = max_over_ranks(max(ms_e2e, wall_e2e))
     clocks = sampler.summary() if sampler is not None else None
+    # ... and what this box can do with the copies ALONE (no kernels): the same pinned buffers, the same bytes per frame set, the
+    # same number of streams, all ranks at once - the ceiling the end-to-end figure is to be read against (PCIe + host memory)
+    copy_streams = [torch.cuda.Stream() for _ in range(depth)]
+    dev_in = [torch.empty_like(pin_in[0], device="cuda") for _ in range(depth)]
+    dev_o = [torch.empty((ph, pw, 3), dtype=torch.uint8, device="cuda") for _ in range(depth)]
+
+    def copy_only(n_frames):
+        for f in range(n_frames):
+            k = f % depth
+            with torch.cuda.stream(copy_streams[k]):
+                dev_in[k].copy_(pin_in[f % n_sets], non_blocking=True)
+                pin_out[f % (depth + 1)].copy_(dev_o[k], non_blocking=True)
+    copy_only(2 * LAP)
+    barrier()
+    tc = time.perf_counter()
+    copy_only(e2e_steps * e2e_laps * LAP)
+    torch.cuda.synchronize()
+    ms_copy = max_over_ranks((time.perf_counter() - tc) * 1e3)
+    barrier()
+    copy_value = world * e2e_steps * e2e_laps * LAP / (ms_copy / 1e3)
+    del dev_in, dev_o, copy_streams
     e2e_frames_per_step = e2e_laps * LAP
     e2e_value = world * e2e_steps * e2e_frames_per_step / (ms_e2e / 1e3)
     h2d_frame, d2h_frame = n * size[0] * size[1] * 3, pw * ph * 3
@@ -312,6 +333,8 @@ def measure(workload, args, rank, world, local, barrier, max_over_ranks, sampler
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_frame * e2e_frames_per_step,
                 "d2h_bytes_per_step": d2h_frame * e2e_frames_per_step, "frame_sets_per_step": e2e_frames_per_step,
                 "ms_per_step": ms_e2e / e2e_steps, "host_buffers": "pinned, one block per frame set",
+                "copy_only_ceiling": {"value": copy_value, "unit": "frames/s", "what": "the same host<->device copies with no kernel in between, all ranks at once",
+                                      "frac": e2e_value / copy_value},
                 "pcie_gbs": {"h2d": h2d_frame * e2e_frames_per_step / (ms_e2e / e2e_steps) / 1e6,
                              "d2h": d2h_frame * e2e_frames_per_step / (ms_e2e / e2e_steps) / 1e6}},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,

@@ -30,6 +30,7 @@ struct Camera {
     sb_point tl;                 // corner of the warped image in panorama coordinates
     int ww = 0, wh = 0;          // warped size (br - tl + 1)
     float gain = 1.f;
+    double gain_bytes = 0;       // SB_COMP_GAIN_BLOCKS: bytes of gain_full inside the camera's weighted column spans
     DevImage gain_full;          // SB_COMP_GAIN_BLOCKS: block gain map resized to the warped image (sequence-constant)
     DevImage gain_rect;          // ... and laid out over the padded feed rect (BORDER_REFLECT, multi-band fast path)
     DevBuf tables;               // col_sin | col_cos | row_a | row_b
@@ -564,6 +565,7 @@ int setup(sb_compositor *c)
             SB_TRY(launch_weight_accumulate(cam.feather_w.v, c->wsum[0].v, cam.tl.x - roi.x, cam.tl.y - roi.y, s));
             cam.spans.emplace_back();
             SB_TRY(weight_spans(cam.feather_w.v, cam.tl.x - roi.x, scratch, s, &cam.spans.back()));
+            cam.gain_bytes = 4.0 * cam.wh * ((cam.spans.back()[1] - cam.spans.back()[0]) + (cam.spans.back()[3] - cam.spans.back()[2]));
         }
         // per panorama tile: which cameras carry weight there
         const int tiles_x = div_up(roi.width, SB_FT_W), tiles_y = div_up(roi.height, SB_FT_H);
@@ -1053,6 +1055,7 @@ int run_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src)
             Fs2Args a{};
             fs2_static_args(c, a);
             double fs2_bytes = c->fs2.table_bytes + img_bytes(s.out.v) + (s.want_mask ? img_bytes(s.out_mask.v) : 0);
+            if (blocks) for (int i = 0; i < n; ++i) fs2_bytes += c->cams[i].gain_bytes;      // the resized gain maps are read once per weighted pixel
             for (int i = 0; i < n; ++i) {
                 fs2_bytes += img_bytes(src[i]);
                 SB_TRY(fs2_tmaps(c, i, src[i], &a.tmap[i * FS2_NCLS]));

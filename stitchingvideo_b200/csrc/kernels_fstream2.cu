@@ -376,10 +376,22 @@ __device__ __forceinline__ float fs2_gain(const Fs2Cam &c, int X, int Y)
 {
     return c.gmap ? __ldg(reinterpret_cast<const float *>(reinterpret_cast<const char *>(c.gmap) + (size_t)(Y - c.dy) * c.gmstep) + (X - c.dx)) : c.gain;
 }
-// saturate_cast<uchar>(v * gain)
+// saturate_cast<uchar>(v * gain) for an 8-bit v: cvRound then clamp == clamp then round-half-even (rounding is monotonic), and
+// both conversions ride the FP32 pipe through the 2^23 constant instead of I2F / F2I (a quarter-rate unit that the 12 gain
+// products of a thread's 4 pixels would otherwise saturate): float(v) = bits(2^23 | v) - 2^23, rint(x) = low byte of bits(x + 2^23).
+// max before min sends a NaN product to 0 like cvRound's INT_MIN.
 __device__ __forceinline__ unsigned fs2_apply_gain(unsigned v, float g)
 {
-    return (unsigned)min(max(__float2int_rn(__fmul_rn((float)v, g)), 0), 255);
+    const float f = __fsub_rn(__uint_as_float(v | 0x4b000000u), 8388608.f);
+    const float x = fminf(fmaxf(__fmul_rn(f, g), 0.f), 255.f);
+    return __float_as_uint(__fadd_rn(x, 8388608.f)) & 0xffu;
+}
+// the same for a value sitting in byte 2 of a dot-product sum (fs2_pixel), result in byte 0
+__device__ __forceinline__ unsigned fs2_apply_gain_b2(unsigned s, float g)
+{
+    const float f = __fsub_rn(__uint_as_float(__byte_perm(s, 0x4b000000u, 0x7442)), 8388608.f);
+    const float x = fminf(fmaxf(__fmul_rn(f, g), 0.f), 255.f);
+    return __float_as_uint(__fadd_rn(x, 8388608.f)) & 0xffu;
 }
 
 // crop_app_fill: camera 0's warped pixel (0, 0), sampled from its frame in global memory (rare: only pixels no camera covers)
@@ -619,7 +631,7 @@ k_fs2(const __grid_constant__ Fs2Args a)
                     const float g = (c.gmap && p >= nx) ? 1.f : fs2_gain(c, X + p, Y);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        unsigned q = fs2_apply_gain(v[p][k] >> 16, g);
+                        unsigned q = fs2_apply_gain_b2(v[p][k], g);
                         if (!NOBLEND) q -= min(q, 1u);
                         v[p][k] = q;
                     }
@@ -655,7 +667,7 @@ k_fs2(const __grid_constant__ Fs2Args a)
                 if (GAIN) {
                     const float g = fs2_gain(a.cam[rec.w & 15u], X + p, Y);
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) v[p][k] = fs2_apply_gain(v[p][k] >> 16, g) << 16;
+                    for (int k = 0; k < 3; ++k) v[p][k] = fs2_apply_gain_b2(v[p][k], g) << 16;
                 }
             }
             __syncwarp();
@@ -686,7 +698,10 @@ k_fs2(const __grid_constant__ Fs2Args a)
                     float f0, f1, f2;
                     if (GAIN) {                             // saturate_cast<uchar>(p * gain)
                         const float g = (dist != 0u) ? fs2_gain(a.cam[rec.w & 15u], X + p, Y) : 1.f;
-                        f0 = (float)fs2_apply_gain(s0 >> 16, g); f1 = (float)fs2_apply_gain(s1 >> 16, g); f2 = (float)fs2_apply_gain(s2 >> 16, g);
+                        // (the rounded product stays a float: bits(x + 2^23) - 2^23)
+                        f0 = __fsub_rn(__uint_as_float(fs2_apply_gain_b2(s0, g) | 0x4b000000u), 8388608.f);
+                        f1 = __fsub_rn(__uint_as_float(fs2_apply_gain_b2(s1, g) | 0x4b000000u), 8388608.f);
+                        f2 = __fsub_rn(__uint_as_float(fs2_apply_gain_b2(s2, g) | 0x4b000000u), 8388608.f);
                     } else {
                         f0 = __fsub_rn(__uint_as_float(__byte_perm(s0, 0x4b000000u, 0x7442)), 8388608.f);
                         f1 = __fsub_rn(__uint_as_float(__byte_perm(s1, 0x4b000000u, 0x7442)), 8388608.f);

@@ -598,7 +598,7 @@ template <typename WT> __global__ void __launch_bounds__(256) k_mb_coarse(const 
         if (st > 0) {                                        // every item of the stage before must be done
             if (threadIdx.x == 0) {
                 const unsigned long long want = a.want[st - 1];
-                while (ld_acquire_u64(a.sync + 1 + (st - 1)) < want) __nanosleep(64);
+                while (ld_acquire_u64(a.sync + 1 + (st - 1)) < want) __nanosleep(256);      // (several frames' kernels may be polling: keep them off the L2)
             }
             __syncthreads();
         }
