@@ -32,6 +32,7 @@ struct Camera {
     float gain = 1.f;
     double gain_bytes = 0;       // SB_COMP_GAIN_BLOCKS: bytes of gain_full inside the camera's weighted column spans
     DevImage gain_full;          // SB_COMP_GAIN_BLOCKS: block gain map resized to the warped image (sequence-constant)
+    DevImage gain_pad;           // ... with one tile of zeros all round (k_fs2 fetches gain tiles by tensor copy; they must lie inside the tensor)
     DevImage gain_rect;          // ... and laid out over the padded feed rect (BORDER_REFLECT, multi-band fast path)
     DevBuf tables;               // col_sin | col_cos | row_a | row_b
     WarpTables wt{};
@@ -129,6 +130,7 @@ struct sb_compositor {
     sb_rect out_rect{};                          // what compose hands back, in dst_roi_final coordinates (crop margins; else all of it)
     bool crop = false;
     unsigned fill_tex[2] = {0, 0};               // crop_app_fill: camera 0's table entry of warped pixel (0, 0)
+    CUtensorMap fs2_gtmap[SB_MAX_CAMERAS];       // ... the cameras' resized gain maps as tensors (SB_COMP_GAIN_BLOCKS)
     Fs2Plan fs2;                                 // second-generation streaming kernel (kernels_fstream2.cu): usable when fs2.ok
     DevBuf fs2_desc;
     unsigned long long tmap_clock = 0;
@@ -626,7 +628,16 @@ int setup(sb_compositor *c)
                                     cam.f2tx0, cam.f2ty0, cam.f2ntx, cam.f2nty, static_cast<unsigned char *>(cam.fs2_blocks.p)};
                 cam.tmaps.clear();
             }
-            SB_TRY(fs2_build(fc.data(), n, c->out_rect.width, c->out_rect.height, c->stream_sharpness, c->sm_count, c->fs2_desc, &c->fs2, s));
+            SB_TRY(fs2_build(fc.data(), n, c->out_rect.width, c->out_rect.height, c->stream_sharpness, c->sm_count, cfg.comp_kind == SB_COMP_GAIN_BLOCKS,
+                             c->fs2_desc, &c->fs2, s));
+            if (c->fs2.ok && c->fs2.gain_tma)
+                for (int i = 0; i < n; ++i) {      // the gain map with one tile of zero padding all round (see fs2_build): every gain tile lies inside it
+                    Camera &cam = c->cams[i];
+                    SB_TRY(cam.gain_pad.create_zero(cam.wh + 2 * FS2_H, cam.ww + 2 * FS2_W + 4, SB_32FC1, s));
+                    SB_CUDA(cudaMemcpy2DAsync(static_cast<char *>(cam.gain_pad.v.data) + (size_t)FS2_H * cam.gain_pad.v.step + (size_t)FS2_W * 4, cam.gain_pad.v.step,
+                                              cam.gain_full.v.data, cam.gain_full.v.step, (size_t)cam.ww * 4, (size_t)cam.wh, cudaMemcpyDeviceToDevice, s));
+                    SB_TRY(fs2_encode_gain_tmap(cam.gain_pad.v.ptr<float>(), cam.gain_pad.v.step, cam.ww + 2 * FS2_W + 4, cam.wh + 2 * FS2_H, &c->fs2_gtmap[i]));
+                }
             if (cfg.crop_app_fill) {   // camera 0's table entry of warped pixel (0, 0): what an uncovered pixel gathers (APP64:165-172)
                 uint2 e;
                 SB_CUDA(cudaMemcpyAsync(&e, c->cams[0].feather_table.p, sizeof e, cudaMemcpyDeviceToHost, s));
@@ -927,6 +938,8 @@ void fs2_static_args(sb_compositor *c, Fs2Args &a)
     a.sharpness = c->stream_sharpness;
     a.no_blend = c->cfg.blender_kind == SB_BLEND_NO;
     a.n_tiles = c->fs2.n_tiles; a.per_cta = c->fs2.per_cta; a.steady = c->fs2.steady ? 1 : 0;
+    a.gain_tma = c->fs2.gain_tma ? 1 : 0;
+    if (c->fs2.gain_tma) std::memcpy(a.gtmap, c->fs2_gtmap, sizeof(CUtensorMap) * (size_t)n);
     a.fill_on = c->cfg.crop_app_fill ? 1 : 0; a.fill_tex[0] = c->fill_tex[0]; a.fill_tex[1] = c->fill_tex[1];
 }
 

@@ -117,11 +117,15 @@ int fs2_grid(int n_tiles, int sm_count) { return std::min(n_tiles, FS2_CTAS_PER_
 //   [4 + j] = copy j of the tile: {destination byte offset inside the tile's ring space,
 //             bulk copy: byte offset of the table block in the camera's blocks, bytes, camera
 //             tensor copy: box x (byte) | box y << 16, tensor map index (camera * FS2_NCLS + class), bit 31 set}
-int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, int sm_count, DevBuf &desc_out, Fs2Plan *plan, cudaStream_t s)
+int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, int sm_count, bool gain_maps, DevBuf &desc_out, Fs2Plan *plan, cudaStream_t s)
 {
     *plan = Fs2Plan{};
     const unsigned cls_w[FS2_NCLS] = {96u, 160u, 224u, 256u};      // pitches of 32 (mod 128) bytes keep the 4 tile rows of a warp on distinct banks
     for (int c = 0; c < FS2_NCLS; ++c) plan->cls_w[c] = cls_w[c];
+    // block gain maps travel with the tile (one more tensor copy per camera slot) when the signed 16-bit tile coordinates reach
+    bool gain_tma = gain_maps;
+    for (int i = 0; i < n; ++i) gain_tma = gain_tma && cams[i].ww < 32768 && cams[i].wh < 32768 && pw < 32768 && ph < 32768;
+    plan->gain_tma = gain_tma;
     // the weight index is one byte: the weight must saturate by distance 255 (Blender::NO: the mask byte itself)
     if (!(sharpness > 0.f) || fminf((float)(255.f * sharpness), 1.f) != 1.f) return SB_OK;
     const int tiles_x = div_up(pw, FS2_W), tiles_y = div_up(ph, FS2_H), n_tiles = tiles_x * tiles_y;
@@ -178,14 +182,30 @@ int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, i
             const unsigned cls = (unsigned)(pl.valid >> 4) & 15u, nops = (unsigned)pl.valid >> 8;
             const unsigned bytes = blk_bytes + nops * FS2_ROWS * (unsigned)pl.pitch, slot_off = units * 128u;
             if (slot_blk[j] * (size_t)FS2_BLOCK_BYTES >= (1ull << 32)) return SB_OK;
-            o[1 + j] = make_uint4(slot_off, (unsigned)pl.pitch, 0u, (unsigned)slot_cam[j]);
+            const unsigned box_bytes = nops * FS2_ROWS * (unsigned)pl.pitch, gain_off = blk_bytes + ((box_bytes + 127u) & ~127u);
+            o[1 + j] = make_uint4(slot_off, (unsigned)pl.pitch, gain_off, (unsigned)slot_cam[j]);
             // copy list: the table block (bulk copy), then the source box, FS2_ROWS rows per tensor copy
             o[1 + FS2_MAXC + n_ops++] = make_uint4(slot_off, (unsigned)(slot_blk[j] * FS2_BLOCK_BYTES), blk_bytes, (unsigned)slot_cam[j]);
             for (unsigned q = 0; q < nops; ++q)
                 o[1 + FS2_MAXC + n_ops++] = make_uint4(slot_off + blk_bytes + q * FS2_ROWS * (unsigned)pl.pitch,
                                                        ((unsigned)pl.xlo & 0xffffu) | ((unsigned)(pl.ylo + (int)(q * FS2_ROWS)) << 16),
                                                        (unsigned)slot_cam[j] * FS2_NCLS + cls, 0x80000000u);
-            units += (bytes + 127u) >> 7;
+            unsigned slot_bytes = bytes;
+            if (gain_tma) {     // the 32x32 floats of the camera's resized gain map under this tile (out-of-range: zero, never used)
+                // (coordinates in the gain map PADDED by one tile all round, so that the 32x32 box always lies inside the tensor: a
+                // tensor copy that overlaps its tensor by a single element in x and y raised an illegal-instruction fault on
+                // B200 - scratch/tma_f32.cu, box at (-31, -31) - although partly outside boxes are fine in general)
+                const int gx = tx * FS2_W - cams[slot_cam[j]].dx + FS2_W, gy = ty * FS2_H - cams[slot_cam[j]].dy + FS2_H;
+                if (gx < 0 || gy < 0) return fail(SB_ERR_ASSERT, "fs2_build: gain tile of a camera that does not touch the tile");
+                // the inner coordinate of a tensor copy must be 16-byte aligned (x = -31 floats faults, -8 and -700 do not): the box
+                // is FS2_GAIN_W = 36 floats wide and starts at the multiple of 4 below gx; the consumers skip the first gx & 3 columns
+                const int gxa = gx & ~3;
+                o[1 + j].z |= (unsigned)(gx - gxa) << 28;
+                o[1 + FS2_MAXC + n_ops++] = make_uint4(slot_off + gain_off, ((unsigned)gxa & 0xffffu) | ((unsigned)gy << 16), (unsigned)slot_cam[j], 0xc0000000u);
+                slot_bytes = gain_off + FS2_GAIN_BYTES;
+                tx_bytes += FS2_GAIN_BYTES;
+            }
+            units += (slot_bytes + 127u) >> 7;
             tx_bytes += bytes;
             table_bytes += blk_bytes;
         }
@@ -302,6 +322,20 @@ int fs2_encode_tmaps(const void *src, size_t sstep, int sw, int sh, const unsign
     return SB_OK;
 }
 
+// a camera's resized block gain map (CV_32FC1 of the warped size + one tile of zero padding on the top and left) as a 2-D float tensor, box = one tile
+int fs2_encode_gain_tmap(const float *gmap, size_t step, int w, int h, CUtensorMap *out)
+{
+    PFN_tmap_encode enc = tmap_encoder();
+    if (!enc) return fail(SB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t gdim[2] = {(cuuint64_t)w, (cuuint64_t)h};
+    const cuuint64_t gstride[1] = {(cuuint64_t)step};
+    const cuuint32_t box[2] = {(cuuint32_t)FS2_GAIN_W, (cuuint32_t)FS2_H}, estr[2] = {1u, 1u};
+    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2u, const_cast<float *>(gmap), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %dx%d gain map, pitch %zu", (int)r, w, h, step);
+    return SB_OK;
+}
+
 // ------------------------------------------------------------------------------------ frame kernel
 struct Fs2Smem {
     unsigned char ring[FS2_RING_BYTES];
@@ -376,6 +410,19 @@ __device__ __forceinline__ float fs2_gain(const Fs2Cam &c, int X, int Y)
 {
     return c.gmap ? __ldg(reinterpret_cast<const float *>(reinterpret_cast<const char *>(c.gmap) + (size_t)(Y - c.dy) * c.gmstep) + (X - c.dx)) : c.gain;
 }
+// ... of the thread's 4 pixels: from the gain tile staged with the tile (rec = the camera slot's stage record), else as above
+__device__ __forceinline__ void fs2_gain4(const Fs2Args &a, const unsigned char *smb, const uint4 &rec, uint32_t gain_idx, int X, int Y, int nx, float (&g)[4])
+{
+    const Fs2Cam &c = a.cam[rec.w & 15u];
+    if (a.gain_tma) {                                       // rec.z = byte offset of the gain tile in the slot | columns to skip << 28
+        const float *t = reinterpret_cast<const float *>(smb + rec.x + (rec.z & 0x0fffffffu) + gain_idx) + (rec.z >> 28);
+        g[0] = t[0]; g[1] = t[1]; g[2] = t[2]; g[3] = t[3];
+        return;
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) g[p] = (c.gmap && p >= nx) ? 1.f : fs2_gain(c, X + p, Y);
+}
+
 // saturate_cast<uchar>(v * gain) for an 8-bit v: cvRound then clamp == clamp then round-half-even (rounding is monotonic), and
 // both conversions ride the FP32 pipe through the 2^23 constant instead of I2F / F2I (a quarter-rate unit that the 12 gain
 // products of a thread's 4 pixels would otherwise saturate): float(v) = bits(2^23 | v) - 2^23, rint(x) = low byte of bits(x + 2^23).
@@ -557,7 +604,12 @@ k_fs2(const __grid_constant__ Fs2Args a)
             // copies: lane 1 + FS2_MAXC + j issues copy j of the tile's list
             if (lane > FS2_MAXC && lane <= FS2_MAXC + n_ops) {
                 const uint32_t dst = ring0 + tile_off + d.x;
-                if (d.w & 0x80000000u) tma_load_2d(dst, tmaps + d.z, (int)(d.y & 0xffffu), (int)(d.y >> 16), &sm.full[stage]);
+                if (d.w & 0x80000000u) {                    // tensor copy: a source box, or (bit 30) a tile of the camera's gain map
+                    // (ONE copy instruction for both kinds: ptxas turned a second call site into a predicated UTMALDG that
+                    // faulted as an illegal instruction on B200)
+                    const CUtensorMap *m = (d.w & 0x40000000u) ? a.gtmap + d.z : tmaps + d.z;
+                    tma_load_2d(dst, m, (int)(d.y & 0xffffu), (int)(d.y >> 16), &sm.full[stage]);
+                }
                 else bulk_g2s_addr(dst, a.cam[d.w].blocks + d.y, d.z, &sm.full[stage]);
             }
             if (lane == 0) FS2_TRACE(5, gs);
@@ -570,6 +622,7 @@ k_fs2(const __grid_constant__ Fs2Args a)
     // rows 4w .. 4w+3, lane = (row << 3 | quad), a thread owns pixels 4*quad .. 4*quad+3 of its row
     const int grp = warp / FS2_GROUP_WARPS, slab = warp % FS2_GROUP_WARPS;
     const int ty = slab * 4 + (lane >> 3), tx = (lane & 7) * 4;
+    const uint32_t gain_idx = (uint32_t)(ty * FS2_GAIN_W + tx) * 4u;     // this thread's 4 gains inside a staged gain tile
     const uint32_t tab_off = (uint32_t)(ty * FS2_W + tx) * 4u, plane_off = (uint32_t)FS2_ENT_BYTES + (uint32_t)(ty * FS2_W + tx);
     const unsigned out_t = (unsigned)ty * a.out_step + (unsigned)tx * (OUT8 ? 3u : 6u), mask_t = (unsigned)ty * a.mask_step + (unsigned)tx;
     const int n_mine = (a.n_tiles - (int)blockIdx.x + G - 1) / G;
@@ -625,10 +678,11 @@ k_fs2(const __grid_constant__ Fs2Args a)
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty[stage]);   // this warp no longer reads the stage
             if (GAIN) {
-                const Fs2Cam &c = a.cam[rec.w & 15u];
+                float g4[4];
+                fs2_gain4(a, smb, rec, gain_idx, X, Y, nx, g4);
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
-                    const float g = (c.gmap && p >= nx) ? 1.f : fs2_gain(c, X + p, Y);
+                    const float g = g4[p];
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         unsigned q = fs2_apply_gain_b2(v[p][k], g);
@@ -665,7 +719,8 @@ k_fs2(const __grid_constant__ Fs2Args a)
                 const uint32_t e = *reinterpret_cast<const uint32_t *>(smb + rec.x + tab_off + 4u * p);
                 fs2_pixel<32768>(smb, rec.x + (uint32_t)FS2_BLOCK_BYTES, rec.y, e, v[p][0], v[p][1], v[p][2]);
                 if (GAIN) {
-                    const float g = fs2_gain(a.cam[rec.w & 15u], X + p, Y);
+                    const float g = a.gain_tma ? reinterpret_cast<const float *>(smb + rec.x + (rec.z & 0x0fffffffu) + gain_idx)[(rec.z >> 28) + p]
+                                               : fs2_gain(a.cam[rec.w & 15u], X + p, Y);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) v[p][k] = fs2_apply_gain_b2(v[p][k], g) << 16;
                 }
@@ -688,6 +743,8 @@ k_fs2(const __grid_constant__ Fs2Args a)
                 const unsigned d4 = *reinterpret_cast<const uint32_t *>(smb + rec.x + plane_off);
                 const uint32_t box = rec.x + (uint32_t)FS2_BLOCK_BYTES;
                 const uint32_t ee[4] = {e4.x, e4.y, e4.z, e4.w};
+                float g4[4] = {1.f, 1.f, 1.f, 1.f};
+                if (GAIN && a.gain_tma) fs2_gain4(a, smb, rec, gain_idx, X, Y, nx, g4);
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
                     const unsigned dist = (d4 >> (8 * p)) & 0xffu;      // 0: short(p * 0) == 0 and dst_w += 0 -> contributes nothing
@@ -697,7 +754,7 @@ k_fs2(const __grid_constant__ Fs2Args a)
                     fs2_pixel<32768>(smb, box, rec.y, ee[p], s0, s1, s2);
                     float f0, f1, f2;
                     if (GAIN) {                             // saturate_cast<uchar>(p * gain)
-                        const float g = (dist != 0u) ? fs2_gain(a.cam[rec.w & 15u], X + p, Y) : 1.f;
+                        const float g = a.gain_tma ? g4[p] : (dist != 0u) ? fs2_gain(a.cam[rec.w & 15u], X + p, Y) : 1.f;
                         // (the rounded product stays a float: bits(x + 2^23) - 2^23)
                         f0 = __fsub_rn(__uint_as_float(fs2_apply_gain_b2(s0, g) | 0x4b000000u), 8388608.f);
                         f1 = __fsub_rn(__uint_as_float(fs2_apply_gain_b2(s1, g) | 0x4b000000u), 8388608.f);

@@ -47,10 +47,12 @@ constexpr int FS2_W = 32, FS2_H = 32;                 // panorama tile
 constexpr int FS2_NCLS = 4;                           // source-box width classes (one tensor map per camera and class)
 constexpr int FS2_ROWS = SB_CFG_FS2_ROWS;             // box rows per tensor copy
 constexpr int FS2_MAX_OPS = 96 / FS2_ROWS;            // <= 96 box rows
-static_assert(1 + 3 + 3 * (1 + FS2_MAX_OPS) <= 16, "a tile's copy list must fit its descriptor");
+static_assert(1 + 3 + 3 * (2 + FS2_MAX_OPS) <= 16, "a tile's copy list must fit its descriptor");
 constexpr int FS2_MAX_BOX_W = 256;                    // TMA box dimension limit
 constexpr int FS2_ENT_BYTES = FS2_W * FS2_H * 4;      // tap entries of one (tile, camera)
 constexpr int FS2_BLOCK_BYTES = FS2_ENT_BYTES + FS2_W * FS2_H;   // + the weight-index plane (fetched only where cameras blend)
+constexpr int FS2_GAIN_W = FS2_W + 4;                 // ... fetched from a 16-byte aligned column: up to 3 leading columns are skipped
+constexpr int FS2_GAIN_BYTES = FS2_GAIN_W * FS2_H * 4; // a tile of a camera's resized block gain map (SB_COMP_GAIN_BLOCKS)
 constexpr int FS2_MAXC = 3;
 constexpr int FS2_DESC_RECS = 16;                      // 16-byte records per tile descriptor: 1 + FS2_MAXC + the tile's copy list                           // cameras with weight inside one tile (more -> k_feather_fused_px1)
 constexpr int FS2_GROUPS = SB_CFG_FS2_GROUPS;         // consumer groups (8 warps each) per CTA, each on its own tile
@@ -60,7 +62,7 @@ constexpr int FS2_CTAS_PER_SM = SB_CFG_FS2_CTAS_PER_SM;
 constexpr int FS2_RING_BYTES = SB_CFG_FS2_RING_KB * 1024;
 constexpr int FS2_PRODUCERS = SB_CFG_FS2_PRODUCERS;   // producer warps, each on its own tile
 constexpr int FS2_THREADS = (FS2_GROUPS * FS2_GROUP_WARPS + FS2_PRODUCERS) * 32;
-static_assert(FS2_MAXC * (FS2_BLOCK_BYTES + FS2_MAX_BOX_W * FS2_ROWS * FS2_MAX_OPS) <= FS2_RING_BYTES, "one tile must fit the ring");
+static_assert(FS2_MAXC * (FS2_BLOCK_BYTES + FS2_MAX_BOX_W * FS2_ROWS * FS2_MAX_OPS + FS2_GAIN_BYTES) <= FS2_RING_BYTES, "one tile must fit the ring");
 
 struct Fs2Cam {
     const unsigned char *blocks;   // tile-major table blocks of this camera (FS2_BLOCK_BYTES each)
@@ -79,6 +81,8 @@ struct alignas(128) Fs2Frame {
 };
 struct alignas(64) Fs2Args {
     CUtensorMap tmap[FS2_TMAP_CAMS * FS2_NCLS];     // source image of camera i as a 2-D byte tensor, box = cls_w[c] x FS2_ROWS
+    CUtensorMap gtmap[FS2_TMAP_CAMS];               // SB_COMP_GAIN_BLOCKS: camera i's resized gain map as a 2-D float tensor, box = one tile
+    int gain_tma;                                   // gain tiles arrive with the tile (else: read from global memory per pixel)
     Fs2Cam cam[SB_MAX_CAMERAS];
     const uint4 *desc;             // per tile in schedule order, CTA-major: FS2_DESC_RECS records (kernels_fstream2.cu)
     unsigned cls_w[FS2_NCLS];
@@ -116,6 +120,7 @@ struct Fs2Plan {                    // host-side result of the setup: what the c
     int n_tiles = 0, grid = 0, per_cta = 0;
     double table_bytes = 0;         // bytes of table blocks one frame fetches (algorithmic bytes of the table stream)
     bool ok = false;
+    bool gain_tma = false;          // the descriptors carry a gain-tile copy per camera slot
     bool steady = false;            // the ring plan of frames >= 1 of a multi-frame launch is cyclic (else the ring is drained between frames)
 };
 
@@ -129,7 +134,8 @@ struct Fs2CamSetup {               // one camera as the setup sees it
 int fs2_grid(int n_tiles, int sm_count);
 // the whole per-calibration setup; plan->ok == false: this calibration needs k_feather_fused_px1 (too many cameras per
 // tile, a source box the ring cannot stage, or a sharpness below 1/255)
-int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, int sm_count, DevBuf &desc_out, Fs2Plan *plan, cudaStream_t s);
+int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, int sm_count, bool gain_maps, DevBuf &desc_out, Fs2Plan *plan, cudaStream_t s);
+int fs2_encode_gain_tmap(const float *gmap, size_t step, int w, int h, CUtensorMap *out);
 // setup, per camera: bounding boxes of the tile blocks covering the camera's warped rect (row-major feather table in)
 int launch_fs2_bbox(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int tx0, int ty0, int ntx, int nty,
                     float sharpness, Fs2Box *boxes, cudaStream_t s);
