@@ -6,7 +6,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-path = os.environ.setdefault("SB_FS2_TRACE", "gpurun_out/fs2_trace.bin")
+path = os.environ.setdefault("SB_FS2_TRACE", "gpurun_out/fs2_trace.bin")      # needs a library built with -DSB_FS2_TRACE (STITCHB200_LIB=variants/...)
 import torch                               # noqa: E402
 import stitchingvideo_b200 as sv          # noqa: E402
 from stitchingvideo_b200 import capi, rigs      # noqa: E402

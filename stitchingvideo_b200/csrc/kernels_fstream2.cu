@@ -512,18 +512,25 @@ __device__ __forceinline__ void fs2_store_mask(uint8_t *m, unsigned word, bool e
         if (p < nx) m[p] = (uint8_t)(word >> (8 * p));
 }
 
-// Pipeline trace (debugging aid, off unless the environment variable SB_FS2_TRACE names a file): per CTA and tile four
-// timestamps - copies issued, consumer group starts waiting, data landed, tile finished.
+// Pipeline trace (debugging aid; builds with -DSB_FS2_TRACE only - scripts/build_variant.sh trace "-DSB_FS2_TRACE" - and then
+// active when the environment variable SB_FS2_TRACE names a file): per CTA and tile the timestamps copies issued / consumer
+// group starts waiting / data landed / tile finished / producer reaches the tile / producer done with it.
 __device__ __forceinline__ unsigned long long fs2_now()
 {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+#ifdef SB_FS2_TRACE
 #define FS2_TRACE(SLOT, SEQ)                                                                        \
     do {                                                                                            \
         if (a.trace && (SEQ) < FS2_TRACE_TILES) a.trace[((size_t)blockIdx.x * FS2_TRACE_TILES + (SEQ)) * 8 + (SLOT)] = fs2_now(); \
     } while (0)
+#define FS2_DEBUG_SUPPLY_ONLY (a.debug == 1)
+#else
+#define FS2_TRACE(SLOT, SEQ) do { } while (0)
+#define FS2_DEBUG_SUPPLY_ONLY false
+#endif
 constexpr int FS2_TRACE_TILES = 64;
 
 // NOBLEND: Blender::feed / blend without blending (blenders.cpp:81-112): the pixel of the LAST camera (feed order)
@@ -643,7 +650,7 @@ k_fs2(const __grid_constant__ Fs2Args a)
         if (tid % (FS2_GROUP_WARPS * 32) == 0) FS2_TRACE(1, seq);
         mbar_wait_hw(&sm.full[stage], (unsigned)(seq / FS2_STAGES) & 1u);
         if (tid % (FS2_GROUP_WARPS * 32) == 0) FS2_TRACE(2, seq);
-        if (a.debug == 1) {                                  // tuning experiment: the supply side alone (results are garbage)
+        if (FS2_DEBUG_SUPPLY_ONLY) {                         // tuning experiment (trace builds): the supply side alone (results are garbage)
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty[stage]);
             continue;
