@@ -1,6 +1,6 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
-for lib in default variants/libstitchb200_noconf.so variants/libstitchb200_nostore.so variants/libstitchb200_both.so; do
+for lib in default $(ls variants/*.so); do
  for dbg in 0; do for NS in 8; do export NSETS=$NS;
   if [ "$lib" = default ]; then unset STITCHB200_LIB; else export STITCHB200_LIB=$PWD/$lib; fi
   SB_FS2_DEBUG=$dbg python - "$lib" $dbg <<'PY'

@@ -15,6 +15,7 @@ int fail(int code, const char *fmt, ...)
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
     g_last_error = buf;
+    if (code == SB_ERR_CUDA) cudaGetLastError();   // a reported CUDA error must not resurface at the next launch check of an unrelated call
     return code;
 }
 

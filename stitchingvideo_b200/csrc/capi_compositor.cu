@@ -1334,12 +1334,24 @@ static int enqueue_on_slot(sb_compositor *c, Slot &s, const sb_image *srcs, sb_i
     s.want_mask = pano_mask != nullptr;
     SB_TRY(undistort_stage(c, s, srcp));
     const std::vector<DImage> src(srcp, srcp + n);
-    SB_TRY(run_frame(c, s, src));
+    // A caller's panorama that already lives on this device is written in place by the frame's last kernel (no 2 x 20 MB
+    // device-to-device copy behind it) when its pitch and alignment suit that kernel's vector stores.
+    auto in_place = [&](const sb_image *u, const DImage &own, size_t align) {
+        return u && u->data && u->device == c->device && c->strip_world == 1 && u->rows == own.rows && u->cols == own.cols && u->type == own.type &&
+               u->step % align == 0 && reinterpret_cast<uintptr_t>(u->data) % 16 == 0;
+    };
+    const DImage own_out = s.out.v, own_mask = s.out_mask.v;
+    const bool direct = in_place(pano, own_out, 8), direct_mask = direct && in_place(pano_mask, own_mask, 4);
+    if (direct) { s.out.v.data = pano->data; s.out.v.step = pano->step; }
+    if (direct_mask) { s.out_mask.v.data = pano_mask->data; s.out_mask.v.step = pano_mask->step; }
+    const int rc = run_frame(c, s, src);
+    s.out.v = own_out; s.out_mask.v = own_mask;
+    SB_TRY(rc);
     if (!pano->data) lend(s.out.v, c->device, pano);
-    else SB_TRY(from_device(s.out.v, pano, s.stream));
+    else if (!direct) SB_TRY(from_device(s.out.v, pano, s.stream));
     if (pano_mask) {
         if (!pano_mask->data) lend(s.out_mask.v, c->device, pano_mask);
-        else SB_TRY(from_device(s.out_mask.v, pano_mask, s.stream));
+        else if (!direct_mask) SB_TRY(from_device(s.out_mask.v, pano_mask, s.stream));
     }
     if (timing) SB_CUDA(cudaEventRecord(s.ev_stop, s.stream));
     return SB_OK;

@@ -122,3 +122,35 @@ def test_multi_device_driver(gpu):
         assert np.array_equal(pano, ref) and np.array_equal(mask, rmask), "frame %d" % f
     with pytest.raises(gpu.StitchError):
         gpu.MultiCompositor([0, 99], 1, size, Ks, Rs, warper="cylindrical", scale=spec["scale"], blender="feather")     # no such device: an error, not a downgrade
+
+
+@pytest.mark.parametrize("rig,blender,variants", [("mini", "multiband", (0, 10, 11, 12, 13, 14)), ("mini_cyl", "feather", (0, 10, 11, 15)),
+                                                  ("mini_cyl", "no", (0, 11, 15))])
+@pytest.mark.parametrize("out16", [False, True])
+def test_device_panorama_is_written_in_place(gpu, rig, blender, variants, out16):
+    """enqueue() with a panorama that already lives on the device: the frame's last kernel writes it directly (aligned pitch)
+    or it is copied (odd pitch) - the same pixels as the oracle either way, for every kernel variant, and nothing outside the
+    panorama's columns is touched."""
+    import torch
+    from stitchingvideo_b200 import capi
+    Ks, Rs, spec = rigs.cameras(rig)
+    size, n = (spec["W"], spec["H"]), spec["n_used"]
+    gains = ([0.95, 1.02, 1.0, 0.98, 1.05] * 2)[:n]
+    otype = gpu.CV_16SC3 if out16 else gpu.CV_8UC3
+    comp = gpu.Compositor(size, Ks, Rs, warper=spec["warper"], scale=spec["scale"], blender=blender, gains=gains, output_type=otype)
+    cal = P.Calibration(size, Ks, Rs, spec["warper"], spec["scale"])
+    frames = [rigs.frame(rig, 1, i) for i in range(n)]
+    ref, ref_mask = P.compose(cal, frames, blender=blender, gains=gains, output_8u=not out16)
+    w, h = comp.pano_size
+    esz = 6 if out16 else 3
+    for v in variants:
+        comp.set_fused(v)
+        for wp in ((w + 7) & ~7, w + 3):                      # in place / through the copy
+            t = torch.full((h, wp, 3), 77, dtype=torch.int16 if out16 else torch.uint8, device="cuda")
+            m = torch.full((h, wp), 77, dtype=torch.uint8, device="cuda")
+            pano = capi.DeviceImage(t.data_ptr(), h, w, otype, wp * esz, 0, owner=t)
+            mask = capi.DeviceImage(m.data_ptr(), h, w, gpu.CV_8UC1, wp, 0, owner=m)
+            comp.wait(comp.enqueue(frames, pano, mask))
+            assert np.array_equal(t[:, :w].cpu().numpy(), ref), "variant %d pitch %d" % (v, wp)
+            assert np.array_equal(m[:, :w].cpu().numpy(), ref_mask), "variant %d pitch %d (mask)" % (v, wp)
+            assert (t[:, w:] == 77).all() and (m[:, w:] == 77).all(), "variant %d pitch %d: wrote outside the panorama" % (v, wp)
