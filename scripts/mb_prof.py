@@ -9,7 +9,8 @@ rig = sys.argv[1] if len(sys.argv) > 1 else "c3"
 Ks, Rs, spec = rigs.cameras(rig); n = spec["n_used"]
 comp = sv.Compositor((spec["W"], spec["H"]), Ks, Rs, warper=spec["warper"], scale=spec["scale"], blender=spec["blender"], gains=spec["gain_values"])
 sets = [[capi.DeviceImage.from_torch(torch.from_numpy(rigs.frame(rig, s, i)).cuda()) for i in range(n)] for s in range(8)]
-for mode in (11, 12):
+modes = [int(m) for m in sys.argv[2].split(',')] if len(sys.argv) > 2 else [11, 12]
+for mode in modes:
     comp.set_fused(mode)
     for it in range(3):
         recs = comp.profile_frame(sets[it % 4])

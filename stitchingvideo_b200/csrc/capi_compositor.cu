@@ -45,6 +45,8 @@ struct Camera {
     DevBuf mb_table;             // multi-band fast path: resolved bilinear taps per padded-rect pixel (8 B)
     size_t mb_tstep = 0;
     DevBuf mbs_tiles, mbs_rec;   // the same taps tile-major + per-tile source boxes (streaming warp stage, kernels_mb_stream.cu)
+    DevBuf mbf_blocks;           // ... and as k_fs2 table blocks (4-byte entries; the warp stage on the frame kernel of the feather path)
+    int mbf_dy = 0;              // first row of this camera's plane in the stacked coordinate system of that launch
     int mbs_ntx = 0, mbs_nty = 0;
     size_t feather_tstep = 0;
     DevBuf feather_tiles;        // the same table tile-major (one 8 KB block per 32x32 panorama tile) for the streaming kernel
@@ -149,6 +151,10 @@ struct sb_compositor {
     int mbs_x0 = 0, mbs_x1 = 0;
     bool mbs_enabled = true;                     // tuning hook (set_fused 12 keeps the gather kernel)
     DevBuf mbs_desc;                             // tile descriptors in schedule order with the ring plan
+    Fs2Plan mbf;                                 // the warp stage as a k_fs2 launch over per-camera output planes (mb_fs2_setup)
+    DevBuf mbf_desc;
+    int mbf_pw = 0, mbf_ph = 0;
+    bool mbf_enabled = true;                     // tuning hook (set_fused 17 keeps the round-1 streaming kernel)
     int mbs_n_tiles = 0;
     bool fused = true;                           // panorama-centric fused kernels (default); false = staged reference-shaped path
     // latency ("strip") mode: this handle produces padded-panorama columns [strip_x0, strip_x1)
@@ -307,6 +313,46 @@ void clip_runs(const std::array<int, 4> &g, int rx, int x0, int x1, int out[4], 
         *max_col = std::max(*max_col, b);
         *cols += b - a;
     }
+}
+
+// The multi-band warp stage on the frame kernel of the feather path (k_fs2, out_mode 2).  Every camera's padded feed rect is
+// an output plane; the planes are stacked vertically (heights rounded up to whole tiles) into the coordinate system the k_fs2
+// setup works in, so each of its tiles sees exactly one camera, "Blender::NO" semantics produce the plane's pixels, and the
+// mask byte says which pixels the pyramid needs (the level-0 column runs).  Whole-frame launches only: a latency-mode strip
+// keeps the streaming kernel with its per-strip schedule.
+int mb_fs2_setup(sb_compositor *c, cudaStream_t s)
+{
+    c->mbf = Fs2Plan{};
+    const int n = c->cfg.n_cameras;
+    if (n > FS2_TMAP_CAMS || n > 16 || c->cfg.src_size.width * 3 > 65535) return SB_OK;
+    int pw = 0, ph = 0;
+    for (int i = 0; i < n; ++i) {
+        Camera &cam = c->cams[i];
+        cam.mbf_dy = ph;
+        ph += div_up(cam.rh, FS2_H) * FS2_H;
+        pw = std::max(pw, cam.rw);
+    }
+    if (pw >= 65536 || ph >= 65536) return SB_OK;
+    std::vector<Fs2CamSetup> cs(n);
+    std::vector<DevBuf> tabs(n);
+    for (int i = 0; i < n; ++i) {
+        Camera &cam = c->cams[i];
+        int cx[4], cmax = 0;
+        double cols = 0;
+        clip_runs(cam.g_runs[0], cam.rx, 0, c->wsum[0].v.cols, cx, &cmax, &cols);
+        const size_t tstep = ((size_t)cam.rw * sizeof(uint2) + 255) & ~(size_t)255;
+        SB_TRY(tabs[i].ensure(tstep * cam.rh));
+        SB_TRY(launch_mbs_feather_format(static_cast<const uint2 *>(cam.mb_table.p), cam.mb_tstep, cam.rw, cam.rh, cx, static_cast<uint2 *>(tabs[i].p), tstep, s));
+        Fs2CamSetup &f = cs[i];
+        f.table = static_cast<const uint2 *>(tabs[i].p); f.tstep = tstep;
+        f.ww = cam.rw; f.wh = cam.rh; f.dx = 0; f.dy = cam.mbf_dy;
+        f.tx0 = 0; f.ty0 = cam.mbf_dy / FS2_H; f.ntx = div_up(cam.rw, FS2_W); f.nty = div_up(cam.rh, FS2_H);
+        SB_TRY(cam.mbf_blocks.ensure((size_t)f.ntx * f.nty * FS2_BLOCK_BYTES));
+        f.blocks = static_cast<unsigned char *>(cam.mbf_blocks.p);
+    }
+    SB_TRY(fs2_build(cs.data(), n, pw, ph, 1.f / 255.f, c->sm_count, false, c->mbf_desc, &c->mbf, s, true));
+    c->mbf_pw = pw; c->mbf_ph = ph;
+    return SB_OK;
 }
 
 // Tile schedule of the streaming warp stage (kernels_mb_stream.cu) for the panorama columns [x0, x1): the tiles of every
@@ -528,6 +574,7 @@ int setup(sb_compositor *c)
                 }
                 c->mbs_tables = ok;
                 SB_TRY(build_mbs_schedule(c, 0, c->wsum[0].v.cols, s));
+                if (ok) SB_TRY(mb_fs2_setup(c, s));
             }
             c->mb_tile_mask.resize(nb + 1);
             for (int l = 0; l <= nb; ++l) {
@@ -668,6 +715,8 @@ double img_bytes(const DImage &d) { return (double)d.rows * d.cols * elem_size(d
 // ---- the multi-band fast path, stage by stage.  [x0, x1) is the range of padded-panorama columns (level-0
 // coordinates, multiples of 2^num_bands) this call produces: the whole width for a frame on one GPU, one
 // column strip in latency mode, where the host exchanges halo columns between the stages.
+int fs2_tmaps(sb_compositor *c, int i, const DImage &src, CUtensorMap *out);
+
 int mb_warp_stage(sb_compositor *c, Slot &s, const std::vector<DImage> &src, int x0, int x1)
 {
     // K1: remap + gain + convertTo(16S) + copyMakeBorder for every camera, one launch
@@ -697,6 +746,30 @@ int mb_warp_stage(sb_compositor *c, Slot &s, const std::vector<DImage> &src, int
     if (mw == 0) return SB_OK;
     bool aligned = true;                                     // cp.async source boxes: 16-byte aligned rows
     for (int i = 0; i < n; ++i) aligned = aligned && (reinterpret_cast<uintptr_t>(src[i].data) & 15) == 0 && (src[i].step & 15) == 0;
+    if (c->mbf.ok && c->mbf_enabled && c->mbs_enabled && aligned && c->strip_world == 1 && x0 <= 0 && x1 >= c->wsum[0].v.cols) {
+        Fs2Args fa{};
+        fa.n = n;
+        double fbytes = c->mbf.table_bytes;
+        for (int i = 0; i < n; ++i) {
+            const Camera &cam = c->cams[i];
+            Fs2Cam &fc = fa.cam[i];
+            fc.blocks = static_cast<const unsigned char *>(cam.mbf_blocks.p);
+            fc.gain = cam.gain; fc.dx = 0; fc.dy = cam.mbf_dy;
+            fc.gmap = a.cam[i].gmap; fc.gmstep = (unsigned)a.cam[i].gmstep;
+            fc.mb_out = reinterpret_cast<unsigned char *>(a.cam[i].g0); fc.mb_step = (unsigned)a.cam[i].gstep;
+            fc.ow = cam.rw; fc.oh = cam.rh;
+            SB_TRY(fs2_tmaps(c, i, src[i], &fa.tmap[i * FS2_NCLS]));
+            const double cols = (a.cam[i].cx[1] - a.cam[i].cx[0]) + (a.cam[i].cx[3] - a.cam[i].cx[2]);
+            fbytes += img_bytes(src[i]) * std::min(1.0, cols / (double)std::min(cam.ww, src[i].cols)) + cols * cam.rh * 4;
+        }
+        fa.desc = static_cast<const uint4 *>(c->mbf_desc.p);
+        for (int k = 0; k < FS2_NCLS; ++k) fa.cls_w[k] = c->mbf.cls_w[k];
+        fa.sharpness = 1.f / 255.f; fa.no_blend = 1;
+        fa.pw = c->mbf_pw; fa.ph = c->mbf_ph;
+        fa.n_tiles = c->mbf.n_tiles; fa.per_cta = c->mbf.per_cta;
+        PROF("mb_warp", fbytes, launch_fs2(fa, c->cfg.comp_kind != SB_COMP_NO, 2, c->mbf.grid, st));
+        return SB_OK;
+    }
     if (c->mbs_ok && c->mbs_enabled && aligned && c->mbs_x0 <= std::max(x0, 0) && std::min(x1, c->wsum[0].v.cols) <= c->mbs_x1) {
         MbStreamArgs sa{};
         sa.n = n;
@@ -900,8 +973,13 @@ int mb_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src, const in
 {
     const int nb = c->num_bands;
     SB_TRY(mb_warp_stage(c, s, src, g_lo[0], g_hi[0]));
-    if (c->mb_multilevel < 0 && nb >= 2 && nb <= SB_MB_MAX_FUSED_LEVELS && c->strip_world == 1) {
-        // default: warp, pyrDown 0 -> 1, every coarser level and every band but the last in one launch, the final band
+    // One frame in flight (latency): warp, pyrDown 0 -> 1, every coarser level and every band but the last in ONE launch
+    // (k_mb_coarse), the final band: 4 launches.  Several frames in flight (throughput): one launch per level - the
+    // latency-bound coarse levels of one frame then hide behind the heavy kernels of the others without a resident
+    // grid of waiting CTAs in their way (measured, C3, 8 in flight: 119 vs 134 us per frame).  set_fused(16) forces the
+    // former, set_fused(12) the latter.
+    const bool coarse = c->mb_multilevel == 2 || (c->mb_multilevel < 0 && c->slots.size() == 1);
+    if (coarse && nb >= 2 && nb <= SB_MB_MAX_FUSED_LEVELS && c->strip_world == 1) {
         SB_TRY(mb_down_stage(c, s, 0, g_lo[1], g_hi[1]));
         SB_TRY(mb_coarse(c, s, 1, 1, g_lo, g_hi, b_lo, b_hi));
         SB_TRY(mb_band_stage(c, s, 0, b_lo[0], b_hi[0]));
@@ -956,7 +1034,7 @@ int fs2_tmaps(sb_compositor *c, int i, const DImage &src, CUtensorMap *out)
         if (cam.tmaps.size() < 32) { cam.tmaps.emplace_back(); hit = &cam.tmaps.back(); }
         else hit = lru;
         hit->p = src.data; hit->step = src.step;
-        SB_TRY(fs2_encode_tmaps(src.data, src.step, src.cols, src.rows, c->fs2.cls_w, hit->m));
+        SB_TRY(fs2_encode_tmaps(src.data, src.step, src.cols, src.rows, c->fs2.ok ? c->fs2.cls_w : c->mbf.cls_w, hit->m));
     }
     hit->stamp = ++c->tmap_clock;
     std::memcpy(out, hit->m, sizeof hit->m);
@@ -1257,8 +1335,9 @@ int sb_compositor_set_fused(sb_compositor *c, int fused)
     if (fused >= 10) {   // 10: CV_16S band kernels / px1 feather; 11: fast paths (default); 12 / 13: fast paths with one launch per
         // pyramid level / with the multi-level launches forced; 14: fast paths with the gather warp stage
         c->feather_variant = fused == 10 ? 0 : fused == 15 ? 3 : 1; c->mb_variant = fused == 10 ? 0 : 1;   // 15: the round-1 feather streaming kernel
-        c->mb_multilevel = fused == 12 ? 0 : fused == 13 ? 1 : -1;
+        c->mb_multilevel = fused == 12 ? 0 : fused == 13 ? 1 : fused == 16 ? 2 : -1;   // 16: k_mb_coarse whatever the number of frames in flight
         c->mbs_enabled = fused != 14;                        // 14: default fast paths with the gather form of the multi-band warp stage
+        c->mbf_enabled = fused != 17;                        // 17: ... with the round-1 streaming kernel (k_mb_warp_stream) as the warp stage
     }   // test/tuning hook: 10 / 11 select the kernel variant
     return SB_OK;
 }

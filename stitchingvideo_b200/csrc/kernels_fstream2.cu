@@ -117,7 +117,8 @@ int fs2_grid(int n_tiles, int sm_count) { return std::min(n_tiles, FS2_CTAS_PER_
 //   [4 + j] = copy j of the tile: {destination byte offset inside the tile's ring space,
 //             bulk copy: byte offset of the table block in the camera's blocks, bytes, camera
 //             tensor copy: box x (byte) | box y << 16, tensor map index (camera * FS2_NCLS + class), bit 31 set}
-int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, int sm_count, bool gain_maps, DevBuf &desc_out, Fs2Plan *plan, cudaStream_t s)
+int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, int sm_count, bool gain_maps, DevBuf &desc_out, Fs2Plan *plan, cudaStream_t s,
+              bool drop_empty)
 {
     *plan = Fs2Plan{};
     const unsigned cls_w[FS2_NCLS] = {96u, 160u, 224u, 256u};      // pitches of 32 (mod 128) bytes keep the 4 tile rows of a warp on distinct banks
@@ -128,7 +129,8 @@ int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, i
     plan->gain_tma = gain_tma;
     // the weight index is one byte: the weight must saturate by distance 255 (Blender::NO: the mask byte itself)
     if (!(sharpness > 0.f) || fminf((float)(255.f * sharpness), 1.f) != 1.f) return SB_OK;
-    const int tiles_x = div_up(pw, FS2_W), tiles_y = div_up(ph, FS2_H), n_tiles = tiles_x * tiles_y;
+    const int tiles_x = div_up(pw, FS2_W), tiles_y = div_up(ph, FS2_H);
+    int n_tiles = tiles_x * tiles_y;
     std::vector<std::vector<Fs2Box>> boxes(n);
     std::vector<std::vector<Fs2Place>> places(n);
     DevBuf tmp;
@@ -216,7 +218,6 @@ int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, i
     // Schedule order: CTA b takes positions b, b + G, ... of the descriptor array, so listing the tiles by descending cost
     // (blended tiles with 3, 2, 1 cameras, then the single-camera short-path tiles, then empty ones; row-major inside a
     // class) deals every CTA the same number of tiles of each class, the expensive ones first ...
-    const int grid = fs2_grid(n_tiles, sm_count);
     std::vector<int> order(n_tiles);
     for (int t = 0; t < n_tiles; ++t) order[t] = t;
     auto cost = [&](int t) {
@@ -225,6 +226,14 @@ int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, i
         return nc == 0 ? 0 : (x & 4u) ? 1 : 1 + nc;
     };
     std::stable_sort(order.begin(), order.end(), [&](int l, int r) { return cost(l) > cost(r); });
+    if (drop_empty) {            // output planes: tiles no camera feeds are not part of any plane - they leave the schedule
+        while (!order.empty() && cost(order.back()) == 0) order.pop_back();
+        if (order.empty()) return SB_OK;
+    }
+    const int n_all = n_tiles;
+    n_tiles = (int)order.size();
+    (void)n_all;
+    const int grid = fs2_grid(n_tiles, sm_count);
     // ... except that every CTA's FIRST tiles are cheap ones: the first wave of copies is what the consumers wait for at
     // kernel start, and a one-camera tile is 2-3x fewer bytes
     if (n_tiles >= 2 * grid * FS2_GROUPS) std::rotate(order.begin(), order.end() - (size_t)grid * FS2_GROUPS, order.end());
@@ -419,8 +428,9 @@ __device__ __forceinline__ void fs2_gain4(const Fs2Args &a, const unsigned char 
         g[0] = t[0]; g[1] = t[1]; g[2] = t[2]; g[3] = t[3];
         return;
     }
+    if (!c.gmap) { g[0] = g[1] = g[2] = g[3] = c.gain; return; }      // GainCompensator: one scalar per camera
 #pragma unroll
-    for (int p = 0; p < 4; ++p) g[p] = (c.gmap && p >= nx) ? 1.f : fs2_gain(c, X + p, Y);
+    for (int p = 0; p < 4; ++p) g[p] = p >= nx ? 1.f : fs2_gain(c, X + p, Y);
 }
 
 // saturate_cast<uchar>(v * gain) for an 8-bit v: cvRound then clamp == clamp then round-half-even (rounding is monotonic), and
@@ -443,7 +453,7 @@ __device__ __forceinline__ unsigned fs2_apply_gain_b2(unsigned s, float g)
 
 // crop_app_fill: camera 0's warped pixel (0, 0), sampled from its frame in global memory (rare: only pixels no camera covers)
 template <bool GAIN>
-__device__ __noinline__ void fs2_fill_pixel(const Fs2Args &a, const uint8_t *src0, unsigned sstep0, unsigned &s0, unsigned &s1, unsigned &s2)
+__device__ __noinline__ uint3 fs2_fill_pixel(const Fs2Args &a, const uint8_t *src0, unsigned sstep0)      // (by value: references would pin the caller's pixel registers to the stack)
 {
     const unsigned tex = a.fill_tex[0], fxy = a.fill_tex[1] & 1023u;
     const unsigned x0 = tex & 0x1fffu, y0 = (tex >> 13) & 0x1fffu;
@@ -459,7 +469,7 @@ __device__ __noinline__ void fs2_fill_pixel(const Fs2Args &a, const uint8_t *src
         const float g = fs2_gain(a.cam[0], a.cam[0].dx, a.cam[0].dy);
         v0 = (int)fs2_apply_gain((unsigned)v0, g); v1 = (int)fs2_apply_gain((unsigned)v1, g); v2 = (int)fs2_apply_gain((unsigned)v2, g);
     }
-    s0 = (unsigned)v0 << 16; s1 = (unsigned)v1 << 16; s2 = (unsigned)v2 << 16;
+    return make_uint3((unsigned)v0 << 16, (unsigned)v1 << 16, (unsigned)v2 << 16);
 }
 
 // The 4 pixels x 3 channels of one thread, each value in byte B of its register (the byte above it zero), as the 12 (8UC3)
@@ -500,6 +510,24 @@ __device__ __forceinline__ void fs2_store_quad(unsigned char *o, const unsigned 
         }
     }
 }
+// ... as 4 RGBX words (multi-band Gaussian level 0): one 16-byte store per thread
+template <int B>
+__device__ __forceinline__ void fs2_store_rgbx(unsigned char *o, const unsigned (&v)[4][3], bool edge, int nx, bool row_ok)
+{
+    constexpr unsigned S = (unsigned)B | ((unsigned)(B + 4) << 4);           // [v0.B, v1.B, -, -]
+    constexpr unsigned T = 0x0010u | ((unsigned)(B + 4) << 8) | ((unsigned)(4 + ((B + 1) & 3)) << 12);   // [lo.0, lo.1, v2.B, 0 (a masked-off byte of v2)]
+    uint4 w;
+    w.x = __byte_perm(__byte_perm(v[0][0], v[0][1], S), v[0][2] & (0xffu << (8 * B)), T);
+    w.y = __byte_perm(__byte_perm(v[1][0], v[1][1], S), v[1][2] & (0xffu << (8 * B)), T);
+    w.z = __byte_perm(__byte_perm(v[2][0], v[2][1], S), v[2][2] & (0xffu << (8 * B)), T);
+    w.w = __byte_perm(__byte_perm(v[3][0], v[3][1], S), v[3][2] & (0xffu << (8 * B)), T);
+    if (!edge) { *reinterpret_cast<uint4 *>(o) = w; return; }
+    if (!row_ok) return;
+    const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+        if (p < nx) reinterpret_cast<uint32_t *>(o)[p] = ws[p];
+}
 __device__ __forceinline__ void fs2_store_mask(uint8_t *m, unsigned word, bool edge, int nx, bool row_ok)
 {
 #ifdef SB_FS2_EXPERIMENT_NOSTORE
@@ -535,10 +563,17 @@ constexpr int FS2_TRACE_TILES = 64;
 
 // NOBLEND: Blender::feed / blend without blending (blenders.cpp:81-112): the pixel of the LAST camera (feed order)
 // whose mask is non-zero, dst_mask = OR of the mask bytes, 0 where no camera has a mask.
-template <bool GAIN, bool OUT8, bool NOBLEND>
+// OUT: 0 = CV_16SC3 panorama, 1 = CV_8UC3 panorama, 2 (with NOBLEND) = the multi-band path's first stage: every "camera" is
+// its own output plane (Gaussian level 0 of the camera's padded feed rect as RGBX words, Fs2Cam::mb_out), the "panorama" only
+// the coordinate system the planes are stacked in (capi_compositor.cu: mb_fs2_setup).
+template <bool GAIN, int OUT, bool NOBLEND>
 __global__ void __launch_bounds__(FS2_THREADS, FS2_CTAS_PER_SM)
 k_fs2(const __grid_constant__ Fs2Args a)
 {
+    constexpr bool OUT8 = OUT == 1;
+    constexpr bool PLANES = OUT == 2;
+    constexpr unsigned PX = OUT == 0 ? 6u : OUT == 1 ? 3u : 4u;
+    static_assert(!PLANES || NOBLEND, "per-camera output planes exist only without blending");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Fs2Smem &sm = *reinterpret_cast<Fs2Smem *>(smem_raw);
     const unsigned char *const smb = smem_raw;
@@ -594,7 +629,7 @@ k_fs2(const __grid_constant__ Fs2Args a)
                 uint4 ds = d;
                 if (lane == 0) {                            // tile origin -> byte offsets of its first pixel in the panorama and the mask
                     const unsigned X0 = d.y & 0xffffu, Y0 = d.y >> 16;
-                    ds.z = Y0 * a.out_step + X0 * (OUT8 ? 3u : 6u); ds.w = Y0 * a.mask_step + X0;
+                    ds.z = Y0 * a.out_step + X0 * PX; ds.w = Y0 * a.mask_step + X0;
                 } else {
                     ds.x += tile_off;                       // the slot's byte offset in the ring
                 }
@@ -631,7 +666,7 @@ k_fs2(const __grid_constant__ Fs2Args a)
     const int ty = slab * 4 + (lane >> 3), tx = (lane & 7) * 4;
     const uint32_t gain_idx = (uint32_t)(ty * FS2_GAIN_W + tx) * 4u;     // this thread's 4 gains inside a staged gain tile
     const uint32_t tab_off = (uint32_t)(ty * FS2_W + tx) * 4u, plane_off = (uint32_t)FS2_ENT_BYTES + (uint32_t)(ty * FS2_W + tx);
-    const unsigned out_t = (unsigned)ty * a.out_step + (unsigned)tx * (OUT8 ? 3u : 6u), mask_t = (unsigned)ty * a.mask_step + (unsigned)tx;
+    const unsigned out_t = (unsigned)ty * a.out_step + (unsigned)tx * PX, mask_t = (unsigned)ty * a.mask_step + (unsigned)tx;
     const int n_mine = (a.n_tiles - (int)blockIdx.x + G - 1) / G;
     const int total = n_mine * max(a.n_frames, 1);
     unsigned char *out_f = reinterpret_cast<unsigned char *>(a.out);
@@ -659,10 +694,19 @@ k_fs2(const __grid_constant__ Fs2Args a)
         const int nc = (int)(d0.x & 3u);
         const bool edge = (d0.x & 8u) != 0u;                // block-uniform: the tile crosses the panorama's right / bottom edge
         const int X = (int)(d0.y & 0xffffu) + tx, Y = (int)(d0.y >> 16) + ty;
-        const int nx = edge ? min(max(a.pw - X, 0), 4) : 4;
-        const bool row_ok = !edge || Y < a.ph;
-        unsigned char *const o = out_f + (out_t + d0.z);
+        int nx = edge ? min(max(a.pw - X, 0), 4) : 4;
+        bool row_ok = !edge || Y < a.ph;
+        unsigned char *o = out_f + (out_t + d0.z);
         uint8_t *const mo = mask_f ? mask_f + (mask_t + d0.w) : nullptr;
+        bool plane_edge = false;
+        if (PLANES) {                                        // the tile's only camera = the output plane; clip to the plane's own size
+            const Fs2Cam &pc = a.cam[sm.desc[stage][1].w & 15u];
+            const int y = Y - pc.dy;
+            o = pc.mb_out + (size_t)y * pc.mb_step + (size_t)X * 4u;
+            plane_edge = (int)(d0.y & 0xffffu) + FS2_W > pc.ow || (int)(d0.y >> 16) - pc.dy + FS2_H > pc.oh;      // block-uniform
+            nx = min(max(pc.ow - X, 0), 4);
+            row_ok = y < pc.oh;
+        }
         unsigned v[4][3];
         if (d0.x & 4u) {
             // Short path (block-uniform; ~2/3 of a ring panorama): ONE camera with weight exactly 1.0f on every pixel of
@@ -697,11 +741,13 @@ k_fs2(const __grid_constant__ Fs2Args a)
                         v[p][k] = q;
                     }
                 }
-                fs2_store_quad<OUT8, 0>(o, v, edge, nx, row_ok);
+                if (PLANES) fs2_store_rgbx<0>(o, v, plane_edge, nx, row_ok);
+                else fs2_store_quad<OUT8, 0>(o, v, edge, nx, row_ok);
             } else {
-                fs2_store_quad<OUT8, 2>(o, v, edge, nx, row_ok);
+                if (PLANES) fs2_store_rgbx<2>(o, v, plane_edge, nx, row_ok);
+                else fs2_store_quad<OUT8, 2>(o, v, edge, nx, row_ok);
             }
-            if (mo) fs2_store_mask(mo, 0xffffffffu, edge, nx, row_ok);
+            if (!PLANES && mo) fs2_store_mask(mo, 0xffffffffu, edge, nx, row_ok);
         } else if (NOBLEND) {
             // which camera slot supplies each pixel (the last one in feed order with a non-zero mask), OR of the masks
             int sel[4] = {-1, -1, -1, -1};
@@ -719,7 +765,10 @@ k_fs2(const __grid_constant__ Fs2Args a)
                 if (sel[p] < 0) {
                     // feedSizeRemap gathers unconditionally (APP64:165-172): where no camera feeds the look-up tables are
                     // zero, i.e. image 0, pixel (0, 0) of its warped, gain-compensated image
-                    if (a.fill_on) fs2_fill_pixel<GAIN>(a, src0, sstep0, v[p][0], v[p][1], v[p][2]);
+                    if (a.fill_on) {
+                        const uint3 f = fs2_fill_pixel<GAIN>(a, src0, sstep0);
+                        v[p][0] = f.x; v[p][1] = f.y; v[p][2] = f.z;
+                    }
                     continue;
                 }
                 const uint4 rec = sm.desc[stage][1 + sel[p]];
@@ -734,8 +783,12 @@ k_fs2(const __grid_constant__ Fs2Args a)
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty[stage]);
-            fs2_store_quad<OUT8, 2>(o, v, edge, nx, row_ok);
-            if (mo) fs2_store_mask(mo, mor, edge, nx, row_ok);
+            if (PLANES) {
+                if (nc) fs2_store_rgbx<2>(o, v, plane_edge, nx, row_ok);
+            } else {
+                fs2_store_quad<OUT8, 2>(o, v, edge, nx, row_ok);
+                if (mo) fs2_store_mask(mo, mor, edge, nx, row_ok);
+            }
         } else {
             // FeatherBlender::feed over the cameras of the tile in feed order (ascending camera index): per channel
             // dst += short(src * w) as integers, dst_w += w in float.  float(v): byte 2 of the sum under the exponent of
@@ -751,7 +804,16 @@ k_fs2(const __grid_constant__ Fs2Args a)
                 const uint32_t box = rec.x + (uint32_t)FS2_BLOCK_BYTES;
                 const uint32_t ee[4] = {e4.x, e4.y, e4.z, e4.w};
                 float g4[4] = {1.f, 1.f, 1.f, 1.f};
-                if (GAIN && a.gain_tma) fs2_gain4(a, smb, rec, gain_idx, X, Y, nx, g4);
+                if (GAIN) {
+                    const Fs2Cam &fc = a.cam[rec.w & 15u];
+                    if (a.gain_tma || !fc.gmap) {
+                        fs2_gain4(a, smb, rec, gain_idx, X, Y, nx, g4);
+                    } else {                                // block gain map in global memory: only where the camera carries weight (inside its rect)
+#pragma unroll
+                        for (int p = 0; p < 4; ++p)
+                            if ((d4 >> (8 * p)) & 0xffu) g4[p] = fs2_gain(fc, X + p, Y);
+                    }
+                }
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
                     const unsigned dist = (d4 >> (8 * p)) & 0xffu;      // 0: short(p * 0) == 0 and dst_w += 0 -> contributes nothing
@@ -761,7 +823,7 @@ k_fs2(const __grid_constant__ Fs2Args a)
                     fs2_pixel<32768>(smb, box, rec.y, ee[p], s0, s1, s2);
                     float f0, f1, f2;
                     if (GAIN) {                             // saturate_cast<uchar>(p * gain)
-                        const float g = a.gain_tma ? g4[p] : (dist != 0u) ? fs2_gain(a.cam[rec.w & 15u], X + p, Y) : 1.f;
+                        const float g = g4[p];
                         // (the rounded product stays a float: bits(x + 2^23) - 2^23)
                         f0 = __fsub_rn(__uint_as_float(fs2_apply_gain_b2(s0, g) | 0x4b000000u), 8388608.f);
                         f1 = __fsub_rn(__uint_as_float(fs2_apply_gain_b2(s1, g) | 0x4b000000u), 8388608.f);
@@ -842,22 +904,30 @@ int fs2_trace_dump()
     return n;
 }
 
-int launch_fs2(const Fs2Args &a, bool apply_gain, bool out8, int grid, cudaStream_t s)
+int launch_fs2(const Fs2Args &a, bool apply_gain, int out_mode, int grid, cudaStream_t s)
 {
+    const bool out8 = out_mode == 1, planes = out_mode == 2;
     SB_ASSERT(a.sharpness > 0.f && a.desc && a.n_tiles > 0 && a.n <= FS2_TMAP_CAMS);
-    SB_ASSERT(a.pw < 65536 && a.ph < 65536 && (unsigned long long)a.ph * a.out_step < (1ull << 32) && (unsigned long long)a.ph * a.mask_step < (1ull << 32));
-    SB_ASSERT(reinterpret_cast<uintptr_t>(a.out) % 8 == 0 && a.out_step % (out8 ? 4 : 8) == 0);
-    SB_ASSERT(!a.out_mask || (reinterpret_cast<uintptr_t>(a.out_mask) % 4 == 0 && a.mask_step % 4 == 0));
+    SB_ASSERT(a.pw < 65536 && a.ph < 65536);
+    if (planes) {
+        SB_ASSERT(a.no_blend && !a.out_mask && !a.frames);
+        for (int i = 0; i < a.n; ++i) SB_ASSERT(a.cam[i].mb_out && reinterpret_cast<uintptr_t>(a.cam[i].mb_out) % 16 == 0 && a.cam[i].mb_step % 16 == 0);
+    } else {
+        SB_ASSERT((unsigned long long)a.ph * a.out_step < (1ull << 32) && (unsigned long long)a.ph * a.mask_step < (1ull << 32));
+        SB_ASSERT(reinterpret_cast<uintptr_t>(a.out) % 8 == 0 && a.out_step % (out8 ? 4 : 8) == 0);
+        SB_ASSERT(!a.out_mask || (reinterpret_cast<uintptr_t>(a.out_mask) % 4 == 0 && a.mask_step % 4 == 0));
+    }
     const size_t smem = sizeof(Fs2Smem);
-    static bool configured_dev[64][8] = {};                  // the attribute is per device (context)
+    static bool configured_dev[64][10] = {};                 // the attribute is per device (context)
     int dev = 0;
     SB_CUDA(cudaGetDevice(&dev));
     bool *configured = configured_dev[dev & 63];
-    const void *fn[8] = {(const void *)k_fs2<false, false, false>, (const void *)k_fs2<false, true, false>,
-                         (const void *)k_fs2<true, false, false>, (const void *)k_fs2<true, true, false>,
-                         (const void *)k_fs2<false, false, true>, (const void *)k_fs2<false, true, true>,
-                         (const void *)k_fs2<true, false, true>, (const void *)k_fs2<true, true, true>};
-    const int v = (a.no_blend ? 4 : 0) + (apply_gain ? 2 : 0) + (out8 ? 1 : 0);
+    const void *fn[10] = {(const void *)k_fs2<false, 0, false>, (const void *)k_fs2<false, 1, false>,
+                          (const void *)k_fs2<true, 0, false>, (const void *)k_fs2<true, 1, false>,
+                          (const void *)k_fs2<false, 0, true>, (const void *)k_fs2<false, 1, true>,
+                          (const void *)k_fs2<true, 0, true>, (const void *)k_fs2<true, 1, true>,
+                          (const void *)k_fs2<false, 2, true>, (const void *)k_fs2<true, 2, true>};
+    const int v = planes ? 8 + (apply_gain ? 1 : 0) : (a.no_blend ? 4 : 0) + (apply_gain ? 2 : 0) + (out8 ? 1 : 0);
     if (!configured[v]) {
         SB_CUDA(cudaFuncSetAttribute(fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[v] = true;

@@ -99,6 +99,31 @@ int launch_mbs_camera_tiles(const uint2 *table, size_t tstep, int rw, int rh, in
     return SB_OK;
 }
 
+// The padded rect's resolved taps in the row-major format the k_fs2 setup reads (kernels_fused.cu: k_build_feather_table):
+//   x = x0 | y0 << 13 | (no second column) << 26 | (no second row) << 27,   y = fx | fy << 5 | 255 << 16 inside the wanted
+// column runs cx (a zero "distance" elsewhere: the pixel is not produced).  The folded and reversed pairs of BORDER_REFLECT
+// become plain pairs exactly as in mbs_resolve: the bilinear products are 32*a*b, so a row or column read twice carries the
+// sum of its two weights, which is the weight of fraction 0.
+__global__ void __launch_bounds__(256) k_mbs_feather_format(const uint2 *table, size_t tstep, int rw, int rh, int c0, int c1, int c2, int c3,
+                                                            uint2 *out, size_t ostep)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= rw || y >= rh) return;
+    const MbsTap m = mbs_resolve(reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(table) + (size_t)y * tstep)[x]);
+    const bool wanted = (x >= c0 && x < c1) || (x >= c2 && x < c3);
+    uint2 t;
+    t.x = m.bx | (m.by << 13) | (m.fx == 0u ? 1u << 26 : 0u) | (m.yfold << 27);
+    t.y = m.fx | ((m.yfold ? 0u : m.fy) << 5) | (wanted ? 255u << 16 : 0u);
+    reinterpret_cast<uint2 *>(reinterpret_cast<char *>(out) + (size_t)y * ostep)[x] = t;
+}
+
+int launch_mbs_feather_format(const uint2 *table, size_t tstep, int rw, int rh, const int cx[4], uint2 *out, size_t ostep, cudaStream_t s)
+{
+    k_mbs_feather_format<<<dim3(div_up(rw, 32), div_up(rh, 8)), 256, 0, s>>>(table, tstep, rw, rh, cx[0], cx[1], cx[2], cx[3], out, ostep);
+    SB_LAUNCHED();
+    return SB_OK;
+}
+
 // pass 3: one 64-byte descriptor per listed tile (list[t] = camera | tile block index << 4), the layout of
 // k_fts_descriptors with exactly one camera slot; tile origin in rect-local pixels
 __global__ void k_mbs_descriptors(MbsSetup a, const unsigned *list, int n_tiles, uint4 *desc)

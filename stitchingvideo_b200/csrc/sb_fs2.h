@@ -70,6 +70,9 @@ struct Fs2Cam {
     unsigned gmstep;
     float gain;
     int dx, dy;                    // warped corner in panorama coordinates (gain map lookup)
+    unsigned char *mb_out;         // output planes (launch_fs2 out_mode 2): this camera's RGBX plane, rows mb_step bytes apart,
+    unsigned mb_step;              // ... whose row 0 is row dy of the stacked coordinate system
+    int ow, oh;                    // ... and its size
 };
 // one frame set of a multi-frame launch (global memory, written by the host before the launch)
 struct alignas(128) Fs2Frame {
@@ -134,7 +137,8 @@ struct Fs2CamSetup {               // one camera as the setup sees it
 int fs2_grid(int n_tiles, int sm_count);
 // the whole per-calibration setup; plan->ok == false: this calibration needs k_feather_fused_px1 (too many cameras per
 // tile, a source box the ring cannot stage, or a sharpness below 1/255)
-int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, int sm_count, bool gain_maps, DevBuf &desc_out, Fs2Plan *plan, cudaStream_t s);
+int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, int sm_count, bool gain_maps, DevBuf &desc_out, Fs2Plan *plan, cudaStream_t s,
+              bool drop_empty = false);      // drop_empty: tiles without a camera leave the schedule (output planes)
 int fs2_encode_gain_tmap(const float *gmap, size_t step, int w, int h, CUtensorMap *out);
 // setup, per camera: bounding boxes of the tile blocks covering the camera's warped rect (row-major feather table in)
 int launch_fs2_bbox(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int tx0, int ty0, int ntx, int nty,
@@ -144,7 +148,7 @@ int launch_fs2_entries(const uint2 *table, size_t tstep, int ww, int wh, int dx,
                        const Fs2Place *place, unsigned dist_cap, unsigned char *blocks, cudaStream_t s);
 // the source image of one camera as FS2_NCLS tensor maps
 int fs2_encode_tmaps(const void *src, size_t sstep, int sw, int sh, const unsigned cls_w[FS2_NCLS], CUtensorMap out[FS2_NCLS]);
-int launch_fs2(const Fs2Args &a, bool apply_gain, bool out8, int grid, cudaStream_t s);
+int launch_fs2(const Fs2Args &a, bool apply_gain, int out_mode, int grid, cudaStream_t s);   // out_mode: 0 CV_16SC3, 1 CV_8UC3, 2 per-camera RGBX planes (k_fs2)
 int fs2_trace_dump();           // debugging aid (SB_FS2_TRACE): see kernels_fstream2.cu
 
 }  // namespace sb

@@ -130,6 +130,8 @@ int launch_mbs_camera_tiles(const uint2 *table, size_t tstep, int rw, int rh, in
 // list_dev[t] = camera | tile block index << 4 for the tiles that have to be produced; grid = fts_grid()
 int launch_mbs_descriptors(const MbsSetup &a, const unsigned *list_dev, int n_tiles, uint4 *desc, int grid, cudaStream_t s);
 int launch_mb_warp_stream(const MbStreamArgs &a, bool apply_gain, int sm_count, cudaStream_t s);
+// the padded rect's taps in the row-major format of the k_fs2 setup (mask 255 inside the column runs cx)
+int launch_mbs_feather_format(const uint2 *table, size_t tstep, int rw, int rh, const int cx[4], uint2 *out, size_t ostep, cudaStream_t s);
 
 int launch_mb_tap_table(const ProjParams &p, int tl_x, int tl_y, int ww, int wh, int left, int top, int sw, int sh,
                         uint2 *table, size_t tstep, int rw, int rh, cudaStream_t s, const DImage *xmap = nullptr, const DImage *ymap = nullptr);
