@@ -8,7 +8,7 @@ SRC=$ROOT/stitchingvideo_b200/csrc
 OUT=$ROOT/variants; mkdir -p $OUT/obj_$NAME
 NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-ffp-contract=off --fmad=false $DEFS"
 # only the files that see the tuning macros are rebuilt; the rest are taken from the main build
-for f in kernels_fstream2 capi_compositor kernels_mb kernels_mb_stream kernels_feather_tma; do
+for f in kernels_fstream2 capi_compositor kernels_mb kernels_mb_pyr kernels_mb_stream kernels_feather_tma; do
   $NV -c $SRC/$f.cu -o $OUT/obj_$NAME/$f.o 2> $OUT/obj_$NAME/$f.log &
 done
 wait

@@ -103,6 +103,7 @@ struct Slot {
     DevImage warped;                             // feather / no-blend: one warped image at a time
     DevImage warped_pad;                         // staged multi-band with block gains: the padded 8UC3 image before convertTo(16S)
     std::vector<std::vector<RawImage>> grgbx;    // fast path: per camera Gaussian pyramid as RGBX bytes
+    std::vector<std::vector<CUtensorMap>> g_tmap; // ... and each level as the tensor k_mb_pyr_down_tma reads its tiles from (empty: not available)
     std::vector<RawImage> rband;                 // fast path: restored bands 1..n as short4 pixels
     std::vector<DevImage> acc;                   // dst_pyr_laplace_ (level 0 = dst_)
     DevImage acc_mask;                           // Blender::NO dst_mask_
@@ -155,6 +156,7 @@ struct sb_compositor {
     DevBuf mbf_desc;
     int mbf_pw = 0, mbf_ph = 0;
     bool mbf_enabled = true;                     // tuning hook (set_fused 17 keeps the round-1 streaming kernel)
+    bool pyr_tma_enabled = true;                 // tuning hook (set_fused 18 keeps the gather form of pyrDown)
     int mbs_n_tiles = 0;
     bool fused = true;                           // panorama-centric fused kernels (default); false = staged reference-shaped path
     // latency ("strip") mode: this handle produces padded-panorama columns [strip_x0, strip_x1)
@@ -212,6 +214,12 @@ int make_slot(sb_compositor *c, Slot &s)
                 r = (r + 1) / 2; w = (w + 1) / 2;
             }
         }
+        s.g_tmap.assign(n, std::vector<CUtensorMap>(levels));     // levels 0 .. n-1 are pyrDown inputs (static buffers: encoded once)
+        for (int i = 0; i < n && !s.g_tmap.empty(); ++i)
+            for (int l = 0; l < levels; ++l) {
+                const RawImage &g = s.grgbx[i][l];
+                if (tmap_encode_u32(g.buf.p, g.step, g.cols, g.rows, MB_PT_IW, MB_PT_IH, &s.g_tmap[i][l]) != SB_OK) { s.g_tmap.clear(); break; }
+            }
         s.rband.resize(levels + 1);
         for (int l = 1; l <= levels; ++l) SB_TRY(s.rband[l].create(s.acc[l].v.rows, s.acc[l].v.cols, 8));
     }
@@ -828,6 +836,13 @@ int mb_down_stage(sb_compositor *c, Slot &s, int l, int ox0, int ox1)
     double bytes = 0;
     if (!fill_down(c, s, l, ox0, ox1, a.p, tx, t, mw, mh, bytes)) return SB_OK;
     static const char *const names[] = {"mb_pyr_down_L0", "mb_pyr_down_L1", "mb_pyr_down_L2", "mb_pyr_down_L3", "mb_pyr_down_L4", "mb_pyr_down_L5+"};
+    if (c->pyr_tma_enabled && !s.g_tmap.empty()) {          // tile-staged form (kernels_mb_pyr.cu); set_fused(18) keeps the gather form
+        MbPyrTmaArgs ta;
+        ta.list = a;
+        for (int i = 0; i < c->cfg.n_cameras; ++i) ta.map[i] = s.g_tmap[i][l];
+        PROF(names[std::min(l, 5)], bytes, launch_mb_pyr_down_tma(ta, st));
+        return SB_OK;
+    }
     PROF(names[std::min(l, 5)], bytes, launch_mb_pyr_down_list(a, st));
     return SB_OK;
 }
@@ -1337,6 +1352,7 @@ int sb_compositor_set_fused(sb_compositor *c, int fused)
         c->feather_variant = fused == 10 ? 0 : fused == 15 ? 3 : 1; c->mb_variant = fused == 10 ? 0 : 1;   // 15: the round-1 feather streaming kernel
         c->mb_multilevel = fused == 12 ? 0 : fused == 13 ? 1 : fused == 16 ? 2 : -1;   // 16: k_mb_coarse whatever the number of frames in flight
         c->mbs_enabled = fused != 14;                        // 14: default fast paths with the gather form of the multi-band warp stage
+        c->pyr_tma_enabled = fused != 18;                    // 18: ... with the gather form of pyrDown (k_mb_pyr_down_list)
         c->mbf_enabled = fused != 17;                        // 17: ... with the round-1 streaming kernel (k_mb_warp_stream) as the warp stage
     }   // test/tuning hook: 10 / 11 select the kernel variant
     return SB_OK;

@@ -331,6 +331,20 @@ int fs2_encode_tmaps(const void *src, size_t sstep, int sw, int sh, const unsign
     return SB_OK;
 }
 
+// an image of 32-bit pixels (RGBX Gaussian level) as a 2-D tensor, box = box_w x box_h pixels
+int tmap_encode_u32(const void *base, size_t step, int w, int h, int box_w, int box_h, CUtensorMap *out)
+{
+    PFN_tmap_encode enc = tmap_encoder();
+    if (!enc) return fail(SB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t gdim[2] = {(cuuint64_t)w, (cuuint64_t)h};
+    const cuuint64_t gstride[1] = {(cuuint64_t)step};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h}, estr[2] = {1u, 1u};
+    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2u, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %dx%d image of 32-bit pixels, pitch %zu", (int)r, w, h, step);
+    return SB_OK;
+}
+
 // a camera's resized block gain map (CV_32FC1 of the warped size + one tile of zero padding on the top and left) as a 2-D float tensor, box = one tile
 int fs2_encode_gain_tmap(const float *gmap, size_t step, int w, int h, CUtensorMap *out)
 {
@@ -354,22 +368,6 @@ struct Fs2Smem {
     uint64_t full[FS2_STAGES], empty[FS2_STAGES];
 };
 static_assert(sizeof(Fs2Smem) * FS2_CTAS_PER_SM + 1024 * FS2_CTAS_PER_SM <= 232448, "shared memory of one SM");
-
-// 2-D tensor copy global -> shared (UTMALDG), completion on `bar`
-__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap *map, int x, int y, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
-}
-// mbarrier wait without polling instructions: try_wait suspends the warp in hardware until the phase completes or a
-// time limit passes (only then does the loop go round)
-__device__ __forceinline__ void mbar_wait_hw(uint64_t *bar, unsigned parity)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
-                 ::"r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
-}
 
 // Bilinear product weights of a table entry (fx = bits 22-26, fy = bits 27-31), times 64, as the two operands of the
 // 16-bit x 8-bit dot products: wx = w00 | w01 << 16, wy = w10 | w11 << 16 with w = a*b*64, a in {32 - fx, fx},

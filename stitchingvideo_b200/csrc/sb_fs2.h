@@ -139,6 +139,7 @@ int fs2_grid(int n_tiles, int sm_count);
 // tile, a source box the ring cannot stage, or a sharpness below 1/255)
 int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, int sm_count, bool gain_maps, DevBuf &desc_out, Fs2Plan *plan, cudaStream_t s,
               bool drop_empty = false);      // drop_empty: tiles without a camera leave the schedule (output planes)
+int tmap_encode_u32(const void *base, size_t step, int w, int h, int box_w, int box_h, CUtensorMap *out);   // image of 32-bit pixels, box in pixels
 int fs2_encode_gain_tmap(const float *gmap, size_t step, int w, int h, CUtensorMap *out);
 // setup, per camera: bounding boxes of the tile blocks covering the camera's warped rect (row-major feather table in)
 int launch_fs2_bbox(const uint2 *table, size_t tstep, int ww, int wh, int dx, int dy, int tx0, int ty0, int ntx, int nty,

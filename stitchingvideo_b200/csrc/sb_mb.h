@@ -1,5 +1,6 @@
 // sb_mb.h — argument blocks of the multi-band fast path (kernels_mb.cu).
 #pragma once
+#include <cuda.h>          // CUtensorMap (types only)
 #include "sb_fused.h"
 
 namespace sb {
@@ -42,6 +43,17 @@ struct MbPyrListArgs {
     int n_seg;
     MbPyrSeg seg[2 * SB_MAX_CAMERAS];
 };
+
+// tile-staged pyrDown (kernels_mb_pyr.cu): a CTA = 64 x 32 outputs from one tensor copy of 136 x 67 inputs
+#ifndef SB_CFG_PT_OH
+#define SB_CFG_PT_OH 32
+#endif
+constexpr int MB_PT_OW = 64, MB_PT_OH = SB_CFG_PT_OH, MB_PT_IW = 2 * MB_PT_OW + 8, MB_PT_IH = 2 * MB_PT_OH + 3;
+struct alignas(64) MbPyrTmaArgs {
+    CUtensorMap map[SB_MAX_CAMERAS];                        // level l of camera i as a 2-D tensor of 32-bit pixels, box MB_PT_IW x MB_PT_IH
+    MbPyrListArgs list;                                     // cameras + the tile list (here: MB_PT_OW-column tiles, MB_PT_OH-row tile rows)
+};
+int launch_mb_pyr_down_tma(MbPyrTmaArgs &a, cudaStream_t s);
 
 struct MbBandCam {
     const uint32_t *fine;    // Gaussian level l (RGBX), rect-local

@@ -62,4 +62,21 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar)
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// 2-D tensor copy global -> shared (UTMALDG), completion on `bar`
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void *map, int x, int y, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+// mbarrier wait without polling instructions: try_wait suspends the warp in hardware until the phase completes or a
+// time limit passes (only then does the loop go round)
+__device__ __forceinline__ void mbar_wait_hw(uint64_t *bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
+}
+
+
 }  // namespace sbt

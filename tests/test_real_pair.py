@@ -82,7 +82,7 @@ def test_cuda_path_on_real_frames(gpu):
     seams = [capi.resize_linear_8u(capi.dilate3x3(G["seam_mask%d" % i]), cal.sizes[i]) for i in range(N)]
     for a, b in zip(seams, oseams):
         assert np.array_equal(a, b)
-    for fused in (11, 12, 14, 16, 17, 10, 0):
+    for fused in (11, 12, 14, 16, 17, 18, 10, 0):
         c = gpu.Compositor(SIZE, KS, RS, warper="spherical", scale=SCALE, blender="multiband", num_bands=5,
                            gains=list(G["gains"]), seam_masks=seams)
         c.set_fused(fused)

@@ -54,7 +54,7 @@ def test_oracle_plus_stored_difference_is_opencvs_panorama():
 @pytest.mark.gpu
 def test_cuda_path_on_the_full_size_real_pair(gpu):
     cal, seams, (opano, omask) = oracle_panorama()
-    for fused in (11, 12, 14, 16, 17, 10, 0):
+    for fused in (11, 12, 14, 16, 17, 18, 10, 0):
         c = gpu.Compositor(SIZE, KS, RS, warper="spherical", scale=SCALE, blender="multiband", num_bands=5, gains=list(G["gains"]), seam_masks=seams)
         c.set_fused(fused)
         pano, mask = c.compose(frames())
