@@ -36,6 +36,8 @@ WORKLOADS = {
     "c4": "C4: 8-camera 4K VR, SphericalWarper + GainCompensator + MultiBandBlender(5 bands) (configs[3])",
     "app6": "APP6: the live app's own per-frame case (BASELINE.md 1; APP64:748-759): 6-camera 1920x1088, cached-map cylindrical remap + BlockApply "
             "(block gain maps) + look-up composite without blending, cropped by the app's margins (0.1 / 0.1 / 10 / 10), panorama ~8020x883",
+    "c5-strip": "C5 latency mode: ONE 8-camera 4K frame set -> 16384-wide panorama (SphericalWarper + GainCompensator + MultiBandBlender, 5 bands), the "
+                "panorama cut into one column strip per GPU (BASELINE.json configs[4]; SURVEY 8e)",
 }
 # the only per-frame figure the reference publishes (REL32/resultTime-at.txt, mean 43.6 ms per frame set,
 # hardware unknown): frames/s for exactly the APP6 workload
@@ -397,6 +399,94 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_strip(args):
+    """--workload c5-strip: latency of ONE very wide panorama split into column strips, one rank (GPU) per strip.  A step is
+    one frame set; value = 1 / (device latency of a frame, max over ranks) - total work is fixed as N grows ("strong").  The
+    strips are compared bit for bit with the unsplit panorama before anything is timed."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import stitchingvideo_b200 as sv
+    from stitchingvideo_b200 import capi, rigs, strips
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rig = "c5"
+    Ks, Rs, spec = rigs.cameras(rig)
+    n, size = spec["n_used"], (spec["W"], spec["H"])
+    mk = lambda: sv.Compositor(size, Ks, Rs, warper=spec["warper"], scale=spec["scale"], blender="multiband", num_bands=5,
+                               gains=spec["gain_values"], device=local)
+    comp = mk()
+    sets = [[torch.from_numpy(rigs.frame(rig, s, i, smooth=0)).to(dev) for i in range(n)] for s in range(2)]
+    dsets = [[capi.DeviceImage.from_torch(t) for t in s] for s in sets]
+    sampler = ClockSampler(local)
+    launches0 = sv.kernel_launch_count()
+    if world == 1:
+        for it in range(args.warmup):
+            comp.wait(comp.enqueue(dsets[it % 2], None, None))
+        sampler.start()
+        launches0 = sv.kernel_launch_count()
+        lat = []
+        for it in range(args.steps):
+            comp.wait(comp.enqueue(dsets[it % 2], None, None))
+            lat.append(comp.last_gpu_ms(0))
+        ok, halo = True, "none (one strip)"
+    else:
+        sc = strips.StripCompositor(comp, rank, world, device=dev, halo=args.halo)
+        strip, smask = sc.compose(dsets[0])
+        pano, pmask = sc.gather(strip, smask, dst=0)
+        ok = True
+        if rank == 0:
+            whole = mk()
+            ref, rmask = whole.compose(dsets[0])
+            ok = bool(np.array_equal(pano, ref) and np.array_equal(pmask, rmask))
+            del whole
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.broadcast(flag, 0)
+        ok = int(flag.item()) == 1
+        for it in range(args.warmup):
+            sc.enqueue(dsets[it % 2])
+        torch.cuda.synchronize()
+        dist.barrier()
+        sampler.start()
+        launches0 = sv.kernel_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lat = []
+        for it in range(args.steps):
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0.record()
+            sc.enqueue(dsets[it % 2])
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            lat.append(float(t.item()))
+        halo = args.halo
+    launches = sv.kernel_launch_count() - launches0
+    clocks = sampler.summary()
+    if rank == 0:
+        ms = float(np.median(lat))
+        pw, ph = comp.pano_size
+        print(json.dumps({
+            "metric": "8x4K->16384-wide panorama frames/s (one frame set in flight)", "value": 1e3 / ms, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8/s16 integer + f32 weights", "data": "synthetic",
+            "config": {"workload": WORKLOADS["c5-strip"], "cameras": n, "frame": "%dx%d" % size, "panorama": "%dx%d" % (pw, ph), "strips": world,
+                       "halo": halo, "timing": "CUDA events around one frame set on the stream the kernels (and the halo traffic) run on, "
+                                               "median of the steps, max over ranks per step"},
+            "bit_exact_vs_unsplit": ok, "latency_ms": {"median": ms, "min": float(np.min(lat)), "max": float(np.max(lat))},
+            "gpu_launches": launches, "clocks": clocks, "e2e": None, "roofline": None}))
+    if world > 1:
+        dist.destroy_process_group()
+    if not ok:
+        sys.exit(1)
+
+
 # ------------------------------------------------------------------------------------------- CPU arms
 def _oracle_ctx(workload):
     from stitchingvideo_b200 import rigs
@@ -553,6 +643,8 @@ def main():
     ap.add_argument("--profile-frames", type=int, default=5)
     ap.add_argument("--cpu-frames", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo", default="recompute", choices=["recompute", "peer", "exchange"], help="c5-strip: how a strip gets the columns next to "
+                    "its boundaries (recompute: no communication; peer: in-kernel peer-memory writes + flags; exchange: NCCL send/recv)")
     ap.add_argument("--variant", type=int, default=None, choices=[0, 1, 2, 3, 4, 5], help="fused kernel variant: 10 + v is passed to set_fused (default: library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -561,7 +653,13 @@ def main():
         args.also = [w for w in ("c3", "app6") if w != args.workload] if (world == 1 and args.workload == "c2") else []
     else:
         args.also = [w for w in args.also.split(",") if w and w != args.workload]
-    if args.impl == "reference":
+    if args.workload == "c5-strip":
+        if args.impl == "reference":      # (the CPU arm of the 16384-wide panorama takes minutes per frame: not run; C2 is the reference arm's workload)
+            if int(os.environ.get("RANK", 0)) == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "c5-strip has no CPU arm (one 8x4K frame set takes minutes on the host); run --workload c2"}))
+            return
+        run_strip(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

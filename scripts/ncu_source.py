@@ -30,7 +30,7 @@ for n, r in enumerate(b["rows"][1:]):
     i = int(r[col["Instructions Executed"]] or 0)
     tot_s += s; tot_i += i
     st = {k.replace("stall_", ""): int(r[col[k]]) for k in KEYS if r[col[k]] not in ("0", "")}
-    out.append((n, r[col["Source"]].strip()[:70], s, i, st, r[col["L1 Wavefronts Shared"]], r[col["L1 Wavefronts Shared Ideal"]]))
+    out.append((n, r[col["Source"]].strip()[:70], s, i, st, r[col["L1 Wavefronts Shared"]] if "L1 Wavefronts Shared" in col else "-", r[col["L1 Wavefronts Shared Ideal"]] if "L1 Wavefronts Shared Ideal" in col else "-"))
 print("#", b["name"], "samples", tot_s, "warp instructions", tot_i)
 for o in out:
     if o[2] >= min_s or any(t in o[1] for t in ("SYNCS.PHASE", "UTMALDG", "UBLKCP", "NANOSLEEP")):

@@ -988,12 +988,13 @@ int mb_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src, const in
 {
     const int nb = c->num_bands;
     SB_TRY(mb_warp_stage(c, s, src, g_lo[0], g_hi[0]));
-    // One frame in flight (latency): warp, pyrDown 0 -> 1, every coarser level and every band but the last in ONE launch
-    // (k_mb_coarse), the final band: 4 launches.  Several frames in flight (throughput): one launch per level - the
-    // latency-bound coarse levels of one frame then hide behind the heavy kernels of the others without a resident
-    // grid of waiting CTAs in their way (measured, C3, 8 in flight: 119 vs 134 us per frame).  set_fused(16) forces the
-    // former, set_fused(12) the latter.
-    const bool coarse = c->mb_multilevel == 2 || (c->mb_multilevel < 0 && c->slots.size() == 1);
+    // Default: one launch per level (warp, pyrDown x n, band x n+1).  set_fused(16): warp, pyrDown 0 -> 1, every coarser level
+    // and every band but the last in ONE launch (k_mb_coarse), the final band - 4 launches.  Fewer launches did not mean less
+    // time: the fused coarse launch is a chain of 2n-1 dependent stages whose CTAs wait on each other's counters, while
+    // separate launches of the tile-staged kernels cost ~9 us each in-stream and, with several frames in flight, hide
+    // behind the other frames' heavy kernels (measured on B200, C3: 8 in flight 105 vs 126 us per frame; one in flight
+    // 169 vs ~200 us).
+    const bool coarse = c->mb_multilevel == 2;
     if (coarse && nb >= 2 && nb <= SB_MB_MAX_FUSED_LEVELS && c->strip_world == 1) {
         SB_TRY(mb_down_stage(c, s, 0, g_lo[1], g_hi[1]));
         SB_TRY(mb_coarse(c, s, 1, 1, g_lo, g_hi, b_lo, b_hi));
