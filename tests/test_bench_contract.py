@@ -20,7 +20,8 @@ def lines(pattern):
     return out
 
 
-@pytest.mark.parametrize("name,d", lines("r01_final_b_c*.json") + lines("r01_final_b_app6.json") + lines("r01_b_c2_n*.json"))
+@pytest.mark.parametrize("name,d", lines("r01_final_b_c*.json") + lines("r01_final_b_app6.json") + lines("r01_b_c2_n*.json") +
+                         lines("r02_final_b_n1.json") + lines("r02_bench_c2_n8.json"))
 def test_committed_bench_lines_follow_the_contract(name, d):
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
@@ -46,8 +47,24 @@ def test_committed_bench_lines_follow_the_contract(name, d):
         assert d["vs_baseline"] == pytest.approx(d["value"] / (1000.0 / 43.6))
 
 
-def test_reference_arm_line():
-    name, d = lines("r01_final_b_ref_c2.json")[0]
+def test_round2_line_carries_the_heavy_workloads():
+    """the default N=1 line reports C3 and the live app's case measured in the same run, the copy-only PCIe
+    ceiling next to e2e, a timed region of ~0.5 s, and the kernel the roofline names is the TMA frame kernel."""
+    name, d = lines("r02_final_b_n1.json")[0]
+    assert set(d["workloads"]) == {"c3", "app6"}
+    for w, m in d["workloads"].items():
+        for k in ("metric", "value", "unit", "ms_per_step", "config", "e2e", "gpu_launches", "clocks", "roofline", "kernels"):
+            assert k in m, "%s: missing %s" % (w, k)
+        assert m["value"] > 0 and m["e2e"]["value"] > 0 and 0 < m["roofline"]["frac"] < 1 and m["gpu_launches"] > 0
+    assert d["workloads"]["app6"]["vs_baseline"] == pytest.approx(d["workloads"]["app6"]["value"] / (1000.0 / 43.6))
+    assert d["steps"] * d["ms_per_step"] >= 400.0                      # timed region >= 0.4 s of device time
+    assert d["e2e"]["copy_only_ceiling"]["value"] >= d["e2e"]["value"] * 0.95
+    assert d["roofline"]["kernel"] == "feather_stream" and d["roofline"]["traffic"]
+
+
+@pytest.mark.parametrize("name", ["r01_final_b_ref_c2.json", "r02_final_b_ref.json"])
+def test_reference_arm_line(name):
+    name, d = lines(name)[0]
     assert d["impl"] == "reference" and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
 
