@@ -196,7 +196,7 @@ int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, i
             if (gain_tma) {     // the 32x32 floats of the camera's resized gain map under this tile (out-of-range: zero, never used)
                 // (coordinates in the gain map PADDED by one tile all round, so that the 32x32 box always lies inside the tensor: a
                 // tensor copy that overlaps its tensor by a single element in x and y raised an illegal-instruction fault on
-                // B200 - scratch/tma_f32.cu, box at (-31, -31) - although partly outside boxes are fine in general)
+                // B200 - scripts/microbench/tma_f32.cu, box at (-31, -31) - although partly outside boxes are fine in general)
                 const int gx = tx * FS2_W - cams[slot_cam[j]].dx + FS2_W, gy = ty * FS2_H - cams[slot_cam[j]].dy + FS2_H;
                 if (gx < 0 || gy < 0) return fail(SB_ERR_ASSERT, "fs2_build: gain tile of a camera that does not touch the tile");
                 // the inner coordinate of a tensor copy must be 16-byte aligned (x = -31 floats faults, -8 and -700 do not): the box
