@@ -236,6 +236,25 @@ int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, i
     const int grid = fs2_grid(n_tiles, sm_count);
     // ... except that every CTA's FIRST tiles are cheap ones: the first wave of copies is what the consumers wait for at
     // kernel start, and a one-camera tile is 2-3x fewer bytes
+    static const int sched_mode = getenv("SB_FS2_SCHED") ? atoi(getenv("SB_FS2_SCHED")) : 0;      // tuning experiment
+    if (sched_mode == 1 && n_tiles >= 2 * grid * FS2_GROUPS) {
+        // interleaved: rounds (one tile per CTA) of blended tiles spread evenly among the rounds of one-camera tiles, so that the
+        // bytes a CTA's ring must hold ahead of its consumers are the average of the two kinds instead of the blended maximum
+        std::vector<int> ex, ch;
+        for (int t : order) (cost(t) >= 2 ? ex : ch).push_back(t);
+        const int ne = div_up((int)ex.size(), grid), nc = div_up((int)ch.size(), grid);
+        std::vector<std::pair<double, int>> seq;                 // (position, chunk id: >= 0 expensive, < 0 cheap)
+        for (int i = 0; i < ne; ++i) seq.push_back({(i + 0.5) / ne, i});
+        for (int j = 0; j < nc; ++j) seq.push_back({j < FS2_GROUPS ? -1.0 + j * 1e-3 : (j - FS2_GROUPS + 0.5) / std::max(1, nc - FS2_GROUPS), -1 - j});
+        std::sort(seq.begin(), seq.end());
+        std::vector<int> merged;
+        for (auto &q : seq) {
+            const std::vector<int> &src = q.second >= 0 ? ex : ch;
+            const size_t c0 = (size_t)(q.second >= 0 ? q.second : -1 - q.second) * grid;
+            for (size_t k = c0; k < std::min(src.size(), c0 + (size_t)grid); ++k) merged.push_back(src[k]);
+        }
+        order.swap(merged);
+    } else
     if (n_tiles >= 2 * grid * FS2_GROUPS) std::rotate(order.begin(), order.end() - (size_t)grid * FS2_GROUPS, order.end());
     // position t of the schedule belongs to CTA t % grid as its tile number t / grid; the CTA's descriptors are contiguous
     const int per_cta = div_up(n_tiles, grid);
