@@ -236,10 +236,11 @@ int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, i
     const int grid = fs2_grid(n_tiles, sm_count);
     // ... except that every CTA's FIRST tiles are cheap ones: the first wave of copies is what the consumers wait for at
     // kernel start, and a one-camera tile is 2-3x fewer bytes
-    static const int sched_mode = getenv("SB_FS2_SCHED") ? atoi(getenv("SB_FS2_SCHED")) : 0;      // tuning experiment
+    static const int sched_mode = getenv("SB_FS2_SCHED") ? atoi(getenv("SB_FS2_SCHED")) : 1;      // 0: the descending-cost order of the first version
     if (sched_mode == 1 && n_tiles >= 2 * grid * FS2_GROUPS) {
         // interleaved: rounds (one tile per CTA) of blended tiles spread evenly among the rounds of one-camera tiles, so that the
         // bytes a CTA's ring must hold ahead of its consumers are the average of the two kinds instead of the blended maximum
+        // (measured: app6 +2 %, C2 +0.4 % over the descending-cost order; the first FS2_GROUPS rounds stay cheap ones)
         std::vector<int> ex, ch;
         for (int t : order) (cost(t) >= 2 ? ex : ch).push_back(t);
         const int ne = div_up((int)ex.size(), grid), nc = div_up((int)ch.size(), grid);

@@ -391,10 +391,11 @@ __device__ __forceinline__ void mb_band_thread(const MbBandArgs &a, int X0, int 
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            up[0][0][k] = sat_s16((e[0][k] + e[1][k] * 6 + e[2][k] + 32) >> 6);
-            up[0][1][k] = sat_s16((o[0][k] + o[1][k] * 6 + o[2][k] + 32) >> 6);
-            up[1][0][k] = sat_s16(((e[1][k] + e[2][k]) * 4 + 32) >> 6);
-            up[1][1][k] = sat_s16(((o[1][k] + o[2][k]) * 4 + 32) >> 6);
+            // (a weighted mean of 16-bit values with weights summing to 64: pyrUp's saturate_cast<short> can never clamp)
+            up[0][0][k] = (e[0][k] + e[1][k] * 6 + e[2][k] + 32) >> 6;
+            up[0][1][k] = (o[0][k] + o[1][k] * 6 + o[2][k] + 32) >> 6;
+            up[1][0][k] = ((e[1][k] + e[2][k]) * 4 + 32) >> 6;
+            up[1][1][k] = ((o[1][k] + o[2][k]) * 4 + 32) >> 6;
         }
     }
 

@@ -57,11 +57,11 @@ int launch_mb_pyr_down_tma(MbPyrTmaArgs &a, cudaStream_t s);
 
 struct MbBandCam {
     const uint32_t *fine;    // Gaussian level l (RGBX), rect-local
-    size_t fstep;
+    unsigned fstep;          // (row pitches as 32-bit values: one IMAD.WIDE.U32 per row address instead of a 64-bit multiply)
     const uint32_t *coarse;  // Gaussian level l+1 (null at the top level)
-    size_t cstep;
+    unsigned cstep;
     const void *weight;      // weight pyramid level l (float or short), sequence-constant
-    size_t wstep;
+    unsigned wstep;
     int rx, ry, rw, rh;      // feed rect at this level in panorama-level coordinates
 };
 struct MbBandGeom {
@@ -74,13 +74,13 @@ struct MbBandArgs {
     const uint32_t *tile_mask;   // per 32x8 tile of band l: cameras with non-zero weight there
     int tiles_x;
     const void *wsum;        // dst_band_weights_[l]
-    size_t wsum_step;
+    unsigned wsum_step;
     const short4 *coarse_r;  // restored band l+1 (CV_16SC3 values in 8-byte pixels); null at the top level
-    size_t coarse_r_step;
+    unsigned coarse_r_step;
     void *out;               // restored band l (short4 pixels), or the final panorama at band 0
-    size_t out_step;
+    unsigned out_step;
     uint8_t *out_mask;
-    size_t mask_step;
+    unsigned mask_step;
     int out_w, out_h;        // band 0 only: dst_roi_final_ size
     int x_begin, x_end;      // band columns to produce (strip mode; whole band: 0, lw)
 };
