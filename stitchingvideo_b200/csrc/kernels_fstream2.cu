@@ -244,15 +244,25 @@ int fs2_build(const Fs2CamSetup *cams, int n, int pw, int ph, float sharpness, i
         std::vector<int> ex, ch;
         for (int t : order) (cost(t) >= 2 ? ex : ch).push_back(t);
         const int ne = div_up((int)ex.size(), grid), nc = div_up((int)ch.size(), grid);
-        std::vector<std::pair<double, int>> seq;                 // (position, chunk id: >= 0 expensive, < 0 cheap)
-        for (int i = 0; i < ne; ++i) seq.push_back({(i + 0.5) / ne, i});
-        for (int j = 0; j < nc; ++j) seq.push_back({j < FS2_GROUPS ? -1.0 + j * 1e-3 : (j - FS2_GROUPS + 0.5) / std::max(1, nc - FS2_GROUPS), -1 - j});
-        std::sort(seq.begin(), seq.end());
+        // Round p of the CTA's sequence is consumed by group p % FS2_GROUPS, so an expensive round goes where the group has had
+        // the fewest so far (a plain 1-in-3 interleave handed every blended tile to the same group: its tiles then retire
+        // late, ring space is handed back in order, and the producers stall - seen in the pipeline trace), paced so that
+        // expensive rounds stay evenly spread; the first FS2_GROUPS rounds are cheap ones.
+        const int rounds = ne + nc;
         std::vector<int> merged;
-        for (auto &q : seq) {
-            const std::vector<int> &src = q.second >= 0 ? ex : ch;
-            const size_t c0 = (size_t)(q.second >= 0 ? q.second : -1 - q.second) * grid;
+        int used_e = 0, used_c = 0, per_group[FS2_GROUPS] = {};
+        for (int r = 0; r < rounds; ++r) {
+            const int g = r % FS2_GROUPS;
+            int least = per_group[0];
+            for (int q = 1; q < FS2_GROUPS; ++q) least = std::min(least, per_group[q]);
+            const bool behind = (long long)used_e * rounds < (long long)r * ne;         // fewer expensive rounds placed than an even spread would have
+            bool take_e = used_e < ne && r >= std::min(FS2_GROUPS, nc) && behind && per_group[g] <= least;
+            if (used_c >= nc) take_e = true;
+            const std::vector<int> &src = take_e ? ex : ch;
+            const size_t c0 = (size_t)(take_e ? used_e : used_c) * grid;
             for (size_t k = c0; k < std::min(src.size(), c0 + (size_t)grid); ++k) merged.push_back(src[k]);
+            per_group[g] += cost(src[c0]);                  // a group's load in units of a one-camera tile (2 / 3 / 4: blended with 1 / 2 / 3 cameras)
+            if (take_e) ++used_e; else ++used_c;
         }
         order.swap(merged);
     } else
