@@ -307,7 +307,8 @@ int  sb_compositor_compose(sb_compositor *c, const sb_image *srcs, sb_image *pan
  * 16: multi-band with every level >= 1 and every band but the last in ONE launch (k_mb_coarse; 4 launches per frame - measured
  *     slower than the default of one launch per level),
  * 17: multi-band with the round-1 streaming kernel as the warp stage instead of k_fs2's output-planes mode,
- * 18: multi-band with the gather form of pyrDown instead of the tile-staged one). */
+ * 18: multi-band with the gather form of pyrDown instead of the tile-staged one,
+ * 19: multi-band with only the levels >= 2 sharing one k_mb_coarse launch (6 launches per frame)). */
 int  sb_compositor_set_fused(sb_compositor *c, int fused);
 /* Which frame kernel this calibration was planned for (tests assert that the fast path really is the one that runs):
  * feather / no blending: 2 = tensor-TMA streaming kernel (k_fs2), 1 = round-1 streaming kernel, 0 = gather kernel;

@@ -1001,7 +1001,17 @@ int mb_frame(sb_compositor *c, Slot &s, const std::vector<DImage> &src, const in
         SB_TRY(mb_band_stage(c, s, 0, b_lo[0], b_hi[0]));
         return SB_OK;
     }
-    const bool multilevel = c->mb_multilevel > 0;
+    if (c->mb_multilevel == 3 && nb >= 4 && nb <= SB_MB_MAX_FUSED_LEVELS && c->strip_world == 1) {
+        // hybrid (set_fused(19)): the levels that carry bytes keep their own tile-staged launches, the tiny ones (level >= 2:
+        // < 15 MB in total, each launch latency-bound) share one k_mb_coarse launch - 6 launches per frame
+        SB_TRY(mb_down_stage(c, s, 0, g_lo[1], g_hi[1]));
+        SB_TRY(mb_down_stage(c, s, 1, g_lo[2], g_hi[2]));
+        SB_TRY(mb_coarse(c, s, 2, 2, g_lo, g_hi, b_lo, b_hi));
+        SB_TRY(mb_band_stage(c, s, 1, b_lo[1], b_hi[1]));
+        SB_TRY(mb_band_stage(c, s, 0, b_lo[0], b_hi[0]));
+        return SB_OK;
+    }
+    const bool multilevel = c->mb_multilevel == 1;
     if (multilevel && nb >= 3 && nb <= SB_MB_MAX_FUSED_LEVELS) {
         SB_TRY(mb_down_stage(c, s, 0, g_lo[1], g_hi[1]));
         SB_TRY(mb_down_tail(c, s, 1, nb, g_lo, g_hi));
@@ -1351,7 +1361,7 @@ int sb_compositor_set_fused(sb_compositor *c, int fused)
     if (fused >= 10) {   // 10: CV_16S band kernels / px1 feather; 11: fast paths (default); 12 / 13: fast paths with one launch per
         // pyramid level / with the multi-level launches forced; 14: fast paths with the gather warp stage
         c->feather_variant = fused == 10 ? 0 : fused == 15 ? 3 : 1; c->mb_variant = fused == 10 ? 0 : 1;   // 15: the round-1 feather streaming kernel
-        c->mb_multilevel = fused == 12 ? 0 : fused == 13 ? 1 : fused == 16 ? 2 : -1;   // 16: k_mb_coarse whatever the number of frames in flight
+        c->mb_multilevel = fused == 12 ? 0 : fused == 13 ? 1 : fused == 16 ? 2 : fused == 19 ? 3 : -1;   // 16: k_mb_coarse whatever the number of frames in flight
         c->mbs_enabled = fused != 14;                        // 14: default fast paths with the gather form of the multi-band warp stage
         c->pyr_tma_enabled = fused != 18;                    // 18: ... with the gather form of pyrDown (k_mb_pyr_down_list)
         c->mbf_enabled = fused != 17;                        // 17: ... with the round-1 streaming kernel (k_mb_warp_stream) as the warp stage

@@ -124,7 +124,7 @@ def test_multi_device_driver(gpu):
         gpu.MultiCompositor([0, 99], 1, size, Ks, Rs, warper="cylindrical", scale=spec["scale"], blender="feather")     # no such device: an error, not a downgrade
 
 
-@pytest.mark.parametrize("rig,blender,variants", [("mini", "multiband", (0, 10, 11, 12, 13, 14, 16, 17, 18)), ("mini_cyl", "feather", (0, 10, 11, 15)),
+@pytest.mark.parametrize("rig,blender,variants", [("mini", "multiband", (0, 10, 11, 12, 13, 14, 16, 17, 18, 19)), ("mini_cyl", "feather", (0, 10, 11, 15)),
                                                   ("mini_cyl", "no", (0, 11, 15))])
 @pytest.mark.parametrize("out16", [False, True])
 def test_device_panorama_is_written_in_place(gpu, rig, blender, variants, out16):

@@ -393,7 +393,7 @@ def test_compositor_blocks_gain(gpu, rig, blender):
     ref, rmask = P.compose(cal, frames, blender=blender, gain_maps=gmaps)
     # every kernel variant, incl. the staged, reference-shaped cross-check path (0: warp -> mul by the resized map -> convertTo ->
     # feed x n -> blend) and the CV_16S band kernels / gather feather kernel (10) and the round-1 streaming kernel (15)
-    for fused in ((11, 12, 13, 14, 16, 17, 18, 10, 0) if blender == "multiband" else (11, 15, 10, 0)):
+    for fused in ((11, 12, 13, 14, 16, 17, 18, 19, 10, 0) if blender == "multiband" else (11, 15, 10, 0)):
         comp.set_fused(fused)
         pano, mask = comp.compose(frames)
         assert_same(pano, ref, "%s/%s blocks gain (variant %d)" % (rig, blender, fused))
