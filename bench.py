@@ -323,6 +323,22 @@ def measure(workload, args, rank, world, local, barrier, max_over_ranks, sampler
                                  "achieved_gbs": total_mb / 1e3 / (frame_ms / 1e3), "frac": total_mb / 1e3 / (frame_ms / 1e3) / peak},
                 "single_stream": {"us_per_frame": serial_frame_ms * 1e3, "achieved_gbs": total_mb / 1e3 / (serial_frame_ms / 1e3),
                                   "frac": total_mb / 1e3 / (serial_frame_ms / 1e3) / peak}}
+    if lap_mode == 1 and len(kernels) == 1 and dom["launches_per_frame"] == 1:
+        # The timed region launched this kernel as ONE persistent launch per lap of LAP frame sets: its average launch duration
+        # over the timed region is (device time between the marks) / (number of launches), its algorithmic bytes per launch
+        # are LAP x the frame's.  The single-frame launch figures of the separate pass stay beside it.
+        n_launch = args.steps * laps
+        launch_us = ms_dev * 1e3 / n_launch
+        bytes_launch = dom["algorithmic_mb_per_frame"] * 1e6 * LAP
+        roofline["single_frame_launch"] = {"avg_launch_us": roofline["avg_launch_us"], "achieved": roofline["achieved"], "frac": roofline["frac"],
+                                           "isolated_launch_us": roofline["isolated_launch_us"], "frac_isolated": roofline["frac_isolated"],
+                                           "how": roofline["how"]}
+        roofline.update({"achieved": bytes_launch / (launch_us * 1e-6) / 1e9, "avg_launch_us": launch_us, "algorithmic_bytes_per_launch": bytes_launch,
+                         "frame_sets_per_launch": LAP,
+                         "how": "achieved = the kernel's algorithmic bytes per launch / its average launch duration over the timed region itself: %d "
+                                "launches of the persistent frame kernel, %d frame sets each, CUDA events (marks) around the region on the launching "
+                                "streams; single_frame_launch = the same kernel launched once per frame set in a separate pass" % (n_launch, LAP)})
+        roofline["frac"] = roofline["achieved"] / peak
     out = {
         "value": value, "unit": "frames/s", "ms_per_step": ms_dev / args.steps,
         "config": {"workload": WORKLOADS[workload], "frame_sets_per_step": frames_per_step, "frame_sets_per_rank": args.steps * frames_per_step,

@@ -7,7 +7,7 @@ d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 
 def show(name, m):
     r = m["roofline"]
-    print("%-5s value %.0f e2e %.0f | dom %s frac %.3f (in-stream %.1f us, isolated %.1f us frac %.3f) | timed %.3f (%.1f us/frame) "
+    print("%-5s value %.0f e2e %.0f | dom %s frac %.3f (launch %.1f us" + (" = %d frame sets" % r["frame_sets_per_launch"] if "frame_sets_per_launch" in r else "") + ", isolated %.1f us frac %.3f) | timed %.3f (%.1f us/frame) "
           "single-stream %.3f (%.1f us) | launches %d" % (
               name, m["value"], m["e2e"]["value"], r["kernel"], r["frac"], r["avg_launch_us"], r["isolated_launch_us"], r["frac_isolated"],
               r["timed_region"]["frac"], r["timed_region"]["us_per_frame"], r["single_stream"]["frac"], r["single_stream"]["us_per_frame"],
