@@ -607,6 +607,7 @@ k_fs2(const __grid_constant__ Fs2Args a)
     const unsigned char *const smb = smem_raw;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x;
+    pdl_release();                                          // programmatic dependent launch: the next kernel of the stream may be set up from here on
     if (tid == 0) {
         for (int s = 0; s < FS2_STAGES; ++s) {
             mbar_init(&sm.full[s], 1);                      // the producer's arrive (+ the copies' expect_tx)
@@ -633,6 +634,7 @@ k_fs2(const __grid_constant__ Fs2Args a)
         auto load_rec = [&](int g) { return lane < FS2_DESC_RECS ? __ldg(dp0 + (size_t)(g % n_mine) * FS2_DESC_RECS + lane) : make_uint4(0u, 0u, 0u, 0u); };
         uint4 nx = make_uint4(0u, 0u, 0u, 0u);
         if (pw < total) nx = load_rec(pw);
+        pdl_wait();                                         // the predecessor grid may still be running up to here (the descriptors are per-calibration data)
         int retired = 0;
         for (int gs = pw; gs < total; gs += FS2_PRODUCERS) {     // gs: tile number counted over the frames
             const uint4 d = nx;
@@ -702,6 +704,7 @@ k_fs2(const __grid_constant__ Fs2Args a)
     const uint8_t *src0 = a.src0;
     unsigned sstep0 = a.sstep0;
     int next_frame_at = a.frames ? 0 : total;               // tile number at which the next frame set's output pointers are due
+    pdl_wait();                                             // (before the first output store, and before shared memory a copy of this grid lands in is read)
     for (int seq = grp; seq < total; seq += FS2_GROUPS) {   // seq: tile number counted over the frames
         if (seq >= next_frame_at) {
             const Fs2Frame *fr = a.frames + seq / n_mine;
@@ -978,7 +981,7 @@ int launch_fs2(const Fs2Args &a, bool apply_gain, int out_mode, int grid, cudaSt
         return SB_OK;
     }
     void *params[] = {const_cast<Fs2Args *>(&a)};
-    SB_CUDA(cudaLaunchKernel(fn[v], dim3(grid), dim3(FS2_THREADS), params, smem, s));
+    SB_CUDA(launch_pdl_c(fn[v], dim3(grid), dim3(FS2_THREADS), params, smem, s));
     SB_LAUNCHED();
     return SB_OK;
 }

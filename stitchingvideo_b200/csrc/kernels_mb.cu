@@ -23,6 +23,7 @@
 #include "sb_device.cuh"
 #include "sb_mb.h"
 #include "sb_warp.cuh"
+#include "sb_tma.cuh"
 
 namespace sb {
 using namespace sbd;
@@ -475,6 +476,8 @@ template <typename WT, bool NOT_TOP, bool FINAL, bool OUT8>
 __global__ void __launch_bounds__(256) k_mb_band(const __grid_constant__ MbBandArgs a)
 {
     // block = 32 x 8 threads = 64 x 16 band pixels = 2 x 2 mask tiles of 32 x 8
+    sbt::pdl_wait();
+    sbt::pdl_release();
     mb_band_thread<WT, NOT_TOP, FINAL, OUT8>(a, (blockIdx.x * 32 + threadIdx.x) * 2, (blockIdx.y * 8 + threadIdx.y) * 2);
 }
 
@@ -483,7 +486,7 @@ int launch_mb_band(const MbBandArgs &a, bool float_weights, bool not_top, bool f
     const int lw = final_band ? a.out_w : a.g.lw, lh = final_band ? a.out_h : a.g.lh;
     dim3 block(32, 8), grid(div_up(lw, 64), div_up(lh, 16));
     SB_ASSERT(div_up(a.g.lw, 32) == a.tiles_x);
-#define SB_MB(WT, NT, FIN, O8) k_mb_band<WT, NT, FIN, O8><<<grid, block, 0, s>>>(a)
+#define SB_MB(WT, NT, FIN, O8) SB_CUDA(launch_pdl(k_mb_band<WT, NT, FIN, O8>, grid, block, 0, s, a))
 #define SB_MB_W(WT)                                                                          \
     do {                                                                                     \
         if (final_band) { if (not_top) { if (out8) SB_MB(WT, true, true, true); else SB_MB(WT, true, true, false); } \

@@ -30,6 +30,8 @@ __global__ void __launch_bounds__(256) k_mb_pyr_down_tma(const __grid_constant__
     __shared__ __align__(128) uint32_t tile[MB_PT_IH][MB_PT_IW];
     __shared__ uint64_t bar;
     const int tid = threadIdx.x;
+    pdl_wait();
+    pdl_release();
     int k = 0;
     while (k + 1 < a.list.n_seg && (int)blockIdx.x >= a.list.seg[k + 1].first) ++k;
     const MbPyrSeg sg = a.list.seg[k];
@@ -125,7 +127,7 @@ int launch_mb_pyr_down_tma(MbPyrTmaArgs &a, cudaStream_t s)
         }
     }
     if (total == 0) return SB_OK;
-    k_mb_pyr_down_tma<<<total, 256, 0, s>>>(a);
+    SB_CUDA(launch_pdl(k_mb_pyr_down_tma, dim3(total), dim3(256), 0, s, a));
     SB_LAUNCHED();
     return SB_OK;
 }

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -53,6 +54,32 @@ inline bool type_supported(int type)
            type == SB_16UC1 || type == SB_16SC2;      // (the last two: fixed-point remap maps only)
 }
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// Programmatic dependent launch (sm_90+): the grid may be set up and its CTAs made resident while its predecessor in the
+// stream is still draining; the kernel calls pdl_wait() (sb_tma.cuh) before it touches memory, so the stream's order of
+// memory effects is unchanged - only the launch latency between two dependent kernels (2.5-3 us on B200) is overlapped.
+// SB_PDL=0 in the environment launches plainly (A/B measurements).
+inline bool pdl_enabled()
+{
+    static const bool on = !(getenv("SB_PDL") && atoi(getenv("SB_PDL")) == 0);
+    return on;
+}
+inline cudaError_t launch_pdl_c(const void *fn, dim3 grid, dim3 block, void **params, size_t smem, cudaStream_t s)
+{
+    if (!pdl_enabled()) return cudaLaunchKernel(fn, grid, block, params, smem, s);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelExC(&cfg, fn, params);
+}
+template <typename A> inline cudaError_t launch_pdl(void (*k)(A), dim3 grid, dim3 block, size_t smem, cudaStream_t s, const A &a)
+{
+    void *params[] = {const_cast<A *>(&a)};
+    return launch_pdl_c(reinterpret_cast<const void *>(k), grid, block, params, smem, s);
+}
 
 // device image view
 struct DImage {

@@ -79,4 +79,10 @@ __device__ __forceinline__ void mbar_wait_hw(uint64_t *bar, unsigned parity)
 }
 
 
+// Programmatic dependent launch, device side (host side: launch_pdl in sb_internal.h).  pdl_wait(): everything the
+// predecessor grid wrote is visible after it (a no-op for a plain launch); it must come before the first access to memory
+// the predecessor touches.  pdl_release(): the successor grid may start being scheduled from here on (it will itself wait).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace sbt
