@@ -66,7 +66,9 @@ inline bool pdl_enabled()
 }
 inline cudaError_t launch_pdl_c(const void *fn, dim3 grid, dim3 block, void **params, size_t smem, cudaStream_t s)
 {
-    if (!pdl_enabled()) return cudaLaunchKernel(fn, grid, block, params, smem, s);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (!pdl_enabled() || cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
+        return cudaLaunchKernel(fn, grid, block, params, smem, s);       // (a stream being captured into a graph keeps plain kernel nodes)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute at[1];

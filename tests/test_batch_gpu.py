@@ -154,3 +154,39 @@ def test_device_panorama_is_written_in_place(gpu, rig, blender, variants, out16)
             assert np.array_equal(t[:, :w].cpu().numpy(), ref), "variant %d pitch %d" % (v, wp)
             assert np.array_equal(m[:, :w].cpu().numpy(), ref_mask), "variant %d pitch %d (mask)" % (v, wp)
             assert (t[:, w:] == 77).all() and (m[:, w:] == 77).all(), "variant %d pitch %d: wrote outside the panorama" % (v, wp)
+
+
+def test_graph_mode_lap_still_matches(gpu):
+    """SB_BATCH_GRAPH=1 (opt-in: a lap recorded as a CUDA graph; kernels launched while a stream is being captured fall back
+    from programmatic dependent launch to plain kernel nodes) gives the same panoramas - run in a fresh process, the switch is
+    read once per process."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np
+import stitchingvideo_b200 as sv
+from stitchingvideo_b200 import rigs
+from oracle import pipeline as P
+rig = "mini_cyl"
+Ks, Rs, spec = rigs.cameras(rig)
+size, n = (spec["W"], spec["H"]), spec["n_used"]
+comp = sv.Compositor(size, Ks, Rs, warper=spec["warper"], scale=spec["scale"], blender="feather")
+comp.set_depth(2)
+cal = P.Calibration(size, Ks, Rs, spec["warper"], spec["scale"])
+sets = [[rigs.frame(rig, f, i) for i in range(n)] for f in range(3)]
+refs = [P.compose(cal, s, blender="feather") for s in sets]
+w, h = comp.pano_size
+panos = [np.zeros((h, w, 3), np.uint8) for _ in range(5)]
+b = comp.batch([sets[f % 3] for f in range(5)], panos)
+assert b.mode == 2, b.mode
+for rep in range(2):
+    b.launch(); b.wait()
+    for f in range(5):
+        assert np.array_equal(panos[f], refs[f % 3][0]), (rep, f)
+print("graph ok")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SB_BATCH_GRAPH="1", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert r.returncode == 0 and "graph ok" in r.stdout, r.stdout[-500:] + r.stderr[-1500:]
