@@ -71,25 +71,11 @@ int prepare_rect(sb_blender *b, sb_rect roi)
 
 int feed_multiband(sb_blender *b, const DImage &img, const DImage &mask, sb_point tl)
 {
-    const int nb = b->num_bands, m = 1 << nb;
+    const int nb = b->num_bands;
     const sb_rect &r = b->dst_roi;
-    const int rbr_x = r.x + r.width, rbr_y = r.y + r.height;
-    // blenders.cpp:241-269
-    const int gap = 3 * m;
-    sb_point tl_new = {std::max(r.x, tl.x - gap), std::max(r.y, tl.y - gap)};
-    sb_point br_new = {std::min(rbr_x, tl.x + img.cols + gap), std::min(rbr_y, tl.y + img.rows + gap)};
-    tl_new.x = r.x + (((tl_new.x - r.x) >> nb) << nb);
-    tl_new.y = r.y + (((tl_new.y - r.y) >> nb) << nb);
-    int width = br_new.x - tl_new.x, height = br_new.y - tl_new.y;
-    width += (m - width % m) % m;
-    height += (m - height % m) % m;
-    br_new.x = tl_new.x + width;
-    br_new.y = tl_new.y + height;
-    const int dy = std::max(br_new.y - rbr_y, 0), dx = std::max(br_new.x - rbr_x, 0);
-    tl_new.x -= dx; br_new.x -= dx;
-    tl_new.y -= dy; br_new.y -= dy;
-    const int top = tl.y - tl_new.y, left = tl.x - tl_new.x;
-    const int bottom = br_new.y - tl.y - img.rows, right = br_new.x - tl.x - img.cols;
+    const FeedRect fr = multiband_feed_rect(r, tl, img.cols, img.rows, nb);       // blenders.cpp:241-269
+    const sb_point tl_new = fr.tl_new;
+    const int width = fr.width, height = fr.height, top = fr.top, left = fr.left, bottom = fr.bottom, right = fr.right;
     if (top < 0 || left < 0 || bottom < 0 || right < 0 || tl_new.x < r.x || tl_new.y < r.y)
         return fail(SB_ERR_ASSERT, "feed: image at (%d,%d) %dx%d does not fit the prepared ROI", tl.x, tl.y, img.cols, img.rows);
 

@@ -520,19 +520,10 @@ int setup(sb_compositor *c)
         DevBuf span_scratch;
         for (int i = 0; i < n; ++i) {
             Camera &cam = c->cams[i];
-            // MultiBandBlender::feed geometry (blenders.cpp:241-269)
-            sb_point tl_new = {std::max(roi.x, cam.tl.x - gap), std::max(roi.y, cam.tl.y - gap)};
-            sb_point br_new = {std::min(rbr_x, cam.tl.x + cam.ww + gap), std::min(rbr_y, cam.tl.y + cam.wh + gap)};
-            tl_new.x = roi.x + (((tl_new.x - roi.x) >> nb) << nb);
-            tl_new.y = roi.y + (((tl_new.y - roi.y) >> nb) << nb);
-            int width = br_new.x - tl_new.x, height = br_new.y - tl_new.y;
-            width += (m - width % m) % m;
-            height += (m - height % m) % m;
-            br_new.x = tl_new.x + width; br_new.y = tl_new.y + height;
-            const int dy = std::max(br_new.y - rbr_y, 0), dx = std::max(br_new.x - rbr_x, 0);
-            tl_new.x -= dx; br_new.x -= dx; tl_new.y -= dy; br_new.y -= dy;
-            cam.top = cam.tl.y - tl_new.y; cam.left = cam.tl.x - tl_new.x;
-            cam.rx = tl_new.x - roi.x; cam.ry = tl_new.y - roi.y; cam.rw = width; cam.rh = height;
+            const FeedRect fr = multiband_feed_rect(roi, cam.tl, cam.ww, cam.wh, nb);      // MultiBandBlender::feed geometry (blenders.cpp:241-269)
+            const int width = fr.width, height = fr.height;
+            cam.top = fr.top; cam.left = fr.left;
+            cam.rx = fr.tl_new.x - roi.x; cam.ry = fr.tl_new.y - roi.y; cam.rw = width; cam.rh = height;
             SB_ASSERT(cam.top >= 0 && cam.left >= 0 && cam.rx >= 0 && cam.ry >= 0);
             // weight pyramid (:282-298) and its contribution to dst_band_weights_ (:324, :349)
             cam.w_pyr.resize(nb + 1);

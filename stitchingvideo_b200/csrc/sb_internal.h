@@ -55,6 +55,34 @@ inline bool type_supported(int type)
 }
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
+// Where MultiBandBlender::feed places an image of `w` x `h` whose top-left corner is `tl` inside the prepared ROI `roi`
+// (blenders.cpp:241-269): the feed rect grows by a gap of 3 * 2^bands, is snapped to multiples of 2^bands relative to the ROI,
+// padded to a multiple of 2^bands and shifted back inside.  tl_new = top-left of the padded rect (panorama coordinates),
+// width / height its size, top / left / bottom / right the borders copyMakeBorder adds around the image.
+struct FeedRect {
+    sb_point tl_new;
+    int width, height, top, left, bottom, right;
+};
+inline FeedRect multiband_feed_rect(const sb_rect &roi, sb_point tl, int w, int h, int num_bands)
+{
+    const int m = 1 << num_bands, gap = 3 * m;
+    const int rbr_x = roi.x + roi.width, rbr_y = roi.y + roi.height;
+    FeedRect f;
+    f.tl_new = {(roi.x > tl.x - gap ? roi.x : tl.x - gap), (roi.y > tl.y - gap ? roi.y : tl.y - gap)};
+    sb_point br = {(rbr_x < tl.x + w + gap ? rbr_x : tl.x + w + gap), (rbr_y < tl.y + h + gap ? rbr_y : tl.y + h + gap)};
+    f.tl_new.x = roi.x + (((f.tl_new.x - roi.x) >> num_bands) << num_bands);
+    f.tl_new.y = roi.y + (((f.tl_new.y - roi.y) >> num_bands) << num_bands);
+    f.width = br.x - f.tl_new.x; f.height = br.y - f.tl_new.y;
+    f.width += (m - f.width % m) % m;
+    f.height += (m - f.height % m) % m;
+    br.x = f.tl_new.x + f.width; br.y = f.tl_new.y + f.height;
+    const int dy = br.y - rbr_y > 0 ? br.y - rbr_y : 0, dx = br.x - rbr_x > 0 ? br.x - rbr_x : 0;
+    f.tl_new.x -= dx; br.x -= dx; f.tl_new.y -= dy; br.y -= dy;
+    f.top = tl.y - f.tl_new.y; f.left = tl.x - f.tl_new.x;
+    f.bottom = br.y - tl.y - h; f.right = br.x - tl.x - w;
+    return f;
+}
+
 // Programmatic dependent launch (sm_90+): the grid may be set up and its CTAs made resident while its predecessor in the
 // stream is still draining; the kernel calls pdl_wait() (sb_tma.cuh) before it touches memory, so the stream's order of
 // memory effects is unchanged - only the launch latency between two dependent kernels (2.5-3 us on B200) is overlapped.
