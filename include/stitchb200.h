@@ -357,7 +357,12 @@ int  sb_compositor_profile_frame(sb_compositor *c, const sb_image *srcs, char *b
  * `world` column strips (boundaries are multiples of 2^num_bands of the padded panorama), one rank per
  * strip.  Multi-band path.  The reference has no counterpart (it bounds the work per image with the
  * padded sub-rectangle of blenders.cpp:242-264); results are bit-identical to the unsplit panorama.
- * One frame on every rank, in lock step (stitchingvideo_b200/strips.py drives this over NCCL send/recv):
+ * Three ways for a strip to get the columns next to its boundaries, all bit-identical (measured on 8 B200, 16384-wide
+ * panorama: one GPU 0.57 ms): RECOMPUTE them locally (set_strip_halo(1); no communication, 0.17 ms - the default of
+ * strips.py and bench.py), PEER writes into the neighbour's memory with flags (strip_peer_*; no host in the loop,
+ * 0.41 ms), or the step-by-step EXCHANGE below over any transport (NCCL send/recv in strips.py: 1.3-2.3 ms, slower than
+ * one GPU - 11 tiny host-driven exchanges per frame cost latency, not bandwidth).
+ * One frame on every rank, in lock step, exchange form:
  *     strip_warp(srcs)
  *     for l = 0 .. num_bands:   exchange(SB_HALO_GAUSS, l);  if l < num_bands: strip_down(l)
  *     for l = num_bands .. 0:   strip_band(l);               if l >= 1: exchange(SB_HALO_RESTORED, l)
